@@ -1,0 +1,45 @@
+# Build of the three shared libraries.  `make` = all; `make gpu` needs nvcc only (no GPU).
+#   vecchio_b200/lib/libvecchio_gpu.so   CUDA kernels + C ABI (include/vecchio_gpu.h)   -- product
+#   vecchio_b200/lib/libvecchio_host.so  host front end (reference scene API + lower())  -- product
+#   oracle/liboracle.so                  CPU restatement of the reference                -- tests only
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       := /usr/bin/g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+CXXFLAGS  := -std=c++17 -O3 -fPIC -ffp-contract=off -Wall -Wextra
+LIBDIR    := vecchio_b200/lib
+CSRC      := vecchio_b200/csrc
+HOSTSRC   := vecchio_b200/host
+
+all: host oracle gpu
+
+host: $(LIBDIR)/libvecchio_host.so
+oracle: oracle/liboracle.so
+gpu: $(LIBDIR)/libvecchio_gpu.so
+
+$(LIBDIR)/libvecchio_host.so: $(HOSTSRC)/vecchio.cpp $(HOSTSRC)/scene.cpp $(HOSTSRC)/capi.cpp $(HOSTSRC)/vecchio.hpp include/vecchio_gpu.h include/vecchio_host.h
+	@mkdir -p $(LIBDIR)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC)/vecchio.cpp $(HOSTSRC)/scene.cpp $(HOSTSRC)/capi.cpp -lz
+
+oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/vecchio_gpu.h
+	$(CXX) $(CXXFLAGS) -fopenmp -shared -o $@ oracle/oracle.cpp
+
+KDEPS := $(CSRC)/vk_device.cuh $(CSRC)/vk_internal.h include/vecchio_gpu.h
+
+# the device code is compiled twice: contracted FMA ("fast") and -fmad=false ("strict", the
+# reference's op sequence, used for hit parity)
+$(CSRC)/vk_kernels_fast.o: $(CSRC)/vk_kernels.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_fast.log || (cat $(CSRC)/ptxas_fast.log; false)
+$(CSRC)/vk_kernels_strict.o: $(CSRC)/vk_kernels.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_strict.log || (cat $(CSRC)/ptxas_strict.log; false)
+$(CSRC)/vk_api.o: $(CSRC)/vk_api.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $^
+
+clean:
+	rm -f $(LIBDIR)/*.so oracle/*.so $(CSRC)/*.o $(CSRC)/*.log
+
+.PHONY: all host oracle gpu clean

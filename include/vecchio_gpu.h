@@ -1,0 +1,301 @@
+/*
+ * vecchio_gpu.h -- C ABI of the B200 (sm_100a) path-tracing sample loop.
+ *
+ * This is the drop-in boundary for the ONE hot path of browserdotsys/vecchio: the
+ * per-pixel sample loop of the reference, `src/main.rs:181-198`, and everything it
+ * calls (`ray_color` `src/main.rs:123-153`, every `Hittable::hit`, `Material::
+ * scatter_with_pdf`, `Texture::value`, the PDF objects of `src/util.rs`).
+ *
+ * The reference has no FFI of its own (pure safe Rust).  The entry points below are
+ * what a `gpu` module of the Rust host would bind with `extern "C"` (see
+ * INTEGRATION.md and rust/gpu.rs); each one names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every host buffer; the library
+ *     keeps no pointer after a call returns.
+ *   - every function returns VK_OK (0) or a negative vk_status; the message is
+ *     available from vk_last_error().  Nothing aborts or throws across the ABI.
+ *   - there is NO CPU fallback: without a CUDA device vk_create fails with
+ *     VK_ERR_NO_DEVICE, and a scene element the GPU path does not implement fails
+ *     vk_scene_upload with VK_ERR_UNSUPPORTED.
+ *   - all arithmetic is IEEE fp32, like the reference (`f32`, `src/vec3.rs:3-8`).
+ */
+#ifndef VECCHIO_GPU_H
+#define VECCHIO_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VK_API_VERSION 1u
+
+typedef enum vk_status {
+    VK_OK = 0,
+    VK_ERR_INVALID = -1,     /* bad argument / malformed scene description          */
+    VK_ERR_NO_DEVICE = -2,   /* no CUDA device (there is no CPU fallback)           */
+    VK_ERR_CUDA = -3,        /* a CUDA runtime call failed                          */
+    VK_ERR_UNSUPPORTED = -4, /* scene element not implemented on the GPU path       */
+    VK_ERR_NO_SCENE = -5,    /* render/intersect before vk_scene_upload             */
+    VK_ERR_OOM = -6
+} vk_status;
+
+/* ------------------------------------------------------------------------------
+ * Flattened scene.  The reference's object graph of `Arc<dyn Hittable>` trait
+ * objects (`src/hittable.rs:33-44`) is lowered to one typed record array per
+ * primitive kind plus 32-bit tagged references between them.
+ * ---------------------------------------------------------------------------- */
+
+typedef uint32_t vk_ref; /* (type << 28) | index ; 0 == none */
+
+enum {
+    VK_T_NONE = 0,
+    VK_T_NODE = 1,    /* BVHNode            src/accel.rs:52-83                 */
+    VK_T_SPHERE = 2,  /* Sphere             src/hittable.rs:46-121             */
+    VK_T_MSPHERE = 3, /* MovingSphere       src/hittable.rs:136-197            */
+    VK_T_RECT = 4,    /* Rect (+FlipFace)   src/hittable.rs:199-312            */
+    VK_T_BOX = 5,     /* Boxy               src/hittable.rs:314-378            */
+    VK_T_XFORM = 6,   /* Translate/Rotate{X,Y,Z}/FlipFace  :294-312, :500-807  */
+    VK_T_MEDIUM = 7   /* ConstantMedium     src/hittable.rs:436-498            */
+};
+#define VK_REF_NONE 0u
+#define VK_REF(type, index) ((((uint32_t)(type)) << 28) | ((uint32_t)(index) & 0x0FFFFFFFu))
+#define VK_REF_TYPE(r) (((uint32_t)(r)) >> 28)
+#define VK_REF_INDEX(r) (((uint32_t)(r)) & 0x0FFFFFFFu)
+
+/* BVHNode {left, right, bb} (src/accel.rs:52-56).  `left == right` marks the
+ * single-object leaf of BVHNode::new (src/accel.rs:102-107): the object is tested
+ * twice, which matters for ConstantMedium (two independent free-flight draws). */
+typedef struct vk_node {
+    float bb_min[3];
+    vk_ref left;
+    float bb_max[3];
+    vk_ref right;
+} vk_node; /* 32 B, two 128-bit loads */
+
+typedef struct vk_sphere {
+    float center[3];
+    float radius; /* may be negative (hollow glass, src/scene.rs:123-127) */
+} vk_sphere;      /* 16 B; material in vk_scene_desc.sphere_mat[] */
+
+typedef struct vk_msphere {
+    float center0[3];
+    float radius;
+    float center1[3];
+    float time0;
+    float time1;
+    uint32_t mat;
+    uint32_t _pad[2];
+} vk_msphere; /* 48 B */
+
+#define VK_RECT_FLIP 0x100u
+typedef struct vk_rect {
+    float c0, c1, d0, d1; /* bounds on axis0 / axis1 (src/hittable.rs:200-210) */
+    float k;              /* plane position on axis2                            */
+    uint32_t axes;        /* axis0 | axis1<<2 | axis2<<4 | VK_RECT_FLIP         */
+    uint32_t mat;
+    uint32_t _pad;
+} vk_rect; /* 32 B */
+
+typedef struct vk_box {
+    float box_min[3];
+    uint32_t mat;
+    float box_max[3];
+    uint32_t _pad;
+} vk_box; /* 32 B; the six sides of Boxy::new (src/hittable.rs:325-353) are implied */
+
+enum {
+    VK_X_TRANSLATE = 0, /* a,b,c = offset          src/hittable.rs:500-532 */
+    VK_X_ROTATE_X = 1,  /* a = sin, b = cos        src/hittable.rs:631-718 */
+    VK_X_ROTATE_Y = 2,  /*                         src/hittable.rs:534-629 */
+    VK_X_ROTATE_Z = 3,  /*                         src/hittable.rs:720-807 */
+    VK_X_FLIP = 4       /* FlipFace of a non-Rect  src/hittable.rs:294-312 */
+};
+#define VK_MAX_XFORM_DEPTH 8
+typedef struct vk_xform {
+    uint32_t kind;
+    vk_ref child;
+    uint32_t _pad0[2];
+    float a, b, c;
+    uint32_t _pad1;
+} vk_xform; /* 32 B; one record per wrapper level, chains are walked child by child */
+
+typedef struct vk_medium {
+    vk_ref boundary;
+    float neg_inv_density; /* -1/density, src/hittable.rs:447 */
+    uint32_t mat;          /* the Isotropic phase material      */
+    uint32_t _pad;
+} vk_medium; /* 16 B */
+
+enum {
+    VK_M_LAMBERTIAN = 0,    /* src/material.rs:45-109  */
+    VK_M_METAL = 1,         /* src/material.rs:111-142 */
+    VK_M_DIELECTRIC = 2,    /* src/material.rs:144-207 */
+    VK_M_DIFFUSE_LIGHT = 3, /* src/material.rs:209-226 */
+    VK_M_ISOTROPIC = 4,     /* src/material.rs:436-465 */
+    VK_M_SPECDIFFUSE = 5    /* src/material.rs:467-488 */
+};
+typedef struct vk_material {
+    uint32_t type;
+    uint32_t tex;   /* albedo / emit texture index; SPECDIFFUSE: specular material index */
+    float param;    /* METAL fuzz | DIELECTRIC ref_idx | SPECDIFFUSE pct                 */
+    uint32_t aux;   /* SPECDIFFUSE: diffuse material index                               */
+} vk_material;      /* 16 B */
+
+enum {
+    VK_TEX_SOLID = 0,   /* src/material.rs:233-242 */
+    VK_TEX_CHECKER = 1, /* src/material.rs:244-259 */
+    VK_TEX_IMAGE = 2,   /* src/material.rs:261-304 */
+    VK_TEX_NOISE = 3    /* src/material.rs:416-434 */
+};
+typedef struct vk_texture {
+    uint32_t type;
+    union {
+        float rgb[3];                                                  /* SOLID   */
+        struct { uint32_t odd, even, _p; } checker;                    /* CHECKER */
+        struct { uint32_t texel_offset, width, height; } image;        /* IMAGE: RGB8, BPP=3 */
+        struct { uint32_t perlin; float scale; uint32_t _p; } noise;   /* NOISE   */
+    };
+} vk_texture; /* 16 B */
+
+/* Perlin tables (src/material.rs:306-311), generated on the host (:357-377). */
+typedef struct vk_perlin {
+    float ranvec[256][3];
+    uint8_t perm_x[256];
+    uint8_t perm_y[256];
+    uint8_t perm_z[256];
+} vk_perlin;
+
+typedef struct vk_scene_desc {
+    uint32_t api_version; /* VK_API_VERSION */
+    vk_ref root;          /* the world: `BVHNode::new(&mut config.world)` src/main.rs:168 */
+
+    const vk_node* nodes;        uint32_t n_nodes;
+    const vk_sphere* spheres;    const uint32_t* sphere_mat; uint32_t n_spheres;
+    const vk_msphere* mspheres;  uint32_t n_mspheres;
+    const vk_rect* rects;        uint32_t n_rects;
+    const vk_box* boxes;         uint32_t n_boxes;
+    const vk_xform* xforms;      uint32_t n_xforms;
+    const vk_medium* media;      uint32_t n_media;
+
+    const vk_ref* lights;        uint32_t n_lights; /* SceneConfig.lights src/scene.rs:19 */
+
+    const vk_material* materials; uint32_t n_materials;
+    const vk_texture* textures;   uint32_t n_textures;
+    const uint8_t* texels;        uint64_t n_texel_bytes;
+    const vk_perlin* perlins;     uint32_t n_perlins;
+} vk_scene_desc;
+
+/* Camera (src/main.rs:56-68): the ten fields, in declaration order. */
+typedef struct vk_camera {
+    float origin[3];
+    float lower_left_corner[3];
+    float horizontal[3];
+    float vertical[3];
+    float u[3], v[3], w[3];
+    float lens_radius;
+    float time0, time1;
+} vk_camera; /* 24 floats */
+
+enum { VK_VARIANT_AUTO = 0, VK_VARIANT_MEGAKERNEL = 1, VK_VARIANT_WAVEFRONT = 2 };
+enum {
+    VK_FLAG_STRICT_MATH = 1u /* no FMA contraction, IEEE div/sqrt, division slab test:
+                                the op sequence of the reference, for hit parity     */
+};
+
+/* The constants of src/main.rs:28-29,171-172 and the choices the reference leaves
+ * to its (unseeded) RNG, as parameters. */
+typedef struct vk_render_params {
+    uint32_t width, height;
+    uint32_t spp;       /* SAMPLES_PER_PIXEL: the divisor of the mean (main.rs:196)     */
+    uint32_t spp_begin; /* this call renders global samples [spp_begin, spp_begin+spp_count) */
+    uint32_t spp_count; /* 0 == all of them (spp - spp_begin)                            */
+    uint32_t max_depth; /* MAX_DEPTH, `depth > MAX_DEPTH` semantics (main.rs:126)        */
+    uint64_t seed;      /* Philox4x32-10 key                                             */
+    float background[3];/* src/main.rs:124 (always 0 at HEAD)                            */
+    uint32_t variant;   /* VK_VARIANT_*                                                  */
+    uint32_t flags;     /* VK_FLAG_*                                                     */
+} vk_render_params;
+
+typedef struct vk_stats {
+    uint64_t paths;           /* samples started = W*H*spp_count                         */
+    uint64_t rays;            /* world.hit() segment queries from ray_color (main.rs:130)*/
+    uint64_t dropped_samples; /* non-finite samples filtered (main.rs:191-194)           */
+    float ms_kernels;         /* CUDA-event time of the render kernels                   */
+    float ms_total;           /* CUDA-event time incl. D2H of the image (vk_render)      */
+    uint32_t variant;         /* variant that ran                                        */
+    uint32_t launches;        /* kernels launched by this call                           */
+} vk_stats;
+
+typedef struct vk_ray {
+    float origin[3];
+    float direction[3];
+    float time;
+    float tmin, tmax;
+} vk_ray; /* 36 B */
+
+/* HitRec (src/hittable.rs:11-20) plus the primitive id the reference lacks. */
+typedef struct vk_hit {
+    vk_ref prim;    /* leaf record that produced the hit; VK_REF_NONE == miss */
+    uint32_t face;  /* BOX: side index 0..5 in Boxy::new order; else 0        */
+    uint32_t mat;
+    uint32_t front;
+    float t;
+    float p[3];
+    float normal[3];
+    float u, v;
+    uint32_t _pad;
+} vk_hit; /* 56 B */
+
+#define VK_MEDIUM_XI_SLOTS 8 /* slot = (medium index * 2 + second-visit) % 8 */
+
+typedef struct vk_ctx vk_ctx;
+
+/* Create a context on CUDA device `device`.  Replaces nothing in the reference
+ * (it has no device); owns the stream, device scene and accumulation buffers. */
+int vk_create(int device, vk_ctx** out);
+void vk_destroy(vk_ctx* ctx);
+/* Message of the last failure on `ctx` (or of the last failed vk_create if NULL). */
+const char* vk_last_error(const vk_ctx* ctx);
+
+/* Copy a flattened scene to the device (host arrays are borrowed for the call).
+ * Replaces the `Arc<BVHNode>` world / `Arc<Vec<..>>` lights handed to the loop at
+ * src/main.rs:168-169. */
+int vk_scene_upload(vk_ctx* ctx, const vk_scene_desc* scene);
+
+/* The sample loop, src/main.rs:181-198.  out_rgb: W*H*3 floats, pixel i = y*W+x,
+ * row 0 = bottom (main.rs:182-183), linear mean over `spp` (main.rs:196).
+ * out_sumsq (nullable): per channel sum of squares of the kept samples.  Host buffers. */
+int vk_render(vk_ctx* ctx, const vk_camera* cam, const vk_render_params* params,
+              float* out_rgb, float* out_sumsq, vk_stats* stats);
+
+/* Same loop, device-resident result: writes per-pixel SUMS (not means) of samples
+ * [spp_begin, spp_begin+spp_count) to d_sum (and d_sumsq, nullable), both device
+ * pointers of W*H*3 floats, enqueued on the context stream and synchronised before
+ * return.  This is the per-GPU spp slice; slices are combined by one NCCL reduce. */
+int vk_render_device(vk_ctx* ctx, const vk_camera* cam, const vk_render_params* params,
+                     float* d_sum, float* d_sumsq, vk_stats* stats);
+
+/* d_rgb[i] = d_sum[i] / spp on the device (main.rs:196), after the reduce. */
+int vk_finalize_device(vk_ctx* ctx, const float* d_sum, float* d_rgb, size_t n_floats,
+                       uint32_t spp);
+
+/* Parity hook: closest hit of `world.hit(&r, tmin, tmax)` (src/accel.rs:58-83) for
+ * a batch of rays.  medium_xi (nullable): n * VK_MEDIUM_XI_SLOTS uniform variates
+ * for ConstantMedium::hit's free-flight draw (src/hittable.rs:473). */
+int vk_intersect(vk_ctx* ctx, const vk_ray* rays, size_t n, const float* medium_xi,
+                 uint32_t flags, vk_hit* out);
+
+/* Microbenchmarks for the roofline denominators the driver does not measure:
+ * dependent-free FFMA throughput (TFLOP/s) and L2-resident read bandwidth (GB/s). */
+int vk_measure_peaks(vk_ctx* ctx, float* fp32_tflops, float* l2_gbs);
+
+/* Device properties for reporting. */
+int vk_device_info(vk_ctx* ctx, int* sm_count, int* clock_khz, char* name, size_t name_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VECCHIO_GPU_H */

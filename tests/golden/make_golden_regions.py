@@ -1,0 +1,54 @@
+"""Regenerate tests/golden/cornell_sample_regions.json from the reference's published render.
+
+Reads /root/reference/sample/therestofyourlife.png (900x900, 8-bit, the book-3 Cornell box at
+src/main.rs defaults: width 900, 1000 spp, depth 100) -- the ONLY result-pinning artefact the
+reference ships (it has no tests).  Only region statistics are committed, not the image.
+Run in the build container (the GPU box has no /root/reference):  python tests/golden/make_golden_regions.py
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+from PIL import Image
+
+SRC = "/root/reference/sample/therestofyourlife.png"
+# name: (x0, x1, y0, y1) in image coordinates (y down), SURVEY.md Appendix C
+REGIONS = {
+    "whole": (0, 900, 0, 900),
+    "light_centre": (400, 500, 125, 145),
+    "green_wall": (60, 140, 400, 500),
+    "red_wall": (760, 840, 400, 500),
+    "back_wall": (400, 500, 250, 350),
+    "floor_front": (300, 400, 820, 860),
+    "ceiling": (200, 300, 60, 100),
+    "tall_box_front": (300, 440, 450, 700),
+    "glass_sphere_centre": (540, 600, 660, 720),
+    "caustic": (545, 605, 798, 810),
+    "border": (0, 15, 0, 15),
+}
+
+
+def main():
+    raw = open(SRC, "rb").read()
+    im = np.asarray(Image.open(SRC).convert("RGB")).astype(np.float64)
+    assert im.shape == (900, 900, 3)
+    nz = np.argwhere(im.sum(axis=2) > 0)
+    out = {
+        "source": "sample/therestofyourlife.png",
+        "sha256": hashlib.sha256(raw).hexdigest(),
+        "size": [900, 900],
+        "scene": "cornell_box (src/scene.rs:630-730), 1000 spp, depth 100, to_color (src/vec3.rs:54-61)",
+        "nonblack_bbox_rows": [int(nz[:, 0].min()), int(nz[:, 0].max())],
+        "nonblack_bbox_cols": [int(nz[:, 1].min()), int(nz[:, 1].max())],
+        "regions": {},
+    }
+    for name, (x0, x1, y0, y1) in REGIONS.items():
+        out["regions"][name] = {"box_xyxy": [x0, x1, y0, y1], "mean_rgb8": [round(float(v), 3) for v in im[y0:y1, x0:x1].mean(axis=(0, 1))]}
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cornell_sample_regions.json")
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

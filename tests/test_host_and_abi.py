@@ -1,0 +1,141 @@
+"""CPU tests of the host front end and of the C-ABI libraries (no compute on a GPU)."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, get_scene
+
+
+def test_gpu_library_exports_every_declared_symbol(vb):
+    hdr = open(os.path.join(ROOT, "include", "vecchio_gpu.h")).read()
+    declared = set(re.findall(r"\b(vk_[a-z_]+)\s*\(", hdr)) - {"vk_ctx"}
+    assert declared == set(vb.GPU_SYMBOLS)
+    lib = C.CDLL(os.path.join(ROOT, "vecchio_b200", "lib", "libvecchio_gpu.so"))
+    for name in declared | {"vk_selftest_philox"}:
+        assert hasattr(lib, name), name
+
+
+def test_host_library_exports_every_declared_symbol(vb):
+    hdr = open(os.path.join(ROOT, "include", "vecchio_host.h")).read()
+    declared = set(re.findall(r"\b(vkh_[a-z_]+)\s*\(", hdr))
+    assert declared == set(vb.HOST_SYMBOLS)
+    lib = vb.host_lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
+def test_no_cpu_fallback_without_a_device(vb):
+    with pytest.raises(vb.VecchioError) as e:
+        vb.Context(0)
+    assert e.value.code == vb.VK_ERR_NO_DEVICE
+
+
+def test_unknown_scene_is_an_error(vb):
+    with pytest.raises(vb.VecchioError):
+        vb.Scene("not_a_scene")
+
+
+# decoded RGB8 bytes of the texture assets (sha256 prefix, first texel, centre texel)
+PNG_KAT = {
+    "earthmap.png": ((512, 1024), "0651e147c9164cf9a7bb9c32", (255, 255, 255), (0, 2, 53)),
+    "bowser_face.png": ((32, 44), "1e8dc13edbc59d9c1d9670ce", (88, 118, 131), (88, 118, 131)),
+    "bowser_top.png": ((32, 44), "b5e8a89a67dcf11f8f3463cb", None, None),
+    "bowser_back.png": ((32, 44), "153364d7b24ef0235d9eebcb", None, None),
+    "bowser_side.png": ((32, 32), "171691359437ce950d0b80d0", (88, 118, 131), (0, 0, 0)),
+    "twitter.png": ((1740, 2904), "a6a0a39b8891b7c27d589c37", None, None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PNG_KAT))
+def test_png_decoder_matches_known_hashes(vb, name):
+    shape, sha, first, centre = PNG_KAT[name]
+    img = vb.decode_png(os.path.join(vb.ASSETS_DIR, name))
+    assert img.shape == shape + (3,)
+    assert hashlib.sha256(img.tobytes()).hexdigest().startswith(sha)
+    if first:
+        assert tuple(img[0, 0]) == first
+        assert tuple(img[shape[0] // 2, shape[1] // 2]) == centre
+
+
+def test_png_decoder_matches_pil(vb):
+    Image = pytest.importorskip("PIL.Image")
+    for name in ("earthmap.png", "bowser_face.png"):
+        ref = np.asarray(Image.open(os.path.join(vb.ASSETS_DIR, name)).convert("RGB"))
+        assert np.array_equal(ref, vb.decode_png(os.path.join(vb.ASSETS_DIR, name)))
+
+
+def test_camera_new_cornell(vb):
+    """Camera::new for the Cornell box (src/main.rs:71-109, src/scene.rs:708-728), SURVEY App. C."""
+    _, cam = get_scene(vb, "cornell_box")
+    assert np.allclose(list(cam.w), [0, 0, -1]) and np.allclose(list(cam.u), [-1, 0, 0]) and np.allclose(list(cam.v), [0, 1, 0])
+    assert np.allclose(list(cam.horizontal), [-7.2794046, 0, 0], rtol=1e-6)
+    assert np.allclose(list(cam.vertical), [0, 7.2794046, 0], rtol=1e-6)
+    assert np.allclose(list(cam.lower_left_corner), [281.63970, 274.36030, -790.0], rtol=1e-6)
+    assert cam.lens_radius == 0.0 and (cam.time0, cam.time1) == (0.0, 1.0)
+
+
+def test_rotating_camera_first_frame(vb):
+    """RotatingCamera first frame of random_spheres_demo (src/scene.rs:65-91, 254-281)."""
+    s, cam = get_scene(vb, "random_spheres_demo")
+    assert np.allclose(list(cam.origin), [18.126156, 2.5, 8.452366], rtol=1e-6)
+    assert s.height_for(400) == 225 and s.height_for(900) == 506 and s.height_for(3840) == 2160
+
+
+def bvh_nodes(n):  # f(1)=f(2)=1, f(n)=1+f(n//2)+f(n-n//2)  (src/accel.rs:102-135)
+    return 1 if n <= 2 else 1 + bvh_nodes(n // 2) + bvh_nodes(n - n // 2)
+
+
+def test_scene_census_matches_reference_builders(vb):
+    c = get_scene(vb, "cornell_box")[0].census()
+    # 8 top-level objects -> 7 nodes; 5 walls + light(flipped) + light(unflipped, light list) rects
+    assert (c["nodes"], c["spheres"], c["rects"], c["boxes"], c["xforms"], c["lights"], c["materials"]) == (7, 1, 7, 1, 2, 1, 5)
+    c = get_scene(vb, "cornell_smoke")[0].census()
+    assert (c["nodes"], c["boxes"], c["xforms"], c["media"], c["materials"]) == (7, 2, 4, 2, 6)
+    c = get_scene(vb, "final_scene")[0].census()
+    assert c["nodes"] == bvh_nodes(11) + bvh_nodes(400) + bvh_nodes(1000) == 13 + 511 + 1023
+    assert (c["spheres"], c["mspheres"], c["boxes"], c["media"], c["perlins"], c["texel_bytes"]) == (1006, 1, 400, 2, 1, 1572864)
+    c = get_scene(vb, "random_spheres_demo")[0].census()
+    n_top = c["spheres"] + 1  # + the flipped light rect
+    assert c["nodes"] == bvh_nodes(n_top) and 470 <= c["spheres"] <= 488 and c["texel_bytes"] == 1572864
+    c = get_scene(vb, "bowser_demo")[0].census()
+    assert (c["boxes"], c["xforms"]) == (22, 4) and c["nodes"] == bvh_nodes(3) + bvh_nodes(28)
+
+
+def test_bvh_structure_invariants(vb):
+    """Every node's box encloses its children; single-object leaves have left == right."""
+    s, _ = get_scene(vb, "final_scene")
+    d = s.desc
+    nodes = np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint32)), shape=(d.n_nodes, 8))
+    f = nodes.view(np.float32)
+    singles = 0
+    for i in range(d.n_nodes):
+        l, r = int(nodes[i, 3]), int(nodes[i, 7])
+        singles += l == r
+        for ch in (l, r):
+            if vb.ref_type(ch) == vb.VK_T_NODE:
+                j = vb.ref_index(ch)
+                assert j > i  # depth-first numbering: children after parents
+                assert np.all(f[j, 0:3] >= f[i, 0:3]) and np.all(f[j, 4:7] <= f[i, 4:7])
+        if vb.ref_type(l) == vb.VK_T_NODE:
+            assert vb.ref_index(l) == i + 1  # left subtree follows its parent immediately
+    assert singles == 3 + 112 + 24  # n=11 -> 3, n=400 -> 112, n=1000 -> 24
+
+
+def test_scene_build_is_deterministic_per_seed(vb):
+    a, b, c = vb.Scene("final_scene", seed=5), vb.Scene("final_scene", seed=5), vb.Scene("final_scene", seed=6)
+
+    def sph(s):
+        return np.ctypeslib.as_array(C.cast(s.desc.spheres, C.POINTER(C.c_float)), shape=(s.desc.n_spheres, 4)).copy()
+
+    assert np.array_equal(sph(a), sph(b)) and not np.array_equal(sph(a), sph(c))
+
+
+def test_stress_scene_small(vb):
+    s = vb.Scene("stress_spheres", param=40)
+    c = s.census()
+    assert c["spheres"] == 1600 and c["nodes"] == bvh_nodes(1602) and c["lights"] == 1

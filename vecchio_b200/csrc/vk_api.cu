@@ -1,0 +1,658 @@
+// vk_api.cu -- the C ABI of include/vecchio_gpu.h: context, scene validation + upload (with the
+// GPU-side re-layout), render orchestration, the parity hook and the roofline microbenchmarks.
+// No CPU fallback anywhere: every entry point either runs CUDA kernels or returns an error.
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "vk_internal.h"
+
+struct vk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    std::string err;
+    std::vector<void*> scene_allocs;
+    DScene scene{};
+    bool has_scene = false;
+    unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
+    float* partial = nullptr;               // chunk partial sums (sum | sumsq)
+    size_t partial_floats = 0;
+    float* frame = nullptr; // vk_render staging: sum | sumsq | rgb
+    size_t frame_floats = 0;
+    float* pinned = nullptr; // pinned host staging for the D2H of vk_render
+    size_t pinned_floats = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(vk_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_err = msg;
+    return code;
+}
+#define CU(ctx, call)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? VK_ERR_OOM : VK_ERR_CUDA,                               \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                                           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// small kernels that do not depend on the math mode
+// ------------------------------------------------------------------------------------------------
+__global__ void k_reduce_chunks(const float* __restrict__ partial, uint32_t n_chunks, size_t n, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = partial[i];
+    for (uint32_t c = 1; c < n_chunks; ++c) acc += partial[(size_t)c * n + i]; // fixed order: deterministic
+    out[i] = acc;
+}
+__global__ void k_finalize(const float* __restrict__ sum, float* __restrict__ rgb, size_t n, float spp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rgb[i] = sum[i] / spp; // c /= SAMPLES_PER_PIXEL as f32 (src/main.rs:196)
+}
+// FP32 peak: 8 independent FFMA chains per thread, no memory traffic
+__global__ void k_ffma_peak(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
+          a7 = a0 + 7.f;
+    const float m = 0.999f, b = 1e-3f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fmaf(a0, m, b); a1 = fmaf(a1, m, b); a2 = fmaf(a2, m, b); a3 = fmaf(a3, m, b);
+            a4 = fmaf(a4, m, b); a5 = fmaf(a5, m, b); a6 = fmaf(a6, m, b); a7 = fmaf(a7, m, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+// L2 bandwidth: every block streams the same L2-resident buffer with 128-bit loads
+__global__ void k_l2_read(const float4* __restrict__ buf, size_t n_vec, int reps, float* out) {
+    float acc = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < reps; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            const float4 v = __ldcg(&buf[i]);
+            acc += v.x + v.y + v.z + v.w;
+        }
+    if (acc == 123.456f) out[0] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene validation (host): everything the kernels assume is checked here, and anything the GPU
+// path does not implement is refused with VK_ERR_UNSUPPORTED instead of being rendered wrongly.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Validator {
+    const vk_scene_desc* d;
+    std::string err;
+    int code = VK_OK;
+    std::vector<int> node_depth;       // 0 = unvisited
+    std::vector<uint8_t> node_medium;  // subtree holds a ConstantMedium
+    std::vector<uint8_t> node_inchain; // visited below an instance
+
+    bool bad(int c, const std::string& m) {
+        if (code == VK_OK) {
+            code = c;
+            err = m;
+        }
+        return false;
+    }
+    bool leaf_ok(vk_ref r) {
+        const uint32_t i = VK_REF_INDEX(r);
+        switch (VK_REF_TYPE(r)) {
+        case VK_T_SPHERE: return i < d->n_spheres || bad(VK_ERR_INVALID, "sphere index out of range");
+        case VK_T_MSPHERE: return i < d->n_mspheres || bad(VK_ERR_INVALID, "moving-sphere index out of range");
+        case VK_T_RECT: return i < d->n_rects || bad(VK_ERR_INVALID, "rect index out of range");
+        case VK_T_BOX: return i < d->n_boxes || bad(VK_ERR_INVALID, "box index out of range");
+        default: return false;
+        }
+    }
+    static bool is_leaf_type(uint32_t t) { return t == VK_T_SPHERE || t == VK_T_MSPHERE || t == VK_T_RECT || t == VK_T_BOX; }
+
+    // returns the first non-wrapper ref of a chain starting at r (or NONE on error)
+    vk_ref chain_end(vk_ref r) {
+        int depth = 0;
+        while (VK_REF_TYPE(r) == VK_T_XFORM) {
+            if (VK_REF_INDEX(r) >= d->n_xforms) return bad(VK_ERR_INVALID, "xform index out of range"), VK_REF_NONE;
+            if (++depth > VK_MAX_XFORM_DEPTH) return bad(VK_ERR_UNSUPPORTED, "wrapper chain deeper than VK_MAX_XFORM_DEPTH"), VK_REF_NONE;
+            if (d->xforms[VK_REF_INDEX(r)].kind > VK_X_FLIP) return bad(VK_ERR_INVALID, "bad xform kind"), VK_REF_NONE;
+            r = d->xforms[VK_REF_INDEX(r)].child;
+        }
+        return r;
+    }
+    bool medium_ok(vk_ref r, bool in_chain) {
+        if (VK_REF_INDEX(r) >= d->n_media) return bad(VK_ERR_INVALID, "medium index out of range");
+        const vk_medium& m = d->media[VK_REF_INDEX(r)];
+        if (m.mat >= d->n_materials) return bad(VK_ERR_INVALID, "medium material out of range");
+        vk_ref b = m.boundary;
+        if (VK_REF_TYPE(b) == VK_T_XFORM) {
+            if (in_chain) return bad(VK_ERR_UNSUPPORTED, "ConstantMedium with a transformed boundary inside another instance");
+            b = chain_end(b);
+            if (code != VK_OK) return false;
+        }
+        if (!is_leaf_type(VK_REF_TYPE(b)))
+            return bad(VK_ERR_UNSUPPORTED, "ConstantMedium boundary must be a sphere, rect or box (optionally translated/rotated)");
+        return leaf_ok(b);
+    }
+    // depth of the traversal stack needed below r; also fills node_medium
+    int visit(vk_ref r, bool in_chain, bool& has_medium) {
+        has_medium = false;
+        const uint32_t t = VK_REF_TYPE(r), i = VK_REF_INDEX(r);
+        if (t == VK_T_NODE) {
+            if (i >= d->n_nodes) return bad(VK_ERR_INVALID, "node index out of range"), 0;
+            if (node_depth[i] == -1) return bad(VK_ERR_INVALID, "cycle in the BVH"), 0;
+            if (node_depth[i] > 0) {
+                if (in_chain && !node_inchain[i]) node_inchain[i] = 1; // (shape already validated; chain rule rechecked below)
+                has_medium = node_medium[i];
+                return node_depth[i];
+            }
+            node_depth[i] = -1;
+            bool ml = false, mr = false;
+            const int dl = visit(d->nodes[i].left, in_chain, ml);
+            const int dr = d->nodes[i].right == d->nodes[i].left ? dl : visit(d->nodes[i].right, in_chain, mr);
+            if (d->nodes[i].right == d->nodes[i].left) mr = ml;
+            if (code != VK_OK) return 0;
+            if (d->nodes[i].right == d->nodes[i].left && ml && VK_REF_TYPE(chain_end(d->nodes[i].left)) != VK_T_MEDIUM)
+                return bad(VK_ERR_UNSUPPORTED, "single-object BVH leaf holding a medium inside a nested BVH"), 0;
+            node_medium[i] = ml || mr;
+            node_inchain[i] = in_chain;
+            has_medium = node_medium[i];
+            node_depth[i] = 1 + (dl > dr ? dl : dr);
+            return node_depth[i];
+        }
+        if (t == VK_T_XFORM) {
+            if (in_chain) return bad(VK_ERR_UNSUPPORTED, "nested instances (a transform below another transform's BVH)"), 0;
+            const vk_ref end = chain_end(r);
+            if (code != VK_OK) return 0;
+            if (VK_REF_TYPE(end) == VK_T_NODE) return 2 + visit(end, true, has_medium);
+            if (VK_REF_TYPE(end) == VK_T_MEDIUM) {
+                has_medium = true;
+                medium_ok(end, true);
+                return 1;
+            }
+            if (!is_leaf_type(VK_REF_TYPE(end))) return bad(VK_ERR_INVALID, "bad reference below a transform"), 0;
+            leaf_ok(end);
+            return 1;
+        }
+        if (t == VK_T_MEDIUM) {
+            has_medium = true;
+            medium_ok(r, in_chain);
+            return 1;
+        }
+        if (is_leaf_type(t)) {
+            leaf_ok(r);
+            return 1;
+        }
+        return bad(VK_ERR_INVALID, "bad hittable reference"), 0;
+    }
+    bool tex_has_image(uint32_t ti, int depth) {
+        if (ti >= d->n_textures || depth > 16) return false;
+        const vk_texture& t = d->textures[ti];
+        if (t.type == VK_TEX_IMAGE) return true;
+        if (t.type == VK_TEX_CHECKER) return tex_has_image(t.checker.odd, depth + 1) || tex_has_image(t.checker.even, depth + 1);
+        return false;
+    }
+    bool run() {
+        if (!d || d->api_version != VK_API_VERSION) return bad(VK_ERR_INVALID, "scene description: wrong api_version");
+        for (uint32_t i = 0; i < d->n_textures; ++i) {
+            const vk_texture& t = d->textures[i];
+            if (t.type > VK_TEX_NOISE) return bad(VK_ERR_INVALID, "bad texture type");
+            if (t.type == VK_TEX_CHECKER && (t.checker.odd >= d->n_textures || t.checker.even >= d->n_textures))
+                return bad(VK_ERR_INVALID, "checker child out of range");
+            if (t.type == VK_TEX_IMAGE && (t.image.width == 0 || t.image.height == 0 ||
+                                           (uint64_t)t.image.texel_offset + (uint64_t)t.image.width * t.image.height * 3 > d->n_texel_bytes))
+                return bad(VK_ERR_INVALID, "image texture outside the texel pool");
+            if (t.type == VK_TEX_NOISE && t.noise.perlin >= d->n_perlins) return bad(VK_ERR_INVALID, "perlin index out of range");
+        }
+        for (uint32_t i = 0; i < d->n_materials; ++i) {
+            const vk_material& m = d->materials[i];
+            if (m.type > VK_M_SPECDIFFUSE) return bad(VK_ERR_INVALID, "bad material type");
+            if (m.type == VK_M_SPECDIFFUSE) {
+                if (m.tex >= d->n_materials || m.aux >= d->n_materials) return bad(VK_ERR_INVALID, "SpecDiffuse child out of range");
+                if (d->materials[m.tex].type == VK_M_SPECDIFFUSE || d->materials[m.aux].type == VK_M_SPECDIFFUSE)
+                    return bad(VK_ERR_UNSUPPORTED, "nested SpecDiffuse");
+            } else if (m.type != VK_M_DIELECTRIC && m.tex >= d->n_textures)
+                return bad(VK_ERR_INVALID, "material texture out of range");
+        }
+        for (uint32_t i = 0; i < d->n_spheres; ++i)
+            if (d->sphere_mat[i] >= d->n_materials) return bad(VK_ERR_INVALID, "sphere material out of range");
+        for (uint32_t i = 0; i < d->n_mspheres; ++i)
+            if (d->mspheres[i].mat >= d->n_materials) return bad(VK_ERR_INVALID, "moving-sphere material out of range");
+        for (uint32_t i = 0; i < d->n_rects; ++i) {
+            const uint32_t ax = d->rects[i].axes;
+            if (d->rects[i].mat >= d->n_materials) return bad(VK_ERR_INVALID, "rect material out of range");
+            if ((ax & 3) > 2 || ((ax >> 2) & 3) > 2 || ((ax >> 4) & 3) > 2) return bad(VK_ERR_INVALID, "rect axis out of range");
+        }
+        for (uint32_t i = 0; i < d->n_boxes; ++i)
+            if (d->boxes[i].mat >= d->n_materials) return bad(VK_ERR_INVALID, "box material out of range");
+        if (d->n_nodes > VKD_INDEX(0xFFFFFFFFu) || d->n_spheres > VKD_INDEX(0xFFFFFFFFu)) return bad(VK_ERR_UNSUPPORTED, "too many primitives");
+        node_depth.assign(d->n_nodes, 0);
+        node_medium.assign(d->n_nodes, 0);
+        node_inchain.assign(d->n_nodes, 0);
+        bool hm = false;
+        const int depth = visit(d->root, false, hm);
+        if (code != VK_OK) return false;
+        if (depth + 2 > VKD_STACK) return bad(VK_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+        if (d->n_lights == 0) return bad(VK_ERR_INVALID, "empty light list (the reference panics: choose().unwrap(), src/hittable.rs:431)");
+        for (uint32_t i = 0; i < d->n_lights; ++i) {
+            const vk_ref l = d->lights[i];
+            const uint32_t t = VK_REF_TYPE(l), ix = VK_REF_INDEX(l);
+            const uint32_t lim = t == VK_T_NODE ? d->n_nodes : t == VK_T_SPHERE ? d->n_spheres : t == VK_T_MSPHERE ? d->n_mspheres
+                               : t == VK_T_RECT ? d->n_rects : t == VK_T_BOX ? d->n_boxes : t == VK_T_XFORM ? d->n_xforms
+                               : t == VK_T_MEDIUM ? d->n_media : 0;
+            if (ix >= lim) return bad(VK_ERR_INVALID, "light reference out of range");
+        }
+        return true;
+    }
+};
+
+template <class T> int upload(vk_ctx* c, const T* src, size_t n, const T** dst) {
+    *dst = nullptr;
+    if (n == 0) n = 1; // keep pointers valid
+    void* p = nullptr;
+    CU(c, cudaMalloc(&p, n * sizeof(T)));
+    c->scene_allocs.push_back(p);
+    if (src) CU(c, cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *dst = (const T*)p;
+    return VK_OK;
+}
+void free_scene(vk_ctx* c) {
+    for (void* p : c->scene_allocs) cudaFree(p);
+    c->scene_allocs.clear();
+    c->has_scene = false;
+}
+int ensure(vk_ctx* c, float** buf, size_t* have, size_t want) {
+    if (*have >= want) return VK_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    CU(c, cudaMalloc((void**)buf, want * sizeof(float)));
+    *have = want;
+    return VK_OK;
+}
+DCamera to_dcam(const vk_camera* k) {
+    DCamera c;
+    auto v3 = [](const float* p) { return make_float3(p[0], p[1], p[2]); };
+    c.origin = v3(k->origin);
+    c.lower_left_corner = v3(k->lower_left_corner);
+    c.horizontal = v3(k->horizontal);
+    c.vertical = v3(k->vertical);
+    c.u = v3(k->u);
+    c.v = v3(k->v);
+    c.lens_radius = k->lens_radius;
+    c.time0 = k->time0;
+    c.time1 = k->time1;
+    return c;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int vk_create(int device, vk_ctx** out) {
+    if (!out) return fail(nullptr, VK_ERR_INVALID, "vk_create: null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, VK_ERR_NO_DEVICE, std::string("vk_create: no CUDA device (") + cudaGetErrorString(e) +
+                                                   "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, VK_ERR_INVALID, "vk_create: device index out of range");
+    vk_ctx* c = new vk_ctx;
+    c->device = device;
+#define CUC(call)                                                                                                      \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess) {                                                                                       \
+            g_create_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                         \
+            delete c;                                                                                                  \
+            return VK_ERR_CUDA;                                                                                        \
+        }                                                                                                              \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        g_create_err = std::string("vk_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                       "; this library is built for sm_100a only";
+        delete c;
+        return VK_ERR_NO_DEVICE;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->clock_khz = prop.clockRate;
+    std::snprintf(c->name, sizeof(c->name), "%.100s", prop.name);
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev0));
+    CUC(cudaEventCreate(&c->ev1));
+    CUC(cudaEventCreate(&c->ev2));
+    CUC(cudaMalloc((void**)&c->counters, 4 * sizeof(unsigned long long)));
+#undef CUC
+    *out = c;
+    return VK_OK;
+}
+
+void vk_destroy(vk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_scene(c);
+    if (c->partial) cudaFree(c->partial);
+    if (c->frame) cudaFree(c->frame);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->counters) cudaFree(c->counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* vk_last_error(const vk_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int vk_device_info(vk_ctx* c, int* sm_count, int* clock_khz, char* name, size_t name_len) {
+    if (!c) return VK_ERR_INVALID;
+    if (sm_count) *sm_count = c->sm_count;
+    if (clock_khz) *clock_khz = c->clock_khz;
+    if (name && name_len) std::snprintf(name, name_len, "%s", c->name);
+    return VK_OK;
+}
+
+int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
+    if (!c) return VK_ERR_INVALID;
+    if (!d) return fail(c, VK_ERR_INVALID, "vk_scene_upload: null scene");
+    Validator v;
+    v.d = d;
+    if (!v.run()) return fail(c, v.code, "vk_scene_upload: " + v.err);
+    CU(c, cudaSetDevice(c->device));
+    free_scene(c);
+
+    // GPU-side re-layout of the node array: a single-object leaf (left == right) is tested twice
+    // by the reference; that only matters for a ConstantMedium (two free-flight draws), so the
+    // second visit is kept (flagged) only there and dropped for deterministic primitives.
+    std::vector<vk_node> nodes(d->nodes, d->nodes + d->n_nodes);
+    for (uint32_t i = 0; i < d->n_nodes; ++i)
+        if (nodes[i].left == nodes[i].right) {
+            vk_ref end = nodes[i].left;
+            while (VK_REF_TYPE(end) == VK_T_XFORM) end = d->xforms[VK_REF_INDEX(end)].child;
+            nodes[i].right = VK_REF_TYPE(end) == VK_T_MEDIUM ? (nodes[i].left | VKD_DUP) : VK_REF_NONE;
+        }
+    std::vector<vk_material> mats(d->materials, d->materials + d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        bool uv;
+        if (mats[i].type == VK_M_SPECDIFFUSE)
+            uv = (d->materials[mats[i].tex].type != VK_M_DIELECTRIC && v.tex_has_image(d->materials[mats[i].tex].tex, 0)) ||
+                 (d->materials[mats[i].aux].type != VK_M_DIELECTRIC && v.tex_has_image(d->materials[mats[i].aux].tex, 0));
+        else
+            uv = mats[i].type != VK_M_DIELECTRIC && v.tex_has_image(mats[i].tex, 0);
+        if (uv) mats[i].aux |= VKD_MAT_NEEDS_UV;
+    }
+    std::vector<float4> pvec((size_t)d->n_perlins * 256);
+    std::vector<uint8_t> pperm((size_t)d->n_perlins * 768);
+    for (uint32_t p = 0; p < d->n_perlins; ++p) {
+        for (int k = 0; k < 256; ++k)
+            pvec[(size_t)p * 256 + k] = make_float4(d->perlins[p].ranvec[k][0], d->perlins[p].ranvec[k][1], d->perlins[p].ranvec[k][2], 0.f);
+        std::memcpy(&pperm[(size_t)p * 768], d->perlins[p].perm_x, 256);
+        std::memcpy(&pperm[(size_t)p * 768 + 256], d->perlins[p].perm_y, 256);
+        std::memcpy(&pperm[(size_t)p * 768 + 512], d->perlins[p].perm_z, 256);
+    }
+
+    DScene s{};
+    int rc;
+#define UP(field, type, src, n)                                                                                        \
+    if ((rc = upload<type>(c, (const type*)(src), (n), (const type**)&s.field)) != VK_OK) {                            \
+        free_scene(c);                                                                                                 \
+        return rc;                                                                                                     \
+    }
+    UP(nodes, float4, nodes.data(), (size_t)d->n_nodes * 2)
+    UP(spheres, float4, d->spheres, d->n_spheres)
+    UP(sphere_mat, uint32_t, d->sphere_mat, d->n_spheres)
+    UP(mspheres, float4, d->mspheres, (size_t)d->n_mspheres * 3)
+    UP(rects, float4, d->rects, (size_t)d->n_rects * 2)
+    UP(boxes, float4, d->boxes, (size_t)d->n_boxes * 2)
+    UP(xforms, float4, d->xforms, (size_t)d->n_xforms * 2)
+    UP(media, float4, d->media, d->n_media)
+    UP(lights, uint32_t, d->lights, d->n_lights)
+    UP(materials, uint4, mats.data(), d->n_materials)
+    UP(textures, uint4, d->textures, d->n_textures)
+    UP(texels, uint8_t, d->texels, (size_t)d->n_texel_bytes)
+    UP(perlin_vec, float4, pvec.data(), pvec.size())
+    UP(perlin_perm, uint8_t, pperm.data(), pperm.size())
+#undef UP
+    s.root = d->root;
+    s.n_lights = d->n_lights;
+    CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
+    c->scene = s;
+    c->has_scene = true;
+    return VK_OK;
+}
+
+// shared body of vk_render / vk_render_device
+static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* d_sum, float* d_sumsq, vk_stats* stats) {
+    if (!c) return VK_ERR_INVALID;
+    if (!c->has_scene) return fail(c, VK_ERR_NO_SCENE, "render: no scene uploaded");
+    if (!cam || !P || !d_sum) return fail(c, VK_ERR_INVALID, "render: null argument");
+    if (P->width < 2 || P->height < 2) return fail(c, VK_ERR_INVALID, "render: width/height must be >= 2 ((width-1) divides, src/main.rs:187)");
+    if (P->spp == 0 || P->spp_begin >= P->spp) return fail(c, VK_ERR_INVALID, "render: bad spp / spp_begin");
+    const uint32_t count = P->spp_count ? P->spp_count : P->spp - P->spp_begin;
+    if ((uint64_t)P->spp_begin + count > P->spp) return fail(c, VK_ERR_INVALID, "render: sample slice exceeds spp");
+    if ((uint64_t)P->width * P->height > 0x7FFFFFFFull / 3) return fail(c, VK_ERR_INVALID, "render: image too large");
+    if (P->variant == VK_VARIANT_WAVEFRONT) return fail(c, VK_ERR_UNSUPPORTED, "render: wavefront variant not built yet");
+    if (!(cam->time0 < cam->time1)) return fail(c, VK_ERR_INVALID, "render: camera time0 >= time1 (gen_range panics, src/main.rs:118)");
+    CU(c, cudaSetDevice(c->device));
+    const bool strict = (P->flags & VK_FLAG_STRICT_MATH) != 0;
+
+    int bps = 0, bt = 0;
+    CU(c, strict ? vkstrict::megakernel_occupancy(&bps, &bt) : vkfast::megakernel_occupancy(&bps, &bt));
+    if (bps < 1) bps = 1;
+    const int grid = c->sm_count * bps;
+    const uint32_t resident_warps = (uint32_t)grid * (uint32_t)bt / 32u;
+
+    RenderArgs a{};
+    a.width = P->width;
+    a.height = P->height;
+    a.spp_begin = P->spp_begin;
+    a.spp_count = count;
+    a.max_depth = P->max_depth;
+    a.seed_lo = (uint32_t)P->seed;
+    a.seed_hi = (uint32_t)(P->seed >> 32);
+    a.background = make_float3(P->background[0], P->background[1], P->background[2]);
+    a.tiles_x = (P->width + 7) / 8;
+    a.tiles_y = (P->height + 3) / 4;
+    // split the samples into chunks until there are ~12 work items per resident warp (dynamic
+    // scheduling evens out the rest), but keep at least 8 samples per chunk
+    const uint32_t n_tiles = a.tiles_x * a.tiles_y;
+    uint32_t n_chunks = (12u * resident_warps + n_tiles - 1) / n_tiles;
+    const uint32_t max_chunks = count >= 8 ? count / 8 : 1;
+    if (n_chunks > max_chunks) n_chunks = max_chunks;
+    if (n_chunks < 1) n_chunks = 1;
+    a.chunk_spp = (count + n_chunks - 1) / n_chunks;
+    a.n_chunks = (count + a.chunk_spp - 1) / a.chunk_spp;
+
+    const size_t plane = (size_t)P->width * P->height * 3;
+    RenderBuffers b{};
+    b.counters = c->counters;
+    if (a.n_chunks == 1) {
+        b.partial_sum = d_sum;
+        b.partial_sumsq = d_sumsq;
+    } else {
+        int rc = ensure(c, &c->partial, &c->partial_floats, plane * a.n_chunks * (d_sumsq ? 2 : 1));
+        if (rc != VK_OK) return rc;
+        b.partial_sum = c->partial;
+        b.partial_sumsq = d_sumsq ? c->partial + plane * a.n_chunks : nullptr;
+    }
+    CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    const DCamera dc = to_dcam(cam);
+    CU(c, strict ? vkstrict::launch_megakernel(c->scene, dc, a, b, grid, c->stream)
+                 : vkfast::launch_megakernel(c->scene, dc, a, b, grid, c->stream));
+    uint32_t launches = 1;
+    if (a.n_chunks > 1) {
+        const unsigned g = (unsigned)((plane + 255) / 256);
+        k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sum, a.n_chunks, plane, d_sum);
+        ++launches;
+        if (d_sumsq) {
+            k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sumsq, a.n_chunks, plane, d_sumsq);
+            ++launches;
+        }
+        CU(c, cudaGetLastError());
+    }
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CU(c, cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->paths = (uint64_t)P->width * P->height * count;
+        stats->rays = h[0];
+        stats->dropped_samples = h[1];
+        CU(c, cudaEventElapsedTime(&stats->ms_kernels, c->ev0, c->ev1));
+        stats->ms_total = stats->ms_kernels;
+        stats->variant = VK_VARIANT_MEGAKERNEL;
+        stats->launches = launches;
+    }
+    return VK_OK;
+}
+
+int vk_render_device(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* d_sum, float* d_sumsq, vk_stats* stats) {
+    return render_into(c, cam, P, d_sum, d_sumsq, stats);
+}
+
+int vk_finalize_device(vk_ctx* c, const float* d_sum, float* d_rgb, size_t n, uint32_t spp) {
+    if (!c || !d_sum || !d_rgb || spp == 0) return fail(c, VK_ERR_INVALID, "vk_finalize_device: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    if (n) k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_sum, d_rgb, n, (float)spp);
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));
+    return VK_OK;
+}
+
+int vk_render(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* out_rgb, float* out_sumsq, vk_stats* stats) {
+    if (!c) return VK_ERR_INVALID;
+    if (!P || !out_rgb) return fail(c, VK_ERR_INVALID, "vk_render: null argument");
+    const size_t plane = (size_t)P->width * P->height * 3;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure(c, &c->frame, &c->frame_floats, plane * 3);
+    if (rc != VK_OK) return rc;
+    if (c->pinned_floats < plane * 2) {
+        if (c->pinned) cudaFreeHost(c->pinned);
+        c->pinned = nullptr;
+        c->pinned_floats = 0;
+        CU(c, cudaMallocHost((void**)&c->pinned, plane * 2 * sizeof(float)));
+        c->pinned_floats = plane * 2;
+    }
+    float *d_sum = c->frame, *d_sq = out_sumsq ? c->frame + plane : nullptr, *d_rgb = c->frame + 2 * plane;
+    CU(c, cudaEventRecord(c->ev2, c->stream));
+    vk_stats st{};
+    rc = render_into(c, cam, P, d_sum, d_sq, &st);
+    if (rc != VK_OK) return rc;
+    k_finalize<<<(unsigned)((plane + 255) / 256), 256, 0, c->stream>>>(d_sum, d_rgb, plane, (float)P->spp);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(c->pinned, d_rgb, plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (out_sumsq) CU(c, cudaMemcpyAsync(c->pinned + plane, d_sq, plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(out_rgb, c->pinned, plane * sizeof(float));
+    if (out_sumsq) std::memcpy(out_sumsq, c->pinned + plane, plane * sizeof(float));
+    st.launches += 1;
+    CU(c, cudaEventElapsedTime(&st.ms_total, c->ev2, c->ev1));
+    if (stats) *stats = st;
+    return VK_OK;
+}
+
+int vk_intersect(vk_ctx* c, const vk_ray* rays, size_t n, const float* medium_xi, uint32_t flags, vk_hit* out) {
+    if (!c) return VK_ERR_INVALID;
+    if (!c->has_scene) return fail(c, VK_ERR_NO_SCENE, "vk_intersect: no scene uploaded");
+    if (n == 0) return VK_OK;
+    if (!rays || !out) return fail(c, VK_ERR_INVALID, "vk_intersect: null argument");
+    CU(c, cudaSetDevice(c->device));
+    vk_ray* d_rays = nullptr;
+    vk_hit* d_hits = nullptr;
+    float* d_xi = nullptr;
+    int rc = VK_OK;
+    cudaError_t e;
+#define STEP(call)                                                                                                     \
+    if (rc == VK_OK && (e = (call)) != cudaSuccess) rc = fail(c, VK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e));
+    STEP(cudaMalloc((void**)&d_rays, n * sizeof(vk_ray)))
+    STEP(cudaMalloc((void**)&d_hits, n * sizeof(vk_hit)))
+    if (medium_xi) {
+        STEP(cudaMalloc((void**)&d_xi, n * VK_MEDIUM_XI_SLOTS * sizeof(float)))
+        STEP(cudaMemcpyAsync(d_xi, medium_xi, n * VK_MEDIUM_XI_SLOTS * sizeof(float), cudaMemcpyHostToDevice, c->stream))
+    }
+    STEP(cudaMemcpyAsync(d_rays, rays, n * sizeof(vk_ray), cudaMemcpyHostToDevice, c->stream))
+    STEP((flags & VK_FLAG_STRICT_MATH) ? vkstrict::launch_intersect(c->scene, d_rays, n, d_xi, d_hits, c->stream)
+                                       : vkfast::launch_intersect(c->scene, d_rays, n, d_xi, d_hits, c->stream))
+    STEP(cudaMemcpyAsync(out, d_hits, n * sizeof(vk_hit), cudaMemcpyDeviceToHost, c->stream))
+    STEP(cudaStreamSynchronize(c->stream))
+#undef STEP
+    cudaFree(d_rays);
+    cudaFree(d_hits);
+    cudaFree(d_xi);
+    return rc;
+}
+
+int vk_measure_peaks(vk_ctx* c, float* fp32_tflops, float* l2_gbs) {
+    if (!c) return VK_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    float* out = nullptr;
+    const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
+    CU(c, cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(float)));
+    float best_ms = 1e30f, ms = 0.f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(c->ev0, c->stream);
+        k_ffma_peak<<<blocks, threads, 0, c->stream>>>(out, iters);
+        cudaEventRecord(c->ev1, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    if (fp32_tflops) *fp32_tflops = (float)((double)blocks * threads * iters * 16.0 * 8.0 * 2.0 / (best_ms * 1e-3) / 1e12);
+    cudaFree(out);
+    const size_t bytes = 32ull << 20; // 32 MiB: well inside the 126 MB L2
+    float4* buf = nullptr;
+    float* sink = nullptr;
+    CU(c, cudaMalloc((void**)&buf, bytes));
+    CU(c, cudaMalloc((void**)&sink, sizeof(float)));
+    CU(c, cudaMemsetAsync(buf, 0, bytes, c->stream));
+    const int reps = 20;
+    best_ms = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(c->ev0, c->stream);
+        k_l2_read<<<c->sm_count * 8, 256, 0, c->stream>>>(buf, bytes / sizeof(float4), reps, sink);
+        cudaEventRecord(c->ev1, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (r > 0 && ms < best_ms) best_ms = ms;
+    }
+    if (l2_gbs) *l2_gbs = (float)((double)bytes * reps / (best_ms * 1e-3) / 1e9);
+    cudaFree(buf);
+    cudaFree(sink);
+    CU(c, cudaGetLastError());
+    return VK_OK;
+}
+
+// Test hook: Philox4x32-10 on the device for the Random123 known-answer vectors.
+int vk_selftest_philox(vk_ctx* c, const uint32_t ctr_key6[6], uint32_t out4[4]) {
+    if (!c || !ctr_key6 || !out4) return VK_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    uint32_t* d = nullptr;
+    CU(c, cudaMalloc((void**)&d, 10 * sizeof(uint32_t)));
+    cudaMemcpyAsync(d, ctr_key6, 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    cudaError_t e = vkfast::launch_philox_kat(d, d + 6, c->stream);
+    cudaMemcpyAsync(out4, d + 6, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    CU(c, e);
+    CU(c, cudaGetLastError());
+    return VK_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,767 @@
+// vk_device.cuh -- device functions of the path-tracing sample loop (sm_100a).
+//
+// Included by vk_kernels.cu, which is compiled twice:
+//   VK_STRICT=0 (namespace vkfast)   FMA contraction on, reciprocal slab test, fast intrinsics where
+//                                    only the distribution matters.  The render path.
+//   VK_STRICT=1 (namespace vkstrict) -fmad=false, IEEE division and sqrt, and the SAME operation
+//                                    order as the reference's Rust, so that hit distances are
+//                                    bit-identical to the CPU restatement (hit-parity path).
+// Every function names the reference code it implements (paths relative to the reference root).
+#pragma once
+#include <math_constants.h>
+
+#include "vk_internal.h"
+
+#ifndef VK_STRICT
+#define VK_STRICT 0
+#endif
+#if VK_STRICT
+#define VK_NS vkstrict
+#else
+#define VK_NS vkfast
+#endif
+
+namespace VK_NS {
+
+#define VKD __device__ __forceinline__
+#define VK_PI 3.14159265358979323846f
+
+// ---------------------------------------------------------------------------------------------
+// Vec3 (src/vec3.rs)
+// ---------------------------------------------------------------------------------------------
+VKD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+VKD float3 f3(float4 v) { return make_float3(v.x, v.y, v.z); }
+VKD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+VKD float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+VKD float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+VKD float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+VKD float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+VKD float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+VKD float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+VKD float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+VKD float length2(float3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+VKD float3 unit_vector(float3 a) { // src/vec3.rs:39-42 (three divisions by sqrt, no rsqrt)
+#if VK_STRICT
+    float n = sqrtf(length2(a));
+    return f3(a.x / n, a.y / n, a.z / n);
+#else
+    return a * rsqrtf(length2(a));
+#endif
+}
+VKD float comp(float3 v, uint32_t a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+VKD bool finite3(float3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); }
+VKD float3 at(float3 o, float3 d, float t) { return o + d * t; } // Ray::at src/main.rs:51-53
+
+// ---------------------------------------------------------------------------------------------
+// RNG: counter-based Philox4x32-10 (Salmon et al. 2011), key = render seed, counter =
+// (pixel, global sample, depth << 8 | block, 0).  Replaces rand::thread_rng() at every call site
+// of the hot path; only the distributions are kept.
+// ---------------------------------------------------------------------------------------------
+VKD uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+VKD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; } // gen::<f32>(): 24-bit [0,1)
+VKD float gen_range(uint32_t x, float lo, float hi) {                           // gen_range(lo,hi): 23-bit [lo,hi)
+    const float scale = hi - lo;
+    const float res = __uint_as_float(0x3F800000u | (x >> 9)) * scale + (lo - scale);
+    return res < hi ? res : lo; // rand 0.7.3 redraws on the 2^-24 rounding event
+}
+struct PathRng {
+    uint32_t pixel, sample;
+    uint2 key;
+    VKD uint4 block(uint32_t depth, uint32_t blk) const {
+        return philox4x32_10(make_uint4(pixel, sample, (depth << 8) | blk, 0u), key);
+    }
+};
+// Source of the ConstantMedium free-flight variate (src/hittable.rs:473): an injected table for
+// vk_intersect, Philox blocks 1..2 of the current segment for the render.
+struct MediumXi {
+    const float* table; // VK_MEDIUM_XI_SLOTS per ray, or nullptr
+    PathRng rng;
+    uint32_t depth;
+    VKD float get(uint32_t medium_index, uint32_t second_visit) const {
+        const uint32_t slot = (medium_index * 2u + second_visit) % VK_MEDIUM_XI_SLOTS;
+        if (table) return table[slot];
+        const uint4 b = rng.block(depth, 1u + (slot >> 2));
+        const uint32_t w = (slot & 3u) == 0 ? b.x : ((slot & 3u) == 1 ? b.y : ((slot & 3u) == 2 ? b.z : b.w));
+        return u01(w);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// AxisBB::hit (src/accel.rs:16-35).  f32::min/max and fminf/fmaxf both return the non-NaN operand.
+// The reference's per-axis early exit is equivalent to one test after the third axis (the
+// interval only shrinks).  STRICT divides like the reference; FAST multiplies by 1/d.
+// ---------------------------------------------------------------------------------------------
+VKD bool aabb_hit(float3 bmin, float3 bmax, float3 o, float3 d, float3 inv_d, float tmin, float tmax) {
+#if VK_STRICT
+    (void)inv_d;
+    const float ax = (bmin.x - o.x) / d.x, bx = (bmax.x - o.x) / d.x;
+    const float ay = (bmin.y - o.y) / d.y, by = (bmax.y - o.y) / d.y;
+    const float az = (bmin.z - o.z) / d.z, bz = (bmax.z - o.z) / d.z;
+#else
+    (void)d;
+    const float ax = (bmin.x - o.x) * inv_d.x, bx = (bmax.x - o.x) * inv_d.x;
+    const float ay = (bmin.y - o.y) * inv_d.y, by = (bmax.y - o.y) * inv_d.y;
+    const float az = (bmin.z - o.z) * inv_d.z, bz = (bmax.z - o.z) * inv_d.z;
+#endif
+    tmin = fmaxf(fminf(ax, bx), tmin);
+    tmax = fminf(fmaxf(ax, bx), tmax);
+    tmin = fmaxf(fminf(ay, by), tmin);
+    tmax = fminf(fmaxf(ay, by), tmax);
+    tmin = fmaxf(fminf(az, bz), tmin);
+    tmax = fminf(fmaxf(az, bz), tmax);
+    return !(tmax <= tmin);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sphere::hit, distance only (src/hittable.rs:65-95): half-b quadratic, a = |d|^2 (directions are
+// never normalised), strict tmin < t < tmax, near root first.
+// ---------------------------------------------------------------------------------------------
+VKD bool sphere_t(float3 c, float radius, float3 o, float3 d, float tmin, float tmax, float& t) {
+    const float3 oc = o - c;
+    const float a = length2(d);
+    const float half_b = dot3(oc, d);
+    const float cc = length2(oc) - radius * radius;
+    const float disc = half_b * half_b - a * cc;
+    if (disc > 0.0f) {
+        const float root = sqrtf(disc);
+        float temp = (-half_b - root) / a;
+        if (tmin < temp && temp < tmax) {
+            t = temp;
+            return true;
+        }
+        temp = (-half_b + root) / a;
+        if (tmin < temp && temp < tmax) {
+            t = temp;
+            return true;
+        }
+    }
+    return false;
+}
+VKD float3 msphere_center(float4 m0, float4 m1, float time1, float time) { // src/hittable.rs:147-150
+    const float3 c0 = f3(m0), c1 = f3(m1);
+    return c0 + (c1 - c0) * ((time - m1.w) / (time1 - m1.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rect::hit, distance only (src/hittable.rs:230-239): inclusive bounds written as the reference
+// writes them, so NaN t / NaN a,b pass exactly where they pass there (Q14).
+// ---------------------------------------------------------------------------------------------
+VKD bool rect_t(float4 bounds, float k, uint32_t axes, float3 o, float3 d, float tmin, float tmax, float& t) {
+    const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u, a2 = (axes >> 4) & 3u;
+    const float tt = (k - comp(o, a2)) / comp(d, a2);
+    if (tt < tmin || tt > tmax) return false;
+    const float a = comp(o, a0) + tt * comp(d, a0);
+    const float b = comp(o, a1) + tt * comp(d, a1);
+    if (a < bounds.x || a > bounds.y || b < bounds.z || b > bounds.w) return false;
+    t = tt;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boxy::hit (src/hittable.rs:363-365) = list hit (:381-394) over the six sides in Boxy::new order
+// (:325-353): first side wins ties (strict rec.t < closest_dist), tmax shrinks as sides hit.
+// ---------------------------------------------------------------------------------------------
+VKD bool box_t(float3 mn, float3 mx, float3 o, float3 d, float tmin, float tmax, float& t_out, uint32_t& face) {
+    float closest = tmax;
+    int f = -1;
+#define VK_SIDE(F, K, O2, D2, O0, D0, C0, C1, O1, D1, E0, E1)                                                          \
+    {                                                                                                                  \
+        const float tt = ((K) - (O2)) / (D2);                                                                          \
+        if (!(tt < tmin || tt > closest)) {                                                                            \
+            const float a = (O0) + tt * (D0), b = (O1) + tt * (D1);                                                    \
+            if (!(a < (C0) || a > (C1) || b < (E0) || b > (E1)) && tt < closest) {                                     \
+                closest = tt;                                                                                          \
+                f = (F);                                                                                               \
+            }                                                                                                          \
+        }                                                                                                              \
+    }
+    VK_SIDE(0, mx.z, o.z, d.z, o.x, d.x, mn.x, mx.x, o.y, d.y, mn.y, mx.y) // XYRect at p1.z
+    VK_SIDE(1, mn.z, o.z, d.z, o.x, d.x, mn.x, mx.x, o.y, d.y, mn.y, mx.y) // FlipFace(XYRect at p0.z)
+    VK_SIDE(2, mx.y, o.y, d.y, o.x, d.x, mn.x, mx.x, o.z, d.z, mn.z, mx.z) // XZRect at p1.y
+    VK_SIDE(3, mn.y, o.y, d.y, o.x, d.x, mn.x, mx.x, o.z, d.z, mn.z, mx.z) // FlipFace(XZRect at p0.y)
+    VK_SIDE(4, mx.x, o.x, d.x, o.y, d.y, mn.y, mx.y, o.z, d.z, mn.z, mx.z) // YZRect at p1.x
+    VK_SIDE(5, mn.x, o.x, d.x, o.y, d.y, mn.y, mx.y, o.z, d.z, mn.z, mx.z) // FlipFace(YZRect at p0.x)
+#undef VK_SIDE
+    if (f < 0) return false;
+    t_out = closest;
+    face = (uint32_t)f;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Translate / RotateY / RotateX / RotateZ / FlipFace: world -> object ray
+// (src/hittable.rs:508, :591-595, :680-684, :769-773) and object -> world point/normal
+// (:511, :603-607, :692-696, :781-785).
+// ---------------------------------------------------------------------------------------------
+VKD void rot_fwd(uint32_t kind, float s, float c, float3& q) {
+    const float3 v = q;
+    if (kind == VK_X_ROTATE_Y) {
+        q.x = c * v.x - s * v.z;
+        q.z = s * v.x + c * v.z;
+    } else if (kind == VK_X_ROTATE_X) {
+        q.y = c * v.y + s * v.z;
+        q.z = -s * v.y + c * v.z;
+    } else if (kind == VK_X_ROTATE_Z) {
+        q.x = c * v.x + s * v.y;
+        q.y = -s * v.x + c * v.y;
+    }
+}
+VKD void rot_back(uint32_t kind, float s, float c, float3& q) {
+    const float3 v = q;
+    if (kind == VK_X_ROTATE_Y) {
+        q.x = c * v.x + s * v.z;
+        q.z = -s * v.x + c * v.z;
+    } else if (kind == VK_X_ROTATE_X) {
+        q.y = c * v.y - s * v.z;
+        q.z = s * v.y + c * v.z;
+    } else if (kind == VK_X_ROTATE_Z) {
+        q.x = c * v.x - s * v.y;
+        q.y = s * v.x + c * v.y;
+    }
+}
+// Walk a wrapper chain down to its first non-wrapper child, transforming the ray on the way.
+VKD uint32_t chain_down(const DScene& sc, uint32_t ref, float3& o, float3& d) {
+#pragma unroll 1
+    while (VKD_TYPE(ref) == VK_T_XFORM) {
+        const float4 x0 = __ldg(&sc.xforms[2 * VKD_INDEX(ref)]);
+        const float4 x1 = __ldg(&sc.xforms[2 * VKD_INDEX(ref) + 1]);
+        const uint32_t kind = __float_as_uint(x0.x);
+        if (kind == VK_X_TRANSLATE) {
+            o = o - f3(x1);
+        } else if (kind != VK_X_FLIP) {
+            rot_fwd(kind, x1.x, x1.y, o);
+            rot_fwd(kind, x1.x, x1.y, d);
+        }
+        ref = __float_as_uint(x0.y);
+    }
+    return ref;
+}
+
+// Distance-only hit of a leaf primitive (no BVH below it): the shared body of the traversal's
+// leaf test and of ConstantMedium's two boundary queries.
+VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax, float& t,
+                uint32_t& face) {
+    const uint32_t i = VKD_INDEX(ref);
+    face = 0;
+    switch (VKD_TYPE(ref)) {
+    case VK_T_SPHERE: {
+        const float4 s = __ldg(&sc.spheres[i]);
+        return sphere_t(f3(s), s.w, o, d, tmin, tmax, t);
+    }
+    case VK_T_MSPHERE: {
+        const float4 m0 = __ldg(&sc.mspheres[3 * i]), m1 = __ldg(&sc.mspheres[3 * i + 1]), m2 = __ldg(&sc.mspheres[3 * i + 2]);
+        return sphere_t(msphere_center(m0, m1, m2.x, time), m0.w, o, d, tmin, tmax, t);
+    }
+    case VK_T_RECT: {
+        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
+        return rect_t(r0, r1.x, __float_as_uint(r1.y), o, d, tmin, tmax, t);
+    }
+    case VK_T_BOX: {
+        const float4 b0 = __ldg(&sc.boxes[2 * i]), b1 = __ldg(&sc.boxes[2 * i + 1]);
+        return box_t(f3(b0), f3(b1), o, d, tmin, tmax, t, face);
+    }
+    default: return false;
+    }
+}
+
+// ConstantMedium::hit (src/hittable.rs:453-493).  The boundary is a leaf, possibly behind a wrapper
+// chain (t is invariant under the chain).
+VKD bool medium_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax,
+                  const MediumXi& xi, float& t) {
+    const float4 m = __ldg(&sc.media[VKD_INDEX(ref)]);
+    float3 bo = o, bd = d;
+    const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
+    float t1, t2;
+    uint32_t face;
+    if (!leaf_t(sc, b, bo, bd, time, -CUDART_INF_F, CUDART_INF_F, t1, face)) return false;
+    if (!leaf_t(sc, b, bo, bd, time, t1 + 0.0001f, CUDART_INF_F, t2, face)) return false;
+    if (t1 < tmin) t1 = tmin;
+    if (t2 > tmax) t2 = tmax;
+    if (t1 >= t2) return false;
+    if (t1 < 0.0f) t1 = 0.0f;
+    const float ray_length = sqrtf(length2(d));
+    const float distance_inside_boundary = (t2 - t1) * ray_length;
+    const float hit_distance = m.y * logf(xi.get(VKD_INDEX(ref), (ref & VKD_DUP) ? 1u : 0u));
+    if (hit_distance > distance_inside_boundary) return false;
+    t = t1 + hit_distance / ray_length;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVHNode::hit (src/accel.rs:58-83) as an explicit-stack loop: left subtree first, then right with
+// tmax = closest so far -- exactly the values the recursion passes, since everything visited
+// before a node is a left sibling of one of its ancestors.  Any hit a child returns replaces the
+// current one (the reference's tie rule `l.t < r.t ? left : right`).  Only (t, primitive,
+// instance) are tracked; the HitRec is built once, after the loop (resolve_hit).
+// ---------------------------------------------------------------------------------------------
+struct TraceHit {
+    float t;
+    uint32_t prim; // leaf ref, VK_REF_NONE = miss
+    uint32_t inst; // outermost wrapper of the chain the leaf was reached through, or 0
+    uint32_t face;
+};
+
+VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin, float tmax, const MediumXi& xi) {
+    uint32_t stack[VKD_STACK];
+    int sp = 0;
+    float3 co = o, cd = d; // ray in the current frame (world, or the frame of the instance being traversed)
+    float3 cinv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    uint32_t cur_inst = 0;
+    TraceHit best;
+    best.t = tmax;
+    best.prim = VK_REF_NONE;
+    best.inst = 0;
+    best.face = 0;
+    uint32_t ref = sc.root;
+#pragma unroll 1
+    for (;;) {
+        const uint32_t type = VKD_TYPE(ref);
+        if (type == VK_T_NODE) {
+            const float4 n0 = __ldg(&sc.nodes[2 * VKD_INDEX(ref)]);
+            const float4 n1 = __ldg(&sc.nodes[2 * VKD_INDEX(ref) + 1]);
+            if (aabb_hit(f3(n0), f3(n1), co, cd, cinv, tmin, best.t)) {
+                const uint32_t right = __float_as_uint(n1.w);
+                if (right != VK_REF_NONE) stack[sp++] = right;
+                ref = __float_as_uint(n0.w);
+                continue;
+            }
+        } else if (type == VK_T_XFORM) {
+            float3 to = co, td = cd;
+            const uint32_t child = chain_down(sc, ref, to, td);
+            if (VKD_TYPE(child) == VK_T_NODE) { // instanced sub-BVH: traverse it in object space
+                stack[sp++] = VKD_T_EXIT << 28;
+                co = to;
+                cd = td;
+                cinv = f3(1.0f / td.x, 1.0f / td.y, 1.0f / td.z);
+                cur_inst = ref & ~VKD_DUP;
+                ref = child;
+                continue;
+            }
+            float t;
+            uint32_t face = 0;
+            bool hit;
+            if (VKD_TYPE(child) == VK_T_MEDIUM) hit = medium_t(sc, child | (ref & VKD_DUP), to, td, time, tmin, best.t, xi, t);
+            else hit = leaf_t(sc, child, to, td, time, tmin, best.t, t, face);
+            if (hit) {
+                best.t = t;
+                best.prim = child & ~VKD_DUP;
+                best.inst = ref & ~VKD_DUP;
+                best.face = face;
+            }
+        } else if (type == VKD_T_EXIT) {
+            co = o;
+            cd = d;
+            cinv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            cur_inst = 0;
+        } else if (type != VK_T_NONE) {
+            float t;
+            uint32_t face = 0;
+            bool hit;
+            if (type == VK_T_MEDIUM) hit = medium_t(sc, ref, co, cd, time, tmin, best.t, xi, t);
+            else hit = leaf_t(sc, ref, co, cd, time, tmin, best.t, t, face);
+            if (hit) {
+                best.t = t;
+                best.prim = ref & ~VKD_DUP;
+                best.inst = cur_inst;
+                best.face = face;
+            }
+        }
+        if (sp == 0) break;
+        ref = stack[--sp];
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// HitRec (src/hittable.rs:11-31) of the winning primitive, built once per segment.
+// ---------------------------------------------------------------------------------------------
+struct HitRecD {
+    float3 p, normal;
+    float t, u, v;
+    uint32_t front, mat;
+};
+
+VKD void spherical(float3 p, float& u, float& v) { // Sphere::spherical src/hittable.rs:54-61
+    const float phi = atan2f(p.z, p.x);
+    const float theta = asinf(p.y);
+    u = 1.0f - ((phi + VK_PI) / (2.0f * VK_PI));
+    v = (theta + VK_PI / 2.0f) / VK_PI;
+}
+VKD void set_face_normal(float3 dir, float3 outward, HitRecD& rec) { // src/hittable.rs:23-30
+    rec.front = dot3(dir, outward) < 0.0f ? 1u : 0u;
+    rec.normal = rec.front ? outward : -outward;
+}
+VKD void rect_record(float4 bounds, float k, uint32_t axes, uint32_t flip, float3 o, float3 d, float t, bool want_uv,
+                     HitRecD& rec) { // src/hittable.rs:240-255 (+ FlipFace :300-308)
+    (void)k;
+    const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u, a2 = (axes >> 4) & 3u;
+    rec.p = at(o, d, t);
+    set_face_normal(d, f3(a2 == 0 ? 1.0f : 0.0f, a2 == 1 ? 1.0f : 0.0f, a2 == 2 ? 1.0f : 0.0f), rec);
+    if (flip) rec.front ^= 1u;
+    if (want_uv) {
+        const float a = comp(o, a0) + t * comp(d, a0);
+        const float b = comp(o, a1) + t * comp(d, a1);
+        rec.u = (a - bounds.x) / (bounds.y - bounds.x);
+        rec.v = (b - bounds.z) / (bounds.w - bounds.z);
+    }
+}
+// the rect record of side `face` of a box (Boxy::new order)
+VKD void box_side(float3 mn, float3 mx, uint32_t face, float4& bounds, float& k, uint32_t& axes) {
+    switch (face >> 1) {
+    case 0: bounds = make_float4(mn.x, mx.x, mn.y, mx.y); k = (face & 1u) ? mn.z : mx.z; axes = 0u | (1u << 2) | (2u << 4); break;
+    case 1: bounds = make_float4(mn.x, mx.x, mn.z, mx.z); k = (face & 1u) ? mn.y : mx.y; axes = 0u | (2u << 2) | (1u << 4); break;
+    default: bounds = make_float4(mn.y, mx.y, mn.z, mx.z); k = (face & 1u) ? mn.x : mx.x; axes = 1u | (2u << 2) | (0u << 4); break;
+    }
+}
+// Full record of a leaf primitive hit at distance t by the ray (o, d) of the leaf's frame.
+VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, float3 d, float time, float t, bool want_uv,
+                     HitRecD& rec) {
+    const uint32_t i = VKD_INDEX(ref);
+    rec.t = t;
+    rec.u = 0.0f;
+    rec.v = 0.0f;
+    switch (VKD_TYPE(ref)) {
+    case VK_T_SPHERE:
+    case VK_T_MSPHERE: { // src/hittable.rs:76-89, :165-178
+        float3 c;
+        float radius;
+        if (VKD_TYPE(ref) == VK_T_SPHERE) {
+            const float4 s = __ldg(&sc.spheres[i]);
+            c = f3(s);
+            radius = s.w;
+            rec.mat = __ldg(&sc.sphere_mat[i]);
+        } else {
+            const float4 m0 = __ldg(&sc.mspheres[3 * i]), m1 = __ldg(&sc.mspheres[3 * i + 1]), m2 = __ldg(&sc.mspheres[3 * i + 2]);
+            c = msphere_center(m0, m1, m2.x, time);
+            radius = m0.w;
+            rec.mat = __float_as_uint(m2.y);
+        }
+        rec.p = at(o, d, t);
+        const float3 outward = (rec.p - c) / radius;
+        set_face_normal(d, outward, rec);
+        if (want_uv) spherical(outward, rec.u, rec.v);
+        break;
+    }
+    case VK_T_RECT: {
+        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
+        const uint32_t axes = __float_as_uint(r1.y);
+        rec.mat = __float_as_uint(r1.z);
+        rect_record(r0, r1.x, axes, axes & VK_RECT_FLIP, o, d, t, want_uv, rec);
+        break;
+    }
+    case VK_T_BOX: {
+        const float4 b0 = __ldg(&sc.boxes[2 * i]), b1 = __ldg(&sc.boxes[2 * i + 1]);
+        float4 bounds;
+        float k;
+        uint32_t axes;
+        box_side(f3(b0), f3(b1), face, bounds, k, axes);
+        rec.mat = __float_as_uint(b0.w);
+        rect_record(bounds, k, axes, face & 1u, o, d, t, want_uv, rec);
+        break;
+    }
+    default: break;
+    }
+}
+
+VKD bool mat_needs_uv(const DScene& sc, uint32_t mat) { return (__ldg(&sc.materials[mat]).w & VKD_MAT_NEEDS_UV) != 0; }
+
+// Build the HitRec the reference's `world.hit()` returns for the winning (prim, inst, t):
+// re-walk the wrapper chain down (same operations -> same bits), make the leaf record in the
+// object frame, then apply each wrapper's output stage on the way back up, including the
+// set_face_normal calls with the child-frame ray (Translate :519, Rotate :618/:707/:796 -- Q9).
+VKD void resolve_hit(const DScene& sc, const TraceHit& h, float3 o, float3 d, float time, bool always_uv, HitRecD& rec) {
+    uint32_t kinds[VK_MAX_XFORM_DEPTH];
+    float4 prm[VK_MAX_XFORM_DEPTH];
+    float3 dchild[VK_MAX_XFORM_DEPTH];
+    int nl = 0;
+    float3 ro = o, rd = d;
+    uint32_t ref = h.inst;
+#pragma unroll 1
+    while (VKD_TYPE(ref) == VK_T_XFORM && nl < VK_MAX_XFORM_DEPTH) {
+        const float4 x0 = __ldg(&sc.xforms[2 * VKD_INDEX(ref)]);
+        const float4 x1 = __ldg(&sc.xforms[2 * VKD_INDEX(ref) + 1]);
+        const uint32_t kind = __float_as_uint(x0.x);
+        if (kind == VK_X_TRANSLATE) ro = ro - f3(x1);
+        else if (kind != VK_X_FLIP) {
+            rot_fwd(kind, x1.x, x1.y, ro);
+            rot_fwd(kind, x1.x, x1.y, rd);
+        }
+        kinds[nl] = kind;
+        prm[nl] = x1;
+        dchild[nl] = rd;
+        ++nl;
+        ref = __float_as_uint(x0.y);
+    }
+    if (VKD_TYPE(h.prim) == VK_T_MEDIUM) { // src/hittable.rs:481-489
+        const float4 m = __ldg(&sc.media[VKD_INDEX(h.prim)]);
+        rec.mat = __float_as_uint(m.z);
+        rec.t = h.t;
+        rec.p = at(ro, rd, h.t);
+        rec.normal = f3(1.0f, 0.0f, 0.0f);
+        rec.front = 1u;
+        rec.u = 0.0f;
+        rec.v = 0.0f;
+        if (always_uv || mat_needs_uv(sc, rec.mat)) { // (u, v) of rec1, the boundary entry hit
+            float3 bo = ro, bd = rd;
+            const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
+            float t1;
+            uint32_t face;
+            if (leaf_t(sc, b, bo, bd, time, -CUDART_INF_F, CUDART_INF_F, t1, face)) {
+                HitRecD r1;
+                leaf_record(sc, b, face, bo, bd, time, t1, true, r1);
+                rec.u = r1.u;
+                rec.v = r1.v;
+            }
+        }
+    } else {
+        uint32_t mat_peek = 0;
+        bool want_uv = always_uv;
+        if (!want_uv) { // spherical() costs an atan2 + asin: only pay for it when a texture reads (u,v)
+            const uint32_t i = VKD_INDEX(h.prim);
+            switch (VKD_TYPE(h.prim)) {
+            case VK_T_SPHERE: mat_peek = __ldg(&sc.sphere_mat[i]); break;
+            case VK_T_MSPHERE: mat_peek = __float_as_uint(__ldg(&sc.mspheres[3 * i + 2]).y); break;
+            case VK_T_RECT: mat_peek = __float_as_uint(__ldg(&sc.rects[2 * i + 1]).z); break;
+            default: mat_peek = __float_as_uint(__ldg(&sc.boxes[2 * i]).w); break;
+            }
+            want_uv = mat_needs_uv(sc, mat_peek);
+        }
+        leaf_record(sc, h.prim, h.face, ro, rd, time, h.t, want_uv, rec);
+    }
+#pragma unroll 1
+    for (int l = nl - 1; l >= 0; --l) {
+        const uint32_t kind = kinds[l];
+        if (kind == VK_X_FLIP) {
+            rec.front ^= 1u;
+        } else if (kind == VK_X_TRANSLATE) {
+            rec.p = rec.p + f3(prm[l]);
+            set_face_normal(dchild[l], rec.normal, rec);
+        } else {
+            rot_back(kind, prm[l].x, prm[l].y, rec.p);
+            float3 n = rec.normal;
+            rot_back(kind, prm[l].x, prm[l].y, n);
+            set_face_normal(dchild[l], n, rec);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Textures (src/material.rs:228-434)
+// ---------------------------------------------------------------------------------------------
+VKD float perlin_noise(const float4* __restrict__ vec, const uint8_t* __restrict__ perm, float3 p) { // :392-413 + :331-352
+    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    const float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    const uint32_t i = __float2uint_rz(fx), j = __float2uint_rz(fy), k = __float2uint_rz(fz); // saturating `as usize` (Q16)
+    const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (uint32_t di = 0; di < 2; ++di)
+#pragma unroll
+        for (uint32_t dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (uint32_t dk = 0; dk < 2; ++dk) {
+                const uint32_t idx = perm[(i + di) & 255u] ^ perm[256u + ((j + dj) & 255u)] ^ perm[512u + ((k + dk) & 255u)];
+                const float4 c = __ldg(&vec[idx]);
+                const float fi = (float)di, fj = (float)dj, fk = (float)dk;
+                accum += (fi * uu + (1.0f - fi) * (1.0f - uu)) * (fj * vv + (1.0f - fj) * (1.0f - vv)) *
+                         (fk * ww + (1.0f - fk) * (1.0f - ww)) * dot3(f3(c), f3(u - fi, v - fj, w - fk));
+            }
+    return accum;
+}
+VKD float perlin_turb(const float4* vec, const uint8_t* perm, float3 p, int depth) { // :379-390
+    float accum = 0.0f, weight = 1.0f;
+    float3 tp = p;
+#pragma unroll 1
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * perlin_noise(vec, perm, tp);
+        weight *= 0.5f;
+        tp = tp * 2.0f;
+    }
+    return fabsf(accum);
+}
+VKD float clamp_ref(float x, float mn, float mx) { return x < mn ? mn : (x > mx ? mx : x); } // Vec3::clamp keeps NaN
+VKD float3 tex_value(const DScene& sc, uint32_t ti, float u, float v, float3 p) {
+    uint4 t = __ldg(&sc.textures[ti]);
+#pragma unroll 1
+    for (int guard = 0; t.x == VK_TEX_CHECKER && guard < 16; ++guard) { // Checker :250-258 (sinf, not __sinf: args ~1e3)
+        const float sins = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
+        t = __ldg(&sc.textures[sins < 0.0f ? t.y : t.z]);
+    }
+    if (t.x == VK_TEX_SOLID) return f3(__uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
+    if (t.x == VK_TEX_IMAGE) { // ImageTexture::value :282-303, nearest texel, v flipped, RGB8
+        const uint32_t width = t.z, height = t.w;
+        const float uc = clamp_ref(u, 0.0f, 1.0f);
+        const float vc = 1.0f - clamp_ref(v, 0.0f, 1.0f);
+        uint32_t i = __float2uint_rz(uc * (float)width);
+        uint32_t j = __float2uint_rz(vc * (float)height);
+        if (i >= width) i = width - 1;
+        if (j >= height) j = height - 1;
+        const uint8_t* pix = sc.texels + (size_t)t.y + ((size_t)j * width + i) * 3u;
+        const float s = 1.0f / 255.0f;
+        return f3(s * (float)__ldg(pix), s * (float)__ldg(pix + 1), s * (float)__ldg(pix + 2));
+    }
+    // NoiseTexture::value :430-433
+    const float scale = __uint_as_float(t.z);
+    const float turb = perlin_turb(sc.perlin_vec + 256u * t.y, sc.perlin_perm + 768u * t.y, p, 7);
+    const float g = 0.5f * (1.0f + sinf(scale * p.z + 10.0f * turb));
+    return f3(g, g, g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// util.rs: reflect / refract / schlick (:14-29), ONB (:94-110), cosine direction (:52-63)
+// ---------------------------------------------------------------------------------------------
+VKD float3 reflect(float3 v, float3 n) { return v - n * dot3(v, n) * 2.0f; }
+VKD float3 refract(float3 uv, float3 n, float etai_over_etat) {
+    const float cos_theta = -dot3(uv, n);
+    const float3 r_out_parallel = (uv + n * cos_theta) * etai_over_etat;
+    const float3 r_out_perp = n * -sqrtf(1.0f - length2(r_out_parallel)); // no abs under the sqrt (Q7)
+    return r_out_parallel + r_out_perp;
+}
+VKD float schlick(float cosine, float ref_idx) {
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    const float x = 1.0f - cosine, x2 = x * x;
+    return r0 + (1.0f - r0) * (x2 * x2 * x); // powf(5.0)
+}
+struct Onb {
+    float3 u, v, w;
+};
+VKD Onb onb_from_w(float3 n) {
+    Onb o;
+    o.w = unit_vector(n);
+    const float3 a = fabsf(o.w.x) > 0.9f ? f3(0.0f, 1.0f, 0.0f) : f3(1.0f, 0.0f, 0.0f);
+    o.v = unit_vector(cross3(o.w, a));
+    o.u = cross3(o.w, o.v);
+    return o;
+}
+VKD float3 random_cosine_direction(float r1, float r2) {
+    const float z = sqrtf(1.0f - r2);
+    float s, c;
+#if VK_STRICT
+    sincosf(2.0f * r1 * VK_PI, &s, &c);
+#else
+    __sincosf(2.0f * r1 * VK_PI, &s, &c);
+#endif
+    const float sr = sqrtf(r2);
+    return f3(c * sr, s * sr, z);
+}
+// random_in_unit_sphere (:31-39) without the rejection loop: uniform direction x cbrt(u) radius
+// is the same distribution (uniform in the unit ball).
+VKD float3 random_in_unit_sphere(float u1, float u2, float u3) {
+    const float z = 1.0f - 2.0f * u1;
+    const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    __sincosf(2.0f * VK_PI * u2, &s, &c);
+    const float rad = cbrtf(u3);
+    return f3(r * c, r * s, z) * rad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Light sampling: `impl Hittable for Vec<Arc<HittableSS>>` pdf_value / random
+// (src/hittable.rs:420-433) over SceneConfig.lights, with the per-type implementations:
+// Rect (:271-291), Sphere (:104-134, keeps the (1-z*z) bug Q18), Boxy (:371-377, whose flipped
+// sides fall back to the trait defaults 0.0 / (1,0,0) :36-41).
+// ---------------------------------------------------------------------------------------------
+VKD float rect_pdf_value(float4 bounds, float k, uint32_t axes, float3 origin, float3 v) {
+    float t;
+    if (!rect_t(bounds, k, axes, origin, v, 0.001f, CUDART_INF_F, t)) return 0.0f;
+    const float area = (bounds.y - bounds.x) * (bounds.w - bounds.z);
+    const float distance_squared = t * t * length2(v);
+    // rec.normal is +-e_axis2, so |v . n| = |v[axis2]|
+    const float cosine = fabsf(comp(v, (axes >> 4) & 3u)) / sqrtf(length2(v));
+    return distance_squared / (cosine * area);
+}
+VKD float3 rect_random(float4 bounds, float k, uint32_t axes, float3 origin, uint32_t x0, uint32_t x1) {
+    const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u;
+    const float pa = gen_range(x0, bounds.x, bounds.y), pb = gen_range(x1, bounds.z, bounds.w);
+    float3 pt;
+    pt.x = a0 == 0 ? pa : (a1 == 0 ? pb : k);
+    pt.y = a0 == 1 ? pa : (a1 == 1 ? pb : k);
+    pt.z = a0 == 2 ? pa : (a1 == 2 ? pb : k);
+    return pt - origin;
+}
+VKD float light_pdf_value(const DScene& sc, uint32_t ref, float3 o, float3 v) {
+    const uint32_t i = VKD_INDEX(ref);
+    switch (VKD_TYPE(ref)) {
+    case VK_T_RECT: {
+        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
+        if (__float_as_uint(r1.y) & VK_RECT_FLIP) return 0.0f; // FlipFace: trait default
+        return rect_pdf_value(r0, r1.x, __float_as_uint(r1.y), o, v);
+    }
+    case VK_T_SPHERE: {
+        const float4 s = __ldg(&sc.spheres[i]);
+        float t;
+        if (!sphere_t(f3(s), s.w, o, v, 0.001f, CUDART_INF_F, t)) return 0.0f;
+        const float cos_theta_max = sqrtf(1.0f - s.w * s.w / length2(f3(s) - o));
+        const float solid_angle = 2.0f * VK_PI * (1.0f - cos_theta_max);
+        return 1.0f / solid_angle;
+    }
+    case VK_T_BOX: {
+        const float4 b0 = __ldg(&sc.boxes[2 * i]), b1 = __ldg(&sc.boxes[2 * i + 1]);
+        const float weight = 1.0f / 6.0f;
+        float sum = 0.0f;
+#pragma unroll 1
+        for (uint32_t f = 0; f < 6; ++f) {
+            float4 bounds;
+            float k;
+            uint32_t axes;
+            box_side(f3(b0), f3(b1), f, bounds, k, axes);
+            sum += weight * ((f & 1u) ? 0.0f : rect_pdf_value(bounds, k, axes, o, v));
+        }
+        return sum;
+    }
+    default: return 0.0f; // Hittable::pdf_value default
+    }
+}
+VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, uint32_t x1, uint32_t x2) {
+    const uint32_t i = VKD_INDEX(ref);
+    switch (VKD_TYPE(ref)) {
+    case VK_T_RECT: {
+        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
+        if (__float_as_uint(r1.y) & VK_RECT_FLIP) return f3(1.0f, 0.0f, 0.0f);
+        return rect_random(r0, r1.x, __float_as_uint(r1.y), o, x0, x1);
+    }
+    case VK_T_SPHERE: {
+        const float4 s = __ldg(&sc.spheres[i]);
+        const float3 direction = f3(s) - o;
+        const float distance_squared = length2(direction);
+        const Onb uvw = onb_from_w(direction);
+        const float r1 = u01(x0), r2 = u01(x1);
+        const float z = 1.0f + r2 * (sqrtf(1.0f - s.w * s.w / distance_squared) - 1.0f);
+        float sn, cs;
+        sincosf(2.0f * VK_PI * r1, &sn, &cs);
+        const float x = cs * (1.0f - z * z), y = sn * (1.0f - z * z);
+        return uvw.u * x + uvw.v * y + uvw.w * z;
+    }
+    case VK_T_BOX: {
+        const float4 b0 = __ldg(&sc.boxes[2 * i]), b1 = __ldg(&sc.boxes[2 * i + 1]);
+        const uint32_t f = min(5u, (uint32_t)(u01(x2) * 6.0f));
+        if (f & 1u) return f3(1.0f, 0.0f, 0.0f);
+        float4 bounds;
+        float k;
+        uint32_t axes;
+        box_side(f3(b0), f3(b1), f, bounds, k, axes);
+        return rect_random(bounds, k, axes, o, x0, x1);
+    }
+    default: return f3(1.0f, 0.0f, 0.0f); // Hittable::random default
+    }
+}
+VKD float lights_pdf_value(const DScene& sc, float3 o, float3 v) {
+    const float weight = 1.0f / (float)sc.n_lights;
+    float sum = 0.0f;
+#pragma unroll 1
+    for (uint32_t l = 0; l < sc.n_lights; ++l) sum += weight * light_pdf_value(sc, __ldg(&sc.lights[l]), o, v);
+    return sum;
+}
+
+} // namespace VK_NS

@@ -1,0 +1,268 @@
+// vk_kernels.cu -- kernels of the sample loop.  Compiled twice (see vk_device.cuh): vkfast / vkstrict.
+//
+//   k_megakernel   persistent path tracer: one lane = one pixel of an 8x4 warp tile, looping over a
+//                  chunk of samples with path regeneration; the bounce loop is the iterative form of
+//                  ray_color (src/main.rs:123-153).
+//   k_intersect    parity hook: world.hit() for a batch of rays.
+#include "vk_device.cuh"
+
+namespace VK_NS {
+
+#define VK_BLOCK 128
+
+// Camera::get_ray (src/main.rs:111-120).  random_in_unit_disk() is always drawn by the reference
+// and multiplied by lens_radius; with lens_radius == 0 the product is exactly 0, so the draw is
+// skipped.  The disk sample is direct (sqrt-radius) instead of the rejection loop: same law.
+VKD void camera_get_ray(const DCamera& cam, const PathRng& rng, uint32_t x, uint32_t y, uint32_t width, uint32_t height,
+                        float3& o, float3& d, float& time) {
+    const uint4 r = rng.block(0u, 0u);
+    const float s = ((float)x + u01(r.x)) / (float)(width - 1);  // src/main.rs:187
+    const float t = ((float)y + u01(r.y)) / (float)(height - 1); // src/main.rs:188
+    float3 offset = f3(0.0f, 0.0f, 0.0f);
+    if (cam.lens_radius != 0.0f) {
+        const uint4 q = rng.block(0u, 1u);
+        const float rad = sqrtf(u01(q.x)) * cam.lens_radius;
+        float sn, cs;
+        __sincosf(2.0f * VK_PI * u01(q.y), &sn, &cs);
+        offset = cam.u * (rad * cs) + cam.v * (rad * sn);
+    }
+    o = cam.origin + offset;
+    d = cam.lower_left_corner + cam.horizontal * s + cam.vertical * t - cam.origin - offset;
+    time = gen_range(r.z, cam.time0, cam.time1);
+}
+
+// One bounce of ray_color's loop body after world.hit() returned `rec` (src/main.rs:131-149).
+// Returns false when the path ends.  `valid` is cleared when the reference's value would be
+// non-finite (the whole sample is then dropped, src/main.rs:191-194).
+VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
+               float3& beta, float3& L, bool& valid) {
+    uint4 m = __ldg(&sc.materials[rec.mat]);
+    uint32_t type = m.x;
+    uint32_t spdf_type = type; // whose scattering_pdf applies
+    float3 emitted = f3(0.0f, 0.0f, 0.0f);
+    if (type == VK_M_SPECDIFFUSE) { // src/material.rs:474-488: emitted() is the trait default (0)
+        const uint4 q = rng.block(depth, 9u);
+        const uint32_t diffuse = m.w & ~VKD_MAT_NEEDS_UV;
+        spdf_type = __ldg(&sc.materials[diffuse]).x;
+        m = __ldg(&sc.materials[u01(q.x) < __uint_as_float(m.z) ? m.y : diffuse]);
+        type = m.x;
+    } else if (type == VK_M_DIFFUSE_LIGHT) { // src/material.rs:218-225; scatter_with_pdf -> None
+        if (rec.front) emitted = tex_value(sc, m.y, rec.u, rec.v, rec.p);
+    }
+    if (type == VK_M_DIFFUSE_LIGHT) { // src/main.rs:147-149
+        L = L + beta * emitted;
+        return false;
+    }
+    const uint4 r = rng.block(depth, 0u);
+    if (type == VK_M_DIELECTRIC) { // src/material.rs:177-206, attenuation (1,1,1)
+        const float ref_idx = __uint_as_float(m.z);
+        const float etai_over_etat = rec.front ? 1.0f / ref_idx : ref_idx;
+        const float3 unit_direction = unit_vector(d);
+        const float cos_theta = fminf(dot3(-unit_direction, rec.normal), 1.0f);
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        float3 nd;
+        if (etai_over_etat * sin_theta > 1.0f) nd = reflect(unit_direction, rec.normal);
+        else if (u01(r.x) < schlick(cos_theta, etai_over_etat)) nd = reflect(unit_direction, rec.normal);
+        else nd = refract(unit_direction, rec.normal, etai_over_etat);
+        o = rec.p;
+        d = nd; // keeps r.time
+        return true;
+    }
+    if (type == VK_M_METAL) { // src/material.rs:134-141: Ray::new -> time 0 (Q6), never absorbed
+        const float fuzz = __uint_as_float(m.z);
+        float3 nd = reflect(unit_vector(d), rec.normal);
+        if (fuzz != 0.0f) nd = nd + random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z)) * fuzz;
+        beta = beta * tex_value(sc, m.y, rec.u, rec.v, rec.p);
+        o = rec.p;
+        d = nd;
+        time = 0.0f;
+        return true;
+    }
+    // Lambertian / Isotropic (src/material.rs:92-108, :448-464): cosine lobe about rec.normal,
+    // mixed 50/50 with light sampling (src/main.rs:139-146).
+    const float3 attenuation = tex_value(sc, m.y, rec.u, rec.v, rec.p);
+    const Onb uvw = onb_from_w(rec.normal);
+    float3 nd;
+    if (u01(r.x) < 0.5f) { // MixturePDF::generate src/util.rs:177-185 -> HittablePDF -> list random
+        const uint32_t li = sc.n_lights > 1 ? min(sc.n_lights - 1u, (uint32_t)(u01(r.w) * (float)sc.n_lights)) : 0u;
+        nd = light_random(sc, __ldg(&sc.lights[li]), rec.p, r.y, r.z, r.w * 0x9E3779B1u);
+    } else {
+        const float3 c = random_cosine_direction(u01(r.y), u01(r.z));
+        nd = uvw.u * c.x + uvw.v * c.y + uvw.w * c.z;
+    }
+    const float3 und = unit_vector(nd);
+    const float cos_w = dot3(und, uvw.w);
+    const float cosine_pdf = cos_w <= 0.0f ? 0.0f : cos_w / VK_PI;                // CosinePDF::value src/util.rs:134-142
+    const float pdf = 0.5f * lights_pdf_value(sc, rec.p, nd) + 0.5f * cosine_pdf; // MixturePDF::value :173-175
+    float spdf = 0.0f;                                                            // Material::scattering_pdf default
+    if (spdf_type == VK_M_LAMBERTIAN || spdf_type == VK_M_ISOTROPIC) {
+        const float cos_n = dot3(rec.normal, und);
+        spdf = cos_n < 0.0f ? 0.0f : cos_n / VK_PI;
+    }
+    const float3 w = f3(attenuation.x * spdf / pdf, attenuation.y * spdf / pdf, attenuation.z * spdf / pdf);
+    if (!finite3(w)) { // reference: NaN/Inf poisons the sample, which main.rs:192 then drops (Q3)
+        valid = false;
+        return false;
+    }
+    beta = beta * w;
+    if (beta.x == 0.0f && beta.y == 0.0f && beta.z == 0.0f) return false; // nothing further can contribute
+    o = rec.p;
+    d = nd; // Ray::new_with_time(c.p, dir, r.time): keeps the camera-sampled time
+    return true;
+}
+
+__global__ void __launch_bounds__(VK_BLOCK) k_megakernel(const DScene sc, const DCamera cam, const RenderArgs a,
+                                                         const RenderBuffers buf) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_tiles = a.tiles_x * a.tiles_y;
+    const uint32_t total = n_tiles * a.n_chunks;
+    const size_t plane = (size_t)a.width * a.height * 3u;
+    unsigned long long n_rays = 0, n_drop = 0;
+
+#pragma unroll 1
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = (uint32_t)atomicAdd(&buf.counters[2], 1ull);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= total) break;
+        const uint32_t chunk = item / n_tiles, tile = item - chunk * n_tiles;
+        const uint32_t px = (tile % a.tiles_x) * 8u + (lane & 7u);
+        const uint32_t py = (tile / a.tiles_x) * 4u + (lane >> 3);
+        if (px < a.width && py < a.height) {
+            const uint32_t pixel = py * a.width + px; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
+            uint32_t s = a.spp_begin + chunk * a.chunk_spp;
+            const uint32_t s_end = min(s + a.chunk_spp, a.spp_begin + a.spp_count);
+            PathRng rng;
+            rng.pixel = pixel;
+            rng.key = make_uint2(a.seed_lo, a.seed_hi);
+            float3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = f3(0.0f, 0.0f, 0.0f);
+            float3 o, d, beta, L;
+            float time = 0.0f;
+            uint32_t depth = 0;
+            bool alive = false, valid = true;
+#pragma unroll 1
+            for (;;) {
+                if (!alive) { // regenerate: this lane starts its next sample while others keep bouncing
+                    if (s >= s_end) break;
+                    rng.sample = s++;
+                    camera_get_ray(cam, rng, px, py, a.width, a.height, o, d, time);
+                    beta = f3(1.0f, 1.0f, 1.0f);
+                    L = f3(0.0f, 0.0f, 0.0f);
+                    depth = 1; // ray_color(ray, .., 1) src/main.rs:190
+                    valid = true;
+                    alive = true;
+                }
+                MediumXi xi;
+                xi.table = nullptr;
+                xi.rng = rng;
+                xi.depth = depth;
+                ++n_rays;
+                const TraceHit h = trace(sc, o, d, time, 0.001f, CUDART_INF_F, xi); // src/main.rs:130
+                if (h.prim == VK_REF_NONE) {
+                    L = L + beta * a.background; // src/main.rs:151
+                    alive = false;
+                } else {
+                    HitRecD rec;
+                    resolve_hit(sc, h, o, d, time, false, rec);
+                    alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
+                    if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
+                }
+                if (!alive) { // sample finished: NaN/Inf filter of src/main.rs:191-194
+                    if (valid && finite3(L)) {
+                        sum = sum + L;
+                        sumsq = sumsq + L * L;
+                    } else {
+                        ++n_drop;
+                    }
+                }
+            }
+            float* ps = buf.partial_sum + (size_t)chunk * plane + (size_t)pixel * 3u;
+            ps[0] = sum.x;
+            ps[1] = sum.y;
+            ps[2] = sum.z;
+            if (buf.partial_sumsq) {
+                float* pq = buf.partial_sumsq + (size_t)chunk * plane + (size_t)pixel * 3u;
+                pq[0] = sumsq.x;
+                pq[1] = sumsq.y;
+                pq[2] = sumsq.z;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_rays += __shfl_xor_sync(0xFFFFFFFFu, n_rays, off);
+        n_drop += __shfl_xor_sync(0xFFFFFFFFu, n_drop, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&buf.counters[0], n_rays);
+        if (n_drop) atomicAdd(&buf.counters[1], n_drop);
+    }
+}
+
+__global__ void __launch_bounds__(VK_BLOCK) k_intersect(const DScene sc, const vk_ray* __restrict__ rays, size_t n,
+                                                        const float* __restrict__ medium_xi, vk_hit* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vk_ray r = rays[i];
+    const float3 o = f3(r.origin[0], r.origin[1], r.origin[2]);
+    const float3 d = f3(r.direction[0], r.direction[1], r.direction[2]);
+    MediumXi xi;
+    xi.table = medium_xi ? medium_xi + i * VK_MEDIUM_XI_SLOTS : nullptr;
+    xi.rng.pixel = (uint32_t)i;
+    xi.rng.sample = (uint32_t)(i >> 32);
+    xi.rng.key = make_uint2(0x243F6A88u, 0x85A308D3u);
+    xi.depth = 1;
+    const TraceHit h = trace(sc, o, d, r.time, r.tmin, r.tmax, xi);
+    vk_hit q;
+    q.prim = h.prim;
+    q.face = 0;
+    q.mat = 0;
+    q.front = 0;
+    q.t = 0.0f;
+    q.p[0] = q.p[1] = q.p[2] = 0.0f;
+    q.normal[0] = q.normal[1] = q.normal[2] = 0.0f;
+    q.u = q.v = 0.0f;
+    q._pad = 0;
+    if (h.prim != VK_REF_NONE) {
+        HitRecD rec;
+        resolve_hit(sc, h, o, d, r.time, true, rec);
+        q.face = h.face;
+        q.mat = rec.mat;
+        q.front = rec.front;
+        q.t = rec.t;
+        q.p[0] = rec.p.x; q.p[1] = rec.p.y; q.p[2] = rec.p.z;
+        q.normal[0] = rec.normal.x; q.normal[1] = rec.normal.y; q.normal[2] = rec.normal.z;
+        q.u = rec.u;
+        q.v = rec.v;
+    }
+    out[i] = q;
+}
+
+__global__ void k_philox_kat(const uint32_t* in6, uint32_t* out4) {
+    const uint4 r = philox4x32_10(make_uint4(in6[0], in6[1], in6[2], in6[3]), make_uint2(in6[4], in6[5]));
+    out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+
+cudaError_t launch_megakernel(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b, int grid,
+                              cudaStream_t st) {
+    k_megakernel<<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
+    return cudaGetLastError();
+}
+cudaError_t launch_intersect(const DScene& sc, const vk_ray* rays, size_t n, const float* medium_xi, vk_hit* out,
+                             cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + VK_BLOCK - 1) / VK_BLOCK);
+    k_intersect<<<grid, VK_BLOCK, 0, st>>>(sc, rays, n, medium_xi, out);
+    return cudaGetLastError();
+}
+cudaError_t megakernel_occupancy(int* blocks_per_sm, int* block_threads) {
+    *block_threads = VK_BLOCK;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel, VK_BLOCK, 0);
+}
+cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st) {
+    k_philox_kat<<<1, 1, 0, st>>>(ctr_key6, out4);
+    return cudaGetLastError();
+}
+
+} // namespace VK_NS
