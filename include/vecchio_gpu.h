@@ -273,14 +273,25 @@ int vk_render(vk_ctx* ctx, const vk_camera* cam, const vk_render_params* params,
 
 /* Same loop, device-resident result: writes per-pixel SUMS (not means) of samples
  * [spp_begin, spp_begin+spp_count) to d_sum (and d_sumsq, nullable), both device
- * pointers of W*H*3 floats, enqueued on the context stream and synchronised before
- * return.  This is the per-GPU spp slice; slices are combined by one NCCL reduce. */
+ * pointers of W*H*3 floats, enqueued on the context stream; synchronised before return
+ * only when stats != NULL.  This is the per-GPU spp slice; slices are combined by one NCCL
+ * reduce. */
 int vk_render_device(vk_ctx* ctx, const vk_camera* cam, const vk_render_params* params,
                      float* d_sum, float* d_sumsq, vk_stats* stats);
 
-/* d_rgb[i] = d_sum[i] / spp on the device (main.rs:196), after the reduce. */
+/* d_rgb[i] = d_sum[i] / spp on the device (main.rs:196), after the reduce.  Asynchronous on the
+ * context stream. */
 int vk_finalize_device(vk_ctx* ctx, const float* d_sum, float* d_rgb, size_t n_floats,
                        uint32_t spp);
+
+/* Enqueue all following work on `stream` (a cudaStream_t of the caller, e.g. the one its NCCL
+ * reduce runs on); NULL restores the context's own stream. */
+int vk_set_stream(vk_ctx* ctx, void* stream);
+
+/* Counters accumulated since the last read (paths, rays, dropped samples, kernel launches);
+ * synchronises the stream.  vk_render_device with stats == NULL is fully asynchronous and leaves
+ * its counts to be collected here. */
+int vk_flush_stats(vk_ctx* ctx, vk_stats* stats);
 
 /* Parity hook: closest hit of `world.hit(&r, tmin, tmax)` (src/accel.rs:58-83) for
  * a batch of rays.  medium_xi (nullable): n * VK_MEDIUM_XI_SLOTS uniform variates

@@ -565,7 +565,10 @@ struct Rect : Hittable { // :199-292
     }
     float pdf_value(Vec3 origin, Vec3 v) const override { // :271-282
         tl_cnt.n_light_pdf++;
-        if (auto rec = hit(Ray(origin, v), 0.001f, INF)) {
+        const Counters keep = tl_cnt;
+        auto rec = hit(Ray(origin, v), 0.001f, INF);
+        tl_cnt = keep; // this rect test is counted in n_light_pdf, not in n_rect_*
+        if (rec) {
             float area = (c1 - c0) * (d1 - d0);
             float distance_squared = rec->t * rec->t * v.length2();
             float cosine = std::fabs(v.dot(rec->normal)) / v.length();

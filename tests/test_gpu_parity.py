@@ -1,0 +1,265 @@
+"""GPU parity tests (run on a B200 with `pytest -m gpu`).  Everything goes through the C ABI
+(libvecchio_gpu.so); the oracle is only the checker.
+
+Bars (BASELINE.json north_star):
+  * hit parity: closest-hit primitive ids bit-exact (ties excepted), t and normal within 1e-5
+    relative, on identical ray batches (camera rays + secondary rays harvested from oracle paths);
+  * image parity: per pixel and channel within 3 sigma of the Monte-Carlo standard error.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, get_scene
+
+pytestmark = pytest.mark.gpu
+INF = np.float32(np.inf)
+
+# (scene, param, image width used for ray generation, rays per batch)
+HIT_SCENES = [("cornell_box", 0, 200, 200_000), ("cornell_smoke", 0, 200, 200_000), ("random_spheres_demo", 0, 200, 200_000),
+              ("final_scene", 0, 200, 200_000), ("bowser_demo", 0, 200, 100_000), ("perlin_demo", 0, 160, 50_000),
+              ("balls_demo", 0, 160, 50_000), ("stress_spheres", 64, 200, 100_000)]
+
+
+def camera_rays(cam, n, rng):
+    """Camera::get_ray (src/main.rs:111-120) for aperture-0 cameras, vectorised in fp32."""
+    s = rng.random(n, dtype=np.float32)
+    t = rng.random(n, dtype=np.float32)
+    f = lambda v: np.array(list(v), dtype=np.float32)  # noqa: E731
+    rays = np.zeros(n, dtype=[("origin", "<f4", 3), ("direction", "<f4", 3), ("time", "<f4"), ("tmin", "<f4"), ("tmax", "<f4")])
+    rays["origin"] = f(cam.origin)
+    rays["direction"] = (f(cam.lower_left_corner)[None] + s[:, None] * f(cam.horizontal)[None] + t[:, None] * f(cam.vertical)[None]
+                         - f(cam.origin)[None]).astype(np.float32)
+    rays["time"] = rng.random(n, dtype=np.float32)
+    rays["tmin"], rays["tmax"] = 0.001, INF
+    return rays
+
+
+def ray_batch(vb, o, scene, cam, width, n, seed):
+    rng = np.random.default_rng(seed)
+    a = camera_rays(cam, n // 2, rng)
+    b = o.harvest_rays(cam, width, scene.height_for(width), 50, seed, n - len(a))
+    return np.concatenate([a, b.astype(a.dtype)])
+
+
+def compare_hits(vb, ref, got, t_rtol, n_tol, uv_tol, label):
+    hit_r, hit_g = ref["prim"] != 0, got["prim"] != 0
+    both = hit_r & hit_g
+    same_prim = (ref["prim"] == got["prim"]) & (ref["face"] == got["face"])
+    t_close = np.abs(ref["t"] - got["t"]) <= t_rtol * np.abs(ref["t"])
+    # a mismatch is excused only as a tie: both hit, at the same distance
+    tie = both & ~same_prim & t_close
+    # hit/miss flips are excused only right at the tmin guard (t ~ 0.001, self-intersection limit)
+    unexcused = (hit_r != hit_g) | (both & ~same_prim & ~t_close)
+    ok = both & same_prim
+    stats = {"rays": len(ref), "hits": int(hit_r.sum()), "ties": int(tie.sum()), "unexcused": int(unexcused.sum())}
+    assert stats["unexcused"] == 0, (label, stats, np.flatnonzero(unexcused)[:5])
+    assert stats["ties"] <= 1e-4 * len(ref) + 2, (label, stats)
+    assert np.all(t_close[ok]), (label, "t", np.abs(ref["t"] - got["t"])[ok].max())
+    assert np.abs(ref["normal"][ok] - got["normal"][ok]).max() <= n_tol, (label, "normal")
+    assert np.array_equal(ref["front"][ok], got["front"][ok]), (label, "front")
+    assert np.array_equal(ref["mat"][ok], got["mat"][ok]), (label, "mat")
+    p_scale = np.maximum(1.0, np.abs(ref["p"][ok]).max(axis=1))
+    assert (np.abs(ref["p"][ok] - got["p"][ok]).max(axis=1) / p_scale).max() <= 10 * t_rtol, (label, "p")
+    # (u, v): skip the atan2 seam of Sphere::spherical (u jumps 0 <-> 1)
+    du = np.abs(ref["u"][ok] - got["u"][ok])
+    du = np.minimum(du, 1.0 - du)
+    assert du.max() <= uv_tol and np.abs(ref["v"][ok] - got["v"][ok]).max() <= uv_tol, (label, "uv", du.max())
+    return stats
+
+
+def test_philox_known_answers(vb, ctx):
+    """Philox4x32-10 against the Random123 known-answer vectors."""
+    L = vb.gpu_lib()
+    L.vk_selftest_philox.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    kat = [([0, 0, 0, 0, 0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 6, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for inp, want in kat:
+        out = (C.c_uint32 * 4)()
+        assert L.vk_selftest_philox(ctx._h, (C.c_uint32 * 6)(*inp), out) == 0
+        assert list(out) == want
+
+
+@pytest.mark.parametrize("name,param,width,n", HIT_SCENES, ids=[s[0] for s in HIT_SCENES])
+def test_hit_parity_strict(vb, po, ctx, name, param, width, n):
+    """Strict math (the reference's op sequence): ids exact, t within 1e-5 (in practice bit-equal)."""
+    scene, cam = get_scene(vb, name, param=param)
+    o = po.OracleScene(scene)
+    ctx.upload(scene)
+    rays = ray_batch(vb, o, scene, cam, width, n, seed=11)
+    xi = np.random.default_rng(5).random((len(rays), vb.VK_MEDIUM_XI_SLOTS), dtype=np.float32)
+    ref = o.intersect(rays, xi)
+    got = ctx.intersect(rays, xi, flags=vb.VK_FLAG_STRICT_MATH)
+    st = compare_hits(vb, ref, got, 1e-5, 1e-5, 1e-5, name)
+    assert st["hits"] > 0.3 * st["rays"]
+    ok = (ref["prim"] == got["prim"]) & (ref["prim"] != 0)
+    not_medium = ok & ((ref["prim"] >> 28) != vb.VK_T_MEDIUM)
+    # distances of deterministic primitives are bit-identical: same IEEE ops in the same order
+    assert np.array_equal(ref["t"][not_medium], got["t"][not_medium]), name
+
+
+@pytest.mark.parametrize("name,param,width,n", HIT_SCENES[:4], ids=[s[0] for s in HIT_SCENES[:4]])
+def test_hit_parity_fast_math(vb, po, ctx, name, param, width, n):
+    """The render build (FMA contraction, reciprocal slab test): same ids except ties, t within 1e-5
+    away from grazing hits; reports how often the two builds disagree."""
+    scene, cam = get_scene(vb, name, param=param)
+    o = po.OracleScene(scene)
+    ctx.upload(scene)
+    rays = ray_batch(vb, o, scene, cam, width, n, seed=12)
+    xi = np.random.default_rng(6).random((len(rays), vb.VK_MEDIUM_XI_SLOTS), dtype=np.float32)
+    ref = o.intersect(rays, xi)
+    got = ctx.intersect(rays, xi, flags=0)
+    hit_r, hit_g = ref["prim"] != 0, got["prim"] != 0
+    same = (ref["prim"] == got["prim"]) & (ref["face"] == got["face"])
+    assert (hit_r != hit_g).mean() <= 2e-5 and (~same).mean() <= 5e-5, (name, (~same).sum())
+    ok = same & hit_r
+    rel = np.abs(ref["t"][ok] - got["t"][ok]) / np.abs(ref["t"][ok])
+    assert np.quantile(rel, 0.999) <= 1e-5 and rel.max() <= 1e-3, (name, rel.max())
+    assert np.quantile(np.abs(ref["normal"][ok] - got["normal"][ok]).max(axis=1), 0.999) <= 1e-4
+    assert (ref["front"][ok] != got["front"][ok]).mean() <= 1e-5
+
+
+def test_intersect_edge_cases(vb, ctx):
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    assert len(ctx.intersect(np.zeros(0, dtype=vb.RAY_DTYPE))) == 0  # empty batch
+    rays = np.zeros(4, dtype=vb.RAY_DTYPE)
+    rays["origin"] = [278, 278, -800]
+    rays["direction"] = [[0, 0.2, 1], [0, 0, -1], [0, 0, 0], [0, 1e-30, 1e30]]  # hit, miss, zero dir, huge dir
+    rays["tmin"], rays["tmax"] = 0.001, INF
+    h = ctx.intersect(rays, flags=vb.VK_FLAG_STRICT_MATH)
+    assert vb.ref_type(h["prim"][0]) == vb.VK_T_RECT and np.isclose(h["t"][0], 1355.0) and h["prim"][1] == 0
+    rays["tmax"] = 100.0  # tmax shorter than the first surface: miss
+    assert (ctx.intersect(rays[:1])["prim"] == 0).all()
+
+
+def zscores(rgb_a, sq_a, n_a, rgb_b, sq_b, n_b):
+    """z of the difference of two per-pixel means given their sum-of-squares buffers."""
+    var_a = np.maximum(sq_a / n_a - rgb_a.astype(np.float64) ** 2, 0.0) * n_a / (n_a - 1)
+    var_b = np.maximum(sq_b / n_b - rgb_b.astype(np.float64) ** 2, 0.0) * n_b / (n_b - 1)
+    se = np.sqrt(var_a / n_a + var_b / n_b)
+    diff = rgb_a.astype(np.float64) - rgb_b.astype(np.float64)
+    z = np.zeros_like(diff)
+    nz = se > 0
+    z[nz] = diff[nz] / se[nz]
+    z[~nz & (np.abs(diff) > 1e-6)] = np.inf
+    return z, nz
+
+
+RENDER_SCENES = [("cornell_box", 0, 96, 256, 2048, 100), ("cornell_smoke", 0, 96, 256, 2048, 100),
+                 ("random_spheres_demo", 0, 128, 128, 1024, 50), ("final_scene", 0, 96, 128, 1024, 100),
+                 ("bowser_demo", 0, 96, 64, 512, 50), ("perlin_demo", 0, 96, 64, 512, 50)]
+
+
+@pytest.mark.parametrize("name,param,W,spp_o,spp_g,depth", RENDER_SCENES, ids=[s[0] for s in RENDER_SCENES])
+def test_image_parity_3_sigma(vb, po, ctx, name, param, W, spp_o, spp_g, depth):
+    scene, cam = get_scene(vb, name, param=param)
+    H = scene.height_for(W)
+    o = po.OracleScene(scene)
+    ctx.upload(scene)
+    ro, qo, so = o.render(cam, vb.render_params(W, H, spp_o, depth, seed=21), want_sumsq=True)
+    rg, qg, sg = ctx.render(cam, vb.render_params(W, H, spp_g, depth, seed=22), want_sumsq=True)
+    assert np.isfinite(rg).all()
+    assert sg.paths == W * H * spp_g
+    # segments per path must agree (a traversal or termination bug shows up here first)
+    assert abs(sg.rays / sg.paths - so.rays / so.paths) <= 0.02 * so.rays / so.paths, (sg.rays / sg.paths, so.rays / so.paths)
+    z, nz = zscores(rg, qg, spp_g, ro, qo, spp_o)
+    frac = (np.abs(z[nz]) <= 3.0).mean()
+    assert frac >= 0.985, (name, frac)  # Gaussian expectation 0.9973; heavy-tailed pixels at 128-256 spp cost a little
+    assert np.isfinite(z[~nz]).all(), "a pixel is exactly constant in both renders but differs"
+    # no spatially coherent bias: mean z over 16x16 tiles
+    zt = np.where(nz, np.clip(z, -6, 6), 0.0)
+    th, tw = H // 16, W // 16
+    tiles = zt[: th * 16, : tw * 16].reshape(th, 16, tw, 16, 3).mean(axis=(1, 3))
+    assert np.abs(tiles).max() <= 0.75, (name, np.abs(tiles).max())
+    assert abs(rg.mean() - ro.mean()) <= 0.01 * ro.mean(), (name, rg.mean(), ro.mean())
+
+
+def test_render_is_deterministic_per_seed(vb, ctx):
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    p = vb.render_params(160, 160, 64, 100, seed=5)
+    a, _, sa = ctx.render(cam, p)
+    b, _, sb = ctx.render(cam, p)
+    assert np.array_equal(a, b) and sa.rays == sb.rays
+    c, _, _ = ctx.render(cam, vb.render_params(160, 160, 64, 100, seed=6))
+    assert not np.array_equal(a, c)
+
+
+def test_spp_slices_combine_like_one_render(vb, ctx):
+    """The multi-GPU decomposition on one GPU: per-slice SUM buffers added == the whole render."""
+    torch = pytest.importorskip("torch")
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    W, spp = 128, 96
+    n = W * W * 3
+    whole, _, _ = ctx.render(cam, vb.render_params(W, W, spp, 100, seed=8))
+    acc = torch.zeros(n, dtype=torch.float32, device="cuda:0")
+    part = torch.empty_like(acc)
+    rays = 0
+    for k in range(3):
+        st = ctx.render_device(cam, vb.render_params(W, W, spp, 100, seed=8, spp_begin=32 * k, spp_count=32), part.data_ptr())
+        acc += part
+        rays += st.rays
+    out = torch.empty_like(acc)
+    torch.cuda.synchronize()  # torch's stream (acc += part) and the context's stream are different streams
+    ctx.finalize_device(acc.data_ptr(), out.data_ptr(), n, spp)
+    torch.cuda.synchronize()
+    assert np.allclose(out.cpu().numpy().reshape(W, W, 3), whole, rtol=1e-5, atol=1e-7)
+
+
+def test_render_edge_cases(vb, ctx):
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    # depth 1: only emitters seen directly contribute (one segment, src/main.rs:126)
+    rgb, _, st = ctx.render(cam, vb.render_params(64, 64, 16, 1, seed=1))
+    assert st.rays == st.paths and rgb.max() == 15.0 and rgb.min() == 0.0
+    # ragged image (not a multiple of the 8x4 warp tile) and spp not a multiple of the chunk
+    rgb, _, st = ctx.render(cam, vb.render_params(61, 37, 13, 100, seed=1))
+    assert rgb.shape == (37, 61, 3) and np.isfinite(rgb).all() and st.paths == 61 * 37 * 13
+    for bad in (vb.render_params(1, 64, 4), vb.render_params(64, 64, 0), vb.render_params(64, 64, 4, spp_begin=4),
+                vb.render_params(64, 64, 4, spp_begin=2, spp_count=3)):
+        with pytest.raises(vb.VecchioError):
+            ctx.render(cam, bad)
+    fresh = vb.Context(0)
+    with pytest.raises(vb.VecchioError) as e:
+        fresh.render(cam, vb.render_params(8, 8, 1))
+    assert e.value.code == vb.VK_ERR_NO_SCENE
+    fresh.close()
+
+
+def test_golden_cornell_render_matches_published_sample(vb, ctx):
+    """GPU Cornell box at the reference's own settings (900^2, 1000 spp, depth 100) against the
+    region means of sample/therestofyourlife.png, within +-3 (8-bit) after to_color."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "cornell_sample_regions.json")))
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    rgb, _, st = ctx.render(cam, vb.render_params(900, 900, 1000, 100, seed=1))
+    assert st.dropped_samples <= 1e-5 * st.paths
+    img = vb.to_color(rgb)[::-1].astype(np.float64)
+    for name, r in g["regions"].items():
+        x0, x1, y0, y1 = r["box_xyxy"]
+        diff = img[y0:y1, x0:x1].mean(axis=(0, 1)) - np.array(r["mean_rgb8"])
+        assert np.all(np.abs(diff) <= 3.0), (name, diff)
+    nz = np.argwhere(img.sum(axis=2) > 0)
+    assert (nz[:, 0].min(), nz[:, 0].max(), nz[:, 1].min(), nz[:, 1].max()) == (22, 879, 21, 878)
+
+
+def test_full_size_cornell_properties(vb, ctx):
+    """BASELINE.json config 2 at full size (600x600, 1000 spp): size-independent properties."""
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    rgb, _, st = ctx.render(cam, vb.render_params(600, 600, 1000, 100, seed=1))
+    assert st.paths == 360_000_000 and np.isfinite(rgb).all() and rgb.min() >= 0.0
+    assert 2.9 <= st.rays / st.paths <= 3.3  # oracle: 3.08 segments per path
+    assert st.dropped_samples <= 1e-5 * st.paths
+    # mirror symmetry of radiance is broken only by the wall colours: red wall redder, green greener
+    left, right = rgb[250:350, 20:60], rgb[250:350, 540:580]  # image-left is +x (green wall)
+    assert left[..., 1].mean() > 2 * left[..., 0].mean() and right[..., 0].mean() > 4 * right[..., 1].mean()
+    # linearity in spp slices: the first half's mean equals the whole within noise
+    half, _, _ = ctx.render(cam, vb.render_params(600, 600, 500, 100, seed=1))
+    assert abs(half.mean() - rgb.mean()) <= 0.005 * rgb.mean()

@@ -79,18 +79,21 @@ def gpu_lib():
         L.vk_render_device.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, vp,
                                        C.POINTER(_abi.vk_stats)]
         L.vk_finalize_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_uint32]
+        L.vk_set_stream.argtypes = [vp, vp]
+        L.vk_flush_stats.argtypes = [vp, C.POINTER(_abi.vk_stats)]
         L.vk_intersect.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, vp]
         L.vk_measure_peaks.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.vk_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
         for f in ("vk_create", "vk_scene_upload", "vk_render", "vk_render_device", "vk_finalize_device",
-                  "vk_intersect", "vk_measure_peaks", "vk_device_info"):
+                  "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks", "vk_device_info"):
             getattr(L, f).restype = C.c_int
         _gpu = L
     return _gpu
 
 
 GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_upload", "vk_render", "vk_render_device",
-               "vk_finalize_device", "vk_intersect", "vk_measure_peaks", "vk_device_info"]
+               "vk_finalize_device", "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks",
+               "vk_device_info"]
 HOST_SYMBOLS = ["vkh_scene_build", "vkh_scene_free", "vkh_scene_desc", "vkh_scene_aspect_ratio",
                 "vkh_scene_next_camera", "vkh_camera_new", "vkh_decode_png", "vkh_last_error"]
 
@@ -209,10 +212,20 @@ class Context:
         shape = (params.height, params.width, 3)
         return rgb.reshape(shape), (sq.reshape(shape) if want_sumsq else None), st
 
-    def render_device(self, cam, params, d_sum_ptr, d_sumsq_ptr=None):
-        st = _abi.vk_stats()
+    def render_device(self, cam, params, d_sum_ptr, d_sumsq_ptr=None, want_stats=True):
+        """``vk_render_device``: per-pixel SUMS of an spp slice into device memory.  With
+        ``want_stats=False`` the call only enqueues work (collect counts with flush_stats())."""
+        st = _abi.vk_stats() if want_stats else None
         self._check(self._L.vk_render_device(self._h, C.byref(cam), C.byref(params), d_sum_ptr, d_sumsq_ptr,
-                                             C.byref(st)))
+                                             C.byref(st) if want_stats else None))
+        return st
+
+    def set_stream(self, stream_ptr):
+        self._check(self._L.vk_set_stream(self._h, stream_ptr))
+
+    def flush_stats(self):
+        st = _abi.vk_stats()
+        self._check(self._L.vk_flush_stats(self._h, C.byref(st)))
         return st
 
     def finalize_device(self, d_sum_ptr, d_rgb_ptr, n_floats, spp):

@@ -14,7 +14,10 @@ struct vk_ctx {
     int sm_count = 0;
     int clock_khz = 0;
     char name[128] = {0};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // stream all work is enqueued on
+    cudaStream_t own_stream = nullptr; // the one created by vk_create
+    uint64_t launches = 0;             // kernels launched since the last stats read
+    uint64_t paths = 0;                // samples started since the last stats read
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::string err;
     std::vector<void*> scene_allocs;
@@ -331,11 +334,13 @@ int vk_create(int device, vk_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->clock_khz = prop.clockRate;
     std::snprintf(c->name, sizeof(c->name), "%.100s", prop.name);
-    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CUC(cudaEventCreate(&c->ev0));
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaEventCreate(&c->ev2));
     CUC(cudaMalloc((void**)&c->counters, 4 * sizeof(unsigned long long)));
+    CUC(cudaMemset(c->counters, 0, 4 * sizeof(unsigned long long)));
 #undef CUC
     *out = c;
     return VK_OK;
@@ -352,7 +357,7 @@ void vk_destroy(vk_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -435,6 +440,8 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     return VK_OK;
 }
 
+extern "C" int vk_flush_stats(vk_ctx* c, vk_stats* stats);
+
 // shared body of vk_render / vk_render_device
 static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* d_sum, float* d_sumsq, vk_stats* stats) {
     if (!c) return VK_ERR_INVALID;
@@ -489,7 +496,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         b.partial_sum = c->partial;
         b.partial_sumsq = d_sumsq ? c->partial + plane * a.n_chunks : nullptr;
     }
-    CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // work-queue head only
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
     CU(c, strict ? vkstrict::launch_megakernel(c->scene, dc, a, b, grid, c->stream)
@@ -506,18 +513,14 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         CU(c, cudaGetLastError());
     }
     CU(c, cudaEventRecord(c->ev1, c->stream));
-    unsigned long long h[4] = {0, 0, 0, 0};
-    CU(c, cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    if (stats) {
-        std::memset(stats, 0, sizeof(*stats));
-        stats->paths = (uint64_t)P->width * P->height * count;
-        stats->rays = h[0];
-        stats->dropped_samples = h[1];
+    c->launches += launches;
+    c->paths += (uint64_t)P->width * P->height * count;
+    if (stats) { // reading the counters synchronises; with stats == NULL the call is fully asynchronous
+        int rc = vk_flush_stats(c, stats);
+        if (rc != VK_OK) return rc;
         CU(c, cudaEventElapsedTime(&stats->ms_kernels, c->ev0, c->ev1));
         stats->ms_total = stats->ms_kernels;
         stats->variant = VK_VARIANT_MEGAKERNEL;
-        stats->launches = launches;
     }
     return VK_OK;
 }
@@ -530,8 +533,34 @@ int vk_finalize_device(vk_ctx* c, const float* d_sum, float* d_rgb, size_t n, ui
     if (!c || !d_sum || !d_rgb || spp == 0) return fail(c, VK_ERR_INVALID, "vk_finalize_device: bad argument");
     CU(c, cudaSetDevice(c->device));
     if (n) k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_sum, d_rgb, n, (float)spp);
+    c->launches += n ? 1 : 0;
     CU(c, cudaGetLastError());
+    return VK_OK;
+}
+
+int vk_set_stream(vk_ctx* c, void* stream) {
+    if (!c) return VK_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return VK_OK;
+}
+
+int vk_flush_stats(vk_ctx* c, vk_stats* stats) {
+    if (!c || !stats) return VK_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    unsigned long long h[2] = {0, 0};
+    CU(c, cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemsetAsync(c->counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::memset(stats, 0, sizeof(*stats));
+    stats->paths = c->paths;
+    stats->rays = h[0];
+    stats->dropped_samples = h[1];
+    stats->launches = (uint32_t)c->launches;
+    stats->variant = VK_VARIANT_MEGAKERNEL;
+    c->paths = 0;
+    c->launches = 0;
     return VK_OK;
 }
 
@@ -563,6 +592,7 @@ int vk_render(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float*
     std::memcpy(out_rgb, c->pinned, plane * sizeof(float));
     if (out_sumsq) std::memcpy(out_sumsq, c->pinned + plane, plane * sizeof(float));
     st.launches += 1;
+    c->launches = 0;
     CU(c, cudaEventElapsedTime(&st.ms_total, c->ev2, c->ev1));
     if (stats) *stats = st;
     return VK_OK;
