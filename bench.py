@@ -150,8 +150,11 @@ def run_ours(args, cfg):
     ctx = vb.Context(local_rank)
     ctx.upload(scene)
     info = ctx.device_info()
-    stream = torch.cuda.current_stream(dev)
-    ctx.set_stream(stream.cuda_stream)  # kernels, reduce and events all on torch's current stream
+    # One explicit (non-default) stream for everything that is timed: our kernels, the NCCL
+    # reduce, the L2 flush and the CUDA events.
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
 
     # spp sharding: rank k renders global samples [k*spp/N, (k+1)*spp/N)
     s0, s1 = rank * spp // world, (rank + 1) * spp // world
@@ -192,6 +195,7 @@ def run_ours(args, cfg):
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps -------------------------
     for i in range(args.warmup):
+        flush.zero_()
         step_device(1000 + i)
     ctx.flush_stats()
     sampler = ClockSampler(local_rank)

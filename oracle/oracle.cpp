@@ -74,7 +74,7 @@ static inline Rng& thread_rng() { return *tl_rng; }
 struct Counters {
     uint64_t rays = 0, n_node = 0, n_sph_rej = 0, n_sph_acc = 0, n_msph = 0, n_rect_rej = 0, n_rect_acc = 0, n_box = 0,
              n_translate = 0, n_rotate = 0, n_medium = 0, n_texel = 0, n_perlin = 0, n_diffuse = 0, n_dielectric = 0,
-             n_metal = 0, n_emit_or_miss = 0, n_light_pdf = 0;
+             n_metal = 0, n_emit_or_miss = 0, n_light_pdf = 0, rays_live = 0;
 };
 static thread_local Counters tl_cnt;
 
@@ -788,10 +788,13 @@ struct RayTap { // optional recorder of every traced segment (orc_harvest_rays)
 };
 static thread_local RayTap* tl_tap = nullptr;
 
+// `live` is instrumentation only: false once the path's accumulated weight is exactly zero or
+// non-finite, i.e. for segments the reference still traces although they cannot change the pixel.
 static Vec3 ray_color(const Ray& r, const Arc<Hittable>& world, const Arc<Hittable>& lights, uint32_t depth,
-                      uint32_t max_depth, Vec3 background) { // :123-153
+                      uint32_t max_depth, Vec3 background, bool live = true) { // :123-153
     if (depth > max_depth) return Vec3::new_const(0.0f);
     tl_cnt.rays++;
+    if (live) tl_cnt.rays_live++;
     if (tl_tap && tl_tap->n < tl_tap->cap) {
         vk_ray& o = tl_tap->out[tl_tap->n++];
         o.origin[0] = r.origin.x; o.origin[1] = r.origin.y; o.origin[2] = r.origin.z;
@@ -802,13 +805,16 @@ static Vec3 ray_color(const Ray& r, const Arc<Hittable>& world, const Arc<Hittab
         Vec3 emitted = c->material->emitted(*c, c->u, c->v, c->p);
         if (auto srec = c->material->scatter_with_pdf(r, *c)) {
             if (srec->specular_ray) // Specular!  (emitted is dropped, Q2)
-                return srec->attenuation * ray_color(*srec->specular_ray, world, lights, depth + 1, max_depth, background);
+                return srec->attenuation * ray_color(*srec->specular_ray, world, lights, depth + 1, max_depth, background,
+                                                     live && !(srec->attenuation.x == 0.0f && srec->attenuation.y == 0.0f && srec->attenuation.z == 0.0f));
             auto p_important = std::make_shared<HittablePDF>(lights, c->p);
             MixturePDF p(p_important, 0.5f, srec->pdf, 0.5f);
             Ray scattered(c->p, p.generate(), r.time);
             float pdf = p.value(scattered.direction);
+            Vec3 w = srec->attenuation * c->material->scattering_pdf(r, *c, scattered) / pdf; // instrumentation
+            bool child_live = live && w.is_finite() && !(w.x == 0.0f && w.y == 0.0f && w.z == 0.0f);
             return emitted + srec->attenuation * c->material->scattering_pdf(r, *c, scattered) *
-                                 ray_color(scattered, world, lights, depth + 1, max_depth, background) / pdf;
+                                 ray_color(scattered, world, lights, depth + 1, max_depth, background, child_live) / pdf;
         }
         tl_cnt.n_emit_or_miss++;
         return emitted;
@@ -1142,6 +1148,7 @@ int orc_render(const orc_scene* s, const vk_camera* cam_, const vk_render_params
         stats->n_medium = total.n_medium; stats->n_texel = total.n_texel; stats->n_perlin = total.n_perlin;
         stats->n_diffuse = total.n_diffuse; stats->n_dielectric = total.n_dielectric; stats->n_metal = total.n_metal;
         stats->n_emit_or_miss = total.n_emit_or_miss; stats->n_light_pdf = total.n_light_pdf;
+        stats->rays_live = total.rays_live;
         stats->seconds = std::chrono::duration<double>(t1 - t0).count();
         stats->threads = n_threads;
     }

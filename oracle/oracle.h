@@ -29,6 +29,7 @@ typedef struct orc_stats {
     /* traversal / shading event counts on the reference's own traversal order */
     uint64_t n_node, n_sph_rej, n_sph_acc, n_msph, n_rect_rej, n_rect_acc, n_box, n_translate, n_rotate,
         n_medium, n_texel, n_perlin, n_diffuse, n_dielectric, n_metal, n_emit_or_miss, n_light_pdf;
+    uint64_t rays_live; /* rays traced while the path weight was still non-zero and finite */
     double seconds;
     int threads;
 } orc_stats;

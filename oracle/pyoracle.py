@@ -18,7 +18,7 @@ class orc_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("paths", "rays", "dropped_samples", "n_node", "n_sph_rej", "n_sph_acc", "n_msph", "n_rect_rej",
                  "n_rect_acc", "n_box", "n_translate", "n_rotate", "n_medium", "n_texel", "n_perlin", "n_diffuse",
-                 "n_dielectric", "n_metal", "n_emit_or_miss", "n_light_pdf")] + [("seconds", C.c_double), ("threads", C.c_int)]
+                 "n_dielectric", "n_metal", "n_emit_or_miss", "n_light_pdf", "rays_live")] + [("seconds", C.c_double), ("threads", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
