@@ -5,7 +5,8 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       := /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+TUNE      ?=
+NVFLAGS   := $(TUNE) $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
 CXXFLAGS  := -std=c++17 -O3 -fPIC -ffp-contract=off -Wall -Wextra
 LIBDIR    := vecchio_b200/lib
 CSRC      := vecchio_b200/csrc
@@ -29,7 +30,7 @@ KDEPS := $(CSRC)/vk_device.cuh $(CSRC)/vk_internal.h include/vecchio_gpu.h
 # the device code is compiled twice: contracted FMA ("fast") and -fmad=false ("strict", the
 # reference's op sequence, used for hit parity)
 $(CSRC)/vk_kernels_fast.o: $(CSRC)/vk_kernels.cu $(KDEPS)
-	$(NVCC) $(NVFLAGS) -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_fast.log || (cat $(CSRC)/ptxas_fast.log; false)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_fast.log || (cat $(CSRC)/ptxas_fast.log; false)
 $(CSRC)/vk_kernels_strict.o: $(CSRC)/vk_kernels.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_strict.log || (cat $(CSRC)/ptxas_strict.log; false)
 $(CSRC)/vk_api.o: $(CSRC)/vk_api.cu $(KDEPS)

@@ -201,8 +201,10 @@ typedef struct vk_camera {
 
 enum { VK_VARIANT_AUTO = 0, VK_VARIANT_MEGAKERNEL = 1, VK_VARIANT_WAVEFRONT = 2 };
 enum {
-    VK_FLAG_STRICT_MATH = 1u /* no FMA contraction, IEEE div/sqrt, division slab test:
-                                the op sequence of the reference, for hit parity     */
+    VK_FLAG_STRICT_MATH = 1u, /* no FMA contraction, IEEE div/sqrt, division slab test:
+                                 the op sequence of the reference, for hit parity    */
+    VK_FLAG_FORCE_BVH = 2u    /* traverse the BVH even when the scene is small enough for
+                                 the flat (divergence-free) traversal program         */
 };
 
 /* The constants of src/main.rs:28-29,171-172 and the choices the reference leaves
@@ -227,6 +229,8 @@ typedef struct vk_stats {
     float ms_total;           /* CUDA-event time incl. D2H of the image (vk_render)      */
     uint32_t variant;         /* variant that ran                                        */
     uint32_t launches;        /* kernels launched by this call                           */
+    uint64_t node_visits;     /* BVH nodes fetched (wide nodes: one fetch tests two boxes) */
+    uint64_t prim_tests;      /* primitive / instance / medium tests                      */
 } vk_stats;
 
 typedef struct vk_ray {

@@ -62,7 +62,7 @@ def gpu_lib():
     """libvecchio_gpu.so (CUDA kernels + C ABI); built by `make gpu`.  Raises if absent."""
     global _gpu
     if _gpu is None:
-        path = os.path.join(_LIBDIR, "libvecchio_gpu.so")
+        path = os.environ.get("VECCHIO_GPU_LIB") or os.path.join(_LIBDIR, "libvecchio_gpu.so")  # env: tuning sweeps
         if not os.path.exists(path):
             raise ImportError(f"{path} is missing: run `make gpu` (or __graft_entry__.build()). "
                               "There is no CPU fallback for the render path.")

@@ -8,6 +8,7 @@ VK_ERR_INVALID, VK_ERR_NO_DEVICE, VK_ERR_CUDA, VK_ERR_UNSUPPORTED, VK_ERR_NO_SCE
 VK_T_NONE, VK_T_NODE, VK_T_SPHERE, VK_T_MSPHERE, VK_T_RECT, VK_T_BOX, VK_T_XFORM, VK_T_MEDIUM = range(8)
 VK_VARIANT_AUTO, VK_VARIANT_MEGAKERNEL, VK_VARIANT_WAVEFRONT = 0, 1, 2
 VK_FLAG_STRICT_MATH = 1
+VK_FLAG_FORCE_BVH = 2
 VK_MEDIUM_XI_SLOTS = 8
 VK_RECT_FLIP = 0x100
 
@@ -96,7 +97,8 @@ class vk_render_params(C.Structure):
 
 class vk_stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("dropped_samples", C.c_uint64),
-                ("ms_kernels", C.c_float), ("ms_total", C.c_float), ("variant", C.c_uint32), ("launches", C.c_uint32)]
+                ("ms_kernels", C.c_float), ("ms_total", C.c_float), ("variant", C.c_uint32), ("launches", C.c_uint32),
+                ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64)]
 
 
 class vk_ray(C.Structure):

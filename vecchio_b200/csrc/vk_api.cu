@@ -22,6 +22,7 @@ struct vk_ctx {
     std::string err;
     std::vector<void*> scene_allocs;
     DScene scene{};
+    FlatProgram flat{}; // flat.n == 0: scene too large, BVH traversal
     bool has_scene = false;
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
     float* partial = nullptr;               // chunk partial sums (sum | sumsq)
@@ -93,6 +94,11 @@ __global__ void k_l2_read(const float4* __restrict__ buf, size_t n_vec, int reps
 // path does not implement is refused with VK_ERR_UNSUPPORTED instead of being rendered wrongly.
 // ------------------------------------------------------------------------------------------------
 namespace {
+inline float __uint_as_float_host(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
 struct Validator {
     const vk_scene_desc* d;
     std::string err;
@@ -257,6 +263,106 @@ struct Validator {
     }
 };
 
+// Unroll the reference's traversal (depth first, left then right) into a flat program; false if the
+// scene has more than VKD_FLAT_MAX entries.  See FlatProgram.
+struct FlatBuilder {
+    const vk_scene_desc* d;
+    FlatProgram* P;
+    bool push(const FlatEntry& e) {
+        if (P->n >= VKD_FLAT_MAX) return false;
+        P->e[P->n++] = e;
+        return true;
+    }
+    bool rect(float c0, float c1, float d0, float d1, float k, uint32_t axes, vk_ref ref, uint32_t aux) {
+        FlatEntry e{};
+        e.a = make_float4(c0, c1, d0, d1);
+        e.k = k;
+        const uint32_t a2 = (axes >> 4) & 3u;
+        e.kind = a2 == 2 ? VKF_RECT_XY : (a2 == 1 ? VKF_RECT_XZ : VKF_RECT_YZ);
+        // the canonical axis order of Rect::XYRect/XZRect/YZRect (src/hittable.rs:214-226) is assumed
+        const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u;
+        const bool canonical = (a2 == 2 && a0 == 0 && a1 == 1) || (a2 == 1 && a0 == 0 && a1 == 2) || (a2 == 0 && a0 == 1 && a1 == 2);
+        if (!canonical) return false;
+        e.ref = ref;
+        e.aux = aux;
+        return push(e);
+    }
+    bool emit(vk_ref ref, uint32_t dup) {
+        const uint32_t i = VK_REF_INDEX(ref);
+        switch (VK_REF_TYPE(ref)) {
+        case VK_T_NODE: {
+            const vk_node& n = d->nodes[i];
+            if (!emit(n.left, dup)) return false;
+            if (n.right != n.left) return emit(n.right, dup);
+            vk_ref end = n.left; // single-object leaf: second visit only matters for a medium
+            while (VK_REF_TYPE(end) == VK_T_XFORM) end = d->xforms[VK_REF_INDEX(end)].child;
+            return VK_REF_TYPE(end) == VK_T_MEDIUM ? emit(n.left, VKD_DUP) : true;
+        }
+        case VK_T_SPHERE: {
+            FlatEntry e{};
+            e.a = make_float4(d->spheres[i].center[0], d->spheres[i].center[1], d->spheres[i].center[2], d->spheres[i].radius);
+            e.kind = VKF_SPHERE;
+            e.ref = ref;
+            return push(e);
+        }
+        case VK_T_MSPHERE: {
+            const vk_msphere& m = d->mspheres[i];
+            FlatEntry e{};
+            e.a = make_float4(m.center0[0], m.center0[1], m.center0[2], m.radius);
+            e.b = make_float4(m.center1[0], m.center1[1], m.center1[2], m.time0);
+            e.k = m.time1;
+            e.kind = VKF_MSPHERE;
+            e.ref = ref;
+            return push(e);
+        }
+        case VK_T_RECT: {
+            const vk_rect& r = d->rects[i];
+            return rect(r.c0, r.c1, r.d0, r.d1, r.k, r.axes, ref, 0);
+        }
+        case VK_T_BOX: { // the six sides in Boxy::new order (src/hittable.rs:325-353)
+            const vk_box& b = d->boxes[i];
+            const float* mn = b.box_min;
+            const float* mx = b.box_max;
+            const uint32_t XY = 0u | (1u << 2) | (2u << 4), XZ = 0u | (2u << 2) | (1u << 4), YZ = 1u | (2u << 2) | (0u << 4);
+            return rect(mn[0], mx[0], mn[1], mx[1], mx[2], XY, ref, 0 | VKF_STRICT) && rect(mn[0], mx[0], mn[1], mx[1], mn[2], XY, ref, 1 | VKF_STRICT) &&
+                   rect(mn[0], mx[0], mn[2], mx[2], mx[1], XZ, ref, 2 | VKF_STRICT) && rect(mn[0], mx[0], mn[2], mx[2], mn[1], XZ, ref, 3 | VKF_STRICT) &&
+                   rect(mn[1], mx[1], mn[2], mx[2], mx[0], YZ, ref, 4 | VKF_STRICT) && rect(mn[1], mx[1], mn[2], mx[2], mn[0], YZ, ref, 5 | VKF_STRICT);
+        }
+        case VK_T_MEDIUM: {
+            FlatEntry e{};
+            e.kind = VKF_MEDIUM;
+            e.ref = ref | dup;
+            return push(e);
+        }
+        case VK_T_XFORM: {
+            vk_ref r = ref;
+            while (VK_REF_TYPE(r) == VK_T_XFORM) {
+                const vk_xform& x = d->xforms[VK_REF_INDEX(r)];
+                FlatEntry e{};
+                e.ref = ref; // instance id = outermost wrapper
+                if (x.kind == VK_X_TRANSLATE) {
+                    e.kind = VKF_PUSH_TRANSLATE;
+                    e.a = make_float4(x.a, x.b, x.c, 0.f);
+                } else if (x.kind == VK_X_FLIP) {
+                    e.kind = VKF_PUSH_TRANSLATE; // the ray is unchanged; the flip happens in resolve_hit
+                    e.a = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    e.kind = x.kind == VK_X_ROTATE_X ? VKF_PUSH_ROTX : (x.kind == VK_X_ROTATE_Y ? VKF_PUSH_ROTY : VKF_PUSH_ROTZ);
+                    e.a = make_float4(x.a, x.b, 0.f, 0.f);
+                }
+                if (!push(e)) return false;
+                r = x.child;
+            }
+            if (!emit(r, dup)) return false;
+            FlatEntry e{};
+            e.kind = VKF_POP;
+            return push(e);
+        }
+        default: return false;
+        }
+    }
+};
+
 template <class T> int upload(vk_ctx* c, const T* src, size_t n, const T** dst) {
     *dst = nullptr;
     if (n == 0) n = 1; // keep pointers valid
@@ -339,8 +445,8 @@ int vk_create(int device, vk_ctx** out) {
     CUC(cudaEventCreate(&c->ev0));
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaEventCreate(&c->ev2));
-    CUC(cudaMalloc((void**)&c->counters, 4 * sizeof(unsigned long long)));
-    CUC(cudaMemset(c->counters, 0, 4 * sizeof(unsigned long long)));
+    CUC(cudaMalloc((void**)&c->counters, 8 * sizeof(unsigned long long)));
+    CUC(cudaMemset(c->counters, 0, 8 * sizeof(unsigned long long)));
 #undef CUC
     *out = c;
     return VK_OK;
@@ -390,6 +496,24 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
             while (VK_REF_TYPE(end) == VK_T_XFORM) end = d->xforms[VK_REF_INDEX(end)].child;
             nodes[i].right = VK_REF_TYPE(end) == VK_T_MEDIUM ? (nodes[i].left | VKD_DUP) : VK_REF_NONE;
         }
+    // wide nodes: children's boxes pulled up into the parent (see DScene)
+    std::vector<float4> wnodes((size_t)d->n_nodes * 4);
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+        const vk_ref l = nodes[i].left, r = nodes[i].right;
+        float4 q[4] = {make_float4(0, 0, 0, __uint_as_float_host(l)), make_float4(0, 0, 0, __uint_as_float_host(r)), make_float4(0, 0, 0, 0),
+                       make_float4(0, 0, 0, 0)};
+        if (VK_REF_TYPE(l) == VK_T_NODE) {
+            const vk_node& c = d->nodes[VK_REF_INDEX(l)];
+            q[0].x = c.bb_min[0]; q[0].y = c.bb_min[1]; q[0].z = c.bb_min[2];
+            q[1].x = c.bb_max[0]; q[1].y = c.bb_max[1]; q[1].z = c.bb_max[2];
+        }
+        if (VK_REF_TYPE(r) == VK_T_NODE) {
+            const vk_node& c = d->nodes[VK_REF_INDEX(r)];
+            q[2].x = c.bb_min[0]; q[2].y = c.bb_min[1]; q[2].z = c.bb_min[2];
+            q[3].x = c.bb_max[0]; q[3].y = c.bb_max[1]; q[3].z = c.bb_max[2];
+        }
+        for (int k = 0; k < 4; ++k) wnodes[(size_t)i * 4 + k] = q[k];
+    }
     std::vector<vk_material> mats(d->materials, d->materials + d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         bool uv;
@@ -417,6 +541,7 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
         free_scene(c);                                                                                                 \
         return rc;                                                                                                     \
     }
+    UP(wnodes, float4, wnodes.data(), wnodes.size())
     UP(nodes, float4, nodes.data(), (size_t)d->n_nodes * 2)
     UP(spheres, float4, d->spheres, d->n_spheres)
     UP(sphere_mat, uint32_t, d->sphere_mat, d->n_spheres)
@@ -436,6 +561,9 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     s.n_lights = d->n_lights;
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
+    c->flat = FlatProgram{};
+    FlatBuilder fb{d, &c->flat};
+    if (!fb.emit(d->root, 0)) c->flat.n = 0;
     c->has_scene = true;
     return VK_OK;
 }
@@ -457,8 +585,9 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     CU(c, cudaSetDevice(c->device));
     const bool strict = (P->flags & VK_FLAG_STRICT_MATH) != 0;
 
+    const FlatProgram* flat = (c->flat.n && !(P->flags & VK_FLAG_FORCE_BVH)) ? &c->flat : nullptr;
     int bps = 0, bt = 0;
-    CU(c, strict ? vkstrict::megakernel_occupancy(&bps, &bt) : vkfast::megakernel_occupancy(&bps, &bt));
+    CU(c, strict ? vkstrict::megakernel_occupancy(flat != nullptr, &bps, &bt) : vkfast::megakernel_occupancy(flat != nullptr, &bps, &bt));
     if (bps < 1) bps = 1;
     const int grid = c->sm_count * bps;
     const uint32_t resident_warps = (uint32_t)grid * (uint32_t)bt / 32u;
@@ -499,8 +628,8 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // work-queue head only
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
-    CU(c, strict ? vkstrict::launch_megakernel(c->scene, dc, a, b, grid, c->stream)
-                 : vkfast::launch_megakernel(c->scene, dc, a, b, grid, c->stream));
+    CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)
+                 : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream));
     uint32_t launches = 1;
     if (a.n_chunks > 1) {
         const unsigned g = (unsigned)((plane + 255) / 256);
@@ -549,14 +678,17 @@ int vk_set_stream(vk_ctx* c, void* stream) {
 int vk_flush_stats(vk_ctx* c, vk_stats* stats) {
     if (!c || !stats) return VK_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
     CU(c, cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemsetAsync(c->counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    CU(c, cudaMemsetAsync(c->counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     std::memset(stats, 0, sizeof(*stats));
     stats->paths = c->paths;
     stats->rays = h[0];
     stats->dropped_samples = h[1];
+    stats->node_visits = h[3];
+    stats->prim_tests = h[4];
     stats->launches = (uint32_t)c->launches;
     stats->variant = VK_VARIANT_MEGAKERNEL;
     c->paths = 0;
@@ -618,8 +750,9 @@ int vk_intersect(vk_ctx* c, const vk_ray* rays, size_t n, const float* medium_xi
         STEP(cudaMemcpyAsync(d_xi, medium_xi, n * VK_MEDIUM_XI_SLOTS * sizeof(float), cudaMemcpyHostToDevice, c->stream))
     }
     STEP(cudaMemcpyAsync(d_rays, rays, n * sizeof(vk_ray), cudaMemcpyHostToDevice, c->stream))
-    STEP((flags & VK_FLAG_STRICT_MATH) ? vkstrict::launch_intersect(c->scene, d_rays, n, d_xi, d_hits, c->stream)
-                                       : vkfast::launch_intersect(c->scene, d_rays, n, d_xi, d_hits, c->stream))
+    const FlatProgram* flat = (c->flat.n && !(flags & VK_FLAG_FORCE_BVH)) ? &c->flat : nullptr;
+    STEP((flags & VK_FLAG_STRICT_MATH) ? vkstrict::launch_intersect(c->scene, flat, d_rays, n, d_xi, d_hits, c->stream)
+                                       : vkfast::launch_intersect(c->scene, flat, d_rays, n, d_xi, d_hits, c->stream))
     STEP(cudaMemcpyAsync(out, d_hits, n * sizeof(vk_hit), cudaMemcpyDeviceToHost, c->stream))
     STEP(cudaStreamSynchronize(c->stream))
 #undef STEP

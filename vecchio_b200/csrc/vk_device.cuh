@@ -68,7 +68,13 @@ VKD uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
+#if VK_STRICT
 VKD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; } // gen::<f32>(): 24-bit [0,1)
+#else
+// 23-bit grid built with integer ops only (I2F runs on the quarter-rate XU pipe); the reference's
+// 24-bit grid and this one are indistinguishable at any spp a render uses
+VKD float u01(uint32_t x) { return __uint_as_float(0x3F800000u | (x >> 9)) - 1.0f; }
+#endif
 VKD float gen_range(uint32_t x, float lo, float hi) {                           // gen_range(lo,hi): 23-bit [lo,hi)
     const float scale = hi - lo;
     const float res = __uint_as_float(0x3F800000u | (x >> 9)) * scale + (lo - scale);
@@ -101,7 +107,7 @@ struct MediumXi {
 // The reference's per-axis early exit is equivalent to one test after the third axis (the
 // interval only shrinks).  STRICT divides like the reference; FAST multiplies by 1/d.
 // ---------------------------------------------------------------------------------------------
-VKD bool aabb_hit(float3 bmin, float3 bmax, float3 o, float3 d, float3 inv_d, float tmin, float tmax) {
+VKD bool aabb_hit(float3 bmin, float3 bmax, float3 o, float3 d, float3 inv_d, float tmin, float tmax, float& t_entry) {
 #if VK_STRICT
     (void)inv_d;
     const float ax = (bmin.x - o.x) / d.x, bx = (bmax.x - o.x) / d.x;
@@ -119,6 +125,7 @@ VKD bool aabb_hit(float3 bmin, float3 bmax, float3 o, float3 d, float3 inv_d, fl
     tmax = fminf(fmaxf(ay, by), tmax);
     tmin = fmaxf(fminf(az, bz), tmin);
     tmax = fminf(fmaxf(az, bz), tmax);
+    t_entry = tmin;
     return !(tmax <= tmin);
 }
 
@@ -156,9 +163,14 @@ VKD float3 msphere_center(float4 m0, float4 m1, float time1, float time) { // sr
 // Rect::hit, distance only (src/hittable.rs:230-239): inclusive bounds written as the reference
 // writes them, so NaN t / NaN a,b pass exactly where they pass there (Q14).
 // ---------------------------------------------------------------------------------------------
-VKD bool rect_t(float4 bounds, float k, uint32_t axes, float3 o, float3 d, float tmin, float tmax, float& t) {
+VKD bool rect_t(float4 bounds, float k, uint32_t axes, float3 o, float3 d, float3 inv_d, float tmin, float tmax, float& t) {
     const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u, a2 = (axes >> 4) & 3u;
+#if VK_STRICT
+    (void)inv_d;
     const float tt = (k - comp(o, a2)) / comp(d, a2);
+#else
+    const float tt = (k - comp(o, a2)) * comp(inv_d, a2);
+#endif
     if (tt < tmin || tt > tmax) return false;
     const float a = comp(o, a0) + tt * comp(d, a0);
     const float b = comp(o, a1) + tt * comp(d, a1);
@@ -171,12 +183,18 @@ VKD bool rect_t(float4 bounds, float k, uint32_t axes, float3 o, float3 d, float
 // Boxy::hit (src/hittable.rs:363-365) = list hit (:381-394) over the six sides in Boxy::new order
 // (:325-353): first side wins ties (strict rec.t < closest_dist), tmax shrinks as sides hit.
 // ---------------------------------------------------------------------------------------------
-VKD bool box_t(float3 mn, float3 mx, float3 o, float3 d, float tmin, float tmax, float& t_out, uint32_t& face) {
+VKD bool box_t(float3 mn, float3 mx, float3 o, float3 d, float3 inv_d, float tmin, float tmax, float& t_out, uint32_t& face) {
     float closest = tmax;
     int f = -1;
-#define VK_SIDE(F, K, O2, D2, O0, D0, C0, C1, O1, D1, E0, E1)                                                          \
+#if VK_STRICT
+    (void)inv_d;
+#define VK_DIV(N, D, I) ((N) / (D))
+#else
+#define VK_DIV(N, D, I) ((N) * (I))
+#endif
+#define VK_SIDE(F, K, O2, D2, I2, O0, D0, C0, C1, O1, D1, E0, E1)                                                      \
     {                                                                                                                  \
-        const float tt = ((K) - (O2)) / (D2);                                                                          \
+        const float tt = VK_DIV((K) - (O2), D2, I2);                                                                   \
         if (!(tt < tmin || tt > closest)) {                                                                            \
             const float a = (O0) + tt * (D0), b = (O1) + tt * (D1);                                                    \
             if (!(a < (C0) || a > (C1) || b < (E0) || b > (E1)) && tt < closest) {                                     \
@@ -185,13 +203,14 @@ VKD bool box_t(float3 mn, float3 mx, float3 o, float3 d, float tmin, float tmax,
             }                                                                                                          \
         }                                                                                                              \
     }
-    VK_SIDE(0, mx.z, o.z, d.z, o.x, d.x, mn.x, mx.x, o.y, d.y, mn.y, mx.y) // XYRect at p1.z
-    VK_SIDE(1, mn.z, o.z, d.z, o.x, d.x, mn.x, mx.x, o.y, d.y, mn.y, mx.y) // FlipFace(XYRect at p0.z)
-    VK_SIDE(2, mx.y, o.y, d.y, o.x, d.x, mn.x, mx.x, o.z, d.z, mn.z, mx.z) // XZRect at p1.y
-    VK_SIDE(3, mn.y, o.y, d.y, o.x, d.x, mn.x, mx.x, o.z, d.z, mn.z, mx.z) // FlipFace(XZRect at p0.y)
-    VK_SIDE(4, mx.x, o.x, d.x, o.y, d.y, mn.y, mx.y, o.z, d.z, mn.z, mx.z) // YZRect at p1.x
-    VK_SIDE(5, mn.x, o.x, d.x, o.y, d.y, mn.y, mx.y, o.z, d.z, mn.z, mx.z) // FlipFace(YZRect at p0.x)
+    VK_SIDE(0, mx.z, o.z, d.z, inv_d.z, o.x, d.x, mn.x, mx.x, o.y, d.y, mn.y, mx.y) // XYRect at p1.z
+    VK_SIDE(1, mn.z, o.z, d.z, inv_d.z, o.x, d.x, mn.x, mx.x, o.y, d.y, mn.y, mx.y) // FlipFace(XYRect at p0.z)
+    VK_SIDE(2, mx.y, o.y, d.y, inv_d.y, o.x, d.x, mn.x, mx.x, o.z, d.z, mn.z, mx.z) // XZRect at p1.y
+    VK_SIDE(3, mn.y, o.y, d.y, inv_d.y, o.x, d.x, mn.x, mx.x, o.z, d.z, mn.z, mx.z) // FlipFace(XZRect at p0.y)
+    VK_SIDE(4, mx.x, o.x, d.x, inv_d.x, o.y, d.y, mn.y, mx.y, o.z, d.z, mn.z, mx.z) // YZRect at p1.x
+    VK_SIDE(5, mn.x, o.x, d.x, inv_d.x, o.y, d.y, mn.y, mx.y, o.z, d.z, mn.z, mx.z) // FlipFace(YZRect at p0.x)
 #undef VK_SIDE
+#undef VK_DIV
     if (f < 0) return false;
     t_out = closest;
     face = (uint32_t)f;
@@ -249,7 +268,9 @@ VKD uint32_t chain_down(const DScene& sc, uint32_t ref, float3& o, float3& d) {
 
 // Distance-only hit of a leaf primitive (no BVH below it): the shared body of the traversal's
 // leaf test and of ConstantMedium's two boundary queries.
-VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax, float& t,
+VKD float3 rcp3(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+
+VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float3 inv_d, float time, float tmin, float tmax, float& t,
                 uint32_t& face) {
     const uint32_t i = VKD_INDEX(ref);
     face = 0;
@@ -264,11 +285,11 @@ VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, 
     }
     case VK_T_RECT: {
         const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
-        return rect_t(r0, r1.x, __float_as_uint(r1.y), o, d, tmin, tmax, t);
+        return rect_t(r0, r1.x, __float_as_uint(r1.y), o, d, inv_d, tmin, tmax, t);
     }
     case VK_T_BOX: {
         const float4 b0 = __ldg(&sc.boxes[2 * i]), b1 = __ldg(&sc.boxes[2 * i + 1]);
-        return box_t(f3(b0), f3(b1), o, d, tmin, tmax, t, face);
+        return box_t(f3(b0), f3(b1), o, d, inv_d, tmin, tmax, t, face);
     }
     default: return false;
     }
@@ -276,15 +297,25 @@ VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, 
 
 // ConstantMedium::hit (src/hittable.rs:453-493).  The boundary is a leaf, possibly behind a wrapper
 // chain (t is invariant under the chain).
-VKD bool medium_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax,
-                  const MediumXi& xi, float& t) {
+__device__ __noinline__ bool medium_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax,
+                                      const MediumXi& xi, float& t) {
     const float4 m = __ldg(&sc.media[VKD_INDEX(ref)]);
     float3 bo = o, bd = d;
     const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
-    float t1, t2;
+    const float3 binv = rcp3(bd);
+    float t1 = 0.0f, t2 = 0.0f;
     uint32_t face;
-    if (!leaf_t(sc, b, bo, bd, time, -CUDART_INF_F, CUDART_INF_F, t1, face)) return false;
-    if (!leaf_t(sc, b, bo, bd, time, t1 + 0.0001f, CUDART_INF_F, t2, face)) return false;
+    float lo = -CUDART_INF_F;
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) { // rec1 = boundary.hit(-inf, inf); rec2 = boundary.hit(rec1.t + 0.0001, inf)
+        float tq;
+        if (!leaf_t(sc, b, bo, bd, binv, time, lo, CUDART_INF_F, tq, face)) return false;
+        if (q == 0) {
+            t1 = tq;
+            lo = tq + 0.0001f;
+        } else
+            t2 = tq;
+    }
     if (t1 < tmin) t1 = tmin;
     if (t2 > tmax) t2 = tmax;
     if (t1 >= t2) return false;
@@ -298,11 +329,15 @@ VKD bool medium_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time
 }
 
 // ---------------------------------------------------------------------------------------------
-// BVHNode::hit (src/accel.rs:58-83) as an explicit-stack loop: left subtree first, then right with
-// tmax = closest so far -- exactly the values the recursion passes, since everything visited
-// before a node is a left sibling of one of its ancestors.  Any hit a child returns replaces the
-// current one (the reference's tie rule `l.t < r.t ? left : right`).  Only (t, primitive,
-// instance) are tracked; the HitRec is built once, after the loop (resolve_hit).
+// BVHNode::hit (src/accel.rs:58-83) as a while-while loop over the wide nodes.
+//
+// The reference recurses left-then-right and prunes the right subtree with tmax = left.t.  The
+// closest hit does not depend on the visiting order (ties excepted), so the GPU (i) tests the
+// boxes of both children at the parent, (ii) descends into the nearer box first and (iii) keeps
+// every lane of a warp in the node loop until it has a primitive to test, then lets all lanes
+// test their primitives together.  Any hit a primitive returns replaces the current one, which
+// is the reference's tie rule (`l.t < r.t ? left : right`) for left-then-right order.  Only
+// (t, primitive, instance) are tracked; the HitRec is built once, after the loop (resolve_hit).
 // ---------------------------------------------------------------------------------------------
 struct TraceHit {
     float t;
@@ -310,12 +345,17 @@ struct TraceHit {
     uint32_t inst; // outermost wrapper of the chain the leaf was reached through, or 0
     uint32_t face;
 };
+#define VKD_DONE 0xFFFFFFFFu
 
-VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin, float tmax, const MediumXi& xi) {
+struct TraceCounters {
+    uint32_t nodes, prims;
+};
+
+VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin, float tmax, const MediumXi& xi, TraceCounters& tc) {
     uint32_t stack[VKD_STACK];
     int sp = 0;
     float3 co = o, cd = d; // ray in the current frame (world, or the frame of the instance being traversed)
-    float3 cinv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float3 cinv = rcp3(d);
     uint32_t cur_inst = 0;
     TraceHit best;
     best.t = tmax;
@@ -323,61 +363,158 @@ VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin,
     best.inst = 0;
     best.face = 0;
     uint32_t ref = sc.root;
+    bool enter = true; // `ref` is a BVH root whose own box has not been tested yet
 #pragma unroll 1
     for (;;) {
+        // ---- node phase ---------------------------------------------------------------------
+#pragma unroll 1
+        while (VKD_TYPE(ref) == VK_T_NODE) {
+            const uint32_t ni = VKD_INDEX(ref);
+            if (enter) { // BVHNode::hit's own `bb.hit` for the world root / an instanced sub-BVH root
+                enter = false;
+                const float4 n0 = __ldg(&sc.nodes[2 * ni]), n1 = __ldg(&sc.nodes[2 * ni + 1]);
+                float te;
+                if (!aabb_hit(f3(n0), f3(n1), co, cd, cinv, tmin, best.t, te)) {
+                    ref = sp ? stack[--sp] : VKD_DONE;
+                    continue;
+                }
+            }
+            ++tc.nodes;
+            const float4 w0 = __ldg(&sc.wnodes[4 * ni]), w1 = __ldg(&sc.wnodes[4 * ni + 1]);
+            const uint32_t left = __float_as_uint(w0.w), right = __float_as_uint(w1.w);
+            bool hl = true, hr = right != VK_REF_NONE;
+            float tl = -CUDART_INF_F, tr = -CUDART_INF_F; // a primitive child is simply visited, left first
+            if (VKD_TYPE(left) == VK_T_NODE) hl = aabb_hit(f3(w0), f3(w1), co, cd, cinv, tmin, best.t, tl);
+            if (VKD_TYPE(right) == VK_T_NODE) {
+                const float4 w2 = __ldg(&sc.wnodes[4 * ni + 2]), w3 = __ldg(&sc.wnodes[4 * ni + 3]);
+                hr = aabb_hit(f3(w2), f3(w3), co, cd, cinv, tmin, best.t, tr);
+            }
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                stack[sp++] = left_first ? right : left;
+                ref = left_first ? left : right;
+            } else if (hl) {
+                ref = left;
+            } else if (hr) {
+                ref = right;
+            } else {
+                ref = sp ? stack[--sp] : VKD_DONE;
+            }
+        }
+        if (ref == VKD_DONE) break;
+        // ---- primitive phase ----------------------------------------------------------------
         const uint32_t type = VKD_TYPE(ref);
-        if (type == VK_T_NODE) {
-            const float4 n0 = __ldg(&sc.nodes[2 * VKD_INDEX(ref)]);
-            const float4 n1 = __ldg(&sc.nodes[2 * VKD_INDEX(ref) + 1]);
-            if (aabb_hit(f3(n0), f3(n1), co, cd, cinv, tmin, best.t)) {
-                const uint32_t right = __float_as_uint(n1.w);
-                if (right != VK_REF_NONE) stack[sp++] = right;
-                ref = __float_as_uint(n0.w);
-                continue;
-            }
-        } else if (type == VK_T_XFORM) {
-            float3 to = co, td = cd;
-            const uint32_t child = chain_down(sc, ref, to, td);
-            if (VKD_TYPE(child) == VK_T_NODE) { // instanced sub-BVH: traverse it in object space
-                stack[sp++] = VKD_T_EXIT << 28;
-                co = to;
-                cd = td;
-                cinv = f3(1.0f / td.x, 1.0f / td.y, 1.0f / td.z);
-                cur_inst = ref & ~VKD_DUP;
-                ref = child;
-                continue;
-            }
-            float t;
-            uint32_t face = 0;
-            bool hit;
-            if (VKD_TYPE(child) == VK_T_MEDIUM) hit = medium_t(sc, child | (ref & VKD_DUP), to, td, time, tmin, best.t, xi, t);
-            else hit = leaf_t(sc, child, to, td, time, tmin, best.t, t, face);
-            if (hit) {
-                best.t = t;
-                best.prim = child & ~VKD_DUP;
-                best.inst = ref & ~VKD_DUP;
-                best.face = face;
-            }
-        } else if (type == VKD_T_EXIT) {
+        if (type == VKD_T_EXIT) { // leave the instanced sub-BVH
             co = o;
             cd = d;
-            cinv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            cinv = rcp3(d);
             cur_inst = 0;
         } else if (type != VK_T_NONE) {
+            float3 to = co, td = cd, tinv = cinv;
+            uint32_t leaf = ref, inst = cur_inst;
+            if (type == VK_T_XFORM) {
+                leaf = chain_down(sc, ref, to, td) | (ref & VKD_DUP);
+                inst = ref & ~VKD_DUP;
+                if (VKD_TYPE(leaf) == VK_T_NODE) { // instanced sub-BVH: traverse it in object space
+                    stack[sp++] = VKD_T_EXIT << 28;
+                    co = to;
+                    cd = td;
+                    cinv = rcp3(td);
+                    cur_inst = inst;
+                    ref = leaf & ~VKD_DUP;
+                    enter = true;
+                    continue;
+                }
+                tinv = rcp3(td);
+            }
             float t;
             uint32_t face = 0;
             bool hit;
-            if (type == VK_T_MEDIUM) hit = medium_t(sc, ref, co, cd, time, tmin, best.t, xi, t);
-            else hit = leaf_t(sc, ref, co, cd, time, tmin, best.t, t, face);
+            ++tc.prims;
+            if (VKD_TYPE(leaf) == VK_T_MEDIUM) hit = medium_t(sc, leaf, to, td, time, tmin, best.t, xi, t);
+            else hit = leaf_t(sc, leaf, to, td, tinv, time, tmin, best.t, t, face);
             if (hit) {
                 best.t = t;
-                best.prim = ref & ~VKD_DUP;
-                best.inst = cur_inst;
+                best.prim = leaf & ~VKD_DUP;
+                best.inst = inst;
                 best.face = face;
             }
         }
         if (sp == 0) break;
         ref = stack[--sp];
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same closest-hit query over a flat program (see FlatProgram in vk_internal.h): every lane
+// executes the same entry at the same time.  Per-entry arithmetic is the reference's, in its order.
+// ---------------------------------------------------------------------------------------------
+#if VK_STRICT
+#define VKF_PLANE_T(K, O, D, I) (((K) - (O)) / (D))
+#else
+#define VKF_PLANE_T(K, O, D, I) (((K) - (O)) * (I))
+#endif
+VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3 d, float time, float tmin, float tmax,
+                        const MediumXi& xi, TraceCounters& tc) {
+    float3 co = o, cd = d, ci = rcp3(d);
+    uint32_t inst = 0;
+    TraceHit best;
+    best.t = tmax;
+    best.prim = VK_REF_NONE;
+    best.inst = 0;
+    best.face = 0;
+    const uint32_t n = P.n;
+    tc.prims += n;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n; ++i) {
+        const FlatEntry& e = P.e[i];
+        const uint32_t kind = e.kind;
+        float tt = 0.0f;
+        bool hit = false;
+        if (kind <= VKF_RECT_YZ) { // Rect::hit src/hittable.rs:230-239
+            float a, b;
+            if (kind == VKF_RECT_XY) {
+                tt = VKF_PLANE_T(e.k, co.z, cd.z, ci.z);
+                a = co.x + tt * cd.x;
+                b = co.y + tt * cd.y;
+            } else if (kind == VKF_RECT_XZ) {
+                tt = VKF_PLANE_T(e.k, co.y, cd.y, ci.y);
+                a = co.x + tt * cd.x;
+                b = co.z + tt * cd.z;
+            } else {
+                tt = VKF_PLANE_T(e.k, co.x, cd.x, ci.x);
+                a = co.y + tt * cd.y;
+                b = co.z + tt * cd.z;
+            }
+            hit = !(tt < tmin || tt > best.t) && !(a < e.a.x || a > e.a.y || b < e.a.z || b > e.a.w);
+        } else if (kind == VKF_SPHERE) {
+            hit = sphere_t(f3(e.a), e.a.w, co, cd, tmin, best.t, tt);
+        } else if (kind == VKF_MSPHERE) {
+            hit = sphere_t(msphere_center(e.a, e.b, e.k, time), e.a.w, co, cd, tmin, best.t, tt);
+        } else if (kind == VKF_MEDIUM) {
+            hit = medium_t(sc, e.ref, co, cd, time, tmin, best.t, xi, tt);
+        } else if (kind == VKF_POP) {
+            co = o;
+            cd = d;
+            ci = rcp3(d);
+            inst = 0;
+        } else { // push one wrapper level
+            if (inst == 0) inst = e.ref;
+            if (kind == VKF_PUSH_TRANSLATE) co = co - f3(e.a);
+            else {
+                const uint32_t xk = kind == VKF_PUSH_ROTX ? VK_X_ROTATE_X : (kind == VKF_PUSH_ROTY ? VK_X_ROTATE_Y : VK_X_ROTATE_Z);
+                rot_fwd(xk, e.a.x, e.a.y, co);
+                rot_fwd(xk, e.a.x, e.a.y, cd);
+                ci = rcp3(cd);
+            }
+        }
+        if (hit && !((e.aux & VKF_STRICT) && !(tt < best.t))) {
+            best.t = tt;
+            best.prim = e.ref & ~VKD_DUP;
+            best.inst = inst;
+            best.face = e.aux & 0xFFu;
+        }
     }
     return best;
 }
@@ -516,7 +653,7 @@ VKD void resolve_hit(const DScene& sc, const TraceHit& h, float3 o, float3 d, fl
             const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
             float t1;
             uint32_t face;
-            if (leaf_t(sc, b, bo, bd, time, -CUDART_INF_F, CUDART_INF_F, t1, face)) {
+            if (leaf_t(sc, b, bo, bd, rcp3(bd), time, -CUDART_INF_F, CUDART_INF_F, t1, face)) {
                 HitRecD r1;
                 leaf_record(sc, b, face, bo, bd, time, t1, true, r1);
                 rec.u = r1.u;
@@ -590,7 +727,7 @@ VKD float perlin_turb(const float4* vec, const uint8_t* perm, float3 p, int dept
     return fabsf(accum);
 }
 VKD float clamp_ref(float x, float mn, float mx) { return x < mn ? mn : (x > mx ? mx : x); } // Vec3::clamp keeps NaN
-VKD float3 tex_value(const DScene& sc, uint32_t ti, float u, float v, float3 p) {
+__device__ __noinline__ float3 tex_value(const DScene& sc, uint32_t ti, float u, float v, float3 p) {
     uint4 t = __ldg(&sc.textures[ti]);
 #pragma unroll 1
     for (int guard = 0; t.x == VK_TEX_CHECKER && guard < 16; ++guard) { // Checker :250-258 (sinf, not __sinf: args ~1e3)
@@ -674,7 +811,7 @@ VKD float3 random_in_unit_sphere(float u1, float u2, float u3) {
 // ---------------------------------------------------------------------------------------------
 VKD float rect_pdf_value(float4 bounds, float k, uint32_t axes, float3 origin, float3 v) {
     float t;
-    if (!rect_t(bounds, k, axes, origin, v, 0.001f, CUDART_INF_F, t)) return 0.0f;
+    if (!rect_t(bounds, k, axes, origin, v, rcp3(v), 0.001f, CUDART_INF_F, t)) return 0.0f;
     const float area = (bounds.y - bounds.x) * (bounds.w - bounds.z);
     const float distance_squared = t * t * length2(v);
     // rec.normal is +-e_axis2, so |v . n| = |v[axis2]|

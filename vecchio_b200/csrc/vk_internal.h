@@ -19,7 +19,14 @@
 // Scene arrays in HBM.  Every record is a multiple of 16 B and fetched with 128-bit loads
 // through the read-only path; one array per primitive kind (struct-of-arrays by type).
 struct DScene {
-    const float4* nodes;    // 2 x float4 per node: {min.xyz, left}, {max.xyz, right}
+    // Traversal layout ("wide" node, 64 B = 4 x float4, one 128-byte-line half): the boxes of BOTH
+    // children live in the parent, so one fetch decides both descents and the nearer child is
+    // visited first.  {lmin.xyz, left}, {lmax.xyz, right}, {rmin.xyz, -}, {rmax.xyz, -}.  A box is
+    // only meaningful for a child that is itself a node: the reference tests no box for a primitive
+    // child (src/accel.rs:64-65 calls its hit() directly).
+    const float4* wnodes;
+    const float4* nodes;    // reference layout, 2 x float4 per node: {min.xyz, left}, {max.xyz, right}; used for
+                            // the box of a BVH root (world root, instanced sub-BVH root)
     const float4* spheres;  // {center.xyz, radius}
     const uint32_t* sphere_mat;
     const float4* mspheres; // 3 x float4: {c0, r}, {c1, time0}, {time1, mat, -, -}
@@ -38,6 +45,36 @@ struct DScene {
 };
 #define VKD_MAT_NEEDS_UV 0x80000000u
 
+// ------------------------------------------------------------------------------------------------
+// Flat traversal program.  A scene with few primitives (Cornell box: 13 rect sides + 1 sphere) gains
+// nothing from its BVH on a GPU: the lanes of a warp sit at different nodes and execute each
+// other's branches.  For such scenes vk_scene_upload unrolls the reference's traversal order
+// (depth first, left then right, a Boxy as its six sides, a wrapper chain as push/pop of the ray
+// frame) into a short straight-line program.  Every lane then tests the SAME primitive at the same
+// time: no stack, no divergence, warp-uniform operand fetches from the constant bank (the program
+// travels as a __grid_constant__ kernel parameter).  Closest hit is order independent, so this is
+// the same function as BVHNode::hit; the BVH path remains for everything larger.
+// ------------------------------------------------------------------------------------------------
+#define VKD_FLAT_MAX 96
+enum {
+    VKF_RECT_XY = 1, VKF_RECT_XZ, VKF_RECT_YZ, VKF_SPHERE, VKF_MSPHERE, VKF_MEDIUM,
+    VKF_PUSH_TRANSLATE, VKF_PUSH_ROTX, VKF_PUSH_ROTY, VKF_PUSH_ROTZ, VKF_POP
+};
+#define VKF_STRICT 0x100u // a side of a Boxy: list semantics, must be strictly closer (src/hittable.rs:386)
+struct FlatEntry {
+    float4 a;      // rect: c0,c1,d0,d1 | sphere: center,r | msphere: c0,r | translate: offset | rotate: sin,cos
+    float4 b;      // msphere: c1,time0
+    float k;       // rect: plane | msphere: time1
+    uint32_t kind; // VKF_*
+    uint32_t ref;  // leaf record (hit id) | push: the chain's outermost wrapper (instance id)
+    uint32_t aux;  // face (0..5) | VKF_STRICT
+};
+struct FlatProgram {
+    uint32_t n; // 0 = no program: use the BVH
+    uint32_t _pad[3];
+    FlatEntry e[VKD_FLAT_MAX];
+};
+
 struct DCamera {
     float3 origin, lower_left_corner, horizontal, vertical, u, v;
     float lens_radius, time0, time1;
@@ -53,7 +90,7 @@ struct RenderArgs {
     uint32_t tiles_x, tiles_y, n_chunks, chunk_spp;
 };
 
-// counters[0] = rays, [1] = dropped samples, [2] = work-queue head
+// counters[0] = rays, [1] = dropped samples, [2] = work-queue head, [3] = node visits, [4] = primitive tests
 struct RenderBuffers {
     float* partial_sum;   // n_chunks x W*H*3 (== d_sum when n_chunks == 1)
     float* partial_sumsq; // same, nullable
@@ -62,11 +99,11 @@ struct RenderBuffers {
 
 #define VK_DECLARE_LAUNCHERS(NS)                                                                                       \
     namespace NS {                                                                                                     \
-    cudaError_t launch_megakernel(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,  \
-                                  int grid, cudaStream_t st);                                                          \
-    cudaError_t launch_intersect(const DScene& sc, const vk_ray* rays, size_t n, const float* medium_xi, vk_hit* out,  \
-                                 cudaStream_t st);                                                                     \
-    cudaError_t megakernel_occupancy(int* blocks_per_sm, int* block_threads);                                          \
+    cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,  \
+                                  const RenderBuffers& b, int grid, cudaStream_t st);                                  \
+    cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk_ray* rays, size_t n,              \
+                                 const float* medium_xi, vk_hit* out, cudaStream_t st);                                \
+    cudaError_t megakernel_occupancy(bool flat, int* blocks_per_sm, int* block_threads);                               \
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
     }
 VK_DECLARE_LAUNCHERS(vkfast)

@@ -8,7 +8,12 @@
 
 namespace VK_NS {
 
+#ifndef VK_BLOCK
 #define VK_BLOCK 128
+#endif
+#ifndef VK_MINB
+#define VK_MINB 4 // resident CTAs per SM the register allocation must allow
+#endif
 
 // Camera::get_ray (src/main.rs:111-120).  random_in_unit_disk() is always drawn by the reference
 // and multiplied by lens_radius; with lens_radius == 0 the product is exactly 0, so the draw is
@@ -111,13 +116,14 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     return true;
 }
 
-__global__ void __launch_bounds__(VK_BLOCK) k_megakernel(const DScene sc, const DCamera cam, const RenderArgs a,
-                                                         const RenderBuffers buf) {
+template <bool FLAT>
+VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
+                         const RenderBuffers& buf) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_tiles = a.tiles_x * a.tiles_y;
     const uint32_t total = n_tiles * a.n_chunks;
     const size_t plane = (size_t)a.width * a.height * 3u;
-    unsigned long long n_rays = 0, n_drop = 0;
+    unsigned long long n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0;
 
 #pragma unroll 1
     for (;;) {
@@ -157,7 +163,11 @@ __global__ void __launch_bounds__(VK_BLOCK) k_megakernel(const DScene sc, const 
                 xi.rng = rng;
                 xi.depth = depth;
                 ++n_rays;
-                const TraceHit h = trace(sc, o, d, time, 0.001f, CUDART_INF_F, xi); // src/main.rs:130
+                TraceCounters tc = {0u, 0u};
+                const TraceHit h = FLAT ? trace_flat(sc, *flat, o, d, time, 0.001f, CUDART_INF_F, xi, tc)
+                                        : trace(sc, o, d, time, 0.001f, CUDART_INF_F, xi, tc); // src/main.rs:130
+                n_nodes += tc.nodes;
+                n_prims += tc.prims;
                 if (h.prim == VK_REF_NONE) {
                     L = L + beta * a.background; // src/main.rs:151
                     alive = false;
@@ -166,6 +176,14 @@ __global__ void __launch_bounds__(VK_BLOCK) k_megakernel(const DScene sc, const 
                     resolve_hit(sc, h, o, d, time, false, rec);
                     alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
                     if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
+                    // A non-finite ray (refract()'s sqrt of a rounding-negative number, Q7) makes every
+                    // comparison of the reference false: it walks the WHOLE BVH, "hits" whichever Rect
+                    // comes last with t = NaN (Q14) and the sample is then NaN and dropped at
+                    // main.rs:192 (unless that Rect is an emitter).  Drop the sample directly.
+                    if (alive && !(finite3(d) && finite3(o))) {
+                        valid = false;
+                        alive = false;
+                    }
                 }
                 if (!alive) { // sample finished: NaN/Inf filter of src/main.rs:191-194
                     if (valid && finite3(L)) {
@@ -193,15 +211,29 @@ __global__ void __launch_bounds__(VK_BLOCK) k_megakernel(const DScene sc, const 
     for (int off = 16; off > 0; off >>= 1) {
         n_rays += __shfl_xor_sync(0xFFFFFFFFu, n_rays, off);
         n_drop += __shfl_xor_sync(0xFFFFFFFFu, n_drop, off);
+        n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, off);
+        n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, off);
     }
     if (lane == 0) {
+        atomicAdd(&buf.counters[3], n_nodes);
+        atomicAdd(&buf.counters[4], n_prims);
         atomicAdd(&buf.counters[0], n_rays);
         if (n_drop) atomicAdd(&buf.counters[1], n_drop);
     }
 }
 
-__global__ void __launch_bounds__(VK_BLOCK) k_intersect(const DScene sc, const vk_ray* __restrict__ rays, size_t n,
-                                                        const float* __restrict__ medium_xi, vk_hit* __restrict__ out) {
+__global__ void __launch_bounds__(VK_BLOCK, VK_MINB) k_megakernel(const DScene sc, const DCamera cam, const RenderArgs a,
+                                                         const RenderBuffers buf) {
+    megakernel_body<false>(sc, nullptr, cam, a, buf);
+}
+__global__ void __launch_bounds__(VK_BLOCK, VK_MINB) k_megakernel_flat(const DScene sc, const __grid_constant__ FlatProgram flat,
+                                                              const DCamera cam, const RenderArgs a, const RenderBuffers buf) {
+    megakernel_body<true>(sc, &flat, cam, a, buf);
+}
+
+template <bool FLAT>
+VKD void intersect_body(const DScene& sc, const FlatProgram* flat, const vk_ray* __restrict__ rays, size_t n,
+                        const float* __restrict__ medium_xi, vk_hit* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const vk_ray r = rays[i];
@@ -213,7 +245,8 @@ __global__ void __launch_bounds__(VK_BLOCK) k_intersect(const DScene sc, const v
     xi.rng.sample = (uint32_t)(i >> 32);
     xi.rng.key = make_uint2(0x243F6A88u, 0x85A308D3u);
     xi.depth = 1;
-    const TraceHit h = trace(sc, o, d, r.time, r.tmin, r.tmax, xi);
+    TraceCounters tc = {0u, 0u};
+    const TraceHit h = FLAT ? trace_flat(sc, *flat, o, d, r.time, r.tmin, r.tmax, xi, tc) : trace(sc, o, d, r.time, r.tmin, r.tmax, xi, tc);
     vk_hit q;
     q.prim = h.prim;
     q.face = 0;
@@ -238,26 +271,38 @@ __global__ void __launch_bounds__(VK_BLOCK) k_intersect(const DScene sc, const v
     }
     out[i] = q;
 }
+__global__ void __launch_bounds__(VK_BLOCK) k_intersect(const DScene sc, const vk_ray* __restrict__ rays, size_t n,
+                                                        const float* __restrict__ medium_xi, vk_hit* __restrict__ out) {
+    intersect_body<false>(sc, nullptr, rays, n, medium_xi, out);
+}
+__global__ void __launch_bounds__(VK_BLOCK) k_intersect_flat(const DScene sc, const __grid_constant__ FlatProgram flat,
+                                                             const vk_ray* __restrict__ rays, size_t n,
+                                                             const float* __restrict__ medium_xi, vk_hit* __restrict__ out) {
+    intersect_body<true>(sc, &flat, rays, n, medium_xi, out);
+}
 
 __global__ void k_philox_kat(const uint32_t* in6, uint32_t* out4) {
     const uint4 r = philox4x32_10(make_uint4(in6[0], in6[1], in6[2], in6[3]), make_uint2(in6[4], in6[5]));
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
 }
 
-cudaError_t launch_megakernel(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b, int grid,
-                              cudaStream_t st) {
-    k_megakernel<<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
+cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
+                              const RenderBuffers& b, int grid, cudaStream_t st) {
+    if (flat && flat->n) k_megakernel_flat<<<grid, VK_BLOCK, 0, st>>>(sc, *flat, cam, a, b);
+    else k_megakernel<<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
     return cudaGetLastError();
 }
-cudaError_t launch_intersect(const DScene& sc, const vk_ray* rays, size_t n, const float* medium_xi, vk_hit* out,
-                             cudaStream_t st) {
+cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk_ray* rays, size_t n, const float* medium_xi,
+                             vk_hit* out, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + VK_BLOCK - 1) / VK_BLOCK);
-    k_intersect<<<grid, VK_BLOCK, 0, st>>>(sc, rays, n, medium_xi, out);
+    if (flat && flat->n) k_intersect_flat<<<grid, VK_BLOCK, 0, st>>>(sc, *flat, rays, n, medium_xi, out);
+    else k_intersect<<<grid, VK_BLOCK, 0, st>>>(sc, rays, n, medium_xi, out);
     return cudaGetLastError();
 }
-cudaError_t megakernel_occupancy(int* blocks_per_sm, int* block_threads) {
+cudaError_t megakernel_occupancy(bool flat, int* blocks_per_sm, int* block_threads) {
     *block_threads = VK_BLOCK;
+    if (flat) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel_flat, VK_BLOCK, 0);
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel, VK_BLOCK, 0);
 }
 cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st) {
