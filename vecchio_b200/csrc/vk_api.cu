@@ -559,6 +559,7 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
 #undef UP
     s.root = d->root;
     s.n_lights = d->n_lights;
+    s.has_media = d->n_media > 0;
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
     c->flat = FlatProgram{};
@@ -587,7 +588,8 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
 
     const FlatProgram* flat = (c->flat.n && !(P->flags & VK_FLAG_FORCE_BVH)) ? &c->flat : nullptr;
     int bps = 0, bt = 0;
-    CU(c, strict ? vkstrict::megakernel_occupancy(flat != nullptr, &bps, &bt) : vkfast::megakernel_occupancy(flat != nullptr, &bps, &bt));
+    CU(c, strict ? vkstrict::megakernel_occupancy(flat != nullptr, c->scene.has_media, &bps, &bt)
+                 : vkfast::megakernel_occupancy(flat != nullptr, c->scene.has_media, &bps, &bt));
     if (bps < 1) bps = 1;
     const int grid = c->sm_count * bps;
     const uint32_t resident_warps = (uint32_t)grid * (uint32_t)bt / 32u;

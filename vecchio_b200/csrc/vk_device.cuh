@@ -351,6 +351,7 @@ struct TraceCounters {
     uint32_t nodes, prims;
 };
 
+template <bool MEDIA>
 VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin, float tmax, const MediumXi& xi, TraceCounters& tc) {
     uint32_t stack[VKD_STACK];
     int sp = 0;
@@ -431,7 +432,7 @@ VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin,
             uint32_t face = 0;
             bool hit;
             ++tc.prims;
-            if (VKD_TYPE(leaf) == VK_T_MEDIUM) hit = medium_t(sc, leaf, to, td, time, tmin, best.t, xi, t);
+            if (MEDIA && VKD_TYPE(leaf) == VK_T_MEDIUM) hit = medium_t(sc, leaf, to, td, time, tmin, best.t, xi, t);
             else hit = leaf_t(sc, leaf, to, td, tinv, time, tmin, best.t, t, face);
             if (hit) {
                 best.t = t;
@@ -455,6 +456,7 @@ VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin,
 #else
 #define VKF_PLANE_T(K, O, D, I) (((K) - (O)) * (I))
 #endif
+template <bool MEDIA>
 VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3 d, float time, float tmin, float tmax,
                         const MediumXi& xi, TraceCounters& tc) {
     float3 co = o, cd = d, ci = rcp3(d);
@@ -493,7 +495,7 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
         } else if (kind == VKF_MSPHERE) {
             hit = sphere_t(msphere_center(e.a, e.b, e.k, time), e.a.w, co, cd, tmin, best.t, tt);
         } else if (kind == VKF_MEDIUM) {
-            hit = medium_t(sc, e.ref, co, cd, time, tmin, best.t, xi, tt);
+            if (MEDIA) hit = medium_t(sc, e.ref, co, cd, time, tmin, best.t, xi, tt);
         } else if (kind == VKF_POP) {
             co = o;
             cd = d;
@@ -526,6 +528,7 @@ struct HitRecD {
     float3 p, normal;
     float t, u, v;
     uint32_t front, mat;
+    uint4 m; // materials[mat], fetched once per segment
 };
 
 VKD void spherical(float3 p, float& u, float& v) { // Sphere::spherical src/hittable.rs:54-61
@@ -561,12 +564,15 @@ VKD void box_side(float3 mn, float3 mx, uint32_t face, float4& bounds, float& k,
     }
 }
 // Full record of a leaf primitive hit at distance t by the ray (o, d) of the leaf's frame.
-VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, float3 d, float time, float t, bool want_uv,
+// (u, v) cost an atan2 + asin on a sphere: they are computed only when a texture of the hit
+// material reads them (VKD_MAT_NEEDS_UV, set at upload) or the caller wants the full record.
+VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, float3 d, float time, float t, bool always_uv,
                      HitRecD& rec) {
     const uint32_t i = VKD_INDEX(ref);
     rec.t = t;
     rec.u = 0.0f;
     rec.v = 0.0f;
+    bool want_uv = always_uv;
     switch (VKD_TYPE(ref)) {
     case VK_T_SPHERE:
     case VK_T_MSPHERE: { // src/hittable.rs:76-89, :165-178
@@ -583,6 +589,8 @@ VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, fl
             radius = m0.w;
             rec.mat = __float_as_uint(m2.y);
         }
+        rec.m = __ldg(&sc.materials[rec.mat]);
+        want_uv = want_uv || (rec.m.w & VKD_MAT_NEEDS_UV);
         rec.p = at(o, d, t);
         const float3 outward = (rec.p - c) / radius;
         set_face_normal(d, outward, rec);
@@ -593,6 +601,8 @@ VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, fl
         const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
         const uint32_t axes = __float_as_uint(r1.y);
         rec.mat = __float_as_uint(r1.z);
+        rec.m = __ldg(&sc.materials[rec.mat]);
+        want_uv = want_uv || (rec.m.w & VKD_MAT_NEEDS_UV);
         rect_record(r0, r1.x, axes, axes & VK_RECT_FLIP, o, d, t, want_uv, rec);
         break;
     }
@@ -603,14 +613,14 @@ VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, fl
         uint32_t axes;
         box_side(f3(b0), f3(b1), face, bounds, k, axes);
         rec.mat = __float_as_uint(b0.w);
+        rec.m = __ldg(&sc.materials[rec.mat]);
+        want_uv = want_uv || (rec.m.w & VKD_MAT_NEEDS_UV);
         rect_record(bounds, k, axes, face & 1u, o, d, t, want_uv, rec);
         break;
     }
     default: break;
     }
 }
-
-VKD bool mat_needs_uv(const DScene& sc, uint32_t mat) { return (__ldg(&sc.materials[mat]).w & VKD_MAT_NEEDS_UV) != 0; }
 
 // Build the HitRec the reference's `world.hit()` returns for the winning (prim, inst, t):
 // re-walk the wrapper chain down (same operations -> same bits), make the leaf record in the
@@ -642,13 +652,14 @@ VKD void resolve_hit(const DScene& sc, const TraceHit& h, float3 o, float3 d, fl
     if (VKD_TYPE(h.prim) == VK_T_MEDIUM) { // src/hittable.rs:481-489
         const float4 m = __ldg(&sc.media[VKD_INDEX(h.prim)]);
         rec.mat = __float_as_uint(m.z);
+        rec.m = __ldg(&sc.materials[rec.mat]);
         rec.t = h.t;
         rec.p = at(ro, rd, h.t);
         rec.normal = f3(1.0f, 0.0f, 0.0f);
         rec.front = 1u;
         rec.u = 0.0f;
         rec.v = 0.0f;
-        if (always_uv || mat_needs_uv(sc, rec.mat)) { // (u, v) of rec1, the boundary entry hit
+        if (always_uv || (rec.m.w & VKD_MAT_NEEDS_UV)) { // (u, v) of rec1, the boundary entry hit
             float3 bo = ro, bd = rd;
             const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
             float t1;
@@ -661,19 +672,7 @@ VKD void resolve_hit(const DScene& sc, const TraceHit& h, float3 o, float3 d, fl
             }
         }
     } else {
-        uint32_t mat_peek = 0;
-        bool want_uv = always_uv;
-        if (!want_uv) { // spherical() costs an atan2 + asin: only pay for it when a texture reads (u,v)
-            const uint32_t i = VKD_INDEX(h.prim);
-            switch (VKD_TYPE(h.prim)) {
-            case VK_T_SPHERE: mat_peek = __ldg(&sc.sphere_mat[i]); break;
-            case VK_T_MSPHERE: mat_peek = __float_as_uint(__ldg(&sc.mspheres[3 * i + 2]).y); break;
-            case VK_T_RECT: mat_peek = __float_as_uint(__ldg(&sc.rects[2 * i + 1]).z); break;
-            default: mat_peek = __float_as_uint(__ldg(&sc.boxes[2 * i]).w); break;
-            }
-            want_uv = mat_needs_uv(sc, mat_peek);
-        }
-        leaf_record(sc, h.prim, h.face, ro, rd, time, h.t, want_uv, rec);
+        leaf_record(sc, h.prim, h.face, ro, rd, time, h.t, always_uv, rec);
     }
 #pragma unroll 1
     for (int l = nl - 1; l >= 0; --l) {
@@ -727,8 +726,13 @@ VKD float perlin_turb(const float4* vec, const uint8_t* perm, float3 p, int dept
     return fabsf(accum);
 }
 VKD float clamp_ref(float x, float mn, float mx) { return x < mn ? mn : (x > mx ? mx : x); } // Vec3::clamp keeps NaN
-__device__ __noinline__ float3 tex_value(const DScene& sc, uint32_t ti, float u, float v, float3 p) {
-    uint4 t = __ldg(&sc.textures[ti]);
+__device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p);
+VKD float3 tex_value(const DScene& sc, uint32_t ti, float u, float v, float3 p) {
+    const uint4 t = __ldg(&sc.textures[ti]);
+    if (t.x == VK_TEX_SOLID) return f3(__uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); // SolidColor :238-242
+    return tex_value_general(sc, t, u, v, p);
+}
+__device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p) {
 #pragma unroll 1
     for (int guard = 0; t.x == VK_TEX_CHECKER && guard < 16; ++guard) { // Checker :250-258 (sinf, not __sinf: args ~1e3)
         const float sins = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);

@@ -42,6 +42,7 @@ struct DScene {
     const uint8_t* perlin_perm; // 768 B per Perlin (x, y, z)
     uint32_t root;
     uint32_t n_lights;
+    uint32_t has_media; // scene holds a ConstantMedium: selects the kernel instantiation with the medium code
 };
 #define VKD_MAT_NEEDS_UV 0x80000000u
 
@@ -103,7 +104,7 @@ struct RenderBuffers {
                                   const RenderBuffers& b, int grid, cudaStream_t st);                                  \
     cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk_ray* rays, size_t n,              \
                                  const float* medium_xi, vk_hit* out, cudaStream_t st);                                \
-    cudaError_t megakernel_occupancy(bool flat, int* blocks_per_sm, int* block_threads);                               \
+    cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads);                               \
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
     }
 VK_DECLARE_LAUNCHERS(vkfast)

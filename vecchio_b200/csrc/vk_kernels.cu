@@ -11,8 +11,15 @@ namespace VK_NS {
 #ifndef VK_BLOCK
 #define VK_BLOCK 128
 #endif
-#ifndef VK_MINB
-#define VK_MINB 4 // resident CTAs per SM the register allocation must allow
+// Resident CTAs per SM the register allocation must allow.  Measured on B200 (profiles/): the flat
+// kernel gains 20 % going from 4 (122 regs) to 8 (64 regs, a few spills) -- it is latency bound on
+// dependent ALU chains and indexed constant loads, so more warps win over fewer spills; the BVH
+// kernel is flat between 5 and 8.
+#ifndef VK_MINB_FLAT
+#define VK_MINB_FLAT 8
+#endif
+#ifndef VK_MINB_BVH
+#define VK_MINB_BVH 6
 #endif
 
 // Camera::get_ray (src/main.rs:111-120).  random_in_unit_disk() is always drawn by the reference
@@ -41,7 +48,7 @@ VKD void camera_get_ray(const DCamera& cam, const PathRng& rng, uint32_t x, uint
 // non-finite (the whole sample is then dropped, src/main.rs:191-194).
 VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
                float3& beta, float3& L, bool& valid) {
-    uint4 m = __ldg(&sc.materials[rec.mat]);
+    uint4 m = rec.m;
     uint32_t type = m.x;
     uint32_t spdf_type = type; // whose scattering_pdf applies
     float3 emitted = f3(0.0f, 0.0f, 0.0f);
@@ -116,14 +123,14 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     return true;
 }
 
-template <bool FLAT>
+template <bool FLAT, bool MEDIA>
 VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
                          const RenderBuffers& buf) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_tiles = a.tiles_x * a.tiles_y;
     const uint32_t total = n_tiles * a.n_chunks;
     const size_t plane = (size_t)a.width * a.height * 3u;
-    unsigned long long n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0;
+    uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0; // per lane: far below 2^32 for any frame
 
 #pragma unroll 1
     for (;;) {
@@ -164,8 +171,8 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
                 xi.depth = depth;
                 ++n_rays;
                 TraceCounters tc = {0u, 0u};
-                const TraceHit h = FLAT ? trace_flat(sc, *flat, o, d, time, 0.001f, CUDART_INF_F, xi, tc)
-                                        : trace(sc, o, d, time, 0.001f, CUDART_INF_F, xi, tc); // src/main.rs:130
+                const TraceHit h = FLAT ? trace_flat<MEDIA>(sc, *flat, o, d, time, 0.001f, CUDART_INF_F, xi, tc)
+                                        : trace<MEDIA>(sc, o, d, time, 0.001f, CUDART_INF_F, xi, tc); // src/main.rs:130
                 n_nodes += tc.nodes;
                 n_prims += tc.prims;
                 if (h.prim == VK_REF_NONE) {
@@ -207,28 +214,32 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
         }
         __syncwarp();
     }
+    unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = n_nodes, w_prims = n_prims;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        n_rays += __shfl_xor_sync(0xFFFFFFFFu, n_rays, off);
-        n_drop += __shfl_xor_sync(0xFFFFFFFFu, n_drop, off);
-        n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, off);
-        n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, off);
+        w_rays += __shfl_xor_sync(0xFFFFFFFFu, w_rays, off);
+        w_drop += __shfl_xor_sync(0xFFFFFFFFu, w_drop, off);
+        w_nodes += __shfl_xor_sync(0xFFFFFFFFu, w_nodes, off);
+        w_prims += __shfl_xor_sync(0xFFFFFFFFu, w_prims, off);
     }
     if (lane == 0) {
-        atomicAdd(&buf.counters[3], n_nodes);
-        atomicAdd(&buf.counters[4], n_prims);
-        atomicAdd(&buf.counters[0], n_rays);
-        if (n_drop) atomicAdd(&buf.counters[1], n_drop);
+        atomicAdd(&buf.counters[3], w_nodes);
+        atomicAdd(&buf.counters[4], w_prims);
+        atomicAdd(&buf.counters[0], w_rays);
+        if (w_drop) atomicAdd(&buf.counters[1], w_drop);
     }
 }
 
-__global__ void __launch_bounds__(VK_BLOCK, VK_MINB) k_megakernel(const DScene sc, const DCamera cam, const RenderArgs a,
-                                                         const RenderBuffers buf) {
-    megakernel_body<false>(sc, nullptr, cam, a, buf);
+// four instantiations: {BVH, flat program} x {scene without / with ConstantMedium}
+template <bool MEDIA>
+__global__ void __launch_bounds__(VK_BLOCK, VK_MINB_BVH) k_megakernel(const DScene sc, const DCamera cam, const RenderArgs a,
+                                                                  const RenderBuffers buf) {
+    megakernel_body<false, MEDIA>(sc, nullptr, cam, a, buf);
 }
-__global__ void __launch_bounds__(VK_BLOCK, VK_MINB) k_megakernel_flat(const DScene sc, const __grid_constant__ FlatProgram flat,
-                                                              const DCamera cam, const RenderArgs a, const RenderBuffers buf) {
-    megakernel_body<true>(sc, &flat, cam, a, buf);
+template <bool MEDIA>
+__global__ void __launch_bounds__(VK_BLOCK, VK_MINB_FLAT) k_megakernel_flat(const DScene sc, const __grid_constant__ FlatProgram flat,
+                                                                       const DCamera cam, const RenderArgs a, const RenderBuffers buf) {
+    megakernel_body<true, MEDIA>(sc, &flat, cam, a, buf);
 }
 
 template <bool FLAT>
@@ -246,7 +257,7 @@ VKD void intersect_body(const DScene& sc, const FlatProgram* flat, const vk_ray*
     xi.rng.key = make_uint2(0x243F6A88u, 0x85A308D3u);
     xi.depth = 1;
     TraceCounters tc = {0u, 0u};
-    const TraceHit h = FLAT ? trace_flat(sc, *flat, o, d, r.time, r.tmin, r.tmax, xi, tc) : trace(sc, o, d, r.time, r.tmin, r.tmax, xi, tc);
+    const TraceHit h = FLAT ? trace_flat<true>(sc, *flat, o, d, r.time, r.tmin, r.tmax, xi, tc) : trace<true>(sc, o, d, r.time, r.tmin, r.tmax, xi, tc);
     vk_hit q;
     q.prim = h.prim;
     q.face = 0;
@@ -288,8 +299,13 @@ __global__ void k_philox_kat(const uint32_t* in6, uint32_t* out4) {
 
 cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
                               const RenderBuffers& b, int grid, cudaStream_t st) {
-    if (flat && flat->n) k_megakernel_flat<<<grid, VK_BLOCK, 0, st>>>(sc, *flat, cam, a, b);
-    else k_megakernel<<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
+    if (flat && flat->n) {
+        if (sc.has_media) k_megakernel_flat<true><<<grid, VK_BLOCK, 0, st>>>(sc, *flat, cam, a, b);
+        else k_megakernel_flat<false><<<grid, VK_BLOCK, 0, st>>>(sc, *flat, cam, a, b);
+    } else {
+        if (sc.has_media) k_megakernel<true><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
+        else k_megakernel<false><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk_ray* rays, size_t n, const float* medium_xi,
@@ -300,10 +316,12 @@ cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk
     else k_intersect<<<grid, VK_BLOCK, 0, st>>>(sc, rays, n, medium_xi, out);
     return cudaGetLastError();
 }
-cudaError_t megakernel_occupancy(bool flat, int* blocks_per_sm, int* block_threads) {
+cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads) {
     *block_threads = VK_BLOCK;
-    if (flat) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel_flat, VK_BLOCK, 0);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel, VK_BLOCK, 0);
+    if (flat) return media ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel_flat<true>, VK_BLOCK, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel_flat<false>, VK_BLOCK, 0);
+    return media ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel<true>, VK_BLOCK, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel<false>, VK_BLOCK, 0);
 }
 cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st) {
     k_philox_kat<<<1, 1, 0, st>>>(ctr_key6, out4);
