@@ -169,7 +169,24 @@ def test_hit_parity_fast_math(vb, po, ctx, name, param, width, n):
     print(f"{name}: hit-point error quantiles (99.9 %, max) = {np.quantile(pos_err, 0.999):.2e}, {pos_err.max():.2e} at scene scale {scale:g}")
     assert np.quantile(pos_err, 0.999) <= 1e-5 * scale, (name, np.quantile(pos_err, 0.999), scale)
     assert np.median(rel[ok]) <= 1e-6 and np.quantile(rel[ok], 0.9) <= 1e-5, (name, np.median(rel[ok]), np.quantile(rel[ok], 0.9))
-    assert np.quantile(np.abs(ref["normal"][ok] - got["normal"][ok]).max(axis=1), 0.999) <= 1e-4
+    # Normals.  Flat primitives (rect, box side, medium): the normal is +-e_axis (rotated by an
+    # instance), no dependence on t: 1e-5.  Spheres: normal = (p - c) / r (src/hittable.rs:79), so a
+    # hit-point difference dp moves it by exactly |dp| / |r|; the bound is that propagation of the
+    # (already bounded) hit-point error plus fp32 rounding, not a free tolerance.
+    dn = np.linalg.norm(ref["normal"][ok].astype(np.float64) - got["normal"][ok], axis=1)
+    dp = np.linalg.norm(ref["p"][ok].astype(np.float64) - got["p"][ok], axis=1)
+    ptype = ref["prim"][ok] >> 28
+    radius = np.full(int(ok.sum()), np.inf)
+    is_s = ptype == vb.VK_T_SPHERE
+    radius[is_s] = np.abs(sph[ref["prim"][ok][is_s] & 0x0FFFFFFF, 3])
+    if d.n_mspheres:
+        msr = np.ctypeslib.as_array(C.cast(d.mspheres, C.POINTER(C.c_float)), shape=(d.n_mspheres, 12))[:, 3].astype(np.float64)
+        is_m = ptype == vb.VK_T_MSPHERE
+        radius[is_m] = np.abs(msr[ref["prim"][ok][is_m] & 0x0FFFFFFF])
+    p_mag = np.maximum(1.0, np.abs(ref["p"][ok]).max(axis=1))
+    bound = 1e-5 + (dp + 4e-7 * p_mag) / radius * 2.0
+    print(f"{name}: normal error max {dn.max():.2e} (flat primitives: {dn[~np.isfinite(radius)].max() if (~np.isfinite(radius)).any() else 0:.2e})")
+    assert np.all(dn <= bound), (name, "normal", float((dn / bound).max()))
     assert (ref["front"][ok] != got["front"][ok]).mean() <= 1e-5
 
 

@@ -605,27 +605,33 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     a.background = make_float3(P->background[0], P->background[1], P->background[2]);
     a.tiles_x = (P->width + 7) / 8;
     a.tiles_y = (P->height + 3) / 4;
-    // split the samples into chunks until there are ~12 work items per resident warp (dynamic
-    // scheduling evens out the rest), but keep at least 8 samples per chunk
+    // Sample blocks ("units"): at most 128 planes of partial sums, at least 8 samples per block.
+    // The block size depends only on the sample count of the call, so a render is bit-identical
+    // for a given (seed, spp slice) whatever the grid or the chunking.
+    a.unit_spp = count <= 8 ? count : (count + 127) / 128;
+    if (a.unit_spp < 8 && count > 8) a.unit_spp = 8;
+    a.n_planes = (count + a.unit_spp - 1) / a.unit_spp;
+    // Chunks of whole blocks, sized for ~48 work items per resident warp (small items keep the
+    // end-of-kernel tail short; an item costs one atomic).
     const uint32_t n_tiles = a.tiles_x * a.tiles_y;
-    uint32_t n_chunks = (12u * resident_warps + n_tiles - 1) / n_tiles;
-    const uint32_t max_chunks = count >= 8 ? count / 8 : 1;
-    if (n_chunks > max_chunks) n_chunks = max_chunks;
+    uint32_t n_chunks = (48u * resident_warps + n_tiles - 1) / n_tiles;
+    if (n_chunks > a.n_planes) n_chunks = a.n_planes;
     if (n_chunks < 1) n_chunks = 1;
-    a.chunk_spp = (count + n_chunks - 1) / n_chunks;
+    const uint32_t planes_per_chunk = (a.n_planes + n_chunks - 1) / n_chunks;
+    a.chunk_spp = planes_per_chunk * a.unit_spp;
     a.n_chunks = (count + a.chunk_spp - 1) / a.chunk_spp;
 
     const size_t plane = (size_t)P->width * P->height * 3;
     RenderBuffers b{};
     b.counters = c->counters;
-    if (a.n_chunks == 1) {
+    if (a.n_planes == 1) {
         b.partial_sum = d_sum;
         b.partial_sumsq = d_sumsq;
     } else {
-        int rc = ensure(c, &c->partial, &c->partial_floats, plane * a.n_chunks * (d_sumsq ? 2 : 1));
+        int rc = ensure(c, &c->partial, &c->partial_floats, plane * a.n_planes * (d_sumsq ? 2 : 1));
         if (rc != VK_OK) return rc;
         b.partial_sum = c->partial;
-        b.partial_sumsq = d_sumsq ? c->partial + plane * a.n_chunks : nullptr;
+        b.partial_sumsq = d_sumsq ? c->partial + plane * a.n_planes : nullptr;
     }
     CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // work-queue head only
     CU(c, cudaEventRecord(c->ev0, c->stream));
@@ -633,12 +639,12 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)
                  : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream));
     uint32_t launches = 1;
-    if (a.n_chunks > 1) {
+    if (a.n_planes > 1) {
         const unsigned g = (unsigned)((plane + 255) / 256);
-        k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sum, a.n_chunks, plane, d_sum);
+        k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sum, a.n_planes, plane, d_sum);
         ++launches;
         if (d_sumsq) {
-            k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sumsq, a.n_chunks, plane, d_sumsq);
+            k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sumsq, a.n_planes, plane, d_sumsq);
             ++launches;
         }
         CU(c, cudaGetLastError());

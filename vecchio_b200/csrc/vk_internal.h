@@ -87,13 +87,14 @@ struct RenderArgs {
     uint32_t max_depth;
     uint32_t seed_lo, seed_hi;
     float3 background;
-    // work decomposition (vk_api.cu decides): warp tiles of 32 pixels x sample chunks
-    uint32_t tiles_x, tiles_y, n_chunks, chunk_spp;
+    // work decomposition (vk_api.cu decides): warp items = 8x4 pixel tiles x sample chunks; inside
+    // an item the lanes share (pixel, block of unit_spp samples) units; one partial plane per block
+    uint32_t tiles_x, tiles_y, n_chunks, chunk_spp, unit_spp, n_planes;
 };
 
 // counters[0] = rays, [1] = dropped samples, [2] = work-queue head, [3] = node visits, [4] = primitive tests
 struct RenderBuffers {
-    float* partial_sum;   // n_chunks x W*H*3 (== d_sum when n_chunks == 1)
+    float* partial_sum;   // n_planes x W*H*3 (== d_sum when n_planes == 1)
     float* partial_sumsq; // same, nullable
     unsigned long long* counters;
 };

@@ -123,13 +123,23 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     return true;
 }
 
+// Work decomposition (deterministic for a seed whatever the grid):
+//   item  = one 8x4 pixel tile x one chunk of samples, fetched by a whole warp from a global queue;
+//   unit  = one pixel of the tile x one BLOCK of `unit_spp` consecutive samples.  The 32 lanes of
+//           the warp draw units from a warp-local counter (ballot + popc, no memory traffic): a
+//           lane whose unit is finished takes the next one, so lanes only idle for the last unit
+//           of an item instead of waiting for the slowest pixel of a whole chunk.
+// A unit's samples are summed in order by one lane and stored to its own plane of the partial
+// buffer (plane = global sample-block index); k_reduce_planes adds the planes in order.
 template <bool FLAT, bool MEDIA>
 VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
                          const RenderBuffers& buf) {
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lanes_below = (1u << lane) - 1u;
     const uint32_t n_tiles = a.tiles_x * a.tiles_y;
     const uint32_t total = n_tiles * a.n_chunks;
     const size_t plane = (size_t)a.width * a.height * 3u;
+    const uint32_t spp_end = a.spp_begin + a.spp_count;
     uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0; // per lane: far below 2^32 for any frame
 
 #pragma unroll 1
@@ -139,80 +149,107 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         if (item >= total) break;
         const uint32_t chunk = item / n_tiles, tile = item - chunk * n_tiles;
-        const uint32_t px = (tile % a.tiles_x) * 8u + (lane & 7u);
-        const uint32_t py = (tile / a.tiles_x) * 4u + (lane >> 3);
-        if (px < a.width && py < a.height) {
-            const uint32_t pixel = py * a.width + px; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
-            uint32_t s = a.spp_begin + chunk * a.chunk_spp;
-            const uint32_t s_end = min(s + a.chunk_spp, a.spp_begin + a.spp_count);
-            PathRng rng;
-            rng.pixel = pixel;
-            rng.key = make_uint2(a.seed_lo, a.seed_hi);
-            float3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = f3(0.0f, 0.0f, 0.0f);
-            float3 o, d, beta, L;
-            float time = 0.0f;
-            uint32_t depth = 0;
-            bool alive = false, valid = true;
+        const uint32_t px0 = (tile % a.tiles_x) * 8u, py0 = (tile / a.tiles_x) * 4u;
+        const uint32_t c0 = a.spp_begin + chunk * a.chunk_spp;     // chunk_spp is a multiple of unit_spp
+        const uint32_t c1 = min(c0 + a.chunk_spp, spp_end);
+        const uint32_t n_units = ((c1 - c0 + a.unit_spp - 1u) / a.unit_spp) * 32u;
+        uint32_t next_unit = 0; // warp-uniform
+
+        PathRng rng;
+        rng.pixel = 0;
+        rng.sample = 0;
+        rng.key = make_uint2(a.seed_lo, a.seed_hi);
+        float3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = f3(0.0f, 0.0f, 0.0f);
+        float3 o = f3(0.0f, 0.0f, 0.0f), d = o, beta = o, L = o;
+        float time = 0.0f;
+        uint32_t depth = 0, s = 0, s_end = 0, px = 0, py = 0, unit_plane = 0;
+        bool alive = false, valid = true, has_unit = false;
 #pragma unroll 1
-            for (;;) {
-                if (!alive) { // regenerate: this lane starts its next sample while others keep bouncing
-                    if (s >= s_end) break;
-                    rng.sample = s++;
-                    camera_get_ray(cam, rng, px, py, a.width, a.height, o, d, time);
-                    beta = f3(1.0f, 1.0f, 1.0f);
-                    L = f3(0.0f, 0.0f, 0.0f);
-                    depth = 1; // ray_color(ray, .., 1) src/main.rs:190
-                    valid = true;
-                    alive = true;
+        for (;;) {
+            // ---- unit bookkeeping (warp-synchronous: every lane is here with the full mask) ----
+            const bool need = !alive && !(has_unit && s < s_end);
+            if (need && has_unit) { // unit finished: its sample-block sum goes to its own plane
+                float* ps = buf.partial_sum + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
+                ps[0] = sum.x;
+                ps[1] = sum.y;
+                ps[2] = sum.z;
+                if (buf.partial_sumsq) {
+                    float* pq = buf.partial_sumsq + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
+                    pq[0] = sumsq.x;
+                    pq[1] = sumsq.y;
+                    pq[2] = sumsq.z;
                 }
-                MediumXi xi;
-                xi.table = nullptr;
-                xi.rng = rng;
-                xi.depth = depth;
-                ++n_rays;
-                TraceCounters tc = {0u, 0u};
-                const TraceHit h = FLAT ? trace_flat<MEDIA>(sc, *flat, o, d, time, 0.001f, CUDART_INF_F, xi, tc)
-                                        : trace<MEDIA>(sc, o, d, time, 0.001f, CUDART_INF_F, xi, tc); // src/main.rs:130
-                n_nodes += tc.nodes;
-                n_prims += tc.prims;
-                if (h.prim == VK_REF_NONE) {
-                    L = L + beta * a.background; // src/main.rs:151
-                    alive = false;
-                } else {
-                    HitRecD rec;
-                    resolve_hit(sc, h, o, d, time, false, rec);
-                    alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
-                    if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
-                    // A non-finite ray (refract()'s sqrt of a rounding-negative number, Q7) makes every
-                    // comparison of the reference false: it walks the WHOLE BVH, "hits" whichever Rect
-                    // comes last with t = NaN (Q14) and the sample is then NaN and dropped at
-                    // main.rs:192 (unless that Rect is an emitter).  Drop the sample directly.
-                    if (alive && !(finite3(d) && finite3(o))) {
-                        valid = false;
-                        alive = false;
-                    }
-                }
-                if (!alive) { // sample finished: NaN/Inf filter of src/main.rs:191-194
-                    if (valid && finite3(L)) {
-                        sum = sum + L;
-                        sumsq = sumsq + L * L;
-                    } else {
-                        ++n_drop;
+                has_unit = false;
+            }
+            const uint32_t want = __ballot_sync(0xFFFFFFFFu, need);
+            if (need) {
+                const uint32_t u = next_unit + __popc(want & lanes_below);
+                if (u < n_units) {
+                    px = px0 + (u & 7u);
+                    py = py0 + ((u >> 3) & 3u);
+                    if (px < a.width && py < a.height) { // ragged tiles: a unit outside the image is void
+                        const uint32_t b = u >> 5;
+                        s = c0 + b * a.unit_spp;
+                        s_end = min(s + a.unit_spp, c1);
+                        unit_plane = (s - a.spp_begin) / a.unit_spp;
+                        rng.pixel = py * a.width + px; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
+                        sum = f3(0.0f, 0.0f, 0.0f);
+                        sumsq = f3(0.0f, 0.0f, 0.0f);
+                        has_unit = true;
                     }
                 }
             }
-            float* ps = buf.partial_sum + (size_t)chunk * plane + (size_t)pixel * 3u;
-            ps[0] = sum.x;
-            ps[1] = sum.y;
-            ps[2] = sum.z;
-            if (buf.partial_sumsq) {
-                float* pq = buf.partial_sumsq + (size_t)chunk * plane + (size_t)pixel * 3u;
-                pq[0] = sumsq.x;
-                pq[1] = sumsq.y;
-                pq[2] = sumsq.z;
+            next_unit += __popc(want);
+            const bool work = alive || (has_unit && s < s_end);
+            if (__ballot_sync(0xFFFFFFFFu, work || (need && next_unit < n_units)) == 0u) break;
+            if (!work) continue;
+
+            // ---- one path segment ---------------------------------------------------------------
+            if (!alive) { // regenerate: this lane starts its next sample while others keep bouncing
+                rng.sample = s++;
+                camera_get_ray(cam, rng, px, py, a.width, a.height, o, d, time);
+                beta = f3(1.0f, 1.0f, 1.0f);
+                L = f3(0.0f, 0.0f, 0.0f);
+                depth = 1; // ray_color(ray, .., 1) src/main.rs:190
+                valid = true;
+                alive = true;
+            }
+            MediumXi xi;
+            xi.table = nullptr;
+            xi.rng = rng;
+            xi.depth = depth;
+            ++n_rays;
+            TraceCounters tc = {0u, 0u};
+            const TraceHit h = FLAT ? trace_flat<MEDIA>(sc, *flat, o, d, time, 0.001f, CUDART_INF_F, xi, tc)
+                                    : trace<MEDIA>(sc, o, d, time, 0.001f, CUDART_INF_F, xi, tc); // src/main.rs:130
+            n_nodes += tc.nodes;
+            n_prims += tc.prims;
+            if (h.prim == VK_REF_NONE) {
+                L = L + beta * a.background; // src/main.rs:151
+                alive = false;
+            } else {
+                HitRecD rec;
+                resolve_hit(sc, h, o, d, time, false, rec);
+                alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
+                if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
+                // A non-finite ray (refract()'s sqrt of a rounding-negative number, Q7) makes every
+                // comparison of the reference false: it walks the WHOLE BVH, "hits" whichever Rect
+                // comes last with t = NaN (Q14) and the sample is then NaN and dropped at
+                // main.rs:192 (unless that Rect is an emitter).  Drop the sample directly.
+                if (alive && !(finite3(d) && finite3(o))) {
+                    valid = false;
+                    alive = false;
+                }
+            }
+            if (!alive) { // sample finished: NaN/Inf filter of src/main.rs:191-194
+                if (valid && finite3(L)) {
+                    sum = sum + L;
+                    sumsq = sumsq + L * L;
+                } else {
+                    ++n_drop;
+                }
             }
         }
-        __syncwarp();
     }
     unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = n_nodes, w_prims = n_prims;
 #pragma unroll
