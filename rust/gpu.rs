@@ -1,0 +1,192 @@
+//! gpu.rs -- the `gpu` module a vecchio maintainer would add next to src/main.rs to call the
+//! B200 library (include/vecchio_gpu.h, libvecchio_gpu.so) instead of the rayon sample loop.
+//!
+//! STATUS: SOURCE ONLY.  This image has no rustc/cargo, so this file has never been compiled or
+//! run; the C ABI it binds is exercised by the Python ctypes harness and the C++ front end
+//! instead (tests/, vecchio_b200/host/).  See INTEGRATION.md for the three edits to the reference
+//! (mod gpu; one `lower()` method per trait; the call in main()).
+//!
+//! Layouts mirror include/vecchio_gpu.h field by field (`#[repr(C)]`); Vec3/Camera/Ray of the
+//! reference are NOT repr(C) (src/vec3.rs:3-8, src/main.rs:31-36,56-68) and are copied.
+#![allow(non_camel_case_types, dead_code)]
+
+use std::collections::HashMap;
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+pub type vk_ref = u32; // (type << 28) | index ; 0 == none
+pub const VK_API_VERSION: u32 = 1;
+pub const VK_T_NODE: u32 = 1;
+pub const VK_T_SPHERE: u32 = 2;
+pub const VK_T_MSPHERE: u32 = 3;
+pub const VK_T_RECT: u32 = 4;
+pub const VK_T_BOX: u32 = 5;
+pub const VK_T_XFORM: u32 = 6;
+pub const VK_T_MEDIUM: u32 = 7;
+pub const VK_RECT_FLIP: u32 = 0x100;
+pub const fn vk_mkref(t: u32, i: u32) -> vk_ref { (t << 28) | (i & 0x0FFF_FFFF) }
+
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_node { pub bb_min: [f32; 3], pub left: vk_ref, pub bb_max: [f32; 3], pub right: vk_ref }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_sphere { pub center: [f32; 3], pub radius: f32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_msphere { pub center0: [f32; 3], pub radius: f32, pub center1: [f32; 3], pub time0: f32, pub time1: f32, pub mat: u32, pub _pad: [u32; 2] }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_rect { pub c0: f32, pub c1: f32, pub d0: f32, pub d1: f32, pub k: f32, pub axes: u32, pub mat: u32, pub _pad: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_box { pub box_min: [f32; 3], pub mat: u32, pub box_max: [f32; 3], pub _pad: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_xform { pub kind: u32, pub child: vk_ref, pub _pad0: [u32; 2], pub a: f32, pub b: f32, pub c: f32, pub _pad1: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_medium { pub boundary: vk_ref, pub neg_inv_density: f32, pub mat: u32, pub _pad: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_material { pub type_: u32, pub tex: u32, pub param: f32, pub aux: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_texture { pub type_: u32, pub w: [u32; 3] } // union payload as 3 words (f32::to_bits for SOLID)
+#[repr(C)] #[derive(Clone, Copy)] pub struct vk_perlin { pub ranvec: [[f32; 3]; 256], pub perm_x: [u8; 256], pub perm_y: [u8; 256], pub perm_z: [u8; 256] }
+
+#[repr(C)]
+pub struct vk_scene_desc {
+    pub api_version: u32, pub root: vk_ref,
+    pub nodes: *const vk_node, pub n_nodes: u32,
+    pub spheres: *const vk_sphere, pub sphere_mat: *const u32, pub n_spheres: u32,
+    pub mspheres: *const vk_msphere, pub n_mspheres: u32,
+    pub rects: *const vk_rect, pub n_rects: u32,
+    pub boxes: *const vk_box, pub n_boxes: u32,
+    pub xforms: *const vk_xform, pub n_xforms: u32,
+    pub media: *const vk_medium, pub n_media: u32,
+    pub lights: *const vk_ref, pub n_lights: u32,
+    pub materials: *const vk_material, pub n_materials: u32,
+    pub textures: *const vk_texture, pub n_textures: u32,
+    pub texels: *const u8, pub n_texel_bytes: u64,
+    pub perlins: *const vk_perlin, pub n_perlins: u32,
+}
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct vk_camera { pub origin: [f32; 3], pub lower_left_corner: [f32; 3], pub horizontal: [f32; 3], pub vertical: [f32; 3],
+                       pub u: [f32; 3], pub v: [f32; 3], pub w: [f32; 3], pub lens_radius: f32, pub time0: f32, pub time1: f32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct vk_render_params { pub width: u32, pub height: u32, pub spp: u32, pub spp_begin: u32, pub spp_count: u32, pub max_depth: u32,
+                              pub seed: u64, pub background: [f32; 3], pub variant: u32, pub flags: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct vk_stats { pub paths: u64, pub rays: u64, pub dropped_samples: u64, pub ms_kernels: f32, pub ms_total: f32,
+                      pub variant: u32, pub launches: u32, pub node_visits: u64, pub prim_tests: u64 }
+#[repr(C)] pub struct vk_ctx { _private: [u8; 0] }
+
+#[link(name = "vecchio_gpu")]
+extern "C" {
+    pub fn vk_create(device: c_int, out: *mut *mut vk_ctx) -> c_int;
+    pub fn vk_destroy(ctx: *mut vk_ctx);
+    pub fn vk_last_error(ctx: *const vk_ctx) -> *const c_char;
+    pub fn vk_scene_upload(ctx: *mut vk_ctx, scene: *const vk_scene_desc) -> c_int;
+    pub fn vk_render(ctx: *mut vk_ctx, cam: *const vk_camera, params: *const vk_render_params,
+                     out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut vk_stats) -> c_int;
+    pub fn vk_render_device(ctx: *mut vk_ctx, cam: *const vk_camera, params: *const vk_render_params,
+                            d_sum: *mut f32, d_sumsq: *mut f32, stats: *mut vk_stats) -> c_int;
+    pub fn vk_finalize_device(ctx: *mut vk_ctx, d_sum: *const f32, d_rgb: *mut f32, n_floats: usize, spp: u32) -> c_int;
+    pub fn vk_set_stream(ctx: *mut vk_ctx, stream: *mut c_void) -> c_int;
+    pub fn vk_flush_stats(ctx: *mut vk_ctx, stats: *mut vk_stats) -> c_int;
+}
+
+#[derive(Debug)]
+pub enum GpuError { Unsupported(&'static str), Library(i32, String) }
+
+/// Accumulates the flat arrays while the object graph is walked.  Shared `Arc`s are lowered once
+/// (keyed by pointer), so the 400 boxes that share one material produce one material record.
+#[derive(Default)]
+pub struct Lowering {
+    pub nodes: Vec<vk_node>, pub spheres: Vec<vk_sphere>, pub sphere_mat: Vec<u32>, pub mspheres: Vec<vk_msphere>,
+    pub rects: Vec<vk_rect>, pub boxes: Vec<vk_box>, pub xforms: Vec<vk_xform>, pub media: Vec<vk_medium>,
+    pub lights: Vec<vk_ref>, pub materials: Vec<vk_material>, pub textures: Vec<vk_texture>, pub texels: Vec<u8>,
+    pub perlins: Vec<vk_perlin>,
+    pub memo: HashMap<usize, u32>, // Arc::as_ptr(..) as *const () as usize -> record index / ref
+}
+
+/// The ONE method added to each of the reference's traits (they are otherwise opaque: no `Any`,
+/// private fields).  The default reports the type as unsupported, so a user-defined Hittable makes
+/// `render` fail loudly instead of being skipped:
+///
+/// ```ignore
+/// // src/hittable.rs:33-42
+/// pub trait Hittable { /* hit, bounding_box, pdf_value, random as before */
+///     fn lower(&self, _b: &mut gpu::Lowering) -> Result<gpu::vk_ref, gpu::GpuError> {
+///         Err(gpu::GpuError::Unsupported("Hittable"))
+///     }
+/// }
+/// impl Hittable for Sphere {                      // src/hittable.rs:63
+///     fn lower(&self, b: &mut gpu::Lowering) -> Result<gpu::vk_ref, gpu::GpuError> {
+///         let mat = self.material.lower(b)?;      // Material::lower -> index into b.materials
+///         b.spheres.push(gpu::vk_sphere { center: self.center.into(), radius: self.radius });
+///         b.sphere_mat.push(mat);
+///         Ok(gpu::vk_mkref(gpu::VK_T_SPHERE, (b.spheres.len() - 1) as u32))
+///     }
+/// }
+/// impl Hittable for BVHNode {                     // src/accel.rs:58
+///     fn lower(&self, b: &mut gpu::Lowering) -> Result<gpu::vk_ref, gpu::GpuError> {
+///         let i = b.nodes.len();                  // depth first, parent before children, left first
+///         b.nodes.push(Default::default());
+///         let left = self.left.lower(b)?;
+///         let right = if Arc::ptr_eq(&self.left, &self.right) { left } else { self.right.lower(b)? };
+///         b.nodes[i] = gpu::vk_node { bb_min: self.bb.min.into(), left, bb_max: self.bb.max.into(), right };
+///         Ok(gpu::vk_mkref(gpu::VK_T_NODE, i as u32))
+///     }
+/// }
+/// // FlipFace(Rect) sets VK_RECT_FLIP on a copy of the rect record; FlipFace of anything else,
+/// // Translate and RotateX/Y/Z push one vk_xform {kind, child, a, b, c} (offset | sin, cos);
+/// // Boxy pushes one vk_box; ConstantMedium one vk_medium {boundary.lower()?, -1/density, phase};
+/// // Material::lower / Texture::lower push the tagged 16-byte records of vecchio_gpu.h.
+/// ```
+pub trait LowerDoc {}
+
+impl Lowering {
+    pub fn desc(&self, root: vk_ref) -> vk_scene_desc {
+        vk_scene_desc {
+            api_version: VK_API_VERSION, root,
+            nodes: self.nodes.as_ptr(), n_nodes: self.nodes.len() as u32,
+            spheres: self.spheres.as_ptr(), sphere_mat: self.sphere_mat.as_ptr(), n_spheres: self.spheres.len() as u32,
+            mspheres: self.mspheres.as_ptr(), n_mspheres: self.mspheres.len() as u32,
+            rects: self.rects.as_ptr(), n_rects: self.rects.len() as u32,
+            boxes: self.boxes.as_ptr(), n_boxes: self.boxes.len() as u32,
+            xforms: self.xforms.as_ptr(), n_xforms: self.xforms.len() as u32,
+            media: self.media.as_ptr(), n_media: self.media.len() as u32,
+            lights: self.lights.as_ptr(), n_lights: self.lights.len() as u32,
+            materials: self.materials.as_ptr(), n_materials: self.materials.len() as u32,
+            textures: self.textures.as_ptr(), n_textures: self.textures.len() as u32,
+            texels: self.texels.as_ptr(), n_texel_bytes: self.texels.len() as u64,
+            perlins: self.perlins.as_ptr(), n_perlins: self.perlins.len() as u32,
+        }
+    }
+}
+
+/// One GPU context; owns the device scene between frames (the 671-frame turntable of
+/// random_spheres_demo uploads once and renders per camera).
+pub struct Gpu { ctx: *mut vk_ctx }
+
+impl Gpu {
+    pub fn new(device: i32) -> Result<Gpu, GpuError> {
+        let mut ctx = std::ptr::null_mut();
+        let rc = unsafe { vk_create(device, &mut ctx) };
+        if rc != 0 { return Err(GpuError::Library(rc, last_error(std::ptr::null()))); }
+        Ok(Gpu { ctx })
+    }
+    fn check(&self, rc: c_int) -> Result<(), GpuError> {
+        if rc == 0 { Ok(()) } else { Err(GpuError::Library(rc, last_error(self.ctx))) }
+    }
+    /// `world` is `Arc<BVHNode>` of src/main.rs:168, `lights` the Vec of :169 -- via their `lower()`.
+    pub fn upload(&mut self, low: &Lowering, root: vk_ref) -> Result<(), GpuError> {
+        let d = low.desc(root);
+        self.check(unsafe { vk_scene_upload(self.ctx, &d) })
+    }
+    /// Replaces the body of src/main.rs:181-198.  Returns W*H*3 floats, pixel i = y*W + x, row 0 =
+    /// bottom, linear mean over `spp` -- the layout of `pixels: Vec<Vec3>`.
+    pub fn render(&mut self, cam: &vk_camera, width: usize, height: usize, spp: u32, max_depth: u32, seed: u64)
+                  -> Result<(Vec<f32>, vk_stats), GpuError> {
+        let p = vk_render_params { width: width as u32, height: height as u32, spp, spp_begin: 0, spp_count: 0, max_depth, seed,
+                                   background: [0.0; 3], variant: 0, flags: 0 };
+        let mut out = vec![0f32; width * height * 3];
+        let mut st = vk_stats::default();
+        self.check(unsafe { vk_render(self.ctx, cam, &p, out.as_mut_ptr(), std::ptr::null_mut(), &mut st) })?;
+        Ok((out, st))
+    }
+}
+impl Drop for Gpu { fn drop(&mut self) { unsafe { vk_destroy(self.ctx) } } }
+
+fn last_error(ctx: *const vk_ctx) -> String {
+    unsafe { let p = vk_last_error(ctx); if p.is_null() { String::new() } else { CStr::from_ptr(p).to_string_lossy().into_owned() } }
+}
+
+// Camera -> vk_camera: the ten fields of src/main.rs:56-68 in declaration order (a `lower()` on
+// Camera inside main.rs, because its fields are private):
+//   vk_camera { origin: self.origin.into(), lower_left_corner: .., horizontal: .., vertical: ..,
+//               u: .., v: .., w: .., lens_radius: self.lens_radius, time0: self.time0, time1: self.time1 }
