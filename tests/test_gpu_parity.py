@@ -346,3 +346,69 @@ def test_full_size_cornell_properties(vb, ctx):
     # linearity in spp slices: the first half's mean equals the whole within noise
     half, _, _ = ctx.render(cam, vb.render_params(600, 600, 500, 100, seed=1))
     assert abs(half.mean() - rgb.mean()) <= 0.005 * rgb.mean()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Wavefront variant (generate -> extend -> material-sorted shade -> accumulate as separate kernels)
+# ---------------------------------------------------------------------------------------------------
+WF_SCENES = [("cornell_box", 0, 96, 64, 100), ("cornell_smoke", 0, 64, 64, 100), ("final_scene", 0, 64, 32, 100),
+             ("random_spheres_demo", 0, 96, 32, 50), ("bowser_demo", 0, 64, 32, 50)]
+
+
+@pytest.mark.parametrize("name,param,W,spp,depth", WF_SCENES, ids=[s[0] for s in WF_SCENES])
+def test_wavefront_equals_megakernel(vb, ctx, name, param, W, spp, depth):
+    """Both variants own (pixel, sample block) units, sum a unit's samples in order and key Philox by
+    (pixel, global sample, bounce): with the strict build (no FMA contraction, so the shared device
+    functions round identically in both kernels) the images are bit-identical, and so are the
+    segment and dropped-sample counts.  The fast build agrees to fp32 rounding."""
+    scene, cam = get_scene(vb, name, param=param)
+    H = scene.height_for(W)
+    ctx.upload(scene)
+    for flags, exact in ((vb.VK_FLAG_STRICT_MATH, True), (0, False)):
+        pm = vb.render_params(W, H, spp, depth, seed=31, variant=vb.VK_VARIANT_MEGAKERNEL, flags=flags)
+        pw = vb.render_params(W, H, spp, depth, seed=31, variant=vb.VK_VARIANT_WAVEFRONT, flags=flags)
+        a, qa, sa = ctx.render(cam, pm, want_sumsq=True)
+        b, qb, sb = ctx.render(cam, pw, want_sumsq=True)
+        assert sb.variant == vb.VK_VARIANT_WAVEFRONT and sa.variant == vb.VK_VARIANT_MEGAKERNEL
+        assert sb.launches > 3 and sa.paths == sb.paths
+        if exact:
+            assert np.array_equal(a, b) and np.array_equal(qa, qb), (name, np.abs(a - b).max())
+            assert (sa.rays, sa.dropped_samples) == (sb.rays, sb.dropped_samples)
+        else:
+            # contraction differs between the two kernels: a path can take another branch at a rounding
+            # boundary, so compare statistically tight instead of bitwise
+            assert abs(sa.rays - sb.rays) <= 2e-3 * sa.rays
+            close = np.isclose(a, b, rtol=1e-3, atol=1e-5)
+            assert close.mean() >= 0.99, (name, close.mean())
+            assert abs(a.mean() - b.mean()) <= 2e-3 * a.mean()
+
+
+def test_wavefront_image_parity_with_oracle(vb, po, ctx):
+    scene, cam = get_scene(vb, "cornell_box")
+    o = po.OracleScene(scene)
+    ctx.upload(scene)
+    W, spp = 80, 512
+    ro, qo, so = o.render(cam, vb.render_params(W, W, spp, 100, seed=41), want_sumsq=True)
+    rg, qg, sg = ctx.render(cam, vb.render_params(W, W, spp, 100, seed=42, variant=vb.VK_VARIANT_WAVEFRONT), want_sumsq=True)
+    assert sg.variant == vb.VK_VARIANT_WAVEFRONT
+    z, nz, diff, se = zscores(rg, qg, spp, ro, qo, spp)
+    frac = (np.abs(z[nz]) <= 3.0).mean()
+    print(f"wavefront cornell: {frac:.4f} within 3 sigma, mean z {z[nz].mean():+.3f}")
+    assert frac >= 0.985 and abs(z[nz].mean()) <= 0.1
+    assert abs(sg.rays / sg.paths - so.rays_live / so.paths) <= 0.02 * so.rays_live / so.paths
+
+
+def test_wavefront_edge_cases(vb, ctx):
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    wf = vb.VK_VARIANT_WAVEFRONT
+    # fewer units than pool slots, ragged image, spp not a multiple of the sample block, depth 1
+    rgb, _, st = ctx.render(cam, vb.render_params(61, 37, 13, 100, seed=1, variant=wf))
+    ref, _, sr = ctx.render(cam, vb.render_params(61, 37, 13, 100, seed=1, variant=vb.VK_VARIANT_MEGAKERNEL))
+    assert rgb.shape == (37, 61, 3) and st.paths == 61 * 37 * 13 and abs(rgb.mean() - ref.mean()) <= 5e-3 * ref.mean()
+    rgb, _, st = ctx.render(cam, vb.render_params(64, 64, 16, 1, seed=1, variant=wf))
+    assert st.rays == st.paths and rgb.max() == 15.0 and rgb.min() == 0.0
+    # an spp slice (the multi-GPU unit of work) through the wavefront
+    a, _, _ = ctx.render(cam, vb.render_params(64, 64, 32, 100, seed=3, variant=wf, flags=vb.VK_FLAG_STRICT_MATH))
+    b, _, _ = ctx.render(cam, vb.render_params(64, 64, 32, 100, seed=3, flags=vb.VK_FLAG_STRICT_MATH))
+    assert np.array_equal(a, b)

@@ -2,6 +2,7 @@
 // GPU-side re-layout), render orchestration, the parity hook and the roofline microbenchmarks.
 // No CPU fallback anywhere: every entry point either runs CUDA kernels or returns an error.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -31,6 +32,12 @@ struct vk_ctx {
     size_t frame_floats = 0;
     float* pinned = nullptr; // pinned host staging for the D2H of vk_render
     size_t pinned_floats = 0;
+    // wavefront variant: the slot pool (allocated on first use) and a pinned word block for the
+    // host's termination checks
+    WfState wf{};
+    void* wf_block = nullptr;
+    bool wf_has_sumsq = false;
+    uint32_t* wf_host_counts = nullptr;
 };
 
 static thread_local std::string g_create_err;
@@ -457,6 +464,8 @@ void vk_destroy(vk_ctx* c) {
     cudaSetDevice(c->device);
     free_scene(c);
     if (c->partial) cudaFree(c->partial);
+    if (c->wf_block) cudaFree(c->wf_block);
+    if (c->wf_host_counts) cudaFreeHost(c->wf_host_counts);
     if (c->frame) cudaFree(c->frame);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->counters) cudaFree(c->counters);
@@ -571,6 +580,87 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
 
 extern "C" int vk_flush_stats(vk_ctx* c, vk_stats* stats);
 
+// Slot pool of the wavefront variant.  One allocation, carved into the arrays of WfState.  Default
+// 2^19 slots: 96 B (112 B with sum of squares) per slot = 50 MB, resident in the 126 MB L2, and
+// 3-4 full waves of 256-thread CTAs per launch.  VECCHIO_WF_SLOTS overrides (tuning sweeps).
+static int wf_ensure(vk_ctx* c, bool want_sumsq) {
+    uint32_t n = 1u << 19;
+    if (const char* e = std::getenv("VECCHIO_WF_SLOTS")) {
+        const long v = std::atol(e);
+        if (v >= 1024 && v <= (1l << 26)) n = (uint32_t)v;
+    }
+    n = (n + 255u) & ~255u;
+    if (c->wf_block && c->wf.n_slots == n && (c->wf_has_sumsq || !want_sumsq)) return VK_OK;
+    if (c->wf_block) cudaFree(c->wf_block);
+    c->wf_block = nullptr;
+    c->wf = WfState{};
+    const size_t per_slot = 16 * (6 + (want_sumsq ? 1 : 0)) + 4 * VKW_CLASSES;
+    const size_t tail = 256; // qcount (2 sets) + unit_head
+    CU(c, cudaMalloc(&c->wf_block, per_slot * n + tail));
+    char* p = (char*)c->wf_block;
+    auto take = [&](size_t bytes) { char* q = p; p += bytes; return q; };
+    c->wf.ray_o = (float4*)take(16ull * n);
+    c->wf.ray_d = (float4*)take(16ull * n);
+    c->wf.beta = (float4*)take(16ull * n);
+    c->wf.unit = (uint4*)take(16ull * n);
+    c->wf.sum = (float4*)take(16ull * n);
+    c->wf.hit = (uint4*)take(16ull * n);
+    c->wf.sumsq = want_sumsq ? (float4*)take(16ull * n) : nullptr;
+    c->wf.queue = (uint32_t*)take(4ull * VKW_CLASSES * n);
+    c->wf.qcount = (uint32_t*)take(64);
+    c->wf.unit_head = (unsigned long long*)take(64);
+    c->wf.n_slots = n;
+    c->wf_has_sumsq = want_sumsq;
+    if (!c->wf_host_counts) CU(c, cudaMallocHost((void**)&c->wf_host_counts, 64));
+    return VK_OK;
+}
+
+// generate -> (extend -> shade)* until the pool has drained.  The host cannot see the pool, so it
+// launches iterations in batches and reads the queue counters of the last extend after each batch
+// (one 32-byte D2H + stream sync); an iteration on a drained pool is two empty launches.
+static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCamera& dc, const RenderArgs& a, const RenderBuffers& b,
+                     bool want_sumsq, uint32_t* launches) {
+    int rc = wf_ensure(c, want_sumsq);
+    if (rc != VK_OK) return rc;
+    WfState w = c->wf;
+    if (!want_sumsq) w.sumsq = nullptr;
+    w.n_pixels = a.width * a.height;
+    w.n_units = (unsigned long long)w.n_pixels * a.n_planes;
+    const unsigned long long head0 = w.n_units < w.n_slots ? w.n_units : w.n_slots;
+    CU(c, cudaMemsetAsync(w.qcount, 0, 64, c->stream));
+    CU(c, cudaMemcpyAsync(w.unit_head, &head0, sizeof(head0), cudaMemcpyHostToDevice, c->stream));
+    CU(c, strict ? vkstrict::launch_wf_generate(dc, a, w, c->stream) : vkfast::launch_wf_generate(dc, a, w, c->stream));
+    ++*launches;
+    // no sample ends before its first segment: at least spp_count * n_pixels / n_slots iterations
+    const unsigned long long min_iters = ((unsigned long long)w.n_pixels * a.spp_count + w.n_slots - 1) / w.n_slots;
+    unsigned long long next_check = min_iters > 8 ? min_iters : 8;
+    for (unsigned long long it = 0;; ++it) {
+        const uint32_t set = (uint32_t)(it & 1u);
+        CU(c, strict ? vkstrict::launch_wf_extend(c->scene, flat, a, w, b, set, c->stream)
+                     : vkfast::launch_wf_extend(c->scene, flat, a, w, b, set, c->stream));
+        CU(c, strict ? vkstrict::launch_wf_shade(c->scene, dc, a, w, b, set, c->stream)
+                     : vkfast::launch_wf_shade(c->scene, dc, a, w, b, set, c->stream));
+        *launches += 2;
+        if (it + 1 >= next_check) {
+            CU(c, cudaMemcpyAsync(c->wf_host_counts, w.qcount + set * VKW_CLASSES, VKW_CLASSES * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            const uint32_t live = c->wf_host_counts[0] + c->wf_host_counts[1] + c->wf_host_counts[2] + c->wf_host_counts[3];
+            if (live == 0) break;
+            // the pool is still busy: look again after about a quarter of what is left at most, at least 8 iterations
+            next_check = it + 1 + (live == w.n_slots ? 32 : 8);
+        }
+    }
+    return VK_OK;
+}
+
+
+// VK_VARIANT_AUTO: the megakernel.  Evidence (profiles/): on every config the
+// persistent megakernel is ahead of the wavefront kernels on B200 -- the scenes are cache resident,
+// so the wavefront's queue traffic and launch boundaries buy coherence the megakernel already has.
+static uint32_t choose_variant(const vk_ctx*, const vk_render_params* P) {
+    return P->variant == VK_VARIANT_WAVEFRONT ? VK_VARIANT_WAVEFRONT : VK_VARIANT_MEGAKERNEL;
+}
+
 // shared body of vk_render / vk_render_device
 static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* d_sum, float* d_sumsq, vk_stats* stats) {
     if (!c) return VK_ERR_INVALID;
@@ -581,7 +671,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     const uint32_t count = P->spp_count ? P->spp_count : P->spp - P->spp_begin;
     if ((uint64_t)P->spp_begin + count > P->spp) return fail(c, VK_ERR_INVALID, "render: sample slice exceeds spp");
     if ((uint64_t)P->width * P->height > 0x7FFFFFFFull / 3) return fail(c, VK_ERR_INVALID, "render: image too large");
-    if (P->variant == VK_VARIANT_WAVEFRONT) return fail(c, VK_ERR_UNSUPPORTED, "render: wavefront variant not built yet");
+    if (P->variant > VK_VARIANT_WAVEFRONT) return fail(c, VK_ERR_INVALID, "render: unknown variant");
     if (!(cam->time0 < cam->time1)) return fail(c, VK_ERR_INVALID, "render: camera time0 >= time1 (gen_range panics, src/main.rs:118)");
     CU(c, cudaSetDevice(c->device));
     const bool strict = (P->flags & VK_FLAG_STRICT_MATH) != 0;
@@ -636,9 +726,16 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // work-queue head only
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
-    CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)
-                 : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream));
-    uint32_t launches = 1;
+    uint32_t launches = 0;
+    const uint32_t variant = choose_variant(c, P);
+    if (variant == VK_VARIANT_WAVEFRONT) {
+        int rc = wf_render(c, strict, flat, dc, a, b, d_sumsq != nullptr, &launches);
+        if (rc != VK_OK) return rc;
+    } else {
+        CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)
+                     : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream));
+        launches = 1;
+    }
     if (a.n_planes > 1) {
         const unsigned g = (unsigned)((plane + 255) / 256);
         k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sum, a.n_planes, plane, d_sum);
@@ -657,7 +754,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         if (rc != VK_OK) return rc;
         CU(c, cudaEventElapsedTime(&stats->ms_kernels, c->ev0, c->ev1));
         stats->ms_total = stats->ms_kernels;
-        stats->variant = VK_VARIANT_MEGAKERNEL;
+        stats->variant = variant;
     }
     return VK_OK;
 }

@@ -297,7 +297,7 @@ VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float3 inv_d
 
 // ConstantMedium::hit (src/hittable.rs:453-493).  The boundary is a leaf, possibly behind a wrapper
 // chain (t is invariant under the chain).
-__device__ __noinline__ bool medium_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax,
+static __device__ __noinline__ bool medium_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax,
                                       const MediumXi& xi, float& t) {
     const float4 m = __ldg(&sc.media[VKD_INDEX(ref)]);
     float3 bo = o, bd = d;
@@ -726,13 +726,13 @@ VKD float perlin_turb(const float4* vec, const uint8_t* perm, float3 p, int dept
     return fabsf(accum);
 }
 VKD float clamp_ref(float x, float mn, float mx) { return x < mn ? mn : (x > mx ? mx : x); } // Vec3::clamp keeps NaN
-__device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p);
+static __device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p);
 VKD float3 tex_value(const DScene& sc, uint32_t ti, float u, float v, float3 p) {
     const uint4 t = __ldg(&sc.textures[ti]);
     if (t.x == VK_TEX_SOLID) return f3(__uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); // SolidColor :238-242
     return tex_value_general(sc, t, u, v, p);
 }
-__device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p) {
+static __device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p) {
 #pragma unroll 1
     for (int guard = 0; t.x == VK_TEX_CHECKER && guard < 16; ++guard) { // Checker :250-258 (sinf, not __sinf: args ~1e3)
         const float sins = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
@@ -903,6 +903,111 @@ VKD float lights_pdf_value(const DScene& sc, float3 o, float3 v) {
 #pragma unroll 1
     for (uint32_t l = 0; l < sc.n_lights; ++l) sum += weight * light_pdf_value(sc, __ldg(&sc.lights[l]), o, v);
     return sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The integrator's two per-sample pieces, shared by the megakernel (vk_kernels.cu) and the
+// wavefront kernels (vk_wavefront.cu): camera ray generation and one bounce of ray_color.
+// ---------------------------------------------------------------------------------------------
+// Camera::get_ray (src/main.rs:111-120).  random_in_unit_disk() is always drawn by the reference
+// and multiplied by lens_radius; with lens_radius == 0 the product is exactly 0, so the draw is
+// skipped.  The disk sample is direct (sqrt-radius) instead of the rejection loop: same law.
+VKD void camera_get_ray(const DCamera& cam, const PathRng& rng, uint32_t x, uint32_t y, uint32_t width, uint32_t height,
+                        float3& o, float3& d, float& time) {
+    const uint4 r = rng.block(0u, 0u);
+    const float s = ((float)x + u01(r.x)) / (float)(width - 1);  // src/main.rs:187
+    const float t = ((float)y + u01(r.y)) / (float)(height - 1); // src/main.rs:188
+    float3 offset = f3(0.0f, 0.0f, 0.0f);
+    if (cam.lens_radius != 0.0f) {
+        const uint4 q = rng.block(0u, 1u);
+        const float rad = sqrtf(u01(q.x)) * cam.lens_radius;
+        float sn, cs;
+        __sincosf(2.0f * VK_PI * u01(q.y), &sn, &cs);
+        offset = cam.u * (rad * cs) + cam.v * (rad * sn);
+    }
+    o = cam.origin + offset;
+    d = cam.lower_left_corner + cam.horizontal * s + cam.vertical * t - cam.origin - offset;
+    time = gen_range(r.z, cam.time0, cam.time1);
+}
+
+// One bounce of ray_color's loop body after world.hit() returned `rec` (src/main.rs:131-149).
+// Returns false when the path ends.  `valid` is cleared when the reference's value would be
+// non-finite (the whole sample is then dropped, src/main.rs:191-194).
+VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
+               float3& beta, float3& L, bool& valid) {
+    uint4 m = rec.m;
+    uint32_t type = m.x;
+    uint32_t spdf_type = type; // whose scattering_pdf applies
+    float3 emitted = f3(0.0f, 0.0f, 0.0f);
+    if (type == VK_M_SPECDIFFUSE) { // src/material.rs:474-488: emitted() is the trait default (0)
+        const uint4 q = rng.block(depth, 9u);
+        const uint32_t diffuse = m.w & ~VKD_MAT_NEEDS_UV;
+        spdf_type = __ldg(&sc.materials[diffuse]).x;
+        m = __ldg(&sc.materials[u01(q.x) < __uint_as_float(m.z) ? m.y : diffuse]);
+        type = m.x;
+    } else if (type == VK_M_DIFFUSE_LIGHT) { // src/material.rs:218-225; scatter_with_pdf -> None
+        if (rec.front) emitted = tex_value(sc, m.y, rec.u, rec.v, rec.p);
+    }
+    if (type == VK_M_DIFFUSE_LIGHT) { // src/main.rs:147-149
+        L = L + beta * emitted;
+        return false;
+    }
+    const uint4 r = rng.block(depth, 0u);
+    if (type == VK_M_DIELECTRIC) { // src/material.rs:177-206, attenuation (1,1,1)
+        const float ref_idx = __uint_as_float(m.z);
+        const float etai_over_etat = rec.front ? 1.0f / ref_idx : ref_idx;
+        const float3 unit_direction = unit_vector(d);
+        const float cos_theta = fminf(dot3(-unit_direction, rec.normal), 1.0f);
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        float3 nd;
+        if (etai_over_etat * sin_theta > 1.0f) nd = reflect(unit_direction, rec.normal);
+        else if (u01(r.x) < schlick(cos_theta, etai_over_etat)) nd = reflect(unit_direction, rec.normal);
+        else nd = refract(unit_direction, rec.normal, etai_over_etat);
+        o = rec.p;
+        d = nd; // keeps r.time
+        return true;
+    }
+    if (type == VK_M_METAL) { // src/material.rs:134-141: Ray::new -> time 0 (Q6), never absorbed
+        const float fuzz = __uint_as_float(m.z);
+        float3 nd = reflect(unit_vector(d), rec.normal);
+        if (fuzz != 0.0f) nd = nd + random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z)) * fuzz;
+        beta = beta * tex_value(sc, m.y, rec.u, rec.v, rec.p);
+        o = rec.p;
+        d = nd;
+        time = 0.0f;
+        return true;
+    }
+    // Lambertian / Isotropic (src/material.rs:92-108, :448-464): cosine lobe about rec.normal,
+    // mixed 50/50 with light sampling (src/main.rs:139-146).
+    const float3 attenuation = tex_value(sc, m.y, rec.u, rec.v, rec.p);
+    const Onb uvw = onb_from_w(rec.normal);
+    float3 nd;
+    if (u01(r.x) < 0.5f) { // MixturePDF::generate src/util.rs:177-185 -> HittablePDF -> list random
+        const uint32_t li = sc.n_lights > 1 ? min(sc.n_lights - 1u, (uint32_t)(u01(r.w) * (float)sc.n_lights)) : 0u;
+        nd = light_random(sc, __ldg(&sc.lights[li]), rec.p, r.y, r.z, r.w * 0x9E3779B1u);
+    } else {
+        const float3 c = random_cosine_direction(u01(r.y), u01(r.z));
+        nd = uvw.u * c.x + uvw.v * c.y + uvw.w * c.z;
+    }
+    const float3 und = unit_vector(nd);
+    const float cos_w = dot3(und, uvw.w);
+    const float cosine_pdf = cos_w <= 0.0f ? 0.0f : cos_w / VK_PI;                // CosinePDF::value src/util.rs:134-142
+    const float pdf = 0.5f * lights_pdf_value(sc, rec.p, nd) + 0.5f * cosine_pdf; // MixturePDF::value :173-175
+    float spdf = 0.0f;                                                            // Material::scattering_pdf default
+    if (spdf_type == VK_M_LAMBERTIAN || spdf_type == VK_M_ISOTROPIC) {
+        const float cos_n = dot3(rec.normal, und);
+        spdf = cos_n < 0.0f ? 0.0f : cos_n / VK_PI;
+    }
+    const float3 w = f3(attenuation.x * spdf / pdf, attenuation.y * spdf / pdf, attenuation.z * spdf / pdf);
+    if (!finite3(w)) { // reference: NaN/Inf poisons the sample, which main.rs:192 then drops (Q3)
+        valid = false;
+        return false;
+    }
+    beta = beta * w;
+    if (beta.x == 0.0f && beta.y == 0.0f && beta.z == 0.0f) return false; // nothing further can contribute
+    o = rec.p;
+    d = nd; // Ray::new_with_time(c.p, dir, r.time): keeps the camera-sampled time
+    return true;
 }
 
 } // namespace VK_NS

@@ -99,6 +99,37 @@ struct RenderBuffers {
     unsigned long long* counters;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Wavefront variant: a pool of path slots in device memory (L2-resident at the default pool size),
+// advanced one segment per iteration by separate kernels:
+//   generate  k_wf_generate  every slot takes a (pixel, sample block) unit and its first camera ray
+//   extend    k_wf_extend    world.hit() for every live slot; the hit is classified by the material's
+//                            shading class and the slot index appended to that class's queue
+//                            (warp ballot + one atomic per warp and class)
+//   shade     k_wf_shade     walks the queues class by class, so a warp shades one kind of material:
+//                            scatter + PDF sampling, or sample end -> accumulate -> next sample / next
+//                            unit (regeneration in place: the pool stays full until units run out)
+// A slot sums the samples of its unit in order and stores the unit's partial sum to the plane of
+// its sample block, exactly like a lane of the megakernel: both variants produce the same image
+// for a seed.  float4 / uint4 arrays: every access is one fully coalesced 16 B per lane.
+// ------------------------------------------------------------------------------------------------
+enum { VKW_TERMINATE = 0, VKW_DIELECTRIC = 1, VKW_METAL = 2, VKW_DIFFUSE = 3, VKW_CLASSES = 4 };
+struct WfState {
+    float4* ray_o;  // origin.xyz, time
+    float4* ray_d;  // direction.xyz, bits: depth of the segment to trace (0 = slot idle)
+    float4* beta;   // path weight.xyz, bits: global index of the current sample
+    uint4* unit;    // pixel, s_end (one past the unit's last sample), plane, -
+    float4* sum;    // partial sum of the unit's finished samples
+    float4* sumsq;  // same for squares; nullptr when not wanted
+    uint4* hit;     // t bits, primitive, instance, face
+    uint32_t* queue;    // VKW_CLASSES x n_slots slot indices
+    uint32_t* qcount;   // 2 sets x VKW_CLASSES counters (set = iteration parity)
+    unsigned long long* unit_head; // next unit to hand out
+    uint32_t n_slots;
+    uint32_t n_pixels;
+    unsigned long long n_units;
+};
+
 #define VK_DECLARE_LAUNCHERS(NS)                                                                                       \
     namespace NS {                                                                                                     \
     cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,  \
@@ -107,6 +138,11 @@ struct RenderBuffers {
                                  const float* medium_xi, vk_hit* out, cudaStream_t st);                                \
     cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads);                               \
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
+    cudaError_t launch_wf_generate(const DCamera& cam, const RenderArgs& a, const WfState& w, cudaStream_t st);        \
+    cudaError_t launch_wf_extend(const DScene& sc, const FlatProgram* flat, const RenderArgs& a, const WfState& w,     \
+                                 const RenderBuffers& b, uint32_t set, cudaStream_t st);                               \
+    cudaError_t launch_wf_shade(const DScene& sc, const DCamera& cam, const RenderArgs& a, const WfState& w,           \
+                                const RenderBuffers& b, uint32_t set, cudaStream_t st);                                \
     }
 VK_DECLARE_LAUNCHERS(vkfast)
 VK_DECLARE_LAUNCHERS(vkstrict)
