@@ -270,103 +270,141 @@ struct Validator {
     }
 };
 
-// Unroll the reference's traversal (depth first, left then right) into a flat program; false if the
-// scene has more than VKD_FLAT_MAX entries.  See FlatProgram.
+// Unroll the reference's traversal into the typed batches of FlatProgram; false if the scene does not
+// fit (then the BVH is traversed).
 struct FlatBuilder {
     const vk_scene_desc* d;
-    FlatProgram* P;
-    bool push(const FlatEntry& e) {
-        if (P->n >= VKD_FLAT_MAX) return false;
-        P->e[P->n++] = e;
-        return true;
-    }
-    bool rect(float c0, float c1, float d0, float d1, float k, uint32_t axes, vk_ref ref, uint32_t aux) {
-        FlatEntry e{};
-        e.a = make_float4(c0, c1, d0, d1);
-        e.k = k;
-        const uint32_t a2 = (axes >> 4) & 3u;
-        e.kind = a2 == 2 ? VKF_RECT_XY : (a2 == 1 ? VKF_RECT_XZ : VKF_RECT_YZ);
+    struct Seg {
+        std::vector<FlatOp> ops;
+        std::vector<std::pair<FlatRect, FlatHit>> rects[6];
+        std::vector<std::pair<FlatSphere, FlatHit>> sph, msph;
+        std::vector<FlatHit> med;
+        uint32_t inst = 0;
+    };
+    std::vector<Seg> segs;
+
+    bool rect(Seg& g, float c0, float c1, float d0, float d1, float k, uint32_t axes, vk_ref ref, uint32_t face, bool box_side) {
+        const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u, a2 = (axes >> 4) & 3u;
         // the canonical axis order of Rect::XYRect/XZRect/YZRect (src/hittable.rs:214-226) is assumed
-        const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u;
         const bool canonical = (a2 == 2 && a0 == 0 && a1 == 1) || (a2 == 1 && a0 == 0 && a1 == 2) || (a2 == 0 && a0 == 1 && a1 == 2);
         if (!canonical) return false;
-        e.ref = ref;
-        e.aux = aux;
-        return push(e);
+        FlatRect e{};
+        e.bounds = make_float4(c0, c1, d0, d1);
+        e.k = k;
+        FlatHit h{ref, g.inst, face, 0u};
+        g.rects[(a2 == 2 ? 0 : (a2 == 1 ? 1 : 2)) + (box_side ? 3 : 0)].push_back({e, h});
+        return true;
     }
-    bool emit(vk_ref ref, uint32_t dup) {
+    bool emit(vk_ref ref, size_t si, uint32_t dup) {
         const uint32_t i = VK_REF_INDEX(ref);
         switch (VK_REF_TYPE(ref)) {
         case VK_T_NODE: {
             const vk_node& n = d->nodes[i];
-            if (!emit(n.left, dup)) return false;
-            if (n.right != n.left) return emit(n.right, dup);
-            vk_ref end = n.left; // single-object leaf: second visit only matters for a medium
+            if (!emit(n.left, si, dup)) return false;
+            if (n.right != n.left) return emit(n.right, si, dup);
+            vk_ref end = n.left; // single-object leaf: the second visit only matters for a medium
             while (VK_REF_TYPE(end) == VK_T_XFORM) end = d->xforms[VK_REF_INDEX(end)].child;
-            return VK_REF_TYPE(end) == VK_T_MEDIUM ? emit(n.left, VKD_DUP) : true;
+            return VK_REF_TYPE(end) == VK_T_MEDIUM ? emit(n.left, si, VKD_DUP) : true;
         }
         case VK_T_SPHERE: {
-            FlatEntry e{};
+            FlatSphere e{};
             e.a = make_float4(d->spheres[i].center[0], d->spheres[i].center[1], d->spheres[i].center[2], d->spheres[i].radius);
-            e.kind = VKF_SPHERE;
-            e.ref = ref;
-            return push(e);
+            segs[si].sph.push_back({e, FlatHit{ref, segs[si].inst, 0u, 0u}});
+            return true;
         }
         case VK_T_MSPHERE: {
             const vk_msphere& m = d->mspheres[i];
-            FlatEntry e{};
+            FlatSphere e{};
             e.a = make_float4(m.center0[0], m.center0[1], m.center0[2], m.radius);
             e.b = make_float4(m.center1[0], m.center1[1], m.center1[2], m.time0);
-            e.k = m.time1;
-            e.kind = VKF_MSPHERE;
-            e.ref = ref;
-            return push(e);
+            e.time1 = m.time1;
+            segs[si].msph.push_back({e, FlatHit{ref, segs[si].inst, 0u, 0u}});
+            return true;
         }
         case VK_T_RECT: {
             const vk_rect& r = d->rects[i];
-            return rect(r.c0, r.c1, r.d0, r.d1, r.k, r.axes, ref, 0);
+            return rect(segs[si], r.c0, r.c1, r.d0, r.d1, r.k, r.axes, ref, 0, false);
         }
         case VK_T_BOX: { // the six sides in Boxy::new order (src/hittable.rs:325-353)
             const vk_box& b = d->boxes[i];
             const float* mn = b.box_min;
             const float* mx = b.box_max;
             const uint32_t XY = 0u | (1u << 2) | (2u << 4), XZ = 0u | (2u << 2) | (1u << 4), YZ = 1u | (2u << 2) | (0u << 4);
-            return rect(mn[0], mx[0], mn[1], mx[1], mx[2], XY, ref, 0 | VKF_STRICT) && rect(mn[0], mx[0], mn[1], mx[1], mn[2], XY, ref, 1 | VKF_STRICT) &&
-                   rect(mn[0], mx[0], mn[2], mx[2], mx[1], XZ, ref, 2 | VKF_STRICT) && rect(mn[0], mx[0], mn[2], mx[2], mn[1], XZ, ref, 3 | VKF_STRICT) &&
-                   rect(mn[1], mx[1], mn[2], mx[2], mx[0], YZ, ref, 4 | VKF_STRICT) && rect(mn[1], mx[1], mn[2], mx[2], mn[0], YZ, ref, 5 | VKF_STRICT);
+            Seg& g = segs[si];
+            return rect(g, mn[0], mx[0], mn[1], mx[1], mx[2], XY, ref, 0, true) && rect(g, mn[0], mx[0], mn[1], mx[1], mn[2], XY, ref, 1, true) &&
+                   rect(g, mn[0], mx[0], mn[2], mx[2], mx[1], XZ, ref, 2, true) && rect(g, mn[0], mx[0], mn[2], mx[2], mn[1], XZ, ref, 3, true) &&
+                   rect(g, mn[1], mx[1], mn[2], mx[2], mx[0], YZ, ref, 4, true) && rect(g, mn[1], mx[1], mn[2], mx[2], mn[0], YZ, ref, 5, true);
         }
-        case VK_T_MEDIUM: {
-            FlatEntry e{};
-            e.kind = VKF_MEDIUM;
-            e.ref = ref | dup;
-            return push(e);
-        }
+        case VK_T_MEDIUM:
+            segs[si].med.push_back(FlatHit{ref | dup, segs[si].inst, 0u, 0u});
+            return true;
         case VK_T_XFORM: {
+            if (si != 0) return false; // nested instances are refused by the validator anyway
+            Seg g;
+            g.inst = ref; // instance id = outermost wrapper
             vk_ref r = ref;
             while (VK_REF_TYPE(r) == VK_T_XFORM) {
                 const vk_xform& x = d->xforms[VK_REF_INDEX(r)];
-                FlatEntry e{};
-                e.ref = ref; // instance id = outermost wrapper
-                if (x.kind == VK_X_TRANSLATE) {
-                    e.kind = VKF_PUSH_TRANSLATE;
-                    e.a = make_float4(x.a, x.b, x.c, 0.f);
-                } else if (x.kind == VK_X_FLIP) {
-                    e.kind = VKF_PUSH_TRANSLATE; // the ray is unchanged; the flip happens in resolve_hit
-                    e.a = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    e.kind = x.kind == VK_X_ROTATE_X ? VKF_PUSH_ROTX : (x.kind == VK_X_ROTATE_Y ? VKF_PUSH_ROTY : VKF_PUSH_ROTZ);
-                    e.a = make_float4(x.a, x.b, 0.f, 0.f);
-                }
-                if (!push(e)) return false;
+                if (x.kind == VK_X_TRANSLATE) g.ops.push_back(FlatOp{VKF_OP_TRANSLATE, x.a, x.b, x.c});
+                else if (x.kind != VK_X_FLIP) // FlipFace leaves the ray alone; the flip happens in resolve_hit
+                    g.ops.push_back(FlatOp{x.kind == VK_X_ROTATE_X ? (uint32_t)VKF_OP_ROTX : (x.kind == VK_X_ROTATE_Y ? (uint32_t)VKF_OP_ROTY : (uint32_t)VKF_OP_ROTZ), x.a, x.b, 0.f});
                 r = x.child;
             }
-            if (!emit(r, dup)) return false;
-            FlatEntry e{};
-            e.kind = VKF_POP;
-            return push(e);
+            segs.push_back(std::move(g));
+            return emit(r, segs.size() - 1, dup);
         }
         default: return false;
         }
+    }
+    bool build(FlatProgram* P) {
+        *P = FlatProgram{};
+        segs.clear();
+        segs.emplace_back();
+        if (!emit(d->root, 0, 0)) return false;
+        if (segs.size() > VKF_MAX_SEGS) return false;
+        uint32_t n_ops = 0, n_rects = 0, n_sph = 0, n_hits = 0, n_med = 0;
+        for (size_t s = 0; s < segs.size(); ++s) {
+            Seg& g = segs[s];
+            FlatSeg& o = P->segs[s];
+            if (n_ops + g.ops.size() > VKF_MAX_OPS) return false;
+            o.op0 = (uint8_t)n_ops;
+            for (const FlatOp& op : g.ops) P->ops[n_ops++] = op;
+            o.op1 = (uint8_t)n_ops;
+            for (int k = 0; k < 6; ++k) {
+                if (n_rects + g.rects[k].size() > VKF_MAX_RECTS) return false;
+                o.rect0[k] = (uint8_t)n_rects;
+                for (auto& e : g.rects[k]) {
+                    e.first.hit = n_hits;
+                    P->hits[n_hits++] = e.second;
+                    P->rects[n_rects++] = e.first;
+                }
+                o.rect1[k] = (uint8_t)n_rects;
+            }
+            if (n_sph + g.sph.size() + g.msph.size() > VKF_MAX_SPHERES) return false;
+            o.sph0 = (uint8_t)n_sph;
+            for (auto& e : g.sph) {
+                e.first.hit = n_hits;
+                P->hits[n_hits++] = e.second;
+                P->spheres[n_sph++] = e.first;
+            }
+            o.sph1 = o.msph0 = (uint8_t)n_sph;
+            for (auto& e : g.msph) {
+                e.first.hit = n_hits;
+                P->hits[n_hits++] = e.second;
+                P->spheres[n_sph++] = e.first;
+            }
+            o.msph1 = (uint8_t)n_sph;
+            if (n_med + g.med.size() > VKF_MAX_MEDIA) return false;
+            o.med0 = (uint8_t)n_hits;
+            for (const FlatHit& h : g.med) {
+                P->hits[n_hits++] = h;
+                ++n_med;
+            }
+            o.med1 = (uint8_t)n_hits;
+        }
+        P->n_segs = (uint32_t)segs.size();
+        P->n = n_hits;
+        return n_hits > 0;
     }
 };
 
@@ -571,9 +609,9 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     s.has_media = d->n_media > 0;
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
-    c->flat = FlatProgram{};
-    FlatBuilder fb{d, &c->flat};
-    if (!fb.emit(d->root, 0)) c->flat.n = 0;
+    FlatBuilder fb;
+    fb.d = d;
+    if (!fb.build(&c->flat)) c->flat = FlatProgram{};
     c->has_scene = true;
     return VK_OK;
 }
@@ -634,7 +672,9 @@ static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCam
     // no sample ends before its first segment: at least spp_count * n_pixels / n_slots iterations
     const unsigned long long min_iters = ((unsigned long long)w.n_pixels * a.spp_count + w.n_slots - 1) / w.n_slots;
     unsigned long long next_check = min_iters > 8 ? min_iters : 8;
+    const unsigned long long max_iters = (min_iters + 2) * (unsigned long long)(a.max_depth ? a.max_depth : 1) + 64; // every path is <= max_depth segments
     for (unsigned long long it = 0;; ++it) {
+        if (it > max_iters) return fail(c, VK_ERR_CUDA, "wavefront: the slot pool did not drain (internal error)");
         const uint32_t set = (uint32_t)(it & 1u);
         CU(c, strict ? vkstrict::launch_wf_extend(c->scene, flat, a, w, b, set, c->stream)
                      : vkfast::launch_wf_extend(c->scene, flat, a, w, b, set, c->stream));

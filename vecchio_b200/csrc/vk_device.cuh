@@ -268,7 +268,18 @@ VKD uint32_t chain_down(const DScene& sc, uint32_t ref, float3& o, float3& d) {
 
 // Distance-only hit of a leaf primitive (no BVH below it): the shared body of the traversal's
 // leaf test and of ConstantMedium's two boundary queries.
+#if VK_STRICT
 VKD float3 rcp3(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+#else
+// one MUFU.RCP per component (1/+-0 = +-inf as the slab and plane tests need; a denormal component
+// flushes to 0 -> inf, where the exact quotient would overflow anyway)
+VKD float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+VKD float3 rcp3(float3 d) { return f3(fast_rcp(d.x), fast_rcp(d.y), fast_rcp(d.z)); }
+#endif
 
 VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float3 inv_d, float time, float tmin, float tmax, float& t,
                 uint32_t& face) {
@@ -448,75 +459,109 @@ VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin,
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same closest-hit query over a flat program (see FlatProgram in vk_internal.h): every lane
-// executes the same entry at the same time.  Per-entry arithmetic is the reference's, in its order.
+// The same closest-hit query over a flat program (see FlatProgram in vk_internal.h): typed batches,
+// every lane runs the same entry at the same time.  Per-entry arithmetic is the reference's, in
+// its order (STRICT divides, FAST multiplies by 1/d).
 // ---------------------------------------------------------------------------------------------
 #if VK_STRICT
 #define VKF_PLANE_T(K, O, D, I) (((K) - (O)) / (D))
 #else
 #define VKF_PLANE_T(K, O, D, I) (((K) - (O)) * (I))
 #endif
+// AX: 0 = XYRect (plane on z), 1 = XZRect (plane on y), 2 = YZRect (plane on x); src/hittable.rs:214-239.
+// BOX_SIDE: the entry is a side of a Boxy -- list semantics, strictly closer only (:386).
+template <int AX, bool BOX_SIDE>
+VKD void flat_rects(const FlatProgram& P, uint32_t i0, uint32_t i1, float3 co, float3 cd, float3 ci, float tmin, float& best_t,
+                    uint32_t& best_hit) {
+#pragma unroll 1
+    for (uint32_t i = i0; i < i1; ++i) {
+        const float4 bd = P.rects[i].bounds;
+        const float k = P.rects[i].k;
+        float tt, a, b;
+        if (AX == 0) {
+            tt = VKF_PLANE_T(k, co.z, cd.z, ci.z);
+            a = co.x + tt * cd.x;
+            b = co.y + tt * cd.y;
+        } else if (AX == 1) {
+            tt = VKF_PLANE_T(k, co.y, cd.y, ci.y);
+            a = co.x + tt * cd.x;
+            b = co.z + tt * cd.z;
+        } else {
+            tt = VKF_PLANE_T(k, co.x, cd.x, ci.x);
+            a = co.y + tt * cd.y;
+            b = co.z + tt * cd.z;
+        }
+        bool hit = !(tt < tmin || tt > best_t) && !(a < bd.x || a > bd.y || b < bd.z || b > bd.w);
+        if (BOX_SIDE) hit = hit && tt < best_t;
+        if (hit) {
+            best_t = tt;
+            best_hit = P.rects[i].hit;
+        }
+    }
+}
 template <bool MEDIA>
 VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3 d, float time, float tmin, float tmax,
                         const MediumXi& xi, TraceCounters& tc) {
-    float3 co = o, cd = d, ci = rcp3(d);
-    uint32_t inst = 0;
+    float best_t = tmax;
+    uint32_t best_hit = 0xFFFFFFFFu;
+    const uint32_t n_segs = P.n_segs;
+    tc.prims += P.n;
+#pragma unroll 1
+    for (uint32_t s = 0; s < n_segs; ++s) {
+        const FlatSeg& g = P.segs[s];
+        float3 co = o, cd = d;
+#pragma unroll 1
+        for (uint32_t k = g.op0; k < g.op1; ++k) { // world ray -> frame of this instance chain
+            const uint32_t kind = P.ops[k].kind;
+            if (kind == VKF_OP_TRANSLATE) co = co - f3(P.ops[k].a, P.ops[k].b, P.ops[k].c);
+            else {
+                rot_fwd(kind, P.ops[k].a, P.ops[k].b, co); // VKF_OP_ROT* == VK_X_ROTATE_*
+                rot_fwd(kind, P.ops[k].a, P.ops[k].b, cd);
+            }
+        }
+        const float3 ci = rcp3(cd);
+        flat_rects<0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects<1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects<2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects<0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects<1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects<2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, tmin, best_t, best_hit);
+#pragma unroll 1
+        for (uint32_t i = g.sph0; i < g.sph1; ++i) {
+            float tt;
+            if (sphere_t(f3(P.spheres[i].a), P.spheres[i].a.w, co, cd, tmin, best_t, tt)) {
+                best_t = tt;
+                best_hit = P.spheres[i].hit;
+            }
+        }
+#pragma unroll 1
+        for (uint32_t i = g.msph0; i < g.msph1; ++i) {
+            float tt;
+            if (sphere_t(msphere_center(P.spheres[i].a, P.spheres[i].b, P.spheres[i].time1, time), P.spheres[i].a.w, co, cd, tmin, best_t, tt)) {
+                best_t = tt;
+                best_hit = P.spheres[i].hit;
+            }
+        }
+        if (MEDIA) {
+#pragma unroll 1
+            for (uint32_t i = g.med0; i < g.med1; ++i) {
+                float tt;
+                if (medium_t(sc, P.hits[i].prim, co, cd, time, tmin, best_t, xi, tt)) {
+                    best_t = tt;
+                    best_hit = i;
+                }
+            }
+        }
+    }
     TraceHit best;
-    best.t = tmax;
+    best.t = best_t;
     best.prim = VK_REF_NONE;
     best.inst = 0;
     best.face = 0;
-    const uint32_t n = P.n;
-    tc.prims += n;
-#pragma unroll 1
-    for (uint32_t i = 0; i < n; ++i) {
-        const FlatEntry& e = P.e[i];
-        const uint32_t kind = e.kind;
-        float tt = 0.0f;
-        bool hit = false;
-        if (kind <= VKF_RECT_YZ) { // Rect::hit src/hittable.rs:230-239
-            float a, b;
-            if (kind == VKF_RECT_XY) {
-                tt = VKF_PLANE_T(e.k, co.z, cd.z, ci.z);
-                a = co.x + tt * cd.x;
-                b = co.y + tt * cd.y;
-            } else if (kind == VKF_RECT_XZ) {
-                tt = VKF_PLANE_T(e.k, co.y, cd.y, ci.y);
-                a = co.x + tt * cd.x;
-                b = co.z + tt * cd.z;
-            } else {
-                tt = VKF_PLANE_T(e.k, co.x, cd.x, ci.x);
-                a = co.y + tt * cd.y;
-                b = co.z + tt * cd.z;
-            }
-            hit = !(tt < tmin || tt > best.t) && !(a < e.a.x || a > e.a.y || b < e.a.z || b > e.a.w);
-        } else if (kind == VKF_SPHERE) {
-            hit = sphere_t(f3(e.a), e.a.w, co, cd, tmin, best.t, tt);
-        } else if (kind == VKF_MSPHERE) {
-            hit = sphere_t(msphere_center(e.a, e.b, e.k, time), e.a.w, co, cd, tmin, best.t, tt);
-        } else if (kind == VKF_MEDIUM) {
-            if (MEDIA) hit = medium_t(sc, e.ref, co, cd, time, tmin, best.t, xi, tt);
-        } else if (kind == VKF_POP) {
-            co = o;
-            cd = d;
-            ci = rcp3(d);
-            inst = 0;
-        } else { // push one wrapper level
-            if (inst == 0) inst = e.ref;
-            if (kind == VKF_PUSH_TRANSLATE) co = co - f3(e.a);
-            else {
-                const uint32_t xk = kind == VKF_PUSH_ROTX ? VK_X_ROTATE_X : (kind == VKF_PUSH_ROTY ? VK_X_ROTATE_Y : VK_X_ROTATE_Z);
-                rot_fwd(xk, e.a.x, e.a.y, co);
-                rot_fwd(xk, e.a.x, e.a.y, cd);
-                ci = rcp3(cd);
-            }
-        }
-        if (hit && !((e.aux & VKF_STRICT) && !(tt < best.t))) {
-            best.t = tt;
-            best.prim = e.ref & ~VKD_DUP;
-            best.inst = inst;
-            best.face = e.aux & 0xFFu;
-        }
+    if (best_hit != 0xFFFFFFFFu) {
+        best.prim = P.hits[best_hit].prim & ~VKD_DUP;
+        best.inst = P.hits[best_hit].inst;
+        best.face = P.hits[best_hit].face;
     }
     return best;
 }

@@ -49,31 +49,67 @@ struct DScene {
 // ------------------------------------------------------------------------------------------------
 // Flat traversal program.  A scene with few primitives (Cornell box: 13 rect sides + 1 sphere) gains
 // nothing from its BVH on a GPU: the lanes of a warp sit at different nodes and execute each
-// other's branches.  For such scenes vk_scene_upload unrolls the reference's traversal order
-// (depth first, left then right, a Boxy as its six sides, a wrapper chain as push/pop of the ray
-// frame) into a short straight-line program.  Every lane then tests the SAME primitive at the same
-// time: no stack, no divergence, warp-uniform operand fetches from the constant bank (the program
-// travels as a __grid_constant__ kernel parameter).  Closest hit is order independent, so this is
-// the same function as BVHNode::hit; the BVH path remains for everything larger.
+// other's branches.  For such scenes vk_scene_upload unrolls the reference's traversal (a Boxy as
+// its six sides, a wrapper chain as a change of ray frame) into typed, branch-free batches:
+//
+//   segment 0 = the world frame, segment s > 0 = one instance chain (its ops transform the world ray
+//   into the object frame: Translate / RotateX,Y,Z, src/hittable.rs:508, :591-595, :680-684, :769-773);
+//   inside a segment: XY rects, XZ rects, YZ rects (each kind once for plain rects and once for box
+//   sides, which keep the list's strict `<` of src/hittable.rs:386), spheres, moving spheres, media.
+//
+// Every lane tests the SAME primitive at the same time with the SAME instruction sequence: no
+// stack, no divergence, no type decode per entry, operands from the constant bank (the program
+// travels as a __grid_constant__ kernel parameter).  Closest hit is order independent (exact ties
+// excepted; a ConstantMedium's accept/reject does not depend on the tmax it is handed, only on
+// whether a nearer surface exists), so this is the same function as BVHNode::hit.  The BVH path
+// remains for everything larger.
 // ------------------------------------------------------------------------------------------------
-#define VKD_FLAT_MAX 96
-enum {
-    VKF_RECT_XY = 1, VKF_RECT_XZ, VKF_RECT_YZ, VKF_SPHERE, VKF_MSPHERE, VKF_MEDIUM,
-    VKF_PUSH_TRANSLATE, VKF_PUSH_ROTX, VKF_PUSH_ROTY, VKF_PUSH_ROTZ, VKF_POP
+#define VKF_MAX_SEGS 12
+#define VKF_MAX_OPS 24
+#define VKF_MAX_RECTS 96
+#define VKF_MAX_SPHERES 16
+#define VKF_MAX_MEDIA 4
+enum { VKF_OP_TRANSLATE = 0, VKF_OP_ROTX = 1, VKF_OP_ROTY = 2, VKF_OP_ROTZ = 3 };
+struct FlatOp { // one wrapper level, outermost first
+    uint32_t kind;
+    float a, b, c; // translate: offset | rotate: sin, cos
 };
-#define VKF_STRICT 0x100u // a side of a Boxy: list semantics, must be strictly closer (src/hittable.rs:386)
-struct FlatEntry {
-    float4 a;      // rect: c0,c1,d0,d1 | sphere: center,r | msphere: c0,r | translate: offset | rotate: sin,cos
-    float4 b;      // msphere: c1,time0
-    float k;       // rect: plane | msphere: time1
-    uint32_t kind; // VKF_*
-    uint32_t ref;  // leaf record (hit id) | push: the chain's outermost wrapper (instance id)
-    uint32_t aux;  // face (0..5) | VKF_STRICT
+struct FlatRect { // Rect::hit src/hittable.rs:230-239
+    float4 bounds; // c0, c1, d0, d1
+    float k;
+    uint32_t hit; // index into FlatProgram::hits
+    uint32_t _pad[2];
+};
+struct FlatSphere { // Sphere::hit :65-95 | MovingSphere::hit :154-184
+    float4 a; // center (center0), radius
+    float4 b; // moving: center1, time0
+    float time1;
+    uint32_t hit;
+    uint32_t _pad[2];
+};
+struct FlatHit { // what the closest entry resolves to
+    uint32_t prim; // leaf record (sphere / msphere / rect / box / medium [| VKD_DUP on a medium's second visit])
+    uint32_t inst; // outermost wrapper of the chain it sits under, or 0
+    uint32_t face; // box side 0..5 in Boxy::new order
+    uint32_t _pad;
+};
+struct FlatSeg {
+    uint8_t op0, op1;           // ops [op0, op1) take the world ray into this segment's frame
+    uint8_t rect0[6], rect1[6]; // rect ranges: XY, XZ, YZ plain, then XY, XZ, YZ box sides (strict)
+    uint8_t sph0, sph1;         // static spheres
+    uint8_t msph0, msph1;       // moving spheres
+    uint8_t med0, med1;         // media: hits[] indices [med0, med1) (their prim is the medium ref)
+    uint8_t _pad[4];
 };
 struct FlatProgram {
-    uint32_t n; // 0 = no program: use the BVH
-    uint32_t _pad[3];
-    FlatEntry e[VKD_FLAT_MAX];
+    uint32_t n;      // number of primitive entries; 0 = no program: use the BVH
+    uint32_t n_segs;
+    uint32_t _pad[2];
+    FlatSeg segs[VKF_MAX_SEGS];
+    FlatOp ops[VKF_MAX_OPS];
+    FlatRect rects[VKF_MAX_RECTS];
+    FlatSphere spheres[VKF_MAX_SPHERES];
+    FlatHit hits[VKF_MAX_RECTS + VKF_MAX_SPHERES + VKF_MAX_MEDIA];
 };
 
 struct DCamera {
