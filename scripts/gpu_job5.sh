@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python scripts/render_once.py cornell 200 1 > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_megakernel -s 1 -c 1 -f -o gpurun_out/prof_r1_cornell_v5 \
+    python scripts/render_once.py cornell 200 1 > gpurun_out/ncu_full.log 2>&1; echo "full rc=$?"
+cat gpurun_out/plain2.log

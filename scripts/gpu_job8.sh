@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -k "variants or edge" > gpurun_out/pytest_staged.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/pytest_staged.log
+for c in "cornell 1000" "cornell_smoke 200" "final_scene 64" "random_spheres 16"; do echo "K2 variant 3: $(timeout 300 python scripts/render_once.py $c 3 2>&1 | tail -1)"; done 2>&1 | tee gpurun_out/configs_v7.log
+for c in "cornell 1000" "cornell_smoke 200"; do echo "K4 variant 3: $(VECCHIO_GPU_LIB=$PWD/build/variants/lib_k4.so timeout 300 python scripts/render_once.py $c 3 2>&1 | tail -1)"; done 2>&1 | tee -a gpurun_out/configs_v7.log

@@ -359,8 +359,9 @@ WF_SCENES = [("cornell_box", 0, 96, 64, 100), ("cornell_smoke", 0, 64, 64, 100),
              ("random_spheres_demo", 0, 96, 32, 50), ("bowser_demo", 0, 64, 32, 50)]
 
 
+@pytest.mark.parametrize("variant", [2, 3], ids=["wavefront", "staged"])
 @pytest.mark.parametrize("name,param,W,spp,depth", WF_SCENES, ids=[s[0] for s in WF_SCENES])
-def test_wavefront_equals_megakernel(vb, ctx, name, param, W, spp, depth):
+def test_variants_equal_megakernel(vb, ctx, name, param, W, spp, depth, variant):
     """Both variants own (pixel, sample block) units, sum a unit's samples in order and key Philox by
     (pixel, global sample, bounce): with the strict build (no FMA contraction, so the shared device
     functions round identically in both kernels) the images are bit-identical, and so are the
@@ -370,11 +371,11 @@ def test_wavefront_equals_megakernel(vb, ctx, name, param, W, spp, depth):
     ctx.upload(scene)
     for flags, exact in ((vb.VK_FLAG_STRICT_MATH, True), (0, False)):
         pm = vb.render_params(W, H, spp, depth, seed=31, variant=vb.VK_VARIANT_MEGAKERNEL, flags=flags)
-        pw = vb.render_params(W, H, spp, depth, seed=31, variant=vb.VK_VARIANT_WAVEFRONT, flags=flags)
+        pw = vb.render_params(W, H, spp, depth, seed=31, variant=variant, flags=flags)
         a, qa, sa = ctx.render(cam, pm, want_sumsq=True)
         b, qb, sb = ctx.render(cam, pw, want_sumsq=True)
-        assert sb.variant == vb.VK_VARIANT_WAVEFRONT and sa.variant == vb.VK_VARIANT_MEGAKERNEL
-        assert sb.launches > 3 and sa.paths == sb.paths
+        assert sb.variant == variant and sa.variant == vb.VK_VARIANT_MEGAKERNEL
+        assert (sb.launches > 3 or variant == vb.VK_VARIANT_STAGED) and sa.paths == sb.paths
         if exact:
             assert np.array_equal(a, b) and np.array_equal(qa, qb), (name, np.abs(a - b).max())
             assert (sa.rays, sa.dropped_samples) == (sb.rays, sb.dropped_samples)
@@ -402,10 +403,10 @@ def test_wavefront_image_parity_with_oracle(vb, po, ctx):
     assert abs(sg.rays / sg.paths - so.rays_live / so.paths) <= 0.02 * so.rays_live / so.paths
 
 
-def test_wavefront_edge_cases(vb, ctx):
+@pytest.mark.parametrize("wf", [2, 3], ids=["wavefront", "staged"])
+def test_wavefront_edge_cases(vb, ctx, wf):
     scene, cam = get_scene(vb, "cornell_box")
     ctx.upload(scene)
-    wf = vb.VK_VARIANT_WAVEFRONT
     # fewer units than pool slots, ragged image, spp not a multiple of the sample block, depth 1
     rgb, _, st = ctx.render(cam, vb.render_params(61, 37, 13, 100, seed=1, variant=wf))
     ref, _, sr = ctx.render(cam, vb.render_params(61, 37, 13, 100, seed=1, variant=vb.VK_VARIANT_MEGAKERNEL))

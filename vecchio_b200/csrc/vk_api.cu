@@ -402,6 +402,21 @@ struct FlatBuilder {
             }
             o.med1 = (uint8_t)n_hits;
         }
+        for (uint32_t h = 0; h < n_hits; ++h) { // shading class of each entry's material
+            const vk_ref pr = P->hits[h].prim & ~VKD_DUP;
+            const uint32_t i = VK_REF_INDEX(pr);
+            uint32_t mat = 0;
+            switch (VK_REF_TYPE(pr)) {
+            case VK_T_SPHERE: mat = d->sphere_mat[i]; break;
+            case VK_T_MSPHERE: mat = d->mspheres[i].mat; break;
+            case VK_T_RECT: mat = d->rects[i].mat; break;
+            case VK_T_BOX: mat = d->boxes[i].mat; break;
+            case VK_T_MEDIUM: mat = d->media[i].mat; break;
+            default: return false;
+            }
+            const uint32_t t = d->materials[mat].type;
+            P->hits[h].cls = t == VK_M_DIFFUSE_LIGHT ? 0u : t == VK_M_DIELECTRIC ? 1u : t == VK_M_METAL ? 2u : 3u;
+        }
         P->n_segs = (uint32_t)segs.size();
         P->n = n_hits;
         return n_hits > 0;
@@ -698,7 +713,7 @@ static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCam
 // persistent megakernel is ahead of the wavefront kernels on B200 -- the scenes are cache resident,
 // so the wavefront's queue traffic and launch boundaries buy coherence the megakernel already has.
 static uint32_t choose_variant(const vk_ctx*, const vk_render_params* P) {
-    return P->variant == VK_VARIANT_WAVEFRONT ? VK_VARIANT_WAVEFRONT : VK_VARIANT_MEGAKERNEL;
+    return P->variant == VK_VARIANT_AUTO ? (uint32_t)VK_VARIANT_MEGAKERNEL : P->variant;
 }
 
 // shared body of vk_render / vk_render_device
@@ -711,7 +726,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     const uint32_t count = P->spp_count ? P->spp_count : P->spp - P->spp_begin;
     if ((uint64_t)P->spp_begin + count > P->spp) return fail(c, VK_ERR_INVALID, "render: sample slice exceeds spp");
     if ((uint64_t)P->width * P->height > 0x7FFFFFFFull / 3) return fail(c, VK_ERR_INVALID, "render: image too large");
-    if (P->variant > VK_VARIANT_WAVEFRONT) return fail(c, VK_ERR_INVALID, "render: unknown variant");
+    if (P->variant > VK_VARIANT_STAGED) return fail(c, VK_ERR_INVALID, "render: unknown variant");
     if (!(cam->time0 < cam->time1)) return fail(c, VK_ERR_INVALID, "render: camera time0 >= time1 (gen_range panics, src/main.rs:118)");
     CU(c, cudaSetDevice(c->device));
     const bool strict = (P->flags & VK_FLAG_STRICT_MATH) != 0;
@@ -771,6 +786,10 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     if (variant == VK_VARIANT_WAVEFRONT) {
         int rc = wf_render(c, strict, flat, dc, a, b, d_sumsq != nullptr, &launches);
         if (rc != VK_OK) return rc;
+    } else if (variant == VK_VARIANT_STAGED) {
+        CU(c, strict ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->sm_count, c->stream)
+                     : vkfast::launch_staged(c->scene, flat, dc, a, b, c->sm_count, c->stream));
+        launches = 1;
     } else {
         CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)
                      : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream));

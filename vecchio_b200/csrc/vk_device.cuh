@@ -566,6 +566,122 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
     return best;
 }
 
+// K rays per thread through the flat program (the staged kernel traces all the slots a thread owns
+// together): an entry's operands are fetched once for the K rays and the K closest-hit chains are
+// independent, which is the instruction-level parallelism a warp-per-SM-quarter schedule lacks.
+template <int K, int AX, bool BOX_SIDE>
+VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const float3 (&co)[K], const float3 (&cd)[K], const float3 (&ci)[K],
+                      float tmin, float (&best_t)[K], uint32_t (&best_hit)[K]) {
+#pragma unroll 1
+    for (uint32_t i = i0; i < i1; ++i) {
+        const float4 bd = P.rects[i].bounds;
+        const float k = P.rects[i].k;
+        const uint32_t id = P.rects[i].hit;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            float tt, a, b;
+            if (AX == 0) {
+                tt = VKF_PLANE_T(k, co[q].z, cd[q].z, ci[q].z);
+                a = co[q].x + tt * cd[q].x;
+                b = co[q].y + tt * cd[q].y;
+            } else if (AX == 1) {
+                tt = VKF_PLANE_T(k, co[q].y, cd[q].y, ci[q].y);
+                a = co[q].x + tt * cd[q].x;
+                b = co[q].z + tt * cd[q].z;
+            } else {
+                tt = VKF_PLANE_T(k, co[q].x, cd[q].x, ci[q].x);
+                a = co[q].y + tt * cd[q].y;
+                b = co[q].z + tt * cd[q].z;
+            }
+            // same predicate as Rect::hit, evaluated without branches (bitwise on the comparison results)
+            bool miss = (tt < tmin) | (tt > best_t[q]) | (a < bd.x) | (a > bd.y) | (b < bd.z) | (b > bd.w);
+            if (BOX_SIDE) miss = miss | !(tt < best_t[q]);
+            best_t[q] = miss ? best_t[q] : tt;
+            best_hit[q] = miss ? best_hit[q] : id;
+        }
+    }
+}
+// `live` masks the rays that exist (an idle slot's ray is traced as a dummy and ignored); out_hit
+// is the index into P.hits or 0xFFFFFFFF.
+template <int K, bool MEDIA>
+VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[K], const float3 (&d)[K], const float (&time)[K],
+                      const bool (&live)[K], float tmin, const MediumXi (&xi)[K], float (&best_t)[K], uint32_t (&best_hit)[K]) {
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        best_t[q] = CUDART_INF_F;
+        best_hit[q] = 0xFFFFFFFFu;
+    }
+    const uint32_t n_segs = P.n_segs;
+#pragma unroll 1
+    for (uint32_t s = 0; s < n_segs; ++s) {
+        const FlatSeg& g = P.segs[s];
+        float3 co[K], cd[K], ci[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            co[q] = o[q];
+            cd[q] = d[q];
+        }
+#pragma unroll 1
+        for (uint32_t k = g.op0; k < g.op1; ++k) {
+            const uint32_t kind = P.ops[k].kind;
+            const float pa = P.ops[k].a, pb = P.ops[k].b, pc = P.ops[k].c;
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                if (kind == VKF_OP_TRANSLATE) co[q] = co[q] - f3(pa, pb, pc);
+                else {
+                    rot_fwd(kind, pa, pb, co[q]);
+                    rot_fwd(kind, pa, pb, cd[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < K; ++q) ci[q] = rcp3(cd[q]);
+        flat_rects_k<K, 0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, tmin, best_t, best_hit);
+#pragma unroll 1
+        for (uint32_t i = g.sph0; i < g.sph1; ++i) {
+            const float4 sp = P.spheres[i].a;
+            const uint32_t id = P.spheres[i].hit;
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                float tt;
+                if (sphere_t(f3(sp), sp.w, co[q], cd[q], tmin, best_t[q], tt)) {
+                    best_t[q] = tt;
+                    best_hit[q] = id;
+                }
+            }
+        }
+#pragma unroll 1
+        for (uint32_t i = g.msph0; i < g.msph1; ++i) {
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                float tt;
+                if (sphere_t(msphere_center(P.spheres[i].a, P.spheres[i].b, P.spheres[i].time1, time[q]), P.spheres[i].a.w, co[q], cd[q], tmin, best_t[q], tt)) {
+                    best_t[q] = tt;
+                    best_hit[q] = P.spheres[i].hit;
+                }
+            }
+        }
+        if (MEDIA) {
+#pragma unroll 1
+            for (uint32_t i = g.med0; i < g.med1; ++i) {
+#pragma unroll 1
+                for (int q = 0; q < K; ++q) {
+                    float tt;
+                    if (live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt)) {
+                        best_t[q] = tt;
+                        best_hit[q] = i;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // HitRec (src/hittable.rs:11-31) of the winning primitive, built once per segment.
 // ---------------------------------------------------------------------------------------------

@@ -91,7 +91,7 @@ struct FlatHit { // what the closest entry resolves to
     uint32_t prim; // leaf record (sphere / msphere / rect / box / medium [| VKD_DUP on a medium's second visit])
     uint32_t inst; // outermost wrapper of the chain it sits under, or 0
     uint32_t face; // box side 0..5 in Boxy::new order
-    uint32_t _pad;
+    uint32_t cls;  // shading class of its material (VKW_* / VKS_C_*: 0 emitter, 1 dielectric, 2 metal, 3 diffuse)
 };
 struct FlatSeg {
     uint8_t op0, op1;           // ops [op0, op1) take the world ray into this segment's frame
@@ -128,7 +128,8 @@ struct RenderArgs {
     uint32_t tiles_x, tiles_y, n_chunks, chunk_spp, unit_spp, n_planes;
 };
 
-// counters[0] = rays, [1] = dropped samples, [2] = work-queue head, [3] = node visits, [4] = primitive tests
+// counters[0] = rays, [1] = dropped samples, [2] = work-queue head, [3] = node visits, [4] = primitive tests,
+// [5] = unit head of the staged kernel
 struct RenderBuffers {
     float* partial_sum;   // n_planes x W*H*3 (== d_sum when n_planes == 1)
     float* partial_sumsq; // same, nullable
@@ -174,6 +175,8 @@ struct WfState {
                                  const float* medium_xi, vk_hit* out, cudaStream_t st);                                \
     cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads);                               \
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
+    cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,      \
+                              const RenderBuffers& b, int sm_count, cudaStream_t st);                              \
     cudaError_t launch_wf_generate(const DCamera& cam, const RenderArgs& a, const WfState& w, cudaStream_t st);        \
     cudaError_t launch_wf_extend(const DScene& sc, const FlatProgram* flat, const RenderArgs& a, const WfState& w,     \
                                  const RenderBuffers& b, uint32_t set, cudaStream_t st);                               \

@@ -1,0 +1,357 @@
+// vk_staged.cu -- the persistent megakernel, staged: a wavefront inside each CTA.
+//
+// Measured on B200 (profiles/r1_cornell_megakernel_*): the one-lane-one-path megakernel issues with
+// 15 of 32 lanes active and stalls mostly on instruction fetch ("no_instruction"): its lanes sit in
+// different materials / regeneration / traversal at the same time, so every warp walks a 70 KB body.
+// The global-memory wavefront fixes the divergence but pays launch boundaries and queue traffic.
+// This kernel keeps the wavefront's stages and sorts, but inside one persistent CTA:
+//
+//   * a pool of VKS_N path slots per CTA lives in shared memory (four 16-byte records per slot, 3 CTAs per SM);
+//   * each iteration runs the stages back to back, separated by __syncthreads():
+//       extend      world.hit() for every live slot, slot == thread mapping   src/main.rs:130
+//       sort        the live slots are appended to the list of their shading class (warp ballot +
+//                   one shared-memory atomic per warp and class)
+//       shade       threads walk the class lists end to end, so a warp runs ONE material
+//                   (src/main.rs:131-149); sample end: NaN filter and accumulate (:191-194), then
+//                   the next sample's camera ray in place (:187-190) -- the emitter/miss class
+//                   does this with full warps
+//   * a slot owns a (pixel, sample block) unit and adds its samples in order into the unit's plane
+//     (read-modify-write in L2: the location belongs to that slot alone), so the image is
+//     bit-identical to the other variants for a seed.
+#include "vk_device.cuh"
+
+namespace VK_NS {
+
+#define VKS_T 256
+#define VKS_N 1024
+#define VKS_ROUNDS (VKS_N / VKS_T)
+#define VKS_NEWUNIT 0x80000000u
+enum { VKS_C_TERMINATE = 0, VKS_C_DIELECTRIC = 1, VKS_C_METAL = 2, VKS_C_DIFFUSE = 3, VKS_CLASSES = 4, VKS_C_IDLE = 7 };
+
+#ifndef VKS_K
+#define VKS_K 2 // rays a thread traces together through the flat program
+#endif
+struct StagedShared {
+    float4 ro[VKS_N];                  // origin.xyz, time
+    float4 rd[VKS_N];                  // direction.xyz, bits: depth of the segment to trace (0 = idle slot)
+    float4 bt[VKS_N];                  // path weight.xyz, bits: global sample index
+    uint4 hp[VKS_N];                   // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; pixel
+    uint16_t list[VKS_CLASSES][VKS_N]; // live slots by shading class (each class can hold the whole pool)
+    uint32_t cnt[2][VKS_CLASSES];      // class counts, double buffered by iteration parity
+    uint32_t next_unit;                // CTA-local unit counter
+};
+
+VKD uint32_t staged_class_of(const DScene& sc, uint32_t prim) {
+    uint32_t mat;
+    const uint32_t i = VKD_INDEX(prim);
+    switch (VKD_TYPE(prim)) {
+    case VK_T_SPHERE: mat = __ldg(&sc.sphere_mat[i]); break;
+    case VK_T_MSPHERE: mat = __float_as_uint(__ldg(&sc.mspheres[3 * i + 2]).y); break;
+    case VK_T_RECT: mat = __float_as_uint(__ldg(&sc.rects[2 * i + 1]).z); break;
+    case VK_T_BOX: mat = __float_as_uint(__ldg(&sc.boxes[2 * i]).w); break;
+    default: mat = __float_as_uint(__ldg(&sc.media[i]).z); break;
+    }
+    const uint32_t t = __ldg(&sc.materials[mat]).x;
+    return t == VK_M_DIFFUSE_LIGHT ? VKS_C_TERMINATE : t == VK_M_DIELECTRIC ? VKS_C_DIELECTRIC : t == VK_M_METAL ? VKS_C_METAL : VKS_C_DIFFUSE;
+}
+
+// Units are dealt to the CTAs statically, 32 at a time round-robin (unit = (pixel, sample block),
+// pixels row-major): every CTA samples the whole frame evenly, so the CTAs finish together without
+// a global queue; inside the CTA the slots draw from `next_unit` with a shared-memory atomic.
+//   local index n  ->  unit ((n / 32) * gridDim.x + blockIdx.x) * 32 + n % 32
+struct StagedCtx {
+    const DCamera& cam;
+    const RenderArgs& a;
+    StagedShared& S;
+    uint32_t n_pixels;
+    unsigned long long n_units;
+};
+// Start the sample `s` of `pixel` in `slot`: Camera::get_ray, depth 1 (src/main.rs:187-190).
+VKD void staged_begin_sample(const StagedCtx& C, uint32_t slot, uint32_t pixel, uint32_t s) {
+    PathRng rng;
+    rng.pixel = pixel;
+    rng.sample = s;
+    rng.key = make_uint2(C.a.seed_lo, C.a.seed_hi);
+    float3 o, d;
+    float time;
+    camera_get_ray(C.cam, rng, pixel % C.a.width, pixel / C.a.width, C.a.width, C.a.height, o, d, time);
+    StagedShared& S = C.S;
+    S.ro[slot] = make_float4(o.x, o.y, o.z, time);
+    S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(1u)); // ray_color(ray, .., 1)
+    S.bt[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(s));
+    S.hp[slot].w = pixel;
+}
+// Warp-synchronous: the lanes with want == true take the CTA's next units (one shared atomic per
+// warp) and start their first sample; a lane whose unit is past the end leaves its slot idle.
+VKD void staged_take_units(const StagedCtx& C, bool want, uint32_t slot, uint32_t lane) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+    if (m == 0u) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&C.S.next_unit, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (!want) return;
+    const uint32_t n = base + __popc(m & ((1u << lane) - 1u));
+    const unsigned long long u = ((unsigned long long)(n >> 5) * gridDim.x + blockIdx.x) * 32ull + (n & 31u);
+    if (u >= C.n_units) {
+        C.S.rd[slot].w = __uint_as_float(0u);
+        return;
+    }
+    const uint32_t b = (uint32_t)(u / C.n_pixels), pixel = (uint32_t)(u - (unsigned long long)b * C.n_pixels);
+    staged_begin_sample(C, slot, pixel, C.a.spp_begin + b * C.a.unit_spp);
+}
+
+template <bool FLAT, bool MEDIA>
+VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf) {
+    extern __shared__ __align__(16) unsigned char vks_raw[];
+    StagedShared& S = *reinterpret_cast<StagedShared*>(vks_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, lanes_below = (1u << lane) - 1u;
+    const StagedCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.n_planes};
+    const size_t plane = (size_t)C.n_pixels * 3u;
+    const uint32_t spp_end = a.spp_begin + a.spp_count;
+    uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0;
+
+    if (tid == 0) S.next_unit = 0u;
+    if (tid < 2 * VKS_CLASSES) (&S.cnt[0][0])[tid] = 0u;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t r = 0; r < VKS_ROUNDS; ++r) staged_take_units(C, true, r * VKS_T + tid, lane); // generate
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t iter = 0;; ++iter) {
+        uint32_t* cnt = S.cnt[iter & 1u];
+        // ---- extend + classify (slot == thread + round * T: conflict-free shared-memory access) -------
+        if (FLAT) {
+#pragma unroll 1
+            for (uint32_t r0 = 0; r0 < VKS_ROUNDS; r0 += VKS_K) {
+                float3 o[VKS_K], d[VKS_K];
+                float tm[VKS_K], best_t[VKS_K];
+                bool live[VKS_K];
+                uint32_t best_hit[VKS_K];
+                MediumXi xi[VKS_K];
+#pragma unroll
+                for (int q = 0; q < VKS_K; ++q) {
+                    const uint32_t slot = (r0 + q) * VKS_T + tid;
+                    const float4 ro = S.ro[slot], rd = S.rd[slot];
+                    o[q] = f3(ro);
+                    d[q] = f3(rd);
+                    tm[q] = ro.w;
+                    live[q] = __float_as_uint(rd.w) != 0u;
+                    xi[q].table = nullptr;
+                    xi[q].depth = __float_as_uint(rd.w);
+                    xi[q].rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                    xi[q].rng.pixel = MEDIA ? S.hp[slot].w : 0u;
+                    xi[q].rng.sample = MEDIA ? __float_as_uint(S.bt[slot].w) : 0u;
+                }
+                trace_flat_k<VKS_K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit); // src/main.rs:130
+#pragma unroll
+                for (int q = 0; q < VKS_K; ++q) {
+                    const uint32_t slot = (r0 + q) * VKS_T + tid;
+                    uint32_t cls = VKS_C_IDLE;
+                    if (live[q]) {
+                        ++n_rays;
+                        n_prims += flat->n;
+                        uint32_t prim = VK_REF_NONE, hi = 0u;
+                        cls = VKS_C_TERMINATE;
+                        if (best_hit[q] != 0xFFFFFFFFu) {
+                            const FlatHit& fh = flat->hits[best_hit[q]];
+                            prim = fh.prim & ~VKD_DUP;
+                            const uint32_t inst = fh.inst;
+                            hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);
+                            cls = fh.cls;
+                        }
+                        S.hp[slot].x = __float_as_uint(best_t[q]);
+                        S.hp[slot].y = prim;
+                        S.hp[slot].z = hi;
+                    }
+#pragma unroll
+                    for (uint32_t c = 0; c < VKS_CLASSES; ++c) {
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cls == c);
+                        if (m) {
+                            uint32_t base = 0;
+                            if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(m));
+                            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                            if (cls == c) S.list[c][base + __popc(m & lanes_below)] = (uint16_t)slot;
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t r = 0; r < VKS_ROUNDS; ++r) {
+                const uint32_t slot = r * VKS_T + tid;
+                const float4 rd = S.rd[slot];
+                const uint32_t depth = __float_as_uint(rd.w);
+                uint32_t cls = VKS_C_IDLE;
+                if (depth) {
+                    const float4 ro = S.ro[slot];
+                    MediumXi xi;
+                    xi.table = nullptr;
+                    xi.depth = depth;
+                    xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                    xi.rng.pixel = MEDIA ? S.hp[slot].w : 0u;
+                    xi.rng.sample = MEDIA ? __float_as_uint(S.bt[slot].w) : 0u;
+                    TraceCounters tc = {0u, 0u};
+                    const TraceHit h = trace<MEDIA>(sc, f3(ro), f3(rd), ro.w, 0.001f, CUDART_INF_F, xi, tc); // src/main.rs:130
+                    ++n_rays;
+                    n_nodes += tc.nodes;
+                    n_prims += tc.prims;
+                    S.hp[slot].x = __float_as_uint(h.t);
+                    S.hp[slot].y = h.prim;
+                    S.hp[slot].z = (h.inst ? (0x80000000u | VKD_INDEX(h.inst)) : 0u) | (h.face << 28);
+                    cls = h.prim == VK_REF_NONE ? (uint32_t)VKS_C_TERMINATE : staged_class_of(sc, h.prim);
+                }
+                // sort: ballot per class, one shared atomic per warp and class, straight into the class's list
+#pragma unroll
+                for (uint32_t c = 0; c < VKS_CLASSES; ++c) {
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, cls == c);
+                    if (m) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(m));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (cls == c) S.list[c][base + __popc(m & lanes_below)] = (uint16_t)slot;
+                    }
+                }
+            }
+        }
+        if (tid < VKS_CLASSES) S.cnt[(iter & 1u) ^ 1u][tid] = 0u; // next iteration's counters (last read before the previous barrier)
+        __syncthreads();
+        const uint32_t c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3];
+        const uint32_t o1 = c0, o2 = c0 + c1, o3 = c0 + c1 + c2, n_live = o3 + c3;
+        if (n_live == 0u) break; // pool drained and no unit left (uniform: every thread reads the same counters)
+        // ---- shade: a warp's 32 consecutive entries are one class (except at the 3 class borders) ------
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < n_live; j0 += VKS_T) {
+            const uint32_t j = j0 + tid;
+            bool new_unit = false;
+            uint32_t slot = 0;
+            if (j < n_live) {
+                slot = j < o1 ? S.list[0][j] : (j < o2 ? S.list[1][j - o1] : (j < o3 ? S.list[2][j - o2] : S.list[3][j - o3]));
+                const float4 ro = S.ro[slot], rd = S.rd[slot], bt = S.bt[slot];
+                const uint4 hp = S.hp[slot];
+                float3 o = f3(ro), d = f3(rd), beta = f3(bt), L = f3(0.0f, 0.0f, 0.0f);
+                float time = ro.w;
+                uint32_t depth = __float_as_uint(rd.w);
+                const uint32_t pixel = hp.w, sample = __float_as_uint(bt.w);
+                const uint32_t prim = hp.y;
+                bool alive, valid = true;
+                if (prim == VK_REF_NONE) {
+                    L = beta * a.background; // src/main.rs:151
+                    alive = false;
+                } else {
+                    PathRng rng;
+                    rng.pixel = pixel;
+                    rng.sample = sample;
+                    rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                    const uint32_t hi = hp.z;
+                    TraceHit h;
+                    h.t = __uint_as_float(hp.x);
+                    h.prim = prim;
+                    h.inst = (hi & 0x80000000u) ? (((uint32_t)VK_T_XFORM << 28) | (hi & 0x07FFFFFFu)) : 0u;
+                    h.face = (hi >> 28) & 7u;
+                    HitRecD rec;
+                    resolve_hit(sc, h, o, d, time, false, rec);
+                    alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
+                    if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
+                    if (alive && !(finite3(d) && finite3(o))) {          // the reference's sample is NaN here (see vk_kernels.cu)
+                        valid = false;
+                        alive = false;
+                    }
+                }
+                if (alive) {
+                    S.ro[slot] = make_float4(o.x, o.y, o.z, time);
+                    S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
+                    S.bt[slot] = make_float4(beta.x, beta.y, beta.z, bt.w);
+                } else { // sample finished: NaN/Inf filter of src/main.rs:191-194, added in order into the unit's plane
+                    const uint32_t rel = sample - a.spp_begin, b = rel / a.unit_spp;
+                    const bool first = rel == b * a.unit_spp;
+                    const uint32_t s_end = min(a.spp_begin + (b + 1u) * a.unit_spp, spp_end);
+                    const bool keep = valid && finite3(L);
+                    if (!keep) ++n_drop;
+                    float* ps = buf.partial_sum + (size_t)b * plane + (size_t)pixel * 3u;
+                    float3 acc = first ? f3(0.0f, 0.0f, 0.0f) : f3(ps[0], ps[1], ps[2]);
+                    if (keep) acc = acc + L;
+                    if (keep || first) {
+                        ps[0] = acc.x;
+                        ps[1] = acc.y;
+                        ps[2] = acc.z;
+                    }
+                    if (buf.partial_sumsq) {
+                        float* pq = buf.partial_sumsq + (size_t)b * plane + (size_t)pixel * 3u;
+                        float3 q = first ? f3(0.0f, 0.0f, 0.0f) : f3(pq[0], pq[1], pq[2]);
+                        if (keep) q = q + L * L;
+                        if (keep || first) {
+                            pq[0] = q.x;
+                            pq[1] = q.y;
+                            pq[2] = q.z;
+                        }
+                    }
+                    if (sample + 1u < s_end) staged_begin_sample(C, slot, pixel, sample + 1u); // regenerate in place
+                    else {
+                        new_unit = true;
+                        S.rd[slot].w = __uint_as_float(0u); // idle unless a unit is left
+                    }
+                }
+            }
+            staged_take_units(C, new_unit, slot, lane);
+        }
+        __syncthreads();
+    }
+    unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = n_nodes, w_prims = n_prims;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        w_rays += __shfl_xor_sync(0xFFFFFFFFu, w_rays, off);
+        w_drop += __shfl_xor_sync(0xFFFFFFFFu, w_drop, off);
+        w_nodes += __shfl_xor_sync(0xFFFFFFFFu, w_nodes, off);
+        w_prims += __shfl_xor_sync(0xFFFFFFFFu, w_prims, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&buf.counters[3], w_nodes);
+        atomicAdd(&buf.counters[4], w_prims);
+        atomicAdd(&buf.counters[0], w_rays);
+        if (w_drop) atomicAdd(&buf.counters[1], w_drop);
+    }
+}
+
+template <bool MEDIA>
+__global__ void __launch_bounds__(VKS_T, 3) k_staged(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf) {
+    staged_body<false, MEDIA>(sc, nullptr, cam, a, buf);
+}
+template <bool MEDIA>
+__global__ void __launch_bounds__(VKS_T, 3) k_staged_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
+                                                          const RenderArgs a, const RenderBuffers buf) {
+    staged_body<true, MEDIA>(sc, &flat, cam, a, buf);
+}
+
+template <class K> static cudaError_t staged_prepare(K kernel, int* blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StagedShared));
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, VKS_T, sizeof(StagedShared));
+}
+
+// grid = sm_count * resident CTAs
+cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
+                          int sm_count, cudaStream_t st) {
+    int bps = 0;
+    cudaError_t e;
+    const size_t smem = sizeof(StagedShared);
+    if (flat && flat->n) {
+        if (sc.has_media) {
+            if ((e = staged_prepare(k_staged_flat<true>, &bps)) != cudaSuccess) return e;
+            k_staged_flat<true><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, *flat, cam, a, b);
+        } else {
+            if ((e = staged_prepare(k_staged_flat<false>, &bps)) != cudaSuccess) return e;
+            k_staged_flat<false><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, *flat, cam, a, b);
+        }
+    } else {
+        if (sc.has_media) {
+            if ((e = staged_prepare(k_staged<true>, &bps)) != cudaSuccess) return e;
+            k_staged<true><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, cam, a, b);
+        } else {
+            if ((e = staged_prepare(k_staged<false>, &bps)) != cudaSuccess) return e;
+            k_staged<false><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, cam, a, b);
+        }
+    }
+    return cudaGetLastError();
+}
+
+} // namespace VK_NS
