@@ -25,6 +25,7 @@ struct vk_ctx {
     DScene scene{};
     FlatProgram flat{}; // flat.n == 0: scene too large, BVH traversal
     bool has_scene = false;
+    unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
     float* partial = nullptr;               // chunk partial sums (sum | sumsq)
     size_t partial_floats = 0;
@@ -507,6 +508,8 @@ int vk_create(int device, vk_ctx** out) {
     CUC(cudaEventCreate(&c->ev2));
     CUC(cudaMalloc((void**)&c->counters, 8 * sizeof(unsigned long long)));
     CUC(cudaMemset(c->counters, 0, 8 * sizeof(unsigned long long)));
+    CUC(cudaMalloc((void**)&c->debug, VK_DEBUG_CTAS * 4 * sizeof(unsigned long long)));
+    CUC(cudaMemset(c->debug, 0, VK_DEBUG_CTAS * 4 * sizeof(unsigned long long)));
 #undef CUC
     *out = c;
     return VK_OK;
@@ -522,6 +525,7 @@ void vk_destroy(vk_ctx* c) {
     if (c->frame) cudaFree(c->frame);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->counters) cudaFree(c->counters);
+    if (c->debug) cudaFree(c->debug);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -709,11 +713,17 @@ static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCam
 }
 
 
-// VK_VARIANT_AUTO: the megakernel.  Evidence (profiles/): on every config the
-// persistent megakernel is ahead of the wavefront kernels on B200 -- the scenes are cache resident,
-// so the wavefront's queue traffic and launch boundaries buy coherence the megakernel already has.
-static uint32_t choose_variant(const vk_ctx*, const vk_render_params* P) {
-    return P->variant == VK_VARIANT_AUTO ? (uint32_t)VK_VARIANT_MEGAKERNEL : P->variant;
+// VK_VARIANT_AUTO, by the measurements recorded in profiles/ and DESIGN.md section 4:
+//   scene small enough for the flat program  -> STAGED (Cornell 600x600x1000: 67 ms against 80 ms for
+//       the lane megakernel and 138 ms for the global wavefront; 20 of 32 lanes active against 15,
+//       instruction-fetch stalls gone)
+//   BVH scenes                               -> MEGAKERNEL (final scene: 49 ms against 78 ms staged and
+//       98 ms wavefront: while-while traversal diverges whatever the staging, and the lane
+//       megakernel keeps 32 warps per SM against 24)
+static uint32_t choose_variant(const vk_ctx* c, const vk_render_params* P) {
+    if (P->variant != VK_VARIANT_AUTO) return P->variant;
+    const bool flat = c->flat.n && !(P->flags & VK_FLAG_FORCE_BVH);
+    return flat ? (uint32_t)VK_VARIANT_STAGED : (uint32_t)VK_VARIANT_MEGAKERNEL;
 }
 
 // shared body of vk_render / vk_render_device
@@ -750,12 +760,26 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     a.background = make_float3(P->background[0], P->background[1], P->background[2]);
     a.tiles_x = (P->width + 7) / 8;
     a.tiles_y = (P->height + 3) / 4;
-    // Sample blocks ("units"): at most 128 planes of partial sums, at least 8 samples per block.
-    // The block size depends only on the sample count of the call, so a render is bit-identical
-    // for a given (seed, spp slice) whatever the grid or the chunking.
-    a.unit_spp = count <= 8 ? count : (count + 127) / 128;
-    if (a.unit_spp < 8 && count > 8) a.unit_spp = 8;
-    a.n_planes = (count + a.unit_spp - 1) / a.unit_spp;
+    // Sample blocks ("units") and their planes of partial sums.  A unit's samples are traced one after
+    // the other by whoever owns the unit, so a unit of k samples on a pixel whose paths run to
+    // max_depth holds a lane for k * max_depth segments while the rest of the GPU has drained
+    // (measured: 8-sample units cost Cornell a 2.8 ms tail, 523 iterations in the slowest CTA).
+    // HBM is cheap here: one plane per SAMPLE when that fits the plane budget (default 6 GiB:
+    // Cornell 600x600x1000 = 4.3 GB of planes, written once with plain stores and summed in order by
+    // k_reduce_chunks at HBM speed), otherwise the smallest block that fits.  The block size depends
+    // only on the call's parameters, so a render is bit-identical per (seed, spp slice, size).
+    {
+        size_t budget = 6ull << 30;
+        if (const char* e = std::getenv("VECCHIO_PLANE_BUDGET_MB")) {
+            const long v = std::atol(e);
+            if (v > 0) budget = (size_t)v << 20;
+        }
+        const size_t plane_bytes = (size_t)P->width * P->height * 3 * sizeof(float) * (d_sumsq ? 2 : 1);
+        size_t max_planes = budget / plane_bytes;
+        if (max_planes < 1) max_planes = 1;
+        a.unit_spp = (uint32_t)((count + max_planes - 1) / max_planes);
+        a.n_planes = (count + a.unit_spp - 1) / a.unit_spp;
+    }
     // Chunks of whole blocks, sized for ~48 work items per resident warp (small items keep the
     // end-of-kernel tail short; an item costs one atomic).
     const uint32_t n_tiles = a.tiles_x * a.tiles_y;
@@ -769,6 +793,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     const size_t plane = (size_t)P->width * P->height * 3;
     RenderBuffers b{};
     b.counters = c->counters;
+    b.debug = c->debug;
     if (a.n_planes == 1) {
         b.partial_sum = d_sum;
         b.partial_sumsq = d_sumsq;
@@ -787,8 +812,11 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         int rc = wf_render(c, strict, flat, dc, a, b, d_sumsq != nullptr, &launches);
         if (rc != VK_OK) return rc;
     } else if (variant == VK_VARIANT_STAGED) {
-        CU(c, strict ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->sm_count, c->stream)
-                     : vkfast::launch_staged(c->scene, flat, dc, a, b, c->sm_count, c->stream));
+        CU(c, cudaMemsetAsync(c->counters + 5, 0xFF, 2 * sizeof(unsigned long long), c->stream)); // CTA start / first end: minima
+        CU(c, cudaMemsetAsync(c->counters + 7, 0, sizeof(unsigned long long), c->stream));        // last end: maximum
+        CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
+        CU(c, strict ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
+                     : vkfast::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream));
         launches = 1;
     } else {
         CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)
@@ -963,6 +991,23 @@ int vk_measure_peaks(vk_ctx* c, float* fp32_tflops, float* l2_gbs) {
     cudaFree(buf);
     cudaFree(sink);
     CU(c, cudaGetLastError());
+    return VK_OK;
+}
+
+// Debug hook: the raw counter block (see RenderBuffers); [5..7] = first CTA start, first and last CTA end of the
+// last staged launch (globaltimer ns).
+int vk_debug_counters(vk_ctx* c, unsigned long long out[8]) {
+    if (!c || !out) return VK_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(out, c->counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return VK_OK;
+}
+int vk_debug_ctas(vk_ctx* c, unsigned long long* out, size_t n_ctas) {
+    if (!c || !out || n_ctas > VK_DEBUG_CTAS) return VK_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(out, c->debug, n_ctas * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return VK_OK;
 }
 

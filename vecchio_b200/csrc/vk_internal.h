@@ -134,7 +134,9 @@ struct RenderBuffers {
     float* partial_sum;   // n_planes x W*H*3 (== d_sum when n_planes == 1)
     float* partial_sumsq; // same, nullable
     unsigned long long* counters;
+    unsigned long long* debug; // VK_DEBUG_CTAS x {end time ns, rays traced, smid, -} of the staged kernel's CTAs
 };
+#define VK_DEBUG_CTAS 2048
 
 // ------------------------------------------------------------------------------------------------
 // Wavefront variant: a pool of path slots in device memory (L2-resident at the default pool size),
@@ -176,7 +178,7 @@ struct WfState {
     cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads);                               \
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
     cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,      \
-                              const RenderBuffers& b, int sm_count, cudaStream_t st);                              \
+                              const RenderBuffers& b, unsigned long long* unit_head, int sm_count, cudaStream_t st);   \
     cudaError_t launch_wf_generate(const DCamera& cam, const RenderArgs& a, const WfState& w, cudaStream_t st);        \
     cudaError_t launch_wf_extend(const DScene& sc, const FlatProgram* flat, const RenderArgs& a, const WfState& w,     \
                                  const RenderBuffers& b, uint32_t set, cudaStream_t st);                               \

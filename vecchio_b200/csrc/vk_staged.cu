@@ -28,6 +28,8 @@ namespace VK_NS {
 #define VKS_NEWUNIT 0x80000000u
 enum { VKS_C_TERMINATE = 0, VKS_C_DIELECTRIC = 1, VKS_C_METAL = 2, VKS_C_DIFFUSE = 3, VKS_CLASSES = 4, VKS_C_IDLE = 7 };
 
+#define VKS_CHUNK 256u // units a CTA takes from the global queue at a time
+#define VKS_RING 8u    // chunk bases kept: RING * CHUNK >= N + 2 * CHUNK
 #ifndef VKS_K
 #define VKS_K 2 // rays a thread traces together through the flat program
 #endif
@@ -38,7 +40,9 @@ struct StagedShared {
     uint4 hp[VKS_N];                   // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; pixel
     uint16_t list[VKS_CLASSES][VKS_N]; // live slots by shading class (each class can hold the whole pool)
     uint32_t cnt[2][VKS_CLASSES];      // class counts, double buffered by iteration parity
-    uint32_t next_unit;                // CTA-local unit counter
+    uint32_t next_unit;                // CTA-local unit counter (local index n)
+    uint32_t fetched;                  // local indices [0, fetched) are backed by a chunk
+    unsigned long long chunk_base[VKS_RING]; // global unit of local index n: chunk_base[(n / VKS_CHUNK) % VKS_RING] + n % VKS_CHUNK
 };
 
 VKD uint32_t staged_class_of(const DScene& sc, uint32_t prim) {
@@ -55,17 +59,27 @@ VKD uint32_t staged_class_of(const DScene& sc, uint32_t prim) {
     return t == VK_M_DIFFUSE_LIGHT ? VKS_C_TERMINATE : t == VK_M_DIELECTRIC ? VKS_C_DIELECTRIC : t == VK_M_METAL ? VKS_C_METAL : VKS_C_DIFFUSE;
 }
 
-// Units are dealt to the CTAs statically, 32 at a time round-robin (unit = (pixel, sample block),
-// pixels row-major): every CTA samples the whole frame evenly, so the CTAs finish together without
-// a global queue; inside the CTA the slots draw from `next_unit` with a shared-memory atomic.
-//   local index n  ->  unit ((n / 32) * gridDim.x + blockIdx.x) * 32 + n % 32
+// Units (unit = (pixel, sample block), pixels row-major) come from one global queue in chunks of
+// VKS_CHUNK: thread 0 refills the CTA's chunk ring during the extend stage whenever fewer than a
+// pool's worth of units is backed (one global atomic per chunk, off everybody's critical path: the
+// barrier between extend and shade publishes it); inside the CTA the slots draw local indices from
+// `next_unit` with a shared-memory atomic.  Fast SMs simply take more chunks, so all CTAs finish
+// within a chunk of each other whatever their speed.
 struct StagedCtx {
     const DCamera& cam;
     const RenderArgs& a;
     StagedShared& S;
     uint32_t n_pixels;
     unsigned long long n_units;
+    unsigned long long* unit_head;
 };
+VKD void staged_refill(const StagedCtx& C) { // one thread
+    StagedShared& S = C.S;
+    while (S.fetched < S.next_unit + VKS_N) {
+        S.chunk_base[(S.fetched / VKS_CHUNK) % VKS_RING] = atomicAdd(C.unit_head, (unsigned long long)VKS_CHUNK);
+        S.fetched += VKS_CHUNK;
+    }
+}
 // Start the sample `s` of `pixel` in `slot`: Camera::get_ray, depth 1 (src/main.rs:187-190).
 VKD void staged_begin_sample(const StagedCtx& C, uint32_t slot, uint32_t pixel, uint32_t s) {
     PathRng rng;
@@ -91,7 +105,7 @@ VKD void staged_take_units(const StagedCtx& C, bool want, uint32_t slot, uint32_
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (!want) return;
     const uint32_t n = base + __popc(m & ((1u << lane) - 1u));
-    const unsigned long long u = ((unsigned long long)(n >> 5) * gridDim.x + blockIdx.x) * 32ull + (n & 31u);
+    const unsigned long long u = C.S.chunk_base[(n / VKS_CHUNK) % VKS_RING] + (n % VKS_CHUNK);
     if (u >= C.n_units) {
         C.S.rd[slot].w = __uint_as_float(0u);
         return;
@@ -101,16 +115,25 @@ VKD void staged_take_units(const StagedCtx& C, bool want, uint32_t slot, uint32_
 }
 
 template <bool FLAT, bool MEDIA>
-VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf) {
+VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
+                     unsigned long long* unit_head) {
     extern __shared__ __align__(16) unsigned char vks_raw[];
     StagedShared& S = *reinterpret_cast<StagedShared*>(vks_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lanes_below = (1u << lane) - 1u;
-    const StagedCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.n_planes};
+    const StagedCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.n_planes, unit_head};
     const size_t plane = (size_t)C.n_pixels * 3u;
     const uint32_t spp_end = a.spp_begin + a.spp_count;
     uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0;
+    uint32_t dbg_iters = 0, dbg_sparse = 0; // iterations run; iterations with fewer than N/8 live slots
 
-    if (tid == 0) S.next_unit = 0u;
+    if (tid == 0) {
+        S.next_unit = 0u;
+        S.fetched = 0u;
+        staged_refill(C);
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        atomicMin(&buf.counters[5], t0); // debug: first CTA start / first and last CTA end (ns)
+    }
     if (tid < 2 * VKS_CLASSES) (&S.cnt[0][0])[tid] = 0u;
     __syncthreads();
 #pragma unroll 1
@@ -119,6 +142,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
 #pragma unroll 1
     for (uint32_t iter = 0;; ++iter) {
         uint32_t* cnt = S.cnt[iter & 1u];
+        if (tid == 0) staged_refill(C); // consumed by the shade stage, after the barrier
         // ---- extend + classify (slot == thread + round * T: conflict-free shared-memory access) -------
         if (FLAT) {
 #pragma unroll 1
@@ -142,6 +166,10 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                     xi[q].rng.pixel = MEDIA ? S.hp[slot].w : 0u;
                     xi[q].rng.sample = MEDIA ? __float_as_uint(S.bt[slot].w) : 0u;
                 }
+                bool any_live = false;
+#pragma unroll
+                for (int q = 0; q < VKS_K; ++q) any_live = any_live || live[q];
+                if (!__any_sync(0xFFFFFFFFu, any_live)) continue; // draining pool: nothing for this warp in these rounds
                 trace_flat_k<VKS_K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit); // src/main.rs:130
 #pragma unroll
                 for (int q = 0; q < VKS_K; ++q) {
@@ -218,6 +246,8 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
         const uint32_t c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3];
         const uint32_t o1 = c0, o2 = c0 + c1, o3 = c0 + c1 + c2, n_live = o3 + c3;
         if (n_live == 0u) break; // pool drained and no unit left (uniform: every thread reads the same counters)
+        ++dbg_iters;
+        if (n_live < VKS_N / 8) ++dbg_sparse;
         // ---- shade: a warp's 32 consecutive entries are one class (except at the 3 class borders) ------
 #pragma unroll 1
         for (uint32_t j0 = 0; j0 < n_live; j0 += VKS_T) {
@@ -296,6 +326,9 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
         }
         __syncthreads();
     }
+    __shared__ unsigned long long s_cta_rays;
+    if (tid == 0) s_cta_rays = 0ull;
+    __syncthreads();
     unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = n_nodes, w_prims = n_prims;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -309,17 +342,34 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
         atomicAdd(&buf.counters[4], w_prims);
         atomicAdd(&buf.counters[0], w_rays);
         if (w_drop) atomicAdd(&buf.counters[1], w_drop);
+        atomicAdd(&s_cta_rays, w_rays);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        atomicMin(&buf.counters[6], t1);
+        atomicMax(&buf.counters[7], t1);
+        if (buf.debug && blockIdx.x < VK_DEBUG_CTAS) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            buf.debug[4 * blockIdx.x + 0] = t1;
+            buf.debug[4 * blockIdx.x + 1] = s_cta_rays;
+            buf.debug[4 * blockIdx.x + 2] = smid;
+            buf.debug[4 * blockIdx.x + 3] = dbg_iters | ((unsigned long long)dbg_sparse << 32);
+        }
     }
 }
 
 template <bool MEDIA>
-__global__ void __launch_bounds__(VKS_T, 3) k_staged(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf) {
-    staged_body<false, MEDIA>(sc, nullptr, cam, a, buf);
+__global__ void __launch_bounds__(VKS_T, 3) k_staged(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
+                                                     unsigned long long* unit_head) {
+    staged_body<false, MEDIA>(sc, nullptr, cam, a, buf, unit_head);
 }
 template <bool MEDIA>
 __global__ void __launch_bounds__(VKS_T, 3) k_staged_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
-                                                          const RenderArgs a, const RenderBuffers buf) {
-    staged_body<true, MEDIA>(sc, &flat, cam, a, buf);
+                                                          const RenderArgs a, const RenderBuffers buf, unsigned long long* unit_head) {
+    staged_body<true, MEDIA>(sc, &flat, cam, a, buf, unit_head);
 }
 
 template <class K> static cudaError_t staged_prepare(K kernel, int* blocks_per_sm) {
@@ -328,27 +378,27 @@ template <class K> static cudaError_t staged_prepare(K kernel, int* blocks_per_s
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, VKS_T, sizeof(StagedShared));
 }
 
-// grid = sm_count * resident CTAs
+// grid = sm_count * resident CTAs; *unit_head must be zero on the stream before the launch
 cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
-                          int sm_count, cudaStream_t st) {
+                          unsigned long long* unit_head, int sm_count, cudaStream_t st) {
     int bps = 0;
     cudaError_t e;
     const size_t smem = sizeof(StagedShared);
     if (flat && flat->n) {
         if (sc.has_media) {
             if ((e = staged_prepare(k_staged_flat<true>, &bps)) != cudaSuccess) return e;
-            k_staged_flat<true><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, *flat, cam, a, b);
+            k_staged_flat<true><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, *flat, cam, a, b, unit_head);
         } else {
             if ((e = staged_prepare(k_staged_flat<false>, &bps)) != cudaSuccess) return e;
-            k_staged_flat<false><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, *flat, cam, a, b);
+            k_staged_flat<false><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, *flat, cam, a, b, unit_head);
         }
     } else {
         if (sc.has_media) {
             if ((e = staged_prepare(k_staged<true>, &bps)) != cudaSuccess) return e;
-            k_staged<true><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, cam, a, b);
+            k_staged<true><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, cam, a, b, unit_head);
         } else {
             if ((e = staged_prepare(k_staged<false>, &bps)) != cudaSuccess) return e;
-            k_staged<false><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, cam, a, b);
+            k_staged<false><<<sm_count * (bps < 1 ? 1 : bps), VKS_T, smem, st>>>(sc, cam, a, b, unit_head);
         }
     }
     return cudaGetLastError();
