@@ -53,6 +53,14 @@ def alg_work(scene_name):
     return d.get(scene_name)
 
 
+def ncu_traffic(config, variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    summary of one `ncu --set full` capture of this config (profiles/ncu_traffic.json, written by
+    profiles/summarize.py from the report); None when no capture of this (config, variant) exists."""
+    d = load_json(os.path.join(ROOT, "profiles", "ncu_traffic.json"), {}) or {}
+    return (d.get(f"{config}:{variant}") or {}).get("dram_bytes_per_launch")
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -157,7 +165,9 @@ def run_ours(args, cfg):
     ctx.set_stream(stream.cuda_stream)
 
     # spp sharding: rank k renders global samples [k*spp/N, (k+1)*spp/N)
-    s0, s1 = rank * spp // world, (rank + 1) * spp // world
+    from vecchio_b200.sharding import reduce_sums_to_root, spp_slice
+    s0, s_count = spp_slice(rank, world, spp)
+    s1 = s0 + s_count
     n = W * H * 3
     d_sum = torch.empty(n, dtype=torch.float32, device=dev)
     d_rgb = torch.empty(n, dtype=torch.float32, device=dev)
@@ -169,8 +179,7 @@ def run_ours(args, cfg):
 
     def step_device(seed):
         ctx.render_device(cam, params(seed), d_sum.data_ptr(), want_stats=False)
-        if world > 1:
-            dist.reduce(d_sum, dst=0, op=dist.ReduceOp.SUM)  # NCCL over NVLink, same stream
+        reduce_sums_to_root(d_sum, world)  # one NCCL reduce(sum) over NVLink on the same stream
         if rank == 0:
             ctx.finalize_device(d_sum.data_ptr(), d_rgb.data_ptr(), n, spp)
 
@@ -221,6 +230,8 @@ def run_ours(args, cfg):
     # ---- kernel-only time of the dominant kernel (CUDA events inside the library) ---------------
     kst = ctx.render_device(cam, params(77), d_sum.data_ptr(), want_stats=True)
     k_ms, k_rays, k_paths = kst.ms_kernels, kst.rays, kst.paths
+    variant_name = {1: "megakernel", 2: "wavefront", 3: "staged"}.get(kst.variant, str(kst.variant))
+    kernel_name = {1: "k_megakernel", 2: "k_wf_extend + k_wf_shade", 3: "k_staged"}.get(kst.variant, "?") + ("_flat" if scene.nbytes() < 4096 and kst.variant != 2 else "")
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------
     for i in range(2):
@@ -243,8 +254,8 @@ def run_ours(args, cfg):
         if flops_ray:
             achieved = flops_ray * k_rays / (k_ms * 1e-3) / 1e12
             roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                        "traffic": (load_json(os.path.join(ROOT, "profiles", "ncu_summary.json"), {}) or {}).get("dram_bytes_per_launch"),
-                        "kernel": "k_megakernel", "kernel_ms": k_ms, "alg_flops_per_ray": flops_ray,
+                        "traffic": ncu_traffic(args.config, variant_name),
+                        "kernel": kernel_name, "kernel_ms": k_ms, "alg_flops_per_ray": flops_ray,
                         "peak_source": "FFMA microbenchmark vk_measure_peaks, measured live (MEASURED_PEAKS.json has no fp32 figure)",
                         "hbm_view": {"alg_bytes_per_ray": bytes_ray, "achieved_gbs": bytes_ray * k_rays / (k_ms * 1e-3) / 1e9 if bytes_ray else None,
                                      "peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "measured" if peaks else "fallback",
@@ -257,7 +268,7 @@ def run_ours(args, cfg):
                                        f"(BASELINE.json configs[{list(CONFIGS).index(args.config)}])",
                            "parallelism": f"spp-sharded x{world}, NCCL reduce(sum) of {n * 4} B to rank 0" if world > 1 else "single GPU",
                            "seed": "1..K (one per step)", "l2": "256 MB memset between timed steps; scene itself is KB-sized and cache-resident by design",
-                           "variant": "megakernel", "scene_bytes": scene.nbytes()},
+                           "variant": variant_name, "scene_bytes": scene.nbytes()},
                 "e2e": {"value": e2e_paths / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene.nbytes() + 96 + 56,
                         "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": int(launches), "dropped_samples": int(dropped), "clocks": clocks, "roofline": roofline,
