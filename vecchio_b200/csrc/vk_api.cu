@@ -25,6 +25,7 @@ struct vk_ctx {
     DScene scene{};
     FlatProgram flat{}; // flat.n == 0: scene too large, BVH traversal
     bool has_scene = false;
+    uint32_t n_nodes = 0; // BVH nodes of the uploaded scene
     unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
     float* partial = nullptr;               // chunk partial sums (sum | sumsq)
@@ -628,6 +629,7 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     s.has_media = d->n_media > 0;
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
+    c->n_nodes = d->n_nodes;
     FlatBuilder fb;
     fb.d = d;
     if (!fb.build(&c->flat)) c->flat = FlatProgram{};
@@ -726,6 +728,20 @@ static uint32_t choose_variant(const vk_ctx* c, const vk_render_params* P) {
     return flat ? (uint32_t)VK_VARIANT_STAGED : (uint32_t)VK_VARIANT_MEGAKERNEL;
 }
 
+// Lane megakernel for a BVH scene: static (one whole ray per lane and loop iteration) or dynamic
+// (resumable traversal under warp votes with re-fill).  Measured on B200 (profiles/r1_configs_dyn.log):
+// the dynamic kernel wins where traversal lengths have a long tail -- 10^6 spheres, 66 node visits per
+// ray: 62 ms against 96 ms, 15.6 against 4.5 lanes active -- and loses on the small heterogeneous
+// scenes (final scene 57 ms against 44 ms, random spheres 13.8 against 13.1 ms), where shading is a
+// larger share of the work and runs with few lanes during a re-fill.  VECCHIO_MEGA=static|dynamic overrides.
+static bool use_dynamic_megakernel(const vk_ctx* c) {
+    if (const char* e = std::getenv("VECCHIO_MEGA")) {
+        if (!std::strcmp(e, "static")) return false;
+        if (!std::strcmp(e, "dynamic")) return true;
+    }
+    return c->n_nodes >= 65536u;
+}
+
 // shared body of vk_render / vk_render_device
 static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* d_sum, float* d_sumsq, vk_stats* stats) {
     if (!c) return VK_ERR_INVALID;
@@ -817,6 +833,11 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
         CU(c, strict ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
                      : vkfast::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream));
+        launches = 1;
+    } else if (!flat && use_dynamic_megakernel(c)) {
+        CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
+        CU(c, strict ? vkstrict::launch_megakernel_dyn(c->scene, dc, a, b, c->counters + 2, c->sm_count, c->stream)
+                     : vkfast::launch_megakernel_dyn(c->scene, dc, a, b, c->counters + 2, c->sm_count, c->stream));
         launches = 1;
     } else {
         CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)

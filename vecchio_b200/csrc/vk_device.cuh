@@ -362,100 +362,124 @@ struct TraceCounters {
     uint32_t nodes, prims;
 };
 
+// The traversal as a resumable state machine: one call of trav_node_step / trav_prim_step advances
+// one lane by one node visit / one primitive test.  trace() below runs it to completion for one ray
+// (while-while); the dynamic megakernel (vk_kernels.cu) interleaves steps of all the lanes of a warp
+// under warp votes and leaves the loop to re-fill idle lanes.
+struct Trav {
+    uint32_t stack[VKD_STACK];
+    int sp;
+    float3 co, cd, cinv; // ray in the current frame (world, or the frame of the instance being traversed)
+    uint32_t cur_inst;
+    uint32_t ref;  // what to process next; VKD_DONE when the traversal has finished
+    bool enter;    // `ref` is a BVH root whose own box has not been tested yet
+    TraceHit best;
+};
+VKD void trav_init(Trav& T, const DScene& sc, float3 o, float3 d, float tmax) {
+    T.sp = 0;
+    T.co = o;
+    T.cd = d;
+    T.cinv = rcp3(d);
+    T.cur_inst = 0;
+    T.best.t = tmax;
+    T.best.prim = VK_REF_NONE;
+    T.best.inst = 0;
+    T.best.face = 0;
+    T.ref = sc.root;
+    T.enter = true;
+}
+VKD uint32_t trav_pop(Trav& T) { return T.sp ? T.stack[--T.sp] : VKD_DONE; }
+VKD bool trav_at_node(const Trav& T) { return T.ref != VKD_DONE && VKD_TYPE(T.ref) == VK_T_NODE; }
+// precondition: trav_at_node(T)
+VKD void trav_node_step(Trav& T, const DScene& sc, float tmin, TraceCounters& tc) {
+    const uint32_t ni = VKD_INDEX(T.ref);
+    if (T.enter) { // BVHNode::hit's own `bb.hit` for the world root / an instanced sub-BVH root
+        T.enter = false;
+        const float4 n0 = __ldg(&sc.nodes[2 * ni]), n1 = __ldg(&sc.nodes[2 * ni + 1]);
+        float te;
+        if (!aabb_hit(f3(n0), f3(n1), T.co, T.cd, T.cinv, tmin, T.best.t, te)) {
+            T.ref = trav_pop(T);
+            return;
+        }
+    }
+    ++tc.nodes;
+    const float4 w0 = __ldg(&sc.wnodes[4 * ni]), w1 = __ldg(&sc.wnodes[4 * ni + 1]);
+    const uint32_t left = __float_as_uint(w0.w), right = __float_as_uint(w1.w);
+    bool hl = true, hr = right != VK_REF_NONE;
+    float tl = -CUDART_INF_F, tr = -CUDART_INF_F; // a primitive child is simply visited, left first
+    if (VKD_TYPE(left) == VK_T_NODE) hl = aabb_hit(f3(w0), f3(w1), T.co, T.cd, T.cinv, tmin, T.best.t, tl);
+    if (VKD_TYPE(right) == VK_T_NODE) {
+        const float4 w2 = __ldg(&sc.wnodes[4 * ni + 2]), w3 = __ldg(&sc.wnodes[4 * ni + 3]);
+        hr = aabb_hit(f3(w2), f3(w3), T.co, T.cd, T.cinv, tmin, T.best.t, tr);
+    }
+    if (hl && hr) {
+        const bool left_first = tl <= tr;
+        T.stack[T.sp++] = left_first ? right : left;
+        T.ref = left_first ? left : right;
+    } else if (hl) {
+        T.ref = left;
+    } else if (hr) {
+        T.ref = right;
+    } else {
+        T.ref = trav_pop(T);
+    }
+}
+// precondition: T.ref is neither VKD_DONE nor a node; (o, d) is the world ray
+template <bool MEDIA>
+VKD void trav_prim_step(Trav& T, const DScene& sc, float3 o, float3 d, float time, float tmin, const MediumXi& xi, TraceCounters& tc) {
+    const uint32_t ref = T.ref;
+    const uint32_t type = VKD_TYPE(ref);
+    if (type == VKD_T_EXIT) { // leave the instanced sub-BVH
+        T.co = o;
+        T.cd = d;
+        T.cinv = rcp3(d);
+        T.cur_inst = 0;
+    } else if (type != VK_T_NONE) {
+        float3 to = T.co, td = T.cd, tinv = T.cinv;
+        uint32_t leaf = ref, inst = T.cur_inst;
+        if (type == VK_T_XFORM) {
+            leaf = chain_down(sc, ref, to, td) | (ref & VKD_DUP);
+            inst = ref & ~VKD_DUP;
+            if (VKD_TYPE(leaf) == VK_T_NODE) { // instanced sub-BVH: traverse it in object space
+                T.stack[T.sp++] = VKD_T_EXIT << 28;
+                T.co = to;
+                T.cd = td;
+                T.cinv = rcp3(td);
+                T.cur_inst = inst;
+                T.ref = leaf & ~VKD_DUP;
+                T.enter = true;
+                return;
+            }
+            tinv = rcp3(td);
+        }
+        float t;
+        uint32_t face = 0;
+        bool hit;
+        ++tc.prims;
+        if (MEDIA && VKD_TYPE(leaf) == VK_T_MEDIUM) hit = medium_t(sc, leaf, to, td, time, tmin, T.best.t, xi, t);
+        else hit = leaf_t(sc, leaf, to, td, tinv, time, tmin, T.best.t, t, face);
+        if (hit) {
+            T.best.t = t;
+            T.best.prim = leaf & ~VKD_DUP;
+            T.best.inst = inst;
+            T.best.face = face;
+        }
+    }
+    T.ref = trav_pop(T);
+}
+
 template <bool MEDIA>
 VKD TraceHit trace(const DScene& sc, float3 o, float3 d, float time, float tmin, float tmax, const MediumXi& xi, TraceCounters& tc) {
-    uint32_t stack[VKD_STACK];
-    int sp = 0;
-    float3 co = o, cd = d; // ray in the current frame (world, or the frame of the instance being traversed)
-    float3 cinv = rcp3(d);
-    uint32_t cur_inst = 0;
-    TraceHit best;
-    best.t = tmax;
-    best.prim = VK_REF_NONE;
-    best.inst = 0;
-    best.face = 0;
-    uint32_t ref = sc.root;
-    bool enter = true; // `ref` is a BVH root whose own box has not been tested yet
+    Trav T;
+    trav_init(T, sc, o, d, tmax);
 #pragma unroll 1
     for (;;) {
-        // ---- node phase ---------------------------------------------------------------------
 #pragma unroll 1
-        while (VKD_TYPE(ref) == VK_T_NODE) {
-            const uint32_t ni = VKD_INDEX(ref);
-            if (enter) { // BVHNode::hit's own `bb.hit` for the world root / an instanced sub-BVH root
-                enter = false;
-                const float4 n0 = __ldg(&sc.nodes[2 * ni]), n1 = __ldg(&sc.nodes[2 * ni + 1]);
-                float te;
-                if (!aabb_hit(f3(n0), f3(n1), co, cd, cinv, tmin, best.t, te)) {
-                    ref = sp ? stack[--sp] : VKD_DONE;
-                    continue;
-                }
-            }
-            ++tc.nodes;
-            const float4 w0 = __ldg(&sc.wnodes[4 * ni]), w1 = __ldg(&sc.wnodes[4 * ni + 1]);
-            const uint32_t left = __float_as_uint(w0.w), right = __float_as_uint(w1.w);
-            bool hl = true, hr = right != VK_REF_NONE;
-            float tl = -CUDART_INF_F, tr = -CUDART_INF_F; // a primitive child is simply visited, left first
-            if (VKD_TYPE(left) == VK_T_NODE) hl = aabb_hit(f3(w0), f3(w1), co, cd, cinv, tmin, best.t, tl);
-            if (VKD_TYPE(right) == VK_T_NODE) {
-                const float4 w2 = __ldg(&sc.wnodes[4 * ni + 2]), w3 = __ldg(&sc.wnodes[4 * ni + 3]);
-                hr = aabb_hit(f3(w2), f3(w3), co, cd, cinv, tmin, best.t, tr);
-            }
-            if (hl && hr) {
-                const bool left_first = tl <= tr;
-                stack[sp++] = left_first ? right : left;
-                ref = left_first ? left : right;
-            } else if (hl) {
-                ref = left;
-            } else if (hr) {
-                ref = right;
-            } else {
-                ref = sp ? stack[--sp] : VKD_DONE;
-            }
-        }
-        if (ref == VKD_DONE) break;
-        // ---- primitive phase ----------------------------------------------------------------
-        const uint32_t type = VKD_TYPE(ref);
-        if (type == VKD_T_EXIT) { // leave the instanced sub-BVH
-            co = o;
-            cd = d;
-            cinv = rcp3(d);
-            cur_inst = 0;
-        } else if (type != VK_T_NONE) {
-            float3 to = co, td = cd, tinv = cinv;
-            uint32_t leaf = ref, inst = cur_inst;
-            if (type == VK_T_XFORM) {
-                leaf = chain_down(sc, ref, to, td) | (ref & VKD_DUP);
-                inst = ref & ~VKD_DUP;
-                if (VKD_TYPE(leaf) == VK_T_NODE) { // instanced sub-BVH: traverse it in object space
-                    stack[sp++] = VKD_T_EXIT << 28;
-                    co = to;
-                    cd = td;
-                    cinv = rcp3(td);
-                    cur_inst = inst;
-                    ref = leaf & ~VKD_DUP;
-                    enter = true;
-                    continue;
-                }
-                tinv = rcp3(td);
-            }
-            float t;
-            uint32_t face = 0;
-            bool hit;
-            ++tc.prims;
-            if (MEDIA && VKD_TYPE(leaf) == VK_T_MEDIUM) hit = medium_t(sc, leaf, to, td, time, tmin, best.t, xi, t);
-            else hit = leaf_t(sc, leaf, to, td, tinv, time, tmin, best.t, t, face);
-            if (hit) {
-                best.t = t;
-                best.prim = leaf & ~VKD_DUP;
-                best.inst = inst;
-                best.face = face;
-            }
-        }
-        if (sp == 0) break;
-        ref = stack[--sp];
+        while (trav_at_node(T)) trav_node_step(T, sc, tmin, tc); // every lane stays here until it holds a primitive
+        if (T.ref == VKD_DONE) break;
+        trav_prim_step<MEDIA>(T, sc, o, d, time, tmin, xi, tc); // then all lanes test their primitives together
     }
-    return best;
+    return T.best;
 }
 
 // ---------------------------------------------------------------------------------------------

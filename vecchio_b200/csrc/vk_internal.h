@@ -173,6 +173,8 @@ struct WfState {
     namespace NS {                                                                                                     \
     cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,  \
                                   const RenderBuffers& b, int grid, cudaStream_t st);                                  \
+    cudaError_t launch_megakernel_dyn(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b, \
+                                      unsigned long long* unit_head, int sm_count, cudaStream_t st);                   \
     cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk_ray* rays, size_t n,              \
                                  const float* medium_xi, vk_hit* out, cudaStream_t st);                                \
     cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads);                               \

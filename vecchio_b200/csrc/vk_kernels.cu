@@ -166,6 +166,185 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Dynamic megakernel for BVH scenes.
+//
+// Measured (profiles/r1_stress_megakernel_full.md, r1_final_scene_megakernel_full.md): when every
+// lane traces one whole ray per loop iteration, the warp waits for its longest traversal -- 4.5 of 32
+// lanes active on the 10^6-sphere scene (mean 66 node visits per ray, long tail), 9.3 on the final
+// scene.  Here the traversal is the resumable state machine of vk_device.cuh and the warp runs it
+// under votes (persistent threads with dynamic re-fill, Aila & Laine 2009):
+//
+//   traverse:  bounded while-while rounds: up to VK_DYN_NODE_STEPS node visits per lane (a lane stops
+//              as soon as it holds a primitive), then one primitive test per lane, then a vote;
+//   re-fill:   when fewer than VK_DYN_MIN_ACTIVE lanes are still traversing and an idle lane can get
+//              work, the warp leaves the loop; idle lanes shade their hit (src/main.rs:131-149),
+//              start their next segment, sample or unit, and join the traversal again.
+//
+// Units (pixel, sample block) come from one global queue, one atomic per re-fill and warp; a lane
+// sums its unit's samples in order, so the image is the same as every other variant's.
+#ifndef VK_DYN_MIN_ACTIVE
+#define VK_DYN_MIN_ACTIVE 16
+#endif
+#ifndef VK_DYN_NODE_STEPS
+#define VK_DYN_NODE_STEPS 4
+#endif
+template <bool MEDIA>
+VKD void megakernel_dyn_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
+                             unsigned long long* unit_head) {
+    const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
+    const uint32_t n_pixels = a.width * a.height;
+    const unsigned long long n_units = (unsigned long long)n_pixels * a.n_planes;
+    const size_t plane = (size_t)n_pixels * 3u;
+    const uint32_t spp_end = a.spp_begin + a.spp_count;
+    uint32_t n_rays = 0, n_drop = 0;
+    TraceCounters tc = {0u, 0u};
+
+    PathRng rng;
+    rng.pixel = 0;
+    rng.sample = 0;
+    rng.key = make_uint2(a.seed_lo, a.seed_hi);
+    float3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = sum, o = sum, d = sum, beta = sum;
+    float time = 0.0f;
+    uint32_t depth = 0, s = 0, s_end = 0, unit_plane = 0;
+    bool has_unit = false, exhausted = false, pending = false; // pending: traversal finished, hit not shaded yet
+    Trav T;
+    T.ref = VKD_DONE;
+    T.sp = 0;
+    T.enter = false;
+    T.cur_inst = 0;
+    T.co = T.cd = T.cinv = sum;
+    T.best.t = 0.0f;
+    T.best.prim = VK_REF_NONE;
+    T.best.inst = 0;
+    T.best.face = 0;
+#pragma unroll 1
+    for (;;) {
+        // ---- re-fill: every lane whose traversal has finished ------------------------------------------
+        bool need_unit = false, new_ray = false;
+        if (T.ref == VKD_DONE && !(exhausted && !pending)) {
+            bool alive = false, valid = true;
+            float3 L = f3(0.0f, 0.0f, 0.0f);
+            if (pending) {
+                pending = false;
+                if (T.best.prim == VK_REF_NONE) {
+                    L = beta * a.background; // src/main.rs:151
+                } else {
+                    HitRecD rec;
+                    resolve_hit(sc, T.best, o, d, time, false, rec);
+                    alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
+                    if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
+                    if (alive && !(finite3(d) && finite3(o))) {          // the reference's sample is NaN here
+                        valid = false;
+                        alive = false;
+                    }
+                }
+                if (!alive) { // sample finished: NaN/Inf filter of src/main.rs:191-194
+                    if (valid && finite3(L)) {
+                        sum = sum + L;
+                        sumsq = sumsq + L * L;
+                    } else {
+                        ++n_drop;
+                    }
+                }
+            }
+            if (alive) new_ray = true;
+            else if (has_unit && s < s_end) { // the unit's next sample
+                rng.sample = s++;
+                camera_get_ray(cam, rng, rng.pixel % a.width, rng.pixel / a.width, a.width, a.height, o, d, time);
+                beta = f3(1.0f, 1.0f, 1.0f);
+                depth = 1; // ray_color(ray, .., 1) src/main.rs:190
+                new_ray = true;
+            } else {
+                if (has_unit) { // unit finished: its sample-block sum goes to its own plane
+                    float* ps = buf.partial_sum + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
+                    ps[0] = sum.x;
+                    ps[1] = sum.y;
+                    ps[2] = sum.z;
+                    if (buf.partial_sumsq) {
+                        float* pq = buf.partial_sumsq + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
+                        pq[0] = sumsq.x;
+                        pq[1] = sumsq.y;
+                        pq[2] = sumsq.z;
+                    }
+                    has_unit = false;
+                }
+                need_unit = !exhausted;
+            }
+        }
+        const uint32_t mu = __ballot_sync(0xFFFFFFFFu, need_unit);
+        if (mu) { // one global atomic per warp and re-fill
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(unit_head, (unsigned long long)__popc(mu));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (need_unit) {
+                const unsigned long long u = base + __popc(mu & lanes_below);
+                if (u < n_units) {
+                    unit_plane = (uint32_t)(u / n_pixels);
+                    rng.pixel = (uint32_t)(u - (unsigned long long)unit_plane * n_pixels); // i = y*width + x (src/main.rs:182-183)
+                    s = a.spp_begin + unit_plane * a.unit_spp;
+                    s_end = min(s + a.unit_spp, spp_end);
+                    sum = f3(0.0f, 0.0f, 0.0f);
+                    sumsq = f3(0.0f, 0.0f, 0.0f);
+                    has_unit = true;
+                    rng.sample = s++;
+                    camera_get_ray(cam, rng, rng.pixel % a.width, rng.pixel / a.width, a.width, a.height, o, d, time);
+                    beta = f3(1.0f, 1.0f, 1.0f);
+                    depth = 1;
+                    new_ray = true;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (new_ray) {
+            trav_init(T, sc, o, d, CUDART_INF_F); // world.hit(&r, 0.001, inf) src/main.rs:130
+            ++n_rays;
+        }
+        if (__ballot_sync(0xFFFFFFFFu, T.ref != VKD_DONE) == 0u) break; // nothing in flight, nothing left
+        // ---- traverse --------------------------------------------------------------------------------------
+        MediumXi xi;
+        xi.table = nullptr;
+#pragma unroll 1
+        for (;;) {
+            const bool active = T.ref != VKD_DONE;
+            const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, active);
+            // an idle lane is worth leaving for if it has a hit to shade or can still get a unit
+            const uint32_t m_fill = __ballot_sync(0xFFFFFFFFu, !active && (pending || !exhausted));
+            if (m_act == 0u || ((uint32_t)__popc(m_act) < VK_DYN_MIN_ACTIVE && m_fill != 0u)) break;
+            // a bounded while-while round between two votes: up to VK_DYN_NODE_STEPS node visits (a lane
+            // leaves the loop as soon as it holds a primitive), then one primitive test per lane
+#pragma unroll 1
+            for (int k = 0; k < VK_DYN_NODE_STEPS && trav_at_node(T); ++k) trav_node_step(T, sc, 0.001f, tc);
+            if (T.ref != VKD_DONE && !trav_at_node(T)) {
+                xi.rng = rng;
+                xi.depth = depth;
+                trav_prim_step<MEDIA>(T, sc, o, d, time, 0.001f, xi, tc);
+            }
+            if (active && T.ref == VKD_DONE) pending = true;
+        }
+    }
+    unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = tc.nodes, w_prims = tc.prims;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        w_rays += __shfl_xor_sync(0xFFFFFFFFu, w_rays, off);
+        w_drop += __shfl_xor_sync(0xFFFFFFFFu, w_drop, off);
+        w_nodes += __shfl_xor_sync(0xFFFFFFFFu, w_nodes, off);
+        w_prims += __shfl_xor_sync(0xFFFFFFFFu, w_prims, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&buf.counters[3], w_nodes);
+        atomicAdd(&buf.counters[4], w_prims);
+        atomicAdd(&buf.counters[0], w_rays);
+        if (w_drop) atomicAdd(&buf.counters[1], w_drop);
+    }
+}
+template <bool MEDIA>
+__global__ void __launch_bounds__(VK_BLOCK, VK_MINB_BVH) k_megakernel_dyn(const DScene sc, const DCamera cam, const RenderArgs a,
+                                                                      const RenderBuffers buf, unsigned long long* unit_head) {
+    megakernel_dyn_body<MEDIA>(sc, cam, a, buf, unit_head);
+}
+
 // four instantiations: {BVH, flat program} x {scene without / with ConstantMedium}
 template <bool MEDIA>
 __global__ void __launch_bounds__(VK_BLOCK, VK_MINB_BVH) k_megakernel(const DScene sc, const DCamera cam, const RenderArgs a,
@@ -233,6 +412,18 @@ __global__ void k_philox_kat(const uint32_t* in6, uint32_t* out4) {
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
 }
 
+// *unit_head must be zero on the stream before the launch
+cudaError_t launch_megakernel_dyn(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
+                                  unsigned long long* unit_head, int sm_count, cudaStream_t st) {
+    int bps = 0;
+    cudaError_t e = sc.has_media ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_megakernel_dyn<true>, VK_BLOCK, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_megakernel_dyn<false>, VK_BLOCK, 0);
+    if (e != cudaSuccess) return e;
+    const int grid = sm_count * (bps < 1 ? 1 : bps);
+    if (sc.has_media) k_megakernel_dyn<true><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b, unit_head);
+    else k_megakernel_dyn<false><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b, unit_head);
+    return cudaGetLastError();
+}
 cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
                               const RenderBuffers& b, int grid, cudaStream_t st) {
     if (flat && flat->n) {
