@@ -279,6 +279,14 @@ int vk_scene_upload(vk_ctx* ctx, const vk_scene_desc* scene);
 int vk_render(vk_ctx* ctx, const vk_camera* cam, const vk_render_params* params,
               float* out_rgb, float* out_sumsq, vk_stats* stats);
 
+/* The sample loop followed by the output conversion of src/main.rs:201-214 on the device: every
+ * channel goes through Vec3::to_color (src/vec3.rs:54-61: (256 * clamp(sqrt(c), 0, 0.999)) as u32, NaN
+ * -> 0) and the rows are written top-down (y = height-1 first, main.rs:209), i.e. out_rgb8 holds the
+ * W*H*3 numbers of the reference's P3 file in file order.  Only a quarter of the bytes cross PCIe.
+ * A turntable (RotatingCamera, src/scene.rs:65-91) calls this once per camera with the scene resident. */
+int vk_render_rgb8(vk_ctx* ctx, const vk_camera* cam, const vk_render_params* params,
+                   uint8_t* out_rgb8, vk_stats* stats);
+
 /* Same loop, device-resident result: writes per-pixel SUMS (not means) of samples
  * [spp_begin, spp_begin+spp_count) to d_sum (and d_sumsq, nullable), both device
  * pointers of W*H*3 floats, enqueued on the context stream; synchronised before return

@@ -72,6 +72,8 @@ extern "C" {
     pub fn vk_scene_upload(ctx: *mut vk_ctx, scene: *const vk_scene_desc) -> c_int;
     pub fn vk_render(ctx: *mut vk_ctx, cam: *const vk_camera, params: *const vk_render_params,
                      out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut vk_stats) -> c_int;
+    pub fn vk_render_rgb8(ctx: *mut vk_ctx, cam: *const vk_camera, params: *const vk_render_params,
+                          out_rgb8: *mut u8, stats: *mut vk_stats) -> c_int;
     pub fn vk_render_device(ctx: *mut vk_ctx, cam: *const vk_camera, params: *const vk_render_params,
                             d_sum: *mut f32, d_sumsq: *mut f32, stats: *mut vk_stats) -> c_int;
     pub fn vk_finalize_device(ctx: *mut vk_ctx, d_sum: *const f32, d_rgb: *mut f32, n_floats: usize, spp: u32) -> c_int;

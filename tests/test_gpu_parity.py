@@ -417,3 +417,24 @@ def test_wavefront_edge_cases(vb, ctx, wf):
     a, _, _ = ctx.render(cam, vb.render_params(64, 64, 32, 100, seed=3, variant=wf, flags=vb.VK_FLAG_STRICT_MATH))
     b, _, _ = ctx.render(cam, vb.render_params(64, 64, 32, 100, seed=3, flags=vb.VK_FLAG_STRICT_MATH))
     assert np.array_equal(a, b)
+
+
+def test_rgb8_frame_is_to_color_of_the_float_frame(vb, ctx):
+    """vk_render_rgb8 = the frame loop's output stage on the device (src/main.rs:201-214): to_color per
+    channel, rows top-down.  Same seed -> same samples, so it must equal the host-side to_color of
+    vk_render's floats bit for bit; and a turntable keeps the scene resident between cameras."""
+    scene = vb.Scene("random_spheres_demo")  # RotatingCamera: 671 frames (src/scene.rs:254-281)
+    ctx.upload(scene)
+    W, H = 96, scene.height_for(96)
+    frames = []
+    for _ in range(3):
+        cam = scene.next_camera()
+        p = vb.render_params(W, H, 8, 50, seed=4)
+        rgb, _, _ = ctx.render(cam, p)
+        rgb8, st = ctx.render_rgb8(cam, p)
+        assert rgb8.shape == (H, W, 3) and st.paths == W * H * 8
+        assert np.array_equal(rgb8, vb.to_color(rgb)[::-1])
+        frames.append(rgb8)
+    assert not np.array_equal(frames[0], frames[1])  # the camera moved
+    # known answers of to_color (SURVEY App. C): 0.25 -> 128, 1.0 -> 255, 0 -> 0
+    assert list(vb.to_color(np.array([0.25, 1.0, 0.0, -1.0, np.nan], dtype=np.float32))) == [128, 255, 0, 0, 0]

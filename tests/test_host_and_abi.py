@@ -12,7 +12,7 @@ from conftest import ROOT, get_scene
 
 def test_gpu_library_exports_every_declared_symbol(vb):
     hdr = open(os.path.join(ROOT, "include", "vecchio_gpu.h")).read()
-    declared = set(re.findall(r"\b(vk_[a-z_]+)\s*\(", hdr)) - {"vk_ctx"}
+    declared = set(re.findall(r"\b(vk_[a-z0-9_]+)\s*\(", hdr)) - {"vk_ctx"}
     assert declared == set(vb.GPU_SYMBOLS)
     lib = C.CDLL(os.path.join(ROOT, "vecchio_b200", "lib", "libvecchio_gpu.so"))
     for name in declared | {"vk_selftest_philox"}:

@@ -76,6 +76,7 @@ def gpu_lib():
         L.vk_scene_upload.argtypes = [vp, C.POINTER(_abi.vk_scene_desc)]
         L.vk_render.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, vp,
                                 C.POINTER(_abi.vk_stats)]
+        L.vk_render_rgb8.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, C.POINTER(_abi.vk_stats)]
         L.vk_render_device.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, vp,
                                        C.POINTER(_abi.vk_stats)]
         L.vk_finalize_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_uint32]
@@ -84,14 +85,14 @@ def gpu_lib():
         L.vk_intersect.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, vp]
         L.vk_measure_peaks.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.vk_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
-        for f in ("vk_create", "vk_scene_upload", "vk_render", "vk_render_device", "vk_finalize_device",
+        for f in ("vk_create", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device", "vk_finalize_device",
                   "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks", "vk_device_info"):
             getattr(L, f).restype = C.c_int
         _gpu = L
     return _gpu
 
 
-GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_upload", "vk_render", "vk_render_device",
+GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device",
                "vk_finalize_device", "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks",
                "vk_device_info"]
 HOST_SYMBOLS = ["vkh_scene_build", "vkh_scene_free", "vkh_scene_desc", "vkh_scene_aspect_ratio",
@@ -211,6 +212,14 @@ class Context:
                                       sq.ctypes.data if want_sumsq else None, C.byref(st)))
         shape = (params.height, params.width, 3)
         return rgb.reshape(shape), (sq.reshape(shape) if want_sumsq else None), st
+
+    def render_rgb8(self, cam, params):
+        """``vk_render_rgb8``: the frame as the reference's PPM holds it -- (H, W, 3) uint8, row 0 = top,
+        every channel through ``Vec3::to_color`` (src/main.rs:201-214).  Returns (rgb8, stats)."""
+        out = np.empty(params.width * params.height * 3, dtype=np.uint8)
+        st = _abi.vk_stats()
+        self._check(self._L.vk_render_rgb8(self._h, C.byref(cam), C.byref(params), out.ctypes.data, C.byref(st)))
+        return out.reshape(params.height, params.width, 3), st
 
     def render_device(self, cam, params, d_sum_ptr, d_sumsq_ptr=None, want_stats=True):
         """``vk_render_device``: per-pixel SUMS of an spp slice into device memory.  With

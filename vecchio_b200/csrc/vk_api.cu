@@ -71,6 +71,16 @@ __global__ void k_finalize(const float* __restrict__ sum, float* __restrict__ rg
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) rgb[i] = sum[i] / spp; // c /= SAMPLES_PER_PIXEL as f32 (src/main.rs:196)
 }
+// Vec3::to_color (src/vec3.rs:54-61) of sum / spp, rows flipped to the PPM's top-down order (src/main.rs:209)
+__global__ void k_to_color(const float* __restrict__ sum, uint8_t* __restrict__ out, uint32_t width, uint32_t height, float spp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)width * height * 3;
+    if (i >= n) return;
+    const size_t row = i / ((size_t)width * 3), col = i - row * (size_t)width * 3;
+    const float c = sum[(size_t)(height - 1 - row) * width * 3 + col] / spp; // c /= SAMPLES_PER_PIXEL (main.rs:196)
+    float v = sqrtf(c);
+    v = v < 0.0f ? 0.0f : (v > 0.999f ? 0.999f : v); // Vec3::clamp keeps NaN
+    out[i] = (uint8_t)__float2uint_rz(256.0f * v);   // `as u32`: NaN -> 0
+}
 // FP32 peak: 8 independent FFMA chains per thread, no memory traffic
 __global__ void k_ffma_peak(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
@@ -936,6 +946,39 @@ int vk_render(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float*
     CU(c, cudaStreamSynchronize(c->stream));
     std::memcpy(out_rgb, c->pinned, plane * sizeof(float));
     if (out_sumsq) std::memcpy(out_sumsq, c->pinned + plane, plane * sizeof(float));
+    st.launches += 1;
+    c->launches = 0;
+    CU(c, cudaEventElapsedTime(&st.ms_total, c->ev2, c->ev1));
+    if (stats) *stats = st;
+    return VK_OK;
+}
+
+int vk_render_rgb8(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, uint8_t* out_rgb8, vk_stats* stats) {
+    if (!c) return VK_ERR_INVALID;
+    if (!P || !out_rgb8) return fail(c, VK_ERR_INVALID, "vk_render_rgb8: null argument");
+    const size_t plane = (size_t)P->width * P->height * 3;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure(c, &c->frame, &c->frame_floats, plane * 3);
+    if (rc != VK_OK) return rc;
+    if (c->pinned_floats < plane * 2) {
+        if (c->pinned) cudaFreeHost(c->pinned);
+        c->pinned = nullptr;
+        c->pinned_floats = 0;
+        CU(c, cudaMallocHost((void**)&c->pinned, plane * 2 * sizeof(float)));
+        c->pinned_floats = plane * 2;
+    }
+    float* d_sum = c->frame;
+    uint8_t* d_rgb8 = (uint8_t*)(c->frame + 2 * plane);
+    CU(c, cudaEventRecord(c->ev2, c->stream));
+    vk_stats st{};
+    rc = render_into(c, cam, P, d_sum, nullptr, &st);
+    if (rc != VK_OK) return rc;
+    k_to_color<<<(unsigned)((plane + 255) / 256), 256, 0, c->stream>>>(d_sum, d_rgb8, P->width, P->height, (float)P->spp);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(c->pinned, d_rgb8, plane, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(out_rgb8, c->pinned, plane);
     st.launches += 1;
     c->launches = 0;
     CU(c, cudaEventElapsedTime(&st.ms_total, c->ev2, c->ev1));
