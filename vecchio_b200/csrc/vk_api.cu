@@ -573,23 +573,81 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
             while (VK_REF_TYPE(end) == VK_T_XFORM) end = d->xforms[VK_REF_INDEX(end)].child;
             nodes[i].right = VK_REF_TYPE(end) == VK_T_MEDIUM ? (nodes[i].left | VKD_DUP) : VK_REF_NONE;
         }
-    // wide nodes: children's boxes pulled up into the parent (see DScene)
-    std::vector<float4> wnodes((size_t)d->n_nodes * 4);
-    for (uint32_t i = 0; i < d->n_nodes; ++i) {
-        const vk_ref l = nodes[i].left, r = nodes[i].right;
-        float4 q[4] = {make_float4(0, 0, 0, __uint_as_float_host(l)), make_float4(0, 0, 0, __uint_as_float_host(r)), make_float4(0, 0, 0, 0),
-                       make_float4(0, 0, 0, 0)};
-        if (VK_REF_TYPE(l) == VK_T_NODE) {
-            const vk_node& c = d->nodes[VK_REF_INDEX(l)];
-            q[0].x = c.bb_min[0]; q[0].y = c.bb_min[1]; q[0].z = c.bb_min[2];
-            q[1].x = c.bb_max[0]; q[1].y = c.bb_max[1]; q[1].z = c.bb_max[2];
+    // 4-wide nodes from the reference's binary tree (see DScene): start from a node's two children and
+    // keep opening the inner child with the largest surface area until four slots are filled.
+    std::vector<float4> wnodes((size_t)d->n_nodes * 8, make_float4(0, 0, 0, 0));
+    {
+        struct Slot {
+            vk_ref ref;
+            float mn[3], mx[3];
+        };
+        std::vector<uint8_t> built(d->n_nodes, 0);
+        std::vector<uint32_t> todo, level(d->n_nodes, 0); // level: 4-wide levels above the node inside its BVH
+        uint32_t levels_world = 0, levels_sub = 0;
+        bool in_sub = false;
+        auto want = [&](vk_ref r, uint32_t lvl) {
+            if (VK_REF_TYPE(r) == VK_T_NODE && !built[VK_REF_INDEX(r)]) {
+                built[VK_REF_INDEX(r)] = 1;
+                level[VK_REF_INDEX(r)] = lvl;
+                todo.push_back(VK_REF_INDEX(r));
+                uint32_t& top = in_sub ? levels_sub : levels_world;
+                if (lvl + 1 > top) top = lvl + 1;
+            }
+        };
+        auto child_slot = [&](vk_ref r, const vk_node& parent) { // a node child brings its own box, a primitive its parent's
+            const vk_node& b = VK_REF_TYPE(r) == VK_T_NODE ? d->nodes[VK_REF_INDEX(r)] : parent;
+            Slot s{r, {b.bb_min[0], b.bb_min[1], b.bb_min[2]}, {b.bb_max[0], b.bb_max[1], b.bb_max[2]}};
+            return s;
+        };
+        auto area = [](const Slot& s) {
+            const float x = s.mx[0] - s.mn[0], y = s.mx[1] - s.mn[1], z = s.mx[2] - s.mn[2];
+            return x * y + y * z + z * x;
+        };
+        // the world's BVH first, then the instanced sub-BVHs (an instance is never nested: see Validator)
+        for (int pass = 0; pass < 2; ++pass) {
+        in_sub = pass == 1;
+        if (pass == 0) want(d->root, 0);
+        else
+            for (uint32_t i = 0; i < d->n_xforms; ++i) want(d->xforms[i].child, 0);
+        while (!todo.empty()) {
+            const uint32_t ni = todo.back();
+            todo.pop_back();
+            std::vector<Slot> slots;
+            auto add_children = [&](uint32_t n) {
+                if (nodes[n].left != VK_REF_NONE) slots.push_back(child_slot(nodes[n].left, d->nodes[n]));
+                if (nodes[n].right != VK_REF_NONE) slots.push_back(child_slot(nodes[n].right, d->nodes[n]));
+            };
+            add_children(ni);
+            while (slots.size() < 4) {
+                int best = -1;
+                for (size_t k = 0; k < slots.size(); ++k)
+                    if (VK_REF_TYPE(slots[k].ref) == VK_T_NODE) {
+                        const uint32_t n = VK_REF_INDEX(slots[k].ref);
+                        const size_t kids = (nodes[n].left != VK_REF_NONE) + (nodes[n].right != VK_REF_NONE);
+                        if (slots.size() - 1 + kids > 4) continue;
+                        if (best < 0 || area(slots[k]) > area(slots[best])) best = (int)k;
+                    }
+                if (best < 0) break;
+                const uint32_t n = VK_REF_INDEX(slots[best].ref);
+                slots.erase(slots.begin() + best);
+                add_children(n);
+            }
+            float4* q = &wnodes[(size_t)ni * 8];
+            float* f = reinterpret_cast<float*>(q);
+            for (size_t k = 0; k < 4; ++k) {
+                const bool have = k < slots.size();
+                for (int ax = 0; ax < 3; ++ax) {
+                    f[(2 * ax) * 4 + k] = have ? slots[k].mn[ax] : 0.f;
+                    f[(2 * ax + 1) * 4 + k] = have ? slots[k].mx[ax] : 0.f;
+                }
+                f[6 * 4 + k] = __uint_as_float_host(have ? slots[k].ref : VK_REF_NONE);
+                if (have) want(slots[k].ref, level[ni] + 1);
+            }
         }
-        if (VK_REF_TYPE(r) == VK_T_NODE) {
-            const vk_node& c = d->nodes[VK_REF_INDEX(r)];
-            q[2].x = c.bb_min[0]; q[2].y = c.bb_min[1]; q[2].z = c.bb_min[2];
-            q[3].x = c.bb_max[0]; q[3].y = c.bb_max[1]; q[3].z = c.bb_max[2];
         }
-        for (int k = 0; k < 4; ++k) wnodes[(size_t)i * 4 + k] = q[k];
+        // a visit pushes at most three siblings; an instance adds its exit marker
+        if (3 * levels_world + 1 + 3 * levels_sub + 2 > VKD_STACK)
+            return fail(c, VK_ERR_UNSUPPORTED, "vk_scene_upload: BVH deeper than the traversal stack");
     }
     std::vector<vk_material> mats(d->materials, d->materials + d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {

@@ -403,26 +403,61 @@ VKD void trav_node_step(Trav& T, const DScene& sc, float tmin, TraceCounters& tc
         }
     }
     ++tc.nodes;
-    const float4 w0 = __ldg(&sc.wnodes[4 * ni]), w1 = __ldg(&sc.wnodes[4 * ni + 1]);
-    const uint32_t left = __float_as_uint(w0.w), right = __float_as_uint(w1.w);
-    bool hl = true, hr = right != VK_REF_NONE;
-    float tl = -CUDART_INF_F, tr = -CUDART_INF_F; // a primitive child is simply visited, left first
-    if (VKD_TYPE(left) == VK_T_NODE) hl = aabb_hit(f3(w0), f3(w1), T.co, T.cd, T.cinv, tmin, T.best.t, tl);
-    if (VKD_TYPE(right) == VK_T_NODE) {
-        const float4 w2 = __ldg(&sc.wnodes[4 * ni + 2]), w3 = __ldg(&sc.wnodes[4 * ni + 3]);
-        hr = aabb_hit(f3(w2), f3(w3), T.co, T.cd, T.cinv, tmin, T.best.t, tr);
+    const float4* w = sc.wnodes + 8u * (size_t)ni;
+    const float4 mnx = __ldg(w), mxx = __ldg(w + 1), mny = __ldg(w + 2), mxy = __ldg(w + 3), mnz = __ldg(w + 4), mxz = __ldg(w + 5);
+    const float4 rf = __ldg(w + 6);
+    uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
+    float t0, t1, t2, t3;
+    // AxisBB::hit per slot (src/accel.rs:16-35); a missed or empty slot drops out (ref 0, t = +inf)
+#if VK_STRICT
+    if (!(r0 != VK_REF_NONE && aabb_hit(f3(mnx.x, mny.x, mnz.x), f3(mxx.x, mxy.x, mxz.x), T.co, T.cd, T.cinv, tmin, T.best.t, t0))) { r0 = VK_REF_NONE; t0 = CUDART_INF_F; }
+    if (!(r1 != VK_REF_NONE && aabb_hit(f3(mnx.y, mny.y, mnz.y), f3(mxx.y, mxy.y, mxz.y), T.co, T.cd, T.cinv, tmin, T.best.t, t1))) { r1 = VK_REF_NONE; t1 = CUDART_INF_F; }
+    if (!(r2 != VK_REF_NONE && aabb_hit(f3(mnx.z, mny.z, mnz.z), f3(mxx.z, mxy.z, mxz.z), T.co, T.cd, T.cinv, tmin, T.best.t, t2))) { r2 = VK_REF_NONE; t2 = CUDART_INF_F; }
+    if (!(r3 != VK_REF_NONE && aabb_hit(f3(mnx.w, mny.w, mnz.w), f3(mxx.w, mxy.w, mxz.w), T.co, T.cd, T.cinv, tmin, T.best.t, t3))) { r3 = VK_REF_NONE; t3 = CUDART_INF_F; }
+#else
+    {   // the same slab test with one FMA per plane: (b - o) * (1/d) = b * (1/d) - o * (1/d)
+        const float3 oi = f3(-T.co.x * T.cinv.x, -T.co.y * T.cinv.y, -T.co.z * T.cinv.z);
+        const float tmax = T.best.t;
+#define VKD_SLAB(C, R, TO)                                                                                             \
+        {                                                                                                              \
+            const float ax = fmaf(mnx.C, T.cinv.x, oi.x), bx = fmaf(mxx.C, T.cinv.x, oi.x);                            \
+            const float ay = fmaf(mny.C, T.cinv.y, oi.y), by = fmaf(mxy.C, T.cinv.y, oi.y);                            \
+            const float az = fmaf(mnz.C, T.cinv.z, oi.z), bz = fmaf(mxz.C, T.cinv.z, oi.z);                            \
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));                   \
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));                   \
+            const bool miss = (R == VK_REF_NONE) | (tf <= tn);                                                         \
+            TO = miss ? CUDART_INF_F : tn;                                                                             \
+            R = miss ? VK_REF_NONE : R;                                                                                \
+        }
+        VKD_SLAB(x, r0, t0)
+        VKD_SLAB(y, r1, t1)
+        VKD_SLAB(z, r2, t2)
+        VKD_SLAB(w, r3, t3)
+#undef VKD_SLAB
     }
-    if (hl && hr) {
-        const bool left_first = tl <= tr;
-        T.stack[T.sp++] = left_first ? right : left;
-        T.ref = left_first ? left : right;
-    } else if (hl) {
-        T.ref = left;
-    } else if (hr) {
-        T.ref = right;
-    } else {
-        T.ref = trav_pop(T);
+#endif
+    // sort the four (t, ref) pairs by entry distance: 5-comparator network, misses sink to the end
+#define VKD_CSWAP(TA, RA, TB, RB)                                                                                      \
+    {                                                                                                                  \
+        const bool sw = TB < TA;                                                                                       \
+        const float tt_ = sw ? TA : TB;                                                                                \
+        const uint32_t rr_ = sw ? RA : RB;                                                                             \
+        TA = sw ? TB : TA;                                                                                             \
+        RA = sw ? RB : RA;                                                                                             \
+        TB = tt_;                                                                                                      \
+        RB = rr_;                                                                                                      \
     }
+    VKD_CSWAP(t0, r0, t1, r1)
+    VKD_CSWAP(t2, r2, t3, r3)
+    VKD_CSWAP(t0, r0, t2, r2)
+    VKD_CSWAP(t1, r1, t3, r3)
+    VKD_CSWAP(t1, r1, t2, r2)
+#undef VKD_CSWAP
+    // nearest first, the others wait on the stack, farthest deepest
+    if (r3 != VK_REF_NONE) T.stack[T.sp++] = r3;
+    if (r2 != VK_REF_NONE) T.stack[T.sp++] = r2;
+    if (r1 != VK_REF_NONE) T.stack[T.sp++] = r1;
+    T.ref = r0 != VK_REF_NONE ? r0 : trav_pop(T);
 }
 // precondition: T.ref is neither VKD_DONE nor a node; (o, d) is the world ray
 template <bool MEDIA>

@@ -14,16 +14,21 @@
 #define VKD_INDEX(r) ((r)&0x07FFFFFFu)
 #define VKD_TYPE(r) ((r) >> 28)
 #define VKD_T_EXIT 15u
-#define VKD_STACK 64
+#define VKD_STACK 96
 
 // Scene arrays in HBM.  Every record is a multiple of 16 B and fetched with 128-bit loads
 // through the read-only path; one array per primitive kind (struct-of-arrays by type).
 struct DScene {
-    // Traversal layout ("wide" node, 64 B = 4 x float4, one 128-byte-line half): the boxes of BOTH
-    // children live in the parent, so one fetch decides both descents and the nearer child is
-    // visited first.  {lmin.xyz, left}, {lmax.xyz, right}, {rmin.xyz, -}, {rmax.xyz, -}.  A box is
-    // only meaningful for a child that is itself a node: the reference tests no box for a primitive
-    // child (src/accel.rs:64-65 calls its hit() directly).
+    // Traversal layout: 4-wide nodes made from the reference's binary tree at upload (no rebuild: the
+    // leaves, their boxes and therefore every closest hit are the reference's; only the grouping
+    // changes).  A 4-wide node keeps the boxes of up to four descendants of one binary node -- its
+    // children, with the larger inner children opened in turn -- so one visit (one 128-byte line,
+    // eight independent 16-byte loads) decides four descents and halves the chain of dependent
+    // memory round trips per ray.  Layout, 8 x float4 per binary node index (only the indices that
+    // head a 4-wide node are filled):
+    //   {min.x[4]} {max.x[4]} {min.y[4]} {max.y[4]} {min.z[4]} {max.z[4]} {ref[4]} {-}
+    // A primitive slot carries the box of the binary node it hung under (the reference visits it only
+    // when that box is hit); an empty slot has ref 0.
     const float4* wnodes;
     const float4* nodes;    // reference layout, 2 x float4 per node: {min.xyz, left}, {max.xyz, right}; used for
                             // the box of a BVH root (world root, instanced sub-BVH root)
