@@ -207,8 +207,16 @@ enum { VK_VARIANT_AUTO = 0, VK_VARIANT_MEGAKERNEL = 1, VK_VARIANT_WAVEFRONT = 2,
 enum {
     VK_FLAG_STRICT_MATH = 1u, /* no FMA contraction, IEEE div/sqrt, division slab test:
                                  the op sequence of the reference, for hit parity    */
-    VK_FLAG_FORCE_BVH = 2u    /* traverse the BVH even when the scene is small enough for
+    VK_FLAG_FORCE_BVH = 2u,   /* traverse the BVH even when the scene is small enough for
                                  the flat (divergence-free) traversal program         */
+    VK_FLAG_LEGACY_SCATTER = 4u, /* the book-1/2 integrator of the reference's legacy `Material::scatter`
+                                 methods (src/material.rs:21-28, 85-90, 118-132, 150-175, 215-217,
+                                 442-446): no light list, no PDFs, `emitted + attenuation *
+                                 ray_color(scattered)`.  HEAD itself cannot render a scene without
+                                 lights (`choose().unwrap()` panics, src/hittable.rs:431)          */
+    VK_FLAG_SKY_BACKGROUND = 8u  /* a missed ray returns the book-1 sky (1-t)*white + t*(0.5,0.7,1),
+                                 t = 0.5*(unit(d).y + 1) (sample/inoneweekend.png) instead of
+                                 `background` (src/main.rs:124)                                    */
 };
 
 /* The constants of src/main.rs:28-29,171-172 and the choices the reference leaves

@@ -347,8 +347,21 @@ struct ScatterRec { // :13-18
     Vec3 attenuation;
     Arc<PDF> pdf;
 };
+static bool g_scatter_unwrap_panic = false; // set where the reference would panic; orc_render reports it
 struct Material { // :20-41
     virtual ~Material() = default;
+    // the book-1/2 method, :21-28: by default built from scatter_with_pdf (`specular_ray.unwrap()`: a
+    // material whose scatter_with_pdf has no specular ray panics there -- reported as an error here)
+    virtual std::optional<std::pair<Vec3, Ray>> scatter(const Ray& r, const HitRec& rec) const {
+        if (auto srec = scatter_with_pdf(r, rec)) {
+            if (!srec->specular_ray) { // `unwrap()` on None panics in the reference (src/material.rs:23)
+                g_scatter_unwrap_panic = true;
+                return std::nullopt;
+            }
+            return std::make_pair(srec->attenuation, *srec->specular_ray);
+        }
+        return std::nullopt;
+    }
     virtual std::optional<ScatterRec> scatter_with_pdf(const Ray&, const HitRec&) const { return std::nullopt; }
     virtual float scattering_pdf(const Ray&, const HitRec&, const Ray&) const { return 0.0f; }
     virtual Vec3 emitted(const HitRec&, float, float, Vec3) const { return Vec3::new_const(0.0f); }
@@ -359,6 +372,18 @@ static float cosine_scattering_pdf(const HitRec& rec, const Ray& s) { // :100-10
 }
 struct Lambertian : Material { // :45-109
     Arc<Texture> albedo;
+    static Vec3 random() { // :51-58: a uniform point on the unit sphere
+        Rng& rng = thread_rng();
+        float a = rng.gen_range(0.0f, 2.0f * PI);
+        float z = rng.gen_range(-1.0f, 1.0f);
+        float r = std::sqrt(1.0f - z * z);
+        return Vec3(r * std::cos(a), r * std::sin(a), z);
+    }
+    std::optional<std::pair<Vec3, Ray>> scatter(const Ray& r, const HitRec& rec) const override { // :85-90
+        Vec3 scatter_direction = rec.normal + Lambertian::random();
+        Ray scattered(rec.p, scatter_direction, r.time);
+        return std::make_pair(albedo->value(rec.u, rec.v, rec.p), scattered);
+    }
     std::optional<ScatterRec> scatter_with_pdf(const Ray&, const HitRec& rec) const override {
         tl_cnt.n_diffuse++;
         return ScatterRec{std::nullopt, albedo->value(rec.u, rec.v, rec.p), std::make_shared<CosinePDF>(rec.normal)};
@@ -368,6 +393,13 @@ struct Lambertian : Material { // :45-109
 struct Metal : Material { // :111-142
     Arc<Texture> albedo;
     float fuzz = 0.0f;
+    std::optional<std::pair<Vec3, Ray>> scatter(const Ray& r, const HitRec& rec) const override { // :118-132
+        Vec3 reflected = reflect(r.direction.unit_vector(), rec.normal);
+        Ray scattered(rec.p, reflected + random_in_unit_sphere() * fuzz, r.time); // keeps r.time here
+        Vec3 attenuation = albedo->value(rec.u, rec.v, rec.p);
+        if (scattered.direction.dot(rec.normal) > 0.0f) return std::make_pair(attenuation, scattered);
+        return std::nullopt;
+    }
     std::optional<ScatterRec> scatter_with_pdf(const Ray& r, const HitRec& rec) const override {
         tl_cnt.n_metal++;
         Vec3 reflected = reflect(r.direction.unit_vector(), rec.normal);
@@ -401,12 +433,17 @@ struct Dielectric : Material { // :144-207
 };
 struct DiffuseLight : Material { // :209-226
     Arc<Texture> emit;
+    std::optional<std::pair<Vec3, Ray>> scatter(const Ray&, const HitRec&) const override { return std::nullopt; } // :215-217
     Vec3 emitted(const HitRec& rec, float u, float v, Vec3 p) const override {
         return rec.front ? emit->value(u, v, p) : Vec3::new_const(0.0f);
     }
 };
 struct Isotropic : Material { // :436-465  (a cosine lobe about rec.normal, Q8)
     Arc<Texture> albedo;
+    std::optional<std::pair<Vec3, Ray>> scatter(const Ray& r, const HitRec& rec) const override { // :442-446
+        Ray scattered(rec.p, random_in_unit_sphere(), r.time);
+        return std::make_pair(albedo->value(rec.u, rec.v, rec.p), scattered);
+    }
     std::optional<ScatterRec> scatter_with_pdf(const Ray&, const HitRec& rec) const override {
         tl_cnt.n_diffuse++;
         return ScatterRec{std::nullopt, albedo->value(rec.u, rec.v, rec.p), std::make_shared<CosinePDF>(rec.normal)};
@@ -823,6 +860,30 @@ static Vec3 ray_color(const Ray& r, const Arc<Hittable>& world, const Arc<Hittab
     return background;
 }
 
+// The book-1/2 integrator the legacy Material::scatter methods (still in the reference's API at HEAD,
+// src/material.rs:21-28, 85-90, 118-132, 150-175, 215-217, 442-446) were written for.  HEAD has no
+// caller for them, so this restates the integrator of the InOneWeekend / TheNextWeek tags in HEAD's
+// conventions: depth counted like :126, `emitted + attenuation * ray_color(scattered)`, and either
+// the constant background of :124 or the book-1 sky, whose colours sample/inoneweekend.png shows
+// ((1-t)*white + t*(0.5,0.7,1.0), t = 0.5*(unit(d).y + 1); its top rows are (220,235,255) = t 0.523).
+static Vec3 sky_color(const Ray& r) {
+    Vec3 unit_direction = r.direction.unit_vector();
+    float t = 0.5f * (unit_direction.y + 1.0f);
+    return Vec3::new_const(1.0f) * (1.0f - t) + Vec3(0.5f, 0.7f, 1.0f) * t;
+}
+static Vec3 ray_color_legacy(const Ray& r, const Arc<Hittable>& world, uint32_t depth, uint32_t max_depth, Vec3 background,
+                             bool sky) {
+    if (depth > max_depth) return Vec3::new_const(0.0f);
+    tl_cnt.rays++;
+    tl_cnt.rays_live++;
+    if (auto c = world->hit(r, 0.001f, INF)) {
+        Vec3 emitted = c->material->emitted(*c, c->u, c->v, c->p);
+        if (auto s = c->material->scatter(r, *c)) return emitted + s->first * ray_color_legacy(s->second, world, depth + 1, max_depth, background, sky);
+        return emitted;
+    }
+    return sky ? sky_color(r) : background;
+}
+
 // ------------------------------------------------------------------------------------------
 // Un-lowering: rebuild the reference's object graph from the flat arrays, so the oracle and
 // the GPU see ONE scene instance.  The inverse of the lower() methods of the host front end.
@@ -1114,7 +1175,10 @@ int orc_render(const orc_scene* s, const vk_camera* cam_, const vk_render_params
                 float u = ((float)x + rng.gen_f32()) / (float)(width - 1);
                 float v = ((float)y + rng.gen_f32()) / (float)(height - 1);
                 Ray ray = cam.get_ray(u, v);
-                Vec3 color = ray_color(ray, s->s.world, s->s.lights, 1, P->max_depth, background);
+                Vec3 color = (P->flags & VK_FLAG_LEGACY_SCATTER)
+                                 ? ray_color_legacy(ray, s->s.world, 1, P->max_depth, background, (P->flags & VK_FLAG_SKY_BACKGROUND) != 0)
+                                 : ray_color(ray, s->s.world, s->s.lights, 1, P->max_depth,
+                                             (P->flags & VK_FLAG_SKY_BACKGROUND) ? sky_color(ray) : background);
                 if (color.is_finite()) { // :192-194
                     c = c + color;
                     c2 = c2 + color * color;
@@ -1137,6 +1201,10 @@ int orc_render(const orc_scene* s, const vk_camera* cam_, const vk_render_params
         tl_rng = nullptr;
     }
     auto t1 = std::chrono::steady_clock::now();
+    if (g_scatter_unwrap_panic) {
+        g_scatter_unwrap_panic = false;
+        return VK_ERR_UNSUPPORTED;
+    }
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->paths = (uint64_t)width * height * s_count;
@@ -1209,6 +1277,9 @@ int orc_kat(const orc_scene* s, const char* name, const float* in, int n_in, flo
         ONB o = ONB::new_from_w(v3(0));
         put3(0, o.u); put3(3, o.v); put3(6, o.w);
         ret = 9;
+    } else if (k == "sky_color" && n_in >= 3 && n_out >= 3) { // direction -> book-1 sky
+        put3(0, sky_color(Ray(Vec3::new_const(0.0f), v3(0))));
+        ret = 3;
     } else if (k == "aabb_hit" && n_in >= 14 && n_out >= 1) { // min3 max3 o3 d3 tmin tmax
         AxisBB bb{v3(0), v3(3)};
         out[0] = bb.hit(Ray(v3(6), v3(9)), in[12], in[13]) ? 1.0f : 0.0f;

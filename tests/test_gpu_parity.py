@@ -21,7 +21,7 @@ INF = np.float32(np.inf)
 # (scene, param, image width used for ray generation, rays per batch)
 HIT_SCENES = [("cornell_box", 0, 200, 200_000), ("cornell_smoke", 0, 200, 200_000), ("random_spheres_demo", 0, 200, 200_000),
               ("final_scene", 0, 200, 200_000), ("bowser_demo", 0, 200, 100_000), ("perlin_demo", 0, 160, 50_000),
-              ("balls_demo", 0, 160, 50_000), ("stress_spheres", 64, 200, 100_000)]
+              ("balls_demo", 0, 160, 50_000), ("stress_spheres", 64, 200, 100_000), ("api_surface_demo", 0, 160, 50_000)]
 
 
 def camera_rays(cam, n, rng):
@@ -233,7 +233,8 @@ def zscores(rgb_a, sq_a, n_a, rgb_b, sq_b, n_b):
 RENDER_SCENES = [("cornell_box", 0, 80, 512, 512, 100), ("cornell_smoke", 0, 80, 512, 512, 100),
                  ("random_spheres_demo", 0, 128, 256, 256, 50), ("final_scene", 0, 64, 512, 512, 100),
                  ("bowser_demo", 0, 96, 256, 256, 50), ("perlin_demo", 0, 96, 256, 256, 50),
-                 ("balls_demo", 0, 96, 256, 256, 50), ("stress_spheres", 64, 96, 128, 128, 50)]
+                 ("balls_demo", 0, 96, 256, 256, 50), ("stress_spheres", 64, 96, 128, 128, 50),
+                 ("api_surface_demo", 0, 96, 512, 512, 50)]
 
 
 @pytest.mark.parametrize("name,param,W,spp_o,spp_g,depth", RENDER_SCENES, ids=[s[0] for s in RENDER_SCENES])
@@ -438,3 +439,47 @@ def test_rgb8_frame_is_to_color_of_the_float_frame(vb, ctx):
     assert not np.array_equal(frames[0], frames[1])  # the camera moved
     # known answers of to_color: 0.25 -> 128, 1.0 -> 255, 0 -> 0
     assert list(vb.to_color(np.array([0.25, 1.0, 0.0, -1.0, np.nan], dtype=np.float32))) == [128, 255, 0, 0, 0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Legacy book-1/2 integrator (VK_FLAG_LEGACY_SCATTER) and sky background
+# ---------------------------------------------------------------------------------------------------
+LEGACY_CASES = [("random_spheres_cover", 96, 128, 50, True), ("cornell_box", 64, 512, 50, False), ("final_scene", 48, 128, 50, False)]
+
+
+@pytest.mark.parametrize("name,W,spp,depth,sky", LEGACY_CASES, ids=[c[0] for c in LEGACY_CASES])
+def test_legacy_integrator_image_parity(vb, po, ctx, name, W, spp, depth, sky):
+    scene, cam = get_scene(vb, name)
+    H = scene.height_for(W)
+    o = po.OracleScene(scene)
+    ctx.upload(scene)
+    flags = vb.VK_FLAG_LEGACY_SCATTER | (vb.VK_FLAG_SKY_BACKGROUND if sky else 0)
+    ro, qo, so = o.render(cam, vb.render_params(W, H, spp, depth, seed=51, flags=flags), want_sumsq=True)
+    rg, qg, sg = ctx.render(cam, vb.render_params(W, H, spp, depth, seed=52, flags=flags), want_sumsq=True)
+    assert sg.variant == vb.VK_VARIANT_MEGAKERNEL and np.isfinite(rg).all()
+    assert abs(sg.rays / sg.paths - so.rays / so.paths) <= 0.02 * so.rays / so.paths, (sg.rays / sg.paths, so.rays / so.paths)
+    z, nz, diff, se = zscores(rg, qg, spp, ro, qo, spp)
+    frac = (np.abs(z[nz]) <= 3.0).mean()
+    print(f"legacy {name}: {frac:.4f} within 3 sigma, mean z {z[nz].mean():+.3f}, image mean ratio {rg.mean() / ro.mean():.4f}")
+    assert frac >= 0.98 and abs(z[nz].mean()) <= 0.1, (name, frac, z[nz].mean())
+    assert abs(rg.mean() - ro.mean()) <= 0.02 * ro.mean()
+
+
+def test_legacy_and_light_list_rules(vb, ctx):
+    cover, cam = get_scene(vb, "random_spheres_cover")
+    ctx.upload(cover)  # no lights: accepted at upload
+    with pytest.raises(vb.VecchioError) as e:  # HEAD's integrator panics on an empty light list (src/hittable.rs:431)
+        ctx.render(cam, vb.render_params(32, 18, 4, 10))
+    assert e.value.code == vb.VK_ERR_INVALID
+    rgb, _, st = ctx.render(cam, vb.render_params(32, 18, 4, 10, flags=vb.VK_FLAG_LEGACY_SCATTER | vb.VK_FLAG_SKY_BACKGROUND))
+    assert rgb.mean() > 0.3  # sky lit
+    # the sky alone: depth 1 from above the scene straight up is the top of the gradient
+    balls, cam2 = get_scene(vb, "api_surface_demo")  # holds a SpecDiffuse
+    ctx.upload(balls)
+    with pytest.raises(vb.VecchioError) as e:
+        ctx.render(cam2, vb.render_params(32, 18, 4, 10, flags=vb.VK_FLAG_LEGACY_SCATTER))
+    assert e.value.code == vb.VK_ERR_UNSUPPORTED
+    # sky background also works under HEAD's integrator (any variant): brighter than the black default
+    a, _, _ = ctx.render(cam2, vb.render_params(64, 36, 16, 20, seed=1, flags=vb.VK_FLAG_SKY_BACKGROUND, variant=vb.VK_VARIANT_WAVEFRONT))
+    b, _, _ = ctx.render(cam2, vb.render_params(64, 36, 16, 20, seed=1, variant=vb.VK_VARIANT_WAVEFRONT))
+    assert a.mean() > 1.5 * b.mean()

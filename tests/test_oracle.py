@@ -146,3 +146,38 @@ def test_oracle_renders_every_scene(po, vb, name):
     rgb, sq, st = o.render(cam, vb.render_params(W, H, 4, 50, seed=2), want_sumsq=True)
     assert np.isfinite(rgb).all() and rgb.min() >= 0 and rgb.mean() > 0
     assert st.rays >= st.paths and st.paths == W * H * 4
+
+
+def test_legacy_sky_matches_the_published_book1_render(vb, po):
+    """The book-1 sky (VK_FLAG_SKY_BACKGROUND) against sample/inoneweekend.png: its top rows, pure sky,
+    are (220, 235, 255) after to_color.  (1-t)*white + t*(0.5, 0.7, 1.0) gives r = 1 - 0.5 t,
+    g = 1 - 0.3 t, b = 1: the red channel fixes t = 0.523 and green must then come out as 235."""
+    r_lin = (220.5 / 256.0) ** 2
+    t = (1.0 - r_lin) / 0.5
+    y = 2.0 * t - 1.0  # t = 0.5 * (unit(d).y + 1)
+    d = [np.sqrt(1.0 - y * y), y, 0.0]
+    col = po.kat("sky_color", d, 3)
+    assert list(vb.to_color(col)) == [220, 235, 255]
+    assert np.allclose(po.kat("sky_color", [0, 1, 0], 3), [0.5, 0.7, 1.0]) and np.allclose(po.kat("sky_color", [0, -2, 0], 3), [1, 1, 1])
+
+
+def test_legacy_integrator_agrees_with_head_in_expectation(vb, po):
+    """`emitted + attenuation * ray_color(scattered)` with Lambertian normal + unit-sphere scattering
+    and HEAD's mixture-PDF estimator are both unbiased for the same light transport: on the Cornell box
+    their image means agree within Monte-Carlo noise (the legacy one is much noisier)."""
+    scene = vb.Scene("cornell_box")
+    cam = scene.next_camera()
+    o = po.OracleScene(scene)
+    a, qa, sa = o.render(cam, vb.render_params(40, 40, 256, 50, seed=3, flags=vb.VK_FLAG_LEGACY_SCATTER), want_sumsq=True)
+    b, _, sb = o.render(cam, vb.render_params(40, 40, 64, 50, seed=4))
+    assert sa.rays / sa.paths > 2 * sb.rays / sb.paths  # no light sampling: paths wander until they find the light
+    se = np.sqrt(np.maximum(qa / 256 - a.astype(np.float64) ** 2, 0).sum() / 256) / a.size  # s.e. of the image mean
+    assert abs(a.mean() - b.mean()) <= 5 * se + 0.01 * b.mean(), (a.mean(), b.mean(), se)
+
+
+def test_legacy_refuses_what_the_reference_panics_on(vb, po):
+    scene = vb.Scene("api_surface_demo")  # holds a SpecDiffuse: its default `scatter` unwraps None
+    cam = scene.next_camera()
+    o = po.OracleScene(scene)
+    with pytest.raises(AssertionError):
+        o.render(cam, vb.render_params(16, 9, 4, 10, seed=1, flags=vb.VK_FLAG_LEGACY_SCATTER))

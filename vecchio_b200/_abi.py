@@ -9,6 +9,8 @@ VK_T_NONE, VK_T_NODE, VK_T_SPHERE, VK_T_MSPHERE, VK_T_RECT, VK_T_BOX, VK_T_XFORM
 VK_VARIANT_AUTO, VK_VARIANT_MEGAKERNEL, VK_VARIANT_WAVEFRONT, VK_VARIANT_STAGED = 0, 1, 2, 3
 VK_FLAG_STRICT_MATH = 1
 VK_FLAG_FORCE_BVH = 2
+VK_FLAG_LEGACY_SCATTER = 4
+VK_FLAG_SKY_BACKGROUND = 8
 VK_MEDIUM_XI_SLOTS = 8
 VK_RECT_FLIP = 0x100
 

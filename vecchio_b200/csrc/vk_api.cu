@@ -26,6 +26,7 @@ struct vk_ctx {
     FlatProgram flat{}; // flat.n == 0: scene too large, BVH traversal
     bool has_scene = false;
     uint32_t n_nodes = 0; // BVH nodes of the uploaded scene
+    bool has_specdiffuse = false;
     unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
     float* partial = nullptr;               // chunk partial sums (sum | sumsq)
@@ -269,7 +270,8 @@ struct Validator {
         const int depth = visit(d->root, false, hm);
         if (code != VK_OK) return false;
         if (depth + 2 > VKD_STACK) return bad(VK_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
-        if (d->n_lights == 0) return bad(VK_ERR_INVALID, "empty light list (the reference panics: choose().unwrap(), src/hittable.rs:431)");
+        // an empty light list is accepted here: HEAD's integrator is refused at render time (the reference
+        // panics, src/hittable.rs:431), the legacy integrator (VK_FLAG_LEGACY_SCATTER) does not use it
         for (uint32_t i = 0; i < d->n_lights; ++i) {
             const vk_ref l = d->lights[i];
             const uint32_t t = VK_REF_TYPE(l), ix = VK_REF_INDEX(l);
@@ -698,6 +700,8 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
     c->n_nodes = d->n_nodes;
+    c->has_specdiffuse = false;
+    for (uint32_t i = 0; i < d->n_materials; ++i) c->has_specdiffuse |= d->materials[i].type == VK_M_SPECDIFFUSE;
     FlatBuilder fb;
     fb.d = d;
     if (!fb.build(&c->flat)) c->flat = FlatProgram{};
@@ -827,8 +831,13 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
 
     const FlatProgram* flat = (c->flat.n && !(P->flags & VK_FLAG_FORCE_BVH)) ? &c->flat : nullptr;
     int bps = 0, bt = 0;
-    CU(c, strict ? vkstrict::megakernel_occupancy(flat != nullptr, c->scene.has_media, &bps, &bt)
-                 : vkfast::megakernel_occupancy(flat != nullptr, c->scene.has_media, &bps, &bt));
+    const bool legacy = (P->flags & VK_FLAG_LEGACY_SCATTER) != 0;
+    if (legacy && c->has_specdiffuse)
+        return fail(c, VK_ERR_UNSUPPORTED, "render: SpecDiffuse has no legacy scatter (the reference's default unwraps a missing specular ray and panics, src/material.rs:21-28)");
+    if (!legacy && c->scene.n_lights == 0)
+        return fail(c, VK_ERR_INVALID, "render: empty light list (the reference panics: choose().unwrap(), src/hittable.rs:431); only VK_FLAG_LEGACY_SCATTER renders without lights");
+    CU(c, strict ? vkstrict::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt)
+                 : vkfast::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt));
     if (bps < 1) bps = 1;
     const int grid = c->sm_count * bps;
     const uint32_t resident_warps = (uint32_t)grid * (uint32_t)bt / 32u;
@@ -842,6 +851,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     a.seed_lo = (uint32_t)P->seed;
     a.seed_hi = (uint32_t)(P->seed >> 32);
     a.background = make_float3(P->background[0], P->background[1], P->background[2]);
+    a.flags = P->flags;
     a.tiles_x = (P->width + 7) / 8;
     a.tiles_y = (P->height + 3) / 4;
     // Sample blocks ("units") and their planes of partial sums.  A unit's samples are traced one after
@@ -891,7 +901,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
     uint32_t launches = 0;
-    const uint32_t variant = choose_variant(c, P);
+    const uint32_t variant = legacy ? (uint32_t)VK_VARIANT_MEGAKERNEL : choose_variant(c, P); // legacy: lane megakernel only
     if (variant == VK_VARIANT_WAVEFRONT) {
         int rc = wf_render(c, strict, flat, dc, a, b, d_sumsq != nullptr, &launches);
         if (rc != VK_OK) return rc;
@@ -902,14 +912,14 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         CU(c, strict ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
                      : vkfast::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream));
         launches = 1;
-    } else if (!flat && use_dynamic_megakernel(c)) {
+    } else if (!flat && !legacy && use_dynamic_megakernel(c)) {
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
         CU(c, strict ? vkstrict::launch_megakernel_dyn(c->scene, dc, a, b, c->counters + 2, c->sm_count, c->stream)
                      : vkfast::launch_megakernel_dyn(c->scene, dc, a, b, c->counters + 2, c->sm_count, c->stream));
         launches = 1;
     } else {
-        CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream)
-                     : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, c->stream));
+        CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, legacy, c->stream)
+                     : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, legacy, c->stream));
         launches = 1;
     }
     if (a.n_planes > 1) {

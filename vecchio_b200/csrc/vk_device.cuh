@@ -1230,4 +1230,63 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     return true;
 }
 
+// A ray that leaves the scene: the constant background of src/main.rs:124,151, or with
+// VK_FLAG_SKY_BACKGROUND the book-1 sky (1-t)*white + t*(0.5,0.7,1.0), t = 0.5*(unit(d).y + 1).
+VKD float3 miss_color(const RenderArgs& a, float3 d) {
+    if (!(a.flags & VK_FLAG_SKY_BACKGROUND)) return a.background;
+    const float t = 0.5f * (unit_vector(d).y + 1.0f);
+    return f3(1.0f, 1.0f, 1.0f) * (1.0f - t) + f3(0.5f, 0.7f, 1.0f) * t;
+}
+
+// One bounce of the book-1/2 integrator built on the legacy `Material::scatter` methods
+// (VK_FLAG_LEGACY_SCATTER): emitted + attenuation * ray_color(scattered), no light list, no PDFs.
+// Lambertian src/material.rs:85-90 (+ :51-58), Metal :118-132, Dielectric :150-175,
+// DiffuseLight :215-217, Isotropic :442-446.  SpecDiffuse has no legacy method of its own (its
+// default `scatter` unwraps a missing specular ray and panics, :21-28): refused before the launch.
+VKD bool shade_legacy(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
+                      float3& beta, float3& L, bool& valid) {
+    const uint4 m = rec.m;
+    const uint32_t type = m.x;
+    if (type == VK_M_DIFFUSE_LIGHT) { // scatter -> None: the path ends with the emission (if lit from the front)
+        if (rec.front) L = L + beta * tex_value(sc, m.y, rec.u, rec.v, rec.p);
+        return false;
+    }
+    if (type == VK_M_SPECDIFFUSE) {
+        valid = false;
+        return false;
+    }
+    const uint4 r = rng.block(depth, 0u);
+    float3 nd;
+    if (type == VK_M_DIELECTRIC) { // same body as scatter_with_pdf, attenuation (1,1,1), keeps r.time
+        const float ref_idx = __uint_as_float(m.z);
+        const float etai_over_etat = rec.front ? 1.0f / ref_idx : ref_idx;
+        const float3 unit_direction = unit_vector(d);
+        const float cos_theta = fminf(dot3(-unit_direction, rec.normal), 1.0f);
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        if (etai_over_etat * sin_theta > 1.0f) nd = reflect(unit_direction, rec.normal);
+        else if (u01(r.x) < schlick(cos_theta, etai_over_etat)) nd = reflect(unit_direction, rec.normal);
+        else nd = refract(unit_direction, rec.normal, etai_over_etat);
+    } else if (type == VK_M_METAL) { // keeps r.time (unlike scatter_with_pdf); absorbed below the surface
+        const float fuzz = __uint_as_float(m.z);
+        nd = reflect(unit_vector(d), rec.normal);
+        if (fuzz != 0.0f) nd = nd + random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z)) * fuzz;
+        if (!(dot3(nd, rec.normal) > 0.0f)) return false; // None: emitted (0) is all that is left
+        beta = beta * tex_value(sc, m.y, rec.u, rec.v, rec.p);
+    } else if (type == VK_M_ISOTROPIC) {
+        nd = random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z));
+        beta = beta * tex_value(sc, m.y, rec.u, rec.v, rec.p);
+    } else { // Lambertian: rec.normal + a uniform point on the unit sphere
+        const float ang = gen_range(r.x, 0.0f, 2.0f * VK_PI), z = gen_range(r.y, -1.0f, 1.0f);
+        const float rr = sqrtf(1.0f - z * z);
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        nd = rec.normal + f3(rr * cs, rr * sn, z);
+        beta = beta * tex_value(sc, m.y, rec.u, rec.v, rec.p);
+    }
+    o = rec.p;
+    d = nd;
+    (void)time;
+    return true;
+}
+
 } // namespace VK_NS

@@ -128,6 +128,7 @@ struct RenderArgs {
     uint32_t max_depth;
     uint32_t seed_lo, seed_hi;
     float3 background;
+    uint32_t flags; // VK_FLAG_* of the call (sky background)
     // work decomposition (vk_api.cu decides): warp items = 8x4 pixel tiles x sample chunks; inside
     // an item the lanes share (pixel, block of unit_spp samples) units; one partial plane per block
     uint32_t tiles_x, tiles_y, n_chunks, chunk_spp, unit_spp, n_planes;
@@ -177,12 +178,12 @@ struct WfState {
 #define VK_DECLARE_LAUNCHERS(NS)                                                                                       \
     namespace NS {                                                                                                     \
     cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,  \
-                                  const RenderBuffers& b, int grid, cudaStream_t st);                                  \
+                                  const RenderBuffers& b, int grid, bool legacy, cudaStream_t st);                     \
     cudaError_t launch_megakernel_dyn(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b, \
                                       unsigned long long* unit_head, int sm_count, cudaStream_t st);                   \
     cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk_ray* rays, size_t n,              \
                                  const float* medium_xi, vk_hit* out, cudaStream_t st);                                \
-    cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads);                               \
+    cudaError_t megakernel_occupancy(bool flat, bool media, bool legacy, int* blocks_per_sm, int* block_threads);      \
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
     cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,      \
                               const RenderBuffers& b, unsigned long long* unit_head, int sm_count, cudaStream_t st);   \

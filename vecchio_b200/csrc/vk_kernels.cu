@@ -30,7 +30,7 @@ namespace VK_NS {
 //           of an item instead of waiting for the slowest pixel of a whole chunk.
 // A unit's samples are summed in order by one lane and stored to its own plane of the partial
 // buffer (plane = global sample-block index); k_reduce_planes adds the planes in order.
-template <bool FLAT, bool MEDIA>
+template <bool FLAT, bool MEDIA, bool LEGACY>
 VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
                          const RenderBuffers& buf) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -124,12 +124,13 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
             n_nodes += tc.nodes;
             n_prims += tc.prims;
             if (h.prim == VK_REF_NONE) {
-                L = L + beta * a.background; // src/main.rs:151
+                L = L + beta * miss_color(a, d); // src/main.rs:151
                 alive = false;
             } else {
                 HitRecD rec;
                 resolve_hit(sc, h, o, d, time, false, rec);
-                alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
+                alive = LEGACY ? shade_legacy(sc, rec, rng, depth, o, d, time, beta, L, valid)
+                               : shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
                 if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
                 // A non-finite ray (refract()'s sqrt of a rounding-negative number, Q7) makes every
                 // comparison of the reference false: it walks the WHOLE BVH, "hits" whichever Rect
@@ -228,7 +229,7 @@ VKD void megakernel_dyn_body(const DScene& sc, const DCamera& cam, const RenderA
             if (pending) {
                 pending = false;
                 if (T.best.prim == VK_REF_NONE) {
-                    L = beta * a.background; // src/main.rs:151
+                    L = beta * miss_color(a, d); // src/main.rs:151
                 } else {
                     HitRecD rec;
                     resolve_hit(sc, T.best, o, d, time, false, rec);
@@ -345,16 +346,16 @@ __global__ void __launch_bounds__(VK_BLOCK, VK_MINB_BVH) k_megakernel_dyn(const 
     megakernel_dyn_body<MEDIA>(sc, cam, a, buf, unit_head);
 }
 
-// four instantiations: {BVH, flat program} x {scene without / with ConstantMedium}
-template <bool MEDIA>
+// instantiations: {BVH, flat program} x {scene without / with ConstantMedium} x {HEAD integrator, legacy scatter}
+template <bool MEDIA, bool LEGACY>
 __global__ void __launch_bounds__(VK_BLOCK, VK_MINB_BVH) k_megakernel(const DScene sc, const DCamera cam, const RenderArgs a,
                                                                   const RenderBuffers buf) {
-    megakernel_body<false, MEDIA>(sc, nullptr, cam, a, buf);
+    megakernel_body<false, MEDIA, LEGACY>(sc, nullptr, cam, a, buf);
 }
-template <bool MEDIA>
+template <bool MEDIA, bool LEGACY>
 __global__ void __launch_bounds__(VK_BLOCK, VK_MINB_FLAT) k_megakernel_flat(const DScene sc, const __grid_constant__ FlatProgram flat,
                                                                        const DCamera cam, const RenderArgs a, const RenderBuffers buf) {
-    megakernel_body<true, MEDIA>(sc, &flat, cam, a, buf);
+    megakernel_body<true, MEDIA, LEGACY>(sc, &flat, cam, a, buf);
 }
 
 template <bool FLAT>
@@ -424,15 +425,22 @@ cudaError_t launch_megakernel_dyn(const DScene& sc, const DCamera& cam, const Re
     else k_megakernel_dyn<false><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b, unit_head);
     return cudaGetLastError();
 }
-cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
-                              const RenderBuffers& b, int grid, cudaStream_t st) {
-    if (flat && flat->n) {
-        if (sc.has_media) k_megakernel_flat<true><<<grid, VK_BLOCK, 0, st>>>(sc, *flat, cam, a, b);
-        else k_megakernel_flat<false><<<grid, VK_BLOCK, 0, st>>>(sc, *flat, cam, a, b);
-    } else {
-        if (sc.has_media) k_megakernel<true><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
-        else k_megakernel<false><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b);
+#define VK_MEGA_DISPATCH(CALL_BVH, CALL_FLAT)                                                                         \
+    if (flat) {                                                                                                        \
+        if (media) { if (legacy) { CALL_FLAT(true, true); } else { CALL_FLAT(true, false); } }                         \
+        else { if (legacy) { CALL_FLAT(false, true); } else { CALL_FLAT(false, false); } }                             \
+    } else {                                                                                                           \
+        if (media) { if (legacy) { CALL_BVH(true, true); } else { CALL_BVH(true, false); } }                           \
+        else { if (legacy) { CALL_BVH(false, true); } else { CALL_BVH(false, false); } }                               \
     }
+cudaError_t launch_megakernel(const DScene& sc, const FlatProgram* flatp, const DCamera& cam, const RenderArgs& a,
+                              const RenderBuffers& b, int grid, bool legacy, cudaStream_t st) {
+    const bool flat = flatp && flatp->n, media = sc.has_media;
+#define VK_LB(M, G) k_megakernel<M, G><<<grid, VK_BLOCK, 0, st>>>(sc, cam, a, b)
+#define VK_LF(M, G) k_megakernel_flat<M, G><<<grid, VK_BLOCK, 0, st>>>(sc, *flatp, cam, a, b)
+    VK_MEGA_DISPATCH(VK_LB, VK_LF)
+#undef VK_LB
+#undef VK_LF
     return cudaGetLastError();
 }
 cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk_ray* rays, size_t n, const float* medium_xi,
@@ -443,12 +451,15 @@ cudaError_t launch_intersect(const DScene& sc, const FlatProgram* flat, const vk
     else k_intersect<<<grid, VK_BLOCK, 0, st>>>(sc, rays, n, medium_xi, out);
     return cudaGetLastError();
 }
-cudaError_t megakernel_occupancy(bool flat, bool media, int* blocks_per_sm, int* block_threads) {
+cudaError_t megakernel_occupancy(bool flat, bool media, bool legacy, int* blocks_per_sm, int* block_threads) {
     *block_threads = VK_BLOCK;
-    if (flat) return media ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel_flat<true>, VK_BLOCK, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel_flat<false>, VK_BLOCK, 0);
-    return media ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel<true>, VK_BLOCK, 0)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel<false>, VK_BLOCK, 0);
+    cudaError_t e = cudaSuccess;
+#define VK_OB(M, G) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel<M, G>, VK_BLOCK, 0)
+#define VK_OF(M, G) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_megakernel_flat<M, G>, VK_BLOCK, 0)
+    VK_MEGA_DISPATCH(VK_OB, VK_OF)
+#undef VK_OB
+#undef VK_OF
+    return e;
 }
 cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st) {
     k_philox_kat<<<1, 1, 0, st>>>(ctr_key6, out4);

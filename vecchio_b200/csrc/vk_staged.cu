@@ -265,7 +265,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                 const uint32_t prim = hp.y;
                 bool alive, valid = true;
                 if (prim == VK_REF_NONE) {
-                    L = beta * a.background; // src/main.rs:151
+                    L = beta * miss_color(a, d); // src/main.rs:151
                     alive = false;
                 } else {
                     PathRng rng;

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(VKW_BLOCK) k_wf_shade(const DScene sc, const D
         const uint32_t sample = f2u(bt.w);
         bool alive, valid = true;
         if (hq.y == VK_REF_NONE) {
-            L = beta * a.background; // src/main.rs:151
+            L = beta * miss_color(a, d); // src/main.rs:151
             alive = false;
         } else {
             PathRng rng;

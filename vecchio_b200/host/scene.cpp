@@ -153,8 +153,32 @@ SceneConfig balls_demo() {
     return s;
 }
 
-// src/scene.rs:167-284
-SceneConfig random_spheres_demo() {
+// Authored with the reference's API to exercise the surface no shipped scene touches (SURVEY 8f rank
+// 4): a SpecDiffuse material (src/material.rs:467-488), and a Sphere and a Boxy in the light list
+// (cone sampling with the reference's (1-z*z) quirk, src/hittable.rs:104-134; Boxy sides, :371-377).
+SceneConfig api_surface_demo() {
+    SceneConfig s;
+    s.world.push_back(arc<Sphere>(Vec3(0, -100.5f, -1), 100.0f, lambert(0.8f, 0.8f, 0.8f)));
+    s.world.push_back(arc<Sphere>(Vec3(0, 0, -1), 0.5f,
+                                  arc<SpecDiffuse>(arc<Metal>(solid(0.9f, 0.9f, 0.9f), 0.05f), lambert(0.1f, 0.2f, 0.5f), 0.25f)));
+    s.world.push_back(arc<Sphere>(Vec3(1, 0, -1), 0.5f, arc<Metal>(solid(0.8f, 0.6f, 0.2f), 0.3f)));
+    s.world.push_back(arc<Sphere>(Vec3(-1, 0, -1), 0.5f, arc<Dielectric>(1.5f)));
+    auto ball_light = arc<Sphere>(Vec3(-2.2f, 1.6f, -0.5f), 0.4f, arc<DiffuseLight>(solid(6.0f, 5.0f, 4.0f)));
+    s.world.push_back(ball_light);
+    s.lights.push_back(ball_light);
+    auto box_light = arc<Boxy>(Vec3(1.8f, 1.2f, -1.6f), Vec3(2.4f, 1.6f, -1.0f), arc<DiffuseLight>(solid(3.0f, 4.0f, 6.0f)));
+    s.world.push_back(box_light);
+    s.lights.push_back(box_light);
+    push_sky_light(s, 3.0f, 6.0f, Vec3::new_const(2.0f));
+    s.aspect_ratio = 16.0f / 9.0f;
+    s.cam_iter = fixed(Vec3(0, 2, 10), Vec3(0, 1, 0), 40.0f, s.aspect_ratio);
+    return s;
+}
+
+// src/scene.rs:167-284; `with_light` = false gives the book-1 cover as it was before the light was
+// added (sample/inoneweekend.png): lit by the sky only, so it needs the legacy integrator
+// (VK_FLAG_LEGACY_SCATTER | VK_FLAG_SKY_BACKGROUND) -- HEAD panics on its empty light list.
+static SceneConfig random_spheres(bool with_light) {
     SceneConfig s;
     auto checker = arc<Checker>(solid(0.1f, 0.1f, 0.1f), solid(0.9f, 0.9f, 0.9f));
     s.world.push_back(arc<Sphere>(Vec3(0, -1000, 0), 1000.0f, arc<Lambertian>(checker)));
@@ -174,12 +198,14 @@ SceneConfig random_spheres_demo() {
     s.world.push_back(arc<Sphere>(Vec3(-4, 1, 0), 1.0f, arc<Lambertian>(arc<ImageTexture>("assets/earthmap.png"))));
     s.world.push_back(arc<Sphere>(Vec3(4, 1, 0), 1.0f, arc<Metal>(solid(0.7f, 0.6f, 0.5f), 0.0f)));
 
-    push_sky_light(s, 11.0f, 8.0f, Vec3(1.0f, 0.77f, 0.56f) * 2.0f);
+    if (with_light) push_sky_light(s, 11.0f, 8.0f, Vec3(1.0f, 0.77f, 0.56f) * 2.0f);
 
     s.aspect_ratio = 16.0f / 9.0f;
     s.cam_iter = rotating(Vec3(0, 1.5f, 0), 20.0f, s.aspect_ratio, 2.5f, 25.0f, 20.0f, 0.5f, 360.0f);
     return s;
 }
+SceneConfig random_spheres_demo() { return random_spheres(true); }
+SceneConfig random_spheres_cover() { return random_spheres(false); }
 
 // src/scene.rs:286-338
 SceneConfig perlin_demo() {

@@ -375,6 +375,8 @@ SceneConfig final_scene();
 // Authored with the same API for BASELINE.json configs 3 and 5 (not in src/scene.rs).
 SceneConfig cornell_smoke();
 SceneConfig stress_spheres(uint32_t grid_side);
+SceneConfig api_surface_demo();     // SpecDiffuse + sphere and box lights (API surface no shipped scene uses)
+SceneConfig random_spheres_cover(); // random_spheres_demo without its light: the sky-lit book-1 cover (legacy integrator)
 
 // A scene lowered for the GPU: the boundary object of src/main.rs:168-169.
 struct LoweredScene {
