@@ -773,7 +773,7 @@ static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCam
                      : vkfast::launch_wf_extend(c->scene, flat, a, w, b, set, c->stream));
         CU(c, strict ? vkstrict::launch_wf_shade(c->scene, dc, a, w, b, set, c->stream)
                      : vkfast::launch_wf_shade(c->scene, dc, a, w, b, set, c->stream));
-        *launches += 2;
+        *launches += flat ? 2 : 3; // BVH scenes: extend + classify + shade
         if (it + 1 >= next_check) {
             CU(c, cudaMemcpyAsync(c->wf_host_counts, w.qcount + set * VKW_CLASSES, VKW_CLASSES * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CU(c, cudaStreamSynchronize(c->stream));

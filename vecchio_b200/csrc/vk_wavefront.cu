@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(VKW_BLOCK) k_wf_shade(const DScene sc, const D
     if (j == 0) { // the next iteration's counters; this iteration's ray count
 #pragma unroll
         for (uint32_t c = 0; c < VKW_CLASSES; ++c) w.qcount[(set ^ 1u) * VKW_CLASSES + c] = 0u;
+        w.qcount[2 * VKW_CLASSES + (set ^ 1u)] = 0u; // slot head of the dynamic extend
         atomicAdd(&buf.counters[0], (unsigned long long)total);
     }
     __syncthreads();
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(VKW_BLOCK) k_wf_shade(const DScene sc, const D
             h.t = u2f(hq.x);
             h.prim = hq.y;
             h.inst = hq.z;
-            h.face = hq.w;
+            h.face = hq.w & 0xFFu; // (the dynamic extend keeps the shading class in the upper bits)
             HitRecD rec;
             resolve_hit(sc, h, o, d, time, false, rec);
             alive = shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
@@ -258,6 +259,128 @@ __global__ void __launch_bounds__(VKW_BLOCK) k_wf_shade(const DScene sc, const D
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// extend for BVH scenes: persistent warps with dynamic fetch.  Traversal lengths have a long tail
+// (10^6 spheres: mean 28 four-wide visits, some rays hundreds), so a thread is not tied to a slot:
+// the warp runs the resumable traversal (Trav) in bounded while-while rounds and a lane whose ray is
+// finished takes the next untraced slot from a global counter.  With 2^19 rays per launch the tail
+// is paid once per launch, not once per warp.  The hit is stored with its shading class;
+// k_wf_classify then builds the class queues (block-aggregated atomics, as in wf_extend_body).
+// ---------------------------------------------------------------------------------------------------
+#ifndef VKW_FETCH_MIN_IDLE
+#define VKW_FETCH_MIN_IDLE 8u
+#endif
+#ifndef VKW_NODE_STEPS
+#define VKW_NODE_STEPS 4
+#endif
+template <bool MEDIA>
+__global__ void __launch_bounds__(128, 6) k_wf_extend_dyn(const DScene sc, const RenderArgs a, const WfState w, const RenderBuffers buf,
+                                                          uint32_t set) {
+    const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
+    uint32_t* slot_head = &w.qcount[2 * VKW_CLASSES + set];
+    Trav T;
+    T.ref = VKD_DONE;
+    T.sp = 0;
+    T.enter = false;
+    T.cur_inst = 0;
+    T.co = T.cd = T.cinv = f3(0.0f, 0.0f, 0.0f);
+    T.best.t = 0.0f;
+    T.best.prim = VK_REF_NONE;
+    T.best.inst = 0;
+    T.best.face = 0;
+    float3 o = f3(0.0f, 0.0f, 0.0f), d = o;
+    float tm = 0.0f;
+    uint32_t cur = 0xFFFFFFFFu;
+    bool pool_empty = false;
+    MediumXi xi;
+    xi.table = nullptr;
+    xi.depth = 0;
+    xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
+    xi.rng.pixel = 0;
+    xi.rng.sample = 0;
+    TraceCounters tc = {0u, 0u};
+#pragma unroll 1
+    for (;;) {
+        const uint32_t m_idle = __ballot_sync(0xFFFFFFFFu, T.ref == VKD_DONE);
+        const uint32_t m_need = __ballot_sync(0xFFFFFFFFu, T.ref == VKD_DONE && !pool_empty);
+        if (m_need != 0u && ((uint32_t)__popc(m_idle) >= VKW_FETCH_MIN_IDLE)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(slot_head, (uint32_t)__popc(m_need));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (T.ref == VKD_DONE && !pool_empty) {
+                const uint32_t my = base + __popc(m_need & lanes_below);
+                if (my >= w.n_slots) pool_empty = true;
+                else {
+                    const float4 rd = w.ray_d[my];
+                    if (f2u(rd.w) != 0u) {
+                        const float4 ro = w.ray_o[my];
+                        o = f3(ro);
+                        d = f3(rd);
+                        tm = ro.w;
+                        xi.depth = f2u(rd.w);
+                        if (MEDIA) {
+                            xi.rng.pixel = w.unit[my].x;
+                            xi.rng.sample = f2u(w.beta[my].w);
+                        }
+                        trav_init(T, sc, o, d, CUDART_INF_F); // world.hit(&r, 0.001, inf) src/main.rs:130
+                        cur = my;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, T.ref != VKD_DONE) == 0u) {
+            if (__ballot_sync(0xFFFFFFFFu, !pool_empty) == 0u) break;
+            continue; // every lane drew an idle slot (only while the pool drains): draw again
+        }
+#pragma unroll 1
+        for (int k = 0; k < VKW_NODE_STEPS && trav_at_node(T); ++k) trav_node_step(T, sc, 0.001f, tc);
+        if (T.ref != VKD_DONE && !trav_at_node(T)) trav_prim_step<MEDIA>(T, sc, o, d, tm, 0.001f, xi, tc);
+        if (cur != 0xFFFFFFFFu && T.ref == VKD_DONE) { // finished: the hit and its shading class
+            uint32_t cls = VKW_TERMINATE;
+            if (T.best.prim != VK_REF_NONE) {
+                const uint32_t mtype = __ldg(&sc.materials[prim_material(sc, T.best.prim)]).x;
+                cls = mtype == VK_M_DIFFUSE_LIGHT ? VKW_TERMINATE : mtype == VK_M_DIELECTRIC ? VKW_DIELECTRIC : mtype == VK_M_METAL ? VKW_METAL : VKW_DIFFUSE;
+            }
+            w.hit[cur] = make_uint4(f2u(T.best.t), T.best.prim, T.best.inst, T.best.face | (cls << 8));
+            cur = 0xFFFFFFFFu;
+        }
+    }
+    uint32_t wn = tc.nodes, wp = tc.prims;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        wn += __shfl_xor_sync(0xFFFFFFFFu, wn, off);
+        wp += __shfl_xor_sync(0xFFFFFFFFu, wp, off);
+    }
+    if (lane == 0 && (wn | wp)) {
+        atomicAdd(&buf.counters[3], (unsigned long long)wn);
+        atomicAdd(&buf.counters[4], (unsigned long long)wp);
+    }
+}
+// class queues from the hits the dynamic extend stored (slot == thread)
+__global__ void __launch_bounds__(VKW_BLOCK) k_wf_classify(const WfState w, uint32_t set) {
+    __shared__ uint32_t s_cnt[VKW_CLASSES], s_base[VKW_CLASSES];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    if (threadIdx.x < VKW_CLASSES) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const bool live = i < w.n_slots && f2u(w.ray_d[i].w) != 0u;
+    const uint32_t cls = live ? ((w.hit[i].w >> 8) & 3u) : 0u;
+    uint32_t my_rank = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < VKW_CLASSES; ++c) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, live && cls == c);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_cnt[c], (uint32_t)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (live && cls == c) my_rank = base + __popc(m & ((1u << lane) - 1u));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < VKW_CLASSES) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&w.qcount[set * VKW_CLASSES + threadIdx.x], s_cnt[threadIdx.x]) : 0u;
+    __syncthreads();
+    if (live) w.queue[(size_t)cls * w.n_slots + s_base[cls] + my_rank] = i;
+}
+
 cudaError_t launch_wf_generate(const DCamera& cam, const RenderArgs& a, const WfState& w, cudaStream_t st) {
     k_wf_generate<<<(w.n_slots + VKW_BLOCK - 1) / VKW_BLOCK, VKW_BLOCK, 0, st>>>(cam, a, w);
     return cudaGetLastError();
@@ -268,9 +391,18 @@ cudaError_t launch_wf_extend(const DScene& sc, const FlatProgram* flat, const Re
     if (flat && flat->n) {
         if (sc.has_media) k_wf_extend_flat<true><<<grid, VKW_BLOCK, 0, st>>>(sc, *flat, a, w, b, set);
         else k_wf_extend_flat<false><<<grid, VKW_BLOCK, 0, st>>>(sc, *flat, a, w, b, set);
-    } else {
-        if (sc.has_media) k_wf_extend<true><<<grid, VKW_BLOCK, 0, st>>>(sc, a, w, b, set);
-        else k_wf_extend<false><<<grid, VKW_BLOCK, 0, st>>>(sc, a, w, b, set);
+    } else { // BVH scene: persistent warps with dynamic fetch, then the class queues
+        int bps = 0;
+        cudaError_t e = sc.has_media ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wf_extend_dyn<true>, 128, 0)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wf_extend_dyn<false>, 128, 0);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned pgrid = (unsigned)(sms * (bps < 1 ? 1 : bps));
+        if (sc.has_media) k_wf_extend_dyn<true><<<pgrid, 128, 0, st>>>(sc, a, w, b, set);
+        else k_wf_extend_dyn<false><<<pgrid, 128, 0, st>>>(sc, a, w, b, set);
+        k_wf_classify<<<grid, VKW_BLOCK, 0, st>>>(w, set);
     }
     return cudaGetLastError();
 }
