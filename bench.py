@@ -32,8 +32,8 @@ import numpy as np  # noqa: E402
 CONFIGS = {
     # name: (scene, param, width, height, spp, max_depth, cpu_spp)   -- BASELINE.json configs[0..4]
     "random_spheres": ("random_spheres_demo", 0, 400, 225, 16, 50, 16),
-    "cornell": ("cornell_box", 0, 600, 600, 1000, 100, 16),
-    "cornell_smoke": ("cornell_smoke", 0, 600, 600, 2000, 100, 16),
+    "cornell": ("cornell_box", 0, 600, 600, 1000, 100, 64),
+    "cornell_smoke": ("cornell_smoke", 0, 600, 600, 2000, 100, 32),
     "final_scene": ("final_scene", 0, 800, 800, 10000, 100, 4),
     "stress_1m": ("stress_spheres", 1000, 3840, 2160, 256, 50, 1),
 }
@@ -231,7 +231,9 @@ def run_ours(args, cfg):
     kst = ctx.render_device(cam, params(77), d_sum.data_ptr(), want_stats=True)
     k_ms, k_rays, k_paths = kst.ms_kernels, kst.rays, kst.paths
     variant_name = {1: "megakernel", 2: "wavefront", 3: "staged"}.get(kst.variant, str(kst.variant))
-    kernel_name = {1: "k_megakernel", 2: "k_wf_extend + k_wf_shade", 3: "k_staged"}.get(kst.variant, "?") + ("_flat" if scene.nbytes() < 4096 and kst.variant != 2 else "")
+    flat_program = kst.node_visits == 0  # the flat traversal program visits no BVH node
+    kernel_name = ({1: "k_megakernel_flat" if flat_program else ("k_megakernel_dyn" if scene.desc.n_nodes >= 65536 else "k_megakernel"),
+                    2: "k_wf_extend + k_wf_shade", 3: "k_staged_flat" if flat_program else "k_staged"}.get(kst.variant, "?"))
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------
     for i in range(2):
