@@ -751,11 +751,17 @@ struct HitRecD {
     uint4 m; // materials[mat], fetched once per segment
 };
 
-VKD void spherical(float3 p, float& u, float& v) { // Sphere::spherical src/hittable.rs:54-61
-    const float phi = atan2f(p.z, p.x);
-    const float theta = asinf(p.y);
-    u = 1.0f - ((phi + VK_PI) / (2.0f * VK_PI));
-    v = (theta + VK_PI / 2.0f) / VK_PI;
+// Out of line (atan2f + asinf are ~160 instructions and only image-textured spheres need them); by
+// value, so that the caller's HitRec stays in registers.
+static __device__ __noinline__ float2 spherical_uv(float px, float py, float pz) { // Sphere::spherical src/hittable.rs:54-61
+    const float phi = atan2f(pz, px);
+    const float theta = asinf(py);
+    return make_float2(1.0f - ((phi + VK_PI) / (2.0f * VK_PI)), (theta + VK_PI / 2.0f) / VK_PI);
+}
+VKD void spherical(float3 p, float& u, float& v) {
+    const float2 uv = spherical_uv(p.x, p.y, p.z);
+    u = uv.x;
+    v = uv.y;
 }
 VKD void set_face_normal(float3 dir, float3 outward, HitRecD& rec) { // src/hittable.rs:23-30
     rec.front = dot3(dir, outward) < 0.0f ? 1u : 0u;
@@ -1051,14 +1057,11 @@ VKD float3 rect_random(float4 bounds, float k, uint32_t axes, float3 origin, uin
     pt.z = a0 == 2 ? pa : (a1 == 2 ? pb : k);
     return pt - origin;
 }
-VKD float light_pdf_value(const DScene& sc, uint32_t ref, float3 o, float3 v) {
+// The light list of every shipped scene holds one Rect; Sphere and Boxy lights are kept out of line so
+// that the hot shading code stays small (the kernels are instruction-fetch sensitive).
+static __device__ __noinline__ float light_pdf_value_other(const DScene& sc, uint32_t ref, float3 o, float3 v) {
     const uint32_t i = VKD_INDEX(ref);
     switch (VKD_TYPE(ref)) {
-    case VK_T_RECT: {
-        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
-        if (__float_as_uint(r1.y) & VK_RECT_FLIP) return 0.0f; // FlipFace: trait default
-        return rect_pdf_value(r0, r1.x, __float_as_uint(r1.y), o, v);
-    }
     case VK_T_SPHERE: {
         const float4 s = __ldg(&sc.spheres[i]);
         float t;
@@ -1084,14 +1087,18 @@ VKD float light_pdf_value(const DScene& sc, uint32_t ref, float3 o, float3 v) {
     default: return 0.0f; // Hittable::pdf_value default
     }
 }
-VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, uint32_t x1, uint32_t x2) {
+VKD float light_pdf_value(const DScene& sc, uint32_t ref, float3 o, float3 v) {
+    if (VKD_TYPE(ref) == VK_T_RECT) {
+        const uint32_t i = VKD_INDEX(ref);
+        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
+        if (__float_as_uint(r1.y) & VK_RECT_FLIP) return 0.0f; // FlipFace: trait default
+        return rect_pdf_value(r0, r1.x, __float_as_uint(r1.y), o, v);
+    }
+    return light_pdf_value_other(sc, ref, o, v);
+}
+static __device__ __noinline__ float3 light_random_other(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, uint32_t x1, uint32_t x2) {
     const uint32_t i = VKD_INDEX(ref);
     switch (VKD_TYPE(ref)) {
-    case VK_T_RECT: {
-        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
-        if (__float_as_uint(r1.y) & VK_RECT_FLIP) return f3(1.0f, 0.0f, 0.0f);
-        return rect_random(r0, r1.x, __float_as_uint(r1.y), o, x0, x1);
-    }
     case VK_T_SPHERE: {
         const float4 s = __ldg(&sc.spheres[i]);
         const float3 direction = f3(s) - o;
@@ -1116,6 +1123,15 @@ VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, u
     }
     default: return f3(1.0f, 0.0f, 0.0f); // Hittable::random default
     }
+}
+VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, uint32_t x1, uint32_t x2) {
+    if (VKD_TYPE(ref) == VK_T_RECT) {
+        const uint32_t i = VKD_INDEX(ref);
+        const float4 r0 = __ldg(&sc.rects[2 * i]), r1 = __ldg(&sc.rects[2 * i + 1]);
+        if (__float_as_uint(r1.y) & VK_RECT_FLIP) return f3(1.0f, 0.0f, 0.0f);
+        return rect_random(r0, r1.x, __float_as_uint(r1.y), o, x0, x1);
+    }
+    return light_random_other(sc, ref, o, x0, x1, x2);
 }
 VKD float lights_pdf_value(const DScene& sc, float3 o, float3 v) {
     const float weight = 1.0f / (float)sc.n_lights;
