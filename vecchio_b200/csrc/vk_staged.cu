@@ -23,7 +23,12 @@
 namespace VK_NS {
 
 #define VKS_T 256
+#ifndef VKS_N
 #define VKS_N 1024
+#endif
+#ifndef VKS_MINB
+#define VKS_MINB 3
+#endif
 #define VKS_ROUNDS (VKS_N / VKS_T)
 #define VKS_NEWUNIT 0x80000000u
 enum { VKS_C_TERMINATE = 0, VKS_C_DIELECTRIC = 1, VKS_C_METAL = 2, VKS_C_DIFFUSE = 3, VKS_CLASSES = 4, VKS_C_IDLE = 7 };
@@ -362,12 +367,12 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
 }
 
 template <bool MEDIA>
-__global__ void __launch_bounds__(VKS_T, 3) k_staged(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
+__global__ void __launch_bounds__(VKS_T, VKS_MINB) k_staged(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
                                                      unsigned long long* unit_head) {
     staged_body<false, MEDIA>(sc, nullptr, cam, a, buf, unit_head);
 }
 template <bool MEDIA>
-__global__ void __launch_bounds__(VKS_T, 3) k_staged_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
+__global__ void __launch_bounds__(VKS_T, VKS_MINB) k_staged_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
                                                           const RenderArgs a, const RenderBuffers buf, unsigned long long* unit_head) {
     staged_body<true, MEDIA>(sc, &flat, cam, a, buf, unit_head);
 }
