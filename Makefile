@@ -39,12 +39,14 @@ $(CSRC)/vk_wavefront_strict.o: $(CSRC)/vk_wavefront.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_wf_strict.log || (cat $(CSRC)/ptxas_wf_strict.log; false)
 $(CSRC)/vk_staged_fast.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_staged_fast.log || (cat $(CSRC)/ptxas_staged_fast.log; false)
+$(CSRC)/vk_staged_simple.o: $(CSRC)/vk_staged.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVK_SIMPLE=1 -c -o $@ $< 2> $(CSRC)/ptxas_staged_simple.log || (cat $(CSRC)/ptxas_staged_simple.log; false)
 $(CSRC)/vk_staged_strict.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_staged_strict.log || (cat $(CSRC)/ptxas_staged_strict.log; false)
 $(CSRC)/vk_api.o: $(CSRC)/vk_api.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o
+$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 

@@ -27,6 +27,7 @@ struct vk_ctx {
     bool has_scene = false;
     uint32_t n_nodes = 0; // BVH nodes of the uploaded scene
     bool has_specdiffuse = false;
+    bool simple_scene = false; // only what the VK_SIMPLE build of the staged kernel keeps (see vk_device.cuh)
     unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
     float* partial = nullptr;               // chunk partial sums (sum | sumsq)
@@ -702,6 +703,15 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     c->n_nodes = d->n_nodes;
     c->has_specdiffuse = false;
     for (uint32_t i = 0; i < d->n_materials; ++i) c->has_specdiffuse |= d->materials[i].type == VK_M_SPECDIFFUSE;
+    // simple: solid textures only; Lambertian / Dielectric / DiffuseLight / Isotropic only; no moving sphere;
+    // exactly one light, an unflipped Rect
+    bool simple = d->n_mspheres == 0 && d->n_lights == 1 && VK_REF_TYPE(d->lights[0]) == VK_T_RECT &&
+                  !(d->rects[VK_REF_INDEX(d->lights[0])].axes & VK_RECT_FLIP);
+    for (uint32_t i = 0; i < d->n_textures && simple; ++i) simple = d->textures[i].type == VK_TEX_SOLID;
+    for (uint32_t i = 0; i < d->n_materials && simple; ++i)
+        simple = d->materials[i].type == VK_M_LAMBERTIAN || d->materials[i].type == VK_M_DIELECTRIC ||
+                 d->materials[i].type == VK_M_DIFFUSE_LIGHT || d->materials[i].type == VK_M_ISOTROPIC;
+    c->simple_scene = simple;
     FlatBuilder fb;
     fb.d = d;
     if (!fb.build(&c->flat)) c->flat = FlatProgram{};
@@ -909,8 +919,11 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         CU(c, cudaMemsetAsync(c->counters + 5, 0xFF, 2 * sizeof(unsigned long long), c->stream)); // CTA start / first end: minima
         CU(c, cudaMemsetAsync(c->counters + 7, 0, sizeof(unsigned long long), c->stream));        // last end: maximum
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
-        CU(c, strict ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
-                     : vkfast::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream));
+        // a "simple" scene runs the build of the same kernel with the unreachable code compiled out
+        const bool simple = !strict && flat && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");
+        CU(c, strict   ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
+              : simple ? vkfast_simple::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
+                       : vkfast::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream));
         launches = 1;
     } else if (!flat && !legacy && use_dynamic_megakernel(c)) {
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head

@@ -15,8 +15,18 @@
 #ifndef VK_STRICT
 #define VK_STRICT 0
 #endif
+// VK_SIMPLE=1 (namespace vkfast_simple, vk_staged.cu only): the same code with everything a "simple" scene
+// cannot reach compiled out -- non-solid textures, Metal, SpecDiffuse, sphere / box lights, more than
+// one light, moving spheres, (u, v).  vk_scene_upload decides whether a scene is simple (Cornell box,
+// Cornell smoke).  No arithmetic changes; the point is the instruction footprint: the staged kernel
+// stalls on instruction fetch when its hot code does not fit the 32 KB instruction cache.
+#ifndef VK_SIMPLE
+#define VK_SIMPLE 0
+#endif
 #if VK_STRICT
 #define VK_NS vkstrict
+#elif VK_SIMPLE
+#define VK_NS vkfast_simple
 #else
 #define VK_NS vkfast
 #endif
@@ -714,6 +724,7 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
                 }
             }
         }
+#if !VK_SIMPLE
 #pragma unroll 1
         for (uint32_t i = g.msph0; i < g.msph1; ++i) {
 #pragma unroll
@@ -725,6 +736,7 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
                 }
             }
         }
+#endif
         if (MEDIA) {
 #pragma unroll 1
             for (uint32_t i = g.med0; i < g.med1; ++i) {
@@ -799,12 +811,18 @@ VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, fl
     rec.u = 0.0f;
     rec.v = 0.0f;
     bool want_uv = always_uv;
+#if VK_SIMPLE
+    want_uv = false; // no texture reads (u, v)
+#endif
     switch (VKD_TYPE(ref)) {
     case VK_T_SPHERE:
-    case VK_T_MSPHERE: { // src/hittable.rs:76-89, :165-178
+#if !VK_SIMPLE
+    case VK_T_MSPHERE:
+#endif
+    { // src/hittable.rs:76-89, :165-178
         float3 c;
         float radius;
-        if (VKD_TYPE(ref) == VK_T_SPHERE) {
+        if (VK_SIMPLE || VKD_TYPE(ref) == VK_T_SPHERE) {
             const float4 s = __ldg(&sc.spheres[i]);
             c = f3(s);
             radius = s.w;
@@ -816,7 +834,7 @@ VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, fl
             rec.mat = __float_as_uint(m2.y);
         }
         rec.m = __ldg(&sc.materials[rec.mat]);
-        want_uv = want_uv || (rec.m.w & VKD_MAT_NEEDS_UV);
+        want_uv = !VK_SIMPLE && (want_uv || (rec.m.w & VKD_MAT_NEEDS_UV));
         rec.p = at(o, d, t);
         const float3 outward = (rec.p - c) / radius;
         set_face_normal(d, outward, rec);
@@ -828,7 +846,7 @@ VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, fl
         const uint32_t axes = __float_as_uint(r1.y);
         rec.mat = __float_as_uint(r1.z);
         rec.m = __ldg(&sc.materials[rec.mat]);
-        want_uv = want_uv || (rec.m.w & VKD_MAT_NEEDS_UV);
+        want_uv = !VK_SIMPLE && (want_uv || (rec.m.w & VKD_MAT_NEEDS_UV));
         rect_record(r0, r1.x, axes, axes & VK_RECT_FLIP, o, d, t, want_uv, rec);
         break;
     }
@@ -840,7 +858,7 @@ VKD void leaf_record(const DScene& sc, uint32_t ref, uint32_t face, float3 o, fl
         box_side(f3(b0), f3(b1), face, bounds, k, axes);
         rec.mat = __float_as_uint(b0.w);
         rec.m = __ldg(&sc.materials[rec.mat]);
-        want_uv = want_uv || (rec.m.w & VKD_MAT_NEEDS_UV);
+        want_uv = !VK_SIMPLE && (want_uv || (rec.m.w & VKD_MAT_NEEDS_UV));
         rect_record(bounds, k, axes, face & 1u, o, d, t, want_uv, rec);
         break;
     }
@@ -885,7 +903,7 @@ VKD void resolve_hit(const DScene& sc, const TraceHit& h, float3 o, float3 d, fl
         rec.front = 1u;
         rec.u = 0.0f;
         rec.v = 0.0f;
-        if (always_uv || (rec.m.w & VKD_MAT_NEEDS_UV)) { // (u, v) of rec1, the boundary entry hit
+        if (!VK_SIMPLE && (always_uv || (rec.m.w & VKD_MAT_NEEDS_UV))) { // (u, v) of rec1, the boundary entry hit
             float3 bo = ro, bd = rd;
             const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
             float t1;
@@ -955,8 +973,13 @@ VKD float clamp_ref(float x, float mn, float mx) { return x < mn ? mn : (x > mx 
 static __device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p);
 VKD float3 tex_value(const DScene& sc, uint32_t ti, float u, float v, float3 p) {
     const uint4 t = __ldg(&sc.textures[ti]);
+#if VK_SIMPLE
+    (void)u, (void)v, (void)p;
+    return f3(__uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); // SolidColor :238-242 (the only kind)
+#else
     if (t.x == VK_TEX_SOLID) return f3(__uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); // SolidColor :238-242
     return tex_value_general(sc, t, u, v, p);
+#endif
 }
 static __device__ __noinline__ float3 tex_value_general(const DScene& sc, uint4 t, float u, float v, float3 p) {
 #pragma unroll 1
@@ -1059,6 +1082,7 @@ VKD float3 rect_random(float4 bounds, float k, uint32_t axes, float3 origin, uin
 }
 // The light list of every shipped scene holds one Rect; Sphere and Boxy lights are kept out of line so
 // that the hot shading code stays small (the kernels are instruction-fetch sensitive).
+#if !VK_SIMPLE
 static __device__ __noinline__ float light_pdf_value_other(const DScene& sc, uint32_t ref, float3 o, float3 v) {
     const uint32_t i = VKD_INDEX(ref);
     switch (VKD_TYPE(ref)) {
@@ -1087,6 +1111,7 @@ static __device__ __noinline__ float light_pdf_value_other(const DScene& sc, uin
     default: return 0.0f; // Hittable::pdf_value default
     }
 }
+#endif
 VKD float light_pdf_value(const DScene& sc, uint32_t ref, float3 o, float3 v) {
     if (VKD_TYPE(ref) == VK_T_RECT) {
         const uint32_t i = VKD_INDEX(ref);
@@ -1094,8 +1119,13 @@ VKD float light_pdf_value(const DScene& sc, uint32_t ref, float3 o, float3 v) {
         if (__float_as_uint(r1.y) & VK_RECT_FLIP) return 0.0f; // FlipFace: trait default
         return rect_pdf_value(r0, r1.x, __float_as_uint(r1.y), o, v);
     }
+#if VK_SIMPLE
+    return 0.0f;
+#else
     return light_pdf_value_other(sc, ref, o, v);
+#endif
 }
+#if !VK_SIMPLE
 static __device__ __noinline__ float3 light_random_other(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, uint32_t x1, uint32_t x2) {
     const uint32_t i = VKD_INDEX(ref);
     switch (VKD_TYPE(ref)) {
@@ -1124,6 +1154,7 @@ static __device__ __noinline__ float3 light_random_other(const DScene& sc, uint3
     default: return f3(1.0f, 0.0f, 0.0f); // Hittable::random default
     }
 }
+#endif
 VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, uint32_t x1, uint32_t x2) {
     if (VKD_TYPE(ref) == VK_T_RECT) {
         const uint32_t i = VKD_INDEX(ref);
@@ -1131,9 +1162,17 @@ VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, u
         if (__float_as_uint(r1.y) & VK_RECT_FLIP) return f3(1.0f, 0.0f, 0.0f);
         return rect_random(r0, r1.x, __float_as_uint(r1.y), o, x0, x1);
     }
+#if VK_SIMPLE
+    (void)x2;
+    return f3(1.0f, 0.0f, 0.0f);
+#else
     return light_random_other(sc, ref, o, x0, x1, x2);
+#endif
 }
 VKD float lights_pdf_value(const DScene& sc, float3 o, float3 v) {
+#if VK_SIMPLE
+    return 0.0f + 1.0f * light_pdf_value(sc, __ldg(&sc.lights[0]), o, v); // sum = 0.0 + weight * pdf with weight 1/1
+#endif
     const float weight = 1.0f / (float)sc.n_lights;
     float sum = 0.0f;
 #pragma unroll 1
@@ -1175,7 +1214,7 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     uint32_t type = m.x;
     uint32_t spdf_type = type; // whose scattering_pdf applies
     float3 emitted = f3(0.0f, 0.0f, 0.0f);
-    if (type == VK_M_SPECDIFFUSE) { // src/material.rs:474-488: emitted() is the trait default (0)
+    if (!VK_SIMPLE && type == VK_M_SPECDIFFUSE) { // src/material.rs:474-488: emitted() is the trait default (0)
         const uint4 q = rng.block(depth, 9u);
         const uint32_t diffuse = m.w & ~VKD_MAT_NEEDS_UV;
         spdf_type = __ldg(&sc.materials[diffuse]).x;
@@ -1203,7 +1242,7 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
         d = nd; // keeps r.time
         return true;
     }
-    if (type == VK_M_METAL) { // src/material.rs:134-141: Ray::new -> time 0 (Q6), never absorbed
+    if (!VK_SIMPLE && type == VK_M_METAL) { // src/material.rs:134-141: Ray::new -> time 0 (Q6), never absorbed
         const float fuzz = __uint_as_float(m.z);
         float3 nd = reflect(unit_vector(d), rec.normal);
         if (fuzz != 0.0f) nd = nd + random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z)) * fuzz;
@@ -1219,8 +1258,12 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     const Onb uvw = onb_from_w(rec.normal);
     float3 nd;
     if (u01(r.x) < 0.5f) { // MixturePDF::generate src/util.rs:177-185 -> HittablePDF -> list random
+#if VK_SIMPLE
+        nd = light_random(sc, __ldg(&sc.lights[0]), rec.p, r.y, r.z, 0u); // the one (unflipped Rect) light
+#else
         const uint32_t li = sc.n_lights > 1 ? min(sc.n_lights - 1u, (uint32_t)(u01(r.w) * (float)sc.n_lights)) : 0u;
         nd = light_random(sc, __ldg(&sc.lights[li]), rec.p, r.y, r.z, r.w * 0x9E3779B1u);
+#endif
     } else {
         const float3 c = random_cosine_direction(u01(r.y), u01(r.z));
         nd = uvw.u * c.x + uvw.v * c.y + uvw.w * c.z;

@@ -195,3 +195,7 @@ struct WfState {
     }
 VK_DECLARE_LAUNCHERS(vkfast)
 VK_DECLARE_LAUNCHERS(vkstrict)
+namespace vkfast_simple { // vk_staged.cu compiled with VK_SIMPLE=1: staged kernel for "simple" flat scenes (see vk_device.cuh)
+cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
+                          unsigned long long* unit_head, int sm_count, cudaStream_t st);
+}
