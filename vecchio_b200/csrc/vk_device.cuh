@@ -1187,18 +1187,23 @@ VKD float lights_pdf_value(const DScene& sc, float3 o, float3 v) {
 // Camera::get_ray (src/main.rs:111-120).  random_in_unit_disk() is always drawn by the reference
 // and multiplied by lens_radius; with lens_radius == 0 the product is exactly 0, so the draw is
 // skipped.  The disk sample is direct (sqrt-radius) instead of the rejection loop: same law.
+// lens_radius * random_in_unit_disk() (src/main.rs:112-113), direct sampling instead of the rejection loop
+static __device__ __noinline__ float2 camera_lens_disk(uint32_t pixel, uint32_t sample, uint32_t k0, uint32_t k1, float lens_radius) {
+    const uint4 q = philox4x32_10(make_uint4(pixel, sample, 1u, 0u), make_uint2(k0, k1)); // block(depth 0, 1)
+    const float rad = sqrtf(u01(q.x)) * lens_radius;
+    float sn, cs;
+    __sincosf(2.0f * VK_PI * u01(q.y), &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
 VKD void camera_get_ray(const DCamera& cam, const PathRng& rng, uint32_t x, uint32_t y, uint32_t width, uint32_t height,
                         float3& o, float3& d, float& time) {
     const uint4 r = rng.block(0u, 0u);
     const float s = ((float)x + u01(r.x)) / (float)(width - 1);  // src/main.rs:187
     const float t = ((float)y + u01(r.y)) / (float)(height - 1); // src/main.rs:188
     float3 offset = f3(0.0f, 0.0f, 0.0f);
-    if (cam.lens_radius != 0.0f) {
-        const uint4 q = rng.block(0u, 1u);
-        const float rad = sqrtf(u01(q.x)) * cam.lens_radius;
-        float sn, cs;
-        __sincosf(2.0f * VK_PI * u01(q.y), &sn, &cs);
-        offset = cam.u * (rad * cs) + cam.v * (rad * sn);
+    if (cam.lens_radius != 0.0f) { // no shipped scene has an aperture: out of line, everything by value
+        const float2 disk = camera_lens_disk(rng.pixel, rng.sample, rng.key.x, rng.key.y, cam.lens_radius);
+        offset = cam.u * disk.x + cam.v * disk.y;
     }
     o = cam.origin + offset;
     d = cam.lower_left_corner + cam.horizontal * s + cam.vertical * t - cam.origin - offset;

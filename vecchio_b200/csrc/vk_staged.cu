@@ -78,11 +78,11 @@ struct StagedCtx {
     unsigned long long n_units;
     unsigned long long* unit_head;
 };
-VKD void staged_refill(const StagedCtx& C) { // one thread
-    StagedShared& S = C.S;
-    while (S.fetched < S.next_unit + VKS_N) {
-        S.chunk_base[(S.fetched / VKS_CHUNK) % VKS_RING] = atomicAdd(C.unit_head, (unsigned long long)VKS_CHUNK);
-        S.fetched += VKS_CHUNK;
+// one thread, every ~20 iterations: out of line, pointers by value
+static __device__ __noinline__ void staged_refill(StagedShared* S, unsigned long long* unit_head) {
+    while (S->fetched < S->next_unit + VKS_N) {
+        S->chunk_base[(S->fetched / VKS_CHUNK) % VKS_RING] = atomicAdd(unit_head, (unsigned long long)VKS_CHUNK);
+        S->fetched += VKS_CHUNK;
     }
 }
 // Start the sample `s` of `pixel` in `slot`: Camera::get_ray, depth 1 (src/main.rs:187-190).
@@ -134,10 +134,12 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
     if (tid == 0) {
         S.next_unit = 0u;
         S.fetched = 0u;
-        staged_refill(C);
+        staged_refill(&S, unit_head);
+#ifdef VKS_DEBUG_TIMES
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        atomicMin(&buf.counters[5], t0); // debug: first CTA start / first and last CTA end (ns)
+        atomicMin(&buf.counters[5], t0); // first CTA start / first and last CTA end (ns), scripts/cta_spread.py
+#endif
     }
     if (tid < 2 * VKS_CLASSES) (&S.cnt[0][0])[tid] = 0u;
     __syncthreads();
@@ -147,7 +149,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
 #pragma unroll 1
     for (uint32_t iter = 0;; ++iter) {
         uint32_t* cnt = S.cnt[iter & 1u];
-        if (tid == 0) staged_refill(C); // consumed by the shade stage, after the barrier
+        if (tid == 0) staged_refill(&S, unit_head); // consumed by the shade stage, after the barrier
         // ---- extend + classify (slot == thread + round * T: conflict-free shared-memory access) -------
         if (FLAT) {
 #pragma unroll 1
@@ -331,9 +333,11 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
         }
         __syncthreads();
     }
+#ifdef VKS_DEBUG_TIMES
     __shared__ unsigned long long s_cta_rays;
     if (tid == 0) s_cta_rays = 0ull;
     __syncthreads();
+#endif
     unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = n_nodes, w_prims = n_prims;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -347,8 +351,11 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
         atomicAdd(&buf.counters[4], w_prims);
         atomicAdd(&buf.counters[0], w_rays);
         if (w_drop) atomicAdd(&buf.counters[1], w_drop);
+#ifdef VKS_DEBUG_TIMES
         atomicAdd(&s_cta_rays, w_rays);
+#endif
     }
+#ifdef VKS_DEBUG_TIMES
     __syncthreads();
     if (tid == 0) {
         unsigned long long t1;
@@ -364,6 +371,9 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
             buf.debug[4 * blockIdx.x + 3] = dbg_iters | ((unsigned long long)dbg_sparse << 32);
         }
     }
+#else
+    (void)dbg_iters, (void)dbg_sparse;
+#endif
 }
 
 template <bool MEDIA>
