@@ -483,3 +483,74 @@ def test_legacy_and_light_list_rules(vb, ctx):
     a, _, _ = ctx.render(cam2, vb.render_params(64, 36, 16, 20, seed=1, flags=vb.VK_FLAG_SKY_BACKGROUND, variant=vb.VK_VARIANT_WAVEFRONT))
     b, _, _ = ctx.render(cam2, vb.render_params(64, 36, 16, 20, seed=1, variant=vb.VK_VARIANT_WAVEFRONT))
     assert a.mean() > 1.5 * b.mean()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs 1, 3, 4, 5 at their full image sizes: size-independent properties
+# (config 2 is test_full_size_cornell_properties).  Samples per pixel are reduced for 4 and 5, and said so.
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_config1_random_spheres(vb, po, ctx):
+    """Config 1 is small enough for the oracle at full size (400x225, 16 spp, depth 50): image statistics
+    of both renders must agree, not just a crop."""
+    scene, cam = get_scene(vb, "random_spheres_demo")
+    ctx.upload(scene)
+    o = po.OracleScene(scene)
+    rg, qg, sg = ctx.render(cam, vb.render_params(400, 225, 16, 50, seed=61), want_sumsq=True)
+    ro, qo, so = o.render(cam, vb.render_params(400, 225, 16, 50, seed=62), want_sumsq=True)
+    assert sg.paths == 400 * 225 * 16 == so.paths and np.isfinite(rg).all()
+    assert abs(sg.rays / sg.paths - so.rays_live / so.paths) <= 0.02 * so.rays_live / so.paths
+    z, nz, _, _ = zscores(rg, qg, 16, ro, qo, 16)
+    assert (np.abs(z[nz]) <= 3).mean() >= 0.97  # 16 spp: heavy-tailed pixels cost a little more than at 256+
+    assert abs(rg.mean() - ro.mean()) <= 0.03 * ro.mean()
+
+
+def test_full_size_config3_cornell_smoke(vb, ctx):
+    scene, cam = get_scene(vb, "cornell_smoke")
+    ctx.upload(scene)
+    rgb, _, st = ctx.render(cam, vb.render_params(600, 600, 2000, 100, seed=1))
+    assert st.paths == 720_000_000 and np.isfinite(rgb).all() and rgb.min() >= 0.0
+    assert 2.1 <= st.rays / st.paths <= 2.4 and st.dropped_samples <= 1e-5 * st.paths
+    # the black smoke box (image right: x ~ 265..430 world = image-left mirrored) is darker than the white one
+    img = rgb[::-1]  # top-down
+    lum = img.mean(axis=2)
+    # the two media sit where the Cornell boxes are: tall box region (dark smoke) vs short box region (white smoke)
+    tall, short = lum[250:400, 170:270].mean(), lum[400:520, 330:440].mean()
+    assert short > 1.3 * tall, (tall, short)
+    half, _, _ = ctx.render(cam, vb.render_params(600, 600, 1000, 100, seed=1))
+    assert abs(half.mean() - rgb.mean()) <= 0.005 * rgb.mean()  # linearity in spp slices
+
+
+def test_full_size_config4_final_scene(vb, po, ctx):
+    """800x800 at 256 spp instead of the config's 10 000 (the properties do not depend on spp)."""
+    scene, cam = get_scene(vb, "final_scene")
+    ctx.upload(scene)
+    rgb, _, st = ctx.render(cam, vb.render_params(800, 800, 256, 100, seed=1))
+    assert st.paths == 800 * 800 * 256 and np.isfinite(rgb).all() and rgb.min() >= 0.0
+    _, _, so = po.OracleScene(scene).render(cam, vb.render_params(100, 100, 16, 100, seed=2))
+    assert abs(st.rays / st.paths - so.rays_live / so.paths) <= 0.03 * so.rays_live / so.paths  # segments per path: size independent
+    assert st.dropped_samples <= 1e-4 * st.paths
+    again, _, st2 = ctx.render(cam, vb.render_params(800, 800, 256, 100, seed=1))
+    assert np.array_equal(rgb, again) and st2.rays == st.rays  # deterministic per seed
+
+
+def test_full_size_config5_million_spheres(vb, po, ctx):
+    """10^6 spheres in one reference-built BVH at 3840x2160, 4 spp instead of 256."""
+    scene = vb.Scene("stress_spheres", seed=1, param=1000)
+    cam = scene.next_camera()
+    assert scene.census()["spheres"] == 1_000_000
+    ctx.upload(scene)
+    rgb, _, st = ctx.render(cam, vb.render_params(3840, 2160, 4, 50, seed=1))
+    assert st.paths == 3840 * 2160 * 4 and np.isfinite(rgb).all() and rgb.min() >= 0.0
+    assert 2.7 <= st.rays / st.paths <= 2.9 and st.dropped_samples <= 1e-3 * st.paths
+    # Segments per path and image mean against the oracle at the oracle's size, with the RENDER (fast) build.
+    # This scene is where FMA contraction in Sphere::hit / Ray::at once changed the statistics (|oc|^2 - r^2
+    # cancels at |oc| ~ 300, r = 0.2: 4.4 % more segments, 1.5 % darker); both are now never contracted.
+    small, _, ss = ctx.render(cam, vb.render_params(192, 108, 16, 50, seed=3))
+    ro, _, so = po.OracleScene(scene).render(cam, vb.render_params(192, 108, 16, 50, seed=2))
+    assert abs(ss.rays / ss.paths - so.rays_live / so.paths) <= 0.01 * so.rays_live / so.paths, (ss.rays / ss.paths, so.rays_live / so.paths)
+    assert abs(small.mean() - ro.mean()) <= 0.01 * ro.mean(), (small.mean(), ro.mean())
+    # spp slices of the same seed add up to the whole (the multi-GPU decomposition) at this size too
+    a, _, _ = ctx.render(cam, vb.render_params(3840, 2160, 4, 50, seed=1, spp_begin=0, spp_count=2))
+    b, _, _ = ctx.render(cam, vb.render_params(3840, 2160, 4, 50, seed=1, spp_begin=2, spp_count=2))
+    assert np.allclose(a + b, rgb, rtol=1e-5, atol=1e-7)
+    scene.close()

@@ -60,7 +60,9 @@ VKD float3 unit_vector(float3 a) { // src/vec3.rs:39-42 (three divisions by sqrt
 }
 VKD float comp(float3 v, uint32_t a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 VKD bool finite3(float3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); }
-VKD float3 at(float3 o, float3 d, float t) { return o + d * t; } // Ray::at src/main.rs:51-53
+VKD float3 at(float3 o, float3 d, float t) { // Ray::at src/main.rs:51-53 (never contracted: see sphere_t)
+    return f3(__fadd_rn(o.x, __fmul_rn(d.x, t)), __fadd_rn(o.y, __fmul_rn(d.y, t)), __fadd_rn(o.z, __fmul_rn(d.z, t)));
+}
 
 // ---------------------------------------------------------------------------------------------
 // RNG: counter-based Philox4x32-10 (Salmon et al. 2011), key = render seed, counter =
@@ -143,12 +145,19 @@ VKD bool aabb_hit(float3 bmin, float3 bmax, float3 o, float3 d, float3 inv_d, fl
 // Sphere::hit, distance only (src/hittable.rs:65-95): half-b quadratic, a = |d|^2 (directions are
 // never normalised), strict tmin < t < tmax, near root first.
 // ---------------------------------------------------------------------------------------------
+// The fast build must not contract these products into FMAs.  c = |oc|^2 - r^2 cancels catastrophically
+// when the sphere is far from the origin relative to its radius (10^6-sphere scene: |oc| ~ 300, r = 0.2),
+// so whether a scattered ray re-hits the sphere it left ("acne" beyond tmin) depends on the exact
+// rounding of oc, |oc|^2 and of the hit point: with contraction the fast build traced 4.4 % more
+// segments per path than the reference's arithmetic and rendered that scene 1.5 % darker (measured,
+// scripts/dbg_stress_rays.py).  __fmul_rn / __fadd_rn are never contracted; the order is the reference's.
+VKD float dot3_rn(float3 a, float3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
 VKD bool sphere_t(float3 c, float radius, float3 o, float3 d, float tmin, float tmax, float& t) {
     const float3 oc = o - c;
-    const float a = length2(d);
-    const float half_b = dot3(oc, d);
-    const float cc = length2(oc) - radius * radius;
-    const float disc = half_b * half_b - a * cc;
+    const float a = dot3_rn(d, d);
+    const float half_b = dot3_rn(oc, d);
+    const float cc = __fadd_rn(dot3_rn(oc, oc), -__fmul_rn(radius, radius));
+    const float disc = __fadd_rn(__fmul_rn(half_b, half_b), -__fmul_rn(a, cc));
     if (disc > 0.0f) {
         const float root = sqrtf(disc);
         float temp = (-half_b - root) / a;
