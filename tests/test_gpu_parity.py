@@ -554,3 +554,26 @@ def test_full_size_config5_million_spheres(vb, po, ctx):
     b, _, _ = ctx.render(cam, vb.render_params(3840, 2160, 4, 50, seed=1, spp_begin=2, spp_count=2))
     assert np.allclose(a + b, rgb, rtol=1e-5, atol=1e-7)
     scene.close()
+
+
+STAT_SCENES = [("cornell_box", 0), ("cornell_smoke", 0), ("random_spheres_demo", 0), ("final_scene", 0), ("bowser_demo", 0),
+               ("perlin_demo", 0), ("balls_demo", 0), ("api_surface_demo", 0), ("stress_spheres", 300)]
+
+
+@pytest.mark.parametrize("name,param", STAT_SCENES, ids=[s[0] for s in STAT_SCENES])
+def test_render_build_has_the_statistics_of_the_strict_build(vb, ctx, name, param):
+    """The render build (FMA contraction, approximate reciprocal / rsqrt) against the strict build (the
+    reference's operation sequence) with the same seed: segments per path within 0.5 %, image mean
+    within 1 %, dropped samples of the same order.  Guards against contraction changing which
+    near-degenerate intersections are found (it did, for spheres far from the origin)."""
+    scene, cam = get_scene(vb, name, param=param)
+    ctx.upload(scene)
+    W = 256
+    H = scene.height_for(W)
+    a, _, sa = ctx.render(cam, vb.render_params(W, H, 16, 50, seed=71))
+    b, _, sb = ctx.render(cam, vb.render_params(W, H, 16, 50, seed=71, flags=vb.VK_FLAG_STRICT_MATH))
+    ra, rb = sa.rays / sa.paths, sb.rays / sb.paths
+    print(f"{name}: segments per path fast {ra:.4f} strict {rb:.4f}; mean fast {a.mean():.5f} strict {b.mean():.5f}; dropped {sa.dropped_samples} / {sb.dropped_samples}")
+    assert abs(ra - rb) <= 5e-3 * rb, (name, ra, rb)
+    assert abs(a.mean() - b.mean()) <= 1e-2 * b.mean(), (name, a.mean(), b.mean())
+    assert abs(int(sa.dropped_samples) - int(sb.dropped_samples)) <= 0.5 * sb.dropped_samples + 50
