@@ -577,3 +577,20 @@ def test_render_build_has_the_statistics_of_the_strict_build(vb, ctx, name, para
     assert abs(ra - rb) <= 5e-3 * rb, (name, ra, rb)
     assert abs(a.mean() - b.mean()) <= 1e-2 * b.mean(), (name, a.mean(), b.mean())
     assert abs(int(sa.dropped_samples) - int(sb.dropped_samples)) <= 0.5 * sb.dropped_samples + 50
+
+
+def test_plane_budget_only_changes_the_order_of_the_sum(vb, ctx, monkeypatch):
+    """One plane per sample is the default; a small plane budget (or a device short of memory) makes the
+    units multi-sample.  Same samples either way: the images agree to fp32 summation order, and the
+    variants stay bit-identical to each other under any budget."""
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    p = lambda v: vb.render_params(96, 96, 48, 100, seed=9, variant=v, flags=vb.VK_FLAG_STRICT_MATH)  # noqa: E731
+    full, _, s0 = ctx.render(cam, p(vb.VK_VARIANT_STAGED))
+    monkeypatch.setenv("VECCHIO_PLANE_BUDGET_MB", "1")  # 96*96*12 B = 110 KB per plane -> 9 planes of 6 samples
+    a, _, s1 = ctx.render(cam, p(vb.VK_VARIANT_STAGED))
+    b, _, _ = ctx.render(cam, p(vb.VK_VARIANT_MEGAKERNEL))
+    w, _, _ = ctx.render(cam, p(vb.VK_VARIANT_WAVEFRONT))
+    monkeypatch.delenv("VECCHIO_PLANE_BUDGET_MB")
+    assert s0.rays == s1.rays and np.allclose(full, a, rtol=2e-6, atol=1e-7) and not np.array_equal(full, a)
+    assert np.array_equal(a, b) and np.array_equal(a, w)

@@ -872,17 +872,38 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     // Cornell 600x600x1000 = 4.3 GB of planes, written once with plain stores and summed in order by
     // k_reduce_chunks at HBM speed), otherwise the smallest block that fits.  The block size depends
     // only on the call's parameters, so a render is bit-identical per (seed, spp slice, size).
+    const size_t plane = (size_t)P->width * P->height * 3;
+    RenderBuffers b{};
+    b.counters = c->counters;
+    b.debug = c->debug;
     {
         size_t budget = 6ull << 30;
         if (const char* e = std::getenv("VECCHIO_PLANE_BUDGET_MB")) {
             const long v = std::atol(e);
             if (v > 0) budget = (size_t)v << 20;
         }
-        const size_t plane_bytes = (size_t)P->width * P->height * 3 * sizeof(float) * (d_sumsq ? 2 : 1);
+        const size_t plane_bytes = plane * sizeof(float) * (d_sumsq ? 2 : 1);
         size_t max_planes = budget / plane_bytes;
         if (max_planes < 1) max_planes = 1;
-        a.unit_spp = (uint32_t)((count + max_planes - 1) / max_planes);
-        a.n_planes = (count + a.unit_spp - 1) / a.unit_spp;
+        for (;;) { // a device with less free memory than the budget gets fewer, larger blocks
+            a.unit_spp = (uint32_t)((count + max_planes - 1) / max_planes);
+            a.n_planes = (count + a.unit_spp - 1) / a.unit_spp;
+            if (a.n_planes == 1) {
+                b.partial_sum = d_sum;
+                b.partial_sumsq = d_sumsq;
+                break;
+            }
+            const int rc = ensure(c, &c->partial, &c->partial_floats, plane * a.n_planes * (d_sumsq ? 2 : 1));
+            if (rc == VK_OK) {
+                b.partial_sum = c->partial;
+                b.partial_sumsq = d_sumsq ? c->partial + plane * a.n_planes : nullptr;
+                break;
+            }
+            if (rc != VK_ERR_OOM) return rc;
+            cudaGetLastError(); // clear the allocation failure
+            max_planes = a.n_planes / 2;
+            if (max_planes < 1) max_planes = 1;
+        }
     }
     // Chunks of whole blocks, sized for ~48 work items per resident warp (small items keep the
     // end-of-kernel tail short; an item costs one atomic).
@@ -894,19 +915,6 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     a.chunk_spp = planes_per_chunk * a.unit_spp;
     a.n_chunks = (count + a.chunk_spp - 1) / a.chunk_spp;
 
-    const size_t plane = (size_t)P->width * P->height * 3;
-    RenderBuffers b{};
-    b.counters = c->counters;
-    b.debug = c->debug;
-    if (a.n_planes == 1) {
-        b.partial_sum = d_sum;
-        b.partial_sumsq = d_sumsq;
-    } else {
-        int rc = ensure(c, &c->partial, &c->partial_floats, plane * a.n_planes * (d_sumsq ? 2 : 1));
-        if (rc != VK_OK) return rc;
-        b.partial_sum = c->partial;
-        b.partial_sumsq = d_sumsq ? c->partial + plane * a.n_planes : nullptr;
-    }
     CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // work-queue head only
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
