@@ -45,6 +45,8 @@ struct StagedShared {
     uint4 hp[VKS_N];                   // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; pixel
     uint16_t list[VKS_CLASSES][VKS_N]; // live slots by shading class (each class can hold the whole pool)
     uint32_t cnt[2][VKS_CLASSES];      // class counts, double buffered by iteration parity
+    uint16_t late[VKS_N];              // slots whose regeneration was queued (| 0x8000: needs a new unit)
+    uint32_t n_late;
     uint32_t next_unit;                // CTA-local unit counter (local index n)
     uint32_t fetched;                  // local indices [0, fetched) are backed by a chunk
     unsigned long long chunk_base[VKS_RING]; // global unit of local index n: chunk_base[(n / VKS_CHUNK) % VKS_RING] + n % VKS_CHUNK
@@ -132,6 +134,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
     uint32_t dbg_iters = 0, dbg_sparse = 0; // iterations run; iterations with fewer than N/8 live slots
 
     if (tid == 0) {
+        S.n_late = 0u;
         S.next_unit = 0u;
         S.fetched = 0u;
         staged_refill(&S, unit_head);
@@ -259,8 +262,8 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
 #pragma unroll 1
         for (uint32_t j0 = 0; j0 < n_live; j0 += VKS_T) {
             const uint32_t j = j0 + tid;
-            bool new_unit = false;
-            uint32_t slot = 0;
+            bool new_unit = false, ended = false;
+            uint32_t slot = 0, next_sample = 0;
             if (j < n_live) {
                 slot = j < o1 ? S.list[0][j] : (j < o2 ? S.list[1][j - o1] : (j < o3 ? S.list[2][j - o2] : S.list[3][j - o3]));
                 const float4 ro = S.ro[slot], rd = S.rd[slot], bt = S.bt[slot];
@@ -322,16 +325,42 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                             pq[2] = q.z;
                         }
                     }
-                    if (sample + 1u < s_end) staged_begin_sample(C, slot, pixel, sample + 1u); // regenerate in place
-                    else {
-                        new_unit = true;
-                        S.rd[slot].w = __uint_as_float(0u); // idle unless a unit is left
-                    }
+                    ended = true;
+                    next_sample = sample + 1u;
+                    new_unit = next_sample >= s_end;
+                    S.rd[slot].w = __uint_as_float(0u); // idle until regenerated
                 }
             }
-            staged_take_units(C, new_unit, slot, lane);
+            // Regenerate in place (src/main.rs:187-190) when at least half the warp ended -- the emitter /
+            // miss class does, every lane -- otherwise queue the slot: in the other classes only a few
+            // lanes end (a light-sampled direction below the surface has weight 0), and the 300
+            // instructions of Philox + camera ray would run with those few lanes active.
+            const uint32_t m_end = __ballot_sync(0xFFFFFFFFu, ended);
+            if ((uint32_t)__popc(m_end) >= 16u) {
+                staged_take_units(C, ended && new_unit, slot, lane);
+                if (ended && !new_unit) staged_begin_sample(C, slot, S.hp[slot].w, next_sample);
+            } else if (m_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&S.n_late, (uint32_t)__popc(m_end));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (ended) S.late[base + __popc(m_end & lanes_below)] = (uint16_t)(slot | (new_unit ? 0x8000u : 0u));
+            }
         }
         __syncthreads();
+        {   // the queued regenerations, with full warps
+            const uint32_t n_late = S.n_late;
+#pragma unroll 1
+            for (uint32_t k0 = 0; k0 < n_late; k0 += VKS_T) {
+                const uint32_t k = k0 + tid;
+                const bool have = k < n_late;
+                const uint32_t e = have ? S.late[k] : 0u, slot = e & 0x7FFFu;
+                const bool new_unit = have && (e & 0x8000u);
+                staged_take_units(C, new_unit, slot, lane);
+                if (have && !new_unit) staged_begin_sample(C, slot, S.hp[slot].w, __float_as_uint(S.bt[slot].w) + 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) S.n_late = 0u; // next written in the shade stage, two barriers away
     }
 #ifdef VKS_DEBUG_TIMES
     __shared__ unsigned long long s_cta_rays;
