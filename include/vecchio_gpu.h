@@ -281,6 +281,22 @@ const char* vk_last_error(const vk_ctx* ctx);
  * src/main.rs:168-169. */
 int vk_scene_upload(vk_ctx* ctx, const vk_scene_desc* scene);
 
+/* Host-only: validate a flattened scene and plan its device layout exactly as vk_scene_upload would,
+ * without a device.  Reports what the upload would build (and lets CPU tests cover the validator, the
+ * 4-wide BVH collapse and the flat-program builder).  Same return codes as vk_scene_upload; the message
+ * goes to err (nullable). */
+typedef struct vk_scene_info {
+    uint32_t flat_entries;         /* primitives in the flat traversal program, 0 = the BVH is traversed   */
+    uint32_t flat_segments;        /* world frame + instance frames                                        */
+    uint32_t simple;               /* 1 = the trimmed ("simple scene") build of the staged kernel applies  */
+    uint32_t wide_nodes;           /* 4-wide nodes made from the reference's binary nodes                  */
+    uint32_t wide_levels_world;    /* 4-wide levels of the world BVH / of the deepest instanced sub-BVH     */
+    uint32_t wide_levels_instance;
+    uint32_t stack_need;           /* traversal stack entries needed (<= 96)                               */
+    uint32_t dynamic_megakernel;   /* 1 = BVH large enough for the dynamic re-fill megakernel               */
+} vk_scene_info;
+int vk_scene_check(const vk_scene_desc* scene, vk_scene_info* info, char* err, size_t err_len);
+
 /* The sample loop, src/main.rs:181-198.  out_rgb: W*H*3 floats, pixel i = y*W+x,
  * row 0 = bottom (main.rs:182-183), linear mean over `spp` (main.rs:196).
  * out_sumsq (nullable): per channel sum of squares of the kept samples.  Host buffers. */

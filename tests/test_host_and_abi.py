@@ -139,3 +139,63 @@ def test_stress_scene_small(vb):
     s = vb.Scene("stress_spheres", param=40)
     c = s.census()
     assert c["spheres"] == 1600 and c["nodes"] == bvh_nodes(1602) and c["lights"] == 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# vk_scene_check: the validator and the device-layout planning of vk_scene_upload, without a device
+# ---------------------------------------------------------------------------------------------------
+def test_scene_check_plans_every_shipped_scene(vb):
+    want = {  # scene: (flat program?, simple build?, dynamic megakernel?)
+        "cornell_box": (True, True, False), "cornell_smoke": (True, True, False), "balls_demo": (True, False, False),
+        "api_surface_demo": (True, False, False), "perlin_demo": (True, False, False), "random_spheres_demo": (False, False, False),
+        "random_spheres_cover": (False, False, False), "final_scene": (False, False, False), "bowser_demo": (False, False, False),
+    }
+    for name, (flat, simple, dyn) in want.items():
+        s, _ = get_scene(vb, name)
+        info = vb.scene_check(s.desc_ptr)
+        assert (info["flat_entries"] > 0, bool(info["simple"]), bool(info["dynamic_megakernel"])) == (flat, simple, dyn), (name, info)
+        assert info["stack_need"] <= 96 and info["wide_nodes"] >= 1
+    c = vb.scene_check(get_scene(vb, "cornell_box")[0].desc_ptr)
+    # 6 world rects (5 walls + the flipped light) + 6 box sides + 1 sphere, in the world frame + one instance frame
+    assert (c["flat_entries"], c["flat_segments"]) == (13, 2)
+    f = vb.scene_check(get_scene(vb, "final_scene")[0].desc_ptr)
+    # 13 + 511 + 1023 binary nodes collapse into far fewer 4-wide nodes; two BVH levels (world, instanced spheres)
+    assert f["wide_nodes"] < (13 + 511 + 1023) * 0.6 and f["wide_levels_instance"] >= 4
+
+
+def test_scene_check_big_bvh_selects_the_dynamic_megakernel(vb):
+    s = vb.Scene("stress_spheres", param=260)  # 67 600 spheres -> 131 071 binary nodes
+    info = vb.scene_check(s.desc_ptr)
+    assert info["dynamic_megakernel"] == 1 and info["flat_entries"] == 0
+    assert info["wide_nodes"] < 0.5 * s.desc.n_nodes and info["stack_need"] <= 96
+
+
+def _broken(vb, name, mutate):
+    """A private copy of a lowered scene with one field broken; returns the VecchioError code and message."""
+    import copy
+    s = vb.Scene(name)
+    d = s.desc
+    keep = mutate(d)  # may return objects that must stay alive
+    try:
+        vb.scene_check(s.desc_ptr)
+    except vb.VecchioError as e:
+        return e.code, str(e), keep
+    return 0, "", keep
+
+
+def test_scene_check_refuses_malformed_and_unsupported_scenes(vb):
+    def bad_version(d): d.api_version = 99
+    def bad_root(d): d.root = (vb.VK_T_NODE << 28) | 0x0FFFFFF
+    def bad_material(d): d.sphere_mat[0] = 10_000
+    def bad_texture_type(d): d.textures[0].type = 17
+    def cycle(d): d.nodes[1].left = (vb.VK_T_NODE << 28) | 0  # node 1 points back at the root
+    def nested_instance(d):  # the child of a Translate made an instance again -> a transform below a transform's BVH is refused
+        d.xforms[1].child = d.root
+    for mutate, code in ((bad_version, vb.VK_ERR_INVALID), (bad_root, vb.VK_ERR_INVALID), (bad_material, vb.VK_ERR_INVALID),
+                         (bad_texture_type, vb.VK_ERR_INVALID), (cycle, vb.VK_ERR_INVALID)):
+        rc, msg, _ = _broken(vb, "cornell_box", mutate)
+        assert rc == code and msg, (mutate.__name__, rc, msg)
+    rc, msg, _ = _broken(vb, "cornell_box", nested_instance)
+    assert rc in (vb.VK_ERR_UNSUPPORTED, vb.VK_ERR_INVALID) and msg
+    # an empty light list is a valid upload (only the legacy integrator can render it)
+    assert vb.scene_check(get_scene(vb, "random_spheres_cover")[0].desc_ptr)["flat_entries"] == 0

@@ -76,6 +76,8 @@ def gpu_lib():
         L.vk_scene_upload.argtypes = [vp, C.POINTER(_abi.vk_scene_desc)]
         L.vk_render.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, vp,
                                 C.POINTER(_abi.vk_stats)]
+        L.vk_scene_check.argtypes = [C.POINTER(_abi.vk_scene_desc), C.POINTER(_abi.vk_scene_info), C.c_char_p, C.c_size_t]
+        L.vk_scene_check.restype = C.c_int
         L.vk_render_rgb8.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, C.POINTER(_abi.vk_stats)]
         L.vk_render_device.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, vp,
                                        C.POINTER(_abi.vk_stats)]
@@ -92,7 +94,7 @@ def gpu_lib():
     return _gpu
 
 
-GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device",
+GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_check", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device",
                "vk_finalize_device", "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks",
                "vk_device_info"]
 HOST_SYMBOLS = ["vkh_scene_build", "vkh_scene_free", "vkh_scene_desc", "vkh_scene_aspect_ratio",
@@ -149,6 +151,17 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+
+def scene_check(desc_ptr):
+    """``vk_scene_check``: validate + plan the device layout on the host (no GPU needed).  Returns a dict of
+    what ``vk_scene_upload`` would build; raises VecchioError exactly where the upload would fail."""
+    info = _abi.vk_scene_info()
+    err = C.create_string_buffer(256)
+    rc = gpu_lib().vk_scene_check(desc_ptr, C.byref(info), err, 256)
+    if rc != 0:
+        raise VecchioError(rc, err.value.decode())
+    return {n: int(getattr(info, n)) for n, _ in info._fields_}
 
 
 def camera_new(lookfrom, lookat, vup, vfov, aspect_ratio, aperture, focus_dist, time0, time1):

@@ -103,6 +103,11 @@ class vk_stats(C.Structure):
                 ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64)]
 
 
+class vk_scene_info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("flat_entries", "flat_segments", "simple", "wide_nodes", "wide_levels_world",
+                                          "wide_levels_instance", "stack_need", "dynamic_megakernel")]
+
+
 class vk_ray(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("direction", C.c_float * 3), ("time", C.c_float), ("tmin", C.c_float),
                 ("tmax", C.c_float)]

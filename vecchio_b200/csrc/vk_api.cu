@@ -438,6 +438,122 @@ struct FlatBuilder {
     }
 };
 
+// Host-side re-layout of a validated scene (no device needed): the node array with single-object
+// leaves resolved, the 4-wide nodes, the flat program and the "simple scene" test.  vk_scene_upload
+// copies the results to the device; vk_scene_check reports them so that CPU tests can cover this code.
+struct Relayout {
+    std::vector<vk_node> nodes;
+    std::vector<float4> wnodes;
+    FlatProgram flat{};
+    uint32_t levels_world = 0, levels_sub = 0, n_wide = 0, stack_need = 0;
+    bool simple = false, has_specdiffuse = false;
+    // returns nullptr or the reason the scene is unsupported
+    const char* run(const vk_scene_desc* d) {
+    // GPU-side re-layout of the node array: a single-object leaf (left == right) is tested twice
+        // by the reference; that only matters for a ConstantMedium (two free-flight draws), so the
+        // second visit is kept (flagged) only there and dropped for deterministic primitives.
+        nodes.assign(d->nodes, d->nodes + d->n_nodes);
+        for (uint32_t i = 0; i < d->n_nodes; ++i)
+            if (nodes[i].left == nodes[i].right) {
+                vk_ref end = nodes[i].left;
+                while (VK_REF_TYPE(end) == VK_T_XFORM) end = d->xforms[VK_REF_INDEX(end)].child;
+                nodes[i].right = VK_REF_TYPE(end) == VK_T_MEDIUM ? (nodes[i].left | VKD_DUP) : VK_REF_NONE;
+            }
+        // 4-wide nodes from the reference's binary tree (see DScene): start from a node's two children and
+        // keep opening the inner child with the largest surface area until four slots are filled.
+        wnodes.assign((size_t)d->n_nodes * 8, make_float4(0, 0, 0, 0));
+        {
+            struct Slot {
+                vk_ref ref;
+                float mn[3], mx[3];
+            };
+            std::vector<uint8_t> built(d->n_nodes, 0);
+            std::vector<uint32_t> todo, level(d->n_nodes, 0); // level: 4-wide levels above the node inside its BVH
+            levels_world = levels_sub = 0;
+            bool in_sub = false;
+            auto want = [&](vk_ref r, uint32_t lvl) {
+                if (VK_REF_TYPE(r) == VK_T_NODE && !built[VK_REF_INDEX(r)]) {
+                    built[VK_REF_INDEX(r)] = 1;
+                    level[VK_REF_INDEX(r)] = lvl;
+                    todo.push_back(VK_REF_INDEX(r));
+                    uint32_t& top = in_sub ? levels_sub : levels_world;
+                    if (lvl + 1 > top) top = lvl + 1;
+                }
+            };
+            auto child_slot = [&](vk_ref r, const vk_node& parent) { // a node child brings its own box, a primitive its parent's
+                const vk_node& b = VK_REF_TYPE(r) == VK_T_NODE ? d->nodes[VK_REF_INDEX(r)] : parent;
+                Slot s{r, {b.bb_min[0], b.bb_min[1], b.bb_min[2]}, {b.bb_max[0], b.bb_max[1], b.bb_max[2]}};
+                return s;
+            };
+            auto area = [](const Slot& s) {
+                const float x = s.mx[0] - s.mn[0], y = s.mx[1] - s.mn[1], z = s.mx[2] - s.mn[2];
+                return x * y + y * z + z * x;
+            };
+            // the world's BVH first, then the instanced sub-BVHs (an instance is never nested: see Validator)
+            for (int pass = 0; pass < 2; ++pass) {
+            in_sub = pass == 1;
+            if (pass == 0) want(d->root, 0);
+            else
+                for (uint32_t i = 0; i < d->n_xforms; ++i) want(d->xforms[i].child, 0);
+            while (!todo.empty()) {
+                const uint32_t ni = todo.back();
+                todo.pop_back();
+                std::vector<Slot> slots;
+                auto add_children = [&](uint32_t n) {
+                    if (nodes[n].left != VK_REF_NONE) slots.push_back(child_slot(nodes[n].left, d->nodes[n]));
+                    if (nodes[n].right != VK_REF_NONE) slots.push_back(child_slot(nodes[n].right, d->nodes[n]));
+                };
+                add_children(ni);
+                while (slots.size() < 4) {
+                    int best = -1;
+                    for (size_t k = 0; k < slots.size(); ++k)
+                        if (VK_REF_TYPE(slots[k].ref) == VK_T_NODE) {
+                            const uint32_t n = VK_REF_INDEX(slots[k].ref);
+                            const size_t kids = (nodes[n].left != VK_REF_NONE) + (nodes[n].right != VK_REF_NONE);
+                            if (slots.size() - 1 + kids > 4) continue;
+                            if (best < 0 || area(slots[k]) > area(slots[best])) best = (int)k;
+                        }
+                    if (best < 0) break;
+                    const uint32_t n = VK_REF_INDEX(slots[best].ref);
+                    slots.erase(slots.begin() + best);
+                    add_children(n);
+                }
+                ++n_wide;
+                float4* q = &wnodes[(size_t)ni * 8];
+                float* f = reinterpret_cast<float*>(q);
+                for (size_t k = 0; k < 4; ++k) {
+                    const bool have = k < slots.size();
+                    for (int ax = 0; ax < 3; ++ax) {
+                        f[(2 * ax) * 4 + k] = have ? slots[k].mn[ax] : 0.f;
+                        f[(2 * ax + 1) * 4 + k] = have ? slots[k].mx[ax] : 0.f;
+                    }
+                    f[6 * 4 + k] = __uint_as_float_host(have ? slots[k].ref : VK_REF_NONE);
+                    if (have) want(slots[k].ref, level[ni] + 1);
+                }
+            }
+            }
+            // a visit pushes at most three siblings; an instance adds its exit marker
+            if (3 * levels_world + 1 + 3 * levels_sub + 2 > VKD_STACK)
+                return "BVH deeper than the traversal stack";
+        }
+        stack_need = 3 * levels_world + 1 + 3 * levels_sub + 2;
+        FlatBuilder fb;
+        fb.d = d;
+        if (!fb.build(&flat)) flat = FlatProgram{};
+        has_specdiffuse = false;
+        for (uint32_t i = 0; i < d->n_materials; ++i) has_specdiffuse |= d->materials[i].type == VK_M_SPECDIFFUSE;
+        // simple: solid textures only; Lambertian / Dielectric / DiffuseLight / Isotropic only; no moving sphere;
+        // exactly one light, an unflipped Rect
+        simple = d->n_mspheres == 0 && d->n_lights == 1 && VK_REF_TYPE(d->lights[0]) == VK_T_RECT &&
+                 !(d->rects[VK_REF_INDEX(d->lights[0])].axes & VK_RECT_FLIP);
+        for (uint32_t i = 0; i < d->n_textures && simple; ++i) simple = d->textures[i].type == VK_TEX_SOLID;
+        for (uint32_t i = 0; i < d->n_materials && simple; ++i)
+            simple = d->materials[i].type == VK_M_LAMBERTIAN || d->materials[i].type == VK_M_DIELECTRIC ||
+                     d->materials[i].type == VK_M_DIFFUSE_LIGHT || d->materials[i].type == VK_M_ISOTROPIC;
+        return nullptr;
+    }
+};
+
 template <class T> int upload(vk_ctx* c, const T* src, size_t n, const T** dst) {
     *dst = nullptr;
     if (n == 0) n = 1; // keep pointers valid
@@ -557,6 +673,31 @@ int vk_device_info(vk_ctx* c, int* sm_count, int* clock_khz, char* name, size_t 
     return VK_OK;
 }
 
+int vk_scene_check(const vk_scene_desc* d, vk_scene_info* info, char* err, size_t err_len) {
+    auto report = [&](int code, const std::string& msg) {
+        if (err && err_len) std::snprintf(err, err_len, "%s", msg.c_str());
+        return code;
+    };
+    if (!d) return report(VK_ERR_INVALID, "null scene");
+    Validator v;
+    v.d = d;
+    if (!v.run()) return report(v.code, v.err);
+    Relayout R;
+    if (const char* why = R.run(d)) return report(VK_ERR_UNSUPPORTED, why);
+    if (info) {
+        info->flat_entries = R.flat.n;
+        info->flat_segments = R.flat.n ? R.flat.n_segs : 0;
+        info->simple = R.simple ? 1u : 0u;
+        info->wide_nodes = R.n_wide;
+        info->stack_need = R.stack_need;
+        info->wide_levels_world = R.levels_world;
+        info->wide_levels_instance = R.levels_sub;
+        info->dynamic_megakernel = d->n_nodes >= 65536u ? 1u : 0u;
+    }
+    if (err && err_len) err[0] = 0;
+    return VK_OK;
+}
+
 int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     if (!c) return VK_ERR_INVALID;
     if (!d) return fail(c, VK_ERR_INVALID, "vk_scene_upload: null scene");
@@ -566,92 +707,10 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     CU(c, cudaSetDevice(c->device));
     free_scene(c);
 
-    // GPU-side re-layout of the node array: a single-object leaf (left == right) is tested twice
-    // by the reference; that only matters for a ConstantMedium (two free-flight draws), so the
-    // second visit is kept (flagged) only there and dropped for deterministic primitives.
-    std::vector<vk_node> nodes(d->nodes, d->nodes + d->n_nodes);
-    for (uint32_t i = 0; i < d->n_nodes; ++i)
-        if (nodes[i].left == nodes[i].right) {
-            vk_ref end = nodes[i].left;
-            while (VK_REF_TYPE(end) == VK_T_XFORM) end = d->xforms[VK_REF_INDEX(end)].child;
-            nodes[i].right = VK_REF_TYPE(end) == VK_T_MEDIUM ? (nodes[i].left | VKD_DUP) : VK_REF_NONE;
-        }
-    // 4-wide nodes from the reference's binary tree (see DScene): start from a node's two children and
-    // keep opening the inner child with the largest surface area until four slots are filled.
-    std::vector<float4> wnodes((size_t)d->n_nodes * 8, make_float4(0, 0, 0, 0));
-    {
-        struct Slot {
-            vk_ref ref;
-            float mn[3], mx[3];
-        };
-        std::vector<uint8_t> built(d->n_nodes, 0);
-        std::vector<uint32_t> todo, level(d->n_nodes, 0); // level: 4-wide levels above the node inside its BVH
-        uint32_t levels_world = 0, levels_sub = 0;
-        bool in_sub = false;
-        auto want = [&](vk_ref r, uint32_t lvl) {
-            if (VK_REF_TYPE(r) == VK_T_NODE && !built[VK_REF_INDEX(r)]) {
-                built[VK_REF_INDEX(r)] = 1;
-                level[VK_REF_INDEX(r)] = lvl;
-                todo.push_back(VK_REF_INDEX(r));
-                uint32_t& top = in_sub ? levels_sub : levels_world;
-                if (lvl + 1 > top) top = lvl + 1;
-            }
-        };
-        auto child_slot = [&](vk_ref r, const vk_node& parent) { // a node child brings its own box, a primitive its parent's
-            const vk_node& b = VK_REF_TYPE(r) == VK_T_NODE ? d->nodes[VK_REF_INDEX(r)] : parent;
-            Slot s{r, {b.bb_min[0], b.bb_min[1], b.bb_min[2]}, {b.bb_max[0], b.bb_max[1], b.bb_max[2]}};
-            return s;
-        };
-        auto area = [](const Slot& s) {
-            const float x = s.mx[0] - s.mn[0], y = s.mx[1] - s.mn[1], z = s.mx[2] - s.mn[2];
-            return x * y + y * z + z * x;
-        };
-        // the world's BVH first, then the instanced sub-BVHs (an instance is never nested: see Validator)
-        for (int pass = 0; pass < 2; ++pass) {
-        in_sub = pass == 1;
-        if (pass == 0) want(d->root, 0);
-        else
-            for (uint32_t i = 0; i < d->n_xforms; ++i) want(d->xforms[i].child, 0);
-        while (!todo.empty()) {
-            const uint32_t ni = todo.back();
-            todo.pop_back();
-            std::vector<Slot> slots;
-            auto add_children = [&](uint32_t n) {
-                if (nodes[n].left != VK_REF_NONE) slots.push_back(child_slot(nodes[n].left, d->nodes[n]));
-                if (nodes[n].right != VK_REF_NONE) slots.push_back(child_slot(nodes[n].right, d->nodes[n]));
-            };
-            add_children(ni);
-            while (slots.size() < 4) {
-                int best = -1;
-                for (size_t k = 0; k < slots.size(); ++k)
-                    if (VK_REF_TYPE(slots[k].ref) == VK_T_NODE) {
-                        const uint32_t n = VK_REF_INDEX(slots[k].ref);
-                        const size_t kids = (nodes[n].left != VK_REF_NONE) + (nodes[n].right != VK_REF_NONE);
-                        if (slots.size() - 1 + kids > 4) continue;
-                        if (best < 0 || area(slots[k]) > area(slots[best])) best = (int)k;
-                    }
-                if (best < 0) break;
-                const uint32_t n = VK_REF_INDEX(slots[best].ref);
-                slots.erase(slots.begin() + best);
-                add_children(n);
-            }
-            float4* q = &wnodes[(size_t)ni * 8];
-            float* f = reinterpret_cast<float*>(q);
-            for (size_t k = 0; k < 4; ++k) {
-                const bool have = k < slots.size();
-                for (int ax = 0; ax < 3; ++ax) {
-                    f[(2 * ax) * 4 + k] = have ? slots[k].mn[ax] : 0.f;
-                    f[(2 * ax + 1) * 4 + k] = have ? slots[k].mx[ax] : 0.f;
-                }
-                f[6 * 4 + k] = __uint_as_float_host(have ? slots[k].ref : VK_REF_NONE);
-                if (have) want(slots[k].ref, level[ni] + 1);
-            }
-        }
-        }
-        // a visit pushes at most three siblings; an instance adds its exit marker
-        if (3 * levels_world + 1 + 3 * levels_sub + 2 > VKD_STACK)
-            return fail(c, VK_ERR_UNSUPPORTED, "vk_scene_upload: BVH deeper than the traversal stack");
-    }
+    Relayout R;
+    if (const char* why = R.run(d)) return fail(c, VK_ERR_UNSUPPORTED, std::string("vk_scene_upload: ") + why);
+    std::vector<vk_node>& nodes = R.nodes;
+    std::vector<float4>& wnodes = R.wnodes;
     std::vector<vk_material> mats(d->materials, d->materials + d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         bool uv;
@@ -701,20 +760,9 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
     c->n_nodes = d->n_nodes;
-    c->has_specdiffuse = false;
-    for (uint32_t i = 0; i < d->n_materials; ++i) c->has_specdiffuse |= d->materials[i].type == VK_M_SPECDIFFUSE;
-    // simple: solid textures only; Lambertian / Dielectric / DiffuseLight / Isotropic only; no moving sphere;
-    // exactly one light, an unflipped Rect
-    bool simple = d->n_mspheres == 0 && d->n_lights == 1 && VK_REF_TYPE(d->lights[0]) == VK_T_RECT &&
-                  !(d->rects[VK_REF_INDEX(d->lights[0])].axes & VK_RECT_FLIP);
-    for (uint32_t i = 0; i < d->n_textures && simple; ++i) simple = d->textures[i].type == VK_TEX_SOLID;
-    for (uint32_t i = 0; i < d->n_materials && simple; ++i)
-        simple = d->materials[i].type == VK_M_LAMBERTIAN || d->materials[i].type == VK_M_DIELECTRIC ||
-                 d->materials[i].type == VK_M_DIFFUSE_LIGHT || d->materials[i].type == VK_M_ISOTROPIC;
-    c->simple_scene = simple;
-    FlatBuilder fb;
-    fb.d = d;
-    if (!fb.build(&c->flat)) c->flat = FlatProgram{};
+    c->has_specdiffuse = R.has_specdiffuse;
+    c->simple_scene = R.simple;
+    c->flat = R.flat;
     c->has_scene = true;
     return VK_OK;
 }
