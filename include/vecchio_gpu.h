@@ -288,6 +288,7 @@ int vk_scene_upload(vk_ctx* ctx, const vk_scene_desc* scene);
 typedef struct vk_scene_info {
     uint32_t flat_entries;         /* primitives in the flat traversal program, 0 = the BVH is traversed   */
     uint32_t flat_segments;        /* world frame + instance frames                                        */
+    uint32_t flat_subtrees;        /* hybrid program: homogeneous subtrees kept as BVH entries (0 = pure)  */
     uint32_t simple;               /* 1 = the trimmed ("simple scene") build of the staged kernel applies  */
     uint32_t wide_nodes;           /* 4-wide nodes made from the reference's binary nodes                  */
     uint32_t wide_levels_world;    /* 4-wide levels of the world BVH / of the deepest instanced sub-BVH     */

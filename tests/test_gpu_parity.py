@@ -594,3 +594,24 @@ def test_plane_budget_only_changes_the_order_of_the_sum(vb, ctx, monkeypatch):
     monkeypatch.delenv("VECCHIO_PLANE_BUDGET_MB")
     assert s0.rays == s1.rays and np.allclose(full, a, rtol=2e-6, atol=1e-7) and not np.array_equal(full, a)
     assert np.array_equal(a, b) and np.array_equal(a, w)
+
+
+def test_hybrid_program_renders_the_same_image(vb, ctx, monkeypatch):
+    """The hybrid flat program (VECCHIO_HYBRID=1, off by default because it measured slower) is the same
+    function as the BVH: identical hits on a ray batch and a bit-identical strict-build image."""
+    scene, cam = get_scene(vb, "final_scene")
+    ctx.upload(scene)
+    p = vb.render_params(64, 64, 16, 50, seed=5, flags=vb.VK_FLAG_STRICT_MATH, variant=vb.VK_VARIANT_MEGAKERNEL)
+    a, _, sa = ctx.render(cam, p)
+    rays = camera_rays(cam, 20000, np.random.default_rng(3))
+    ha = ctx.intersect(rays, flags=vb.VK_FLAG_STRICT_MATH)
+    monkeypatch.setenv("VECCHIO_HYBRID", "1")
+    ctx.upload(scene)
+    b, _, sb = ctx.render(cam, p)
+    hb = ctx.intersect(rays, flags=vb.VK_FLAG_STRICT_MATH)
+    monkeypatch.delenv("VECCHIO_HYBRID")
+    ctx.upload(scene)
+    assert sb.node_visits < sa.node_visits  # the flat top replaces the upper nodes
+    same = ha["prim"] == hb["prim"]
+    assert same.mean() >= 0.999 and np.array_equal(ha["t"][same], hb["t"][same])  # exact ties may resolve differently
+    assert np.array_equal(a, b) or np.isclose(a, b, rtol=1e-5, atol=1e-6).mean() > 0.999

@@ -294,9 +294,36 @@ struct FlatBuilder {
         std::vector<std::pair<FlatRect, FlatHit>> rects[6];
         std::vector<std::pair<FlatSphere, FlatHit>> sph, msph;
         std::vector<FlatHit> med;
+        std::vector<uint32_t> bvh; // roots of homogeneous subtrees kept as BVHs (hybrid program)
         uint32_t inst = 0;
     };
     std::vector<Seg> segs;
+    // hybrid mode: a subtree whose leaves are all of ONE plain primitive kind (no wrapper, no medium) and
+    // that holds more than VKF_SUBTREE_MIN of them stays a BVH; only the mixed top of the tree is unrolled
+    bool hybrid = false;
+    struct NodeInfo {
+        uint32_t leaves = 0;
+        uint8_t kind = 0; // VK_T_* shared by every leaf below, 0xFF = mixed / wrapper / medium
+        bool done = false;
+    };
+    std::vector<NodeInfo> info;
+    NodeInfo classify(vk_ref r) {
+        NodeInfo out;
+        const uint32_t t = VK_REF_TYPE(r);
+        if (t != VK_T_NODE) {
+            out.leaves = 1;
+            out.kind = (t == VK_T_SPHERE || t == VK_T_RECT || t == VK_T_BOX) ? (uint8_t)t : (uint8_t)0xFF;
+            return out;
+        }
+        NodeInfo& me = info[VK_REF_INDEX(r)];
+        if (me.done) return me;
+        const vk_node& n = d->nodes[VK_REF_INDEX(r)];
+        const NodeInfo a = classify(n.left), b = n.right == n.left ? a : classify(n.right);
+        me.leaves = a.leaves + (n.right == n.left ? 0 : b.leaves);
+        me.kind = (a.kind == b.kind) ? a.kind : (uint8_t)0xFF;
+        me.done = true;
+        return me;
+    }
 
     bool rect(Seg& g, float c0, float c1, float d0, float d1, float k, uint32_t axes, vk_ref ref, uint32_t face, bool box_side) {
         const uint32_t a0 = axes & 3u, a1 = (axes >> 2) & 3u, a2 = (axes >> 4) & 3u;
@@ -314,6 +341,13 @@ struct FlatBuilder {
         const uint32_t i = VK_REF_INDEX(ref);
         switch (VK_REF_TYPE(ref)) {
         case VK_T_NODE: {
+            if (hybrid) {
+                const NodeInfo ni = classify(ref);
+                if (ni.kind != 0xFF && ni.leaves > 8) { // homogeneous and worth a BVH: keep it as one entry
+                    segs[si].bvh.push_back(ref);
+                    return true;
+                }
+            }
             const vk_node& n = d->nodes[i];
             if (!emit(n.left, si, dup)) return false;
             if (n.right != n.left) return emit(n.right, si, dup);
@@ -371,13 +405,15 @@ struct FlatBuilder {
         default: return false;
         }
     }
-    bool build(FlatProgram* P) {
+    bool build(FlatProgram* P, bool hybrid_mode) {
         *P = FlatProgram{};
+        hybrid = hybrid_mode;
+        info.assign(hybrid ? d->n_nodes : 0, NodeInfo{});
         segs.clear();
         segs.emplace_back();
         if (!emit(d->root, 0, 0)) return false;
         if (segs.size() > VKF_MAX_SEGS) return false;
-        uint32_t n_ops = 0, n_rects = 0, n_sph = 0, n_hits = 0, n_med = 0;
+        uint32_t n_ops = 0, n_rects = 0, n_sph = 0, n_hits = 0, n_med = 0, n_bvh = 0;
         for (size_t s = 0; s < segs.size(); ++s) {
             Seg& g = segs[s];
             FlatSeg& o = P->segs[s];
@@ -416,7 +452,13 @@ struct FlatBuilder {
                 ++n_med;
             }
             o.med1 = (uint8_t)n_hits;
+            if (n_bvh + g.bvh.size() > VKF_MAX_BVH) return false;
+            o.bvh0 = (uint8_t)n_bvh;
+            for (uint32_t r : g.bvh) P->bvh[n_bvh++] = r;
+            o.bvh1 = (uint8_t)n_bvh;
+            P->seg_inst[s] = g.inst;
         }
+        P->n_bvh = n_bvh;
         for (uint32_t h = 0; h < n_hits; ++h) { // shading class of each entry's material
             const vk_ref pr = P->hits[h].prim & ~VKD_DUP;
             const uint32_t i = VK_REF_INDEX(pr);
@@ -433,8 +475,8 @@ struct FlatBuilder {
             P->hits[h].cls = t == VK_M_DIFFUSE_LIGHT ? 0u : t == VK_M_DIELECTRIC ? 1u : t == VK_M_METAL ? 2u : 3u;
         }
         P->n_segs = (uint32_t)segs.size();
-        P->n = n_hits;
-        return n_hits > 0;
+        P->n = n_hits + n_bvh;
+        return P->n > 0;
     }
 };
 
@@ -537,9 +579,18 @@ struct Relayout {
                 return "BVH deeper than the traversal stack";
         }
         stack_need = 3 * levels_world + 1 + 3 * levels_sub + 2;
+        // the whole scene as typed batches if it is small; else, for a heterogeneous scene (wrappers or media
+        // present), the mixed top of the tree as batches and its homogeneous subtrees as BVH entries
         FlatBuilder fb;
         fb.d = d;
-        if (!fb.build(&flat)) flat = FlatProgram{};
+        if (!fb.build(&flat, false)) {
+            const bool heterogeneous = d->n_media > 0 || d->n_xforms > 0;
+            // Off by default: measured on the final scene (800x800x64) the hybrid program renders in 52.5 ms
+            // against 50.0 ms for the plain 4-wide BVH -- the flat top tests all nine loose objects (two
+            // media included) for every ray where the BVH culls some, and the subtree traversals keep their
+            // divergence.  VECCHIO_HYBRID=1 enables it (parity-tested: same image bit for bit).
+            if (!(heterogeneous && std::getenv("VECCHIO_HYBRID") && fb.build(&flat, true) && flat.n_bvh > 0)) flat = FlatProgram{};
+        }
         has_specdiffuse = false;
         for (uint32_t i = 0; i < d->n_materials; ++i) has_specdiffuse |= d->materials[i].type == VK_M_SPECDIFFUSE;
         // simple: solid textures only; Lambertian / Dielectric / DiffuseLight / Isotropic only; no moving sphere;
@@ -687,6 +738,7 @@ int vk_scene_check(const vk_scene_desc* d, vk_scene_info* info, char* err, size_
     if (info) {
         info->flat_entries = R.flat.n;
         info->flat_segments = R.flat.n ? R.flat.n_segs : 0;
+        info->flat_subtrees = R.flat.n ? R.flat.n_bvh : 0;
         info->simple = R.simple ? 1u : 0u;
         info->wide_nodes = R.n_wide;
         info->stack_need = R.stack_need;
@@ -855,7 +907,9 @@ static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCam
 static uint32_t choose_variant(const vk_ctx* c, const vk_render_params* P) {
     if (P->variant != VK_VARIANT_AUTO) return P->variant;
     const bool flat = c->flat.n && !(P->flags & VK_FLAG_FORCE_BVH);
-    return flat ? (uint32_t)VK_VARIANT_STAGED : (uint32_t)VK_VARIANT_MEGAKERNEL;
+    // (a hybrid program holds subtrees whose traversal lengths vary: the lane megakernel, not the
+    // barrier-synchronised staged kernel, runs it)
+    return flat && c->flat.n_bvh == 0 ? (uint32_t)VK_VARIANT_STAGED : (uint32_t)VK_VARIANT_MEGAKERNEL;
 }
 
 // Lane megakernel for a BVH scene: static (one whole ray per lane and loop iteration) or dynamic
@@ -976,10 +1030,12 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         CU(c, cudaMemsetAsync(c->counters + 7, 0, sizeof(unsigned long long), c->stream));        // last end: maximum
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
         // a "simple" scene runs the build of the same kernel with the unreachable code compiled out
-        const bool simple = !strict && flat && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");
-        CU(c, strict   ? vkstrict::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
-              : simple ? vkfast_simple::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
-                       : vkfast::launch_staged(c->scene, flat, dc, a, b, c->counters + 2, c->sm_count, c->stream));
+        // (the staged kernel's K-ray flat trace has no subtree entries: a hybrid program means its BVH path)
+        const FlatProgram* sflat = flat && flat->n_bvh == 0 ? flat : nullptr;
+        const bool simple = !strict && sflat && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");
+        CU(c, strict   ? vkstrict::launch_staged(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
+              : simple ? vkfast_simple::launch_staged(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, c->stream)
+                       : vkfast::launch_staged(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, c->stream));
         launches = 1;
     } else if (!flat && !legacy && use_dynamic_megakernel(c)) {
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head

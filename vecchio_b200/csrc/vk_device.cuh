@@ -582,6 +582,11 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
                         const MediumXi& xi, TraceCounters& tc) {
     float best_t = tmax;
     uint32_t best_hit = 0xFFFFFFFFu;
+    TraceHit sub; // closest hit inside a subtree of a hybrid program
+    sub.t = tmax;
+    sub.prim = VK_REF_NONE;
+    sub.inst = 0;
+    sub.face = 0;
     const uint32_t n_segs = P.n_segs;
     tc.prims += P.n;
 #pragma unroll 1
@@ -630,12 +635,41 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
                 }
             }
         }
+        // homogeneous subtrees of a hybrid program: while-while over the 4-wide nodes in this frame
+#pragma unroll 1
+        for (uint32_t i = g.bvh0; i < g.bvh1; ++i) {
+            Trav T;
+            T.sp = 0;
+            T.co = co;
+            T.cd = cd;
+            T.cinv = ci;
+            T.cur_inst = P.seg_inst[s];
+            T.best.t = best_t;
+            T.best.prim = VK_REF_NONE;
+            T.best.inst = 0;
+            T.best.face = 0;
+            T.ref = P.bvh[i];
+            T.enter = true;
+#pragma unroll 1
+            for (;;) {
+#pragma unroll 1
+                while (trav_at_node(T)) trav_node_step(T, sc, tmin, tc);
+                if (T.ref == VKD_DONE) break;
+                trav_prim_step<false>(T, sc, o, d, time, tmin, xi, tc); // leaves only: no wrapper, no medium below
+            }
+            if (T.best.prim != VK_REF_NONE) {
+                best_t = T.best.t;
+                sub = T.best;
+                best_hit = 0xFFFFFFFEu;
+            }
+        }
     }
     TraceHit best;
     best.t = best_t;
     best.prim = VK_REF_NONE;
     best.inst = 0;
     best.face = 0;
+    if (best_hit == 0xFFFFFFFEu) return sub; // the closest hit came from a subtree
     if (best_hit != 0xFFFFFFFFu) {
         best.prim = P.hits[best_hit].prim & ~VKD_DUP;
         best.inst = P.hits[best_hit].inst;

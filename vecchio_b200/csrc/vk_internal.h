@@ -74,6 +74,7 @@ struct DScene {
 #define VKF_MAX_RECTS 96
 #define VKF_MAX_SPHERES 16
 #define VKF_MAX_MEDIA 4
+#define VKF_MAX_BVH 32
 enum { VKF_OP_TRANSLATE = 0, VKF_OP_ROTX = 1, VKF_OP_ROTY = 2, VKF_OP_ROTZ = 3 };
 struct FlatOp { // one wrapper level, outermost first
     uint32_t kind;
@@ -104,7 +105,8 @@ struct FlatSeg {
     uint8_t sph0, sph1;         // static spheres
     uint8_t msph0, msph1;       // moving spheres
     uint8_t med0, med1;         // media: hits[] indices [med0, med1) (their prim is the medium ref)
-    uint8_t _pad[4];
+    uint8_t bvh0, bvh1;         // sub-BVH roots [bvh0, bvh1) of FlatProgram::bvh, traversed in this segment's frame
+    uint8_t _pad[2];
 };
 struct FlatProgram {
     uint32_t n;      // number of primitive entries; 0 = no program: use the BVH
@@ -115,6 +117,16 @@ struct FlatProgram {
     FlatRect rects[VKF_MAX_RECTS];
     FlatSphere spheres[VKF_MAX_SPHERES];
     FlatHit hits[VKF_MAX_RECTS + VKF_MAX_SPHERES + VKF_MAX_MEDIA];
+    // Hybrid programs.  A heterogeneous scene (final scene: spheres, a moving sphere, media, a box field,
+    // an instanced sphere cluster under one 13-node BVH) makes every lane of a warp test a different
+    // KIND of primitive at the same time when it is traversed as a BVH (measured: 7.7 of 32 lanes
+    // active, in the megakernel and in the dynamic-fetch wavefront extend alike).  The flat program
+    // therefore unrolls only the heterogeneous top of the tree into typed batches and keeps each large
+    // homogeneous subtree (all boxes, all spheres) as ONE entry: its root node, traversed through
+    // the 4-wide nodes in the segment's frame, where every leaf test is the same code.
+    uint32_t n_bvh;
+    uint32_t bvh[VKF_MAX_BVH];           // node refs of the sub-BVH roots
+    uint32_t seg_inst[VKF_MAX_SEGS];     // instance (outermost wrapper) of each segment, 0 for the world frame
 };
 
 struct DCamera {
