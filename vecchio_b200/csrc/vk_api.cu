@@ -337,7 +337,9 @@ struct FlatBuilder {
         g.rects[(a2 == 2 ? 0 : (a2 == 1 ? 1 : 2)) + (box_side ? 3 : 0)].push_back({e, h});
         return true;
     }
+    size_t n_emitted = 0; // entries so far: a scene that cannot fit is abandoned early, not walked to the end
     bool emit(vk_ref ref, size_t si, uint32_t dup) {
+        if (++n_emitted > 4 * (VKF_MAX_RECTS + VKF_MAX_SPHERES + VKF_MAX_MEDIA + VKF_MAX_BVH + VKF_MAX_OPS)) return false;
         const uint32_t i = VK_REF_INDEX(ref);
         switch (VK_REF_TYPE(ref)) {
         case VK_T_NODE: {
@@ -408,6 +410,7 @@ struct FlatBuilder {
     bool build(FlatProgram* P, bool hybrid_mode) {
         *P = FlatProgram{};
         hybrid = hybrid_mode;
+        n_emitted = 0;
         info.assign(hybrid ? d->n_nodes : 0, NodeInfo{});
         segs.clear();
         segs.emplace_back();
@@ -540,31 +543,33 @@ struct Relayout {
             while (!todo.empty()) {
                 const uint32_t ni = todo.back();
                 todo.pop_back();
-                std::vector<Slot> slots;
+                Slot slots[6]; // never more than four after a round; two are added before one is removed
+                size_t n_slots = 0;
                 auto add_children = [&](uint32_t n) {
-                    if (nodes[n].left != VK_REF_NONE) slots.push_back(child_slot(nodes[n].left, d->nodes[n]));
-                    if (nodes[n].right != VK_REF_NONE) slots.push_back(child_slot(nodes[n].right, d->nodes[n]));
+                    if (nodes[n].left != VK_REF_NONE) slots[n_slots++] = child_slot(nodes[n].left, d->nodes[n]);
+                    if (nodes[n].right != VK_REF_NONE) slots[n_slots++] = child_slot(nodes[n].right, d->nodes[n]);
                 };
                 add_children(ni);
-                while (slots.size() < 4) {
+                while (n_slots < 4) {
                     int best = -1;
-                    for (size_t k = 0; k < slots.size(); ++k)
+                    for (size_t k = 0; k < n_slots; ++k)
                         if (VK_REF_TYPE(slots[k].ref) == VK_T_NODE) {
                             const uint32_t n = VK_REF_INDEX(slots[k].ref);
                             const size_t kids = (nodes[n].left != VK_REF_NONE) + (nodes[n].right != VK_REF_NONE);
-                            if (slots.size() - 1 + kids > 4) continue;
+                            if (n_slots - 1 + kids > 4) continue;
                             if (best < 0 || area(slots[k]) > area(slots[best])) best = (int)k;
                         }
                     if (best < 0) break;
                     const uint32_t n = VK_REF_INDEX(slots[best].ref);
-                    slots.erase(slots.begin() + best);
+                    for (size_t k = (size_t)best; k + 1 < n_slots; ++k) slots[k] = slots[k + 1];
+                    --n_slots;
                     add_children(n);
                 }
                 ++n_wide;
                 float4* q = &wnodes[(size_t)ni * 8];
                 float* f = reinterpret_cast<float*>(q);
                 for (size_t k = 0; k < 4; ++k) {
-                    const bool have = k < slots.size();
+                    const bool have = k < n_slots;
                     for (int ax = 0; ax < 3; ++ax) {
                         f[(2 * ax) * 4 + k] = have ? slots[k].mn[ax] : 0.f;
                         f[(2 * ax + 1) * 4 + k] = have ? slots[k].mx[ax] : 0.f;
