@@ -25,7 +25,7 @@ $(LIBDIR)/libvecchio_host.so: $(HOSTSRC)/vecchio.cpp $(HOSTSRC)/scene.cpp $(HOST
 oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/vecchio_gpu.h
 	$(CXX) $(CXXFLAGS) -fopenmp -shared -o $@ oracle/oracle.cpp
 
-KDEPS := $(CSRC)/vk_device.cuh $(CSRC)/vk_internal.h include/vecchio_gpu.h Makefile
+KDEPS := $(CSRC)/vk_device.cuh $(CSRC)/vk_internal.h $(CSRC)/vk_relayout.h include/vecchio_gpu.h Makefile
 
 # the device code is compiled twice: contracted FMA ("fast") and -fmad=false ("strict", the
 # reference's op sequence, used for hit parity)
@@ -47,8 +47,10 @@ $(CSRC)/vk_staged_strict.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_staged_strict.log || (cat $(CSRC)/ptxas_staged_strict.log; false)
 $(CSRC)/vk_api.o: $(CSRC)/vk_api.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(CSRC)/vk_relayout.o: $(CSRC)/vk_relayout.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o
+$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 
