@@ -121,6 +121,17 @@ VKD void staged_take_units(const StagedCtx& C, bool want, uint32_t slot, uint32_
     staged_begin_sample(C, slot, pixel, C.a.spp_begin + b * C.a.unit_spp);
 }
 
+// The sort: one __match_any_sync groups the lanes of the warp by shading class; the first lane of each
+// group reserves the group's entries in the class list with one shared-memory atomic (full warp, converged).
+VKD void staged_sort_append(StagedShared& S, uint32_t* cnt, uint32_t cls, uint32_t slot, uint32_t lane, uint32_t lanes_below) {
+    const uint32_t m = __match_any_sync(0xFFFFFFFFu, cls); // lanes of my class (idle lanes form their own group)
+    const uint32_t leader = __ffs(m) - 1u;
+    uint32_t base = 0;
+    if (lane == leader && cls != VKS_C_IDLE) base = atomicAdd(&cnt[cls], (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (cls != VKS_C_IDLE) S.list[cls][base + __popc(m & lanes_below)] = (uint16_t)slot;
+}
+
 template <bool FLAT, bool MEDIA>
 VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
                      unsigned long long* unit_head) {
@@ -201,16 +212,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                         S.hp[slot].y = prim;
                         S.hp[slot].z = hi;
                     }
-#pragma unroll
-                    for (uint32_t c = 0; c < VKS_CLASSES; ++c) {
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cls == c);
-                        if (m) {
-                            uint32_t base = 0;
-                            if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(m));
-                            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                            if (cls == c) S.list[c][base + __popc(m & lanes_below)] = (uint16_t)slot;
-                        }
-                    }
+                    staged_sort_append(S, cnt, cls, slot, lane, lanes_below);
                 }
             }
         } else {
@@ -238,17 +240,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                     S.hp[slot].z = (h.inst ? (0x80000000u | VKD_INDEX(h.inst)) : 0u) | (h.face << 28);
                     cls = h.prim == VK_REF_NONE ? (uint32_t)VKS_C_TERMINATE : staged_class_of(sc, h.prim);
                 }
-                // sort: ballot per class, one shared atomic per warp and class, straight into the class's list
-#pragma unroll
-                for (uint32_t c = 0; c < VKS_CLASSES; ++c) {
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, cls == c);
-                    if (m) {
-                        uint32_t base = 0;
-                        if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(m));
-                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                        if (cls == c) S.list[c][base + __popc(m & lanes_below)] = (uint16_t)slot;
-                    }
-                }
+                staged_sort_append(S, cnt, cls, slot, lane, lanes_below);
             }
         }
         if (tid < VKS_CLASSES) S.cnt[(iter & 1u) ^ 1u][tid] = 0u; // next iteration's counters (last read before the previous barrier)
