@@ -49,7 +49,7 @@ struct StagedShared {
     uint32_t n_late;
     uint32_t next_unit;                // CTA-local unit counter (local index n)
     uint32_t fetched;                  // local indices [0, fetched) are backed by a chunk
-    unsigned long long chunk_base[VKS_RING]; // global unit of local index n: chunk_base[(n / VKS_CHUNK) % VKS_RING] + n % VKS_CHUNK
+    uint32_t chunk_b[VKS_RING], chunk_y[VKS_RING], chunk_x[VKS_RING]; // first unit of each chunk of the ring: sample block, row, column
 };
 
 VKD uint32_t staged_class_of(const DScene& sc, uint32_t prim) {
@@ -80,27 +80,38 @@ struct StagedCtx {
     unsigned long long n_units;
     unsigned long long* unit_head;
 };
-// one thread, every ~20 iterations: out of line, pointers by value
-static __device__ __noinline__ void staged_refill(StagedShared* S, unsigned long long* unit_head) {
+// one thread, every ~20 iterations: out of line, arguments by value.  The chunk's first unit is split into
+// (sample block, row, column) here, once per chunk, so that the per-path code needs no division.
+static __device__ __noinline__ void staged_refill(StagedShared* S, unsigned long long* unit_head, uint32_t width, uint32_t n_pixels) {
     while (S->fetched < S->next_unit + VKS_N) {
-        S->chunk_base[(S->fetched / VKS_CHUNK) % VKS_RING] = atomicAdd(unit_head, (unsigned long long)VKS_CHUNK);
+        const unsigned long long u = atomicAdd(unit_head, (unsigned long long)VKS_CHUNK);
+        const uint32_t e = (S->fetched / VKS_CHUNK) % VKS_RING;
+        const unsigned long long b = u / n_pixels;
+        const uint32_t p = (uint32_t)(u - b * n_pixels);
+        S->chunk_b[e] = b > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)b;
+        S->chunk_y[e] = p / width;
+        S->chunk_x[e] = p - (p / width) * width;
         S->fetched += VKS_CHUNK;
     }
 }
-// Start the sample `s` of `pixel` in `slot`: Camera::get_ray, depth 1 (src/main.rs:187-190).
-VKD void staged_begin_sample(const StagedCtx& C, uint32_t slot, uint32_t pixel, uint32_t s) {
+// Start the sample `s` of pixel (x, y) in `slot`: Camera::get_ray, depth 1 (src/main.rs:187-190).
+VKD void staged_begin_sample_xy(const StagedCtx& C, uint32_t slot, uint32_t x, uint32_t y, uint32_t s) {
+    const uint32_t pixel = y * C.a.width + x; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
     PathRng rng;
     rng.pixel = pixel;
     rng.sample = s;
     rng.key = make_uint2(C.a.seed_lo, C.a.seed_hi);
     float3 o, d;
     float time;
-    camera_get_ray(C.cam, rng, pixel % C.a.width, pixel / C.a.width, C.a.width, C.a.height, o, d, time);
+    camera_get_ray(C.cam, rng, x, y, C.a.width, C.a.height, o, d, time);
     StagedShared& S = C.S;
     S.ro[slot] = make_float4(o.x, o.y, o.z, time);
     S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(1u)); // ray_color(ray, .., 1)
     S.bt[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(s));
     S.hp[slot].w = pixel;
+}
+VKD void staged_begin_sample(const StagedCtx& C, uint32_t slot, uint32_t pixel, uint32_t s) { // (multi-sample units only)
+    staged_begin_sample_xy(C, slot, pixel % C.a.width, pixel / C.a.width, s);
 }
 // Warp-synchronous: the lanes with want == true take the CTA's next units (one shared atomic per
 // warp) and start their first sample; a lane whose unit is past the end leaves its slot idle.
@@ -112,13 +123,22 @@ VKD void staged_take_units(const StagedCtx& C, bool want, uint32_t slot, uint32_
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (!want) return;
     const uint32_t n = base + __popc(m & ((1u << lane) - 1u));
-    const unsigned long long u = C.S.chunk_base[(n / VKS_CHUNK) % VKS_RING] + (n % VKS_CHUNK);
-    if (u >= C.n_units) {
+    // unit = chunk start + n % CHUNK, walked in (sample block, row, column) without dividing
+    const uint32_t e = (n / VKS_CHUNK) % VKS_RING;
+    uint32_t b = C.S.chunk_b[e], y = C.S.chunk_y[e], x = C.S.chunk_x[e] + (n % VKS_CHUNK);
+    while (x >= C.a.width) {
+        x -= C.a.width;
+        ++y;
+    }
+    while (y >= C.a.height) {
+        y -= C.a.height;
+        ++b;
+    }
+    if (b >= C.a.n_planes) { // past the last unit: the queue is empty
         C.S.rd[slot].w = __uint_as_float(0u);
         return;
     }
-    const uint32_t b = (uint32_t)(u / C.n_pixels), pixel = (uint32_t)(u - (unsigned long long)b * C.n_pixels);
-    staged_begin_sample(C, slot, pixel, C.a.spp_begin + b * C.a.unit_spp);
+    staged_begin_sample_xy(C, slot, x, y, C.a.spp_begin + b * C.a.unit_spp);
 }
 
 // The sort: one __match_any_sync groups the lanes of the warp by shading class; the first lane of each
@@ -148,7 +168,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
         S.n_late = 0u;
         S.next_unit = 0u;
         S.fetched = 0u;
-        staged_refill(&S, unit_head);
+        staged_refill(&S, unit_head, a.width, C.n_pixels);
 #ifdef VKS_DEBUG_TIMES
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -163,7 +183,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
 #pragma unroll 1
     for (uint32_t iter = 0;; ++iter) {
         uint32_t* cnt = S.cnt[iter & 1u];
-        if (tid == 0) staged_refill(&S, unit_head); // consumed by the shade stage, after the barrier
+        if (tid == 0) staged_refill(&S, unit_head, a.width, C.n_pixels); // consumed by the shade stage, after the barrier
         // ---- extend + classify (slot == thread + round * T: conflict-free shared-memory access) -------
         if (FLAT) {
 #pragma unroll 1
@@ -294,7 +314,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                     S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
                     S.bt[slot] = make_float4(beta.x, beta.y, beta.z, bt.w);
                 } else { // sample finished: NaN/Inf filter of src/main.rs:191-194, added in order into the unit's plane
-                    const uint32_t rel = sample - a.spp_begin, b = rel / a.unit_spp;
+                    const uint32_t rel = sample - a.spp_begin, b = a.unit_spp == 1u ? rel : rel / a.unit_spp;
                     const bool first = rel == b * a.unit_spp;
                     const uint32_t s_end = min(a.spp_begin + (b + 1u) * a.unit_spp, spp_end);
                     const bool keep = valid && finite3(L);
