@@ -47,6 +47,7 @@ struct StagedShared {
     uint32_t cnt[2][VKS_CLASSES];      // class counts, double buffered by iteration parity
     uint16_t late[VKS_N];              // slots whose regeneration was queued (| 0x8000: needs a new unit)
     uint32_t n_late;
+    uint32_t no_units;                 // set once a slot drew a unit past the end: the global queue is empty
     uint32_t next_unit;                // CTA-local unit counter (local index n)
     uint32_t fetched;                  // local indices [0, fetched) are backed by a chunk
     uint32_t chunk_b[VKS_RING], chunk_y[VKS_RING], chunk_x[VKS_RING]; // first unit of each chunk of the ring: sample block, row, column
@@ -136,6 +137,7 @@ VKD void staged_take_units(const StagedCtx& C, bool want, uint32_t slot, uint32_
     }
     if (b >= C.a.n_planes) { // past the last unit: the queue is empty
         C.S.rd[slot].w = __uint_as_float(0u);
+        C.S.no_units = 1u;
         return;
     }
     staged_begin_sample_xy(C, slot, x, y, C.a.spp_begin + b * C.a.unit_spp);
@@ -166,6 +168,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
 
     if (tid == 0) {
         S.n_late = 0u;
+        S.no_units = 0u;
         S.next_unit = 0u;
         S.fetched = 0u;
         staged_refill(&S, unit_head, a.width, C.n_pixels);
@@ -270,14 +273,9 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
         if (n_live == 0u) break; // pool drained and no unit left (uniform: every thread reads the same counters)
         ++dbg_iters;
         if (n_live < VKS_N / 8) ++dbg_sparse;
-        // ---- shade: a warp's 32 consecutive entries are one class (except at the 3 class borders) ------
-#pragma unroll 1
-        for (uint32_t j0 = 0; j0 < n_live; j0 += VKS_T) {
-            const uint32_t j = j0 + tid;
-            bool new_unit = false, ended = false;
-            uint32_t slot = 0, next_sample = 0;
-            if (j < n_live) {
-                slot = j < o1 ? S.list[0][j] : (j < o2 ? S.list[1][j - o1] : (j < o3 ? S.list[2][j - o2] : S.list[3][j - o3]));
+        // One slot of the shade stage: resolve + scatter (src/main.rs:131-149); a finished sample goes through the
+        // NaN/Inf filter into its plane (:191-194).  Reports whether the sample ended and what the slot needs next.
+        auto shade_slot = [&](uint32_t slot, bool& ended, bool& new_unit, uint32_t& next_sample) {
                 const float4 ro = S.ro[slot], rd = S.rd[slot], bt = S.bt[slot];
                 const uint4 hp = S.hp[slot];
                 float3 o = f3(ro), d = f3(rd), beta = f3(bt), L = f3(0.0f, 0.0f, 0.0f);
@@ -342,6 +340,54 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                     new_unit = next_sample >= s_end;
                     S.rd[slot].w = __uint_as_float(0u); // idle until regenerated
                 }
+        };
+        auto slot_of = [&](uint32_t j) -> uint32_t {
+            return j < o1 ? S.list[0][j] : (j < o2 ? S.list[1][j - o1] : (j < o3 ? S.list[2][j - o2] : S.list[3][j - o3]));
+        };
+        // ---- drain: the queue is empty and one warp's worth of paths is left (the long ones: up to max_depth
+        // segments each).  A staged iteration costs ~5 us however few slots are live, so warp 0 finishes them
+        // alone, one lane per path, trace and shade back to back without barriers; the other warps leave.
+        if (S.no_units != 0u && n_live <= 32u) {
+            if (tid < 32u && lane < n_live) {
+                const uint32_t slot = slot_of(lane);
+#pragma unroll 1
+                for (;;) {
+                    bool ended = false, new_unit = false;
+                    uint32_t next_sample = 0;
+                    shade_slot(slot, ended, new_unit, next_sample);
+                    if (ended) {
+                        if (new_unit) break; // no unit left: the slot is done
+                        staged_begin_sample(C, slot, S.hp[slot].w, next_sample);
+                    }
+                    const float4 ro = S.ro[slot], rd = S.rd[slot];
+                    MediumXi xi;
+                    xi.table = nullptr;
+                    xi.depth = __float_as_uint(rd.w);
+                    xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                    xi.rng.pixel = S.hp[slot].w;
+                    xi.rng.sample = __float_as_uint(S.bt[slot].w);
+                    TraceCounters tc = {0u, 0u};
+                    const TraceHit h = FLAT ? trace_flat<MEDIA>(sc, *flat, f3(ro), f3(rd), ro.w, 0.001f, CUDART_INF_F, xi, tc)
+                                            : trace<MEDIA>(sc, f3(ro), f3(rd), ro.w, 0.001f, CUDART_INF_F, xi, tc); // src/main.rs:130
+                    ++n_rays;
+                    n_nodes += tc.nodes;
+                    n_prims += tc.prims;
+                    S.hp[slot].x = __float_as_uint(h.t);
+                    S.hp[slot].y = h.prim;
+                    S.hp[slot].z = (h.inst ? (0x80000000u | VKD_INDEX(h.inst)) : 0u) | (h.face << 28);
+                }
+            }
+            break;
+        }
+        // ---- shade: a warp's 32 consecutive entries are one class (except at the 3 class borders) ------
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < n_live; j0 += VKS_T) {
+            const uint32_t j = j0 + tid;
+            bool new_unit = false, ended = false;
+            uint32_t slot = 0, next_sample = 0;
+            if (j < n_live) {
+                slot = slot_of(j);
+                shade_slot(slot, ended, new_unit, next_sample);
             }
             // Regenerate in place (src/main.rs:187-190) when at least half the warp ended -- the emitter /
             // miss class does, every lane -- otherwise queue the slot: in the other classes only a few
