@@ -1,6 +1,7 @@
-# Build of the three shared libraries.  `make` = all; `make gpu` needs nvcc only (no GPU).
+# Build of the three shared libraries and the frame-loop program.  `make` = all; `make gpu` needs nvcc only (no GPU).
 #   vecchio_b200/lib/libvecchio_gpu.so   CUDA kernels + C ABI (include/vecchio_gpu.h)   -- product
 #   vecchio_b200/lib/libvecchio_host.so  host front end (reference scene API + lower())  -- product
+#   vecchio_b200/lib/vecchio_gpu_render  the reference's main() over the C ABI (frame loop, P3 output) -- product
 #   oracle/liboracle.so                  CPU restatement of the reference                -- tests only
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       := /usr/bin/g++
@@ -12,11 +13,12 @@ LIBDIR    := vecchio_b200/lib
 CSRC      := vecchio_b200/csrc
 HOSTSRC   := vecchio_b200/host
 
-all: host oracle gpu
+all: host oracle gpu render
 
 host: $(LIBDIR)/libvecchio_host.so
 oracle: oracle/liboracle.so
 gpu: $(LIBDIR)/libvecchio_gpu.so
+render: $(LIBDIR)/vecchio_gpu_render
 
 $(LIBDIR)/libvecchio_host.so: $(HOSTSRC)/vecchio.cpp $(HOSTSRC)/scene.cpp $(HOSTSRC)/capi.cpp $(HOSTSRC)/vecchio.hpp include/vecchio_gpu.h include/vecchio_host.h
 	@mkdir -p $(LIBDIR)
@@ -54,7 +56,11 @@ $(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_k
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 
-clean:
-	rm -f $(LIBDIR)/*.so oracle/*.so $(CSRC)/*.o $(CSRC)/*.log
+# the program finds its two libraries next to itself
+$(LIBDIR)/vecchio_gpu_render: $(HOSTSRC)/main.cpp include/vecchio_gpu.h include/vecchio_host.h $(LIBDIR)/libvecchio_host.so $(LIBDIR)/libvecchio_gpu.so
+	$(CXX) $(CXXFLAGS) -fPIE -o $@ $(HOSTSRC)/main.cpp -L$(LIBDIR) -lvecchio_host -lvecchio_gpu -pthread -Wl,-rpath,'$$ORIGIN'
 
-.PHONY: all host oracle gpu clean
+clean:
+	rm -f $(LIBDIR)/*.so $(LIBDIR)/vecchio_gpu_render oracle/*.so $(CSRC)/*.o $(CSRC)/*.log
+
+.PHONY: all host oracle gpu render clean

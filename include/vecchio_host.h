@@ -35,6 +35,19 @@ void vkh_camera_new(const float lookfrom[3], const float lookat[3], const float 
 /* ImageTexture::new (src/material.rs:269-279): decoded RGB8 bytes; returns byte count or -1.
  * buf may be NULL to query the size. */
 long vkh_decode_png(const char* path, uint8_t* buf, size_t buf_len, uint32_t* width, uint32_t* height);
+/* Output conversion of src/main.rs:201-214 on the host: frame = W*H*3 linear floats, pixel i = y*W+x, row 0 =
+ * bottom (what vk_render writes); out_rgb8 = the W*H*3 numbers of the reference's P3 file in file order
+ * (row height-1 first), every channel through Vec3::to_color (src/vec3.rs:54-61: (256*clamp(sqrt(c),0,0.999))
+ * as u32, NaN -> 0).  vk_render_rgb8 does the same on the device; this one serves frames that were summed on
+ * the host (several GPUs in one process, merged checkpoints). */
+void vkh_frame_to_rgb8(const float* frame, uint32_t width, uint32_t height, uint8_t* out_rgb8);
+/* The file writer of src/main.rs:201-213: "P3", "W H", "255", then one "r g b" line per pixel in the order
+ * of rgb8 (file order, as vk_render_rgb8 / vkh_frame_to_rgb8 produce it).  0 = OK, VK_ERR_INVALID on an I/O
+ * failure (message in vkh_last_error) where the reference unwraps File::create. */
+int vkh_write_ppm(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);
+/* "output_{:04}.ppm" (src/main.rs:201) under dir (NULL or "" = current directory) into buf; returns the length
+ * or -1 if buf is too small. */
+int vkh_frame_filename(const char* dir, uint32_t file_idx, char* buf, size_t buf_len);
 const char* vkh_last_error(void);
 
 #ifdef __cplusplus

@@ -14,6 +14,7 @@ def pytest_configure(config):
     # only, no GPU needed) so a fresh checkout can run the suite.
     need = [os.path.join(ROOT, "vecchio_b200", "lib", "libvecchio_host.so"),
             os.path.join(ROOT, "vecchio_b200", "lib", "libvecchio_gpu.so"),
+            os.path.join(ROOT, "vecchio_b200", "lib", "vecchio_gpu_render"),
             os.path.join(ROOT, "oracle", "liboracle.so")]
     if not all(os.path.exists(p) for p in need):
         subprocess.run(["make", "-j4", "all"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)

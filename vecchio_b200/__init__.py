@@ -53,6 +53,12 @@ def host_lib():
         L.vkh_camera_new.restype = None
         L.vkh_decode_png.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.vkh_decode_png.restype = C.c_long
+        L.vkh_frame_to_rgb8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.vkh_frame_to_rgb8.restype = None
+        L.vkh_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.vkh_write_ppm.restype = C.c_int
+        L.vkh_frame_filename.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_size_t]
+        L.vkh_frame_filename.restype = C.c_int
         L.vkh_last_error.restype = C.c_char_p
         _host = L
     return _host
@@ -98,7 +104,8 @@ GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_check", "vk
                "vk_finalize_device", "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks",
                "vk_device_info"]
 HOST_SYMBOLS = ["vkh_scene_build", "vkh_scene_free", "vkh_scene_desc", "vkh_scene_aspect_ratio",
-                "vkh_scene_next_camera", "vkh_camera_new", "vkh_decode_png", "vkh_last_error"]
+                "vkh_scene_next_camera", "vkh_camera_new", "vkh_decode_png", "vkh_frame_to_rgb8", "vkh_write_ppm",
+                "vkh_frame_filename", "vkh_last_error"]
 
 
 class Scene:
@@ -183,6 +190,34 @@ def decode_png(path):
     buf = np.empty(n, dtype=np.uint8)
     L.vkh_decode_png(path.encode(), buf.ctypes.data, n, C.byref(w), C.byref(h))
     return buf.reshape(h.value, w.value, 3)
+
+
+def frame_to_rgb8(frame):
+    """``vkh_frame_to_rgb8``: an (H, W, 3) linear frame with row 0 = bottom (what ``Context.render`` returns) ->
+    the (H, W, 3) uint8 numbers of the reference's P3 file, top row first (src/main.rs:209-212)."""
+    frame = np.ascontiguousarray(frame, dtype=np.float32)
+    h, w, _ = frame.shape
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    host_lib().vkh_frame_to_rgb8(frame.ctypes.data, w, h, out.ctypes.data)
+    return out
+
+
+def frame_filename(file_idx, out_dir=""):
+    """``format!("output_{:04}.ppm", file_idx)`` (src/main.rs:201), under out_dir."""
+    buf = C.create_string_buffer(4096)
+    if host_lib().vkh_frame_filename(out_dir.encode(), file_idx, buf, 4096) < 0:
+        raise ValueError("frame file name too long")
+    return buf.value.decode()
+
+
+def write_ppm(path, rgb8):
+    """``vkh_write_ppm``: the P3 writer of src/main.rs:201-213; rgb8 = (H, W, 3) uint8 in file order (what
+    ``Context.render_rgb8`` and ``frame_to_rgb8`` return)."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, _ = rgb8.shape
+    L = host_lib()
+    if L.vkh_write_ppm(path.encode(), rgb8.ctypes.data, w, h) != 0:
+        raise VecchioError(-1, L.vkh_last_error().decode())
 
 
 def render_params(width, height, spp, max_depth=100, seed=1, spp_begin=0, spp_count=0, variant=0, flags=0,

@@ -1,6 +1,10 @@
 // capi.cpp -- extern "C" view of the host front end (include/vecchio_host.h).
 #include "../../include/vecchio_host.h"
 #include "vecchio.hpp"
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
 
 using namespace vecchio;
 
@@ -88,6 +92,73 @@ long vkh_decode_png(const char* path, uint8_t* buf, size_t buf_len, uint32_t* wi
         g_err = e.what();
         return -1;
     }
+}
+
+// Vec3::to_color (src/vec3.rs:54-61) for one channel.  Vec3::clamp (src/vec3.rs:44-52) is two `<`/`>` tests,
+// so NaN falls through it and `NaN as u32` is 0.
+static inline uint8_t to_color1(float c) {
+    float x = std::sqrt(c);
+    if (x < 0.0f) x = 0.0f;
+    else if (x > 0.999f) x = 0.999f;
+    float v = 256.0f * x;
+    return v == v ? (uint8_t)(uint32_t)v : (uint8_t)0;
+}
+
+void vkh_frame_to_rgb8(const float* frame, uint32_t width, uint32_t height, uint8_t* out_rgb8) {
+    if (!frame || !out_rgb8) return;
+    for (uint32_t row = 0; row < height; row++) { // file row `row` = image row height-1-row (main.rs:209)
+        const float* src = frame + (size_t)(height - 1 - row) * width * 3;
+        uint8_t* dst = out_rgb8 + (size_t)row * width * 3;
+        for (size_t i = 0; i < (size_t)width * 3; i++) dst[i] = to_color1(src[i]);
+    }
+}
+
+int vkh_write_ppm(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height) {
+    if (!path || !rgb8) {
+        g_err = "vkh_write_ppm: null argument";
+        return VK_ERR_INVALID;
+    }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) {
+        g_err = std::string("vkh_write_ppm: cannot create ") + path + ": " + std::strerror(errno);
+        return VK_ERR_INVALID;
+    }
+    // the decimal text of 0..255 once; a pixel line is at most "255 255 255\n" = 12 bytes
+    char digits[256][4];
+    uint8_t ndig[256];
+    for (int v = 0; v < 256; v++) ndig[v] = (uint8_t)std::snprintf(digits[v], 4, "%d", v);
+    std::string buf;
+    buf.reserve((size_t)width * 12 + 32);
+    buf = "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
+    bool ok = true;
+    for (uint32_t row = 0; row < height && ok; row++) {
+        const uint8_t* px = rgb8 + (size_t)row * width * 3;
+        for (uint32_t x = 0; x < width; x++, px += 3) {
+            buf.append(digits[px[0]], ndig[px[0]]);
+            buf.push_back(' ');
+            buf.append(digits[px[1]], ndig[px[1]]);
+            buf.push_back(' ');
+            buf.append(digits[px[2]], ndig[px[2]]);
+            buf.push_back('\n');
+        }
+        ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+        buf.clear();
+    }
+    if (height == 0) ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    if (std::fclose(f) != 0) ok = false;
+    if (!ok) {
+        g_err = std::string("vkh_write_ppm: write failed on ") + path;
+        return VK_ERR_INVALID;
+    }
+    return VK_OK;
+}
+
+int vkh_frame_filename(const char* dir, uint32_t file_idx, char* buf, size_t buf_len) {
+    if (!buf) return -1;
+    const bool has_dir = dir && dir[0];
+    const bool slash = has_dir && dir[std::strlen(dir) - 1] == '/';
+    int n = std::snprintf(buf, buf_len, "%s%soutput_%04u.ppm", has_dir ? dir : "", has_dir && !slash ? "/" : "", file_idx);
+    return n < 0 || (size_t)n >= buf_len ? -1 : n;
 }
 
 const char* vkh_last_error(void) { return g_err.c_str(); }
