@@ -21,7 +21,7 @@ def test_gpu_library_exports_every_declared_symbol(vb):
 
 def test_host_library_exports_every_declared_symbol(vb):
     hdr = open(os.path.join(ROOT, "include", "vecchio_host.h")).read()
-    declared = set(re.findall(r"\b(vkh_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(vkh_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(vb.HOST_SYMBOLS)
     lib = vb.host_lib()
     for name in declared:
