@@ -1,8 +1,13 @@
-"""Regenerate tests/golden/cornell_sample_regions.json from the reference's published render.
+"""Regenerate tests/golden/cornell_sample_regions.json and tests/golden/thenextweek_sample_regions.json from the
+reference's published renders.
 
 Reads /root/reference/sample/therestofyourlife.png (900x900, 8-bit, the book-3 Cornell box at
 src/main.rs defaults: width 900, 1000 spp, depth 100) -- the ONLY result-pinning artefact the
 reference ships (it has no tests).  Only region statistics are committed, not the image.
+sample/thenextweek.png (900x900) is the book-2 final scene (src/scene.rs:732-874) rendered by the reference; its
+scene is unseeded, so only regions on the seed-independent objects are kept (no ground boxes; not the blue
+subsurface sphere either, whose published pixels hold clamped fireflies), as LINEAR means
+((v + 0.5) / 256)^2 -- the inverse of Vec3::to_color at the centre of the 8-bit bin -- of unsaturated pixels.
 Run in the build container (the GPU box has no /root/reference):  python tests/golden/make_golden_regions.py
 """
 import hashlib
@@ -50,5 +55,41 @@ def main():
     print(json.dumps(out, indent=1))
 
 
+SRC2 = "/root/reference/sample/thenextweek.png"
+REGIONS2 = {
+    "fog_upper_right": (650, 850, 150, 250),   # the rho = 1e-4 medium that fills the room, in front of the dark wall
+    "fog_mid_left": (260, 330, 250, 330),
+    "moving_sphere": (100, 180, 220, 300),     # MovingSphere, Lambertian (0.7, 0.3, 0.1), motion-blurred
+    "fuzzy_metal": (350, 450, 400, 500),       # Metal (0.8, 0.8, 0.9) fuzz 10
+    "earth_land": (100, 170, 450, 520),        # ImageTexture earthmap.png: Asia
+    "earth_ocean": (50, 110, 560, 620),        # ... Indian Ocean
+    "grey_sphere": (730, 800, 600, 680),       # NoiseTexture(0.1)
+    "white_cluster": (520, 640, 320, 420),     # 1000 random white spheres, rotated 15 degrees and translated
+}
+
+
+def main2():
+    raw = open(SRC2, "rb").read()
+    im = np.asarray(Image.open(SRC2).convert("RGB")).astype(np.float64)
+    assert im.shape == (900, 900, 3)
+    out = {
+        "source": "sample/thenextweek.png",
+        "sha256": hashlib.sha256(raw).hexdigest(),
+        "size": [900, 900],
+        "scene": "final_scene (src/scene.rs:732-874), unseeded; linear = ((v + 0.5) / 256)^2",
+        "regions": {},
+    }
+    for name, (x0, x1, y0, y1) in REGIONS2.items():
+        px = im[y0:y1, x0:x1]
+        assert (px >= 255).any(axis=2).mean() < 1e-3, name  # (3 clamped pixels of 12 000 in the cluster)
+        lin = ((px + 0.5) / 256.0) ** 2
+        out["regions"][name] = {"box_xyxy": [x0, x1, y0, y1], "mean_linear": [round(float(v), 5) for v in lin.mean(axis=(0, 1))],
+                                "mean_rgb8": [round(float(v), 3) for v in px.mean(axis=(0, 1))]}
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "thenextweek_sample_regions.json")
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     main()
+    main2()

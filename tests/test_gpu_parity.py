@@ -337,6 +337,30 @@ def test_golden_cornell_render_matches_published_sample(vb, ctx):
     assert (nz[:, 0].min(), nz[:, 0].max(), nz[:, 1].min(), nz[:, 1].max()) == (22, 879, 21, 878)
 
 
+def test_golden_final_scene_render_matches_published_sample(vb, ctx):
+    """GPU final scene at the reference's own settings (900^2, 1000 spp, depth 100) against the linear region
+    means of sample/thenextweek.png (seed-independent objects only: the reference's scene is unseeded).  HEAD's
+    integrator must agree within 15 % (20 % on the dark ocean and on the cluster of random spheres); the legacy
+    integrator must NOT agree in the fog, i.e. the image does pin HEAD's Isotropic-through-CosinePDF quirk."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "thenextweek_sample_regions.json")))
+    scene, cam = get_scene(vb, "final_scene")
+    ctx.upload(scene)
+
+    def ratios(flags, spp):
+        rgb, _, st = ctx.render(cam, vb.render_params(900, 900, spp, 100, seed=1, flags=flags))
+        assert st.dropped_samples <= 1e-5 * st.paths
+        img = rgb[::-1].astype(np.float64)
+        return {name: img[r["box_xyxy"][2]:r["box_xyxy"][3], r["box_xyxy"][0]:r["box_xyxy"][1]].mean(axis=(0, 1)) / np.array(r["mean_linear"])
+                for name, r in g["regions"].items()}
+
+    head = ratios(0, 1000)
+    for name, ratio in head.items():
+        tol = 0.20 if name in ("earth_ocean", "white_cluster") else 0.15
+        assert np.all(np.abs(ratio - 1.0) <= tol), (name, ratio)
+    legacy = ratios(vb.VK_FLAG_LEGACY_SCATTER, 250)
+    assert np.all(legacy["fog_upper_right"] < 0.75) and np.all(legacy["fog_mid_left"] > 1.4), legacy
+
+
 def test_full_size_cornell_properties(vb, ctx):
     """BASELINE.json config 2 at full size (600x600, 1000 spp): size-independent properties."""
     scene, cam = get_scene(vb, "cornell_box")

@@ -124,6 +124,30 @@ def test_oracle_matches_published_cornell_render(po, vb):
     assert abs(nz[:, 1].min() - 21 * k) <= 1.5 and abs(nz[:, 1].max() - 878 * k) <= 1.5
 
 
+def test_oracle_matches_published_final_scene_render(po, vb):
+    """Second golden image: the reference's sample/thenextweek.png, the book-2 final scene (config 4's scene:
+    both media, the image and noise textures, the moving sphere, fuzzy metal, the instanced sphere BVH).  The
+    reference's scene is unseeded, so the fixture holds LINEAR means of regions on the seed-independent objects
+    only; the oracle renders 180^2 at 48 spp (region = a few hundred pixels) and must agree within 20 %
+    (25 % on the dark ocean).  Measured spread over scene and render seeds: 0.85 .. 1.16.
+    The image pins HEAD's integrator including its Isotropic quirk (a CosinePDF about the medium's dummy normal
+    (1,0,0), src/material.rs:448-464): the legacy integrator's uniform phase function gives 0.57x / 1.9x in the
+    two fog regions (tested on the GPU, where the second render is cheap)."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "thenextweek_sample_regions.json")))
+    s, cam = get_scene(vb, "final_scene")
+    o = po.OracleScene(s)
+    W = 180
+    rgb, _, st = o.render(cam, vb.render_params(W, W, 48, 100, seed=1))
+    assert st.dropped_samples == 0
+    img = rgb[::-1].astype(np.float64)
+    k = W / 900.0
+    for name, r in g["regions"].items():
+        x0, x1, y0, y1 = [int(round(v * k)) for v in r["box_xyxy"]]
+        ratio = img[y0:y1, x0:x1].mean(axis=(0, 1)) / np.array(r["mean_linear"])
+        tol = 0.25 if name == "earth_ocean" else 0.20
+        assert np.all(np.abs(ratio - 1.0) <= tol), (name, ratio)
+
+
 def test_oracle_spp_slices_sum_to_the_whole(po, vb):
     """The sharding arithmetic of SURVEY 8(e) on the CPU: N spp slices summed == one render."""
     s, cam = get_scene(vb, "cornell_box")
