@@ -19,7 +19,8 @@ typedef struct vkh_scene vkh_scene;
 /* name: balls_demo | random_spheres_demo | perlin_demo | bowser_demo | cornell_box |
  *       final_scene | cornell_smoke | stress_spheres (param = grid side, 1000 => 1M spheres) |
  *       api_surface_demo (SpecDiffuse, sphere and box lights) |
- *       random_spheres_cover (random_spheres_demo without its light: sky-lit, legacy integrator only)
+ *       random_spheres_cover (random_spheres_demo without its light: sky-lit, legacy integrator only) |
+ *       book1_cover (the book-1 final scene of sample/inoneweekend.png: grey ground, fixed camera; legacy only)
  * seed: seeds the host RNG standing in for rand::thread_rng() (scene + BVH axis choices).
  * assets_dir: directory holding earthmap.png etc. (NULL => "assets"). */
 int vkh_scene_build(const char* name, uint64_t seed, const char* assets_dir, uint32_t param, vkh_scene** out);

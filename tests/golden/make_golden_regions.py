@@ -90,6 +90,42 @@ def main2():
     print(json.dumps(out, indent=1))
 
 
+SRC3 = "/root/reference/sample/inoneweekend.png"
+# The book-1 final scene (1024x576), rendered before the reference grew lights: sky-lit, legacy Material::scatter.
+# HEAD's scene.rs no longer has this variant; the host front end authors it as `book1_cover`.  Regions on the
+# sky and the three big spheres, which do not depend on the unseeded small spheres (beyond their reflections).
+REGIONS3 = {
+    "sky_top": (100, 900, 0, 30),            # blue is clamped at 255 here: only red and green are compared
+    "metal_top": (600, 740, 70, 150),        # Metal (0.7, 0.6, 0.5) fuzz 0 reflecting the sky
+    "metal_upper_mid": (560, 780, 170, 215),
+    "brown_sphere": (345, 395, 90, 150),     # Lambertian (0.4, 0.2, 0.1)
+    "glass_lower": (420, 480, 185, 225),     # Dielectric 1.5: the sky seen through the lower half
+    "ground_far_left": (20, 300, 138, 150),  # Lambertian (0.5, 0.5, 0.5) near the horizon
+}
+
+
+def main3():
+    raw = open(SRC3, "rb").read()
+    im = np.asarray(Image.open(SRC3).convert("RGB")).astype(np.float64)
+    assert im.shape == (576, 1024, 3)
+    out = {
+        "source": "sample/inoneweekend.png",
+        "sha256": hashlib.sha256(raw).hexdigest(),
+        "size": [1024, 576],
+        "scene": "book-1 final scene (book1_cover), sky-lit, legacy integrator; linear = ((v + 0.5) / 256)^2",
+        "regions": {},
+    }
+    for name, (x0, x1, y0, y1) in REGIONS3.items():
+        px = im[y0:y1, x0:x1]
+        lin = ((px + 0.5) / 256.0) ** 2
+        out["regions"][name] = {"box_xyxy": [x0, x1, y0, y1], "mean_linear": [round(float(v), 5) for v in lin.mean(axis=(0, 1))],
+                                "clamped_fraction": [round(float(v), 4) for v in (px >= 255).mean(axis=(0, 1))]}
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "inoneweekend_sample_regions.json")
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     main()
     main2()
+    main3()

@@ -361,6 +361,21 @@ def test_golden_final_scene_render_matches_published_sample(vb, ctx):
     assert np.all(legacy["fog_upper_right"] < 0.75) and np.all(legacy["fog_mid_left"] > 1.4), legacy
 
 
+def test_golden_book1_render_matches_published_sample(vb, ctx):
+    """GPU legacy integrator + sky on the book-1 final scene at the published size (1024x576) against the linear
+    region means of sample/inoneweekend.png; same tolerances as the oracle's test (they are set by the unseeded
+    small spheres, not by noise)."""
+    from test_oracle import BOOK1_TOL, book1_region_ratios
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "inoneweekend_sample_regions.json")))
+    scene, cam = get_scene(vb, "book1_cover")
+    ctx.upload(scene)
+    flags = vb.VK_FLAG_LEGACY_SCATTER | vb.VK_FLAG_SKY_BACKGROUND
+    rgb, _, st = ctx.render(cam, vb.render_params(1024, 576, 256, 50, seed=1, flags=flags))
+    assert st.dropped_samples == 0
+    for name, ratio in book1_region_ratios(g, rgb[::-1].astype(np.float64)).items():
+        assert np.all(np.abs(ratio - 1.0) <= BOOK1_TOL[name]), (name, ratio)
+
+
 def test_full_size_cornell_properties(vb, ctx):
     """BASELINE.json config 2 at full size (600x600, 1000 spp): size-independent properties."""
     scene, cam = get_scene(vb, "cornell_box")

@@ -148,6 +148,39 @@ def test_oracle_matches_published_final_scene_render(po, vb):
         assert np.all(np.abs(ratio - 1.0) <= tol), (name, ratio)
 
 
+def book1_region_ratios(g, img):
+    """{region: rendered / published} linear means; img = (H, W, 3) with row 0 = top.  Channels the published
+    image clamps (the blue of the sky) are left out."""
+    k = img.shape[1] / g["size"][0]
+    out = {}
+    for name, r in g["regions"].items():
+        x0, x1, y0, y1 = [int(round(v * k)) for v in r["box_xyxy"]]
+        keep = np.array(r["clamped_fraction"]) < 0.01
+        out[name] = (img[y0:y1, x0:x1].mean(axis=(0, 1)) / np.array(r["mean_linear"]))[keep]
+    return out
+
+
+BOOK1_TOL = {"sky_top": 0.02, "metal_top": 0.04, "metal_upper_mid": 0.04, "glass_lower": 0.04, "brown_sphere": 0.15,
+             "ground_far_left": 0.10}  # the last two see the unseeded small spheres (measured: 1.03..1.11, 1.03..1.06)
+
+
+def test_oracle_legacy_integrator_matches_published_book1_render(po, vb):
+    """Third golden image: sample/inoneweekend.png, rendered by the reference before it had lights -- the legacy
+    `Material::scatter` path (src/material.rs:85-90, 118-132, 150-175) under the sky.  The scene (`book1_cover`)
+    is authored with the reference's constructors from the book's listing, because HEAD's scene.rs has moved on;
+    that the sky, the metal sphere's mirror image of it and the view through the glass sphere come out within
+    1-4 % of the published pixels confirms camera, geometry and the legacy Metal / Dielectric / Lambertian."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "inoneweekend_sample_regions.json")))
+    s, cam = get_scene(vb, "book1_cover")
+    o = po.OracleScene(s)
+    W = 256
+    flags = vb.VK_FLAG_LEGACY_SCATTER | vb.VK_FLAG_SKY_BACKGROUND
+    rgb, _, st = o.render(cam, vb.render_params(W, s.height_for(W), 64, 50, seed=1, flags=flags))
+    assert s.height_for(W) == 144 and st.dropped_samples == 0
+    for name, ratio in book1_region_ratios(g, rgb[::-1].astype(np.float64)).items():
+        assert np.all(np.abs(ratio - 1.0) <= BOOK1_TOL[name]), (name, ratio)
+
+
 def test_oracle_spp_slices_sum_to_the_whole(po, vb):
     """The sharding arithmetic of SURVEY 8(e) on the CPU: N spp slices summed == one render."""
     s, cam = get_scene(vb, "cornell_box")

@@ -178,10 +178,17 @@ SceneConfig api_surface_demo() {
 // src/scene.rs:167-284; `with_light` = false gives the book-1 cover as it was before the light was
 // added (sample/inoneweekend.png): lit by the sky only, so it needs the legacy integrator
 // (VK_FLAG_LEGACY_SCATTER | VK_FLAG_SKY_BACKGROUND) -- HEAD panics on its empty light list.
-static SceneConfig random_spheres(bool with_light) {
+//
+// `book1` = the scene as the book's first volume ends and as sample/inoneweekend.png shows it: grey ground
+// (0.5, 0.5, 0.5), a brown Lambertian (0.4, 0.2, 0.1) where HEAD has the earth, no light, and the book's
+// fixed camera: lookfrom (13, 2, 3), lookat origin, vfov 20, aperture 0.1, focus 10.  HEAD's scene.rs no
+// longer holds this variant; it is authored here with the reference's constructors so that the legacy
+// integrator can be checked against the published render.
+static SceneConfig random_spheres(bool with_light, bool book1 = false) {
     SceneConfig s;
     auto checker = arc<Checker>(solid(0.1f, 0.1f, 0.1f), solid(0.9f, 0.9f, 0.9f));
-    s.world.push_back(arc<Sphere>(Vec3(0, -1000, 0), 1000.0f, arc<Lambertian>(checker)));
+    s.world.push_back(arc<Sphere>(Vec3(0, -1000, 0), 1000.0f,
+                                  book1 ? lambert(0.5f, 0.5f, 0.5f) : Arc<MaterialSS>(arc<Lambertian>(checker))));
 
     auto& rng = thread_rng();
     for (int a = -11; a < 11; ++a)
@@ -195,17 +202,24 @@ static SceneConfig random_spheres(bool with_light) {
         }
 
     s.world.push_back(arc<Sphere>(Vec3(0, 1, 0), 1.0f, arc<Dielectric>(1.5f)));
-    s.world.push_back(arc<Sphere>(Vec3(-4, 1, 0), 1.0f, arc<Lambertian>(arc<ImageTexture>("assets/earthmap.png"))));
+    s.world.push_back(arc<Sphere>(Vec3(-4, 1, 0), 1.0f,
+                                  book1 ? lambert(0.4f, 0.2f, 0.1f)
+                                        : Arc<MaterialSS>(arc<Lambertian>(arc<ImageTexture>("assets/earthmap.png")))));
     s.world.push_back(arc<Sphere>(Vec3(4, 1, 0), 1.0f, arc<Metal>(solid(0.7f, 0.6f, 0.5f), 0.0f)));
 
     if (with_light) push_sky_light(s, 11.0f, 8.0f, Vec3(1.0f, 0.77f, 0.56f) * 2.0f);
 
     s.aspect_ratio = 16.0f / 9.0f;
-    s.cam_iter = rotating(Vec3(0, 1.5f, 0), 20.0f, s.aspect_ratio, 2.5f, 25.0f, 20.0f, 0.5f, 360.0f);
+    if (book1)
+        s.cam_iter = std::make_unique<FixedCamera>(
+            Camera::make(Vec3(13, 2, 3), Vec3(0, 0, 0), Vec3(0, 1, 0), 20.0f, s.aspect_ratio, 0.1f, 10.0f, 0.0f, 1.0f));
+    else
+        s.cam_iter = rotating(Vec3(0, 1.5f, 0), 20.0f, s.aspect_ratio, 2.5f, 25.0f, 20.0f, 0.5f, 360.0f);
     return s;
 }
 SceneConfig random_spheres_demo() { return random_spheres(true); }
 SceneConfig random_spheres_cover() { return random_spheres(false); }
+SceneConfig book1_cover() { return random_spheres(false, true); }
 
 // src/scene.rs:286-338
 SceneConfig perlin_demo() {

@@ -376,6 +376,7 @@ SceneConfig final_scene();
 SceneConfig cornell_smoke();
 SceneConfig stress_spheres(uint32_t grid_side);
 SceneConfig api_surface_demo();     // SpecDiffuse + sphere and box lights (API surface no shipped scene uses)
+SceneConfig book1_cover();          // the book-1 final scene as sample/inoneweekend.png shows it (grey ground, brown sphere, fixed camera; legacy integrator)
 SceneConfig random_spheres_cover(); // random_spheres_demo without its light: the sky-lit book-1 cover (legacy integrator)
 
 // A scene lowered for the GPU: the boundary object of src/main.rs:168-169.
