@@ -181,8 +181,53 @@ impl Gpu {
         self.check(unsafe { vk_render(self.ctx, cam, &p, out.as_mut_ptr(), std::ptr::null_mut(), &mut st) })?;
         Ok((out, st))
     }
+    /// The same loop followed by `Vec3::to_color` and the top-down row order of src/main.rs:209-212 on the
+    /// device: the W*H*3 numbers of the P3 file in file order (a quarter of the bytes cross PCIe).
+    pub fn render_rgb8(&mut self, cam: &vk_camera, width: usize, height: usize, spp: u32, max_depth: u32, seed: u64)
+                       -> Result<(Vec<u8>, vk_stats), GpuError> {
+        let p = vk_render_params { width: width as u32, height: height as u32, spp, spp_begin: 0, spp_count: 0, max_depth, seed,
+                                   background: [0.0; 3], variant: 0, flags: 0 };
+        let mut out = vec![0u8; width * height * 3];
+        let mut st = vk_stats::default();
+        self.check(unsafe { vk_render_rgb8(self.ctx, cam, &p, out.as_mut_ptr(), &mut st) })?;
+        Ok((out, st))
+    }
+    /// One spp slice [begin, begin+count) of the frame, already divided by the full `spp`: slices of disjoint
+    /// sample ranges ADD to the frame (the Philox counter holds the global sample index).
+    pub fn render_slice(&mut self, cam: &vk_camera, width: usize, height: usize, spp: u32, begin: u32, count: u32,
+                        max_depth: u32, seed: u64) -> Result<(Vec<f32>, vk_stats), GpuError> {
+        let p = vk_render_params { width: width as u32, height: height as u32, spp, spp_begin: begin, spp_count: count, max_depth, seed,
+                                   background: [0.0; 3], variant: 0, flags: 0 };
+        let mut out = vec![0f32; width * height * 3];
+        let mut st = vk_stats::default();
+        self.check(unsafe { vk_render(self.ctx, cam, &p, out.as_mut_ptr(), std::ptr::null_mut(), &mut st) })?;
+        Ok((out, st))
+    }
 }
 impl Drop for Gpu { fn drop(&mut self) { unsafe { vk_destroy(self.ctx) } } }
+// A context is used by one thread at a time and owns its device: it may move between threads.
+unsafe impl Send for Gpu {}
+
+/// Several GPUs in the reference's single process (what `vecchio_gpu_render --gpus N` does in C++,
+/// vecchio_b200/host/main.cpp): one context and one scoped thread per device, GPU k renders the global samples
+/// [k*spp/N, (k+1)*spp/N); the partial means are summed in device order.
+pub fn render_on_all(gpus: &mut [Gpu], cam: &vk_camera, width: usize, height: usize, spp: u32, max_depth: u32, seed: u64)
+                     -> Result<Vec<f32>, GpuError> {
+    let n = gpus.len() as u64;
+    let parts: Vec<Result<(Vec<f32>, vk_stats), GpuError>> = std::thread::scope(|sc| {
+        let handles: Vec<_> = gpus.iter_mut().enumerate().map(|(k, g)| {
+            let (b, e) = ((k as u64 * spp as u64 / n) as u32, ((k as u64 + 1) * spp as u64 / n) as u32);
+            sc.spawn(move || g.render_slice(cam, width, height, spp, b, e - b, max_depth, seed))
+        }).collect();
+        handles.into_iter().map(|h| h.join().unwrap()).collect()
+    });
+    let mut frame = vec![0f32; width * height * 3];
+    for part in parts {
+        let (p, _) = part?;
+        for (a, b) in frame.iter_mut().zip(p.iter()) { *a += *b; }
+    }
+    Ok(frame)
+}
 
 fn last_error(ctx: *const vk_ctx) -> String {
     unsafe { let p = vk_last_error(ctx); if p.is_null() { String::new() } else { CStr::from_ptr(p).to_string_lossy().into_owned() } }
