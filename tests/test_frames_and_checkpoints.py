@@ -42,9 +42,25 @@ def test_frame_to_rgb8_is_to_color_with_rows_flipped(vb, po):
         assert list(po.kat("to_color", f[y, x], 3)) == list(out[8 - y, x])
 
 
+@pytest.mark.parametrize("h,w", [(7, 11), (64, 64), (225, 400)])
+def test_frame_to_rgb8_vector_and_scalar_paths_agree_with_to_color(vb, h, w):
+    """Rows are converted 16 channels at a time with a scalar tail: bin edges ((k/256)^2), NaN, +-inf and negative
+    values at every lane position, row lengths that are and are not multiples of 16."""
+    rng = np.random.default_rng(h * 1000 + w)
+    f = (rng.random((h, w, 3), dtype=np.float32) * 1.5 - 0.1).astype(np.float32)
+    for value, share in ((np.nan, 0.02), (np.inf, 0.02), (-np.inf, 0.02)):
+        f[rng.random(f.shape) < share] = value
+    edges = ((rng.integers(0, 257, f.shape) / 256.0) ** 2).astype(np.float32)
+    m = rng.random(f.shape) < 0.3
+    f[m] = edges[m]
+    m = rng.random(f.shape) < 0.1
+    f[m] = np.nextafter(edges[m], np.float32(0))
+    assert (vb.frame_to_rgb8(f) == vb.to_color(f)[::-1]).all()
+
+
 def test_write_ppm_is_byte_for_byte_the_reference_writer(vb, tmp_path):
     rng = np.random.default_rng(3)
-    for h, w in [(1, 1), (3, 5), (17, 33)]:
+    for h, w in [(1, 1), (3, 5), (17, 33), (400, 300)]:  # the last one spans two 1 MiB blocks of text
         rgb8 = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
         rgb8[0, 0] = (0, 9, 10)
         rgb8[-1, -1] = (99, 100, 255)

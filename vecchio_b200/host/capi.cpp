@@ -1,10 +1,14 @@
 // capi.cpp -- extern "C" view of the host front end (include/vecchio_host.h).
 #include "../../include/vecchio_host.h"
 #include "vecchio.hpp"
+#include <array>
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 using namespace vecchio;
 
@@ -96,21 +100,40 @@ long vkh_decode_png(const char* path, uint8_t* buf, size_t buf_len, uint32_t* wi
 }
 
 // Vec3::to_color (src/vec3.rs:54-61) for one channel.  Vec3::clamp (src/vec3.rs:44-52) is two `<`/`>` tests,
-// so NaN falls through it and `NaN as u32` is 0.
+// so NaN falls through it and `NaN as u32` is 0.  Written without branches so the row loop vectorises:
+// the two selects mirror the two tests, and the final select on v == v is the NaN -> 0 of the cast.
 static inline uint8_t to_color1(float c) {
     float x = std::sqrt(c);
-    if (x < 0.0f) x = 0.0f;
-    else if (x > 0.999f) x = 0.999f;
+    x = x < 0.0f ? 0.0f : x;
+    x = x > 0.999f ? 0.999f : x;
     float v = 256.0f * x;
-    return v == v ? (uint8_t)(uint32_t)v : (uint8_t)0;
+    v = v == v ? v : 0.0f;
+    return (uint8_t)(int)v; // 0 <= v < 256
 }
 
 void vkh_frame_to_rgb8(const float* frame, uint32_t width, uint32_t height, uint8_t* out_rgb8) {
     if (!frame || !out_rgb8) return;
+    const size_t row_len = (size_t)width * 3;
     for (uint32_t row = 0; row < height; row++) { // file row `row` = image row height-1-row (main.rs:209)
-        const float* src = frame + (size_t)(height - 1 - row) * width * 3;
-        uint8_t* dst = out_rgb8 + (size_t)row * width * 3;
-        for (size_t i = 0; i < (size_t)width * 3; i++) dst[i] = to_color1(src[i]);
+        const float* src = frame + (size_t)(height - 1 - row) * row_len;
+        uint8_t* dst = out_rgb8 + (size_t)row * row_len;
+        size_t i = 0;
+#if defined(__SSE2__)
+        // 16 channels per step.  sqrtps is correctly rounded like sqrtf; maxps/minps return their SECOND operand
+        // when the first is NaN, so max(x, 0) already turns NaN into the 0 that `NaN as u32` gives.
+        const __m128 zero = _mm_setzero_ps(), top = _mm_set1_ps(0.999f), scale = _mm_set1_ps(256.0f);
+        for (; i + 16 <= row_len; i += 16) {
+            __m128i q[4];
+            for (int k = 0; k < 4; k++) {
+                __m128 x = _mm_sqrt_ps(_mm_loadu_ps(src + i + 4 * k));
+                x = _mm_min_ps(_mm_max_ps(x, zero), top);
+                q[k] = _mm_cvttps_epi32(_mm_mul_ps(scale, x));
+            }
+            __m128i lo = _mm_packs_epi32(q[0], q[1]), hi = _mm_packs_epi32(q[2], q[3]);
+            _mm_storeu_si128((__m128i*)(dst + i), _mm_packus_epi16(lo, hi));
+        }
+#endif
+        for (; i < row_len; i++) dst[i] = to_color1(src[i]);
     }
 }
 
@@ -124,28 +147,44 @@ int vkh_write_ppm(const char* path, const uint8_t* rgb8, uint32_t width, uint32_
         g_err = std::string("vkh_write_ppm: cannot create ") + path + ": " + std::strerror(errno);
         return VK_ERR_INVALID;
     }
-    // the decimal text of 0..255 once; a pixel line is at most "255 255 255\n" = 12 bytes
-    char digits[256][4];
-    uint8_t ndig[256];
-    for (int v = 0; v < 256; v++) ndig[v] = (uint8_t)std::snprintf(digits[v], 4, "%d", v);
-    std::string buf;
-    buf.reserve((size_t)width * 12 + 32);
-    buf = "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
-    bool ok = true;
-    for (uint32_t row = 0; row < height && ok; row++) {
-        const uint8_t* px = rgb8 + (size_t)row * width * 3;
-        for (uint32_t x = 0; x < width; x++, px += 3) {
-            buf.append(digits[px[0]], ndig[px[0]]);
-            buf.push_back(' ');
-            buf.append(digits[px[1]], ndig[px[1]]);
-            buf.push_back(' ');
-            buf.append(digits[px[2]], ndig[px[2]]);
-            buf.push_back('\n');
+    std::setvbuf(f, nullptr, _IONBF, 0); // the text is assembled in 1 MiB blocks below
+    // the decimal text of 0..255 followed by a blank, and its length; a pixel line is at most
+    // "255 255 255\n" = 12 bytes, written as three 4-byte stores of which the cursor keeps 2..4
+    struct Dec {
+        char text[4];
+        uint32_t len;
+    };
+    static const std::array<Dec, 256> dec = [] {
+        std::array<Dec, 256> t{};
+        for (int v = 0; v < 256; v++) {
+            char tmp[8];
+            int n = std::snprintf(tmp, sizeof tmp, "%d ", v);
+            std::memcpy(t[v].text, tmp, 4);
+            t[v].len = (uint32_t)n;
         }
-        ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-        buf.clear();
+        return t;
+    }();
+    const size_t kBlock = 1u << 20;
+    std::vector<char> buf(kBlock + 16);
+    char* cur = buf.data();
+    cur += std::snprintf(cur, 64, "P3\n%u %u\n255\n", width, height);
+    bool ok = true;
+    const size_t n_pixels = (size_t)width * height;
+    const uint8_t* px = rgb8;
+    for (size_t i = 0; i < n_pixels && ok; i++, px += 3) {
+        std::memcpy(cur, dec[px[0]].text, 4);
+        cur += dec[px[0]].len;
+        std::memcpy(cur, dec[px[1]].text, 4);
+        cur += dec[px[1]].len;
+        std::memcpy(cur, dec[px[2]].text, 4);
+        cur += dec[px[2]].len;
+        cur[-1] = '\n';
+        if ((size_t)(cur - buf.data()) >= kBlock) {
+            ok = std::fwrite(buf.data(), 1, (size_t)(cur - buf.data()), f) == (size_t)(cur - buf.data());
+            cur = buf.data();
+        }
     }
-    if (height == 0) ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    if (ok && cur != buf.data()) ok = std::fwrite(buf.data(), 1, (size_t)(cur - buf.data()), f) == (size_t)(cur - buf.data());
     if (std::fclose(f) != 0) ok = false;
     if (!ok) {
         g_err = std::string("vkh_write_ppm: write failed on ") + path;

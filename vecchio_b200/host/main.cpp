@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -230,7 +231,28 @@ int main(int argc, char** argv) {
     }
     const size_t n_floats = (size_t)width * height * 3;
     const uint32_t world = (uint32_t)gpus.size();
-    std::vector<uint8_t> rgb8(n_floats);
+    // two output buffers: the P3 text of frame f is written by a helper thread while frame f+1 renders
+    std::vector<uint8_t> rgb8_buf[2] = {std::vector<uint8_t>(n_floats), std::vector<uint8_t>(n_floats)};
+    struct Pending {
+        std::future<std::string> done; // "" = written, else the writer's error message
+        std::string filename;
+        std::chrono::steady_clock::time_point start;
+        uint64_t rays = 0;
+    } pending;
+    auto finish_pending = [&]() -> bool {
+        if (!pending.done.valid()) return true;
+        std::string err = pending.done.get();
+        if (!err.empty()) {
+            std::fprintf(stderr, "vecchio_gpu_render: %s\n", err.c_str());
+            return false;
+        }
+        if (!opt.quiet) {
+            double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - pending.start).count();
+            std::fprintf(stderr, "Wrote frame %s in %.3fs (%.1f Mpaths/s, %.1f Mrays/s)\n", pending.filename.c_str(), s,
+                         (double)width * height * opt.spp / s * 1e-6, (double)pending.rays / s * 1e-6);
+        }
+        return true;
+    };
     if (world > 1)
         for (auto& g : gpus) g.partial.resize(n_floats);
 
@@ -243,6 +265,7 @@ int main(int argc, char** argv) {
         }
         if (opt.frames && written >= opt.frames) break;
         auto start = std::chrono::steady_clock::now();
+        std::vector<uint8_t>& rgb8 = rgb8_buf[written & 1];
 
         vk_render_params P{};
         P.width = width;
@@ -293,22 +316,30 @@ int main(int argc, char** argv) {
             vkh_frame_to_rgb8(acc.data(), width, height, rgb8.data());
         }
 
-        // Write output (main.rs:200-214)
-        char filename[4096];
-        if (vkh_frame_filename(opt.out_dir.c_str(), file_idx, filename, sizeof filename) < 0 ||
-            vkh_write_ppm(filename, rgb8.data(), width, height) != VK_OK) {
-            std::fprintf(stderr, "vecchio_gpu_render: %s\n", vkh_last_error());
+        // Write output (main.rs:200-214), overlapped with the next frame's render.  At most one write is in
+        // flight, so the other buffer is free by the time the next frame is converted into it.
+        if (!finish_pending()) {
             destroy_all(gpus, scene);
             return 1;
         }
-        if (!opt.quiet) {
-            double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
-            std::fprintf(stderr, "Wrote frame %s in %.3fs (%.1f Mpaths/s, %.1f Mrays/s)\n", filename, s,
-                         (double)width * height * opt.spp / s * 1e-6, (double)rays / s * 1e-6);
+        char filename[4096];
+        if (vkh_frame_filename(opt.out_dir.c_str(), file_idx, filename, sizeof filename) < 0) {
+            std::fprintf(stderr, "vecchio_gpu_render: output path too long\n");
+            destroy_all(gpus, scene);
+            return 1;
         }
+        pending.filename = filename;
+        pending.start = start;
+        pending.rays = rays;
+        const uint8_t* data = rgb8.data();
+        pending.done = std::async(std::launch::async, [data, width, height, name = pending.filename]() -> std::string {
+            // vkh_last_error is per thread: read it on the thread that failed
+            return vkh_write_ppm(name.c_str(), data, width, height) == VK_OK ? std::string() : std::string(vkh_last_error());
+        });
         file_idx++;
         written++;
     }
+    const bool ok = finish_pending();
     destroy_all(gpus, scene);
-    return 0;
+    return ok ? 0 : 1;
 }
