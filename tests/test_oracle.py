@@ -84,6 +84,79 @@ def test_image_texture_kat(po, vb):  # ImageTexture::value src/material.rs:282-3
         assert np.allclose(got, img[j, i].astype(np.float32) * np.float32(1 / 255.0), atol=1e-7), (u, v)
 
 
+def _noise_texture_value_numpy(perlin, scale, p):
+    """NoiseTexture::value -> Perlin::turb(p, 7) -> noise -> perlin_interp (src/material.rs:331-352, 379-413, 430-433)
+    restated a second time, independently of oracle.cpp, in float32 numpy scalars with the reference's order of
+    operations.  `p.x.floor() as usize` saturates: a negative coordinate gives index 0 (Q16)."""
+    f = np.float32
+    ranvec = np.array(perlin.ranvec, dtype=np.float32)
+    px, py, pz = (np.array(a, dtype=np.int64) for a in (perlin.perm_x, perlin.perm_y, perlin.perm_z))
+
+    def noise(q):
+        fl = np.floor(q)
+        u, v, w = (q - fl).astype(np.float32)
+        i, j, k = (int(max(x, 0.0)) for x in fl)
+        uu, vv, ww = u * u * (f(3) - f(2) * u), v * v * (f(3) - f(2) * v), w * w * (f(3) - f(2) * w)
+        accum = f(0)
+        for di in (0, 1):
+            for dj in (0, 1):
+                for dk in (0, 1):
+                    c = ranvec[px[(i + di) & 255] ^ py[(j + dj) & 255] ^ pz[(k + dk) & 255]]
+                    wv = np.array([u - f(di), v - f(dj), w - f(dk)], dtype=np.float32)
+                    dot = c[0] * wv[0] + c[1] * wv[1] + c[2] * wv[2]
+                    accum = accum + (f(di) * uu + (f(1) - f(di)) * (f(1) - uu)) * (f(dj) * vv + (f(1) - f(dj)) * (f(1) - vv)) \
+                        * (f(dk) * ww + (f(1) - f(dk)) * (f(1) - ww)) * dot
+        return accum
+
+    accum, weight, q = f(0), f(1), np.array(p, dtype=np.float32)
+    for _ in range(7):
+        accum = accum + weight * noise(q)
+        weight = weight * f(0.5)
+        q = q * f(2)
+    return f(0.5) * (f(1) + np.sin(f(scale) * q.dtype.type(p[2]) + f(10) * np.abs(accum), dtype=np.float32))
+
+
+@pytest.mark.parametrize("name", ["perlin_demo", "final_scene"])
+def test_noise_texture_matches_an_independent_restatement(po, vb, name):
+    """Marble texture of the oracle against a second, numpy restatement of src/material.rs on points in every
+    octant (negative coordinates exercise the saturating index), with the scene's own Perlin tables."""
+    s, _ = get_scene(vb, name)
+    o = po.OracleScene(s)
+    d = s.desc
+    ti = [i for i in range(d.n_textures) if d.textures[i].type == 3][0]
+    perlin_index = d.textures[ti].w[0]
+    scale = np.array([d.textures[ti].w[1]], dtype=np.uint32).view(np.float32)[0]
+    assert scale == np.float32(2.0 if name == "perlin_demo" else 0.1)
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform(-6, 6, (40, 3)), rng.uniform(0, 600, (40, 3)), [[0, 0, 0], [-0.5, 2.25, -3.75], [255.5, 256.5, 511.25]]])
+    for p in pts.astype(np.float32):
+        got = o.kat("texture_value", [ti, 0.3, 0.7, *p], 3)
+        want = _noise_texture_value_numpy(d.perlins[perlin_index], scale, p)
+        assert got[0] == got[1] == got[2] and 0.0 <= got[0] <= 1.0
+        # sin of an argument up to ~80 amplifies the last-bit differences of the two summation orders
+        assert abs(got[0] - want) <= 2e-4, (p, got[0], want)
+
+
+def test_checker_texture_matches_an_independent_restatement(po, vb):
+    """Checker::value (src/material.rs:250-258): sign of sin(10x) sin(10y) sin(10z) picks odd / even."""
+    s, _ = get_scene(vb, "bowser_demo")  # ground: Checker((0.1,0.1,0.1), (0.9,0.9,0.9))
+    o = po.OracleScene(s)
+    d = s.desc
+    ti = [i for i in range(d.n_textures) if d.textures[i].type == 1][0]
+    odd, even = d.textures[ti].w[0], d.textures[ti].w[1]
+    col = lambda i: np.array(list(d.textures[i].w), dtype=np.uint32).view(np.float32)  # noqa: E731
+    rng = np.random.default_rng(6)
+    seen = set()
+    for p in rng.uniform(-20, 20, (200, 3)).astype(np.float32):
+        sines = np.sin(np.float32(10) * p[0]) * np.sin(np.float32(10) * p[1]) * np.sin(np.float32(10) * p[2])
+        if abs(sines) < 1e-4:
+            continue  # on a cell boundary the two libm's last bits decide
+        want = col(odd) if sines < 0 else col(even)
+        assert np.allclose(o.kat("texture_value", [ti, 0, 0, *p], 3), want), p
+        seen.add(bool(sines < 0))
+    assert seen == {True, False}
+
+
 def test_oracle_intersect_cornell_known_rays(po, vb):
     s, cam = get_scene(vb, "cornell_box")
     o = po.OracleScene(s)
