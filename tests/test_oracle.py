@@ -171,6 +171,131 @@ def test_oracle_intersect_cornell_known_rays(po, vb):
     assert h["prim"][2] == 0
 
 
+def test_translate_rotate_box_chain_matches_an_independent_restatement(po, vb):
+    """`Translate(RotateY(Boxy((0,0,0),(165,330,165)), 15), (265,0,295))` (src/scene.rs:679-682), the only
+    instanced object of config 2, against a float64 numpy restatement of the chain written from
+    src/hittable.rs:507-524 (Translate), :579-624 (RotateY: the world->object and object->world formulas, Q10)
+    and the box as three slabs.  Rays that the oracle says hit the block must agree in t, p and the normal
+    (which the enclosing Translate face-forwards against the world ray, Q9)."""
+    s, cam = get_scene(vb, "cornell_box")
+    o = po.OracleScene(s)
+    rng = np.random.default_rng(12)
+    n = 4000
+    origin = np.stack([rng.uniform(20, 535, n), rng.uniform(20, 535, n), rng.uniform(-800, 500, n)], axis=1)
+    target = np.stack([rng.uniform(265 - 60, 265 + 220, n), rng.uniform(0, 340, n), rng.uniform(295 - 60, 295 + 220, n)], axis=1)
+    rays = np.zeros(n, dtype=vb.RAY_DTYPE)
+    rays["origin"], rays["direction"] = origin, (target - origin) * rng.uniform(0.2, 3.0, (n, 1))  # never normalised (Q5)
+    rays["tmin"], rays["tmax"] = 0.001, INF
+    h = o.intersect(rays)
+    on_block = np.array([vb.ref_type(r) == vb.VK_T_BOX for r in h["prim"]])  # prim = the leaf record under the wrappers
+    assert on_block.sum() > 800
+
+    th = np.radians(np.float32(15.0)).astype(np.float64)
+    c, sn = np.cos(th), np.sin(th)
+    offset = np.array([265.0, 0.0, 295.0])
+    lo, hi = np.zeros(3), np.array([165.0, 330.0, 165.0])
+    checked = 0
+    for i in np.flatnonzero(on_block):
+        ro = rays["origin"][i].astype(np.float64) - offset                       # Translate: moved_r (:509)
+        rd = rays["direction"][i].astype(np.float64)
+        oo = np.array([c * ro[0] - sn * ro[2], ro[1], sn * ro[0] + c * ro[2]])   # RotateY world -> object (:591-595)
+        od = np.array([c * rd[0] - sn * rd[2], rd[1], sn * rd[0] + c * rd[2]])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t0, t1 = (lo - oo) / od, (hi - oo) / od
+        tn, tf = np.minimum(t0, t1), np.maximum(t0, t1)
+        t_enter, t_exit = tn.max(), tf.min()
+        if not (t_enter < t_exit):
+            continue  # a grazing ray the slab form and the six rects may decide differently
+        inside = t_enter <= 0.001
+        t = t_exit if inside else t_enter
+        axis = int(np.argmin(tf)) if inside else int(np.argmax(tn))
+        if np.sort(tn)[-1] - np.sort(tn)[-2] < 1e-3 and not inside:
+            continue  # an edge: two faces within a hair, either is a legitimate closest hit
+        pobj = oo + t * od
+        nobj = np.zeros(3)
+        nobj[axis] = 1.0
+        pw = np.array([c * pobj[0] + sn * pobj[2], pobj[1], -sn * pobj[0] + c * pobj[2]]) + offset  # object -> world (:603-604), + offset (:512)
+        nw = np.array([c * nobj[0] + sn * nobj[2], nobj[1], -sn * nobj[0] + c * nobj[2]])
+        if np.dot(rd, nw) > 0:
+            nw = -nw  # Translate's set_face_normal against the world-direction ray (:519)
+        assert abs(h["t"][i] - t) <= 2e-4 * abs(t), (i, h["t"][i], t)
+        assert np.allclose(h["p"][i], pw, atol=2e-2), (i, h["p"][i], pw)
+        assert np.allclose(h["normal"][i], nw, atol=1e-5), (i, h["normal"][i], nw)
+        checked += 1
+    assert checked > 700
+
+
+def test_constant_medium_matches_an_independent_restatement(po, vb):
+    """`ConstantMedium::hit` (src/hittable.rs:453-493) over the two smoke blocks of config 3, restated in float64
+    numpy with the free-flight variate supplied to both sides: entry/exit of the transformed box on the whole
+    line (tmin = -inf), `rec1.t` clamped to tmin and then to 0, `hit_distance = -1/density * ln(xi)` against
+    `(t2 - t1) * |d|` (directions are not normalised, Q5), `t = t1 + hit_distance / |d|`, record normal (1,0,0)."""
+    s, cam = get_scene(vb, "cornell_smoke")
+    o = po.OracleScene(s)
+    d = s.desc
+    assert d.n_media == 2
+    rng = np.random.default_rng(21)
+    n = 6000
+    origin = np.stack([rng.uniform(10, 545, n), rng.uniform(10, 545, n), rng.uniform(-800, 545, n)], axis=1)
+    target = np.stack([rng.uniform(60, 500, n), rng.uniform(0, 340, n), rng.uniform(40, 480, n)], axis=1)
+    rays = np.zeros(n, dtype=vb.RAY_DTYPE)
+    rays["origin"], rays["direction"] = origin, (target - origin) * rng.uniform(0.01, 2.0, (n, 1))
+    rays["tmin"], rays["tmax"] = 0.001, INF
+    xi = rng.uniform(0.02, 1.0, (n, vb.VK_MEDIUM_XI_SLOTS)).astype(np.float32)
+    h = o.intersect(rays, medium_xi=xi)
+
+    by_albedo = {0.0: (np.array([165.0, 330.0, 165.0]), 15.0, np.array([265.0, 0.0, 295.0])),   # black smoke, tall block
+                 1.0: (np.array([165.0, 165.0, 165.0]), -18.0, np.array([130.0, 0.0, 65.0]))}   # white fog, short block
+    # media are numbered in the order the lowering meets them in the BVH: tell them apart by their albedo
+    albedo = lambda m: float(np.array([d.textures[d.materials[d.media[m].mat].tex].w[0]], dtype=np.uint32).view(np.float32)[0])  # noqa: E731
+    blocks = [by_albedo[albedo(0)], by_albedo[albedo(1)]]
+    assert albedo(0) != albedo(1)
+
+    def medium_t(m, ro, rd, x):
+        hi, deg, offset = blocks[m]
+        th = np.radians(np.float32(deg)).astype(np.float64)
+        c, sn = np.cos(th), np.sin(th)
+        q = ro - offset
+        oo = np.array([c * q[0] - sn * q[2], q[1], sn * q[0] + c * q[2]])
+        od = np.array([c * rd[0] - sn * rd[2], rd[1], sn * rd[0] + c * rd[2]])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t0, t1 = (0.0 - oo) / od, (hi - oo) / od
+        t_in, t_out = np.minimum(t0, t1).max(), np.maximum(t0, t1).min()
+        if not (t_in < t_out):
+            return None, abs(t_in - t_out) < 1e-3  # the line misses the block (a near-miss is left out)
+        edge = t_out - t_in < 1e-3  # the second boundary hit starts at rec1.t + 0.0001: too thin a crossing is a toss-up
+        t_a = max(t_in, 0.001)      # rec1.t < tmin -> tmin ; (rec1.t < 0 -> 0 cannot trigger after that)
+        if t_a >= t_out:
+            return None, edge
+        length = np.linalg.norm(rd)
+        hit_distance = (-1.0 / np.float32(0.01)) * np.log(np.float64(x))
+        if hit_distance > (t_out - t_a) * length:
+            return None, edge or abs(hit_distance - (t_out - t_a) * length) < 1e-2
+        return t_a + hit_distance / length, edge
+
+    n_medium = checked = 0
+    for i in range(n):
+        ro, rd = rays["origin"][i].astype(np.float64), rays["direction"][i].astype(np.float64)
+        cand = [medium_t(m, ro, rd, xi[i, (2 * m) % vb.VK_MEDIUM_XI_SLOTS]) for m in (0, 1)]
+        if any(e for _, e in cand):
+            continue
+        got_type, got_index = vb.ref_type(h["prim"][i]), int(h["prim"][i]) & 0x0FFFFFFF
+        ts = [t for t, _ in cand]
+        if got_type == vb.VK_T_MEDIUM:
+            n_medium += 1
+            t = ts[got_index]
+            assert t is not None and abs(h["t"][i] - t) <= 2e-4 * t, (i, got_index, h["t"][i], t)
+            other = ts[1 - got_index]
+            assert other is None or other >= t * (1 - 1e-4)
+            assert np.allclose(h["normal"][i], [1, 0, 0]) and h["front"][i] == 1
+            assert np.allclose(h["p"][i], ro + t * rd, atol=3e-2)
+        else:
+            for t in ts:  # a wall (or nothing) is closer than any smoke event
+                assert t is None or h["prim"][i] == 0 or t >= h["t"][i] * (1 - 1e-4), (i, ts, h["t"][i])
+        checked += 1
+    assert checked > 5000 and n_medium > 800
+
+
 def test_oracle_matches_published_cornell_render(po, vb):
     """Golden image: the reference's sample/therestofyourlife.png (900^2, 1000 spp).  The oracle
     renders 225^2 at 128 spp; region means after to_color must agree within +-4 (8-bit): the
