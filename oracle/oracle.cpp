@@ -1324,6 +1324,28 @@ int orc_kat(const orc_scene* s, const char* name, const float* in, int n_in, flo
     } else if (k == "cosine_pdf_value" && n_in >= 6 && n_out >= 1) {
         out[0] = CosinePDF(v3(0)).value(v3(3));
         ret = 1;
+    } else if (k == "sphere_pdf_value" && n_in >= 10 && n_out >= 1) { // c3 r o3 d3
+        Sphere sp;
+        sp.center = v3(0);
+        sp.radius = in[3];
+        sp.material = std::make_shared<Dielectric>();
+        out[0] = sp.pdf_value(v3(4), v3(7));
+        ret = 1;
+    } else if (k == "sphere_random" && n_in >= 7 && n_out >= 3) { // c3 r o3 -> n_out/3 draws of Sphere::random
+        Sphere sp;
+        sp.center = v3(0);
+        sp.radius = in[3];
+        sp.material = std::make_shared<Dielectric>();
+        ret = 0;
+        for (int i = 0; i + 3 <= n_out; i += 3, ret += 3) put3(i, sp.random(v3(4)));
+    } else if (k == "box_pdf_value" && n_in >= 12 && n_out >= 1) { // p0 p1 o3 v3
+        Boxy bx(v3(0), v3(3), std::make_shared<Dielectric>(), VK_REF_NONE);
+        out[0] = bx.pdf_value(v3(6), v3(9));
+        ret = 1;
+    } else if (k == "box_random" && n_in >= 9 && n_out >= 3) { // p0 p1 o3 -> n_out/3 draws of Boxy::random
+        Boxy bx(v3(0), v3(3), std::make_shared<Dielectric>(), VK_REF_NONE);
+        ret = 0;
+        for (int i = 0; i + 3 <= n_out; i += 3, ret += 3) put3(i, bx.random(v3(6)));
     }
     tl_rng = nullptr;
     return ret;

@@ -37,6 +37,63 @@ def test_rect_pdf_value_kat(po):  # Rect::pdf_value src/hittable.rs:271-282, Cor
     assert po.kat("rect_pdf_value", rect + [278, 0, 279.5, 1, 0.01, 0], 1)[0] == 0.0  # misses the light
 
 
+def test_sphere_light_sampling_kat(po):  # Sphere::pdf_value / random, random_to_sphere src/hittable.rs:104-134
+    c, r, o = np.array([0.5, 2.0, -5.0]), 1.25, np.array([0.2, -0.3, 0.4])
+    dist2 = ((c - o) ** 2).sum()
+    cos_max = np.sqrt(1 - r * r / dist2)
+    want = 1.0 / (2 * np.pi * (1 - cos_max))
+    for scale in (1.0, 0.01, 37.0):  # the direction is never normalised; the value does not depend on its length
+        assert np.isclose(po.kat("sphere_pdf_value", [*c, r, *o, *((c - o) * scale)], 1)[0], want, rtol=1e-5)
+    assert po.kat("sphere_pdf_value", [*c, r, *o, 1, 0, 0], 1)[0] == 0.0  # misses the sphere
+    assert po.kat("sphere_pdf_value", [*c, r, *o, *(o - c)], 1)[0] == 0.0  # points away
+    d = np.array(po.kat("sphere_random", [*c, r, *o], 3 * 400)).reshape(-1, 3).astype(np.float64)
+    w = (c - o) / np.sqrt(dist2)
+    z = d @ w
+    radial = np.sqrt(np.maximum((d * d).sum(axis=1) - z * z, 0))
+    assert z.min() >= cos_max - 1e-5 and z.max() <= 1 + 1e-6
+    # Q18: x, y are scaled by (1 - z^2), not by sqrt(1 - z^2) -- the reference's bug, kept
+    assert np.allclose(radial, 1 - z * z, atol=2e-5)
+    assert np.abs(radial - np.sqrt(np.maximum(1 - z * z, 0))).max() > 0.05
+    # z is uniform on [cos_max, 1]
+    assert abs(z.mean() - (1 + cos_max) / 2) < 4 * (1 - cos_max) / np.sqrt(12 * len(z))
+
+
+def test_box_light_sampling_kat(po):  # Boxy::pdf_value / random src/hittable.rs:371-377 over its six sides (:325-353)
+    p0, p1, o = np.array([-1.0, -0.5, -6.0]), np.array([1.5, 1.0, -4.0]), np.array([3.0, 2.5, 0.5])
+
+    def side_pdf(axis, v):  # the three sides at p1[axis] are plain Rects; the three at p0[axis] sit in a FlipFace -> default 0
+        a, b = [i for i in range(3) if i != axis]
+        if v[axis] == 0:
+            return 0.0
+        t = (p1[axis] - o[axis]) / v[axis]
+        q = o + t * v
+        if t < 0.001 or not (p0[a] <= q[a] <= p1[a] and p0[b] <= q[b] <= p1[b]):
+            return 0.0
+        area = (p1[a] - p0[a]) * (p1[b] - p0[b])
+        length = np.linalg.norm(v)
+        return t * t * length * length / (abs(v[axis]) / length * area)  # Rect::pdf_value :271-282
+
+    rng = np.random.default_rng(8)
+    nonzero = 0
+    for _ in range(200):
+        target = p0 + (p1 - p0) * rng.uniform(-0.2, 1.2, 3)
+        v = (target - o) * rng.uniform(0.1, 4.0)
+        want = sum(side_pdf(ax, v) for ax in range(3)) / 6.0  # weight 1/len(sides) each (:420-427)
+        got = po.kat("box_pdf_value", [*p0, *p1, *o, *v], 1)[0]
+        assert np.isclose(got, want, rtol=2e-4, atol=1e-7), (v, got, want)
+        nonzero += got > 0
+    assert nonzero > 50
+    d = np.array(po.kat("box_random", [*p0, *p1, *o], 3 * 1200)).reshape(-1, 3).astype(np.float64)
+    default = np.all(d == [1.0, 0.0, 0.0], axis=1)  # FlipFace has no `random`: Hittable's default (src/hittable.rs:40)
+    assert abs(default.mean() - 0.5) < 0.06
+    pts = d[~default] + o
+    on_face = [np.isclose(pts[:, ax], p1[ax], atol=1e-4) for ax in range(3)]
+    assert np.all(on_face[0] | on_face[1] | on_face[2])
+    assert np.all((pts >= p0 - 1e-4) & (pts <= p1 + 1e-4))
+    for f in on_face:
+        assert abs(f.mean() - 1 / 3) < 0.08
+
+
 def test_aabb_kat(po):  # AxisBB::hit src/accel.rs:16-35 incl. the inf / NaN slab cases
     box = [0, 0, 0, 1, 1, 1]
     assert po.kat("aabb_hit", box + [-1, .5, .5, 1, 0, 0, 0.001, INF], 1)[0] == 1
@@ -223,6 +280,45 @@ def test_translate_rotate_box_chain_matches_an_independent_restatement(po, vb):
         assert np.allclose(h["normal"][i], nw, atol=1e-5), (i, h["normal"][i], nw)
         checked += 1
     assert checked > 700
+
+
+def test_moving_sphere_matches_an_independent_restatement(po, vb):
+    """`MovingSphere::hit` (src/hittable.rs:154-184) with `center(time)` (:147-150) on the final scene's one moving
+    sphere: rays at random shutter times whose closest hit the oracle attributes to it, against the half-b
+    quadratic about the interpolated centre in float64."""
+    s, cam = get_scene(vb, "final_scene")
+    o = po.OracleScene(s)
+    d = s.desc
+    assert d.n_mspheres == 1
+    ms = d.mspheres[0]
+    c0, c1 = np.array(list(ms.center0), dtype=np.float64), np.array(list(ms.center1), dtype=np.float64)
+    assert np.allclose(c0, [400, 400, 200]) and np.allclose(c1, [430, 400, 200]) and ms.radius == 50.0  # src/scene.rs:775-783
+    assert (ms.time0, ms.time1) == (0.0, 1.0)
+    rng = np.random.default_rng(31)
+    n = 3000
+    origin = np.stack([rng.uniform(200, 600, n), rng.uniform(250, 540, n), rng.uniform(-500, 100, n)], axis=1)
+    target = np.stack([rng.uniform(340, 490, n), rng.uniform(340, 460, n), rng.uniform(150, 250, n)], axis=1)
+    rays = np.zeros(n, dtype=vb.RAY_DTYPE)
+    rays["origin"], rays["direction"] = origin, (target - origin) * rng.uniform(0.05, 2.0, (n, 1))
+    rays["time"] = rng.uniform(0, 1, n)
+    rays["tmin"], rays["tmax"] = 0.001, INF
+    xi = np.full((n, vb.VK_MEDIUM_XI_SLOTS), 1e-30, dtype=np.float32)  # free flight far beyond the room: the media never hit
+    h = o.intersect(rays, medium_xi=xi)
+    mine = np.array([vb.ref_type(r) == vb.VK_T_MSPHERE for r in h["prim"]])
+    assert mine.sum() > 600
+    for i in np.flatnonzero(mine):
+        ro, rd, tm = rays["origin"][i].astype(np.float64), rays["direction"][i].astype(np.float64), float(rays["time"][i])
+        centre = c0 + (c1 - c0) * ((tm - 0.0) / (1.0 - 0.0))
+        oc = ro - centre
+        a, half_b, c = rd @ rd, oc @ rd, oc @ oc - 50.0 * 50.0
+        disc = half_b * half_b - a * c
+        assert disc > 0
+        roots = [(-half_b - np.sqrt(disc)) / a, (-half_b + np.sqrt(disc)) / a]
+        t = next(r for r in roots if 0.001 < r)
+        assert abs(h["t"][i] - t) <= 1e-4 * t, (i, h["t"][i], t)
+        normal = (ro + t * rd - centre) / 50.0
+        front = rd @ normal < 0
+        assert np.allclose(h["normal"][i], normal if front else -normal, atol=2e-3) and bool(h["front"][i]) == front  # fp32 quadratic: t is good to ~1e-4
 
 
 def test_constant_medium_matches_an_independent_restatement(po, vb):
