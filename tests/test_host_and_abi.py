@@ -149,7 +149,7 @@ def test_scene_check_plans_every_shipped_scene(vb):
         "cornell_box": (True, True, False), "cornell_smoke": (True, True, False), "balls_demo": (True, False, False),
         "api_surface_demo": (True, False, False), "perlin_demo": (True, False, False), "random_spheres_demo": (False, False, False),
         "random_spheres_cover": (False, False, False), "final_scene": (False, False, False), "bowser_demo": (False, False, False),
-        "book1_cover": (False, False, False),
+        "book1_cover": (False, False, False), "furnace_demo": (True, True, False),
     }
     for name, (flat, simple, dyn) in want.items():
         s, _ = get_scene(vb, name)

@@ -475,6 +475,47 @@ def test_oracle_legacy_integrator_matches_published_book1_render(po, vb):
         assert np.all(np.abs(ratio - 1.0) <= BOOK1_TOL[name]), (name, ratio)
 
 
+FURNACE_E = np.array([0.8, 0.6, 0.4])
+
+
+def test_furnace_lambertian_closed_form(po, vb):
+    """`ray_color` (src/main.rs:123-153) against a closed form: a Lambertian sphere in a uniformly emitting room
+    radiates exactly albedo * E, whatever the mix of cosine and light sampling -- provided the estimator weights
+    `attenuation * scattering_pdf / mixture_pdf` are right (the light list holds a rect outside the room that no ray
+    can reach: its pdf still enters the mixture).  Mean over the pixels fully on the sphere, 4 sigma and 0.5 %."""
+    s, cam = get_scene(vb, "furnace_demo", param=0)
+    o = po.OracleScene(s)
+    W, spp = 64, 256
+    rgb, sq, st = o.render(cam, vb.render_params(W, W, spp, 100, seed=7), want_sumsq=True)
+    assert st.dropped_samples == 0
+    rgb = rgb.astype(np.float64)
+    assert np.allclose(rgb[:4, :4], FURNACE_E, rtol=1e-5)  # beside the sphere: the room itself
+    yy, xx = np.mgrid[0:W, 0:W]
+    disc = ((yy - 31.5) ** 2 + (xx - 31.5) ** 2) < 12 ** 2
+    want = np.array([0.5, 0.25, 0.75]) * FURNACE_E
+    mean = rgb[disc].mean(axis=0)
+    sigma = np.sqrt((sq[disc] / spp - rgb[disc] ** 2).mean(axis=0) / spp / disc.sum())
+    assert np.all(np.abs(mean - want) <= 4 * sigma) and np.all(np.abs(mean / want - 1) < 5e-3), (mean / want, (mean - want) / sigma)
+    assert np.all(sigma / want > 1e-4)  # the estimator does have variance: this is not a tautology
+
+
+@pytest.mark.parametrize("kind,albedo", [(1, (0.7, 0.6, 0.5)), (2, (1.0, 1.0, 1.0))])
+def test_furnace_specular_closed_form(po, vb, kind, albedo):
+    """The specular branch of `ray_color` (src/main.rs:134-137): a fuzz-0 Metal sphere shows albedo * E, a Dielectric
+    sphere E (attenuation 1, every chain of refractions and reflections ends on the room) -- per sample, so every
+    pixel is exact: on the sphere, beside it, and any mixture of the two on its silhouette."""
+    s, cam = get_scene(vb, "furnace_demo", param=kind)
+    o = po.OracleScene(s)
+    W = 48
+    rgb, _, st = o.render(cam, vb.render_params(W, W, 32, 100, seed=3))
+    assert st.dropped_samples == 0
+    want = np.array(albedo) * FURNACE_E
+    assert np.allclose(rgb[20:28, 20:28], want, rtol=2e-5)
+    assert np.allclose(rgb[:4, :4], FURNACE_E, rtol=1e-5)
+    lo, hi = np.minimum(want, FURNACE_E), np.maximum(want, FURNACE_E)
+    assert np.all(rgb >= lo * (1 - 1e-5)) and np.all(rgb <= hi * (1 + 1e-5))
+
+
 def test_oracle_spp_slices_sum_to_the_whole(po, vb):
     """The sharding arithmetic of SURVEY 8(e) on the CPU: N spp slices summed == one render."""
     s, cam = get_scene(vb, "cornell_box")

@@ -1,0 +1,41 @@
+"""The furnace closed forms (tests/test_oracle.py) on the GPU path.
+
+Written after this round's GPU minutes were spent: the oracle versions are green, these have not run on a B200
+yet, hence the non-strict xfail -- an XPASS in the round-end log is the first run succeeding, an XFAIL is a
+finding to look at, neither hides the rest of the suite.  Drop the marker once seen green."""
+import numpy as np
+import pytest
+
+from conftest import get_scene
+from test_oracle import FURNACE_E
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU budget was spent)")]
+
+
+def test_furnace_lambertian_closed_form_gpu(vb, ctx):
+    scene, cam = get_scene(vb, "furnace_demo", param=0)
+    ctx.upload(scene)
+    W, spp = 128, 1024
+    rgb, sq, st = ctx.render(cam, vb.render_params(W, W, spp, 100, seed=7), want_sumsq=True)
+    assert st.dropped_samples == 0
+    rgb = rgb.astype(np.float64)
+    assert np.allclose(rgb[:8, :8], FURNACE_E, rtol=1e-5)
+    yy, xx = np.mgrid[0:W, 0:W]
+    disc = ((yy - 63.5) ** 2 + (xx - 63.5) ** 2) < 24 ** 2
+    want = np.array([0.5, 0.25, 0.75]) * FURNACE_E
+    mean = rgb[disc].mean(axis=0)
+    sigma = np.sqrt((sq[disc] / spp - rgb[disc] ** 2).mean(axis=0) / spp / disc.sum())
+    assert np.all(np.abs(mean - want) <= 4 * sigma) and np.all(np.abs(mean / want - 1) < 2e-3), (mean / want, (mean - want) / sigma)
+
+
+@pytest.mark.parametrize("kind,albedo", [(1, (0.7, 0.6, 0.5)), (2, (1.0, 1.0, 1.0))])
+def test_furnace_specular_closed_form_gpu(vb, ctx, kind, albedo):
+    scene, cam = get_scene(vb, "furnace_demo", param=kind)
+    ctx.upload(scene)
+    W = 96
+    rgb, _, st = ctx.render(cam, vb.render_params(W, W, 64, 100, seed=3))
+    assert st.dropped_samples == 0
+    want = np.array(albedo) * FURNACE_E
+    assert np.allclose(rgb[40:56, 40:56], want, rtol=5e-5)
+    assert np.allclose(rgb[:8, :8], FURNACE_E, rtol=1e-5)

@@ -36,6 +36,7 @@ int vkh_scene_build(const char* name, uint64_t seed, const char* assets_dir, uin
         else if (n == "random_spheres_cover") cfg = random_spheres_cover();
         else if (n == "api_surface_demo") cfg = api_surface_demo();
         else if (n == "book1_cover") cfg = book1_cover();
+        else if (n == "furnace_demo") cfg = furnace_demo(param);
         else if (n == "perlin_demo") cfg = perlin_demo();
         else if (n == "bowser_demo") cfg = bowser_demo();
         else if (n == "cornell_box") cfg = cornell_box();

@@ -47,7 +47,8 @@ void usage(FILE* f) {
         "usage: vecchio_gpu_render [options]\n"
         "  --scene N|NAME     0 bowser_demo, 1 cornell_box (default), 2 final_scene, 3 random_spheres_demo,\n"
         "                     4 perlin_demo, 5 balls_demo (src/main.rs:159-167); by name also cornell_smoke,\n"
-        "                     stress_spheres, api_surface_demo, random_spheres_cover, book1_cover\n"
+        "                     stress_spheres, api_surface_demo, random_spheres_cover, book1_cover,\n"
+        "                     furnace_demo\n"
         "  --param K          scene parameter (stress_spheres: grid side)\n"
         "  --width W          image width, height = (W / aspect_ratio) as usize (default 900)\n"
         "  --spp S            SAMPLES_PER_PIXEL (default 1000)\n"

@@ -175,6 +175,36 @@ SceneConfig api_surface_demo() {
     return s;
 }
 
+// A furnace, authored with the reference's constructors for its closed-form answer: one convex object inside a
+// uniformly emitting room (six DiffuseLight rects at +-40, those on the + side in a FlipFace so that the inside
+// is their front, as the Cornell light is built, src/scene.rs:660-668; emission E).  A Sphere of negative radius
+// would not do: its bounding box is inverted (src/hittable.rs:97-102) and the BVH would only find it through the
+// other object's box.  Every direction leaving the object ends on the room, so the object's radiance is exactly
+// albedo * E for a Lambertian (`kind` 0) whatever the sampling strategy, albedo * E for a fuzz-0 Metal (1), and E
+// for a Dielectric (2, up to the depth cap); pixels beside the object show E.  The light list holds a rect OUTSIDE
+// the room and not in the world -- the reference keeps lights in their own list (src/main.rs:169) and
+// `pdf_value` tests only the light's own geometry -- so the mixture estimator must weight light-sampled
+// directions correctly although they never reach that rect.
+SceneConfig furnace_demo(uint32_t kind) {
+    SceneConfig s;
+    auto glow = arc<DiffuseLight>(solid(0.8f, 0.6f, 0.4f));
+    const float L = 40.0f;
+    s.world.push_back(rect(Rect::XYRect(-L, L, -L, L, -L, glow)));
+    s.world.push_back(flip(rect(Rect::XYRect(-L, L, -L, L, L, glow))));
+    s.world.push_back(rect(Rect::XZRect(-L, L, -L, L, -L, glow)));
+    s.world.push_back(flip(rect(Rect::XZRect(-L, L, -L, L, L, glow))));
+    s.world.push_back(rect(Rect::YZRect(-L, L, -L, L, -L, glow)));
+    s.world.push_back(flip(rect(Rect::YZRect(-L, L, -L, L, L, glow))));
+    Arc<MaterialSS> m = kind == 1   ? Arc<MaterialSS>(arc<Metal>(solid(0.7f, 0.6f, 0.5f), 0.0f))
+                        : kind == 2 ? Arc<MaterialSS>(arc<Dielectric>(1.5f))
+                                    : lambert(0.5f, 0.25f, 0.75f);
+    s.world.push_back(arc<Sphere>(Vec3(0, 0, 0), 2.0f, m));
+    s.lights.push_back(rect(Rect::XZRect(-6, 6, -6, 6, 70, arc<DiffuseLight>(solid(1, 1, 1)))));
+    s.aspect_ratio = 1.0f;
+    s.cam_iter = fixed(Vec3(0, 0, 12), Vec3(0, 0, 0), 40.0f, s.aspect_ratio);
+    return s;
+}
+
 // src/scene.rs:167-284; `with_light` = false gives the book-1 cover as it was before the light was
 // added (sample/inoneweekend.png): lit by the sky only, so it needs the legacy integrator
 // (VK_FLAG_LEGACY_SCATTER | VK_FLAG_SKY_BACKGROUND) -- HEAD panics on its empty light list.
