@@ -516,6 +516,38 @@ def test_furnace_specular_closed_form(po, vb, kind, albedo):
     assert np.all(rgb >= lo * (1 - 1e-5)) and np.all(rgb <= hi * (1 + 1e-5))
 
 
+def test_furnace_white_medium_conserves_energy(po, vb):
+    """`ConstantMedium` + `Isotropic` through `ray_color`: a medium of albedo 1 in the furnace shows E in expectation
+    however often the path scatters inside -- with HEAD's Isotropic (a cosine lobe about the record's dummy normal,
+    Q8) mixed with light sampling, i.e. only if scattering_pdf and the mixture pdf cancel as they should.  The
+    legacy integrator has no pdf at all: exact per sample."""
+    s, cam = get_scene(vb, "furnace_demo", param=3)
+    o = po.OracleScene(s)
+    W, spp = 64, 512
+    rgb, sq, st = o.render(cam, vb.render_params(W, W, spp, 100, seed=1), want_sumsq=True)
+    assert st.dropped_samples == 0 and st.rays > 1.2 * st.paths  # the medium does scatter
+    rgb = rgb.astype(np.float64)
+    yy, xx = np.mgrid[0:W, 0:W]
+    disc = ((yy - 31.5) ** 2 + (xx - 31.5) ** 2) < 12 ** 2
+    mean = rgb[disc].mean(axis=0)
+    sigma = np.sqrt((sq[disc] / spp - rgb[disc] ** 2).mean(axis=0) / spp / disc.sum())
+    assert np.all(np.abs(mean - FURNACE_E) <= 4 * sigma) and np.all(np.abs(mean / FURNACE_E - 1) < 0.03), (mean / FURNACE_E, sigma)
+    assert np.abs(rgb[disc] / FURNACE_E - 1).max() > 0.05  # per pixel it is an estimate, not an identity
+    legacy, _, _ = o.render(cam, vb.render_params(W, W, 16, 100, seed=1, flags=vb.VK_FLAG_LEGACY_SCATTER))
+    assert np.allclose(legacy, FURNACE_E, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind,albedo", [(1, (0.7, 0.6, 0.5)), (2, (1.0, 1.0, 1.0))])
+def test_furnace_legacy_specular_closed_form(po, vb, kind, albedo):
+    """The same closed forms through the legacy `Material::scatter` of Metal and Dielectric (src/material.rs:118-132,
+    150-175)."""
+    s, cam = get_scene(vb, "furnace_demo", param=kind)
+    o = po.OracleScene(s)
+    rgb, _, _ = o.render(cam, vb.render_params(48, 48, 32, 100, seed=3, flags=vb.VK_FLAG_LEGACY_SCATTER))
+    assert np.allclose(rgb[20:28, 20:28], np.array(albedo) * FURNACE_E, rtol=2e-5)
+    assert np.allclose(rgb[:4, :4], FURNACE_E, rtol=1e-5)
+
+
 def test_oracle_spp_slices_sum_to_the_whole(po, vb):
     """The sharding arithmetic of SURVEY 8(e) on the CPU: N spp slices summed == one render."""
     s, cam = get_scene(vb, "cornell_box")

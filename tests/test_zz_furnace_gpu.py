@@ -39,3 +39,19 @@ def test_furnace_specular_closed_form_gpu(vb, ctx, kind, albedo):
     want = np.array(albedo) * FURNACE_E
     assert np.allclose(rgb[40:56, 40:56], want, rtol=5e-5)
     assert np.allclose(rgb[:8, :8], FURNACE_E, rtol=1e-5)
+
+
+def test_furnace_white_medium_conserves_energy_gpu(vb, ctx):
+    scene, cam = get_scene(vb, "furnace_demo", param=3)
+    ctx.upload(scene)
+    W, spp = 128, 2048
+    rgb, sq, st = ctx.render(cam, vb.render_params(W, W, spp, 100, seed=1), want_sumsq=True)
+    assert st.dropped_samples == 0 and st.rays > 1.2 * st.paths
+    rgb = rgb.astype(np.float64)
+    yy, xx = np.mgrid[0:W, 0:W]
+    disc = ((yy - 63.5) ** 2 + (xx - 63.5) ** 2) < 24 ** 2
+    mean = rgb[disc].mean(axis=0)
+    sigma = np.sqrt((sq[disc] / spp - rgb[disc] ** 2).mean(axis=0) / spp / disc.sum())
+    assert np.all(np.abs(mean - FURNACE_E) <= 4 * sigma) and np.all(np.abs(mean / FURNACE_E - 1) < 0.01), (mean / FURNACE_E, sigma)
+    legacy, _, _ = ctx.render(cam, vb.render_params(W, W, 16, 100, seed=1, flags=vb.VK_FLAG_LEGACY_SCATTER))
+    assert np.allclose(legacy, FURNACE_E, rtol=1e-5)

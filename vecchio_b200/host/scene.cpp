@@ -181,7 +181,8 @@ SceneConfig api_surface_demo() {
 // would not do: its bounding box is inverted (src/hittable.rs:97-102) and the BVH would only find it through the
 // other object's box.  Every direction leaving the object ends on the room, so the object's radiance is exactly
 // albedo * E for a Lambertian (`kind` 0) whatever the sampling strategy, albedo * E for a fuzz-0 Metal (1), and E
-// for a Dielectric (2, up to the depth cap); pixels beside the object show E.  The light list holds a rect OUTSIDE
+// for a Dielectric (2, up to the depth cap) and, in expectation, for a white ConstantMedium (3); pixels beside
+// the object show E.  The light list holds a rect OUTSIDE
 // the room and not in the world -- the reference keeps lights in their own list (src/main.rs:169) and
 // `pdf_value` tests only the light's own geometry -- so the mixture estimator must weight light-sampled
 // directions correctly although they never reach that rect.
@@ -198,7 +199,10 @@ SceneConfig furnace_demo(uint32_t kind) {
     Arc<MaterialSS> m = kind == 1   ? Arc<MaterialSS>(arc<Metal>(solid(0.7f, 0.6f, 0.5f), 0.0f))
                         : kind == 2 ? Arc<MaterialSS>(arc<Dielectric>(1.5f))
                                     : lambert(0.5f, 0.25f, 0.75f);
-    s.world.push_back(arc<Sphere>(Vec3(0, 0, 0), 2.0f, m));
+    if (kind == 3) // a white medium conserves energy: E in expectation however often the path scatters inside
+        s.world.push_back(arc<ConstantMedium>(arc<Sphere>(Vec3(0, 0, 0), 2.0f, m), 0.8f, solid(1, 1, 1)));
+    else
+        s.world.push_back(arc<Sphere>(Vec3(0, 0, 0), 2.0f, m));
     s.lights.push_back(rect(Rect::XZRect(-6, 6, -6, 6, 70, arc<DiffuseLight>(solid(1, 1, 1)))));
     s.aspect_ratio = 1.0f;
     s.cam_iter = fixed(Vec3(0, 0, 12), Vec3(0, 0, 0), 40.0f, s.aspect_ratio);
