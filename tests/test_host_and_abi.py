@@ -209,3 +209,26 @@ def test_scene_check_refuses_malformed_and_unsupported_scenes(vb):
     assert rc in (vb.VK_ERR_UNSUPPORTED, vb.VK_ERR_INVALID) and msg
     # an empty light list is a valid upload (only the legacy integrator can render it)
     assert vb.scene_check(get_scene(vb, "random_spheres_cover")[0].desc_ptr)["flat_entries"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# the headers are C, not C++: examples/minimal.c is built with a pedantic C11 compiler against both libraries
+# ---------------------------------------------------------------------------------------------------
+def build_minimal_c(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "minimal")
+    lib = os.path.join(ROOT, "vecchio_b200", "lib")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "minimal.c"), "-L" + lib, "-lvecchio_host", "-lvecchio_gpu",
+                        "-Wl,-rpath," + lib, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_abi_compiles_and_links_from_plain_c(tmp_path):
+    import subprocess
+    exe = build_minimal_c(tmp_path)
+    r = subprocess.run([exe, str(tmp_path / "out.ppm")], capture_output=True, text=True, cwd=ROOT)
+    assert "layout: 13 flat entries in 2 segments" in r.stderr  # vk_scene_check ran (host only)
+    if not os.path.exists("/dev/nvidia0"):
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr and not (tmp_path / "out.ppm").exists()

@@ -100,3 +100,17 @@ def test_slices_merge_into_the_frame(vb, ctx, tmp_path):
     assert np.allclose(acc.sumsq, full_sq, rtol=1e-5, atol=1e-6)
     se = acc.standard_error()
     assert np.isfinite(se).all() and 0 < se.mean() < 0.2
+
+
+@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU budget was spent)")
+def test_plain_c_example_renders_the_same_frame(vb, ctx, tmp_path):
+    """examples/minimal.c (the ABI from C11) against the same calls made through ctypes."""
+    from test_host_and_abi import build_minimal_c
+    exe = build_minimal_c(tmp_path)
+    out = tmp_path / "c.ppm"
+    r = subprocess.run([exe, str(out)], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr
+    scene, cam = get_scene(vb, "cornell_box")
+    ctx.upload(scene)
+    rgb8, _ = ctx.render_rgb8(cam, vb.render_params(200, 200, 64, 100, seed=1))
+    assert (parse_ppm(str(out)) == rgb8).all()
