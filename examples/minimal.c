@@ -27,6 +27,7 @@ int main(int argc, char** argv) {
     char why[256];
     if (vk_scene_check(vkh_scene_desc(scene), &info, why, sizeof why) != VK_OK) { /* host only: no device needed */
         fprintf(stderr, "scene check: %s\n", why);
+        vkh_scene_free(scene);
         return 1;
     }
     fprintf(stderr, "layout: %u flat entries in %u segments, %u wide nodes, stack %u\n", info.flat_entries,
