@@ -8,10 +8,12 @@
  * The oracle is a C++ restatement of the reference's Rust (browserdotsys/vecchio), function by
  * function, in oracle.cpp.  PARITY PINNING: the reference has no tests, golden vectors or
  * fixtures; rustc is absent so the reference cannot run here (no oracle/_ref).  The oracle is
- * pinned by (i) the analytic known-answer vectors derived from the cited formulas and (ii) the
- * reference's published Cornell render sample/therestofyourlife.png (region means, see
- * tests/golden/).  By the task's rule this is "parity unpinned" by reference tests; it is
- * pinned only by the sample image and the source.
+ * pinned by (i) the analytic known-answer vectors derived from the cited formulas, (ii) second,
+ * independent numpy restatements of its trickier functions (tests/test_oracle.py), (iii) closed
+ * forms of ray_color in a furnace scene, and (iv) region means of the three renders the reference
+ * publishes, sample/{therestofyourlife,thenextweek,inoneweekend}.png (tests/golden/).  By the
+ * task's rule this is "parity unpinned" by reference tests; it is pinned only by those images
+ * and the source.
  */
 #ifndef VECCHIO_ORACLE_H
 #define VECCHIO_ORACLE_H
