@@ -1324,6 +1324,36 @@ int orc_kat(const orc_scene* s, const char* name, const float* in, int n_in, flo
     } else if (k == "cosine_pdf_value" && n_in >= 6 && n_out >= 1) {
         out[0] = CosinePDF(v3(0)).value(v3(3));
         ret = 1;
+    } else if (k == "material_scatter" && n_in >= 19 && n_out >= 12) {
+        // type(0 Lambertian 1 Metal 2 Dielectric 4 Isotropic) albedo3 param | ray o3 d3 time | hit p3 n3 front  ->
+        // n_out/12 draws of scatter_with_pdf: {scattered?, specular?, ray o3 d3 time, attenuation3, pdf.value(d) or 0}
+        auto tex = std::make_shared<SolidColor>(v3(1));
+        Arc<Material> m;
+        const int type = (int)in[0];
+        if (type == 0) { auto x = std::make_shared<Lambertian>(); x->albedo = tex; m = x; }
+        else if (type == 1) { auto x = std::make_shared<Metal>(); x->albedo = tex; x->fuzz = in[4]; m = x; }
+        else if (type == 2) { auto x = std::make_shared<Dielectric>(); x->ref_idx = in[4]; m = x; }
+        else if (type == 4) { auto x = std::make_shared<Isotropic>(); x->albedo = tex; m = x; }
+        if (m) {
+            Ray r(v3(5), v3(8), in[11]);
+            HitRec rec(v3(12), v3(15), 1.0f, 0.0f, 0.0f, in[18] != 0.0f, m);
+            Vec3 probe = v3(19 <= n_in - 3 ? 19 : 15); // direction at which the returned pdf is evaluated (default: the normal)
+            ret = 0;
+            for (int i = 0; i + 12 <= n_out; i += 12, ret += 12) {
+                float* o = out + i;
+                for (int j = 0; j < 12; j++) o[j] = 0.0f;
+                auto srec = m->scatter_with_pdf(r, rec);
+                if (!srec) continue;
+                o[0] = 1.0f;
+                if (srec->specular_ray) {
+                    o[1] = 1.0f;
+                    put3(i + 2, srec->specular_ray->origin); put3(i + 5, srec->specular_ray->direction);
+                    o[8] = srec->specular_ray->time;
+                } else
+                    o[8] = srec->pdf->value(probe);
+                put3(i + 9, srec->attenuation);
+            }
+        }
     } else if (k == "sphere_pdf_value" && n_in >= 10 && n_out >= 1) { // c3 r o3 d3
         Sphere sp;
         sp.center = v3(0);

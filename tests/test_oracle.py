@@ -94,6 +94,61 @@ def test_box_light_sampling_kat(po):  # Boxy::pdf_value / random src/hittable.rs
         assert abs(f.mean() - 1 / 3) < 0.08
 
 
+def _scatter(po, mtype, albedo, param, o, d, time, p, n, front, draws=1, probe=None):
+    vals = [mtype, *albedo, param, *o, *d, time, *p, *n, 1.0 if front else 0.0] + (list(probe) if probe is not None else [])
+    return np.array(po.kat("material_scatter", vals, 12 * draws)).reshape(draws, 12)
+
+
+def test_metal_scatter_with_pdf_kat(po):  # src/material.rs:134-141 (Q6)
+    alb, n = (0.8, 0.6, 0.2), (0, 1, 0)
+    r = _scatter(po, 1, alb, 0.0, (0, 1, 0), (2.5, -2.5, 0), 0.7, (1, 0, 0), n, True)[0]
+    assert r[0] == 1 and r[1] == 1 and np.allclose(r[2:5], (1, 0, 0))
+    assert np.allclose(r[5:8], (np.sqrt(0.5), np.sqrt(0.5), 0), atol=1e-6)  # reflect(unit(d), n): the unit vector is reflected
+    assert r[8] == 0.0                                                      # Ray::new, not new_with_time: the ray's time is lost
+    assert np.allclose(r[9:12], alb)
+    # fuzz 0.5 at grazing incidence: a good share of the rays point into the surface, and all are returned
+    d = np.array([1.0, -0.05, 0.0])
+    refl = d / np.linalg.norm(d) * np.array([1, -1, 1])
+    rr = _scatter(po, 1, alb, 0.5, (0, 1, 0), d, 0.7, (1, 0, 0), n, True, draws=400)
+    assert np.all(rr[:, 0] == 1) and np.all(rr[:, 1] == 1)
+    off = rr[:, 5:8] - refl
+    assert np.all(np.linalg.norm(off, axis=1) < 0.5 + 1e-6) and np.linalg.norm(off, axis=1).max() > 0.4
+    below = (rr[:, 5:8] @ np.array(n)) < 0
+    assert 0.2 < below.mean() < 0.6
+
+
+def test_dielectric_scatter_with_pdf_kat(po):  # src/material.rs:177-206 (Q7)
+    n = (0, 1, 0)
+    # normal incidence from outside: eta = 1/1.5, reflect with probability schlick(1, eta) = 0.04, else straight through
+    r = _scatter(po, 2, (0, 0, 0), 1.5, (0, 1, 0), (0, -3, 0), 0.7, (0, 0, 0), n, True, draws=3000)
+    assert np.all(r[:, 0] == 1) and np.all(r[:, 1] == 1) and np.all(r[:, 8] == np.float32(0.7)) and np.allclose(r[:, 9:12], 1.0)
+    up = r[:, 6] > 0
+    assert np.allclose(r[up, 5:8], (0, 1, 0), atol=1e-6) and np.allclose(r[~up, 5:8], (0, -1, 0), atol=1e-6)
+    assert abs(up.mean() - 0.04) < 4 * np.sqrt(0.04 * 0.96 / 3000)
+    # 60 degrees from the normal: cos = 0.5; schlick is handed eta (0.6667) as its "index": 0.04 + 0.96 * 0.5^5 = 0.07
+    d = np.array([np.sqrt(0.75), -0.5, 0.0])
+    r = _scatter(po, 2, (0, 0, 0), 1.5, (0, 1, 0), d * 2, 0.1, (0, 0, 0), n, True, draws=3000)
+    up = r[:, 6] > 0
+    assert abs(up.mean() - 0.07) < 4 * np.sqrt(0.07 * 0.93 / 3000)
+    sin_t = np.sqrt(0.75) / 1.5  # Snell
+    assert np.allclose(r[~up, 5:8], (sin_t, -np.sqrt(1 - sin_t * sin_t), 0), atol=1e-5)
+    assert np.allclose(r[up, 5:8], (d[0], 0.5, 0), atol=1e-6)
+    # from inside (front = false, eta = 1.5) at a grazing angle: total internal reflection, no random draw
+    d = np.array([1.0, -0.2, 0.0])
+    d /= np.linalg.norm(d)
+    r = _scatter(po, 2, (0, 0, 0), 1.5, (0, 1, 0), d * 0.3, 0.25, (0, 0, 0), n, False, draws=50)
+    assert np.allclose(r[:, 5:8], (d[0], -d[1], 0), atol=1e-6) and np.all(r[:, 8] == 0.25)
+
+
+def test_diffuse_scatter_with_pdf_kat(po):  # Lambertian src/material.rs:92-98, Isotropic :448-454
+    for mtype, n in ((0, (0, 1, 0)), (4, (1, 0, 0))):  # the medium's record carries the dummy normal (1,0,0) (Q8)
+        for probe in ((0.0, 2.0, 0.0), (1.0, 1.0, 0.0), (3.0, 0.0, 0.0), (-1.0, -1.0, 0.0)):
+            r = _scatter(po, mtype, (0.3, 0.5, 0.7), 0.0, (0, 1, 0), (1, -1, 0), 0.4, (0, 0, 0), n, True, probe=probe)[0]
+            cos = np.dot(probe, n) / np.linalg.norm(probe)
+            assert r[0] == 1 and r[1] == 0 and np.allclose(r[9:12], (0.3, 0.5, 0.7))
+            assert np.isclose(r[8], max(cos, 0.0) / np.pi, atol=1e-7)  # CosinePDF(rec.normal).value: src/util.rs:127-136
+
+
 def test_aabb_kat(po):  # AxisBB::hit src/accel.rs:16-35 incl. the inf / NaN slab cases
     box = [0, 0, 0, 1, 1, 1]
     assert po.kat("aabb_hit", box + [-1, .5, .5, 1, 0, 0, 0.001, INF], 1)[0] == 1
