@@ -7,6 +7,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       := /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 TUNE      ?=
+WQ_SIMPLE ?=
 NVFLAGS   := $(TUNE) $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
 CXXFLAGS  := -std=c++17 -O3 -fPIC -ffp-contract=off -Wall -Wextra
 LIBDIR    := vecchio_b200/lib
@@ -47,12 +48,19 @@ $(CSRC)/vk_staged_simple.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVK_SIMPLE=1 -DVKS_N=768 -DVKS_K=3 -DVKS_MINB=4 -c -o $@ $< 2> $(CSRC)/ptxas_staged_simple.log || (cat $(CSRC)/ptxas_staged_simple.log; false)
 $(CSRC)/vk_staged_strict.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_staged_strict.log || (cat $(CSRC)/ptxas_staged_strict.log; false)
+# the warp-queue kernel: 128 registers, 4 warps x 192 slots per CTA, 4 CTAs per SM
+$(CSRC)/vk_warpq_fast.o: $(CSRC)/vk_warpq.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_warpq_fast.log || (cat $(CSRC)/ptxas_warpq_fast.log; false)
+$(CSRC)/vk_warpq_simple.o: $(CSRC)/vk_warpq.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVK_SIMPLE=1 $(WQ_SIMPLE) -c -o $@ $< 2> $(CSRC)/ptxas_warpq_simple.log || (cat $(CSRC)/ptxas_warpq_simple.log; false)
+$(CSRC)/vk_warpq_strict.o: $(CSRC)/vk_warpq.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_warpq_strict.log || (cat $(CSRC)/ptxas_warpq_strict.log; false)
 $(CSRC)/vk_api.o: $(CSRC)/vk_api.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 $(CSRC)/vk_relayout.o: $(CSRC)/vk_relayout.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o
+$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o $(CSRC)/vk_warpq_fast.o $(CSRC)/vk_warpq_strict.o $(CSRC)/vk_warpq_simple.o
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 

@@ -33,7 +33,7 @@ struct vk_ctx {
     bool simple_scene = false; // only what the VK_SIMPLE build of the staged kernel keeps (see vk_device.cuh)
     unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
-    float* partial = nullptr;               // chunk partial sums (sum | sumsq)
+    float* partial = nullptr;               // accumulators: W*H*3 x u64 fixed-point sums | W*H*3 x double sums of squares
     size_t partial_floats = 0;
     float* frame = nullptr; // vk_render staging: sum | sumsq | rgb
     size_t frame_floats = 0;
@@ -43,7 +43,6 @@ struct vk_ctx {
     // host's termination checks
     WfState wf{};
     void* wf_block = nullptr;
-    bool wf_has_sumsq = false;
     uint32_t* wf_host_counts = nullptr;
 };
 
@@ -65,12 +64,13 @@ static int fail(vk_ctx* c, int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------
 // small kernels that do not depend on the math mode
 // ------------------------------------------------------------------------------------------------
-__global__ void k_reduce_chunks(const float* __restrict__ partial, uint32_t n_chunks, size_t n, float* __restrict__ out) {
+// fixed-point accumulators -> fp32 per-pixel sums (the buffers the NCCL reduce combines)
+__global__ void k_acc_to_sum(const unsigned long long* __restrict__ acc, const double* __restrict__ accsq, size_t n,
+                             float* __restrict__ sum, float* __restrict__ sumsq) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float acc = partial[i];
-    for (uint32_t c = 1; c < n_chunks; ++c) acc += partial[(size_t)c * n + i]; // fixed order: deterministic
-    out[i] = acc;
+    sum[i] = (float)((double)(long long)acc[i] * VK_ACC_INV_SCALE);
+    if (sumsq) sumsq[i] = (float)accsq[i];
 }
 __global__ void k_finalize(const float* __restrict__ sum, float* __restrict__ rgb, size_t n, float spp) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,20 +306,20 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
 extern "C" int vk_flush_stats(vk_ctx* c, vk_stats* stats);
 
 // Slot pool of the wavefront variant.  One allocation, carved into the arrays of WfState.  Default
-// 2^19 slots: 96 B (112 B with sum of squares) per slot = 50 MB, resident in the 126 MB L2, and
+// 2^19 slots: 96 B per slot = 50 MB, resident in the 126 MB L2, and
 // 3-4 full waves of 256-thread CTAs per launch.  VECCHIO_WF_SLOTS overrides (tuning sweeps).
-static int wf_ensure(vk_ctx* c, bool want_sumsq) {
+static int wf_ensure(vk_ctx* c) {
     uint32_t n = 1u << 19;
     if (const char* e = std::getenv("VECCHIO_WF_SLOTS")) {
         const long v = std::atol(e);
         if (v >= 1024 && v <= (1l << 26)) n = (uint32_t)v;
     }
     n = (n + 255u) & ~255u;
-    if (c->wf_block && c->wf.n_slots == n && (c->wf_has_sumsq || !want_sumsq)) return VK_OK;
+    if (c->wf_block && c->wf.n_slots == n) return VK_OK;
     if (c->wf_block) cudaFree(c->wf_block);
     c->wf_block = nullptr;
     c->wf = WfState{};
-    const size_t per_slot = 16 * (6 + (want_sumsq ? 1 : 0)) + 4 * VKW_CLASSES;
+    const size_t per_slot = 16 * 5 + 4 * VKW_CLASSES;
     const size_t tail = 256; // qcount (2 sets) + unit_head
     CU(c, cudaMalloc(&c->wf_block, per_slot * n + tail));
     char* p = (char*)c->wf_block;
@@ -328,14 +328,11 @@ static int wf_ensure(vk_ctx* c, bool want_sumsq) {
     c->wf.ray_d = (float4*)take(16ull * n);
     c->wf.beta = (float4*)take(16ull * n);
     c->wf.unit = (uint4*)take(16ull * n);
-    c->wf.sum = (float4*)take(16ull * n);
     c->wf.hit = (uint4*)take(16ull * n);
-    c->wf.sumsq = want_sumsq ? (float4*)take(16ull * n) : nullptr;
     c->wf.queue = (uint32_t*)take(4ull * VKW_CLASSES * n);
     c->wf.qcount = (uint32_t*)take(64);
     c->wf.unit_head = (unsigned long long*)take(64);
     c->wf.n_slots = n;
-    c->wf_has_sumsq = want_sumsq;
     if (!c->wf_host_counts) CU(c, cudaMallocHost((void**)&c->wf_host_counts, 64));
     return VK_OK;
 }
@@ -344,13 +341,12 @@ static int wf_ensure(vk_ctx* c, bool want_sumsq) {
 // launches iterations in batches and reads the queue counters of the last extend after each batch
 // (one 32-byte D2H + stream sync); an iteration on a drained pool is two empty launches.
 static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCamera& dc, const RenderArgs& a, const RenderBuffers& b,
-                     bool want_sumsq, uint32_t* launches) {
-    int rc = wf_ensure(c, want_sumsq);
+                     uint32_t* launches) {
+    int rc = wf_ensure(c);
     if (rc != VK_OK) return rc;
     WfState w = c->wf;
-    if (!want_sumsq) w.sumsq = nullptr;
     w.n_pixels = a.width * a.height;
-    w.n_units = (unsigned long long)w.n_pixels * a.n_planes;
+    w.n_units = (unsigned long long)w.n_pixels * a.spp_count;
     const unsigned long long head0 = w.n_units < w.n_slots ? w.n_units : w.n_slots;
     CU(c, cudaMemsetAsync(w.qcount, 0, 64, c->stream));
     CU(c, cudaMemcpyAsync(w.unit_head, &head0, sizeof(head0), cudaMemcpyHostToDevice, c->stream));
@@ -393,7 +389,11 @@ static uint32_t choose_variant(const vk_ctx* c, const vk_render_params* P) {
     const bool flat = c->flat.n && !(P->flags & VK_FLAG_FORCE_BVH);
     // (a hybrid program holds subtrees whose traversal lengths vary: the lane megakernel, not the
     // barrier-synchronised staged kernel, runs it)
-    return flat && c->flat.n_bvh == 0 ? (uint32_t)VK_VARIANT_STAGED : (uint32_t)VK_VARIANT_MEGAKERNEL;
+    const char* e = std::getenv("VECCHIO_AUTO"); // tuning sweeps: staged | warpq | mega
+    if (e && !std::strcmp(e, "staged")) return flat && c->flat.n_bvh == 0 ? (uint32_t)VK_VARIANT_STAGED : (uint32_t)VK_VARIANT_MEGAKERNEL;
+    if (e && !std::strcmp(e, "warpq")) return (uint32_t)VK_VARIANT_WARPQ;
+    if (e && !std::strcmp(e, "mega")) return (uint32_t)VK_VARIANT_MEGAKERNEL;
+    return flat && c->flat.n_bvh == 0 ? (uint32_t)VK_VARIANT_WARPQ : (uint32_t)VK_VARIANT_MEGAKERNEL;
 }
 
 // Lane megakernel for a BVH scene: static (one whole ray per lane and loop iteration) or dynamic
@@ -420,7 +420,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     const uint32_t count = P->spp_count ? P->spp_count : P->spp - P->spp_begin;
     if ((uint64_t)P->spp_begin + count > P->spp) return fail(c, VK_ERR_INVALID, "render: sample slice exceeds spp");
     if ((uint64_t)P->width * P->height > 0x7FFFFFFFull / 3) return fail(c, VK_ERR_INVALID, "render: image too large");
-    if (P->variant > VK_VARIANT_STAGED) return fail(c, VK_ERR_INVALID, "render: unknown variant");
+    if (P->variant > VK_VARIANT_WARPQ) return fail(c, VK_ERR_INVALID, "render: unknown variant");
     if (!(cam->time0 < cam->time1)) return fail(c, VK_ERR_INVALID, "render: camera time0 >= time1 (gen_range panics, src/main.rs:118)");
     CU(c, cudaSetDevice(c->device));
     const bool strict = (P->flags & VK_FLAG_STRICT_MATH) != 0;
@@ -450,64 +450,44 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     a.flags = P->flags;
     a.tiles_x = (P->width + 7) / 8;
     a.tiles_y = (P->height + 3) / 4;
-    // Sample blocks ("units") and their planes of partial sums.  A unit's samples are traced one after
-    // the other by whoever owns the unit, so a unit of k samples on a pixel whose paths run to
-    // max_depth holds a lane for k * max_depth segments while the rest of the GPU has drained
-    // (measured: 8-sample units cost Cornell a 2.8 ms tail, 523 iterations in the slowest CTA).
-    // HBM is cheap here: one plane per SAMPLE when that fits the plane budget (default 6 GiB:
-    // Cornell 600x600x1000 = 4.3 GB of planes, written once with plain stores and summed in order by
-    // k_reduce_chunks at HBM speed), otherwise the smallest block that fits.  The block size depends
-    // only on the call's parameters, so a render is bit-identical per (seed, spp slice, size).
+    // Accumulators (see RenderBuffers): u64 fixed-point sums, plus double sums of squares when asked for.
     const size_t plane = (size_t)P->width * P->height * 3;
     RenderBuffers b{};
     b.counters = c->counters;
     b.debug = c->debug;
     {
-        size_t budget = 6ull << 30;
-        if (const char* e = std::getenv("VECCHIO_PLANE_BUDGET_MB")) {
-            const long v = std::atol(e);
-            if (v > 0) budget = (size_t)v << 20;
-        }
-        const size_t plane_bytes = plane * sizeof(float) * (d_sumsq ? 2 : 1);
-        size_t max_planes = budget / plane_bytes;
-        if (max_planes < 1) max_planes = 1;
-        for (;;) { // a device with less free memory than the budget gets fewer, larger blocks
-            a.unit_spp = (uint32_t)((count + max_planes - 1) / max_planes);
-            a.n_planes = (count + a.unit_spp - 1) / a.unit_spp;
-            if (a.n_planes == 1) {
-                b.partial_sum = d_sum;
-                b.partial_sumsq = d_sumsq;
-                break;
-            }
-            const int rc = ensure(c, &c->partial, &c->partial_floats, plane * a.n_planes * (d_sumsq ? 2 : 1));
-            if (rc == VK_OK) {
-                b.partial_sum = c->partial;
-                b.partial_sumsq = d_sumsq ? c->partial + plane * a.n_planes : nullptr;
-                break;
-            }
-            if (rc != VK_ERR_OOM) return rc;
-            cudaGetLastError(); // clear the allocation failure
-            max_planes = a.n_planes / 2;
-            if (max_planes < 1) max_planes = 1;
-        }
+        const int rc = ensure(c, &c->partial, &c->partial_floats, plane * (d_sumsq ? 4 : 2));
+        if (rc != VK_OK) return rc;
+        b.acc = (unsigned long long*)c->partial;
+        b.accsq = d_sumsq ? (double*)(c->partial + plane * 2) : nullptr;
+        CU(c, cudaMemsetAsync(c->partial, 0, plane * (d_sumsq ? 4 : 2) * sizeof(float), c->stream));
     }
-    // Chunks of whole blocks, sized for ~48 work items per resident warp (small items keep the
-    // end-of-kernel tail short; an item costs one atomic).
+    // Lane megakernel: chunks of samples, sized for ~48 work items per resident warp (small items keep
+    // the end-of-kernel tail short; an item costs one atomic).
     const uint32_t n_tiles = a.tiles_x * a.tiles_y;
     uint32_t n_chunks = (48u * resident_warps + n_tiles - 1) / n_tiles;
-    if (n_chunks > a.n_planes) n_chunks = a.n_planes;
+    if (n_chunks > count) n_chunks = count;
     if (n_chunks < 1) n_chunks = 1;
-    const uint32_t planes_per_chunk = (a.n_planes + n_chunks - 1) / n_chunks;
-    a.chunk_spp = planes_per_chunk * a.unit_spp;
+    a.chunk_spp = (count + n_chunks - 1) / n_chunks;
     a.n_chunks = (count + a.chunk_spp - 1) / a.chunk_spp;
 
     CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // work-queue head only
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
     uint32_t launches = 0;
-    const uint32_t variant = legacy ? (uint32_t)VK_VARIANT_MEGAKERNEL : choose_variant(c, P); // legacy: lane megakernel only
-    if (variant == VK_VARIANT_WAVEFRONT) {
-        int rc = wf_render(c, strict, flat, dc, a, b, d_sumsq != nullptr, &launches);
+    uint32_t variant = choose_variant(c, P);
+    if (legacy && variant != VK_VARIANT_WARPQ) variant = VK_VARIANT_MEGAKERNEL; // legacy integrator: lane megakernel and warp queues
+    if (variant == VK_VARIANT_WARPQ) {
+        CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
+        // (the K-ray flat trace has no subtree entries: a hybrid program means the BVH path)
+        const FlatProgram* sflat = flat && flat->n_bvh == 0 ? flat : nullptr;
+        const bool simple = !strict && !legacy && sflat && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");
+        CU(c, strict   ? vkstrict::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream)
+              : simple ? vkfast_simple::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream)
+                       : vkfast::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream));
+        launches = 1;
+    } else if (variant == VK_VARIANT_WAVEFRONT) {
+        int rc = wf_render(c, strict, flat, dc, a, b, &launches);
         if (rc != VK_OK) return rc;
     } else if (variant == VK_VARIANT_STAGED) {
         CU(c, cudaMemsetAsync(c->counters + 5, 0xFF, 2 * sizeof(unsigned long long), c->stream)); // CTA start / first end: minima
@@ -531,16 +511,9 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
                      : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, legacy, c->stream));
         launches = 1;
     }
-    if (a.n_planes > 1) {
-        const unsigned g = (unsigned)((plane + 255) / 256);
-        k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sum, a.n_planes, plane, d_sum);
-        ++launches;
-        if (d_sumsq) {
-            k_reduce_chunks<<<g, 256, 0, c->stream>>>(b.partial_sumsq, a.n_planes, plane, d_sumsq);
-            ++launches;
-        }
-        CU(c, cudaGetLastError());
-    }
+    k_acc_to_sum<<<(unsigned)((plane + 255) / 256), 256, 0, c->stream>>>(b.acc, b.accsq, plane, d_sum, d_sumsq);
+    ++launches;
+    CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->ev1, c->stream));
     c->launches += launches;
     c->paths += (uint64_t)P->width * P->height * count;

@@ -1337,6 +1337,23 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     return true;
 }
 
+// Sample end (src/main.rs:191-194, `c += color` for a finite sample): three integer atomics into the pixel's
+// fixed-point sums (see RenderBuffers), which makes the frame independent of who adds what when.  A zero
+// component adds nothing and is skipped (most paths end on weight 0 or on a black miss).
+VKD void accumulate_sample(const RenderBuffers& buf, uint32_t pixel, float3 L) {
+    unsigned long long* p = buf.acc + (size_t)pixel * 3u;
+    const float lim = 4294967296.0f; // 2^32 * 2^30 fits the 64-bit accumulator
+    if (L.x != 0.0f) atomicAdd(p + 0, (unsigned long long)__float2ll_rn(fminf(fmaxf(L.x, -lim), lim) * VK_ACC_SCALE));
+    if (L.y != 0.0f) atomicAdd(p + 1, (unsigned long long)__float2ll_rn(fminf(fmaxf(L.y, -lim), lim) * VK_ACC_SCALE));
+    if (L.z != 0.0f) atomicAdd(p + 2, (unsigned long long)__float2ll_rn(fminf(fmaxf(L.z, -lim), lim) * VK_ACC_SCALE));
+    if (buf.accsq) {
+        double* q = buf.accsq + (size_t)pixel * 3u;
+        if (L.x != 0.0f) atomicAdd(q + 0, (double)L.x * (double)L.x);
+        if (L.y != 0.0f) atomicAdd(q + 1, (double)L.y * (double)L.y);
+        if (L.z != 0.0f) atomicAdd(q + 2, (double)L.z * (double)L.z);
+    }
+}
+
 // A ray that leaves the scene: the constant background of src/main.rs:124,151, or with
 // VK_FLAG_SKY_BACKGROUND the book-1 sky (1-t)*white + t*(0.5,0.7,1.0), t = 0.5*(unit(d).y + 1).
 VKD float3 miss_color(const RenderArgs& a, float3 d) {

@@ -141,16 +141,24 @@ struct RenderArgs {
     uint32_t seed_lo, seed_hi;
     float3 background;
     uint32_t flags; // VK_FLAG_* of the call (sky background)
-    // work decomposition (vk_api.cu decides): warp items = 8x4 pixel tiles x sample chunks; inside
-    // an item the lanes share (pixel, block of unit_spp samples) units; one partial plane per block
-    uint32_t tiles_x, tiles_y, n_chunks, chunk_spp, unit_spp, n_planes;
+    // work decomposition of the lane megakernel (vk_api.cu decides): warp items = 8x4 pixel tiles x
+    // chunks of chunk_spp samples; inside an item the lanes draw (pixel, sample) units
+    uint32_t tiles_x, tiles_y, n_chunks, chunk_spp;
 };
 
-// counters[0] = rays, [1] = dropped samples, [2] = work-queue head, [3] = node visits, [4] = primitive tests,
-// [5] = unit head of the staged kernel
+// Accumulation.  Every finished sample is added to its pixel with three 64-bit integer atomics
+// (fixed point, VK_ACC_SCALE = 2^30 units per 1.0): integer addition is associative, so the frame is
+// bit-identical for a (seed, sample range, image size) whatever the kernel variant, the scheduling of
+// paths onto lanes, the grid or the number of GPUs that rendered other sample ranges -- and no lane
+// has to own a pixel's samples in order (round 1 spent one fp32 plane per sample, 4.3 GB per Cornell
+// frame, to get the same property).  Range +-2^33 per pixel and channel, resolution 9.3e-10; a sample
+// is clamped to +-2^32 before conversion.  The sums of squares (tests only) are double atomics.
+// counters[0] = rays, [1] = dropped samples, [2] = work-queue head, [3] = node visits, [4] = primitive tests
+#define VK_ACC_SCALE 1073741824.0f
+#define VK_ACC_INV_SCALE (1.0 / 1073741824.0)
 struct RenderBuffers {
-    float* partial_sum;   // n_planes x W*H*3 (== d_sum when n_planes == 1)
-    float* partial_sumsq; // same, nullable
+    unsigned long long* acc; // W*H*3 fixed-point sums (two's complement)
+    double* accsq;           // W*H*3 sums of squares, nullable
     unsigned long long* counters;
     unsigned long long* debug; // VK_DEBUG_CTAS x {end time ns, rays traced, smid, -} of the staged kernel's CTAs
 };
@@ -166,18 +174,16 @@ struct RenderBuffers {
 //   shade     k_wf_shade     walks the queues class by class, so a warp shades one kind of material:
 //                            scatter + PDF sampling, or sample end -> accumulate -> next sample / next
 //                            unit (regeneration in place: the pool stays full until units run out)
-// A slot sums the samples of its unit in order and stores the unit's partial sum to the plane of
-// its sample block, exactly like a lane of the megakernel: both variants produce the same image
-// for a seed.  float4 / uint4 arrays: every access is one fully coalesced 16 B per lane.
+// A finished sample goes into its pixel's integer accumulators, exactly like a lane of the megakernel:
+// both variants produce the same image for a seed.  float4 / uint4 arrays: every access is one fully
+// coalesced 16 B per lane.
 // ------------------------------------------------------------------------------------------------
 enum { VKW_TERMINATE = 0, VKW_DIELECTRIC = 1, VKW_METAL = 2, VKW_DIFFUSE = 3, VKW_CLASSES = 4 };
 struct WfState {
     float4* ray_o;  // origin.xyz, time
     float4* ray_d;  // direction.xyz, bits: depth of the segment to trace (0 = slot idle)
     float4* beta;   // path weight.xyz, bits: global index of the current sample
-    uint4* unit;    // pixel, s_end (one past the unit's last sample), plane, -
-    float4* sum;    // partial sum of the unit's finished samples
-    float4* sumsq;  // same for squares; nullptr when not wanted
+    uint4* unit;    // pixel, -, -, -
     uint4* hit;     // t bits, primitive, instance, face
     uint32_t* queue;    // VKW_CLASSES x n_slots slot indices
     uint32_t* qcount;   // 2 sets x VKW_CLASSES counters (set = iteration parity)
@@ -199,6 +205,9 @@ struct WfState {
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
     cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,      \
                               const RenderBuffers& b, unsigned long long* unit_head, int sm_count, cudaStream_t st);   \
+    cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,       \
+                             const RenderBuffers& b, unsigned long long* unit_head, int sm_count, bool legacy,         \
+                             cudaStream_t st);                                                                         \
     cudaError_t launch_wf_generate(const DCamera& cam, const RenderArgs& a, const WfState& w, cudaStream_t st);        \
     cudaError_t launch_wf_extend(const DScene& sc, const FlatProgram* flat, const RenderArgs& a, const WfState& w,     \
                                  const RenderBuffers& b, uint32_t set, cudaStream_t st);                               \
@@ -207,7 +216,9 @@ struct WfState {
     }
 VK_DECLARE_LAUNCHERS(vkfast)
 VK_DECLARE_LAUNCHERS(vkstrict)
-namespace vkfast_simple { // vk_staged.cu compiled with VK_SIMPLE=1: staged kernel for "simple" flat scenes (see vk_device.cuh)
+namespace vkfast_simple { // vk_staged.cu / vk_warpq.cu compiled with VK_SIMPLE=1: kernels for "simple" flat scenes (see vk_device.cuh)
 cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
                           unsigned long long* unit_head, int sm_count, cudaStream_t st);
+cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
+                         unsigned long long* unit_head, int sm_count, bool legacy, cudaStream_t st);
 }

@@ -24,12 +24,10 @@ namespace VK_NS {
 
 // Work decomposition (deterministic for a seed whatever the grid):
 //   item  = one 8x4 pixel tile x one chunk of samples, fetched by a whole warp from a global queue;
-//   unit  = one pixel of the tile x one BLOCK of `unit_spp` consecutive samples.  The 32 lanes of
-//           the warp draw units from a warp-local counter (ballot + popc, no memory traffic): a
-//           lane whose unit is finished takes the next one, so lanes only idle for the last unit
-//           of an item instead of waiting for the slowest pixel of a whole chunk.
-// A unit's samples are summed in order by one lane and stored to its own plane of the partial
-// buffer (plane = global sample-block index); k_reduce_planes adds the planes in order.
+//   unit  = one pixel of the tile x one sample.  The 32 lanes of the warp draw units from a
+//           warp-local counter (ballot + popc, no memory traffic): a lane whose path has ended takes
+//           the next one, so lanes only idle for the last unit of an item.
+// A finished sample goes straight into its pixel's integer accumulators (accumulate_sample).
 template <bool FLAT, bool MEDIA, bool LEGACY>
 VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,
                          const RenderBuffers& buf) {
@@ -37,7 +35,6 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
     const uint32_t lanes_below = (1u << lane) - 1u;
     const uint32_t n_tiles = a.tiles_x * a.tiles_y;
     const uint32_t total = n_tiles * a.n_chunks;
-    const size_t plane = (size_t)a.width * a.height * 3u;
     const uint32_t spp_end = a.spp_begin + a.spp_count;
     uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0; // per lane: far below 2^32 for any frame
 
@@ -49,37 +46,24 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
         if (item >= total) break;
         const uint32_t chunk = item / n_tiles, tile = item - chunk * n_tiles;
         const uint32_t px0 = (tile % a.tiles_x) * 8u, py0 = (tile / a.tiles_x) * 4u;
-        const uint32_t c0 = a.spp_begin + chunk * a.chunk_spp;     // chunk_spp is a multiple of unit_spp
+        const uint32_t c0 = a.spp_begin + chunk * a.chunk_spp;
         const uint32_t c1 = min(c0 + a.chunk_spp, spp_end);
-        const uint32_t n_units = ((c1 - c0 + a.unit_spp - 1u) / a.unit_spp) * 32u;
+        const uint32_t n_units = (c1 - c0) * 32u;
         uint32_t next_unit = 0; // warp-uniform
 
         PathRng rng;
         rng.pixel = 0;
         rng.sample = 0;
         rng.key = make_uint2(a.seed_lo, a.seed_hi);
-        float3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = f3(0.0f, 0.0f, 0.0f);
         float3 o = f3(0.0f, 0.0f, 0.0f), d = o, beta = o, L = o;
         float time = 0.0f;
-        uint32_t depth = 0, s = 0, s_end = 0, px = 0, py = 0, unit_plane = 0;
+        uint32_t depth = 0, s = 0, s_end = 0, px = 0, py = 0;
         bool alive = false, valid = true, has_unit = false;
 #pragma unroll 1
         for (;;) {
             // ---- unit bookkeeping (warp-synchronous: every lane is here with the full mask) ----
             const bool need = !alive && !(has_unit && s < s_end);
-            if (need && has_unit) { // unit finished: its sample-block sum goes to its own plane
-                float* ps = buf.partial_sum + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
-                ps[0] = sum.x;
-                ps[1] = sum.y;
-                ps[2] = sum.z;
-                if (buf.partial_sumsq) {
-                    float* pq = buf.partial_sumsq + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
-                    pq[0] = sumsq.x;
-                    pq[1] = sumsq.y;
-                    pq[2] = sumsq.z;
-                }
-                has_unit = false;
-            }
+            if (need) has_unit = false;
             const uint32_t want = __ballot_sync(0xFFFFFFFFu, need);
             if (need) {
                 const uint32_t u = next_unit + __popc(want & lanes_below);
@@ -87,13 +71,9 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
                     px = px0 + (u & 7u);
                     py = py0 + ((u >> 3) & 3u);
                     if (px < a.width && py < a.height) { // ragged tiles: a unit outside the image is void
-                        const uint32_t b = u >> 5;
-                        s = c0 + b * a.unit_spp;
-                        s_end = min(s + a.unit_spp, c1);
-                        unit_plane = (s - a.spp_begin) / a.unit_spp;
+                        s = c0 + (u >> 5);
+                        s_end = s + 1u;
                         rng.pixel = py * a.width + px; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
-                        sum = f3(0.0f, 0.0f, 0.0f);
-                        sumsq = f3(0.0f, 0.0f, 0.0f);
                         has_unit = true;
                     }
                 }
@@ -142,12 +122,8 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
                 }
             }
             if (!alive) { // sample finished: NaN/Inf filter of src/main.rs:191-194
-                if (valid && finite3(L)) {
-                    sum = sum + L;
-                    sumsq = sumsq + L * L;
-                } else {
-                    ++n_drop;
-                }
+                if (valid && finite3(L)) accumulate_sample(buf, rng.pixel, L);
+                else ++n_drop;
             }
         }
     }
@@ -182,8 +158,8 @@ VKD void megakernel_body(const DScene& sc, const FlatProgram* flat, const DCamer
 //              work, the warp leaves the loop; idle lanes shade their hit (src/main.rs:131-149),
 //              start their next segment, sample or unit, and join the traversal again.
 //
-// Units (pixel, sample block) come from one global queue, one atomic per re-fill and warp; a lane
-// sums its unit's samples in order, so the image is the same as every other variant's.
+// Units (pixel, sample) come from one global queue, one atomic per re-fill and warp; finished samples
+// go into the pixel's integer accumulators, so the image is the same as every other variant's.
 #ifndef VK_DYN_MIN_ACTIVE
 #define VK_DYN_MIN_ACTIVE 16
 #endif
@@ -195,9 +171,7 @@ VKD void megakernel_dyn_body(const DScene& sc, const DCamera& cam, const RenderA
                              unsigned long long* unit_head) {
     const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
     const uint32_t n_pixels = a.width * a.height;
-    const unsigned long long n_units = (unsigned long long)n_pixels * a.n_planes;
-    const size_t plane = (size_t)n_pixels * 3u;
-    const uint32_t spp_end = a.spp_begin + a.spp_count;
+    const unsigned long long n_units = (unsigned long long)n_pixels * a.spp_count;
     uint32_t n_rays = 0, n_drop = 0;
     TraceCounters tc = {0u, 0u};
 
@@ -205,16 +179,16 @@ VKD void megakernel_dyn_body(const DScene& sc, const DCamera& cam, const RenderA
     rng.pixel = 0;
     rng.sample = 0;
     rng.key = make_uint2(a.seed_lo, a.seed_hi);
-    float3 sum = f3(0.0f, 0.0f, 0.0f), sumsq = sum, o = sum, d = sum, beta = sum;
+    float3 zero3 = f3(0.0f, 0.0f, 0.0f), o = zero3, d = zero3, beta = zero3;
     float time = 0.0f;
-    uint32_t depth = 0, s = 0, s_end = 0, unit_plane = 0;
-    bool has_unit = false, exhausted = false, pending = false; // pending: traversal finished, hit not shaded yet
+    uint32_t depth = 0;
+    bool exhausted = false, pending = false; // pending: traversal finished, hit not shaded yet
     Trav T;
     T.ref = VKD_DONE;
     T.sp = 0;
     T.enter = false;
     T.cur_inst = 0;
-    T.co = T.cd = T.cinv = sum;
+    T.co = T.cd = T.cinv = zero3;
     T.best.t = 0.0f;
     T.best.prim = VK_REF_NONE;
     T.best.inst = 0;
@@ -241,37 +215,12 @@ VKD void megakernel_dyn_body(const DScene& sc, const DCamera& cam, const RenderA
                     }
                 }
                 if (!alive) { // sample finished: NaN/Inf filter of src/main.rs:191-194
-                    if (valid && finite3(L)) {
-                        sum = sum + L;
-                        sumsq = sumsq + L * L;
-                    } else {
-                        ++n_drop;
-                    }
+                    if (valid && finite3(L)) accumulate_sample(buf, rng.pixel, L);
+                    else ++n_drop;
                 }
             }
             if (alive) new_ray = true;
-            else if (has_unit && s < s_end) { // the unit's next sample
-                rng.sample = s++;
-                camera_get_ray(cam, rng, rng.pixel % a.width, rng.pixel / a.width, a.width, a.height, o, d, time);
-                beta = f3(1.0f, 1.0f, 1.0f);
-                depth = 1; // ray_color(ray, .., 1) src/main.rs:190
-                new_ray = true;
-            } else {
-                if (has_unit) { // unit finished: its sample-block sum goes to its own plane
-                    float* ps = buf.partial_sum + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
-                    ps[0] = sum.x;
-                    ps[1] = sum.y;
-                    ps[2] = sum.z;
-                    if (buf.partial_sumsq) {
-                        float* pq = buf.partial_sumsq + (size_t)unit_plane * plane + (size_t)rng.pixel * 3u;
-                        pq[0] = sumsq.x;
-                        pq[1] = sumsq.y;
-                        pq[2] = sumsq.z;
-                    }
-                    has_unit = false;
-                }
-                need_unit = !exhausted;
-            }
+            else need_unit = !exhausted;
         }
         const uint32_t mu = __ballot_sync(0xFFFFFFFFu, need_unit);
         if (mu) { // one global atomic per warp and re-fill
@@ -281,14 +230,9 @@ VKD void megakernel_dyn_body(const DScene& sc, const DCamera& cam, const RenderA
             if (need_unit) {
                 const unsigned long long u = base + __popc(mu & lanes_below);
                 if (u < n_units) {
-                    unit_plane = (uint32_t)(u / n_pixels);
-                    rng.pixel = (uint32_t)(u - (unsigned long long)unit_plane * n_pixels); // i = y*width + x (src/main.rs:182-183)
-                    s = a.spp_begin + unit_plane * a.unit_spp;
-                    s_end = min(s + a.unit_spp, spp_end);
-                    sum = f3(0.0f, 0.0f, 0.0f);
-                    sumsq = f3(0.0f, 0.0f, 0.0f);
-                    has_unit = true;
-                    rng.sample = s++;
+                    const uint32_t sb = (uint32_t)(u / n_pixels);
+                    rng.pixel = (uint32_t)(u - (unsigned long long)sb * n_pixels); // i = y*width + x (src/main.rs:182-183)
+                    rng.sample = a.spp_begin + sb;
                     camera_get_ray(cam, rng, rng.pixel % a.width, rng.pixel / a.width, a.width, a.height, o, d, time);
                     beta = f3(1.0f, 1.0f, 1.0f);
                     depth = 1;

@@ -15,9 +15,8 @@
 //                   (src/main.rs:131-149); sample end: NaN filter and accumulate (:191-194), then
 //                   the next sample's camera ray in place (:187-190) -- the emitter/miss class
 //                   does this with full warps
-//   * a slot owns a (pixel, sample block) unit and adds its samples in order into the unit's plane
-//     (read-modify-write in L2: the location belongs to that slot alone), so the image is
-//     bit-identical to the other variants for a seed.
+//   * a slot owns a (pixel, sample) unit; the finished sample goes into the pixel's integer accumulators,
+//     so the image is bit-identical to the other variants for a seed.
 #include "vk_device.cuh"
 
 namespace VK_NS {
@@ -135,12 +134,12 @@ VKD void staged_take_units(const StagedCtx& C, bool want, uint32_t slot, uint32_
         y -= C.a.height;
         ++b;
     }
-    if (b >= C.a.n_planes) { // past the last unit: the queue is empty
+    if (b >= C.a.spp_count) { // past the last unit: the queue is empty
         C.S.rd[slot].w = __uint_as_float(0u);
         C.S.no_units = 1u;
         return;
     }
-    staged_begin_sample_xy(C, slot, x, y, C.a.spp_begin + b * C.a.unit_spp);
+    staged_begin_sample_xy(C, slot, x, y, C.a.spp_begin + b);
 }
 
 // The sort: one __match_any_sync groups the lanes of the warp by shading class; the first lane of each
@@ -160,9 +159,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
     extern __shared__ __align__(16) unsigned char vks_raw[];
     StagedShared& S = *reinterpret_cast<StagedShared*>(vks_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lanes_below = (1u << lane) - 1u;
-    const StagedCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.n_planes, unit_head};
-    const size_t plane = (size_t)C.n_pixels * 3u;
-    const uint32_t spp_end = a.spp_begin + a.spp_count;
+    const StagedCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head};
     uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0;
     uint32_t dbg_iters = 0, dbg_sparse = 0; // iterations run; iterations with fewer than N/8 live slots
 
@@ -311,33 +308,13 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                     S.ro[slot] = make_float4(o.x, o.y, o.z, time);
                     S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
                     S.bt[slot] = make_float4(beta.x, beta.y, beta.z, bt.w);
-                } else { // sample finished: NaN/Inf filter of src/main.rs:191-194, added in order into the unit's plane
-                    const uint32_t rel = sample - a.spp_begin, b = a.unit_spp == 1u ? rel : rel / a.unit_spp;
-                    const bool first = rel == b * a.unit_spp;
-                    const uint32_t s_end = min(a.spp_begin + (b + 1u) * a.unit_spp, spp_end);
+                } else { // sample finished: NaN/Inf filter of src/main.rs:191-194, into the pixel's integer accumulators
                     const bool keep = valid && finite3(L);
                     if (!keep) ++n_drop;
-                    float* ps = buf.partial_sum + (size_t)b * plane + (size_t)pixel * 3u;
-                    float3 acc = first ? f3(0.0f, 0.0f, 0.0f) : f3(ps[0], ps[1], ps[2]);
-                    if (keep) acc = acc + L;
-                    if (keep || first) {
-                        ps[0] = acc.x;
-                        ps[1] = acc.y;
-                        ps[2] = acc.z;
-                    }
-                    if (buf.partial_sumsq) {
-                        float* pq = buf.partial_sumsq + (size_t)b * plane + (size_t)pixel * 3u;
-                        float3 q = first ? f3(0.0f, 0.0f, 0.0f) : f3(pq[0], pq[1], pq[2]);
-                        if (keep) q = q + L * L;
-                        if (keep || first) {
-                            pq[0] = q.x;
-                            pq[1] = q.y;
-                            pq[2] = q.z;
-                        }
-                    }
+                    else accumulate_sample(buf, pixel, L);
                     ended = true;
                     next_sample = sample + 1u;
-                    new_unit = next_sample >= s_end;
+                    new_unit = true; // a unit is one sample
                     S.rd[slot].w = __uint_as_float(0u); // idle until regenerated
                 }
         };

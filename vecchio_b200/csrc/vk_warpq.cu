@@ -1,0 +1,434 @@
+// vk_warpq.cu -- the persistent megakernel as a wavefront inside each WARP ("warp queues").
+//
+// Round 1's staged kernel (vk_staged.cu) ran generate / extend / sort / shade as CTA-wide stages over a slot
+// pool in shared memory.  Its ncu report (profiles/r1_cornell_staged_full.md) names what that costs: 14 % of
+// the PC samples sit on the three __syncthreads() of an iteration, the class lists are consumed in order so
+// every class border and every list tail is a partial warp (24.9 of 32 lanes), all eight warps of a CTA run
+// the same stage at the same time (the ALU-heavy extend of one cannot overlap the MUFU / memory-heavy shade of
+// another) and the rotated-box hits shade inside the diffuse class at 5.1 lanes.
+//
+// Here every warp is its own wavefront machine and nothing is ever synchronised across warps:
+//
+//   * a warp owns VKQ_N path slots in shared memory (64 B each, the staged kernel's record) and one ring
+//     buffer of slot indices per QUEUE: rays to extend, samples to regenerate, and one queue per shading
+//     class (emitter / miss, dielectric, metal, diffuse, diffuse behind an instance chain);
+//   * each iteration the warp takes up to 32 entries (extend: 32 x VKQ_K, K rays per lane through the flat
+//     program for instruction-level parallelism) from its FULLEST queue and runs that one stage on them, so
+//     the 32 lanes execute one code path; what is left in a queue simply waits for the next entries -- no
+//     partial warps at class borders, the pool only has to be large enough that some queue is full;
+//   * the results are appended to the queues of the next stage with one __match_any_sync per batch; counters
+//     live in shared memory and are touched by this warp alone (no atomics, __syncwarp only);
+//   * units (pixel, sample) come from one global counter in chunks of 256 per warp; a finished sample goes
+//     into its pixel's integer accumulators (RenderBuffers), so the image does not depend on any of this
+//     scheduling and is bit-identical to the other variants for a seed.
+//
+// Reference semantics are untouched: extend = world.hit (src/main.rs:130) through the same trace functions,
+// shade = the same resolve_hit + shade of vk_device.cuh (src/main.rs:131-149), sample end = the NaN filter
+// of src/main.rs:191-194, regeneration = Camera::get_ray (src/main.rs:187-190).
+#include "vk_device.cuh"
+
+namespace VK_NS {
+
+#ifndef VKQ_N
+#define VKQ_N 192 // slots per warp (<= 256: ring indices are bytes)
+#endif
+#ifndef VKQ_WARPS
+#define VKQ_WARPS 4
+#endif
+#ifndef VKQ_K
+#define VKQ_K 2 // rays per lane in a flat-program extend batch
+#endif
+#ifndef VKQ_MINB
+#define VKQ_MINB 4
+#endif
+#ifndef VKQ_REGEN_MIN
+#define VKQ_REGEN_MIN 16u // ended lanes of a shade batch are regenerated at once when at least this many ended
+#endif
+#define VKQ_CHUNK 256u
+enum { VKQ_EXT = 0, VKQ_END = 1, VKQ_EMIT = 2, VKQ_DIEL = 3, VKQ_METAL = 4, VKQ_DIFF = 5, VKQ_DIFFI = 6, VKQ_NQ = 7, VKQ_NONE = 8 };
+
+struct WqWarp {
+    float4 ro[VKQ_N];            // origin.xyz, time
+    float4 rd[VKQ_N];            // direction.xyz, bits: depth of the segment to trace
+    float4 bt[VKQ_N];            // path weight.xyz, bits: global sample index
+    uint4 hp[VKQ_N];             // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; pixel
+    uint8_t ring[VKQ_NQ][256];   // slot indices, one ring per queue
+    uint2 ct[8];                 // per queue: .x = entries, .y = ring write position
+    uint32_t cur_s, cur_p, left; // unit cursor: next unit is (sample cur_s, pixel cur_p), `left` units remain in the chunk
+    uint32_t exhausted;          // the global unit counter has run past the end
+};
+
+struct WqCtx {
+    const DCamera& cam;
+    const RenderArgs& a;
+    WqWarp& S;
+    uint32_t n_pixels;
+    unsigned long long n_units;
+    unsigned long long* unit_head;
+    uint32_t lane, below;
+};
+
+// Append the lanes with cls != VKQ_NONE to the queue of their class: one match groups the lanes, the first
+// lane of each group moves that queue's counters (no other lane touches them: different groups, different queues).
+VKD void wq_push(WqWarp& S, uint32_t cls, uint32_t slot, uint32_t lane, uint32_t below) {
+    const uint32_t m = __match_any_sync(0xFFFFFFFFu, cls);
+    const uint32_t leader = __ffs(m) - 1u;
+    uint32_t pos = 0;
+    if (lane == leader && cls != VKQ_NONE) {
+        const uint2 c = S.ct[cls];
+        pos = c.y;
+        S.ct[cls] = make_uint2(c.x + (uint32_t)__popc(m), c.y + (uint32_t)__popc(m));
+    }
+    pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+    if (cls != VKQ_NONE) S.ring[cls][(pos + __popc(m & below)) & 255u] = (uint8_t)slot;
+    __syncwarp();
+}
+
+// The lanes with want == true take the warp's next units and start their camera ray (src/main.rs:187-190).
+// Returns whether this lane got one (false: the frame has no unit left, the slot retires).
+VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
+    WqWarp& S = C.S;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+    if (m == 0u) return false;
+    const uint32_t need = (uint32_t)__popc(m), rank = (uint32_t)__popc(m & C.below);
+    uint32_t served = 0, s = 0, p = 0;
+    bool got = false;
+#pragma unroll 1
+    while (served < need) { // at most two rounds: what the current chunk still holds, then a new chunk
+        uint32_t left = S.left;
+        if (left == 0u) {
+            if (S.exhausted) break;
+            __syncwarp();
+            if (C.lane == 0) {
+                const unsigned long long u0 = atomicAdd(C.unit_head, (unsigned long long)VKQ_CHUNK);
+                if (u0 >= C.n_units) S.exhausted = 1u;
+                else {
+                    const unsigned long long rem = C.n_units - u0;
+                    const unsigned long long sb = u0 / C.n_pixels;
+                    S.left = rem < VKQ_CHUNK ? (uint32_t)rem : VKQ_CHUNK;
+                    S.cur_s = (uint32_t)sb;
+                    S.cur_p = (uint32_t)(u0 - sb * C.n_pixels);
+                }
+            }
+            __syncwarp();
+            if (S.exhausted) break;
+            left = S.left;
+        }
+        const uint32_t take = min(need - served, left);
+        const uint32_t cs = S.cur_s, cp = S.cur_p;
+        if (want && rank >= served && rank < served + take) {
+            p = cp + (rank - served);
+            s = cs;
+            while (p >= C.n_pixels) { // units run pixel-major inside a sample
+                p -= C.n_pixels;
+                ++s;
+            }
+            got = true;
+        }
+        __syncwarp();
+        if (C.lane == 0) {
+            uint32_t np = cp + take, ns = cs;
+            while (np >= C.n_pixels) {
+                np -= C.n_pixels;
+                ++ns;
+            }
+            S.cur_p = np;
+            S.cur_s = ns;
+            S.left = left - take;
+        }
+        __syncwarp();
+        served += take;
+    }
+    if (got) {
+        const uint32_t y = p / C.a.width, x = p - y * C.a.width; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
+        PathRng rng;
+        rng.pixel = p;
+        rng.sample = C.a.spp_begin + s;
+        rng.key = make_uint2(C.a.seed_lo, C.a.seed_hi);
+        float3 o, d;
+        float time;
+        camera_get_ray(C.cam, rng, x, y, C.a.width, C.a.height, o, d, time);
+        S.ro[slot] = make_float4(o.x, o.y, o.z, time);
+        S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(1u)); // ray_color(ray, .., 1)
+        S.bt[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng.sample));
+        S.hp[slot].w = p;
+    }
+    return got;
+}
+
+VKD uint32_t wq_class_of(const DScene& sc, uint32_t prim, uint32_t inst) {
+    uint32_t mat;
+    const uint32_t i = VKD_INDEX(prim);
+    switch (VKD_TYPE(prim)) {
+    case VK_T_SPHERE: mat = __ldg(&sc.sphere_mat[i]); break;
+    case VK_T_MSPHERE: mat = __float_as_uint(__ldg(&sc.mspheres[3 * i + 2]).y); break;
+    case VK_T_RECT: mat = __float_as_uint(__ldg(&sc.rects[2 * i + 1]).z); break;
+    case VK_T_BOX: mat = __float_as_uint(__ldg(&sc.boxes[2 * i]).w); break;
+    default: mat = __float_as_uint(__ldg(&sc.media[i]).z); break;
+    }
+    const uint32_t t = __ldg(&sc.materials[mat]).x;
+    return t == VK_M_DIFFUSE_LIGHT ? VKQ_EMIT : t == VK_M_DIELECTRIC ? VKQ_DIEL : t == VK_M_METAL ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
+}
+
+template <bool FLAT, bool MEDIA, bool LEGACY>
+VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
+                    unsigned long long* unit_head) {
+    extern __shared__ __align__(16) unsigned char vkq_raw[];
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    WqWarp& S = reinterpret_cast<WqWarp*>(vkq_raw)[threadIdx.x >> 5];
+    const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
+    uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0;
+    constexpr uint32_t EXT_CAP = FLAT ? 32u * VKQ_K : 32u;
+
+    // every slot starts in the regeneration queue
+    if (lane < 8) S.ct[lane] = make_uint2(0u, 0u);
+    for (uint32_t i = lane; i < VKQ_N; i += 32u) S.ring[VKQ_END][i] = (uint8_t)i;
+    if (lane == 0) {
+        S.left = 0u;
+        S.exhausted = 0u;
+        S.cur_s = 0u;
+        S.cur_p = 0u;
+    }
+    __syncwarp();
+    if (lane == 0) S.ct[VKQ_END] = make_uint2(VKQ_N, VKQ_N);
+    __syncwarp();
+
+#pragma unroll 1
+    for (;;) {
+        // ---- pick the fullest queue (extend batches are EXT_CAP wide, the others 32) -------------------------
+        uint32_t q = VKQ_EXT, n_q, tail_q;
+        {
+            const uint4 c01 = *reinterpret_cast<const uint4*>(&S.ct[0]), c23 = *reinterpret_cast<const uint4*>(&S.ct[2]),
+                        c45 = *reinterpret_cast<const uint4*>(&S.ct[4]), c67 = *reinterpret_cast<const uint4*>(&S.ct[6]);
+            uint32_t best = c01.x * 32u; // score = entries x 32 / batch width
+            n_q = c01.x;
+            tail_q = c01.y;
+#define VKQ_CONSIDER(Q, CNT, TAIL)                                                                                     \
+    {                                                                                                                  \
+        const uint32_t sc_ = (CNT) * EXT_CAP;                                                                          \
+        if (sc_ > best) {                                                                                              \
+            best = sc_;                                                                                                \
+            q = (Q);                                                                                                   \
+            n_q = (CNT);                                                                                               \
+            tail_q = (TAIL);                                                                                           \
+        }                                                                                                              \
+    }
+            VKQ_CONSIDER(VKQ_EMIT, c23.x, c23.y)
+            VKQ_CONSIDER(VKQ_DIFF, c45.z, c45.w)
+            VKQ_CONSIDER(VKQ_DIFFI, c67.x, c67.y)
+            VKQ_CONSIDER(VKQ_DIEL, c23.z, c23.w)
+            VKQ_CONSIDER(VKQ_METAL, c45.x, c45.y)
+            VKQ_CONSIDER(VKQ_END, c01.z, c01.w)
+#undef VKQ_CONSIDER
+            if (best == 0u) break; // every queue is empty: all slots have retired
+        }
+        const uint32_t cap = q == VKQ_EXT ? EXT_CAP : 32u;
+        const uint32_t n = min(n_q, cap), head = tail_q - n_q;
+        __syncwarp();
+        if (lane == 0) S.ct[q].x = n_q - n;
+        __syncwarp();
+        // (the entries [head, head + n) stay readable: pushes only write at the ring's tail, and a ring holds 256 >= VKQ_N entries)
+
+        if (q == VKQ_EXT) {
+            // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------
+            if (FLAT) {
+                float3 o[VKQ_K], d[VKQ_K];
+                float tm[VKQ_K], best_t[VKQ_K];
+                bool live[VKQ_K];
+                uint32_t best_hit[VKQ_K], slot[VKQ_K];
+                MediumXi xi[VKQ_K];
+#pragma unroll
+                for (int k = 0; k < VKQ_K; ++k) {
+                    const uint32_t e = lane + 32u * k;
+                    live[k] = e < n;
+                    slot[k] = S.ring[VKQ_EXT][(head + (live[k] ? e : 0u)) & 255u];
+                    const float4 ro = S.ro[slot[k]], rd = S.rd[slot[k]];
+                    o[k] = f3(ro);
+                    d[k] = f3(rd);
+                    tm[k] = ro.w;
+                    xi[k].table = nullptr;
+                    xi[k].depth = __float_as_uint(rd.w);
+                    xi[k].rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                    xi[k].rng.pixel = MEDIA ? S.hp[slot[k]].w : 0u;
+                    xi[k].rng.sample = MEDIA ? __float_as_uint(S.bt[slot[k]].w) : 0u;
+                }
+                trace_flat_k<VKQ_K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit);
+#pragma unroll
+                for (int k = 0; k < VKQ_K; ++k) {
+                    uint32_t cls = VKQ_NONE;
+                    if (live[k]) {
+                        ++n_rays;
+                        n_prims += flat->n;
+                        uint32_t prim = VK_REF_NONE, hi = 0u;
+                        cls = VKQ_EMIT; // a miss ends the sample like an emitter does
+                        if (best_hit[k] != 0xFFFFFFFFu) {
+                            const FlatHit& fh = flat->hits[best_hit[k]];
+                            prim = fh.prim & ~VKD_DUP;
+                            const uint32_t inst = fh.inst;
+                            hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);
+                            cls = fh.cls == 0u ? VKQ_EMIT : fh.cls == 1u ? VKQ_DIEL : fh.cls == 2u ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
+                        }
+                        uint4& hp = S.hp[slot[k]];
+                        hp.x = __float_as_uint(best_t[k]);
+                        hp.y = prim;
+                        hp.z = hi;
+                    }
+                    if (k == 0 || n > 32u * k) wq_push(S, cls, slot[k], lane, below); // (warp-uniform condition)
+                }
+            } else {
+                const bool live = lane < n;
+                const uint32_t slot = S.ring[VKQ_EXT][(head + (live ? lane : 0u)) & 255u];
+                uint32_t cls = VKQ_NONE;
+                if (live) {
+                    const float4 ro = S.ro[slot], rd = S.rd[slot];
+                    MediumXi xi;
+                    xi.table = nullptr;
+                    xi.depth = __float_as_uint(rd.w);
+                    xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                    xi.rng.pixel = MEDIA ? S.hp[slot].w : 0u;
+                    xi.rng.sample = MEDIA ? __float_as_uint(S.bt[slot].w) : 0u;
+                    TraceCounters tc = {0u, 0u};
+                    const TraceHit h = trace<MEDIA>(sc, f3(ro), f3(rd), ro.w, 0.001f, CUDART_INF_F, xi, tc);
+                    ++n_rays;
+                    n_nodes += tc.nodes;
+                    n_prims += tc.prims;
+                    uint4& hp = S.hp[slot];
+                    hp.x = __float_as_uint(h.t);
+                    hp.y = h.prim;
+                    hp.z = (h.inst ? (0x80000000u | VKD_INDEX(h.inst)) : 0u) | (h.face << 28);
+                    cls = h.prim == VK_REF_NONE ? (uint32_t)VKQ_EMIT : wq_class_of(sc, h.prim, h.inst);
+                }
+                wq_push(S, cls, slot, lane, below);
+            }
+            continue;
+        }
+
+        const bool act = lane < n;
+        const uint32_t slot = S.ring[q][(head + (act ? lane : 0u)) & 255u];
+        bool alive = false, ended = false;
+        if (q != VKQ_END) {
+            // ---- shade one class: resolve + scatter (src/main.rs:131-149); a finished sample goes through the NaN / Inf
+            // filter (:191-194) into its pixel ---------------------------------------------------------------------------
+            if (act) {
+                const float4 ro = S.ro[slot], rd = S.rd[slot], bt = S.bt[slot];
+                const uint4 hp = S.hp[slot];
+                float3 o = f3(ro), d = f3(rd), beta = f3(bt), L = f3(0.0f, 0.0f, 0.0f);
+                float time = ro.w;
+                uint32_t depth = __float_as_uint(rd.w);
+                const uint32_t pixel = hp.w, prim = hp.y;
+                bool valid = true;
+                if (prim == VK_REF_NONE) {
+                    L = beta * miss_color(a, d); // src/main.rs:151
+                } else {
+                    PathRng rng;
+                    rng.pixel = pixel;
+                    rng.sample = __float_as_uint(bt.w);
+                    rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                    const uint32_t hi = hp.z;
+                    TraceHit h;
+                    h.t = __uint_as_float(hp.x);
+                    h.prim = prim;
+                    h.inst = (hi & 0x80000000u) ? (((uint32_t)VK_T_XFORM << 28) | (hi & 0x07FFFFFFu)) : 0u;
+                    h.face = (hi >> 28) & 7u;
+                    HitRecD rec;
+                    resolve_hit(sc, h, o, d, time, false, rec);
+                    alive = LEGACY ? shade_legacy(sc, rec, rng, depth, o, d, time, beta, L, valid)
+                                   : shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
+                    if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
+                    if (alive && !(finite3(d) && finite3(o))) {          // the reference's sample is NaN here (see vk_kernels.cu)
+                        valid = false;
+                        alive = false;
+                    }
+                }
+                if (alive) {
+                    S.ro[slot] = make_float4(o.x, o.y, o.z, time);
+                    S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
+                    S.bt[slot] = make_float4(beta.x, beta.y, beta.z, bt.w);
+                } else {
+                    if (valid && finite3(L)) accumulate_sample(buf, pixel, L);
+                    else ++n_drop;
+                    ended = true;
+                }
+            }
+        } else {
+            ended = act; // queued regenerations
+        }
+        // Regenerate in place when enough lanes ended -- the emitter / miss class does, every lane; in the other classes
+        // only a few lanes end (a light-sampled direction below the surface has weight 0): those are queued and
+        // regenerated together, with full warps.
+        const uint32_t m_end = __ballot_sync(0xFFFFFFFFu, ended);
+        bool to_end = false;
+        if (q == VKQ_END || (uint32_t)__popc(m_end) >= VKQ_REGEN_MIN) alive = wq_regen(C, ended, slot) || alive;
+        else to_end = ended;
+        wq_push(S, alive ? (uint32_t)VKQ_EXT : (to_end ? (uint32_t)VKQ_END : (uint32_t)VKQ_NONE), slot, lane, below);
+    }
+
+    unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = n_nodes, w_prims = n_prims;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        w_rays += __shfl_xor_sync(0xFFFFFFFFu, w_rays, off);
+        w_drop += __shfl_xor_sync(0xFFFFFFFFu, w_drop, off);
+        w_nodes += __shfl_xor_sync(0xFFFFFFFFu, w_nodes, off);
+        w_prims += __shfl_xor_sync(0xFFFFFFFFu, w_prims, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&buf.counters[3], w_nodes);
+        atomicAdd(&buf.counters[4], w_prims);
+        atomicAdd(&buf.counters[0], w_rays);
+        if (w_drop) atomicAdd(&buf.counters[1], w_drop);
+    }
+}
+
+template <bool MEDIA, bool LEGACY>
+__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB) k_warpq(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
+                                                                unsigned long long* unit_head) {
+    warpq_body<false, MEDIA, LEGACY>(sc, nullptr, cam, a, buf, unit_head);
+}
+template <bool MEDIA, bool LEGACY>
+__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB) k_warpq_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
+                                                                     const RenderArgs a, const RenderBuffers buf, unsigned long long* unit_head) {
+    warpq_body<true, MEDIA, LEGACY>(sc, &flat, cam, a, buf, unit_head);
+}
+
+template <class K> static cudaError_t warpq_prepare(K kernel, int* blocks_per_sm) {
+    const size_t smem = VKQ_WARPS * sizeof(WqWarp);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, 32 * VKQ_WARPS, smem);
+}
+
+// grid = sm_count * resident CTAs (persistent); *unit_head must be zero on the stream before the launch
+cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
+                         unsigned long long* unit_head, int sm_count, bool legacy, cudaStream_t st) {
+    int bps = 0;
+    cudaError_t e;
+    const size_t smem = VKQ_WARPS * sizeof(WqWarp);
+    const bool media = sc.has_media != 0u;
+#define VKQ_LAUNCH_FLAT(M, G)                                                                                          \
+    {                                                                                                                  \
+        if ((e = warpq_prepare(k_warpq_flat<M, G>, &bps)) != cudaSuccess) return e;                                    \
+        k_warpq_flat<M, G><<<sm_count * (bps < 1 ? 1 : bps), 32 * VKQ_WARPS, smem, st>>>(sc, *flat, cam, a, b, unit_head); \
+    }
+#define VKQ_LAUNCH_BVH(M, G)                                                                                           \
+    {                                                                                                                  \
+        if ((e = warpq_prepare(k_warpq<M, G>, &bps)) != cudaSuccess) return e;                                         \
+        k_warpq<M, G><<<sm_count * (bps < 1 ? 1 : bps), 32 * VKQ_WARPS, smem, st>>>(sc, cam, a, b, unit_head);          \
+    }
+#if VK_SIMPLE
+    (void)legacy; // the trimmed build exists for the HEAD integrator on flat scenes only
+    if (media) VKQ_LAUNCH_FLAT(true, false) else VKQ_LAUNCH_FLAT(false, false)
+#else
+    if (flat && flat->n) {
+        if (media) { if (legacy) VKQ_LAUNCH_FLAT(true, true) else VKQ_LAUNCH_FLAT(true, false) }
+        else { if (legacy) VKQ_LAUNCH_FLAT(false, true) else VKQ_LAUNCH_FLAT(false, false) }
+    } else {
+        if (media) { if (legacy) VKQ_LAUNCH_BVH(true, true) else VKQ_LAUNCH_BVH(true, false) }
+        else { if (legacy) VKQ_LAUNCH_BVH(false, true) else VKQ_LAUNCH_BVH(false, false) }
+    }
+#endif
+#undef VKQ_LAUNCH_FLAT
+#undef VKQ_LAUNCH_BVH
+    return cudaGetLastError();
+}
+
+} // namespace VK_NS

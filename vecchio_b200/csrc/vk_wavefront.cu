@@ -28,16 +28,12 @@ VKD void wf_begin_sample(const DCamera& cam, const RenderArgs& a, const WfState&
     w.ray_d[slot] = make_float4(d.x, d.y, d.z, u2f(1u));           // ray_color(ray, .., 1)
     w.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(s));
 }
-// Unit u = (sample block b, pixel): b = u / n_pixels.  Pixels run row-major, so the 32 slots a
+// Unit u = (sample b, pixel): b = u / n_pixels.  Pixels run row-major, so the 32 slots a
 // warp fills together get 32 neighbouring pixels of a row.
 VKD void wf_start_unit(const DCamera& cam, const RenderArgs& a, const WfState& w, uint32_t slot, unsigned long long u) {
     const uint32_t b = (uint32_t)(u / w.n_pixels), pixel = (uint32_t)(u - (unsigned long long)b * w.n_pixels);
-    const uint32_t s = a.spp_begin + b * a.unit_spp;
-    const uint32_t s_end = min(s + a.unit_spp, a.spp_begin + a.spp_count);
-    w.unit[slot] = make_uint4(pixel, s_end, b, 0u);
-    w.sum[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (w.sumsq) w.sumsq[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    wf_begin_sample(cam, a, w, slot, pixel, s);
+    w.unit[slot] = make_uint4(pixel, 0u, 0u, 0u);
+    wf_begin_sample(cam, a, w, slot, pixel, a.spp_begin + b);
 }
 
 __global__ void __launch_bounds__(VKW_BLOCK) k_wf_generate(const DCamera cam, const RenderArgs a, const WfState w) {
@@ -198,42 +194,11 @@ __global__ void __launch_bounds__(VKW_BLOCK) k_wf_shade(const DScene sc, const D
             w.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
             w.ray_d[slot] = make_float4(d.x, d.y, d.z, u2f(depth));
             w.beta[slot] = make_float4(beta.x, beta.y, beta.z, bt.w);
-        } else { // sample finished: NaN/Inf filter of src/main.rs:191-194, then the unit's next sample
-            float4 sm = w.sum[slot];
+        } else { // sample finished: NaN/Inf filter of src/main.rs:191-194, then the slot's next unit
             const bool keep = valid && finite3(L);
             dropped = !keep;
-            if (keep) {
-                sm.x += L.x;
-                sm.y += L.y;
-                sm.z += L.z;
-            }
-            float4 sq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (w.sumsq) {
-                sq = w.sumsq[slot];
-                if (keep) {
-                    sq.x += L.x * L.x;
-                    sq.y += L.y * L.y;
-                    sq.z += L.z * L.z;
-                }
-            }
-            if (sample + 1u < un.y) {
-                w.sum[slot] = sm;
-                if (w.sumsq) w.sumsq[slot] = sq;
-                wf_begin_sample(cam, a, w, slot, un.x, sample + 1u);
-            } else { // unit finished: its sample-block sum goes to its own plane
-                const size_t plane = (size_t)a.width * a.height * 3u;
-                float* ps = buf.partial_sum + (size_t)un.z * plane + (size_t)un.x * 3u;
-                ps[0] = sm.x;
-                ps[1] = sm.y;
-                ps[2] = sm.z;
-                if (buf.partial_sumsq) {
-                    float* pq = buf.partial_sumsq + (size_t)un.z * plane + (size_t)un.x * 3u;
-                    pq[0] = sq.x;
-                    pq[1] = sq.y;
-                    pq[2] = sq.z;
-                }
-                need_unit = true;
-            }
+            if (keep) accumulate_sample(buf, un.x, L);
+            need_unit = true;
         }
     }
     // next units: ballot + shared-memory atomic per warp, one global atomic per block
