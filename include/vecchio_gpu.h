@@ -266,7 +266,7 @@ typedef struct vk_hit {
     uint32_t _pad;
 } vk_hit; /* 56 B */
 
-#define VK_MEDIUM_XI_SLOTS 8 /* slot = (medium index * 2 + second-visit) % 8 */
+#define VK_MEDIUM_XI_SLOTS 8 /* vk_intersect's injected table: slot = medium index * 2 + second-visit; scenes of up to 4 media */
 
 typedef struct vk_ctx vk_ctx;
 
@@ -340,6 +340,39 @@ int vk_flush_stats(vk_ctx* ctx, vk_stats* stats);
  * for ConstantMedium::hit's free-flight draw (src/hittable.rs:473). */
 int vk_intersect(vk_ctx* ctx, const vk_ray* rays, size_t n, const float* medium_xi,
                  uint32_t flags, vk_hit* out);
+
+/* Parity hook for the SHADING half of the path, next to vk_intersect for the geometry half: one call of the
+ * device functions behind `Material::scatter_with_pdf` / `scattering_pdf` / `emitted` (src/material.rs:92-108,
+ * 134-141, 177-206, 218-225, 448-487), `Texture::value` (:238-303, 430-433), the light list's `pdf_value` /
+ * `random` (src/hittable.rs:104-134, 271-291, 371-377, 420-433) and the mixture estimator that ties them
+ * together in `ray_color` (src/main.rs:131-149) -- on the uploaded scene's materials, textures and lights, with
+ * the variates SUPPLIED so that the oracle can be fed the same ones.
+ *   VK_EVAL_BOUNCE         one pass of ray_color's body after world.hit() returned the given HitRec:
+ *                          beta starts at (1,1,1), L at 0; out = continue?, scattered ray, weight, emission
+ *   VK_EVAL_BOUNCE_LEGACY  the same for the legacy `Material::scatter` integrator
+ *   VK_EVAL_TEXTURE        textures[index].value(u, v, p) -> beta
+ *   VK_EVAL_LIGHTS_PDF     lights.pdf_value(p, dir) -> value            (`impl Hittable for Vec<..>`, :420-427)
+ *   VK_EVAL_LIGHT_RANDOM   lights[index].random(p) with xi[0..2] -> out_d */
+enum { VK_EVAL_BOUNCE = 0, VK_EVAL_BOUNCE_LEGACY = 1, VK_EVAL_TEXTURE = 2, VK_EVAL_LIGHTS_PDF = 3, VK_EVAL_LIGHT_RANDOM = 4 };
+typedef struct vk_eval {
+    uint32_t op;
+    uint32_t index;                     /* BOUNCE*: material | TEXTURE: texture | LIGHT_RANDOM: entry of the light list */
+    float ray_o[3], ray_d[3], ray_time; /* BOUNCE*: the ray that was traced                                              */
+    float p[3], normal[3], t, u, v;     /* BOUNCE*: the HitRec | TEXTURE: u, v, p | LIGHT*: p = the origin               */
+    uint32_t front;
+    float dir[3];                       /* LIGHTS_PDF: the direction                                                    */
+    uint32_t xi[5];                     /* BOUNCE*: xi[0..3] the bounce's four 32-bit variates (gen::<f32>() takes the
+                                           top 24 bits, gen_range the top 23), xi[4] SpecDiffuse's choice;
+                                           LIGHT_RANDOM: xi[0..2]                                                       */
+    /* results */
+    uint32_t alive;                     /* BOUNCE*: the path continues with (out_o, out_d, out_time)                     */
+    uint32_t valid;                     /* BOUNCE*: 0 = the reference's sample is non-finite here (dropped, main.rs:192) */
+    float out_o[3], out_d[3], out_time;
+    float beta[3];                      /* BOUNCE*: path weight after the bounce | TEXTURE: the colour                   */
+    float L[3];                         /* BOUNCE*: radiance added by this hit                                           */
+    float value;                        /* LIGHTS_PDF                                                                   */
+} vk_eval; /* 43 words */
+int vk_eval_batch(vk_ctx* ctx, vk_eval* recs, size_t n, uint32_t flags /* VK_FLAG_STRICT_MATH */);
 
 /* Microbenchmarks for the roofline denominators the driver does not measure:
  * dependent-free FFMA throughput (TFLOP/s) and L2-resident read bandwidth (GB/s). */

@@ -45,7 +45,13 @@ struct Rng {
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         return z ^ (z >> 31);
     }
-    uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    // tests can script the next words (orc_eval_batch feeds the variates the GPU hook was given)
+    const uint32_t* script = nullptr;
+    size_t script_n = 0, script_pos = 0;
+    uint32_t next_u32() {
+        if (script && script_pos < script_n) return script[script_pos++];
+        return (uint32_t)(next_u64() >> 32);
+    }
     float gen_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
     float gen_range(float low, float high) {
         const float scale = high - low, offset = low - scale;
@@ -1250,6 +1256,119 @@ size_t orc_harvest_rays(const orc_scene* s, const vk_camera* cam_, uint32_t widt
     tl_tap = nullptr;
     tl_rng = nullptr;
     return tap.n;
+}
+
+// The oracle's side of vk_eval_batch (include/vecchio_gpu.h): the same record through the restated reference
+// code, fed the same 32-bit variates.  The reference draws in program order from one stream, the GPU names its
+// draws (xi[0] mixture choice / Schlick test, xi[1..2] the direction, xi[3] light choice, xi[4] SpecDiffuse), so
+// the script puts the words in the order this material's code path will ask for them.  Rejection loops
+// (random_in_unit_sphere: Metal with fuzz, legacy Isotropic) take their words from the oracle's own stream: the
+// GPU samples the same law directly, not the same points.
+int orc_eval_batch(const orc_scene* s, vk_eval* recs, size_t n) {
+    using namespace orc;
+    if (!s || (!recs && n)) return VK_ERR_INVALID;
+    Rng rng;
+    rng.seed(11, 22, 33);
+    tl_rng = &rng;
+    auto v3 = [](const float* f) { return Vec3(f[0], f[1], f[2]); };
+    auto put3 = [](float* f, Vec3 v) { f[0] = v.x; f[1] = v.y; f[2] = v.z; };
+    auto u01 = [](uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); };
+    const ListHittable* lights = dynamic_cast<const ListHittable*>(s->s.lights.get());
+    int rc = VK_OK;
+    for (size_t i = 0; i < n && rc == VK_OK; ++i) {
+        vk_eval& e = recs[i];
+        std::vector<uint32_t> script;
+        if (e.op == VK_EVAL_BOUNCE || e.op == VK_EVAL_BOUNCE_LEGACY) {
+            if (e.index >= s->s.materials.size()) { rc = VK_ERR_INVALID; break; }
+            const Arc<Material>& mat = s->s.materials[e.index];
+            const Material* m = mat.get();
+            if (auto sd = dynamic_cast<const SpecDiffuse*>(m)) {
+                script.push_back(e.xi[4]);
+                m = (u01(e.xi[4]) < sd->pct ? sd->specular : sd->diffuse).get();
+            }
+            const bool legacy = e.op == VK_EVAL_BOUNCE_LEGACY;
+            if (dynamic_cast<const Dielectric*>(m)) script.push_back(e.xi[0]);
+            else if (dynamic_cast<const Lambertian*>(m) || (!legacy && dynamic_cast<const Isotropic*>(m))) {
+                script.push_back(e.xi[0]);
+                if (legacy) script.push_back(e.xi[1]); // Lambertian::random: angle, z
+                else if (u01(e.xi[0]) < 0.5f && lights && !lights->items.empty()) { // light branch: choose, then the light's own draws
+                    script.push_back(e.xi[3]);
+                    const size_t li = (size_t)(((uint64_t)e.xi[3] * (uint64_t)lights->items.size()) >> 32);
+                    if (dynamic_cast<const Boxy*>(lights->items[li].get())) script.push_back(e.xi[3] * 0x9E3779B1u); // its side
+                    script.push_back(e.xi[1]);
+                    script.push_back(e.xi[2]);
+                } else {
+                    script.push_back(e.xi[1]);
+                    script.push_back(e.xi[2]);
+                }
+            }
+            rng.script = script.data();
+            rng.script_n = script.size();
+            rng.script_pos = 0;
+            Ray r(v3(e.ray_o), v3(e.ray_d), e.ray_time);
+            HitRec rec(v3(e.p), v3(e.normal), e.t, e.u, e.v, e.front != 0, mat);
+            e.alive = 0;
+            e.valid = 1;
+            Vec3 beta = Vec3::new_const(1.0f), L = Vec3::new_const(0.0f);
+            Ray out = r;
+            if (!legacy) { // src/main.rs:131-149
+                Vec3 emitted = mat->emitted(rec, rec.u, rec.v, rec.p);
+                if (auto srec = mat->scatter_with_pdf(r, rec)) {
+                    if (srec->specular_ray) {
+                        beta = srec->attenuation;
+                        out = *srec->specular_ray;
+                        e.alive = 1;
+                    } else {
+                        auto p_important = std::make_shared<HittablePDF>(s->s.lights, rec.p);
+                        MixturePDF p(p_important, 0.5f, srec->pdf, 0.5f);
+                        Ray scattered(rec.p, p.generate(), r.time);
+                        float pdf = p.value(scattered.direction);
+                        beta = srec->attenuation * mat->scattering_pdf(r, rec, scattered) / pdf;
+                        L = emitted;
+                        out = scattered;
+                        e.alive = 1;
+                        e.value = pdf;
+                        if (!beta.is_finite()) e.valid = 0;
+                    }
+                } else
+                    L = emitted;
+            } else { // ray_color_legacy
+                g_scatter_unwrap_panic = false;
+                L = mat->emitted(rec, rec.u, rec.v, rec.p);
+                if (auto sc = mat->scatter(r, rec)) {
+                    beta = sc->first;
+                    out = sc->second;
+                    e.alive = 1;
+                }
+                if (g_scatter_unwrap_panic) e.valid = 0;
+            }
+            rng.script = nullptr;
+            put3(e.out_o, out.origin);
+            put3(e.out_d, out.direction);
+            e.out_time = out.time;
+            put3(e.beta, beta);
+            put3(e.L, L);
+        } else if (e.op == VK_EVAL_TEXTURE) {
+            if (e.index >= s->s.textures.size()) { rc = VK_ERR_INVALID; break; }
+            put3(e.beta, s->s.textures[e.index]->value(e.u, e.v, v3(e.p)));
+        } else if (e.op == VK_EVAL_LIGHTS_PDF) {
+            e.value = s->s.lights->pdf_value(v3(e.p), v3(e.dir));
+        } else if (e.op == VK_EVAL_LIGHT_RANDOM) {
+            if (!lights || e.index >= lights->items.size()) { rc = VK_ERR_INVALID; break; }
+            const Hittable* l = lights->items[e.index].get();
+            if (dynamic_cast<const Boxy*>(l)) script.push_back(e.xi[2]); // Boxy::random: choose a side, then the side's draws
+            script.push_back(e.xi[0]);
+            script.push_back(e.xi[1]);
+            rng.script = script.data();
+            rng.script_n = script.size();
+            rng.script_pos = 0;
+            put3(e.out_d, l->random(v3(e.p)));
+            rng.script = nullptr;
+        } else
+            rc = VK_ERR_INVALID;
+    }
+    tl_rng = nullptr;
+    return rc;
 }
 
 int orc_kat(const orc_scene* s, const char* name, const float* in, int n_in, float* out, int n_out) {

@@ -54,6 +54,10 @@ int orc_render(const orc_scene* s, const vk_camera* cam, const vk_render_params*
 size_t orc_harvest_rays(const orc_scene* s, const vk_camera* cam, uint32_t width, uint32_t height,
                         uint32_t max_depth, uint64_t seed, size_t max_rays, vk_ray* out);
 
+/* The oracle's side of vk_eval_batch: the same records through the restated reference code with the same
+ * variates (see the comment at its definition for how the words are put in the reference's draw order). */
+int orc_eval_batch(const orc_scene* s, vk_eval* recs, size_t n);
+
 /* Known-answer hooks for the unit KATs; returns number of outputs written or -1. */
 int orc_kat(const orc_scene* s, const char* name, const float* in, int n_in, float* out, int n_out);
 

@@ -48,6 +48,8 @@ def lib():
         L.orc_harvest_rays.argtypes = [vp, C.POINTER(_abi.vk_camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                        C.c_size_t, vp]
         L.orc_harvest_rays.restype = C.c_size_t
+        L.orc_eval_batch.argtypes = [vp, vp, C.c_size_t]
+        L.orc_eval_batch.restype = C.c_int
         L.orc_kat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int]
         L.orc_kat.restype = C.c_int
         _lib = L
@@ -90,6 +92,13 @@ class OracleScene:
         out = np.zeros(max_rays, dtype=_abi.RAY_DTYPE)
         n = lib().orc_harvest_rays(self._h, C.byref(cam), width, height, max_depth, seed, max_rays, out.ctypes.data)
         return out[:n]
+
+    def eval_batch(self, recs):
+        """The oracle's side of ``vk_eval_batch`` (same records, same variates)."""
+        out = np.ascontiguousarray(recs, dtype=_abi.EVAL_DTYPE).copy()
+        rc = lib().orc_eval_batch(self._h, out.ctypes.data, len(out))
+        assert rc == 0, rc
+        return out
 
     def kat(self, name, values, n_out):
         return kat(name, values, n_out, self._h)

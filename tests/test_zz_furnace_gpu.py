@@ -1,16 +1,19 @@
 """The furnace closed forms (tests/test_oracle.py) on the GPU path.
 
-Written after this round's GPU minutes were spent: the oracle versions are green, these have not run on a B200
-yet, hence the non-strict xfail -- an XPASS in the round-end log is the first run succeeding, an XFAIL is a
-finding to look at, neither hides the rest of the suite.  Drop the marker once seen green."""
+Round 1 shipped these behind a non-strict xfail and the driver's B200 run XFAILED the white-medium one.  Measured
+since (scripts/diag_furnace.py, profiles/r2_diag_furnace.log): on every variant and both math builds the medium
+furnace drops no sample, its mean is E within 1.1 sigma (ratio 1.0019 / 1.0011 on two seeds) and the legacy
+integrator is exact to 4e-8 -- the assert that tripped was the sanity bound `rays > 1.2 * paths` copied from the
+oracle test: the oracle counts the segments the reference keeps tracing after a bounce weight of exactly 0
+(`rays`), the GPU ends such a path (the comparable oracle figure is `rays_live`) and traces 1.182
+segments per path here.  The bound is now 1.1 and the marker is gone."""
 import numpy as np
 import pytest
 
 from conftest import get_scene
 from test_oracle import FURNACE_E
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_furnace_lambertian_closed_form_gpu(vb, ctx):
@@ -46,7 +49,8 @@ def test_furnace_white_medium_conserves_energy_gpu(vb, ctx):
     ctx.upload(scene)
     W, spp = 128, 2048
     rgb, sq, st = ctx.render(cam, vb.render_params(W, W, spp, 100, seed=1), want_sumsq=True)
-    assert st.dropped_samples == 0 and st.rays > 1.2 * st.paths
+    assert st.dropped_samples == 0
+    assert st.rays > 1.1 * st.paths  # the medium does scatter (1.18 segments per path; zero-weight continuations are not traced)
     rgb = rgb.astype(np.float64)
     yy, xx = np.mgrid[0:W, 0:W]
     disc = ((yy - 63.5) ** 2 + (xx - 63.5) ** 2) < 24 ** 2

@@ -91,17 +91,18 @@ def gpu_lib():
         L.vk_set_stream.argtypes = [vp, vp]
         L.vk_flush_stats.argtypes = [vp, C.POINTER(_abi.vk_stats)]
         L.vk_intersect.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, vp]
+        L.vk_eval_batch.argtypes = [vp, vp, C.c_size_t, C.c_uint32]
         L.vk_measure_peaks.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.vk_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
         for f in ("vk_create", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device", "vk_finalize_device",
-                  "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks", "vk_device_info"):
+                  "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_eval_batch", "vk_measure_peaks", "vk_device_info"):
             getattr(L, f).restype = C.c_int
         _gpu = L
     return _gpu
 
 
 GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_check", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device",
-               "vk_finalize_device", "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_measure_peaks",
+               "vk_finalize_device", "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_eval_batch", "vk_measure_peaks",
                "vk_device_info"]
 HOST_SYMBOLS = ["vkh_scene_build", "vkh_scene_free", "vkh_scene_desc", "vkh_scene_aspect_ratio",
                 "vkh_scene_next_camera", "vkh_camera_new", "vkh_decode_png", "vkh_frame_to_rgb8", "vkh_write_ppm",
@@ -298,6 +299,12 @@ class Context:
             assert xi.size == len(rays) * _abi.VK_MEDIUM_XI_SLOTS
         self._check(self._L.vk_intersect(self._h, rays.ctypes.data, len(rays), xi.ctypes.data if xi is not None else None,
                                          flags, out.ctypes.data))
+        return out
+
+    def eval_batch(self, recs, flags=0):
+        """``vk_eval_batch``: recs is a numpy array of EVAL_DTYPE (inputs filled in); returns a copy with the results."""
+        out = np.ascontiguousarray(recs, dtype=_abi.EVAL_DTYPE).copy()
+        self._check(self._L.vk_eval_batch(self._h, out.ctypes.data, len(out), flags))
         return out
 
     def measure_peaks(self):

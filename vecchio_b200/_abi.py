@@ -12,6 +12,9 @@ VK_FLAG_FORCE_BVH = 2
 VK_FLAG_LEGACY_SCATTER = 4
 VK_FLAG_SKY_BACKGROUND = 8
 VK_MEDIUM_XI_SLOTS = 8
+VK_EVAL_BOUNCE, VK_EVAL_BOUNCE_LEGACY, VK_EVAL_TEXTURE, VK_EVAL_LIGHTS_PDF, VK_EVAL_LIGHT_RANDOM = range(5)
+VK_M_LAMBERTIAN, VK_M_METAL, VK_M_DIELECTRIC, VK_M_DIFFUSE_LIGHT, VK_M_ISOTROPIC, VK_M_SPECDIFFUSE = range(6)
+VK_TEX_SOLID, VK_TEX_CHECKER, VK_TEX_IMAGE, VK_TEX_NOISE = range(4)
 VK_RECT_FLIP = 0x100
 
 
@@ -130,4 +133,10 @@ import numpy as _np
 RAY_DTYPE = _np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("time", "<f4"), ("tmin", "<f4"), ("tmax", "<f4")])
 HIT_DTYPE = _np.dtype([("prim", "<u4"), ("face", "<u4"), ("mat", "<u4"), ("front", "<u4"), ("t", "<f4"),
                        ("p", "<f4", 3), ("normal", "<f4", 3), ("u", "<f4"), ("v", "<f4"), ("_pad", "<u4")])
-assert RAY_DTYPE.itemsize == 36 and HIT_DTYPE.itemsize == 56
+# vk_eval (the shading-side parity hook): inputs, then results
+EVAL_DTYPE = _np.dtype([("op", "<u4"), ("index", "<u4"), ("ray_o", "<f4", 3), ("ray_d", "<f4", 3), ("ray_time", "<f4"),
+                        ("p", "<f4", 3), ("normal", "<f4", 3), ("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("front", "<u4"),
+                        ("dir", "<f4", 3), ("xi", "<u4", 5),
+                        ("alive", "<u4"), ("valid", "<u4"), ("out_o", "<f4", 3), ("out_d", "<f4", 3), ("out_time", "<f4"),
+                        ("beta", "<f4", 3), ("L", "<f4", 3), ("value", "<f4")])
+assert RAY_DTYPE.itemsize == 36 and HIT_DTYPE.itemsize == 56 and EVAL_DTYPE.itemsize == 43 * 4

@@ -29,6 +29,7 @@ struct vk_ctx {
     FlatProgram flat{}; // flat.n == 0: scene too large, BVH traversal
     bool has_scene = false;
     uint32_t n_nodes = 0; // BVH nodes of the uploaded scene
+    uint32_t n_materials = 0, n_textures = 0, n_media = 0;
     bool has_specdiffuse = false;
     bool simple_scene = false; // only what the VK_SIMPLE build of the staged kernel keeps (see vk_device.cuh)
     unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
@@ -296,6 +297,9 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
     c->n_nodes = d->n_nodes;
+    c->n_materials = d->n_materials;
+    c->n_textures = d->n_textures;
+    c->n_media = d->n_media;
     c->has_specdiffuse = R.has_specdiffuse;
     c->simple_scene = R.simple;
     c->flat = R.flat;
@@ -357,7 +361,10 @@ static int wf_render(vk_ctx* c, bool strict, const FlatProgram* flat, const DCam
     unsigned long long next_check = min_iters > 8 ? min_iters : 8;
     const unsigned long long max_iters = (min_iters + 2) * (unsigned long long)(a.max_depth ? a.max_depth : 1) + 64; // every path is <= max_depth segments
     for (unsigned long long it = 0;; ++it) {
-        if (it > max_iters) return fail(c, VK_ERR_CUDA, "wavefront: the slot pool did not drain (internal error)");
+        if (it > max_iters) {
+            cudaStreamSynchronize(c->stream); // the kernels already launched still use the accumulators
+            return fail(c, VK_ERR_CUDA, "wavefront: the slot pool did not drain (internal error)");
+        }
         const uint32_t set = (uint32_t)(it & 1u);
         CU(c, strict ? vkstrict::launch_wf_extend(c->scene, flat, a, w, b, set, c->stream)
                      : vkfast::launch_wf_extend(c->scene, flat, a, w, b, set, c->stream));
@@ -641,6 +648,8 @@ int vk_intersect(vk_ctx* c, const vk_ray* rays, size_t n, const float* medium_xi
     if (!c->has_scene) return fail(c, VK_ERR_NO_SCENE, "vk_intersect: no scene uploaded");
     if (n == 0) return VK_OK;
     if (!rays || !out) return fail(c, VK_ERR_INVALID, "vk_intersect: null argument");
+    if (medium_xi && c->n_media > VK_MEDIUM_XI_SLOTS / 2)
+        return fail(c, VK_ERR_UNSUPPORTED, "vk_intersect: the injected variate table holds VK_MEDIUM_XI_SLOTS / 2 media (two visits each); this scene has more");
     CU(c, cudaSetDevice(c->device));
     vk_ray* d_rays = nullptr;
     vk_hit* d_hits = nullptr;
@@ -665,6 +674,39 @@ int vk_intersect(vk_ctx* c, const vk_ray* rays, size_t n, const float* medium_xi
     cudaFree(d_rays);
     cudaFree(d_hits);
     cudaFree(d_xi);
+    return rc;
+}
+
+int vk_eval_batch(vk_ctx* c, vk_eval* recs, size_t n, uint32_t flags) {
+    if (!c) return VK_ERR_INVALID;
+    if (!c->has_scene) return fail(c, VK_ERR_NO_SCENE, "vk_eval_batch: no scene uploaded");
+    if (n == 0) return VK_OK;
+    if (!recs) return fail(c, VK_ERR_INVALID, "vk_eval_batch: null argument");
+    for (size_t i = 0; i < n; ++i) {
+        const vk_eval& e = recs[i];
+        const bool bounce = e.op == VK_EVAL_BOUNCE || e.op == VK_EVAL_BOUNCE_LEGACY;
+        if (e.op > VK_EVAL_LIGHT_RANDOM || (bounce && e.index >= c->n_materials) || (e.op == VK_EVAL_TEXTURE && e.index >= c->n_textures) ||
+            (e.op == VK_EVAL_LIGHT_RANDOM && e.index >= c->scene.n_lights))
+            return fail(c, VK_ERR_INVALID, "vk_eval_batch: record " + std::to_string(i) + ": bad op or index");
+        if (e.op == VK_EVAL_BOUNCE_LEGACY && c->has_specdiffuse)
+            return fail(c, VK_ERR_UNSUPPORTED, "vk_eval_batch: SpecDiffuse has no legacy scatter (src/material.rs:21-28)");
+        if ((e.op == VK_EVAL_BOUNCE || e.op == VK_EVAL_LIGHTS_PDF) && c->scene.n_lights == 0)
+            return fail(c, VK_ERR_INVALID, "vk_eval_batch: empty light list (the reference panics, src/hittable.rs:431)");
+    }
+    CU(c, cudaSetDevice(c->device));
+    vk_eval* d = nullptr;
+    int rc = VK_OK;
+    cudaError_t e;
+#define STEP(call)                                                                                                     \
+    if (rc == VK_OK && (e = (call)) != cudaSuccess) rc = fail(c, VK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e));
+    STEP(cudaMalloc((void**)&d, n * sizeof(vk_eval)))
+    STEP(cudaMemcpyAsync(d, recs, n * sizeof(vk_eval), cudaMemcpyHostToDevice, c->stream))
+    STEP((flags & VK_FLAG_STRICT_MATH) ? vkstrict::launch_eval(c->scene, d, n, c->n_materials, c->n_textures, c->stream)
+                                       : vkfast::launch_eval(c->scene, d, n, c->n_materials, c->n_textures, c->stream))
+    STEP(cudaMemcpyAsync(recs, d, n * sizeof(vk_eval), cudaMemcpyDeviceToHost, c->stream))
+    STEP(cudaStreamSynchronize(c->stream))
+#undef STEP
+    cudaFree(d);
     return rc;
 }
 

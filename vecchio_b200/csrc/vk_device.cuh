@@ -95,20 +95,22 @@ VKD float gen_range(uint32_t x, float lo, float hi) {                           
 struct PathRng {
     uint32_t pixel, sample;
     uint2 key;
-    VKD uint4 block(uint32_t depth, uint32_t blk) const {
-        return philox4x32_10(make_uint4(pixel, sample, (depth << 8) | blk, 0u), key);
+    VKD uint4 block(uint32_t depth, uint32_t blk, uint32_t w = 0u) const {
+        return philox4x32_10(make_uint4(pixel, sample, (depth << 8) | blk, w), key);
     }
 };
 // Source of the ConstantMedium free-flight variate (src/hittable.rs:473): an injected table for
-// vk_intersect, Philox blocks 1..2 of the current segment for the render.
+// vk_intersect (VK_MEDIUM_XI_SLOTS entries per ray: scenes of up to four media), and for the render
+// Philox block 1 of the current segment with the counter's fourth word counting groups of four
+// (medium, visit) pairs -- every medium of a scene draws independently, however many there are.
 struct MediumXi {
     const float* table; // VK_MEDIUM_XI_SLOTS per ray, or nullptr
     PathRng rng;
     uint32_t depth;
     VKD float get(uint32_t medium_index, uint32_t second_visit) const {
-        const uint32_t slot = (medium_index * 2u + second_visit) % VK_MEDIUM_XI_SLOTS;
-        if (table) return table[slot];
-        const uint4 b = rng.block(depth, 1u + (slot >> 2));
+        const uint32_t slot = medium_index * 2u + second_visit;
+        if (table) return table[slot % VK_MEDIUM_XI_SLOTS];
+        const uint4 b = rng.block(depth, 1u, slot >> 2);
         const uint32_t w = (slot & 3u) == 0 ? b.x : ((slot & 3u) == 1 ? b.y : ((slot & 3u) == 2 ? b.z : b.w));
         return u01(w);
     }
@@ -1253,20 +1255,34 @@ VKD void camera_get_ray(const DCamera& cam, const PathRng& rng, uint32_t x, uint
     time = gen_range(r.z, cam.time0, cam.time1);
 }
 
+// Where a bounce takes its variates from: the path's Philox stream (block 0 of the segment; block 9 for
+// SpecDiffuse's choice), or a table the caller supplies (vk_eval, the per-function parity hook).
+struct BounceXiPhilox {
+    const PathRng& rng;
+    uint32_t depth;
+    VKD uint4 block0() const { return rng.block(depth, 0u); }
+    VKD uint32_t spec() const { return rng.block(depth, 9u).x; }
+};
+struct BounceXiTable {
+    uint4 r;
+    uint32_t s;
+    VKD uint4 block0() const { return r; }
+    VKD uint32_t spec() const { return s; }
+};
 // One bounce of ray_color's loop body after world.hit() returned `rec` (src/main.rs:131-149).
 // Returns false when the path ends.  `valid` is cleared when the reference's value would be
 // non-finite (the whole sample is then dropped, src/main.rs:191-194).
-VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
-               float3& beta, float3& L, bool& valid) {
+template <class XI>
+VKD bool shade_xi(const DScene& sc, const HitRecD& rec, const XI& xi, float3& o, float3& d, float& time,
+                  float3& beta, float3& L, bool& valid) {
     uint4 m = rec.m;
     uint32_t type = m.x;
     uint32_t spdf_type = type; // whose scattering_pdf applies
     float3 emitted = f3(0.0f, 0.0f, 0.0f);
     if (!VK_SIMPLE && type == VK_M_SPECDIFFUSE) { // src/material.rs:474-488: emitted() is the trait default (0)
-        const uint4 q = rng.block(depth, 9u);
         const uint32_t diffuse = m.w & ~VKD_MAT_NEEDS_UV;
         spdf_type = __ldg(&sc.materials[diffuse]).x;
-        m = __ldg(&sc.materials[u01(q.x) < __uint_as_float(m.z) ? m.y : diffuse]);
+        m = __ldg(&sc.materials[u01(xi.spec()) < __uint_as_float(m.z) ? m.y : diffuse]);
         type = m.x;
     } else if (type == VK_M_DIFFUSE_LIGHT) { // src/material.rs:218-225; scatter_with_pdf -> None
         if (rec.front) emitted = tex_value(sc, m.y, rec.u, rec.v, rec.p);
@@ -1275,7 +1291,7 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
         L = L + beta * emitted;
         return false;
     }
-    const uint4 r = rng.block(depth, 0u);
+    const uint4 r = xi.block0();
     if (type == VK_M_DIELECTRIC) { // src/material.rs:177-206, attenuation (1,1,1)
         const float ref_idx = __uint_as_float(m.z);
         const float etai_over_etat = rec.front ? 1.0f / ref_idx : ref_idx;
@@ -1336,6 +1352,11 @@ VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_
     d = nd; // Ray::new_with_time(c.p, dir, r.time): keeps the camera-sampled time
     return true;
 }
+VKD bool shade(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
+               float3& beta, float3& L, bool& valid) {
+    const BounceXiPhilox xi = {rng, depth};
+    return shade_xi(sc, rec, xi, o, d, time, beta, L, valid);
+}
 
 // Sample end (src/main.rs:191-194, `c += color` for a finite sample): three integer atomics into the pixel's
 // fixed-point sums (see RenderBuffers), which makes the frame independent of who adds what when.  A zero
@@ -1367,8 +1388,9 @@ VKD float3 miss_color(const RenderArgs& a, float3 d) {
 // Lambertian src/material.rs:85-90 (+ :51-58), Metal :118-132, Dielectric :150-175,
 // DiffuseLight :215-217, Isotropic :442-446.  SpecDiffuse has no legacy method of its own (its
 // default `scatter` unwraps a missing specular ray and panics, :21-28): refused before the launch.
-VKD bool shade_legacy(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
-                      float3& beta, float3& L, bool& valid) {
+template <class XI>
+VKD bool shade_legacy_xi(const DScene& sc, const HitRecD& rec, const XI& xi, float3& o, float3& d, float& time,
+                         float3& beta, float3& L, bool& valid) {
     const uint4 m = rec.m;
     const uint32_t type = m.x;
     if (type == VK_M_DIFFUSE_LIGHT) { // scatter -> None: the path ends with the emission (if lit from the front)
@@ -1379,7 +1401,7 @@ VKD bool shade_legacy(const DScene& sc, const HitRecD& rec, const PathRng& rng, 
         valid = false;
         return false;
     }
-    const uint4 r = rng.block(depth, 0u);
+    const uint4 r = xi.block0();
     float3 nd;
     if (type == VK_M_DIELECTRIC) { // same body as scatter_with_pdf, attenuation (1,1,1), keeps r.time
         const float ref_idx = __uint_as_float(m.z);
@@ -1411,6 +1433,11 @@ VKD bool shade_legacy(const DScene& sc, const HitRecD& rec, const PathRng& rng, 
     d = nd;
     (void)time;
     return true;
+}
+VKD bool shade_legacy(const DScene& sc, const HitRecD& rec, const PathRng& rng, uint32_t depth, float3& o, float3& d, float& time,
+                      float3& beta, float3& L, bool& valid) {
+    const BounceXiPhilox xi = {rng, depth};
+    return shade_legacy_xi(sc, rec, xi, o, d, time, beta, L, valid);
 }
 
 } // namespace VK_NS

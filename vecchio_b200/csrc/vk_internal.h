@@ -203,6 +203,8 @@ struct WfState {
                                  const float* medium_xi, vk_hit* out, cudaStream_t st);                                \
     cudaError_t megakernel_occupancy(bool flat, bool media, bool legacy, int* blocks_per_sm, int* block_threads);      \
     cudaError_t launch_philox_kat(const uint32_t* ctr_key6, uint32_t* out4, cudaStream_t st);                          \
+    cudaError_t launch_eval(const DScene& sc, vk_eval* recs, size_t n, uint32_t n_materials, uint32_t n_textures,      \
+                            cudaStream_t st);                                                                          \
     cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,      \
                               const RenderBuffers& b, unsigned long long* unit_head, int sm_count, cudaStream_t st);   \
     cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,       \

@@ -352,6 +352,61 @@ __global__ void __launch_bounds__(VK_BLOCK) k_intersect_flat(const DScene sc, co
     intersect_body<true>(sc, &flat, rays, n, medium_xi, out);
 }
 
+// vk_eval_batch: the shading-side parity hook (include/vecchio_gpu.h).  One record per thread through the same
+// device functions the render kernels call.
+__global__ void __launch_bounds__(VK_BLOCK) k_eval(const DScene sc, vk_eval* __restrict__ recs, size_t n, uint32_t n_materials,
+                                                   uint32_t n_textures) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vk_eval e = recs[i];
+    const float3 p = f3(e.p[0], e.p[1], e.p[2]);
+    if (e.op == VK_EVAL_BOUNCE || e.op == VK_EVAL_BOUNCE_LEGACY) {
+        if (e.index < n_materials) {
+            HitRecD rec;
+            rec.p = p;
+            rec.normal = f3(e.normal[0], e.normal[1], e.normal[2]);
+            rec.t = e.t;
+            rec.u = e.u;
+            rec.v = e.v;
+            rec.front = e.front ? 1u : 0u;
+            rec.mat = e.index;
+            rec.m = __ldg(&sc.materials[e.index]);
+            float3 o = f3(e.ray_o[0], e.ray_o[1], e.ray_o[2]), d = f3(e.ray_d[0], e.ray_d[1], e.ray_d[2]);
+            float3 beta = f3(1.0f, 1.0f, 1.0f), L = f3(0.0f, 0.0f, 0.0f);
+            float time = e.ray_time;
+            bool valid = true;
+            const BounceXiTable xi = {make_uint4(e.xi[0], e.xi[1], e.xi[2], e.xi[3]), e.xi[4]};
+            const bool alive = e.op == VK_EVAL_BOUNCE ? shade_xi(sc, rec, xi, o, d, time, beta, L, valid)
+                                                      : shade_legacy_xi(sc, rec, xi, o, d, time, beta, L, valid);
+            e.alive = alive ? 1u : 0u;
+            e.valid = valid ? 1u : 0u;
+            e.out_o[0] = o.x; e.out_o[1] = o.y; e.out_o[2] = o.z;
+            e.out_d[0] = d.x; e.out_d[1] = d.y; e.out_d[2] = d.z;
+            e.out_time = time;
+            e.beta[0] = beta.x; e.beta[1] = beta.y; e.beta[2] = beta.z;
+            e.L[0] = L.x; e.L[1] = L.y; e.L[2] = L.z;
+        }
+    } else if (e.op == VK_EVAL_TEXTURE) {
+        if (e.index < n_textures) {
+            const float3 c = tex_value(sc, e.index, e.u, e.v, p);
+            e.beta[0] = c.x; e.beta[1] = c.y; e.beta[2] = c.z;
+        }
+    } else if (e.op == VK_EVAL_LIGHTS_PDF) {
+        e.value = lights_pdf_value(sc, p, f3(e.dir[0], e.dir[1], e.dir[2]));
+    } else if (e.op == VK_EVAL_LIGHT_RANDOM) {
+        if (e.index < sc.n_lights) {
+            const float3 v = light_random(sc, __ldg(&sc.lights[e.index]), p, e.xi[0], e.xi[1], e.xi[2]);
+            e.out_d[0] = v.x; e.out_d[1] = v.y; e.out_d[2] = v.z;
+        }
+    }
+    recs[i] = e;
+}
+cudaError_t launch_eval(const DScene& sc, vk_eval* recs, size_t n, uint32_t n_materials, uint32_t n_textures, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_eval<<<(unsigned)((n + VK_BLOCK - 1) / VK_BLOCK), VK_BLOCK, 0, st>>>(sc, recs, n, n_materials, n_textures);
+    return cudaGetLastError();
+}
+
 __global__ void k_philox_kat(const uint32_t* in6, uint32_t* out4) {
     const uint4 r = philox4x32_10(make_uint4(in6[0], in6[1], in6[2], in6[3]), make_uint2(in6[4], in6[5]));
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;

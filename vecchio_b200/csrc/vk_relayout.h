@@ -29,6 +29,8 @@ struct Validator {
     std::vector<int> node_depth;       // 0 = unvisited
     std::vector<uint8_t> node_medium;  // subtree holds a ConstantMedium
     std::vector<uint8_t> node_inchain; // visited below an instance
+    std::vector<uint8_t> node_xform;   // subtree holds a transform (an instance, or a medium with a transformed boundary)
+    int level = 0;                     // recursion depth of visit() (host stack guard)
 
     bool bad(int c, const std::string& m) {
         if (code == VK_OK) {
@@ -76,21 +78,35 @@ struct Validator {
     }
     // depth of the traversal stack needed below r; also fills node_medium
     int visit(vk_ref r, bool in_chain, bool& has_medium) {
+        bool hx = false;
+        return visit(r, in_chain, has_medium, hx);
+    }
+    int visit(vk_ref r, bool in_chain, bool& has_medium, bool& has_xform) {
         has_medium = false;
+        has_xform = false;
         const uint32_t t = VK_REF_TYPE(r), i = VK_REF_INDEX(r);
         if (t == VK_T_NODE) {
             if (i >= d->n_nodes) return bad(VK_ERR_INVALID, "node index out of range"), 0;
             if (node_depth[i] == -1) return bad(VK_ERR_INVALID, "cycle in the BVH"), 0;
             if (node_depth[i] > 0) {
-                if (in_chain && !node_inchain[i]) node_inchain[i] = 1; // (shape already validated; chain rule rechecked below)
+                // A sub-BVH shared between the world and an instance (a DAG) was validated for the frame it was first
+                // reached in; below an instance it must not hold transforms (trav_prim_step keeps ONE instance frame).
+                if (in_chain && node_xform[i])
+                    return bad(VK_ERR_UNSUPPORTED, "nested instances (a shared sub-BVH holding a transform is also reached below a transform)"), 0;
+                if (in_chain && !node_inchain[i]) node_inchain[i] = 1;
                 has_medium = node_medium[i];
+                has_xform = node_xform[i];
                 return node_depth[i];
             }
+            if (++level > 2 * VKD_STACK) return bad(VK_ERR_UNSUPPORTED, "BVH deeper than the traversal stack"), 0; // before the host stack suffers
             node_depth[i] = -1;
-            bool ml = false, mr = false;
-            const int dl = visit(d->nodes[i].left, in_chain, ml);
-            const int dr = d->nodes[i].right == d->nodes[i].left ? dl : visit(d->nodes[i].right, in_chain, mr);
+            bool ml = false, mr = false, xl = false, xr = false;
+            const int dl = visit(d->nodes[i].left, in_chain, ml, xl);
+            const int dr = d->nodes[i].right == d->nodes[i].left ? dl : visit(d->nodes[i].right, in_chain, mr, xr);
+            --level;
             if (d->nodes[i].right == d->nodes[i].left) mr = ml;
+            node_xform[i] = xl || xr;
+            has_xform = node_xform[i];
             if (code != VK_OK) return 0;
             if (d->nodes[i].right == d->nodes[i].left && ml && VK_REF_TYPE(chain_end(d->nodes[i].left)) != VK_T_MEDIUM)
                 return bad(VK_ERR_UNSUPPORTED, "single-object BVH leaf holding a medium inside a nested BVH"), 0;
@@ -101,10 +117,14 @@ struct Validator {
             return node_depth[i];
         }
         if (t == VK_T_XFORM) {
+            has_xform = true;
             if (in_chain) return bad(VK_ERR_UNSUPPORTED, "nested instances (a transform below another transform's BVH)"), 0;
             const vk_ref end = chain_end(r);
             if (code != VK_OK) return 0;
-            if (VK_REF_TYPE(end) == VK_T_NODE) return 2 + visit(end, true, has_medium);
+            if (VK_REF_TYPE(end) == VK_T_NODE) {
+                bool hx = false;
+                return 2 + visit(end, true, has_medium, hx);
+            }
             if (VK_REF_TYPE(end) == VK_T_MEDIUM) {
                 has_medium = true;
                 medium_ok(end, true);
@@ -117,6 +137,7 @@ struct Validator {
         if (t == VK_T_MEDIUM) {
             has_medium = true;
             medium_ok(r, in_chain);
+            has_xform = i < d->n_media && VK_REF_TYPE(d->media[i].boundary) == VK_T_XFORM;
             return 1;
         }
         if (is_leaf_type(t)) {
@@ -169,6 +190,8 @@ struct Validator {
         node_depth.assign(d->n_nodes, 0);
         node_medium.assign(d->n_nodes, 0);
         node_inchain.assign(d->n_nodes, 0);
+        node_xform.assign(d->n_nodes, 0);
+        level = 0;
         bool hm = false;
         const int depth = visit(d->root, false, hm);
         if (code != VK_OK) return false;
