@@ -1,21 +1,20 @@
 set -x
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-python scripts/diag_furnace.py > gpurun_out/r2_diag_furnace.log 2>&1
-python - > gpurun_out/r2_ab.log 2>&1 <<'PY'
-import time, numpy as np
-import vecchio_b200 as vb
-ctx = vb.Context(0)
-for name, W, H, spp in (("cornell_box", 600, 600, 1000), ("cornell_smoke", 600, 600, 500)):
-    scene = vb.Scene(name); cam = scene.next_camera(); ctx.upload(scene)
-    ref = None
-    for v in (3, 4, 1):
-        for rep in range(3):
-            rgb, _, st = ctx.render(cam, vb.render_params(W, H, spp, 100, seed=1, variant=v))
-        print(name, "variant", v, "ms_kernels %.3f" % st.ms_kernels, "rays/path %.4f" % (st.rays / st.paths), "dropped", st.dropped_samples,
-              "mean %.6f" % rgb.mean(), "Mpaths/s %.1f" % (st.paths / st.ms_kernels / 1e3), flush=True)
-        if ref is None: ref = rgb
-        else: print("   max rel diff of image mean vs variant 3: %.3e" % abs(rgb.mean() / ref.mean() - 1))
-PY
-python -m pytest tests -m gpu -x -q -rxX > gpurun_out/r2_pytest_gpu_0.log 2>&1
-python bench.py > gpurun_out/r2_bench_0.log 2> gpurun_out/r2_bench_0.err
-tail -3 gpurun_out/r2_diag_furnace.log gpurun_out/r2_pytest_gpu_0.log gpurun_out/r2_bench_0.log; cat gpurun_out/r2_ab.log
+python -m pytest tests -m gpu -q -rxXs > gpurun_out/r2_pytest_gpu_1.log 2>&1
+tail -5 gpurun_out/r2_pytest_gpu_1.log
+FLAT="cornell_box:600:600:1000:100:4 cornell_smoke:600:600:500:100:4"
+for tag in a2 a1 a3 b1 b2 c1 c2 a2r8 a2r33; do
+  VECCHIO_GPU_LIB=build/libvk_$tag.so python scripts/_sweep.py $tag $FLAT >> gpurun_out/r2_sweep_1.log 2>&1
+done
+python scripts/_sweep.py default cornell_box:600:600:1000:100:3 cornell_smoke:600:600:500:100:3 cornell_box:600:600:1000:100:4 cornell_smoke:600:600:500:100:4 \
+   final_scene:800:800:64:100:1 final_scene:800:800:64:100:4 random_spheres_demo:400:225:256:50:1 random_spheres_demo:400:225:256:50:4 \
+   stress_spheres@1000:1920:1080:4:50:1 stress_spheres@1000:1920:1080:4:50:4 bowser_demo:600:337:64:50:1 bowser_demo:600:337:64:50:4 >> gpurun_out/r2_sweep_1.log 2>&1
+cat gpurun_out/r2_sweep_1.log
+python scripts/render_once.py cornell 64 4 > gpurun_out/r2_plain_wq.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_warpq -s 1 -c 1 -f -o gpurun_out/prof_r2_warpq_v0 \
+    python scripts/render_once.py cornell 64 4 > gpurun_out/r2_ncu_wq.log 2>&1; echo "full rc=$?"
+python scripts/render_once.py cornell 64 3 > gpurun_out/r2_plain_st.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_staged -s 1 -c 1 -f -o gpurun_out/prof_r2_staged_v0 \
+    python scripts/render_once.py cornell 64 3 > gpurun_out/r2_ncu_st.log 2>&1; echo "full rc=$?"
+python bench.py > gpurun_out/r2_bench_1.log 2> gpurun_out/r2_bench_1.err
+cat gpurun_out/r2_bench_1.log | cut -c1-600

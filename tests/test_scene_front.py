@@ -1,0 +1,89 @@
+"""The product's scene path (vecchio_b200/host/scene.cpp builders -> BVHNode::new -> every lower()) against the oracle's
+own front end (oracle/scene_front.py: the reference's scene.rs / accel.rs / hittable.rs bounding boxes / Perlin::new /
+Camera::new restated independently in Python).  Record by record: every constant, every seeded random draw in the
+reference's draw order, every BVH split and box, the decoded texture bytes (a different PNG decoder), the camera.
+Without this, a wrong constant in scene.cpp or a wrong field in a lower() would be common to both sides of every
+oracle-vs-GPU comparison (the C++ oracle rebuilds its objects from the flattened scene)."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import get_scene
+from oracle import scene_front as sf
+
+NAMES = ["cornell_box", "cornell_smoke", "random_spheres_demo", "final_scene"]
+
+
+@pytest.fixture(scope="module")
+def pairs(vb):
+    out = {}
+    for name in NAMES:
+        scene, cam = get_scene(vb, name, seed=1)
+        out[name] = (sf.build(name, seed=1, assets_dir=vb.ASSETS_DIR), sf.unlower(scene.desc, cam, scene.aspect_ratio), scene)
+    return out
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_lowered_scene_equals_the_independent_front_end(pairs, name):
+    front, product, scene = pairs[name]
+    st = sf.compare(front, product)
+    # almost everything is bit-identical; only values that went through sin / cos / tan may differ in the last place
+    assert st["leaves"] > 100 and st["exact"] >= 0.98 * st["leaves"], st
+    c = scene.census()
+    if name == "cornell_box":
+        assert (c["nodes"], c["rects"], c["boxes"], c["spheres"], c["xforms"], c["lights"]) == (7, 7, 1, 1, 2, 1)
+    if name == "final_scene":
+        assert (c["nodes"], c["boxes"], c["spheres"], c["mspheres"], c["media"], c["perlins"]) == (13 + 511 + 1023, 400, 1006, 1, 2, 1)
+
+
+def test_another_seed_is_another_scene_and_still_agrees(vb):
+    scene = vb.Scene("random_spheres_demo", seed=7)
+    cam = scene.next_camera()
+    sf.compare(sf.build("random_spheres_demo", seed=7, assets_dir=vb.ASSETS_DIR), sf.unlower(scene.desc, cam, scene.aspect_ratio))
+    with pytest.raises(AssertionError):
+        sf.compare(sf.build("random_spheres_demo", seed=1, assets_dir=vb.ASSETS_DIR), sf.unlower(scene.desc, cam, scene.aspect_ratio))
+
+
+def _first(tree, kind):
+    stack = [tree]
+    while stack:
+        n = stack.pop()
+        if isinstance(n, dict):
+            if n.get("kind") == kind:
+                return n
+            stack.extend(n.values())
+        elif isinstance(n, list):
+            stack.extend(n)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind,key", [("rect", "k"), ("rect", "c1"), ("box", "max"), ("sphere", "radius"), ("translate", "offset"),
+                                      ("rotate_y", "sin"), ("dielectric", "ior"), ("solid", "rgb"), ("bvh", "min")])
+def test_the_comparison_notices_one_changed_value(pairs, kind, key):
+    """What the check is for: one constant of scene.cpp, or one field a lower() writes, off by a little."""
+    front, product, _ = pairs["cornell_box"]
+    bad = copy.deepcopy(product)
+    node = _first(bad["world"], kind)
+    node[key] = (np.asarray(node[key], dtype=np.float32) * np.float32(1.0001) + np.float32(1e-4)).astype(np.float32)
+    with pytest.raises(AssertionError):
+        sf.compare(front, bad)
+
+
+def test_the_comparison_notices_structure_changes(pairs):
+    front, product, _ = pairs["cornell_box"]
+    bad = copy.deepcopy(product)
+    r = _first(bad["world"], "rect")
+    r["flip"] = not r["flip"]
+    with pytest.raises(AssertionError):
+        sf.compare(front, bad)
+    bad = copy.deepcopy(product)
+    n = _first(bad["world"], "bvh")
+    n["left"], n["right"] = n["right"], n["left"]
+    with pytest.raises(AssertionError):
+        sf.compare(front, bad)
+    bad = copy.deepcopy(pairs["final_scene"][1])
+    p = _first(bad["world"], "noise")["perlin"]
+    p["perm_y"][3], p["perm_y"][4] = p["perm_y"][4], p["perm_y"][3]
+    with pytest.raises(AssertionError):
+        sf.compare(pairs["final_scene"][0], bad)

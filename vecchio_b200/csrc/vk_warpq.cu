@@ -30,7 +30,7 @@
 namespace VK_NS {
 
 #ifndef VKQ_N
-#define VKQ_N 192 // slots per warp (<= 256: ring indices are bytes)
+#define VKQ_N 192 // slots per warp (<= VKQ_RN <= 256: ring indices are bytes)
 #endif
 #ifndef VKQ_WARPS
 #define VKQ_WARPS 4
@@ -44,6 +44,10 @@ namespace VK_NS {
 #ifndef VKQ_REGEN_MIN
 #define VKQ_REGEN_MIN 16u // ended lanes of a shade batch are regenerated at once when at least this many ended
 #endif
+#ifndef VKQ_RN
+#define VKQ_RN 256 // ring capacity: a power of two >= VKQ_N
+#endif
+#define VKQ_RMASK (VKQ_RN - 1u)
 #define VKQ_CHUNK 256u
 enum { VKQ_EXT = 0, VKQ_END = 1, VKQ_EMIT = 2, VKQ_DIEL = 3, VKQ_METAL = 4, VKQ_DIFF = 5, VKQ_DIFFI = 6, VKQ_NQ = 7, VKQ_NONE = 8 };
 
@@ -51,12 +55,15 @@ struct WqWarp {
     float4 ro[VKQ_N];            // origin.xyz, time
     float4 rd[VKQ_N];            // direction.xyz, bits: depth of the segment to trace
     float4 bt[VKQ_N];            // path weight.xyz, bits: global sample index
-    uint4 hp[VKQ_N];             // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; pixel
-    uint8_t ring[VKQ_NQ][256];   // slot indices, one ring per queue
+    uint4 hp[VKQ_N];             // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; -
+    uint32_t px[VKQ_N];          // pixel of the slot's sample
+    uint8_t ring[VKQ_NQ][VKQ_RN]; // slot indices, one ring per queue
     uint2 ct[8];                 // per queue: .x = entries, .y = ring write position
     uint32_t cur_s, cur_p, left; // unit cursor: next unit is (sample cur_s, pixel cur_p), `left` units remain in the chunk
     uint32_t exhausted;          // the global unit counter has run past the end
 };
+
+static_assert((VKQ_RN & (VKQ_RN - 1)) == 0 && VKQ_RN >= VKQ_N && VKQ_RN <= 256, "ring capacity: power of two, >= slots, byte indices");
 
 struct WqCtx {
     const DCamera& cam;
@@ -80,7 +87,7 @@ VKD void wq_push(WqWarp& S, uint32_t cls, uint32_t slot, uint32_t lane, uint32_t
         S.ct[cls] = make_uint2(c.x + (uint32_t)__popc(m), c.y + (uint32_t)__popc(m));
     }
     pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-    if (cls != VKQ_NONE) S.ring[cls][(pos + __popc(m & below)) & 255u] = (uint8_t)slot;
+    if (cls != VKQ_NONE) S.ring[cls][(pos + __popc(m & below)) & VKQ_RMASK] = (uint8_t)slot;
     __syncwarp();
 }
 
@@ -151,7 +158,7 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
         S.ro[slot] = make_float4(o.x, o.y, o.z, time);
         S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(1u)); // ray_color(ray, .., 1)
         S.bt[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng.sample));
-        S.hp[slot].w = p;
+        S.px[slot] = p;
     }
     return got;
 }
@@ -227,7 +234,7 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
         __syncwarp();
         if (lane == 0) S.ct[q].x = n_q - n;
         __syncwarp();
-        // (the entries [head, head + n) stay readable: pushes only write at the ring's tail, and a ring holds 256 >= VKQ_N entries)
+        // (the entries [head, head + n) stay readable: pushes only write at the ring's tail, and a ring holds VKQ_RN >= VKQ_N entries)
 
         if (q == VKQ_EXT) {
             // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------
@@ -241,7 +248,7 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
                 for (int k = 0; k < VKQ_K; ++k) {
                     const uint32_t e = lane + 32u * k;
                     live[k] = e < n;
-                    slot[k] = S.ring[VKQ_EXT][(head + (live[k] ? e : 0u)) & 255u];
+                    slot[k] = S.ring[VKQ_EXT][(head + (live[k] ? e : 0u)) & VKQ_RMASK];
                     const float4 ro = S.ro[slot[k]], rd = S.rd[slot[k]];
                     o[k] = f3(ro);
                     d[k] = f3(rd);
@@ -249,7 +256,7 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
                     xi[k].table = nullptr;
                     xi[k].depth = __float_as_uint(rd.w);
                     xi[k].rng.key = make_uint2(a.seed_lo, a.seed_hi);
-                    xi[k].rng.pixel = MEDIA ? S.hp[slot[k]].w : 0u;
+                    xi[k].rng.pixel = MEDIA ? S.px[slot[k]] : 0u;
                     xi[k].rng.sample = MEDIA ? __float_as_uint(S.bt[slot[k]].w) : 0u;
                 }
                 trace_flat_k<VKQ_K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit);
@@ -268,16 +275,13 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
                             hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);
                             cls = fh.cls == 0u ? VKQ_EMIT : fh.cls == 1u ? VKQ_DIEL : fh.cls == 2u ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
                         }
-                        uint4& hp = S.hp[slot[k]];
-                        hp.x = __float_as_uint(best_t[k]);
-                        hp.y = prim;
-                        hp.z = hi;
+                        S.hp[slot[k]] = make_uint4(__float_as_uint(best_t[k]), prim, hi, 0u);
                     }
                     if (k == 0 || n > 32u * k) wq_push(S, cls, slot[k], lane, below); // (warp-uniform condition)
                 }
             } else {
                 const bool live = lane < n;
-                const uint32_t slot = S.ring[VKQ_EXT][(head + (live ? lane : 0u)) & 255u];
+                const uint32_t slot = S.ring[VKQ_EXT][(head + (live ? lane : 0u)) & VKQ_RMASK];
                 uint32_t cls = VKQ_NONE;
                 if (live) {
                     const float4 ro = S.ro[slot], rd = S.rd[slot];
@@ -285,17 +289,14 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
                     xi.table = nullptr;
                     xi.depth = __float_as_uint(rd.w);
                     xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
-                    xi.rng.pixel = MEDIA ? S.hp[slot].w : 0u;
+                    xi.rng.pixel = MEDIA ? S.px[slot] : 0u;
                     xi.rng.sample = MEDIA ? __float_as_uint(S.bt[slot].w) : 0u;
                     TraceCounters tc = {0u, 0u};
                     const TraceHit h = trace<MEDIA>(sc, f3(ro), f3(rd), ro.w, 0.001f, CUDART_INF_F, xi, tc);
                     ++n_rays;
                     n_nodes += tc.nodes;
                     n_prims += tc.prims;
-                    uint4& hp = S.hp[slot];
-                    hp.x = __float_as_uint(h.t);
-                    hp.y = h.prim;
-                    hp.z = (h.inst ? (0x80000000u | VKD_INDEX(h.inst)) : 0u) | (h.face << 28);
+                    S.hp[slot] = make_uint4(__float_as_uint(h.t), h.prim, (h.inst ? (0x80000000u | VKD_INDEX(h.inst)) : 0u) | (h.face << 28), 0u);
                     cls = h.prim == VK_REF_NONE ? (uint32_t)VKQ_EMIT : wq_class_of(sc, h.prim, h.inst);
                 }
                 wq_push(S, cls, slot, lane, below);
@@ -304,7 +305,7 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
         }
 
         const bool act = lane < n;
-        const uint32_t slot = S.ring[q][(head + (act ? lane : 0u)) & 255u];
+        const uint32_t slot = S.ring[q][(head + (act ? lane : 0u)) & VKQ_RMASK];
         bool alive = false, ended = false;
         if (q != VKQ_END) {
             // ---- shade one class: resolve + scatter (src/main.rs:131-149); a finished sample goes through the NaN / Inf
@@ -315,7 +316,7 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
                 float3 o = f3(ro), d = f3(rd), beta = f3(bt), L = f3(0.0f, 0.0f, 0.0f);
                 float time = ro.w;
                 uint32_t depth = __float_as_uint(rd.w);
-                const uint32_t pixel = hp.w, prim = hp.y;
+                const uint32_t pixel = S.px[slot], prim = hp.y;
                 bool valid = true;
                 if (prim == VK_REF_NONE) {
                     L = beta * miss_color(a, d); // src/main.rs:151
