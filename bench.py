@@ -11,8 +11,12 @@ reduce to rank 0 (strong scaling: the frame is fixed).
 
 One JSON line on stdout (rank 0).  `value` = whole-job Mpaths/s with the scene resident in HBM,
 timed with CUDA events on the stream every kernel and the reduce run on, max over ranks.
-`e2e` = the same metric through the C ABI with host buffers: per step the flattened scene is
-uploaded again (H2D) and the finished image is copied back (D2H) inside the timed region.
+`e2e` = the same metric through the reference-facing calls with HOST buffers: per step `vk_scene_upload`
+of the flattened scene (H2D) and ONE `vk_render` call whose output is the caller's host frame (D2H inside);
+with N > 1 ranks each rank's `vk_render_device` slice, the NCCL reduce and the D2H on rank 0.
+`roofline` follows SURVEY 8(d): max(algorithmic flops / FP32 peak, algorithmic bytes / bandwidth of the level
+the scene's working set lives in), the bound named by whichever is larger.  `other_configs` (N = 1 only)
+are short runs of BASELINE.json's other four configurations so that they appear in the driver's record too.
 `--impl reference` times the CPU restatement of the reference (oracle/, the Rust itself cannot be
 built here) on the host cores with the same config, on a bounded sample of the frame's spp.
 """
@@ -101,6 +105,46 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+VARIANT_NAMES = {1: "megakernel", 2: "wavefront", 3: "staged", 4: "warpq"}
+
+
+def kernel_of(kst, scene):
+    flat_program = kst.node_visits == 0  # the flat traversal program visits no BVH node
+    return {1: "k_megakernel_flat" if flat_program else ("k_megakernel_dyn" if scene.desc.n_nodes >= 65536 else "k_megakernel"),
+            2: "k_wf_extend + k_wf_shade", 3: "k_staged_flat" if flat_program else "k_staged",
+            4: "k_warpq_flat" if flat_program else "k_warpq"}.get(kst.variant, "?")
+
+
+def make_roofline(config, variant_name, kernel_name, aw, k_rays, k_ms, fp32_peak, l2_gbs, peaks, scene_bytes):
+    """achieved = max(flops_alg * rays/s / FP32 peak, bytes_alg * rays/s / bandwidth of the bound level).
+    The level is where the TRAVERSAL working set (nodes + primitives, texels excluded) lives.  SURVEY 8(d): configs 1-4
+    are KBs to ~2 MB, L1 / L2 resident and re-read by every ray -> no bandwidth bound is claimed, FP32 issue is the
+    roofline; config 5 (64 MB of wide nodes + 20 MB of spheres, random access) is L2-bandwidth bound (peak: the L2 read
+    microbenchmark measured live); anything over 100 MB would be HBM (peak: MEASURED_PEAKS.json).
+    Units per launch = ray segments traced by that launch (vk_stats.rays)."""
+    flops_ray, bytes_ray = aw.get("flops_per_ray"), aw.get("bytes_per_ray")
+    if not flops_ray or not k_ms:
+        return None
+    rate = k_rays / (k_ms * 1e-3)
+    f_ach, f_frac = flops_ray * rate / 1e12, flops_ray * rate / 1e12 / fp32_peak
+    level = "l1" if scene_bytes <= (4 << 20) else ("l2" if scene_bytes <= (100 << 20) else "hbm")
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    b_peak = {"l1": None, "l2": l2_gbs, "hbm": hbm_peak}[level]
+    b_ach = bytes_ray * rate / 1e9 if bytes_ray else None
+    b_frac = b_ach / b_peak if (b_ach and b_peak) else None
+    views = {"fp32": {"achieved": f_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": f_frac, "alg_flops_per_ray": flops_ray,
+                      "peak_source": "FFMA microbenchmark vk_measure_peaks, measured live (MEASURED_PEAKS.json has no fp32 figure)"},
+             "bytes": {"level": level, "achieved": b_ach, "peak": b_peak, "unit": "GB/s", "frac": b_frac, "alg_bytes_per_ray": bytes_ray,
+                       "peak_source": {"l1": "traversal working set <= 4 MB, L1 / L2 / constant-bank resident: no bandwidth bound claimed",
+                                       "l2": "L2-resident 32 MiB read microbenchmark vk_measure_peaks, measured live",
+                                       "hbm": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}[level]}}
+    use_bytes = b_frac is not None and b_frac > f_frac
+    r = {"bound": level if use_bytes else "fp32", "achieved": b_ach if use_bytes else f_ach, "peak": b_peak if use_bytes else fp32_peak,
+         "unit": "GB/s" if use_bytes else "TFLOP/s", "frac": b_frac if use_bytes else f_frac,
+         "traffic": ncu_traffic(config, variant_name), "kernel": kernel_name, "kernel_ms": k_ms, "views": views}
+    return r
+
+
 def run_reference(args, cfg):
     """The reference's CPU implementation of the path (its C++ restatement, oracle/) on all host
     cores: same scene, resolution, depth; each step renders a bounded `cpu_spp` slice."""
@@ -183,8 +227,16 @@ def run_ours(args, cfg):
         if rank == 0:
             ctx.finalize_device(d_sum.data_ptr(), d_rgb.data_ptr(), n, spp)
 
+    h_frame = np.empty(n, dtype=np.float32)  # the caller's (pageable) host frame, as a Rust Vec<Vec3> would be
+
     def step_e2e(seed):
-        ctx.upload(scene)  # H2D of the flattened scene (host arrays -> device), every step
+        ctx.upload(scene)  # vk_scene_upload: H2D of the flattened scene (host arrays -> device), every step
+        if world == 1:     # the plugin call itself: vk_render(host params) -> host frame (D2H + copy-out inside)
+            import ctypes as C
+            st_ = vb.vk_stats()
+            p_ = params(seed)
+            ctx._check(ctx._L.vk_render(ctx._h, C.byref(cam), C.byref(p_), h_frame.ctypes.data, None, C.byref(st_)))
+            return
         step_device(seed)
         if rank == 0:
             h_rgb.copy_(d_rgb, non_blocking=True)  # D2H of the finished frame
@@ -230,10 +282,8 @@ def run_ours(args, cfg):
     # ---- kernel-only time of the dominant kernel (CUDA events inside the library) ---------------
     kst = ctx.render_device(cam, params(77), d_sum.data_ptr(), want_stats=True)
     k_ms, k_rays, k_paths = kst.ms_kernels, kst.rays, kst.paths
-    variant_name = {1: "megakernel", 2: "wavefront", 3: "staged"}.get(kst.variant, str(kst.variant))
-    flat_program = kst.node_visits == 0  # the flat traversal program visits no BVH node
-    kernel_name = ({1: "k_megakernel_flat" if flat_program else ("k_megakernel_dyn" if scene.desc.n_nodes >= 65536 else "k_megakernel"),
-                    2: "k_wf_extend + k_wf_shade", 3: "k_staged_flat" if flat_program else "k_staged"}.get(kst.variant, "?"))
+    variant_name = VARIANT_NAMES.get(kst.variant, str(kst.variant))
+    kernel_name = kernel_of(kst, scene)
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------
     for i in range(2):
@@ -252,17 +302,7 @@ def run_ours(args, cfg):
         fp32_peak, l2_gbs = ctx.measure_peaks()
         aw = alg_work(scene_name) or {}
         flops_ray, bytes_ray = aw.get("flops_per_ray"), aw.get("bytes_per_ray")
-        roofline = None
-        if flops_ray:
-            achieved = flops_ray * k_rays / (k_ms * 1e-3) / 1e12
-            roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                        "traffic": ncu_traffic(args.config, variant_name),
-                        "kernel": kernel_name, "kernel_ms": k_ms, "alg_flops_per_ray": flops_ray,
-                        "peak_source": "FFMA microbenchmark vk_measure_peaks, measured live (MEASURED_PEAKS.json has no fp32 figure)",
-                        "hbm_view": {"alg_bytes_per_ray": bytes_ray, "achieved_gbs": bytes_ray * k_rays / (k_ms * 1e-3) / 1e9 if bytes_ray else None,
-                                     "peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "measured" if peaks else "fallback",
-                                     "l2_gbs_measured": l2_gbs,
-                                     "note": "scene is cache-resident (KBs): these bytes are L1/L2 hits, not DRAM traffic"}}
+        roofline = make_roofline(args.config, variant_name, kernel_name, aw, k_rays, k_ms, fp32_peak, l2_gbs, peaks, scene.nbytes() - int(scene.desc.n_texel_bytes))
         line = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "mrays_per_s": mrays, "rays_per_path": rays / paths,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

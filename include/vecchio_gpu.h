@@ -335,6 +335,24 @@ int vk_set_stream(vk_ctx* ctx, void* stream);
  * its counts to be collected here. */
 int vk_flush_stats(vk_ctx* ctx, vk_stats* stats);
 
+/* One context over several GPUs of a node: what replaces the rayon pool of src/main.rs:181 when the host has more
+ * than one device.  The frame's samples are split by GLOBAL sample index (device k of N renders
+ * [k * count / N, (k + 1) * count / N) of the requested range, for every pixel), every device keeps its slice in
+ * 64-bit fixed-point accumulators, and device devices[0] adds its peers' accumulators to its own with a kernel that
+ * reads them over NVLink (peer-mapped memory; no communicator, no host staging).  Integer addition: the frame is
+ * bit-identical to the frame one GPU renders for the same seed, whatever N.  Same conventions as the single-device
+ * calls; vk_multi_last_error(NULL) reports a failed vk_multi_create. */
+typedef struct vk_multi vk_multi;
+int vk_multi_create(const int* devices, int n_devices, vk_multi** out);
+void vk_multi_destroy(vk_multi* m);
+const char* vk_multi_last_error(const vk_multi* m);
+int vk_multi_device_count(const vk_multi* m);
+int vk_multi_scene_upload(vk_multi* m, const vk_scene_desc* scene);            /* the scene is replicated on every device */
+int vk_multi_render(vk_multi* m, const vk_camera* cam, const vk_render_params* params, float* out_rgb, float* out_sumsq,
+                    vk_stats* stats);                                           /* vk_render over all devices              */
+int vk_multi_render_rgb8(vk_multi* m, const vk_camera* cam, const vk_render_params* params, uint8_t* out_rgb8,
+                         vk_stats* stats);                                      /* vk_render_rgb8 over all devices         */
+
 /* Parity hook: closest hit of `world.hit(&r, tmin, tmax)` (src/accel.rs:58-83) for
  * a batch of rays.  medium_xi (nullable): n * VK_MEDIUM_XI_SLOTS uniform variates
  * for ConstantMedium::hit's free-flight draw (src/hittable.rs:473). */

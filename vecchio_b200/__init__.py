@@ -94,6 +94,17 @@ def gpu_lib():
         L.vk_eval_batch.argtypes = [vp, vp, C.c_size_t, C.c_uint32]
         L.vk_measure_peaks.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.vk_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+        L.vk_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+        L.vk_multi_destroy.argtypes = [vp]
+        L.vk_multi_destroy.restype = None
+        L.vk_multi_last_error.argtypes = [vp]
+        L.vk_multi_last_error.restype = C.c_char_p
+        L.vk_multi_device_count.argtypes = [vp]
+        L.vk_multi_scene_upload.argtypes = [vp, C.POINTER(_abi.vk_scene_desc)]
+        L.vk_multi_render.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, vp, C.POINTER(_abi.vk_stats)]
+        L.vk_multi_render_rgb8.argtypes = [vp, C.POINTER(_abi.vk_camera), C.POINTER(_abi.vk_render_params), vp, C.POINTER(_abi.vk_stats)]
+        for f in ("vk_multi_create", "vk_multi_device_count", "vk_multi_scene_upload", "vk_multi_render", "vk_multi_render_rgb8"):
+            getattr(L, f).restype = C.c_int
         for f in ("vk_create", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device", "vk_finalize_device",
                   "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_eval_batch", "vk_measure_peaks", "vk_device_info"):
             getattr(L, f).restype = C.c_int
@@ -103,7 +114,8 @@ def gpu_lib():
 
 GPU_SYMBOLS = ["vk_create", "vk_destroy", "vk_last_error", "vk_scene_check", "vk_scene_upload", "vk_render", "vk_render_rgb8", "vk_render_device",
                "vk_finalize_device", "vk_set_stream", "vk_flush_stats", "vk_intersect", "vk_eval_batch", "vk_measure_peaks",
-               "vk_device_info"]
+               "vk_device_info", "vk_multi_create", "vk_multi_destroy", "vk_multi_last_error", "vk_multi_device_count",
+               "vk_multi_scene_upload", "vk_multi_render", "vk_multi_render_rgb8"]
 HOST_SYMBOLS = ["vkh_scene_build", "vkh_scene_free", "vkh_scene_desc", "vkh_scene_aspect_ratio",
                 "vkh_scene_next_camera", "vkh_camera_new", "vkh_decode_png", "vkh_frame_to_rgb8", "vkh_write_ppm",
                 "vkh_frame_filename", "vkh_last_error"]
@@ -321,6 +333,54 @@ class Context:
     def close(self):
         if getattr(self, "_h", None):
             self._L.vk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiContext:
+    """``vk_multi_create``: one context over several GPUs of the node (spp slices per device, the peers' integer
+    accumulators added on the first device over NVLink).  Same frame as one GPU, bit for bit."""
+
+    def __init__(self, devices):
+        L = gpu_lib()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = L.vk_multi_create(arr, len(devices), C.byref(h))
+        if rc != 0:
+            raise VecchioError(rc, (L.vk_multi_last_error(None) or b"").decode())
+        self._h, self._L, self.devices = h, L, list(devices)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VecchioError(rc, (self._L.vk_multi_last_error(self._h) or b"").decode())
+
+    def upload(self, scene):
+        self._check(self._L.vk_multi_scene_upload(self._h, scene.desc_ptr))
+
+    def render(self, cam, params, want_sumsq=False):
+        n = params.width * params.height * 3
+        rgb = np.empty(n, dtype=np.float32)
+        sq = np.empty(n, dtype=np.float32) if want_sumsq else None
+        st = _abi.vk_stats()
+        self._check(self._L.vk_multi_render(self._h, C.byref(cam), C.byref(params), rgb.ctypes.data,
+                                            sq.ctypes.data if want_sumsq else None, C.byref(st)))
+        shape = (params.height, params.width, 3)
+        return rgb.reshape(shape), (sq.reshape(shape) if want_sumsq else None), st
+
+    def render_rgb8(self, cam, params):
+        out = np.empty(params.width * params.height * 3, dtype=np.uint8)
+        st = _abi.vk_stats()
+        self._check(self._L.vk_multi_render_rgb8(self._h, C.byref(cam), C.byref(params), out.ctypes.data, C.byref(st)))
+        return out.reshape(params.height, params.width, 3), st
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vk_multi_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -418,10 +418,14 @@ static bool use_dynamic_megakernel(const vk_ctx* c) {
 }
 
 // shared body of vk_render / vk_render_device
-static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* d_sum, float* d_sumsq, vk_stats* stats) {
+// acc_only: leave the result in the context's integer accumulators (c->partial) and skip the conversion to fp32 sums
+// (the multi-GPU context reduces the accumulators of all its devices itself); want_sq then says whether squares are kept
+static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float* d_sum, float* d_sumsq, vk_stats* stats,
+                       bool acc_only = false, bool want_sq = false) {
     if (!c) return VK_ERR_INVALID;
     if (!c->has_scene) return fail(c, VK_ERR_NO_SCENE, "render: no scene uploaded");
-    if (!cam || !P || !d_sum) return fail(c, VK_ERR_INVALID, "render: null argument");
+    if (!cam || !P || (!d_sum && !acc_only)) return fail(c, VK_ERR_INVALID, "render: null argument");
+    if (!acc_only) want_sq = d_sumsq != nullptr;
     if (P->width < 2 || P->height < 2) return fail(c, VK_ERR_INVALID, "render: width/height must be >= 2 ((width-1) divides, src/main.rs:187)");
     if (P->spp == 0 || P->spp_begin >= P->spp) return fail(c, VK_ERR_INVALID, "render: bad spp / spp_begin");
     const uint32_t count = P->spp_count ? P->spp_count : P->spp - P->spp_begin;
@@ -463,11 +467,11 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     b.counters = c->counters;
     b.debug = c->debug;
     {
-        const int rc = ensure(c, &c->partial, &c->partial_floats, plane * (d_sumsq ? 4 : 2));
+        const int rc = ensure(c, &c->partial, &c->partial_floats, plane * (want_sq ? 4 : 2));
         if (rc != VK_OK) return rc;
         b.acc = (unsigned long long*)c->partial;
-        b.accsq = d_sumsq ? (double*)(c->partial + plane * 2) : nullptr;
-        CU(c, cudaMemsetAsync(c->partial, 0, plane * (d_sumsq ? 4 : 2) * sizeof(float), c->stream));
+        b.accsq = want_sq ? (double*)(c->partial + plane * 2) : nullptr;
+        CU(c, cudaMemsetAsync(c->partial, 0, plane * (want_sq ? 4 : 2) * sizeof(float), c->stream));
     }
     // Lane megakernel: chunks of samples, sized for ~48 work items per resident warp (small items keep
     // the end-of-kernel tail short; an item costs one atomic).
@@ -518,8 +522,10 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
                      : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, legacy, c->stream));
         launches = 1;
     }
-    k_acc_to_sum<<<(unsigned)((plane + 255) / 256), 256, 0, c->stream>>>(b.acc, b.accsq, plane, d_sum, d_sumsq);
-    ++launches;
+    if (!acc_only) {
+        k_acc_to_sum<<<(unsigned)((plane + 255) / 256), 256, 0, c->stream>>>(b.acc, b.accsq, plane, d_sum, d_sumsq);
+        ++launches;
+    }
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->ev1, c->stream));
     c->launches += launches;
@@ -675,6 +681,223 @@ int vk_intersect(vk_ctx* c, const vk_ray* rays, size_t n, const float* medium_xi
     cudaFree(d_hits);
     cudaFree(d_xi);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One context over several GPUs of a node: the frame's samples are split by global sample
+// index, device k renders [k * spp / N, (k + 1) * spp / N) of every pixel into ITS integer accumulators,
+// and device 0 adds the accumulators of its peers to its own by reading them over NVLink (peer-mapped
+// loads from a reduce kernel: no staging copies, no host round trip, no communicator).  Integer sums:
+// the frame is bit-identical to the one a single GPU renders for the same seed.
+// ------------------------------------------------------------------------------------------------
+#define VK_MULTI_MAX 16
+struct PeerAcc {
+    const unsigned long long* acc[VK_MULTI_MAX];
+    const double* accsq[VK_MULTI_MAX];
+    int n;
+};
+__global__ void k_reduce_peers(PeerAcc pa, size_t n, float* __restrict__ sum, float* __restrict__ sumsq) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long a = 0;
+    for (int k = 0; k < pa.n; ++k) a += (long long)pa.acc[k][i]; // device 0's own buffer first, then the peers' (NVLink loads)
+    sum[i] = (float)((double)a * VK_ACC_INV_SCALE);
+    if (sumsq) {
+        double q = 0.0;
+        for (int k = 0; k < pa.n; ++k) q += pa.accsq[k][i];
+        sumsq[i] = (float)q;
+    }
+}
+struct vk_multi {
+    std::vector<vk_ctx*> ctx;
+    std::vector<cudaEvent_t> done; // device k's slice has finished (recorded on its stream)
+    std::string err;
+};
+static thread_local std::string g_multi_err;
+static int mfail(vk_multi* m, int code, const std::string& msg) {
+    if (m) m->err = msg;
+    else g_multi_err = msg;
+    return code;
+}
+
+int vk_multi_create(const int* devices, int n, vk_multi** out) {
+    if (!out) return mfail(nullptr, VK_ERR_INVALID, "vk_multi_create: null out pointer");
+    *out = nullptr;
+    if (!devices || n < 1 || n > VK_MULTI_MAX) return mfail(nullptr, VK_ERR_INVALID, "vk_multi_create: 1 .. 16 devices");
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return mfail(nullptr, VK_ERR_INVALID, "vk_multi_create: a device is listed twice");
+    vk_multi* m = new vk_multi;
+    for (int i = 0; i < n; ++i) {
+        vk_ctx* c = nullptr;
+        const int rc = vk_create(devices[i], &c);
+        if (rc != VK_OK) {
+            g_multi_err = std::string("vk_multi_create: ") + vk_last_error(nullptr);
+            vk_multi_destroy(m);
+            return rc;
+        }
+        m->ctx.push_back(c);
+        cudaEvent_t ev = nullptr;
+        cudaSetDevice(devices[i]);
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        m->done.push_back(ev);
+    }
+    // device 0 reads every peer's accumulators
+    cudaSetDevice(devices[0]);
+    for (int i = 1; i < n; ++i) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
+        if (!can) {
+            g_multi_err = "vk_multi_create: device " + std::to_string(devices[0]) + " cannot map the memory of device " + std::to_string(devices[i]) +
+                          " (no peer access); there is no staged fallback";
+            vk_multi_destroy(m);
+            return VK_ERR_UNSUPPORTED;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devices[i], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            g_multi_err = std::string("vk_multi_create: cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+            vk_multi_destroy(m);
+            return VK_ERR_CUDA;
+        }
+        cudaGetLastError();
+    }
+    *out = m;
+    return VK_OK;
+}
+void vk_multi_destroy(vk_multi* m) {
+    if (!m) return;
+    for (size_t i = 0; i < m->ctx.size(); ++i) {
+        if (i < m->done.size() && m->done[i]) {
+            cudaSetDevice(m->ctx[i]->device);
+            cudaEventDestroy(m->done[i]);
+        }
+        vk_destroy(m->ctx[i]);
+    }
+    delete m;
+}
+const char* vk_multi_last_error(const vk_multi* m) { return m ? m->err.c_str() : g_multi_err.c_str(); }
+int vk_multi_device_count(const vk_multi* m) { return m ? (int)m->ctx.size() : 0; }
+
+int vk_multi_scene_upload(vk_multi* m, const vk_scene_desc* scene) {
+    if (!m) return VK_ERR_INVALID;
+    for (vk_ctx* c : m->ctx) {
+        const int rc = vk_scene_upload(c, scene);
+        if (rc != VK_OK) return mfail(m, rc, c->err);
+    }
+    return VK_OK;
+}
+
+// shared body of vk_multi_render / vk_multi_render_rgb8: every device accumulates its slice, device 0 reduces
+static int multi_render_sums(vk_multi* m, const vk_camera* cam, const vk_render_params* P, bool want_sq, float** d_sum, float** d_sq, vk_stats* st) {
+    if (!m || !cam || !P) return mfail(m, VK_ERR_INVALID, "vk_multi_render: null argument");
+    const int n = (int)m->ctx.size();
+    const uint32_t begin = P->spp_begin, count = P->spp_count ? P->spp_count : (P->spp > P->spp_begin ? P->spp - P->spp_begin : 0u);
+    if (P->spp == 0 || count == 0 || (uint64_t)begin + count > P->spp) return mfail(m, VK_ERR_INVALID, "vk_multi_render: bad spp range");
+    vk_ctx* c0 = m->ctx[0];
+    const size_t plane = (size_t)P->width * P->height * 3;
+    cudaSetDevice(c0->device);
+    cudaEventRecord(c0->ev2, c0->stream);
+    int active = 0;
+    PeerAcc pa{};
+    for (int k = 0; k < n; ++k) { // global samples [begin + k * count / n, begin + (k + 1) * count / n)
+        const uint32_t s0 = begin + (uint32_t)((uint64_t)count * k / n), s1 = begin + (uint32_t)((uint64_t)count * (k + 1) / n);
+        if (s1 == s0) continue; // more devices than samples
+        vk_render_params q = *P;
+        q.spp_begin = s0;
+        q.spp_count = s1 - s0;
+        vk_ctx* c = m->ctx[k];
+        const int rc = render_into(c, cam, &q, nullptr, nullptr, nullptr, true, want_sq);
+        if (rc != VK_OK) return mfail(m, rc, c->err);
+        cudaSetDevice(c->device);
+        cudaEventRecord(m->done[k], c->stream);
+        pa.acc[active] = (const unsigned long long*)c->partial;
+        pa.accsq[active] = want_sq ? (const double*)(c->partial + plane * 2) : nullptr;
+        ++active;
+    }
+    // device 0's stream waits for every slice, then reads the peers' accumulators
+    cudaSetDevice(c0->device);
+    for (int k = 0; k < n; ++k) cudaStreamWaitEvent(c0->stream, m->done[k], 0);
+    int rc = ensure(c0, &c0->frame, &c0->frame_floats, plane * 3);
+    if (rc != VK_OK) return mfail(m, rc, c0->err);
+    *d_sum = c0->frame;
+    *d_sq = want_sq ? c0->frame + plane : nullptr;
+    pa.n = active;
+    k_reduce_peers<<<(unsigned)((plane + 255) / 256), 256, 0, c0->stream>>>(pa, plane, *d_sum, *d_sq);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return mfail(m, VK_ERR_CUDA, std::string("k_reduce_peers: ") + cudaGetErrorString(e));
+    c0->launches += 1;
+    // counters of all devices (synchronises each)
+    vk_stats total{};
+    float ms_max = 0.0f;
+    for (int k = 0; k < n; ++k) {
+        vk_stats s{};
+        vk_ctx* c = m->ctx[k];
+        if ((rc = vk_flush_stats(c, &s)) != VK_OK) return mfail(m, rc, c->err);
+        float ms = 0.0f;
+        if (s.paths) cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        ms_max = ms > ms_max ? ms : ms_max;
+        total.paths += s.paths; total.rays += s.rays; total.dropped_samples += s.dropped_samples;
+        total.node_visits += s.node_visits; total.prim_tests += s.prim_tests; total.launches += s.launches;
+    }
+    total.ms_kernels = ms_max; // the slowest device's render kernels
+    total.variant = VK_VARIANT_AUTO;
+    *st = total;
+    return VK_OK;
+}
+static int multi_pinned(vk_multi* m, vk_ctx* c0, size_t floats) {
+    if (c0->pinned_floats >= floats) return VK_OK;
+    if (c0->pinned) cudaFreeHost(c0->pinned);
+    c0->pinned = nullptr;
+    c0->pinned_floats = 0;
+    if (cudaMallocHost((void**)&c0->pinned, floats * sizeof(float)) != cudaSuccess) return mfail(m, VK_ERR_OOM, "vk_multi_render: pinned staging");
+    c0->pinned_floats = floats;
+    return VK_OK;
+}
+int vk_multi_render(vk_multi* m, const vk_camera* cam, const vk_render_params* P, float* out_rgb, float* out_sumsq, vk_stats* stats) {
+    if (!m || !P || !out_rgb) return mfail(m, VK_ERR_INVALID, "vk_multi_render: null argument");
+    float *d_sum = nullptr, *d_sq = nullptr;
+    vk_stats st{};
+    int rc = multi_render_sums(m, cam, P, out_sumsq != nullptr, &d_sum, &d_sq, &st);
+    if (rc != VK_OK) return rc;
+    vk_ctx* c0 = m->ctx[0];
+    const size_t plane = (size_t)P->width * P->height * 3;
+    if ((rc = multi_pinned(m, c0, plane * 2)) != VK_OK) return rc;
+    cudaSetDevice(c0->device);
+    float* d_rgb = c0->frame + 2 * plane;
+    k_finalize<<<(unsigned)((plane + 255) / 256), 256, 0, c0->stream>>>(d_sum, d_rgb, plane, (float)P->spp);
+    cudaMemcpyAsync(c0->pinned, d_rgb, plane * sizeof(float), cudaMemcpyDeviceToHost, c0->stream);
+    if (out_sumsq) cudaMemcpyAsync(c0->pinned + plane, d_sq, plane * sizeof(float), cudaMemcpyDeviceToHost, c0->stream);
+    cudaEventRecord(c0->ev1, c0->stream);
+    cudaError_t e = cudaStreamSynchronize(c0->stream);
+    if (e != cudaSuccess) return mfail(m, VK_ERR_CUDA, std::string("vk_multi_render: ") + cudaGetErrorString(e));
+    std::memcpy(out_rgb, c0->pinned, plane * sizeof(float));
+    if (out_sumsq) std::memcpy(out_sumsq, c0->pinned + plane, plane * sizeof(float));
+    cudaEventElapsedTime(&st.ms_total, c0->ev2, c0->ev1);
+    st.launches += 1;
+    if (stats) *stats = st;
+    return VK_OK;
+}
+int vk_multi_render_rgb8(vk_multi* m, const vk_camera* cam, const vk_render_params* P, uint8_t* out_rgb8, vk_stats* stats) {
+    if (!m || !P || !out_rgb8) return mfail(m, VK_ERR_INVALID, "vk_multi_render_rgb8: null argument");
+    float *d_sum = nullptr, *d_sq = nullptr;
+    vk_stats st{};
+    int rc = multi_render_sums(m, cam, P, false, &d_sum, &d_sq, &st);
+    if (rc != VK_OK) return rc;
+    vk_ctx* c0 = m->ctx[0];
+    const size_t plane = (size_t)P->width * P->height * 3;
+    if ((rc = multi_pinned(m, c0, plane)) != VK_OK) return rc;
+    cudaSetDevice(c0->device);
+    uint8_t* d_rgb8 = (uint8_t*)(c0->frame + 2 * plane);
+    k_to_color<<<(unsigned)((plane + 255) / 256), 256, 0, c0->stream>>>(d_sum, d_rgb8, P->width, P->height, (float)P->spp);
+    cudaMemcpyAsync(c0->pinned, d_rgb8, plane, cudaMemcpyDeviceToHost, c0->stream);
+    cudaEventRecord(c0->ev1, c0->stream);
+    cudaError_t e = cudaStreamSynchronize(c0->stream);
+    if (e != cudaSuccess) return mfail(m, VK_ERR_CUDA, std::string("vk_multi_render_rgb8: ") + cudaGetErrorString(e));
+    std::memcpy(out_rgb8, c0->pinned, plane);
+    cudaEventElapsedTime(&st.ms_total, c0->ev2, c0->ev1);
+    st.launches += 1;
+    if (stats) *stats = st;
+    return VK_OK;
 }
 
 int vk_eval_batch(vk_ctx* c, vk_eval* recs, size_t n, uint32_t flags) {

@@ -5,11 +5,11 @@
 // (the scene number of main.rs:159-167, `width`, SAMPLES_PER_PIXEL, MAX_DEPTH) is a command-line option
 // here, with the reference's values as defaults.
 //
-// Several GPUs in ONE process (--gpus N): GPU k renders the global samples [k*spp/N, (k+1)*spp/N) of every
-// pixel through its own context on its own host thread; vk_render returns each slice already divided by the
-// full spp, so the frame is the plain sum of the N host buffers (the torch.distributed launch of
-// bench.py does the same sum with one NCCL reduce).  There is no CPU render path: without a device vk_create
-// fails and so does this program.
+// Several GPUs in ONE process (--gpus N): vk_multi_* of the C ABI.  GPU k renders the global samples
+// [k*spp/N, (k+1)*spp/N) of every pixel into its own integer accumulators and GPU 0 adds its peers' accumulators
+// to its own by reading them over NVLink (the torch.distributed launch of bench.py does the same sum
+// with one NCCL reduce) -- the frame is bit-identical to the one-GPU frame.  There is no CPU render path: without
+// a device vk_create fails and so does this program.
 #include "../../include/vecchio_gpu.h"
 #include "../../include/vecchio_host.h"
 
@@ -152,6 +152,7 @@ int parse(int argc, char** argv, Options& o) {
             else if (s == "megakernel") o.variant = VK_VARIANT_MEGAKERNEL;
             else if (s == "wavefront") o.variant = VK_VARIANT_WAVEFRONT;
             else if (s == "staged") o.variant = VK_VARIANT_STAGED;
+            else if (s == "warpq") o.variant = VK_VARIANT_WARPQ;
             else return 2;
         } else if (a == "--strict") {
             o.flags |= VK_FLAG_STRICT_MATH;
@@ -173,18 +174,18 @@ int parse(int argc, char** argv, Options& o) {
     return 0;
 }
 
-struct Gpu {
-    int device = 0;
-    vk_ctx* ctx = nullptr;
-    std::vector<float> partial; // this GPU's spp slice of the frame, already divided by the full spp
-    vk_stats stats{};
-    int rc = VK_OK;
-    std::string err;
+// one device: vk_ctx; several: vk_multi (spp slices per device, the peers' accumulators added on device 0 over NVLink)
+struct Gpus {
+    vk_ctx* one = nullptr;
+    vk_multi* many = nullptr;
+    const char* error() const { return many ? vk_multi_last_error(many) : vk_last_error(one); }
 };
 
-void destroy_all(std::vector<Gpu>& gpus, vkh_scene* scene) {
-    for (auto& g : gpus)
-        if (g.ctx) vk_destroy(g.ctx);
+void destroy_all(Gpus& g, vkh_scene* scene) {
+    if (g.one) vk_destroy(g.one);
+    if (g.many) vk_multi_destroy(g.many);
+    g.one = nullptr;
+    g.many = nullptr;
     if (scene) vkh_scene_free(scene);
 }
 
@@ -214,24 +215,26 @@ int main(int argc, char** argv) {
         return 2;
     }
 
-    // one context per device, the scene resident on each for the whole frame loop
-    std::vector<Gpu> gpus(opt.devices.size());
-    for (size_t k = 0; k < gpus.size(); k++) {
-        Gpu& g = gpus[k];
-        g.device = opt.devices[k];
-        if (vk_create(g.device, &g.ctx) != VK_OK) {
-            std::fprintf(stderr, "vecchio_gpu_render: device %d: %s\n", g.device, vk_last_error(nullptr));
+    // the scene stays resident on every device for the whole frame loop
+    Gpus gpus;
+    const uint32_t world = (uint32_t)opt.devices.size();
+    if (world == 1) {
+        if (vk_create(opt.devices[0], &gpus.one) != VK_OK) {
+            std::fprintf(stderr, "vecchio_gpu_render: device %d: %s\n", opt.devices[0], vk_last_error(nullptr));
             destroy_all(gpus, scene);
             return 1;
         }
-        if (vk_scene_upload(g.ctx, vkh_scene_desc(scene)) != VK_OK) {
-            std::fprintf(stderr, "vecchio_gpu_render: device %d: %s\n", g.device, vk_last_error(g.ctx));
-            destroy_all(gpus, scene);
-            return 1;
-        }
+    } else if (vk_multi_create(opt.devices.data(), (int)world, &gpus.many) != VK_OK) {
+        std::fprintf(stderr, "vecchio_gpu_render: %s\n", vk_multi_last_error(nullptr));
+        destroy_all(gpus, scene);
+        return 1;
+    }
+    if ((world == 1 ? vk_scene_upload(gpus.one, vkh_scene_desc(scene)) : vk_multi_scene_upload(gpus.many, vkh_scene_desc(scene))) != VK_OK) {
+        std::fprintf(stderr, "vecchio_gpu_render: %s\n", gpus.error());
+        destroy_all(gpus, scene);
+        return 1;
     }
     const size_t n_floats = (size_t)width * height * 3;
-    const uint32_t world = (uint32_t)gpus.size();
     // two output buffers: the P3 text of frame f is written by a helper thread while frame f+1 renders
     std::vector<uint8_t> rgb8_buf[2] = {std::vector<uint8_t>(n_floats), std::vector<uint8_t>(n_floats)};
     struct Pending {
@@ -254,9 +257,6 @@ int main(int argc, char** argv) {
         }
         return true;
     };
-    if (world > 1)
-        for (auto& g : gpus) g.partial.resize(n_floats);
-
     uint32_t file_idx = 0, written = 0;
     vk_camera cam;
     while (vkh_scene_next_camera(scene, &cam)) { // for cam in config.cam_iter (main.rs:176)
@@ -277,45 +277,14 @@ int main(int argc, char** argv) {
         P.variant = opt.variant;
         P.flags = opt.flags;
 
-        uint64_t rays = 0;
-        if (world == 1) {
-            // sample loop + Vec3::to_color on the device; a quarter of the bytes come back
-            Gpu& g = gpus[0];
-            if (vk_render_rgb8(g.ctx, &cam, &P, rgb8.data(), &g.stats) != VK_OK) {
-                std::fprintf(stderr, "vecchio_gpu_render: device %d: %s\n", g.device, vk_last_error(g.ctx));
-                destroy_all(gpus, scene);
-                return 1;
-            }
-            rays = g.stats.rays;
-        } else {
-            std::vector<std::thread> workers;
-            for (uint32_t k = 0; k < world; k++) {
-                workers.emplace_back([&, k] {
-                    Gpu& g = gpus[k];
-                    vk_render_params Pk = P;
-                    Pk.spp_begin = (uint32_t)((uint64_t)k * P.spp / world); // the slices tile [0, spp) exactly
-                    Pk.spp_count = (uint32_t)((uint64_t)(k + 1) * P.spp / world) - Pk.spp_begin;
-                    g.rc = vk_render(g.ctx, &cam, &Pk, g.partial.data(), nullptr, &g.stats);
-                    if (g.rc != VK_OK) g.err = vk_last_error(g.ctx);
-                });
-            }
-            for (auto& w : workers) w.join();
-            for (auto& g : gpus) {
-                if (g.rc != VK_OK) {
-                    std::fprintf(stderr, "vecchio_gpu_render: device %d: %s\n", g.device, g.err.c_str());
-                    destroy_all(gpus, scene);
-                    return 1;
-                }
-                rays += g.stats.rays;
-            }
-            // partial means add up to the mean; summed in device order so the frame does not depend on timing
-            std::vector<float>& acc = gpus[0].partial;
-            for (uint32_t k = 1; k < world; k++) {
-                const float* p = gpus[k].partial.data();
-                for (size_t i = 0; i < n_floats; i++) acc[i] += p[i];
-            }
-            vkh_frame_to_rgb8(acc.data(), width, height, rgb8.data());
+        // sample loop + Vec3::to_color on the device(s); a quarter of the bytes come back
+        vk_stats stats{};
+        if ((world == 1 ? vk_render_rgb8(gpus.one, &cam, &P, rgb8.data(), &stats) : vk_multi_render_rgb8(gpus.many, &cam, &P, rgb8.data(), &stats)) != VK_OK) {
+            std::fprintf(stderr, "vecchio_gpu_render: %s\n", gpus.error());
+            destroy_all(gpus, scene);
+            return 1;
         }
+        const uint64_t rays = stats.rays;
 
         // Write output (main.rs:200-214), overlapped with the next frame's render.  At most one write is in
         // flight, so the other buffer is free by the time the next frame is converted into it.
