@@ -177,17 +177,122 @@ VKD uint32_t wq_class_of(const DScene& sc, uint32_t prim, uint32_t inst) {
     return t == VK_M_DIFFUSE_LIGHT ? VKQ_EMIT : t == VK_M_DIELECTRIC ? VKQ_DIEL : t == VK_M_METAL ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
 }
 
-template <bool FLAT, bool MEDIA, bool LEGACY>
-VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
-                    unsigned long long* unit_head) {
-    extern __shared__ __align__(16) unsigned char vkq_raw[];
-    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-    WqWarp& S = reinterpret_cast<WqWarp*>(vkq_raw)[threadIdx.x >> 5];
-    const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
-    uint32_t n_rays = 0, n_drop = 0, n_nodes = 0, n_prims = 0;
-    constexpr uint32_t EXT_CAP = FLAT ? 32u * VKQ_K : 32u;
+// Queue counters of the warp: {entries, ring write position} per queue.
+struct WqCounts {
+    uint4 c01, c23, c45, c67; // EXT END | EMIT DIEL | METAL DIFF | DIFFI -
+};
+VKD WqCounts wq_counts(const WqWarp& S) {
+    WqCounts c;
+    c.c01 = *reinterpret_cast<const uint4*>(&S.ct[0]);
+    c.c23 = *reinterpret_cast<const uint4*>(&S.ct[2]);
+    c.c45 = *reinterpret_cast<const uint4*>(&S.ct[4]);
+    c.c67 = *reinterpret_cast<const uint4*>(&S.ct[6]);
+    return c;
+}
+// The fullest queue: score = entries / batch width (EXT batches are ext_cap wide, the others 32; ext_cap == 0 leaves
+// the extend queue out).  Returns false when every considered queue is empty.
+VKD bool wq_pick(const WqCounts& c, uint32_t ext_cap, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
+    uint32_t best = ext_cap ? c.c01.x * 32u : 0u;
+    const uint32_t w = ext_cap ? ext_cap : 32u;
+    q = VKQ_EXT;
+    n_q = c.c01.x;
+    tail_q = c.c01.y;
+#define VKQ_CONSIDER(Q, CNT, TAIL)                                                                                     \
+    {                                                                                                                  \
+        const uint32_t sc_ = (CNT) * w;                                                                                \
+        if (sc_ > best) {                                                                                              \
+            best = sc_;                                                                                                \
+            q = (Q);                                                                                                   \
+            n_q = (CNT);                                                                                               \
+            tail_q = (TAIL);                                                                                           \
+        }                                                                                                              \
+    }
+    VKQ_CONSIDER(VKQ_EMIT, c.c23.x, c.c23.y)
+    VKQ_CONSIDER(VKQ_DIFF, c.c45.z, c.c45.w)
+    VKQ_CONSIDER(VKQ_DIFFI, c.c67.x, c.c67.y)
+    VKQ_CONSIDER(VKQ_DIEL, c.c23.z, c.c23.w)
+    VKQ_CONSIDER(VKQ_METAL, c.c45.x, c.c45.y)
+    VKQ_CONSIDER(VKQ_END, c.c01.z, c.c01.w)
+#undef VKQ_CONSIDER
+    return best != 0u;
+}
+// Take up to `cap` entries off queue q: returns how many, and the ring position of the first.
+VKD uint32_t wq_pop(WqWarp& S, uint32_t q, uint32_t n_q, uint32_t tail_q, uint32_t cap, uint32_t lane, uint32_t& head) {
+    const uint32_t n = min(n_q, cap);
+    head = tail_q - n_q;
+    __syncwarp();
+    if (lane == 0) S.ct[q].x = n_q - n;
+    __syncwarp();
+    // (the entries [head, head + n) stay readable: pushes only write at the ring's tail, and a ring holds VKQ_RN >= VKQ_N entries)
+    return n;
+}
 
-    // every slot starts in the regeneration queue
+// One batch of a shading class (or of the regeneration queue): resolve + scatter (src/main.rs:131-149); a finished sample
+// goes through the NaN / Inf filter (:191-194) into its pixel; survivors go to the extend queue.
+template <bool LEGACY>
+VKD void wq_shade_batch(const DScene& sc, const WqCtx& C, const RenderBuffers& buf, uint32_t q, uint32_t n, uint32_t head, uint32_t& n_drop) {
+    WqWarp& S = C.S;
+    const RenderArgs& a = C.a;
+    const uint32_t lane = C.lane;
+    const bool act = lane < n;
+    const uint32_t slot = S.ring[q][(head + (act ? lane : 0u)) & VKQ_RMASK];
+    bool alive = false, ended = false;
+    if (q != VKQ_END) {
+        if (act) {
+            const float4 ro = S.ro[slot], rd = S.rd[slot], bt = S.bt[slot];
+            const uint4 hp = S.hp[slot];
+            float3 o = f3(ro), d = f3(rd), beta = f3(bt), L = f3(0.0f, 0.0f, 0.0f);
+            float time = ro.w;
+            uint32_t depth = __float_as_uint(rd.w);
+            const uint32_t pixel = S.px[slot], prim = hp.y;
+            bool valid = true;
+            if (prim == VK_REF_NONE) {
+                L = beta * miss_color(a, d); // src/main.rs:151
+            } else {
+                PathRng rng;
+                rng.pixel = pixel;
+                rng.sample = __float_as_uint(bt.w);
+                rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                const uint32_t hi = hp.z;
+                TraceHit h;
+                h.t = __uint_as_float(hp.x);
+                h.prim = prim;
+                h.inst = (hi & 0x80000000u) ? (((uint32_t)VK_T_XFORM << 28) | (hi & 0x07FFFFFFu)) : 0u;
+                h.face = (hi >> 28) & 7u;
+                HitRecD rec;
+                resolve_hit(sc, h, o, d, time, false, rec);
+                alive = LEGACY ? shade_legacy(sc, rec, rng, depth, o, d, time, beta, L, valid)
+                               : shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
+                if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
+                if (alive && !(finite3(d) && finite3(o))) {          // the reference's sample is NaN here (see vk_kernels.cu)
+                    valid = false;
+                    alive = false;
+                }
+            }
+            if (alive) {
+                S.ro[slot] = make_float4(o.x, o.y, o.z, time);
+                S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
+                S.bt[slot] = make_float4(beta.x, beta.y, beta.z, bt.w);
+            } else {
+                if (valid && finite3(L)) accumulate_sample(buf, pixel, L);
+                else ++n_drop;
+                ended = true;
+            }
+        }
+    } else {
+        ended = act; // queued regenerations
+    }
+    // Regenerate in place when enough lanes ended -- the emitter / miss class does, every lane; in the other classes
+    // only a few lanes end (a light-sampled direction below the surface has weight 0): those are queued and
+    // regenerated together, with full warps.
+    const uint32_t m_end = __ballot_sync(0xFFFFFFFFu, ended);
+    bool to_end = false;
+    if (q == VKQ_END || (uint32_t)__popc(m_end) >= VKQ_REGEN_MIN) alive = wq_regen(C, ended, slot) || alive;
+    else to_end = ended;
+    wq_push(S, alive ? (uint32_t)VKQ_EXT : (to_end ? (uint32_t)VKQ_END : (uint32_t)VKQ_NONE), slot, lane, C.below);
+}
+
+VKD void wq_init(WqWarp& S, uint32_t lane) { // every slot starts in the regeneration queue
     if (lane < 8) S.ct[lane] = make_uint2(0u, 0u);
     for (uint32_t i = lane; i < VKQ_N; i += 32u) S.ring[VKQ_END][i] = (uint8_t)i;
     if (lane == 0) {
@@ -199,171 +304,8 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
     __syncwarp();
     if (lane == 0) S.ct[VKQ_END] = make_uint2(VKQ_N, VKQ_N);
     __syncwarp();
-
-#pragma unroll 1
-    for (;;) {
-        // ---- pick the fullest queue (extend batches are EXT_CAP wide, the others 32) -------------------------
-        uint32_t q = VKQ_EXT, n_q, tail_q;
-        {
-            const uint4 c01 = *reinterpret_cast<const uint4*>(&S.ct[0]), c23 = *reinterpret_cast<const uint4*>(&S.ct[2]),
-                        c45 = *reinterpret_cast<const uint4*>(&S.ct[4]), c67 = *reinterpret_cast<const uint4*>(&S.ct[6]);
-            uint32_t best = c01.x * 32u; // score = entries x 32 / batch width
-            n_q = c01.x;
-            tail_q = c01.y;
-#define VKQ_CONSIDER(Q, CNT, TAIL)                                                                                     \
-    {                                                                                                                  \
-        const uint32_t sc_ = (CNT) * EXT_CAP;                                                                          \
-        if (sc_ > best) {                                                                                              \
-            best = sc_;                                                                                                \
-            q = (Q);                                                                                                   \
-            n_q = (CNT);                                                                                               \
-            tail_q = (TAIL);                                                                                           \
-        }                                                                                                              \
-    }
-            VKQ_CONSIDER(VKQ_EMIT, c23.x, c23.y)
-            VKQ_CONSIDER(VKQ_DIFF, c45.z, c45.w)
-            VKQ_CONSIDER(VKQ_DIFFI, c67.x, c67.y)
-            VKQ_CONSIDER(VKQ_DIEL, c23.z, c23.w)
-            VKQ_CONSIDER(VKQ_METAL, c45.x, c45.y)
-            VKQ_CONSIDER(VKQ_END, c01.z, c01.w)
-#undef VKQ_CONSIDER
-            if (best == 0u) break; // every queue is empty: all slots have retired
-        }
-        const uint32_t cap = q == VKQ_EXT ? EXT_CAP : 32u;
-        const uint32_t n = min(n_q, cap), head = tail_q - n_q;
-        __syncwarp();
-        if (lane == 0) S.ct[q].x = n_q - n;
-        __syncwarp();
-        // (the entries [head, head + n) stay readable: pushes only write at the ring's tail, and a ring holds VKQ_RN >= VKQ_N entries)
-
-        if (q == VKQ_EXT) {
-            // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------
-            if (FLAT) {
-                float3 o[VKQ_K], d[VKQ_K];
-                float tm[VKQ_K], best_t[VKQ_K];
-                bool live[VKQ_K];
-                uint32_t best_hit[VKQ_K], slot[VKQ_K];
-                MediumXi xi[VKQ_K];
-#pragma unroll
-                for (int k = 0; k < VKQ_K; ++k) {
-                    const uint32_t e = lane + 32u * k;
-                    live[k] = e < n;
-                    slot[k] = S.ring[VKQ_EXT][(head + (live[k] ? e : 0u)) & VKQ_RMASK];
-                    const float4 ro = S.ro[slot[k]], rd = S.rd[slot[k]];
-                    o[k] = f3(ro);
-                    d[k] = f3(rd);
-                    tm[k] = ro.w;
-                    xi[k].table = nullptr;
-                    xi[k].depth = __float_as_uint(rd.w);
-                    xi[k].rng.key = make_uint2(a.seed_lo, a.seed_hi);
-                    xi[k].rng.pixel = MEDIA ? S.px[slot[k]] : 0u;
-                    xi[k].rng.sample = MEDIA ? __float_as_uint(S.bt[slot[k]].w) : 0u;
-                }
-                trace_flat_k<VKQ_K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit);
-#pragma unroll
-                for (int k = 0; k < VKQ_K; ++k) {
-                    uint32_t cls = VKQ_NONE;
-                    if (live[k]) {
-                        ++n_rays;
-                        n_prims += flat->n;
-                        uint32_t prim = VK_REF_NONE, hi = 0u;
-                        cls = VKQ_EMIT; // a miss ends the sample like an emitter does
-                        if (best_hit[k] != 0xFFFFFFFFu) {
-                            const FlatHit& fh = flat->hits[best_hit[k]];
-                            prim = fh.prim & ~VKD_DUP;
-                            const uint32_t inst = fh.inst;
-                            hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);
-                            cls = fh.cls == 0u ? VKQ_EMIT : fh.cls == 1u ? VKQ_DIEL : fh.cls == 2u ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
-                        }
-                        S.hp[slot[k]] = make_uint4(__float_as_uint(best_t[k]), prim, hi, 0u);
-                    }
-                    if (k == 0 || n > 32u * k) wq_push(S, cls, slot[k], lane, below); // (warp-uniform condition)
-                }
-            } else {
-                const bool live = lane < n;
-                const uint32_t slot = S.ring[VKQ_EXT][(head + (live ? lane : 0u)) & VKQ_RMASK];
-                uint32_t cls = VKQ_NONE;
-                if (live) {
-                    const float4 ro = S.ro[slot], rd = S.rd[slot];
-                    MediumXi xi;
-                    xi.table = nullptr;
-                    xi.depth = __float_as_uint(rd.w);
-                    xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
-                    xi.rng.pixel = MEDIA ? S.px[slot] : 0u;
-                    xi.rng.sample = MEDIA ? __float_as_uint(S.bt[slot].w) : 0u;
-                    TraceCounters tc = {0u, 0u};
-                    const TraceHit h = trace<MEDIA>(sc, f3(ro), f3(rd), ro.w, 0.001f, CUDART_INF_F, xi, tc);
-                    ++n_rays;
-                    n_nodes += tc.nodes;
-                    n_prims += tc.prims;
-                    S.hp[slot] = make_uint4(__float_as_uint(h.t), h.prim, (h.inst ? (0x80000000u | VKD_INDEX(h.inst)) : 0u) | (h.face << 28), 0u);
-                    cls = h.prim == VK_REF_NONE ? (uint32_t)VKQ_EMIT : wq_class_of(sc, h.prim, h.inst);
-                }
-                wq_push(S, cls, slot, lane, below);
-            }
-            continue;
-        }
-
-        const bool act = lane < n;
-        const uint32_t slot = S.ring[q][(head + (act ? lane : 0u)) & VKQ_RMASK];
-        bool alive = false, ended = false;
-        if (q != VKQ_END) {
-            // ---- shade one class: resolve + scatter (src/main.rs:131-149); a finished sample goes through the NaN / Inf
-            // filter (:191-194) into its pixel ---------------------------------------------------------------------------
-            if (act) {
-                const float4 ro = S.ro[slot], rd = S.rd[slot], bt = S.bt[slot];
-                const uint4 hp = S.hp[slot];
-                float3 o = f3(ro), d = f3(rd), beta = f3(bt), L = f3(0.0f, 0.0f, 0.0f);
-                float time = ro.w;
-                uint32_t depth = __float_as_uint(rd.w);
-                const uint32_t pixel = S.px[slot], prim = hp.y;
-                bool valid = true;
-                if (prim == VK_REF_NONE) {
-                    L = beta * miss_color(a, d); // src/main.rs:151
-                } else {
-                    PathRng rng;
-                    rng.pixel = pixel;
-                    rng.sample = __float_as_uint(bt.w);
-                    rng.key = make_uint2(a.seed_lo, a.seed_hi);
-                    const uint32_t hi = hp.z;
-                    TraceHit h;
-                    h.t = __uint_as_float(hp.x);
-                    h.prim = prim;
-                    h.inst = (hi & 0x80000000u) ? (((uint32_t)VK_T_XFORM << 28) | (hi & 0x07FFFFFFu)) : 0u;
-                    h.face = (hi >> 28) & 7u;
-                    HitRecD rec;
-                    resolve_hit(sc, h, o, d, time, false, rec);
-                    alive = LEGACY ? shade_legacy(sc, rec, rng, depth, o, d, time, beta, L, valid)
-                                   : shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
-                    if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
-                    if (alive && !(finite3(d) && finite3(o))) {          // the reference's sample is NaN here (see vk_kernels.cu)
-                        valid = false;
-                        alive = false;
-                    }
-                }
-                if (alive) {
-                    S.ro[slot] = make_float4(o.x, o.y, o.z, time);
-                    S.rd[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
-                    S.bt[slot] = make_float4(beta.x, beta.y, beta.z, bt.w);
-                } else {
-                    if (valid && finite3(L)) accumulate_sample(buf, pixel, L);
-                    else ++n_drop;
-                    ended = true;
-                }
-            }
-        } else {
-            ended = act; // queued regenerations
-        }
-        // Regenerate in place when enough lanes ended -- the emitter / miss class does, every lane; in the other classes
-        // only a few lanes end (a light-sampled direction below the surface has weight 0): those are queued and
-        // regenerated together, with full warps.
-        const uint32_t m_end = __ballot_sync(0xFFFFFFFFu, ended);
-        bool to_end = false;
-        if (q == VKQ_END || (uint32_t)__popc(m_end) >= VKQ_REGEN_MIN) alive = wq_regen(C, ended, slot) || alive;
-        else to_end = ended;
-        wq_push(S, alive ? (uint32_t)VKQ_EXT : (to_end ? (uint32_t)VKQ_END : (uint32_t)VKQ_NONE), slot, lane, below);
-    }
-
+}
+VKD void wq_flush_counters(const RenderBuffers& buf, uint32_t lane, uint32_t n_rays, uint32_t n_drop, uint32_t n_nodes, uint32_t n_prims) {
     unsigned long long w_rays = n_rays, w_drop = n_drop, w_nodes = n_nodes, w_prims = n_prims;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -380,15 +322,180 @@ VKD void warpq_body(const DScene& sc, const FlatProgram* flat, const DCamera& ca
     }
 }
 
+// ---- flat scenes: extend = K rays per lane through the flat program, one queue batch at a time ----------------------
+template <bool MEDIA, bool LEGACY>
+VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
+                         unsigned long long* unit_head) {
+    extern __shared__ __align__(16) unsigned char vkq_raw[];
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    WqWarp& S = reinterpret_cast<WqWarp*>(vkq_raw)[threadIdx.x >> 5];
+    const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
+    uint32_t n_rays = 0, n_drop = 0, n_prims = 0;
+    constexpr uint32_t EXT_CAP = 32u * VKQ_K;
+    wq_init(S, lane);
+#pragma unroll 1
+    for (;;) {
+        uint32_t q, n_q, tail_q, head;
+        if (!wq_pick(wq_counts(S), EXT_CAP, q, n_q, tail_q)) break; // every queue is empty: all slots have retired
+        const uint32_t n = wq_pop(S, q, n_q, tail_q, q == VKQ_EXT ? EXT_CAP : 32u, lane, head);
+        if (q != VKQ_EXT) {
+            wq_shade_batch<LEGACY>(sc, C, buf, q, n, head, n_drop);
+            continue;
+        }
+        // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------------
+        float3 o[VKQ_K], d[VKQ_K];
+        float tm[VKQ_K], best_t[VKQ_K];
+        bool live[VKQ_K];
+        uint32_t best_hit[VKQ_K], slot[VKQ_K];
+        MediumXi xi[VKQ_K];
+#pragma unroll
+        for (int k = 0; k < VKQ_K; ++k) {
+            const uint32_t e = lane + 32u * k;
+            live[k] = e < n;
+            slot[k] = S.ring[VKQ_EXT][(head + (live[k] ? e : 0u)) & VKQ_RMASK];
+            const float4 ro = S.ro[slot[k]], rd = S.rd[slot[k]];
+            o[k] = f3(ro);
+            d[k] = f3(rd);
+            tm[k] = ro.w;
+            xi[k].table = nullptr;
+            xi[k].depth = __float_as_uint(rd.w);
+            xi[k].rng.key = make_uint2(a.seed_lo, a.seed_hi);
+            xi[k].rng.pixel = MEDIA ? S.px[slot[k]] : 0u;
+            xi[k].rng.sample = MEDIA ? __float_as_uint(S.bt[slot[k]].w) : 0u;
+        }
+        trace_flat_k<VKQ_K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit);
+#pragma unroll
+        for (int k = 0; k < VKQ_K; ++k) {
+            uint32_t cls = VKQ_NONE;
+            if (live[k]) {
+                ++n_rays;
+                n_prims += flat->n;
+                uint32_t prim = VK_REF_NONE, hi = 0u;
+                cls = VKQ_EMIT; // a miss ends the sample like an emitter does
+                if (best_hit[k] != 0xFFFFFFFFu) {
+                    const FlatHit& fh = flat->hits[best_hit[k]];
+                    prim = fh.prim & ~VKD_DUP;
+                    const uint32_t inst = fh.inst;
+                    hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);
+                    cls = fh.cls == 0u ? VKQ_EMIT : fh.cls == 1u ? VKQ_DIEL : fh.cls == 2u ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
+                }
+                S.hp[slot[k]] = make_uint4(__float_as_uint(best_t[k]), prim, hi, 0u);
+            }
+            if (k == 0 || n > 32u * k) wq_push(S, cls, slot[k], lane, below); // (warp-uniform condition)
+        }
+    }
+    wq_flush_counters(buf, lane, n_rays, n_drop, 0u, n_prims);
+}
+
+// ---- BVH scenes: extend = the resumable traversal (Trav, vk_device.cuh) with dynamic fetch ------------------------------
+// Traversal lengths differ by orders of magnitude between rays (10^6 spheres: mean 28 four-wide visits, some hundreds),
+// so a lane is not tied to a batch: every lane keeps ONE ray's traversal in registers (stack in local memory), the warp
+// steps all of them in bounded while-while rounds under votes, and a lane whose ray has finished stores the hit, files
+// the slot under its shading class and takes the next entry of the extend queue.  Only when the extend queue is empty
+// and VKQ_BVH_IDLE lanes have nothing to traverse does the warp leave the traversal -- its other rays stay in flight in
+// registers -- to shade one full batch of the fullest class, which refills the extend queue.  Shading therefore always
+// runs on whole batches of one class, and traversal with at most VKQ_BVH_IDLE - 1 idle lanes.
+#ifndef VKQ_BVH_IDLE
+#define VKQ_BVH_IDLE 8u
+#endif
+#ifndef VKQ_NODE_STEPS
+#define VKQ_NODE_STEPS 4
+#endif
+template <bool MEDIA, bool LEGACY>
+VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf, unsigned long long* unit_head) {
+    extern __shared__ __align__(16) unsigned char vkq_raw[];
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    WqWarp& S = reinterpret_cast<WqWarp*>(vkq_raw)[threadIdx.x >> 5];
+    const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
+    uint32_t n_rays = 0, n_drop = 0;
+    TraceCounters tc = {0u, 0u};
+    wq_init(S, lane);
+
+    Trav T; // this lane's ray in flight (T.ref == VKD_DONE: none)
+    T.ref = VKD_DONE;
+    T.sp = 0;
+    T.enter = false;
+    T.cur_inst = 0;
+    T.co = T.cd = T.cinv = f3(0.0f, 0.0f, 0.0f);
+    T.best.t = 0.0f;
+    T.best.prim = VK_REF_NONE;
+    T.best.inst = 0;
+    T.best.face = 0;
+    float3 o = f3(0.0f, 0.0f, 0.0f), d = o;
+    float tm = 0.0f;
+    uint32_t cur = 0xFFFFFFFFu; // slot of the ray in flight
+    MediumXi xi;
+    xi.table = nullptr;
+    xi.depth = 0;
+    xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
+    xi.rng.pixel = 0;
+    xi.rng.sample = 0;
+#pragma unroll 1
+    for (;;) {
+        const WqCounts cnt = wq_counts(S);
+        const bool idle = T.ref == VKD_DONE;
+        const uint32_t m_idle = __ballot_sync(0xFFFFFFFFu, idle);
+        uint32_t n_ext = cnt.c01.x;
+        if (m_idle != 0u && n_ext != 0u) { // ---- fetch: idle lanes take the next rays of the extend queue -------------------
+            uint32_t head;
+            const uint32_t take = wq_pop(S, VKQ_EXT, n_ext, cnt.c01.y, (uint32_t)__popc(m_idle), lane, head);
+            const uint32_t rank = (uint32_t)__popc(m_idle & below);
+            if (idle && rank < take) {
+                cur = S.ring[VKQ_EXT][(head + rank) & VKQ_RMASK];
+                const float4 ro = S.ro[cur], rd = S.rd[cur];
+                o = f3(ro);
+                d = f3(rd);
+                tm = ro.w;
+                xi.depth = __float_as_uint(rd.w);
+                if (MEDIA) {
+                    xi.rng.pixel = S.px[cur];
+                    xi.rng.sample = __float_as_uint(S.bt[cur].w);
+                }
+                trav_init(T, sc, o, d, CUDART_INF_F); // world.hit(&r, 0.001, inf) src/main.rs:130
+                ++n_rays;
+            }
+            n_ext -= take;
+        }
+        const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, T.ref != VKD_DONE);
+        const uint32_t n_idle = 32u - (uint32_t)__popc(m_act);
+        if (n_idle >= VKQ_BVH_IDLE && n_ext == 0u) { // ---- shade: refill the extend queue from the fullest class -----------
+            uint32_t q, n_q, tail_q, head;
+            if (wq_pick(cnt, 0u, q, n_q, tail_q)) {
+                const uint32_t n = wq_pop(S, q, n_q, tail_q, 32u, lane, head);
+                wq_shade_batch<LEGACY>(sc, C, buf, q, n, head, n_drop);
+                continue;
+            }
+            if (m_act == 0u) break; // nothing in flight, nothing queued: all slots have retired
+        }
+        // ---- traverse: a bounded while-while round for every ray in flight ---------------------------------------------
+#pragma unroll 1
+        for (int k = 0; k < VKQ_NODE_STEPS && trav_at_node(T); ++k) trav_node_step(T, sc, 0.001f, tc);
+        if (T.ref != VKD_DONE && !trav_at_node(T)) trav_prim_step<MEDIA>(T, sc, o, d, tm, 0.001f, xi, tc);
+        const bool fin = cur != 0xFFFFFFFFu && T.ref == VKD_DONE;
+        if (__ballot_sync(0xFFFFFFFFu, fin) != 0u) { // finished rays: the hit, filed under its shading class
+            uint32_t cls = VKQ_NONE, slot = 0u;
+            if (fin) {
+                slot = cur;
+                cur = 0xFFFFFFFFu;
+                S.hp[slot] = make_uint4(__float_as_uint(T.best.t), T.best.prim,
+                                        (T.best.inst ? (0x80000000u | VKD_INDEX(T.best.inst)) : 0u) | (T.best.face << 28), 0u);
+                cls = T.best.prim == VK_REF_NONE ? (uint32_t)VKQ_EMIT : wq_class_of(sc, T.best.prim, T.best.inst);
+            }
+            wq_push(S, cls, slot, lane, below);
+        }
+    }
+    wq_flush_counters(buf, lane, n_rays, n_drop, tc.nodes, tc.prims);
+}
+
 template <bool MEDIA, bool LEGACY>
 __global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB) k_warpq(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
                                                                 unsigned long long* unit_head) {
-    warpq_body<false, MEDIA, LEGACY>(sc, nullptr, cam, a, buf, unit_head);
+    warpq_bvh_body<MEDIA, LEGACY>(sc, cam, a, buf, unit_head);
 }
 template <bool MEDIA, bool LEGACY>
 __global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB) k_warpq_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
                                                                      const RenderArgs a, const RenderBuffers buf, unsigned long long* unit_head) {
-    warpq_body<true, MEDIA, LEGACY>(sc, &flat, cam, a, buf, unit_head);
+    warpq_flat_body<MEDIA, LEGACY>(sc, &flat, cam, a, buf, unit_head);
 }
 
 template <class K> static cudaError_t warpq_prepare(K kernel, int* blocks_per_sm) {
