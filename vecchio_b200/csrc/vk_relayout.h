@@ -258,6 +258,7 @@ struct FlatBuilder {
         FlatRect e{};
         e.bounds = make_float4(c0, c1, d0, d1);
         e.k = k;
+
         FlatHit h{ref, g.inst, face, 0u};
         g.rects[(a2 == 2 ? 0 : (a2 == 1 ? 1 : 2)) + (box_side ? 3 : 0)].push_back({e, h});
         return true;
@@ -355,6 +356,8 @@ struct FlatBuilder {
                 for (auto& e : g.rects[k]) {
                     e.first.hit = n_hits;
                     P->hits[n_hits++] = e.second;
+                    const float4 bd = e.first.bounds;
+                    P->rectc[n_rects] = FlatRectC{0.5f * (bd.x + bd.y), 0.5f * (bd.y - bd.x), 0.5f * (bd.z + bd.w), 0.5f * (bd.w - bd.z)};
                     P->rects[n_rects++] = e.first;
                 }
                 o.rect1[k] = (uint8_t)n_rects;

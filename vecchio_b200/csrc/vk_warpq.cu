@@ -65,6 +65,21 @@ struct WqWarp {
 
 static_assert((VKQ_RN & (VKQ_RN - 1)) == 0 && VKQ_RN >= VKQ_N && VKQ_RN <= 256, "ring capacity: power of two, >= slots, byte indices");
 
+// A barrier of the warp with itself (named barrier 1 + warp index, 32 threads).  Functionally a __syncwarp; what it buys
+// is in the compiler: ptxas only uses the uniform datapath (uniform loop counters, LDCU constant loads, BRA.U) in code
+// it can prove the whole warp executes together, and inside this kernel's scheduler loop it cannot -- after an ALIGNED
+// barrier it can.  Without it the flat program's operands are fetched with per-thread indexed constant loads
+// (measured in SASS: 37 -> 77 uniform loads, all six rect loops on the uniform datapath).
+#ifndef VKQ_CONVERGE
+#define VKQ_CONVERGE 1
+#endif
+VKD void wq_converge() {
+#if VKQ_CONVERGE
+    asm volatile("barrier.sync.aligned %0, 32;" ::"r"((threadIdx.x >> 5) + 1u) : "memory");
+#endif
+}
+static_assert(VKQ_WARPS <= 15, "one named barrier per warp of the CTA");
+
 struct WqCtx {
     const DCamera& cam;
     const RenderArgs& a;
@@ -102,9 +117,11 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
     bool got = false;
 #pragma unroll 1
     while (served < need) { // at most two rounds: what the current chunk still holds, then a new chunk
-        uint32_t left = S.left;
+        // (the warp reductions / votes only make values every lane already agrees on PROVABLY uniform: __syncwarp
+        // under a branch the compiler must assume divergent costs the whole kernel its uniform-datapath code)
+        uint32_t left = __reduce_max_sync(0xFFFFFFFFu, S.left);
         if (left == 0u) {
-            if (S.exhausted) break;
+            if (__any_sync(0xFFFFFFFFu, S.exhausted != 0u)) break;
             __syncwarp();
             if (C.lane == 0) {
                 const unsigned long long u0 = atomicAdd(C.unit_head, (unsigned long long)VKQ_CHUNK);
@@ -118,8 +135,8 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
                 }
             }
             __syncwarp();
-            if (S.exhausted) break;
-            left = S.left;
+            if (__any_sync(0xFFFFFFFFu, S.exhausted != 0u)) break;
+            left = __reduce_max_sync(0xFFFFFFFFu, S.left);
         }
         const uint32_t take = min(need - served, left);
         const uint32_t cs = S.cur_s, cp = S.cur_p;
@@ -214,7 +231,11 @@ VKD bool wq_pick(const WqCounts& c, uint32_t ext_cap, uint32_t& q, uint32_t& n_q
     VKQ_CONSIDER(VKQ_METAL, c.c45.x, c.c45.y)
     VKQ_CONSIDER(VKQ_END, c.c01.z, c.c01.w)
 #undef VKQ_CONSIDER
-    return best != 0u;
+    // Every lane computed the same values from the same shared-memory words, but the compiler cannot know that: a
+    // warp reduction (REDUX, result in a uniform register) makes the choice provably warp-uniform, so the stage it
+    // selects runs under uniform control flow (uniform-datapath loop counters and constant loads in the traversal).
+    q = __reduce_max_sync(0xFFFFFFFFu, q);
+    return __reduce_max_sync(0xFFFFFFFFu, best) != 0u;
 }
 // Take up to `cap` entries off queue q: returns how many, and the ring position of the first.
 VKD uint32_t wq_pop(WqWarp& S, uint32_t q, uint32_t n_q, uint32_t tail_q, uint32_t cap, uint32_t lane, uint32_t& head) {
@@ -343,6 +364,7 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
             continue;
         }
         // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------------
+        wq_converge();
         float3 o[VKQ_K], d[VKQ_K];
         float tm[VKQ_K], best_t[VKQ_K];
         bool live[VKQ_K];
@@ -435,7 +457,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
         const WqCounts cnt = wq_counts(S);
         const bool idle = T.ref == VKD_DONE;
         const uint32_t m_idle = __ballot_sync(0xFFFFFFFFu, idle);
-        uint32_t n_ext = cnt.c01.x;
+        uint32_t n_ext = __reduce_max_sync(0xFFFFFFFFu, cnt.c01.x); // (provably uniform, see wq_pick)
         if (m_idle != 0u && n_ext != 0u) { // ---- fetch: idle lanes take the next rays of the extend queue -------------------
             uint32_t head;
             const uint32_t take = wq_pop(S, VKQ_EXT, n_ext, cnt.c01.y, (uint32_t)__popc(m_idle), lane, head);
@@ -468,6 +490,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
             if (m_act == 0u) break; // nothing in flight, nothing queued: all slots have retired
         }
         // ---- traverse: a bounded while-while round for every ray in flight ---------------------------------------------
+        wq_converge();
 #pragma unroll 1
         for (int k = 0; k < VKQ_NODE_STEPS && trav_at_node(T); ++k) trav_node_step(T, sc, 0.001f, tc);
         if (T.ref != VKD_DONE && !trav_at_node(T)) trav_prim_step<MEDIA>(T, sc, o, d, tm, 0.001f, xi, tc);
