@@ -79,7 +79,17 @@ extern "C" {
     pub fn vk_finalize_device(ctx: *mut vk_ctx, d_sum: *const f32, d_rgb: *mut f32, n_floats: usize, spp: u32) -> c_int;
     pub fn vk_set_stream(ctx: *mut vk_ctx, stream: *mut c_void) -> c_int;
     pub fn vk_flush_stats(ctx: *mut vk_ctx, stats: *mut vk_stats) -> c_int;
+    // one context over several GPUs of the node (samples split by global index, peer-memory reduce on devices[0])
+    pub fn vk_multi_create(devices: *const c_int, n_devices: c_int, out: *mut *mut vk_multi) -> c_int;
+    pub fn vk_multi_destroy(m: *mut vk_multi);
+    pub fn vk_multi_last_error(m: *const vk_multi) -> *const c_char;
+    pub fn vk_multi_scene_upload(m: *mut vk_multi, scene: *const vk_scene_desc) -> c_int;
+    pub fn vk_multi_render(m: *mut vk_multi, cam: *const vk_camera, params: *const vk_render_params,
+                           out_rgb: *mut f32, out_sumsq: *mut f32, stats: *mut vk_stats) -> c_int;
+    pub fn vk_multi_render_rgb8(m: *mut vk_multi, cam: *const vk_camera, params: *const vk_render_params,
+                                out_rgb8: *mut u8, stats: *mut vk_stats) -> c_int;
 }
+#[repr(C)] pub struct vk_multi { _private: [u8; 0] }
 
 #[derive(Debug)]
 pub enum GpuError { Unsupported(&'static str), Library(i32, String) }
@@ -209,24 +219,38 @@ impl Drop for Gpu { fn drop(&mut self) { unsafe { vk_destroy(self.ctx) } } }
 unsafe impl Send for Gpu {}
 
 /// Several GPUs in the reference's single process (what `vecchio_gpu_render --gpus N` does in C++,
-/// vecchio_b200/host/main.cpp): one context and one scoped thread per device, GPU k renders the global samples
-/// [k*spp/N, (k+1)*spp/N); the partial means are summed in device order.
-pub fn render_on_all(gpus: &mut [Gpu], cam: &vk_camera, width: usize, height: usize, spp: u32, max_depth: u32, seed: u64)
-                     -> Result<Vec<f32>, GpuError> {
-    let n = gpus.len() as u64;
-    let parts: Vec<Result<(Vec<f32>, vk_stats), GpuError>> = std::thread::scope(|sc| {
-        let handles: Vec<_> = gpus.iter_mut().enumerate().map(|(k, g)| {
-            let (b, e) = ((k as u64 * spp as u64 / n) as u32, ((k as u64 + 1) * spp as u64 / n) as u32);
-            sc.spawn(move || g.render_slice(cam, width, height, spp, b, e - b, max_depth, seed))
-        }).collect();
-        handles.into_iter().map(|h| h.join().unwrap()).collect()
-    });
-    let mut frame = vec![0f32; width * height * 3];
-    for part in parts {
-        let (p, _) = part?;
-        for (a, b) in frame.iter_mut().zip(p.iter()) { *a += *b; }
+/// vecchio_b200/host/main.cpp): ONE multi-device context.  Device k renders the global samples [k*spp/N, (k+1)*spp/N)
+/// into its own integer accumulators; devices[0] adds its peers' accumulators over NVLink (peer-mapped memory) and
+/// returns the frame -- bit-identical to the one-GPU frame for the same seed.
+pub struct MultiGpu { m: *mut vk_multi }
+impl MultiGpu {
+    pub fn new(devices: &[i32]) -> Result<MultiGpu, GpuError> {
+        let mut m = std::ptr::null_mut();
+        let rc = unsafe { vk_multi_create(devices.as_ptr(), devices.len() as c_int, &mut m) };
+        if rc != 0 { return Err(GpuError::Library(rc, multi_error(std::ptr::null()))); }
+        Ok(MultiGpu { m })
     }
-    Ok(frame)
+    fn check(&self, rc: c_int) -> Result<(), GpuError> {
+        if rc == 0 { Ok(()) } else { Err(GpuError::Library(rc, multi_error(self.m))) }
+    }
+    pub fn upload(&mut self, low: &Lowering, root: vk_ref) -> Result<(), GpuError> {
+        let d = low.desc(root);
+        self.check(unsafe { vk_multi_scene_upload(self.m, &d) })
+    }
+    pub fn render(&mut self, cam: &vk_camera, width: usize, height: usize, spp: u32, max_depth: u32, seed: u64)
+                  -> Result<(Vec<f32>, vk_stats), GpuError> {
+        let p = vk_render_params { width: width as u32, height: height as u32, spp, spp_begin: 0, spp_count: 0, max_depth, seed,
+                                   background: [0.0; 3], variant: 0, flags: 0 };
+        let mut out = vec![0f32; width * height * 3];
+        let mut st = vk_stats::default();
+        self.check(unsafe { vk_multi_render(self.m, cam, &p, out.as_mut_ptr(), std::ptr::null_mut(), &mut st) })?;
+        Ok((out, st))
+    }
+}
+impl Drop for MultiGpu { fn drop(&mut self) { unsafe { vk_multi_destroy(self.m) } } }
+unsafe impl Send for MultiGpu {}
+fn multi_error(m: *const vk_multi) -> String {
+    unsafe { let p = vk_multi_last_error(m); if p.is_null() { String::new() } else { CStr::from_ptr(p).to_string_lossy().into_owned() } }
 }
 
 fn last_error(ctx: *const vk_ctx) -> String {
