@@ -145,6 +145,46 @@ def make_roofline(config, variant_name, kernel_name, aw, k_rays, k_ms, fp32_peak
     return r
 
 
+# short runs of the other BASELINE.json configurations (N = 1): (spp of the short run, why)
+OTHER_SPP = {"random_spheres": (16, "full config"), "cornell": (1000, "full config"), "cornell_smoke": (2000, "full config"),
+             "final_scene": (64, "64 of the 10 000 spp (the config is quoted over 8 GPUs; throughput does not depend on spp)"),
+             "stress_1m": (8, "8 of the 256 spp (throughput does not depend on spp)")}
+
+
+def other_configs(vb, ctx, args, fp32_peak, l2_gbs, peaks):
+    """One warm-up and two timed frames of every other configuration through vk_render_device (scene resident, kernels
+    timed by the library's CUDA events on its stream), so that all five appear in the driver-run record."""
+    out = []
+    for name, (scene_name, param, W, H, spp_full, depth, _) in CONFIGS.items():
+        if name == args.config:
+            continue
+        spp, why = OTHER_SPP[name]
+        try:
+            scene = vb.Scene(scene_name, seed=1, param=param)
+            cam = scene.next_camera()
+            ctx.upload(scene)
+            import torch
+            d_sum = torch.empty(W * H * 3, dtype=torch.float32, device="cuda")
+            best = None
+            for rep in range(3):
+                st = ctx.render_device(cam, vb.render_params(W, H, spp, depth, seed=1 + rep, variant=args.variant), d_sum.data_ptr(), want_stats=True)
+                if rep and (best is None or st.ms_kernels < best.ms_kernels):
+                    best = st
+            vname = VARIANT_NAMES.get(best.variant, str(best.variant))
+            kname = kernel_of(best, scene)
+            rl = make_roofline(name, vname, kname, alg_work(scene_name) or {}, best.rays, best.ms_kernels, fp32_peak, l2_gbs, peaks,
+                               scene.nbytes() - int(scene.desc.n_texel_bytes))
+            out.append({"config": name, "workload": f"{scene_name} {W}x{H}, max depth {depth}, {spp} spp measured ({why}; BASELINE.json configs[{list(CONFIGS).index(name)}] is {spp_full} spp)",
+                        "ms": best.ms_kernels, "mpaths_per_s": best.paths / best.ms_kernels / 1e3, "mrays_per_s": best.rays / best.ms_kernels / 1e3,
+                        "rays_per_path": best.rays / best.paths, "variant": vname, "kernel": kname,
+                        "roofline": None if rl is None else {k: rl[k] for k in ("bound", "achieved", "peak", "unit", "frac")}})
+            del d_sum
+            scene.close()
+        except Exception as e:  # a short extra run must never cost the main line
+            out.append({"config": name, "error": str(e)})
+    return out
+
+
 def run_reference(args, cfg):
     """The reference's CPU implementation of the path (its C++ restatement, oracle/) on all host
     cores: same scene, resolution, depth; each step renders a bounded `cpu_spp` slice."""
@@ -316,6 +356,9 @@ def run_ours(args, cfg):
                 "gpu_launches": int(launches), "dropped_samples": int(dropped), "clocks": clocks, "roofline": roofline,
                 "kernel_only": {"mpaths_per_s": k_paths / (k_ms * 1e-3) / 1e6, "mrays_per_s": k_rays / (k_ms * 1e-3) / 1e6, "ms": k_ms},
                 "device": info}
+        if world == 1 and not args.no_other_configs:
+            line["other_configs"] = other_configs(vb, ctx, args, fp32_peak, l2_gbs, peaks)
+            ctx.upload(scene)
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as po
             o = po.OracleScene(scene)
@@ -342,6 +385,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override the config's spp (reduced-budget runs; say so when quoting)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other four BASELINE.json configurations")
     args = ap.parse_args()
     cfg = list(CONFIGS[args.config])
     if args.spp:

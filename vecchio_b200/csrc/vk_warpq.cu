@@ -30,7 +30,7 @@
 namespace VK_NS {
 
 #ifndef VKQ_N
-#define VKQ_N 192 // slots per warp (<= VKQ_RN <= 256: ring indices are bytes)
+#define VKQ_N 176 // slots per warp (16 warps x (68 B x 176 + rings) = 222 KB of the SM's 227 KB; (<= VKQ_RN <= 256: ring indices are bytes)
 #endif
 #ifndef VKQ_WARPS
 #define VKQ_WARPS 4
@@ -59,7 +59,7 @@ struct WqWarp {
     uint32_t px[VKQ_N];          // pixel of the slot's sample
     uint8_t ring[VKQ_NQ][VKQ_RN]; // slot indices, one ring per queue
     uint2 ct[8];                 // per queue: .x = entries, .y = ring write position
-    uint32_t cur_s, cur_p, left; // unit cursor: next unit is (sample cur_s, pixel cur_p), `left` units remain in the chunk
+    uint32_t cur_s, cur_y, cur_x, left; // unit cursor: next unit is (sample cur_s, row cur_y, column cur_x); `left` units remain in the chunk
     uint32_t exhausted;          // the global unit counter has run past the end
 };
 
@@ -113,7 +113,7 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
     if (m == 0u) return false;
     const uint32_t need = (uint32_t)__popc(m), rank = (uint32_t)__popc(m & C.below);
-    uint32_t served = 0, s = 0, p = 0;
+    uint32_t served = 0, s = 0, y = 0, x = 0;
     bool got = false;
 #pragma unroll 1
     while (served < need) { // at most two rounds: what the current chunk still holds, then a new chunk
@@ -130,8 +130,10 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
                     const unsigned long long rem = C.n_units - u0;
                     const unsigned long long sb = u0 / C.n_pixels;
                     S.left = rem < VKQ_CHUNK ? (uint32_t)rem : VKQ_CHUNK;
+                    const uint32_t p0 = (uint32_t)(u0 - sb * C.n_pixels); // once per chunk: the per-path code divides nothing
                     S.cur_s = (uint32_t)sb;
-                    S.cur_p = (uint32_t)(u0 - sb * C.n_pixels);
+                    S.cur_y = p0 / C.a.width;
+                    S.cur_x = p0 - (p0 / C.a.width) * C.a.width;
                 }
             }
             __syncwarp();
@@ -139,24 +141,34 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
             left = __reduce_max_sync(0xFFFFFFFFu, S.left);
         }
         const uint32_t take = min(need - served, left);
-        const uint32_t cs = S.cur_s, cp = S.cur_p;
-        if (want && rank >= served && rank < served + take) {
-            p = cp + (rank - served);
+        const uint32_t cs = S.cur_s, cy = S.cur_y, cx = S.cur_x;
+        if (want && rank >= served && rank < served + take) { // units run row-major inside a sample (i = y*width + x)
+            x = cx + (rank - served);
+            y = cy;
             s = cs;
-            while (p >= C.n_pixels) { // units run pixel-major inside a sample
-                p -= C.n_pixels;
+            while (x >= C.a.width) {
+                x -= C.a.width;
+                ++y;
+            }
+            while (y >= C.a.height) {
+                y -= C.a.height;
                 ++s;
             }
             got = true;
         }
         __syncwarp();
         if (C.lane == 0) {
-            uint32_t np = cp + take, ns = cs;
-            while (np >= C.n_pixels) {
-                np -= C.n_pixels;
+            uint32_t nx = cx + take, ny = cy, ns = cs;
+            while (nx >= C.a.width) {
+                nx -= C.a.width;
+                ++ny;
+            }
+            while (ny >= C.a.height) {
+                ny -= C.a.height;
                 ++ns;
             }
-            S.cur_p = np;
+            S.cur_x = nx;
+            S.cur_y = ny;
             S.cur_s = ns;
             S.left = left - take;
         }
@@ -164,7 +176,7 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
         served += take;
     }
     if (got) {
-        const uint32_t y = p / C.a.width, x = p - y * C.a.width; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
+        const uint32_t p = y * C.a.width + x; // i = y*width + x, row 0 = bottom (src/main.rs:182-183)
         PathRng rng;
         rng.pixel = p;
         rng.sample = C.a.spp_begin + s;
@@ -180,6 +192,9 @@ VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
     return got;
 }
 
+VKD bool wq_black_miss(const RenderArgs& a) {
+    return !(a.flags & VK_FLAG_SKY_BACKGROUND) && a.background.x == 0.0f && a.background.y == 0.0f && a.background.z == 0.0f;
+}
 VKD uint32_t wq_class_of(const DScene& sc, uint32_t prim, uint32_t inst) {
     uint32_t mat;
     const uint32_t i = VKD_INDEX(prim);
@@ -320,7 +335,8 @@ VKD void wq_init(WqWarp& S, uint32_t lane) { // every slot starts in the regener
         S.left = 0u;
         S.exhausted = 0u;
         S.cur_s = 0u;
-        S.cur_p = 0u;
+        S.cur_y = 0u;
+        S.cur_x = 0u;
     }
     __syncwarp();
     if (lane == 0) S.ct[VKQ_END] = make_uint2(VKQ_N, VKQ_N);
@@ -353,6 +369,8 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
     const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
     uint32_t n_rays = 0, n_drop = 0, n_prims = 0;
     constexpr uint32_t EXT_CAP = 32u * VKQ_K;
+    // a miss under the constant black background of src/main.rs:124 adds nothing: the slot goes straight to regeneration
+    const uint32_t miss_cls = wq_black_miss(a) ? (uint32_t)VKQ_END : (uint32_t)VKQ_EMIT;
     wq_init(S, lane);
 #pragma unroll 1
     for (;;) {
@@ -393,7 +411,7 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
                 ++n_rays;
                 n_prims += flat->n;
                 uint32_t prim = VK_REF_NONE, hi = 0u;
-                cls = VKQ_EMIT; // a miss ends the sample like an emitter does
+                cls = miss_cls; // a miss ends the sample like an emitter does
                 if (best_hit[k] != 0xFFFFFFFFu) {
                     const FlatHit& fh = flat->hits[best_hit[k]];
                     prim = fh.prim & ~VKD_DUP;
@@ -431,6 +449,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
     const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
     uint32_t n_rays = 0, n_drop = 0;
     TraceCounters tc = {0u, 0u};
+    const uint32_t miss_cls = wq_black_miss(a) ? (uint32_t)VKQ_END : (uint32_t)VKQ_EMIT;
     wq_init(S, lane);
 
     Trav T; // this lane's ray in flight (T.ref == VKD_DONE: none)
@@ -502,7 +521,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
                 cur = 0xFFFFFFFFu;
                 S.hp[slot] = make_uint4(__float_as_uint(T.best.t), T.best.prim,
                                         (T.best.inst ? (0x80000000u | VKD_INDEX(T.best.inst)) : 0u) | (T.best.face << 28), 0u);
-                cls = T.best.prim == VK_REF_NONE ? (uint32_t)VKQ_EMIT : wq_class_of(sc, T.best.prim, T.best.inst);
+                cls = T.best.prim == VK_REF_NONE ? miss_cls : wq_class_of(sc, T.best.prim, T.best.inst);
             }
             wq_push(S, cls, slot, lane, below);
         }
