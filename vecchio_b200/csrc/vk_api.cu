@@ -30,6 +30,8 @@ struct vk_ctx {
     bool has_scene = false;
     uint32_t n_nodes = 0; // BVH nodes of the uploaded scene
     uint32_t n_materials = 0, n_textures = 0, n_media = 0;
+    size_t wnodes_bytes = 0;                    // size of the 4-wide node array (the L2 access-policy window covers it)
+    size_t l2_persist_max = 0, l2_window_max = 0; // device limits for persisting L2 lines / the policy window
     bool has_specdiffuse = false;
     bool simple_scene = false; // only what the VK_SIMPLE build of the staged kernel keeps (see vk_device.cuh)
     unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
@@ -191,6 +193,10 @@ int vk_create(int device, vk_ctx** out) {
         return VK_ERR_NO_DEVICE;
     }
     c->sm_count = prop.multiProcessorCount;
+    c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (c->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max); // used by large BVHs only
+    cudaGetLastError();
     c->clock_khz = prop.clockRate;
     std::snprintf(c->name, sizeof(c->name), "%.100s", prop.name);
     CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -300,6 +306,7 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     c->n_materials = d->n_materials;
     c->n_textures = d->n_textures;
     c->n_media = d->n_media;
+    c->wnodes_bytes = wnodes.size() * sizeof(float4);
     c->has_specdiffuse = R.has_specdiffuse;
     c->simple_scene = R.simple;
     c->flat = R.flat;
@@ -417,6 +424,26 @@ static bool use_dynamic_megakernel(const vk_ctx* c) {
     return c->n_nodes >= 65536u;
 }
 
+// Large BVHs (the 10^6-sphere scene: 64 MB of 4-wide nodes, every ray touches ~30 of them at random) share the
+// 126 MB L2 with the frame's accumulators (a 4K frame is 199 MB of atomics streaming through).  An access-policy window
+// on the node array keeps the nodes' lines resident (persisting) and lets everything else stream.  Small scenes are
+// L1 / L2 resident anyway and get no window.  VECCHIO_L2_PERSIST=0 turns it off (A/B runs).
+static void apply_l2_window(vk_ctx* c) {
+    cudaStreamAttrValue v{};
+    const char* e = std::getenv("VECCHIO_L2_PERSIST");
+    const bool on = c->wnodes_bytes >= (8u << 20) && c->l2_persist_max && c->l2_window_max && !(e && e[0] == '0');
+    if (on) {
+        const size_t bytes = c->wnodes_bytes < c->l2_window_max ? c->wnodes_bytes : c->l2_window_max;
+        v.accessPolicyWindow.base_ptr = (void*)c->scene.wnodes;
+        v.accessPolicyWindow.num_bytes = bytes;
+        v.accessPolicyWindow.hitRatio = bytes <= c->l2_persist_max ? 1.0f : (float)((double)c->l2_persist_max / (double)bytes);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } // else: a zero-sized window clears a previous scene's
+    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
+}
+
 // shared body of vk_render / vk_render_device
 // acc_only: leave the result in the context's integer accumulators (c->partial) and skip the conversion to fp32 sums
 // (the multi-GPU context reduces the accumulators of all its devices itself); want_sq then says whether squares are kept
@@ -483,6 +510,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     a.n_chunks = (count + a.chunk_spp - 1) / a.chunk_spp;
 
     CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // work-queue head only
+    apply_l2_window(c);
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
     uint32_t launches = 0;
