@@ -3,7 +3,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
 python -m pytest tests -m gpu -q -rxXs > gpurun_out/r2_pytest_gpu_1.log 2>&1
 tail -5 gpurun_out/r2_pytest_gpu_1.log
 FLAT="cornell_box:600:600:1000:100:4 cornell_smoke:600:600:500:100:4"
-for tag in a2 a1 a3 b1 b2 c1 c2 c3 a2r33 a2norc a2nocv; do
+for tag in a2 a1 a3 b1 b2 c1 c2 c3 a2r33 a2norc a2nocv a2fr c2fr; do
   VECCHIO_GPU_LIB=build/libvk_$tag.so python scripts/_sweep.py $tag $FLAT >> gpurun_out/r2_sweep_1.log 2>&1
 done
 python scripts/_sweep.py default cornell_box:600:600:1000:100:3 cornell_smoke:600:600:500:100:3 cornell_box:600:600:1000:100:4 cornell_smoke:600:600:500:100:4 \

@@ -79,21 +79,33 @@ def compare_bounces(vb, desc, ref, got, tol_dir, tol_w, legacy=False):
     ref_bad = ~np.all(np.isfinite(ref["beta"]), axis=1)
     assert np.array_equal(got["valid"] == 0, ref_bad | (ref["valid"] == 0)), "validity (non-finite weight) differs"
     ok = ~ref_bad & (ref["valid"] != 0)
-    # the GPU ends a path whose weight became 0 (nothing further can contribute); the reference recurses with weight 0
+    # the GPU ends a path whose weight became 0 (nothing further can contribute); the reference recurses with weight 0.
+    # A cosine that is zero to rounding (|cos| < 1e-5) may be positive on one side and negative on the other.
     alive_ref = (ref["alive"] != 0) & ~ref_w0
     alive_got = (got["alive"] != 0) & ~np.all(got["beta"] == 0.0, axis=1)
-    assert np.array_equal(alive_got[ok], alive_ref[ok]), "continue / end differs"
-    cont = ok & alive_ref
-    if legacy:  # legacy Metal absorbs below the surface: with fuzz the two sides draw different points -> compare only where both continue
-        cont = cont & (got["alive"] != 0)
+    und = unit(ref["out_d"].astype(np.float64) + 1e-300)
+    grazing = (np.abs(np.sum(und * ref["normal"], axis=1)) < 1e-4) | (np.abs(ref["beta"]).max(axis=1) < 1e-4) | (np.abs(got["beta"]).max(axis=1) < 1e-4)
+    differ = ok & ~rejection & (alive_got != alive_ref)  # (a rejection-sampled direction may be absorbed on one side only: legacy Metal)
+    assert not (differ & ~grazing).any(), ("continue / end differs", int((differ & ~grazing).sum()), eff[differ & ~grazing][:8].tolist())
+    assert differ.sum() <= 1e-3 * len(ref), ("too many grazing disagreements", int(differ.sum()))
+    cont = ok & alive_ref & alive_got
     det = cont & ~rejection
-    # a weight is albedo * cos / pdf: a grazing cosine is a difference of O(1) terms, so its error is absolute
-    werr = np.abs(got["beta"][det].astype(np.float64) - ref["beta"][det]) - tol_w * np.abs(ref["beta"][det])
-    wbad = werr > tol_w * 0.1
-    assert not wbad.any(), ("weights differ", int(wbad.sum()), float(werr.max()), eff[det][wbad.any(axis=1)][:8].tolist(),
-                            got["beta"][det][wbad.any(axis=1)][:4].tolist(), ref["beta"][det][wbad.any(axis=1)][:4].tolist())
-    scale = np.abs(ref["out_d"][det]).max(axis=1, keepdims=True)
-    assert np.all(np.abs(got["out_d"][det] - ref["out_d"][det]) <= tol_dir * scale), np.abs(got["out_d"][det] - ref["out_d"][det]).max()
+    # A weight is albedo * cos / pdf and the direction itself carries ~1e-6 of rounding (sincos, the association of
+    # 2 pi r1): the weight's error is that over the cosine, so it is bounded relative to the weight only away from grazing
+    cosn = np.abs(np.sum(und * ref["normal"], axis=1))
+    tol_i = (tol_w + 3.0 * tol_dir / np.maximum(cosn, 1e-3))[:, None]
+    werr = np.abs(got["beta"].astype(np.float64) - ref["beta"]) - tol_i * np.abs(ref["beta"])
+    wbad = det[:, None] & (werr > 1e-7)
+    assert not wbad.any(), ("weights differ", int(wbad.sum()), float(werr[wbad].max()), eff[wbad.any(axis=1)][:8].tolist(),
+                            got["beta"][wbad.any(axis=1)][:4].tolist(), ref["beta"][wbad.any(axis=1)][:4].tolist(), cosn[wbad.any(axis=1)][:4].tolist())
+    # directions: error relative to the magnitude of what was added up (a light-sampled direction is point - origin,
+    # legacy Lambertian is normal + unit vector: both can cancel)
+    u0 = (ref["xi"][:, 0] >> 8).astype(np.float32) * np.float32(2.0 ** -24)
+    light_branch = (not legacy) & (u0 < 0.5) & np.isin(eff, (vb.VK_M_LAMBERTIAN, vb.VK_M_ISOTROPIC))
+    scale = np.abs(ref["out_d"]).max(axis=1, keepdims=True) + 1.0 + (np.abs(ref["p"]).max(axis=1) * light_branch)[:, None]
+    derr = np.abs(got["out_d"].astype(np.float64) - ref["out_d"])
+    dbad = det[:, None] & (derr > tol_dir * scale)
+    assert not dbad.any(), ("directions differ", int(dbad.sum()), float(derr[dbad].max()), eff[dbad.any(axis=1)][:8].tolist())
     assert np.array_equal(got["out_o"][cont], ref["out_o"][cont]) and np.array_equal(got["out_time"][cont], ref["out_time"][cont])
     # rejection-sampled directions: inside the law's support, same attenuation
     rj = cont & rejection
@@ -178,7 +190,10 @@ def run_eval_parity(vb, scene, oracle, evaluate, strict):
         both = (ref["value"] > 0) & (got["value"] > 0)
         # a direction that grazes a light's edge may be in on one side and out on the other
         assert (both | ((ref["value"] == 0) & (got["value"] == 0))).mean() > 0.999
-        assert np.allclose(got["value"][both], ref["value"][both], rtol=1e-5 if strict else 1e-4)
+        # a sphere light's pdf is 1 / (2 pi (1 - cos_max)) with cos_max = sqrt(1 - r^2 / d^2) (src/hittable.rs:104-111): for a
+        # small far light 1 - cos_max cancels, an fp32 rounding of cos_max is a relative error of eps * 2 pi * pdf
+        rel = np.abs(got["value"][both].astype(np.float64) / ref["value"][both] - 1.0)
+        assert np.all(rel <= (1e-5 if strict else 1e-4) + (4e-7 if strict else 2e-6) * ref["value"][both]), float(rel.max())
         out["lights"] = {"random": len(r), "pdf": len(q), "pdf_nonzero": int(both.sum())}
     return out
 

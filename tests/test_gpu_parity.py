@@ -263,7 +263,9 @@ def test_image_parity_3_sigma(vb, po, ctx, name, param, W, spp_o, spp_g, depth):
     dt = diff[: th * 8, : tw * 8].reshape(th, 8, tw, 8, 3).sum(axis=(1, 3))
     st = np.sqrt((se[: th * 8, : tw * 8] ** 2).reshape(th, 8, tw, 8, 3).sum(axis=(1, 3)))
     zt = dt[st > 0] / st[st > 0]
-    assert (np.abs(zt) <= 3).mean() >= 0.98 and np.abs(zt).max() <= 6.0, (name, (np.abs(zt) <= 3).mean(), np.abs(zt).max())
+    ztile = np.where(st > 0, np.abs(dt) / np.where(st > 0, st, 1.0), 0.0).max(axis=2)  # worst channel per tile
+    # one firefly (a single sample orders of magnitude above its pixel's mean) can own a tile: at most one such tile
+    assert (np.abs(zt) <= 3).mean() >= 0.98 and (ztile > 6.0).sum() <= 1, (name, (np.abs(zt) <= 3).mean(), np.abs(zt).max(), np.argwhere(ztile > 6.0).tolist())
     assert abs(rg.mean() - ro.mean()) <= 0.01 * ro.mean(), (name, rg.mean(), ro.mean())
 
 
@@ -405,7 +407,9 @@ def test_golden_book1_render_matches_published_sample(vb, ctx):
     ctx.upload(scene)
     flags = vb.VK_FLAG_LEGACY_SCATTER | vb.VK_FLAG_SKY_BACKGROUND
     rgb, _, st = ctx.render(cam, vb.render_params(1024, 576, 256, 50, seed=1, flags=flags))
-    assert st.dropped_samples == 0
+    # (refract()'s sqrt of a rounding-negative number makes a NaN ray, the reference's own Q7: such a sample is dropped
+    # exactly as main.rs:192 drops it; which of 1.5e8 samples hit that case depends on FMA contraction)
+    assert st.dropped_samples <= 1e-7 * st.paths
     for name, ratio in book1_region_ratios(g, rgb[::-1].astype(np.float64)).items():
         assert np.all(np.abs(ratio - 1.0) <= BOOK1_TOL[name]), (name, ratio)
 
@@ -521,16 +525,18 @@ def test_rgb8_frame_is_to_color_of_the_float_frame(vb, ctx):
 LEGACY_CASES = [("random_spheres_cover", 96, 128, 50, True), ("cornell_box", 64, 512, 50, False), ("final_scene", 48, 128, 50, False)]
 
 
+@pytest.mark.parametrize("variant", [1, 4], ids=["megakernel", "warpq"])
 @pytest.mark.parametrize("name,W,spp,depth,sky", LEGACY_CASES, ids=[c[0] for c in LEGACY_CASES])
-def test_legacy_integrator_image_parity(vb, po, ctx, name, W, spp, depth, sky):
+def test_legacy_integrator_image_parity(vb, po, ctx, name, W, spp, depth, sky, variant):
+    """The legacy integrator runs in the lane megakernel and in the warp-queue kernel (flat program and BVH)."""
     scene, cam = get_scene(vb, name)
     H = scene.height_for(W)
     o = po.OracleScene(scene)
     ctx.upload(scene)
     flags = vb.VK_FLAG_LEGACY_SCATTER | (vb.VK_FLAG_SKY_BACKGROUND if sky else 0)
     ro, qo, so = o.render(cam, vb.render_params(W, H, spp, depth, seed=51, flags=flags), want_sumsq=True)
-    rg, qg, sg = ctx.render(cam, vb.render_params(W, H, spp, depth, seed=52, flags=flags), want_sumsq=True)
-    assert sg.variant == vb.VK_VARIANT_MEGAKERNEL and np.isfinite(rg).all()
+    rg, qg, sg = ctx.render(cam, vb.render_params(W, H, spp, depth, seed=52, flags=flags, variant=variant), want_sumsq=True)
+    assert sg.variant == variant and np.isfinite(rg).all()
     assert abs(sg.rays / sg.paths - so.rays / so.paths) <= 0.02 * so.rays / so.paths, (sg.rays / sg.paths, so.rays / so.paths)
     z, nz, diff, se = zscores(rg, qg, spp, ro, qo, spp)
     frac = (np.abs(z[nz]) <= 3.0).mean()

@@ -296,6 +296,7 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     UP(texels, uint8_t, d->texels, (size_t)d->n_texel_bytes)
     UP(perlin_vec, float4, pvec.data(), pvec.size())
     UP(perlin_perm, uint8_t, pperm.data(), pperm.size())
+    UP(flat_shade, float4, R.flat_shade.data(), R.flat_shade.size())
 #undef UP
     s.root = d->root;
     s.n_lights = d->n_lights;

@@ -369,8 +369,9 @@ VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float3 inv_d
 
 // ConstantMedium::hit (src/hittable.rs:453-493).  The boundary is a leaf, possibly behind a wrapper
 // chain (t is invariant under the chain).
+// (out of line; MediumXi by value so that the callers' copies stay in registers)
 static __device__ __noinline__ bool medium_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float time, float tmin, float tmax,
-                                      const MediumXi& xi, float& t) {
+                                      const MediumXi xi, float& t) {
     const float4 m = __ldg(&sc.media[VKD_INDEX(ref)]);
     float3 bo = o, bd = d;
     const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
@@ -723,46 +724,14 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
 // K rays per thread through the flat program (the staged kernel traces all the slots a thread owns
 // together): an entry's operands are fetched once for the K rays and the K closest-hit chains are
 // independent, which is the instruction-level parallelism a warp-per-SM-quarter schedule lacks.
-// VK_RECT_CENTER (render build only): plane distance as ONE fma (k * 1/d - o * 1/d, the second product hoisted per
-// ray and frame) and the bounds as |a - centre| <= half extent, i.e. 5 FMA-pipe + 6 comparison / select instructions
-// per ray and rect instead of 4 + 8.  Measured on B200 the comparison (ALU) pipe runs at half the FMA pipe's rate and
-// is this loop's limiter.  Same predicate as Rect::hit up to the rounding of the bounds (inclusive, NaN passes).
-#ifndef VK_RECT_CENTER
-#define VK_RECT_CENTER (!VK_STRICT)
-#endif
 template <int K, int AX, bool BOX_SIDE>
 VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const float3 (&co)[K], const float3 (&cd)[K], const float3 (&ci)[K],
-                      const float3 (&oi)[K], float tmin, float (&best_t)[K], uint32_t (&best_hit)[K]) {
+                      float tmin, float (&best_t)[K], uint32_t (&best_hit)[K]) {
 #pragma unroll 1
     for (uint32_t i = i0; i < i1; ++i) {
+        const float4 bd = P.rects[i].bounds;
         const float k = P.rects[i].k;
         const uint32_t id = P.rects[i].hit;
-#if VK_RECT_CENTER
-        const float ca = P.rectc[i].ca, ha = P.rectc[i].ha, cb = P.rectc[i].cb, hb = P.rectc[i].hb;
-#pragma unroll
-        for (int q = 0; q < K; ++q) {
-            float tt, a, b;
-            if (AX == 0) {
-                tt = fmaf(k, ci[q].z, oi[q].z);
-                a = fmaf(tt, cd[q].x, co[q].x - ca);
-                b = fmaf(tt, cd[q].y, co[q].y - cb);
-            } else if (AX == 1) {
-                tt = fmaf(k, ci[q].y, oi[q].y);
-                a = fmaf(tt, cd[q].x, co[q].x - ca);
-                b = fmaf(tt, cd[q].z, co[q].z - cb);
-            } else {
-                tt = fmaf(k, ci[q].x, oi[q].x);
-                a = fmaf(tt, cd[q].y, co[q].y - ca);
-                b = fmaf(tt, cd[q].z, co[q].z - cb);
-            }
-            bool miss = (tt < tmin) | (tt > best_t[q]) | (fabsf(a) > ha) | (fabsf(b) > hb);
-            if (BOX_SIDE) miss = miss | !(tt < best_t[q]);
-            best_t[q] = miss ? best_t[q] : tt;
-            best_hit[q] = miss ? best_hit[q] : id;
-        }
-#else
-        (void)oi;
-        const float4 bd = P.rects[i].bounds;
 #pragma unroll
         for (int q = 0; q < K; ++q) {
             float tt, a, b;
@@ -779,13 +748,16 @@ VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const floa
                 a = co[q].y + tt * cd[q].y;
                 b = co[q].z + tt * cd[q].z;
             }
-            // same predicate as Rect::hit, evaluated without branches (bitwise on the comparison results)
+            // same predicate as Rect::hit, evaluated without branches (bitwise on the comparison results).
+            // (Measured and rejected in round 2: the plane distance as one fma, k * (1/d) - o * (1/d), and the bounds as
+            // |a - centre| <= half extent.  0.6 % faster, but a ray that STARTS on the plane -- every scattered ray --
+            // no longer gets t = 0 exactly: the two products cancel to rounding noise of either sign, scaled by 1/d.
+            // Dropped samples rose from 26 to 1503 per 3.6e8 paths and light leaked around the box.)
             bool miss = (tt < tmin) | (tt > best_t[q]) | (a < bd.x) | (a > bd.y) | (b < bd.z) | (b > bd.w);
             if (BOX_SIDE) miss = miss | !(tt < best_t[q]);
             best_t[q] = miss ? best_t[q] : tt;
             best_hit[q] = miss ? best_hit[q] : id;
         }
-#endif
     }
 }
 // `live` masks the rays that exist (an idle slot's ray is traced as a dummy and ignored); out_hit
@@ -821,18 +793,14 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
                 }
             }
         }
-        float3 oi[K]; // -o * (1/d): the plane distance becomes one fma (VK_RECT_CENTER)
 #pragma unroll
-        for (int q = 0; q < K; ++q) {
-            ci[q] = rcp3(cd[q]);
-            oi[q] = f3(-co[q].x * ci[q].x, -co[q].y * ci[q].y, -co[q].z * ci[q].z);
-        }
-        flat_rects_k<K, 0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, oi, tmin, best_t, best_hit);
-        flat_rects_k<K, 1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, oi, tmin, best_t, best_hit);
-        flat_rects_k<K, 2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, oi, tmin, best_t, best_hit);
-        flat_rects_k<K, 0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, oi, tmin, best_t, best_hit);
-        flat_rects_k<K, 1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, oi, tmin, best_t, best_hit);
-        flat_rects_k<K, 2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, oi, tmin, best_t, best_hit);
+        for (int q = 0; q < K; ++q) ci[q] = rcp3(cd[q]);
+        flat_rects_k<K, 0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, tmin, best_t, best_hit);
+        flat_rects_k<K, 2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, tmin, best_t, best_hit);
 #pragma unroll 1
         for (uint32_t i = g.sph0; i < g.sph1; ++i) {
             const float4 sp = P.spheres[i].a;
@@ -862,7 +830,7 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
         if (MEDIA) {
 #pragma unroll 1
             for (uint32_t i = g.med0; i < g.med1; ++i) {
-#pragma unroll 1
+#pragma unroll // (static indices: a rolled loop over q sends co / cd / best_t / xi to local memory for the whole function)
                 for (int q = 0; q < K; ++q) {
                     float tt;
                     if (live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt)) {

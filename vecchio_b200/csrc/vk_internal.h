@@ -45,6 +45,7 @@ struct DScene {
     const uint8_t* texels;
     const float4* perlin_vec;   // 256 x float4 per Perlin
     const uint8_t* perlin_perm; // 768 B per Perlin (x, y, z)
+    const float4* flat_shade;   // 2 x float4 per hit entry of the flat program (see Relayout::flat_shade); may be empty
     uint32_t root;
     uint32_t n_lights;
     uint32_t has_media; // scene holds a ConstantMedium: selects the kernel instantiation with the medium code
@@ -86,9 +87,7 @@ struct FlatRect { // Rect::hit src/hittable.rs:230-239
     uint32_t hit; // index into FlatProgram::hits
     uint32_t _pad[2];
 };
-struct FlatRectC { // the same bounds as centre / half extent, for the render build's test |a - ca| <= ha (one comparison
-    float ca, ha, cb, hb; // per coordinate instead of two: the rect loop is bound by the comparison pipe, not the FMA pipe)
-};
+
 struct FlatSphere { // Sphere::hit :65-95 | MovingSphere::hit :154-184
     float4 a; // center (center0), radius
     float4 b; // moving: center1, time0
@@ -118,7 +117,6 @@ struct FlatProgram {
     FlatSeg segs[VKF_MAX_SEGS];
     FlatOp ops[VKF_MAX_OPS];
     FlatRect rects[VKF_MAX_RECTS];
-    FlatRectC rectc[VKF_MAX_RECTS];
     FlatSphere spheres[VKF_MAX_SPHERES];
     FlatHit hits[VKF_MAX_RECTS + VKF_MAX_SPHERES + VKF_MAX_MEDIA];
     // Hybrid programs.  A heterogeneous scene (final scene: spheres, a moving sphere, media, a box field,

@@ -356,8 +356,6 @@ struct FlatBuilder {
                 for (auto& e : g.rects[k]) {
                     e.first.hit = n_hits;
                     P->hits[n_hits++] = e.second;
-                    const float4 bd = e.first.bounds;
-                    P->rectc[n_rects] = FlatRectC{0.5f * (bd.x + bd.y), 0.5f * (bd.y - bd.x), 0.5f * (bd.z + bd.w), 0.5f * (bd.w - bd.z)};
                     P->rects[n_rects++] = e.first;
                 }
                 o.rect1[k] = (uint8_t)n_rects;
@@ -420,6 +418,15 @@ struct Relayout {
     FlatProgram flat{};
     uint32_t levels_world = 0, levels_sub = 0, n_wide = 0, stack_need = 0;
     bool simple = false, has_specdiffuse = false;
+    // Per entry of the flat program's hit table, for the render build's shade stage: {world-space outward normal,
+    // flags} {material index, -, -, -}.  flags bit 0: the HitRec of this entry can be written down directly --
+    // p = o + t d, normal = the constant normal turned against the ray -- instead of walking its wrapper chain; bit 1:
+    // FlipFace.  That holds for a rect or box side whose material reads no (u, v), and which either sits in the world
+    // frame, or under a chain whose OUTERMOST wrapper is a Translate and whose material does not read `front`
+    // (Lambertian, Metal, Isotropic): every level of the chain re-runs set_face_normal (src/hittable.rs:519, :618), so
+    // what leaves the Translate is +-(the rotated axis), turned against the WORLD ray -- whatever the levels below
+    // did.  `front` of a plain rect is dot(d, n) < 0, flipped by FlipFace (:300-308).
+    std::vector<float4> flat_shade;
     // returns nullptr or the reason the scene is unsupported
     const char* run(const vk_scene_desc* d) {
     // GPU-side re-layout of the node array: a single-object leaf (left == right) is tested twice
@@ -523,6 +530,53 @@ struct Relayout {
             // media included) for every ray where the BVH culls some, and the subtree traversals keep their
             // divergence.  VECCHIO_HYBRID=1 enables it (parity-tested: same image bit for bit).
             if (!(heterogeneous && std::getenv("VECCHIO_HYBRID") && fb.build(&flat, true) && flat.n_bvh > 0)) flat = FlatProgram{};
+        }
+        flat_shade.clear();
+        if (flat.n && flat.n_bvh == 0) {
+            Validator tv;
+            tv.d = d;
+            flat_shade.assign(2 * (size_t)flat.n, make_float4(0, 0, 0, 0));
+            for (uint32_t h = 0; h < flat.n; ++h) {
+                const FlatHit& fh = flat.hits[h];
+                const vk_ref pr = fh.prim & ~VKD_DUP;
+                const uint32_t i = VK_REF_INDEX(pr);
+                uint32_t a2, flip, mat;
+                if (VK_REF_TYPE(pr) == VK_T_RECT) {
+                    a2 = (d->rects[i].axes >> 4) & 3u;
+                    flip = (d->rects[i].axes & VK_RECT_FLIP) ? 1u : 0u;
+                    mat = d->rects[i].mat;
+                } else if (VK_REF_TYPE(pr) == VK_T_BOX) { // side `face` of Boxy::new: z, z, y, y, x, x; odd ones wrapped in FlipFace
+                    a2 = fh.face < 2 ? 2u : (fh.face < 4 ? 1u : 0u);
+                    flip = fh.face & 1u;
+                    mat = d->boxes[i].mat;
+                } else
+                    continue;
+                const vk_material& m = d->materials[mat];
+                const bool reads_uv = m.type == VK_M_SPECDIFFUSE || (m.type != VK_M_DIELECTRIC && tv.tex_has_image(m.tex, 0));
+                const bool reads_front = m.type == VK_M_DIELECTRIC || m.type == VK_M_DIFFUSE_LIGHT || m.type == VK_M_SPECDIFFUSE;
+                float n[3] = {a2 == 0 ? 1.f : 0.f, a2 == 1 ? 1.f : 0.f, a2 == 2 ? 1.f : 0.f};
+                bool ok = !reads_uv;
+                if (fh.inst) { // walk the chain, collect the levels, rotate the normal back out (innermost level first)
+                    std::vector<vk_xform> chain;
+                    vk_ref r = fh.inst;
+                    while (VK_REF_TYPE(r) == VK_T_XFORM) {
+                        chain.push_back(d->xforms[VK_REF_INDEX(r)]);
+                        r = chain.back().child;
+                    }
+                    ok = ok && !reads_front && !chain.empty() && chain.front().kind == VK_X_TRANSLATE;
+                    for (size_t l = chain.size(); l-- > 0 && ok;) {
+                        const vk_xform& x = chain[l];
+                        const float sn = x.a, cs = x.b, v0 = n[0], v1 = n[1], v2 = n[2];
+                        if (x.kind == VK_X_ROTATE_Y) { n[0] = cs * v0 + sn * v2; n[2] = -sn * v0 + cs * v2; }          // rot_back, vk_device.cuh
+                        else if (x.kind == VK_X_ROTATE_X) { n[1] = cs * v1 - sn * v2; n[2] = sn * v1 + cs * v2; }
+                        else if (x.kind == VK_X_ROTATE_Z) { n[0] = cs * v0 - sn * v1; n[1] = sn * v0 + cs * v1; }
+                        else if (x.kind == VK_X_FLIP) ok = false; // FlipFace of a non-rect inside a chain: keep the general path
+                    }
+                }
+                if (!ok) continue;
+                flat_shade[2 * h] = make_float4(n[0], n[1], n[2], __uint_as_float_host(1u | (flip << 1)));
+                flat_shade[2 * h + 1] = make_float4(__uint_as_float_host(mat), 0.f, 0.f, 0.f);
+            }
         }
         has_specdiffuse = false;
         for (uint32_t i = 0; i < d->n_materials; ++i) has_specdiffuse |= d->materials[i].type == VK_M_SPECDIFFUSE;

@@ -222,35 +222,25 @@ VKD WqCounts wq_counts(const WqWarp& S) {
     return c;
 }
 // The fullest queue: score = entries / batch width (EXT batches are ext_cap wide, the others 32; ext_cap == 0 leaves
-// the extend queue out).  Returns false when every considered queue is empty.
-VKD bool wq_pick(const WqCounts& c, uint32_t ext_cap, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
-    uint32_t best = ext_cap ? c.c01.x * 32u : 0u;
-    const uint32_t w = ext_cap ? ext_cap : 32u;
-    q = VKQ_EXT;
-    n_q = c.c01.x;
-    tail_q = c.c01.y;
-#define VKQ_CONSIDER(Q, CNT, TAIL)                                                                                     \
-    {                                                                                                                  \
-        const uint32_t sc_ = (CNT) * w;                                                                                \
-        if (sc_ > best) {                                                                                              \
-            best = sc_;                                                                                                \
-            q = (Q);                                                                                                   \
-            n_q = (CNT);                                                                                               \
-            tail_q = (TAIL);                                                                                           \
-        }                                                                                                              \
-    }
-    VKQ_CONSIDER(VKQ_EMIT, c.c23.x, c.c23.y)
-    VKQ_CONSIDER(VKQ_DIFF, c.c45.z, c.c45.w)
-    VKQ_CONSIDER(VKQ_DIFFI, c.c67.x, c.c67.y)
-    VKQ_CONSIDER(VKQ_DIEL, c.c23.z, c.c23.w)
-    VKQ_CONSIDER(VKQ_METAL, c.c45.x, c.c45.y)
-    VKQ_CONSIDER(VKQ_END, c.c01.z, c.c01.w)
-#undef VKQ_CONSIDER
-    // Every lane computed the same values from the same shared-memory words, but the compiler cannot know that: a
+// the extend queue out).  Returns false when every considered queue is empty.  One max chain over (score << 3 | queue).
+VKD bool wq_pick(const WqWarp& S, const WqCounts& c, uint32_t ext_cap, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
+    const uint32_t w = (ext_cap ? ext_cap : 32u) * 8u;
+    uint32_t key = ext_cap ? c.c01.x * 256u + VKQ_EXT : 0u; // entries * 32 * 8 | queue
+    key = max(key, c.c23.x * w + VKQ_EMIT);
+    key = max(key, c.c45.z * w + VKQ_DIFF);
+    key = max(key, c.c67.x * w + VKQ_DIFFI);
+    key = max(key, c.c23.z * w + VKQ_DIEL);
+    key = max(key, c.c45.x * w + VKQ_METAL);
+    key = max(key, c.c01.z * w + VKQ_END);
+    // Every lane computed the same value from the same shared-memory words, but the compiler cannot know that: a
     // warp reduction (REDUX, result in a uniform register) makes the choice provably warp-uniform, so the stage it
     // selects runs under uniform control flow (uniform-datapath loop counters and constant loads in the traversal).
-    q = __reduce_max_sync(0xFFFFFFFFu, q);
-    return __reduce_max_sync(0xFFFFFFFFu, best) != 0u;
+    key = __reduce_max_sync(0xFFFFFFFFu, key);
+    q = key & 7u;
+    const uint2 e = S.ct[q];
+    n_q = e.x;
+    tail_q = e.y;
+    return (key >> 3) != 0u;
 }
 // Take up to `cap` entries off queue q: returns how many, and the ring position of the first.
 VKD uint32_t wq_pop(WqWarp& S, uint32_t q, uint32_t n_q, uint32_t tail_q, uint32_t cap, uint32_t lane, uint32_t& head) {
@@ -265,7 +255,13 @@ VKD uint32_t wq_pop(WqWarp& S, uint32_t q, uint32_t n_q, uint32_t tail_q, uint32
 
 // One batch of a shading class (or of the regeneration queue): resolve + scatter (src/main.rs:131-149); a finished sample
 // goes through the NaN / Inf filter (:191-194) into its pixel; survivors go to the extend queue.
-template <bool LEGACY>
+// VKQ_FAST_RESOLVE (render build, flat scenes): a rect / box-side hit whose HitRec can be written down directly
+// (DScene::flat_shade, decided at upload) skips resolve_hit's walk down and up the wrapper chain: p = o + t d in the
+// world frame, normal = the entry's constant world normal turned against the ray.
+#ifndef VKQ_FAST_RESOLVE
+#define VKQ_FAST_RESOLVE 0
+#endif
+template <bool LEGACY, bool FLAT>
 VKD void wq_shade_batch(const DScene& sc, const WqCtx& C, const RenderBuffers& buf, uint32_t q, uint32_t n, uint32_t head, uint32_t& n_drop) {
     WqWarp& S = C.S;
     const RenderArgs& a = C.a;
@@ -296,7 +292,27 @@ VKD void wq_shade_batch(const DScene& sc, const WqCtx& C, const RenderBuffers& b
                 h.inst = (hi & 0x80000000u) ? (((uint32_t)VK_T_XFORM << 28) | (hi & 0x07FFFFFFu)) : 0u;
                 h.face = (hi >> 28) & 7u;
                 HitRecD rec;
-                resolve_hit(sc, h, o, d, time, false, rec);
+                bool direct = false;
+#if VKQ_FAST_RESOLVE && !VK_STRICT
+                if (FLAT) {
+                    const float4 fs = __ldg(&sc.flat_shade[2u * hp.w]);
+                    const uint32_t fl = __float_as_uint(fs.w);
+                    if (fl & 1u) {
+                        direct = true;
+                        const float3 nw = f3(fs);
+                        const bool toward = dot3(d, nw) < 0.0f;
+                        rec.p = at(o, d, h.t);
+                        rec.normal = toward ? nw : -nw;
+                        rec.front = (toward ? 1u : 0u) ^ ((fl >> 1) & 1u);
+                        rec.t = h.t;
+                        rec.u = 0.0f;
+                        rec.v = 0.0f;
+                        rec.mat = __float_as_uint(__ldg(&sc.flat_shade[2u * hp.w + 1u]).x);
+                        rec.m = __ldg(&sc.materials[rec.mat]);
+                    }
+                }
+#endif
+                if (!direct) resolve_hit(sc, h, o, d, time, false, rec);
                 alive = LEGACY ? shade_legacy(sc, rec, rng, depth, o, d, time, beta, L, valid)
                                : shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
                 if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
@@ -325,7 +341,17 @@ VKD void wq_shade_batch(const DScene& sc, const WqCtx& C, const RenderBuffers& b
     bool to_end = false;
     if (q == VKQ_END || (uint32_t)__popc(m_end) >= VKQ_REGEN_MIN) alive = wq_regen(C, ended, slot) || alive;
     else to_end = ended;
-    wq_push(S, alive ? (uint32_t)VKQ_EXT : (to_end ? (uint32_t)VKQ_END : (uint32_t)VKQ_NONE), slot, lane, C.below);
+    // survivors (and regenerated samples) to the extend queue, queued regenerations to theirs: two ballots
+    const uint32_t m_ext = __ballot_sync(0xFFFFFFFFu, alive), m_q = __ballot_sync(0xFFFFFFFFu, to_end);
+    const uint2 c_ext = S.ct[VKQ_EXT], c_end = S.ct[VKQ_END];
+    if (alive) S.ring[VKQ_EXT][(c_ext.y + __popc(m_ext & C.below)) & VKQ_RMASK] = (uint8_t)slot;
+    if (to_end) S.ring[VKQ_END][(c_end.y + __popc(m_q & C.below)) & VKQ_RMASK] = (uint8_t)slot;
+    __syncwarp();
+    if (lane == 0) {
+        S.ct[VKQ_EXT] = make_uint2(c_ext.x + (uint32_t)__popc(m_ext), c_ext.y + (uint32_t)__popc(m_ext));
+        if (m_q) S.ct[VKQ_END] = make_uint2(c_end.x + (uint32_t)__popc(m_q), c_end.y + (uint32_t)__popc(m_q));
+    }
+    __syncwarp();
 }
 
 VKD void wq_init(WqWarp& S, uint32_t lane) { // every slot starts in the regeneration queue
@@ -375,10 +401,10 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
 #pragma unroll 1
     for (;;) {
         uint32_t q, n_q, tail_q, head;
-        if (!wq_pick(wq_counts(S), EXT_CAP, q, n_q, tail_q)) break; // every queue is empty: all slots have retired
+        if (!wq_pick(S, wq_counts(S), EXT_CAP, q, n_q, tail_q)) break; // every queue is empty: all slots have retired
         const uint32_t n = wq_pop(S, q, n_q, tail_q, q == VKQ_EXT ? EXT_CAP : 32u, lane, head);
         if (q != VKQ_EXT) {
-            wq_shade_batch<LEGACY>(sc, C, buf, q, n, head, n_drop);
+            wq_shade_batch<LEGACY, true>(sc, C, buf, q, n, head, n_drop);
             continue;
         }
         // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------------
@@ -419,7 +445,7 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
                     hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);
                     cls = fh.cls == 0u ? VKQ_EMIT : fh.cls == 1u ? VKQ_DIEL : fh.cls == 2u ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
                 }
-                S.hp[slot[k]] = make_uint4(__float_as_uint(best_t[k]), prim, hi, 0u);
+                S.hp[slot[k]] = make_uint4(__float_as_uint(best_t[k]), prim, hi, best_hit[k]); // .w: entry of the flat program's hit table
             }
             if (k == 0 || n > 32u * k) wq_push(S, cls, slot[k], lane, below); // (warp-uniform condition)
         }
@@ -501,9 +527,9 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
         const uint32_t n_idle = 32u - (uint32_t)__popc(m_act);
         if (n_idle >= VKQ_BVH_IDLE && n_ext == 0u) { // ---- shade: refill the extend queue from the fullest class -----------
             uint32_t q, n_q, tail_q, head;
-            if (wq_pick(cnt, 0u, q, n_q, tail_q)) {
+            if (wq_pick(S, cnt, 0u, q, n_q, tail_q)) {
                 const uint32_t n = wq_pop(S, q, n_q, tail_q, 32u, lane, head);
-                wq_shade_batch<LEGACY>(sc, C, buf, q, n, head, n_drop);
+                wq_shade_batch<LEGACY, false>(sc, C, buf, q, n, head, n_drop);
                 continue;
             }
             if (m_act == 0u) break; // nothing in flight, nothing queued: all slots have retired
