@@ -455,12 +455,14 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
 
 // ---- BVH scenes: extend = the resumable traversal (Trav, vk_device.cuh) with dynamic fetch ------------------------------
 // Traversal lengths differ by orders of magnitude between rays (10^6 spheres: mean 28 four-wide visits, some hundreds),
-// so a lane is not tied to a batch: every lane keeps ONE ray's traversal in registers (stack in local memory), the warp
-// steps all of them in bounded while-while rounds under votes, and a lane whose ray has finished stores the hit, files
-// the slot under its shading class and takes the next entry of the extend queue.  Only when the extend queue is empty
-// and VKQ_BVH_IDLE lanes have nothing to traverse does the warp leave the traversal -- its other rays stay in flight in
-// registers -- to shade one full batch of the fullest class, which refills the extend queue.  Shading therefore always
-// runs on whole batches of one class, and traversal with at most VKQ_BVH_IDLE - 1 idle lanes.
+// so a lane is not tied to a batch: every lane keeps ONE ray's traversal in registers (stack in local memory) and the
+// warp steps all of them in bounded while-while rounds.  A round costs one vote beyond the traversal itself; only when
+// VKQ_BVH_IDLE lanes have nothing left to traverse does the warp do a TURNOVER: the finished rays store their hits and
+// are filed under their shading classes, the idle lanes take the next entries of the extend queue, and if that queue
+// could not feed them the warp shades one full batch of the fullest class -- its other rays stay in flight in
+// registers -- which refills the extend queue.  Shading therefore always runs on whole batches of one class, and
+// traversal with at most VKQ_BVH_IDLE - 1 idle lanes.  (First version: fetch and retire in every round, whenever one
+// lane was idle or finished -- ~190 instructions of bookkeeping per ~300 of traversal, half the lane megakernel's speed.)
 #ifndef VKQ_BVH_IDLE
 #define VKQ_BVH_IDLE 8u
 #endif
@@ -499,58 +501,60 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
     xi.rng.sample = 0;
 #pragma unroll 1
     for (;;) {
-        const WqCounts cnt = wq_counts(S);
-        const bool idle = T.ref == VKD_DONE;
-        const uint32_t m_idle = __ballot_sync(0xFFFFFFFFu, idle);
-        uint32_t n_ext = __reduce_max_sync(0xFFFFFFFFu, cnt.c01.x); // (provably uniform, see wq_pick)
-        if (m_idle != 0u && n_ext != 0u) { // ---- fetch: idle lanes take the next rays of the extend queue -------------------
-            uint32_t head;
-            const uint32_t take = wq_pop(S, VKQ_EXT, n_ext, cnt.c01.y, (uint32_t)__popc(m_idle), lane, head);
-            const uint32_t rank = (uint32_t)__popc(m_idle & below);
-            if (idle && rank < take) {
-                cur = S.ring[VKQ_EXT][(head + rank) & VKQ_RMASK];
-                const float4 ro = S.ro[cur], rd = S.rd[cur];
-                o = f3(ro);
-                d = f3(rd);
-                tm = ro.w;
-                xi.depth = __float_as_uint(rd.w);
-                if (MEDIA) {
-                    xi.rng.pixel = S.px[cur];
-                    xi.rng.sample = __float_as_uint(S.bt[cur].w);
+        // ---- turnover, only when VKQ_BVH_IDLE lanes have nothing to traverse (one vote per round otherwise): retire the
+        // finished rays, fetch new ones for every idle lane, and if the extend queue could not feed them, shade a batch
+        const bool done_lane = T.ref == VKD_DONE;
+        const uint32_t m_done = __ballot_sync(0xFFFFFFFFu, done_lane);
+        if ((uint32_t)__popc(m_done) >= VKQ_BVH_IDLE) {
+            const bool fin = done_lane && cur != 0xFFFFFFFFu;
+            if (__ballot_sync(0xFFFFFFFFu, fin) != 0u) { // finished rays: the hit, filed under its shading class
+                uint32_t cls = VKQ_NONE, slot = 0u;
+                if (fin) {
+                    slot = cur;
+                    cur = 0xFFFFFFFFu;
+                    S.hp[slot] = make_uint4(__float_as_uint(T.best.t), T.best.prim,
+                                            (T.best.inst ? (0x80000000u | VKD_INDEX(T.best.inst)) : 0u) | (T.best.face << 28), 0u);
+                    cls = T.best.prim == VK_REF_NONE ? miss_cls : wq_class_of(sc, T.best.prim, T.best.inst);
                 }
-                trav_init(T, sc, o, d, CUDART_INF_F); // world.hit(&r, 0.001, inf) src/main.rs:130
-                ++n_rays;
+                wq_push(S, cls, slot, lane, below);
             }
-            n_ext -= take;
-        }
-        const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, T.ref != VKD_DONE);
-        const uint32_t n_idle = 32u - (uint32_t)__popc(m_act);
-        if (n_idle >= VKQ_BVH_IDLE && n_ext == 0u) { // ---- shade: refill the extend queue from the fullest class -----------
-            uint32_t q, n_q, tail_q, head;
-            if (wq_pick(S, cnt, 0u, q, n_q, tail_q)) {
-                const uint32_t n = wq_pop(S, q, n_q, tail_q, 32u, lane, head);
-                wq_shade_batch<LEGACY, false>(sc, C, buf, q, n, head, n_drop);
-                continue;
+            const WqCounts cnt = wq_counts(S);
+            const uint32_t n_ext = __reduce_max_sync(0xFFFFFFFFu, cnt.c01.x); // (provably uniform, see wq_pick)
+            if (n_ext != 0u) { // fetch: the idle lanes take the next rays of the extend queue
+                uint32_t head;
+                const uint32_t take = wq_pop(S, VKQ_EXT, n_ext, cnt.c01.y, (uint32_t)__popc(m_done), lane, head);
+                const uint32_t rank = (uint32_t)__popc(m_done & below);
+                if (done_lane && rank < take) {
+                    cur = S.ring[VKQ_EXT][(head + rank) & VKQ_RMASK];
+                    const float4 ro = S.ro[cur], rd = S.rd[cur];
+                    o = f3(ro);
+                    d = f3(rd);
+                    tm = ro.w;
+                    xi.depth = __float_as_uint(rd.w);
+                    if (MEDIA) {
+                        xi.rng.pixel = S.px[cur];
+                        xi.rng.sample = __float_as_uint(S.bt[cur].w);
+                    }
+                    trav_init(T, sc, o, d, CUDART_INF_F); // world.hit(&r, 0.001, inf) src/main.rs:130
+                    ++n_rays;
+                }
             }
-            if (m_act == 0u) break; // nothing in flight, nothing queued: all slots have retired
+            const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, T.ref != VKD_DONE);
+            if (32u - (uint32_t)__popc(m_act) >= VKQ_BVH_IDLE) { // still starved: refill the extend queue from the fullest class
+                uint32_t q, n_q, tail_q, head;
+                if (wq_pick(S, wq_counts(S), 0u, q, n_q, tail_q)) {
+                    const uint32_t n = wq_pop(S, q, n_q, tail_q, 32u, lane, head);
+                    wq_shade_batch<LEGACY, false>(sc, C, buf, q, n, head, n_drop);
+                    continue;
+                }
+                if (m_act == 0u) break; // nothing in flight, nothing queued: all slots have retired
+            }
         }
         // ---- traverse: a bounded while-while round for every ray in flight ---------------------------------------------
         wq_converge();
 #pragma unroll 1
         for (int k = 0; k < VKQ_NODE_STEPS && trav_at_node(T); ++k) trav_node_step(T, sc, 0.001f, tc);
         if (T.ref != VKD_DONE && !trav_at_node(T)) trav_prim_step<MEDIA>(T, sc, o, d, tm, 0.001f, xi, tc);
-        const bool fin = cur != 0xFFFFFFFFu && T.ref == VKD_DONE;
-        if (__ballot_sync(0xFFFFFFFFu, fin) != 0u) { // finished rays: the hit, filed under its shading class
-            uint32_t cls = VKQ_NONE, slot = 0u;
-            if (fin) {
-                slot = cur;
-                cur = 0xFFFFFFFFu;
-                S.hp[slot] = make_uint4(__float_as_uint(T.best.t), T.best.prim,
-                                        (T.best.inst ? (0x80000000u | VKD_INDEX(T.best.inst)) : 0u) | (T.best.face << 28), 0u);
-                cls = T.best.prim == VK_REF_NONE ? miss_cls : wq_class_of(sc, T.best.prim, T.best.inst);
-            }
-            wq_push(S, cls, slot, lane, below);
-        }
     }
     wq_flush_counters(buf, lane, n_rays, n_drop, tc.nodes, tc.prims);
 }
