@@ -780,6 +780,7 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
             co[q] = o[q];
             cd[q] = d[q];
         }
+#if VK_STRICT
 #pragma unroll 1
         for (uint32_t k = g.op0; k < g.op1; ++k) {
             const uint32_t kind = P.ops[k].kind;
@@ -793,6 +794,21 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
                 }
             }
         }
+#else
+        if (g.op1 != g.op0) { // the chain as one affine map (composed at upload): no loop, no switch on the wrapper kind
+            const float* m = P.seg_affine[s];
+            const float r00 = m[0], r01 = m[1], r02 = m[2], r10 = m[3], r11 = m[4], r12 = m[5], r20 = m[6], r21 = m[7], r22 = m[8];
+            const float t0 = m[9], t1 = m[10], t2 = m[11];
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                const float3 wo = co[q], wd = cd[q];
+                co[q] = f3(fmaf(r00, wo.x, fmaf(r01, wo.y, fmaf(r02, wo.z, t0))), fmaf(r10, wo.x, fmaf(r11, wo.y, fmaf(r12, wo.z, t1))),
+                           fmaf(r20, wo.x, fmaf(r21, wo.y, fmaf(r22, wo.z, t2))));
+                cd[q] = f3(fmaf(r00, wd.x, fmaf(r01, wd.y, r02 * wd.z)), fmaf(r10, wd.x, fmaf(r11, wd.y, r12 * wd.z)),
+                           fmaf(r20, wd.x, fmaf(r21, wd.y, r22 * wd.z)));
+            }
+        }
+#endif
 #pragma unroll
         for (int q = 0; q < K; ++q) ci[q] = rcp3(cd[q]);
         flat_rects_k<K, 0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);

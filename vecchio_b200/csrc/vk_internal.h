@@ -129,6 +129,10 @@ struct FlatProgram {
     uint32_t n_bvh;
     uint32_t bvh[VKF_MAX_BVH];           // node refs of the sub-BVH roots
     uint32_t seg_inst[VKF_MAX_SEGS];     // instance (outermost wrapper) of each segment, 0 for the world frame
+    // The segment's chain of ops composed into one affine map (render build): object = R * world + t, rows of R then t.
+    // The reference applies the wrappers one after the other (src/hittable.rs:508, :591-595); composing them on the host
+    // changes the rounding only, so the strict build keeps walking the ops.
+    float seg_affine[VKF_MAX_SEGS][12];
 };
 
 struct DCamera {

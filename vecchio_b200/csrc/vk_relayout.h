@@ -386,6 +386,36 @@ struct FlatBuilder {
             for (uint32_t r : g.bvh) P->bvh[n_bvh++] = r;
             o.bvh1 = (uint8_t)n_bvh;
             P->seg_inst[s] = g.inst;
+            {   // compose the ops (outermost first) into object = R * world + t, in double
+                double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3] = {0, 0, 0};
+                for (const FlatOp& op : g.ops) {
+                    if (op.kind == VKF_OP_TRANSLATE) {
+                        t[0] -= op.a; t[1] -= op.b; t[2] -= op.c; // o - offset ... but in the CURRENT frame: see below
+                        continue;
+                    }
+                    // world -> object rotations of rot_fwd (vk_device.cuh): Y: x' = c x - s z, z' = s x + c z;
+                    // X: y' = c y + s z, z' = -s y + c z;  Z: x' = c x + s y, y' = -s x + c y
+                    const double sn = op.a, cs = op.b;
+                    double M[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+                    if (op.kind == VKF_OP_ROTY) { M[0][0] = cs; M[0][2] = -sn; M[2][0] = sn; M[2][2] = cs; }
+                    else if (op.kind == VKF_OP_ROTX) { M[1][1] = cs; M[1][2] = sn; M[2][1] = -sn; M[2][2] = cs; }
+                    else { M[0][0] = cs; M[0][1] = sn; M[1][0] = -sn; M[1][1] = cs; }
+                    double R2[3][3], t2[3];
+                    for (int i = 0; i < 3; ++i) {
+                        t2[i] = M[i][0] * t[0] + M[i][1] * t[1] + M[i][2] * t[2];
+                        for (int j = 0; j < 3; ++j) R2[i][j] = M[i][0] * R[0][j] + M[i][1] * R[1][j] + M[i][2] * R[2][j];
+                    }
+                    for (int i = 0; i < 3; ++i) {
+                        t[i] = t2[i];
+                        for (int j = 0; j < 3; ++j) R[i][j] = R2[i][j];
+                    }
+                }
+                // (a translate subtracts its offset from the point in the frame reached so far, which is exactly t -= offset)
+                for (int i = 0; i < 3; ++i) {
+                    for (int j = 0; j < 3; ++j) P->seg_affine[s][3 * i + j] = (float)R[i][j];
+                    P->seg_affine[s][9 + i] = (float)t[i];
+                }
+            }
         }
         P->n_bvh = n_bvh;
         for (uint32_t h = 0; h < n_hits; ++h) { // shading class of each entry's material
