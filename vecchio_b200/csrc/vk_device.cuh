@@ -1380,7 +1380,12 @@ VKD bool shade_xi(const DScene& sc, const HitRecD& rec, const XI& xi, float3& o,
     // Lambertian / Isotropic (src/material.rs:92-108, :448-464): cosine lobe about rec.normal,
     // mixed 50/50 with light sampling (src/main.rs:139-146).
     const float3 attenuation = tex_value(sc, m.y, rec.u, rec.v, rec.p);
+#if VK_STRICT
     const Onb uvw = onb_from_w(rec.normal);
+    const float3 onb_w = uvw.w;
+#else
+    const float3 onb_w = unit_vector(rec.normal); // ONB::new_from_w: w; u and v are built only where they are used
+#endif
     float3 nd;
     if (u01(r.x) < 0.5f) { // MixturePDF::generate src/util.rs:177-185 -> HittablePDF -> list random
 #if VK_SIMPLE
@@ -1391,10 +1396,13 @@ VKD bool shade_xi(const DScene& sc, const HitRecD& rec, const XI& xi, float3& o,
 #endif
     } else {
         const float3 c = random_cosine_direction(u01(r.y), u01(r.z));
+#if !VK_STRICT
+        const Onb uvw = onb_from_w(rec.normal);
+#endif
         nd = uvw.u * c.x + uvw.v * c.y + uvw.w * c.z;
     }
     const float3 und = unit_vector(nd);
-    const float cos_w = dot3(und, uvw.w);
+    const float cos_w = dot3(und, onb_w);
     const float cosine_pdf = cos_w <= 0.0f ? 0.0f : cos_w / VK_PI;                // CosinePDF::value src/util.rs:134-142
     const float pdf = 0.5f * lights_pdf_value(sc, rec.p, nd) + 0.5f * cosine_pdf; // MixturePDF::value :173-175
     float spdf = 0.0f;                                                            // Material::scattering_pdf default
@@ -1402,7 +1410,11 @@ VKD bool shade_xi(const DScene& sc, const HitRecD& rec, const XI& xi, float3& o,
         const float cos_n = dot3(rec.normal, und);
         spdf = cos_n < 0.0f ? 0.0f : cos_n / VK_PI;
     }
+#if VK_STRICT
     const float3 w = f3(attenuation.x * spdf / pdf, attenuation.y * spdf / pdf, attenuation.z * spdf / pdf);
+#else
+    const float3 w = attenuation * (spdf / pdf); // one division (same value up to rounding; 0 / 0 and x / 0 stay NaN / inf)
+#endif
     if (!finite3(w)) { // reference: NaN/Inf poisons the sample, which main.rs:192 then drops (Q3)
         valid = false;
         return false;
