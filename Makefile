@@ -48,7 +48,7 @@ $(CSRC)/vk_staged_simple.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVK_SIMPLE=1 -DVKS_N=768 -DVKS_K=3 -DVKS_MINB=4 -c -o $@ $< 2> $(CSRC)/ptxas_staged_simple.log || (cat $(CSRC)/ptxas_staged_simple.log; false)
 $(CSRC)/vk_staged_strict.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_staged_strict.log || (cat $(CSRC)/ptxas_staged_strict.log; false)
-# the warp-queue kernel: <= 128 registers, 4 warps x 176 slots per CTA, 4 CTAs per SM
+# the warp-queue kernels (slots, rays per lane and CTAs per SM are set per kernel family in vk_warpq.cu)
 $(CSRC)/vk_warpq_fast.o: $(CSRC)/vk_warpq.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_warpq_fast.log || (cat $(CSRC)/ptxas_warpq_fast.log; false)
 $(CSRC)/vk_warpq_simple.o: $(CSRC)/vk_warpq.cu $(KDEPS)

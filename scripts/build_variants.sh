@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B builds of the warp-queue kernels: one library per parameter set under build/, selected at run time with
 # VECCHIO_GPU_LIB.  Both flavours of vk_warpq.cu (trimmed "simple scene" build and general render build) are compiled
-# with the tag's defines.  usage: scripts/build_variants.sh tag:"-DVKQ_N=.. -DVKQ_K=.." ...
+# with the tag's defines.  usage: scripts/build_variants.sh tag:"-DVKQ_N_FLAT=.. -DVKQ_K_FLAT=.." ...
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build
@@ -15,6 +15,6 @@ for spec in "$@"; do
   ( $NVCC $FLAGS -DVK_SIMPLE=1 $defs -c -o build/wq_$tag.o $C/vk_warpq.cu 2> build/wq_$tag.log || { cat build/wq_$tag.log; exit 1; }
     $NVCC $FLAGS $defs -c -o build/wqf_$tag.o $C/vk_warpq.cu 2> build/wqf_$tag.log || { cat build/wqf_$tag.log; exit 1; }
     $NVCC $ARCH -shared -o build/libvk_$tag.so $OTHERS build/wq_$tag.o build/wqf_$tag.o
-    echo "$tag: flat-simple $(grep -A2 'k_warpq_flatILb0ELb0' build/wq_$tag.log | grep -oE 'Used [0-9]+ registers|[0-9]+ bytes spill stores' | tr '\n' ' ') | bvh $(grep -A2 'k_warpqILb0ELb0' build/wqf_$tag.log | grep -oE 'Used [0-9]+ registers|[0-9]+ bytes spill stores' | tr '\n' ' ')" ) &
+    echo "$tag: flat-simple $(grep -A2 'k_warpq_flatILb0E' build/wq_$tag.log | grep -oE 'Used [0-9]+ registers|[0-9]+ bytes spill stores' | tr '\n' ' ') | bvh $(grep -A2 'k_warpqILb0ELb0' build/wqf_$tag.log | grep -oE 'Used [0-9]+ registers|[0-9]+ bytes spill stores' | tr '\n' ' ')" ) &
 done
 wait

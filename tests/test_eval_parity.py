@@ -94,7 +94,14 @@ def compare_bounces(vb, desc, ref, got, tol_dir, tol_w, legacy=False):
     # 2 pi r1): the weight's error is that over the cosine, so it is bounded relative to the weight only away from grazing
     cosn = np.abs(np.sum(und * ref["normal"], axis=1))
     tol_i = (tol_w + 3.0 * tol_dir / np.maximum(cosn, 1e-3))[:, None]
-    werr = np.abs(got["beta"].astype(np.float64) - ref["beta"]) - tol_i * np.abs(ref["beta"])
+    # a NoiseTexture albedo is sin(scale z + 10 turb) with seven octaves of fp32 sums behind an argument of order 10^2: its
+    # absolute error (see the texture records below: 2e-5 strict, 2e-3 render build) times spdf / pdf <= 2 enters the weight
+    def noisy(ti, depth=0):
+        t = desc.textures[ti]
+        return t.type == vb.VK_TEX_NOISE or (t.type == vb.VK_TEX_CHECKER and depth < 8 and (noisy(t.w[0], depth + 1) or noisy(t.w[1], depth + 1)))
+    mat_noisy = np.array([desc.materials[i].type not in (vb.VK_M_DIELECTRIC, vb.VK_M_SPECDIFFUSE) and noisy(desc.materials[i].tex) for i in range(desc.n_materials)])
+    tex_atol = np.where(mat_noisy[ref["index"]], 4.0 * (2e-5 if tol_dir <= 1e-6 else 2e-3), 0.0)[:, None]
+    werr = np.abs(got["beta"].astype(np.float64) - ref["beta"]) - tol_i * np.abs(ref["beta"]) - tex_atol
     wbad = det[:, None] & (werr > 1e-7)
     assert not wbad.any(), ("weights differ", int(wbad.sum()), float(werr[wbad].max()), eff[wbad.any(axis=1)][:8].tolist(),
                             got["beta"][wbad.any(axis=1)][:4].tolist(), ref["beta"][wbad.any(axis=1)][:4].tolist(), cosn[wbad.any(axis=1)][:4].tolist())
@@ -164,7 +171,8 @@ def run_eval_parity(vb, scene, oracle, evaluate, strict):
     """`evaluate(recs) -> recs` is the side under test (the GPU hook; the oracle itself in the CPU self-check)."""
     desc = scene.desc
     rng = np.random.default_rng(2024)
-    tol_dir, tol_w = (1e-6, 1e-5) if strict else (2e-5, 1e-4)
+    # render build: __sincosf on [0, 2 pi) (absolute error grows past pi), rsqrt, FMA contraction
+    tol_dir, tol_w = (1e-6, 1e-5) if strict else (1e-4, 1e-4)
     out = {}
     if desc.n_lights:
         recs = bounce_records(vb, desc, rng, 4000, vb.VK_EVAL_BOUNCE)

@@ -9,10 +9,10 @@
 //
 // Here every warp is its own wavefront machine and nothing is ever synchronised across warps:
 //
-//   * a warp owns VKQ_N path slots in shared memory (64 B each, the staged kernel's record) and one ring
+//   * a warp owns 120 - 176 path slots in shared memory (68 B each) and one ring
 //     buffer of slot indices per QUEUE: rays to extend, samples to regenerate, and one queue per shading
 //     class (emitter / miss, dielectric, metal, diffuse, diffuse behind an instance chain);
-//   * each iteration the warp takes up to 32 entries (extend: 32 x VKQ_K, K rays per lane through the flat
+//   * each iteration the warp takes up to 32 entries (extend: 32 x K, K rays per lane through the flat
 //     program for instruction-level parallelism) from its FULLEST queue and runs that one stage on them, so
 //     the 32 lanes execute one code path; what is left in a queue simply waits for the next entries -- no
 //     partial warps at class borders, the pool only has to be large enough that some queue is full;
@@ -29,41 +29,74 @@
 
 namespace VK_NS {
 
-#ifndef VKQ_N
-#define VKQ_N 176 // slots per warp (16 warps x (68 B x 176 + rings) = 222 KB of the SM's 227 KB; (<= VKQ_RN <= 256: ring indices are bytes)
-#endif
+// Per kernel family (measured on B200, profiles/r2_sweep_*.log):
+//   flat program, no medium   176 slots, 2 rays per lane in extend, 4 CTAs x 4 warps per SM: the extend's instruction-
+//                             level parallelism and a pool deep enough that every batch is full matter, more warps do not
+//                             (24 warps x 120 slots: 43.0 against 40.0 ms per Cornell frame; 1 / 3 rays per lane: 47.4 / 38.9)
+//   flat program with media   120 slots, 1 ray per lane, 6 CTAs per SM: the medium test is a call per ray with a Philox
+//                             block and a logf behind it -- latency, not issue -- and wants the warps (Cornell smoke, 500 spp:
+//                             26.9 ms against 30.9 with the first configuration and 36.3 for the CTA-staged kernel)
+//   BVH                       120 slots, 6 CTAs per SM (traversal is memory latency: 63.8 against 65.5 ms on the final scene,
+//                             37.6 against 48.6 on 10^6 spheres)
+// A slot is 68 B; rings hold slot indices as bytes (capacity a power of two >= slots); 16 x (68 x 176 + 7 x 256) and
+// 24 x (68 x 120 + 7 x 128) both come to 220 KB of the SM's 227 KB of shared memory.
 #ifndef VKQ_WARPS
 #define VKQ_WARPS 4
 #endif
-#ifndef VKQ_K
-#define VKQ_K 2 // rays per lane in a flat-program extend batch
+#ifndef VKQ_N_FLAT
+#define VKQ_N_FLAT 176
 #endif
-#ifndef VKQ_MINB
-#define VKQ_MINB 4
+#ifndef VKQ_RN_FLAT
+#define VKQ_RN_FLAT 256
+#endif
+#ifndef VKQ_K_FLAT
+#define VKQ_K_FLAT 2
+#endif
+#ifndef VKQ_MINB_FLAT
+#define VKQ_MINB_FLAT 4
+#endif
+#ifndef VKQ_N_MEDIA
+#define VKQ_N_MEDIA 120
+#endif
+#ifndef VKQ_RN_MEDIA
+#define VKQ_RN_MEDIA 128
+#endif
+#ifndef VKQ_K_MEDIA
+#define VKQ_K_MEDIA 1
+#endif
+#ifndef VKQ_MINB_MEDIA
+#define VKQ_MINB_MEDIA 6
+#endif
+#ifndef VKQ_N_BVH
+#define VKQ_N_BVH 120
+#endif
+#ifndef VKQ_RN_BVH
+#define VKQ_RN_BVH 128
+#endif
+#ifndef VKQ_MINB_BVH
+#define VKQ_MINB_BVH 6
 #endif
 #ifndef VKQ_REGEN_MIN
 #define VKQ_REGEN_MIN 16u // ended lanes of a shade batch are regenerated at once when at least this many ended
 #endif
-#ifndef VKQ_RN
-#define VKQ_RN 256 // ring capacity: a power of two >= VKQ_N
-#endif
-#define VKQ_RMASK (VKQ_RN - 1u)
 #define VKQ_CHUNK 256u
 enum { VKQ_EXT = 0, VKQ_END = 1, VKQ_EMIT = 2, VKQ_DIEL = 3, VKQ_METAL = 4, VKQ_DIFF = 5, VKQ_DIFFI = 6, VKQ_NQ = 7, VKQ_NONE = 8 };
 
+template <int N_, int RN_>
 struct WqWarp {
-    float4 ro[VKQ_N];            // origin.xyz, time
-    float4 rd[VKQ_N];            // direction.xyz, bits: depth of the segment to trace
-    float4 bt[VKQ_N];            // path weight.xyz, bits: global sample index
-    uint4 hp[VKQ_N];             // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; -
-    uint32_t px[VKQ_N];          // pixel of the slot's sample
-    uint8_t ring[VKQ_NQ][VKQ_RN]; // slot indices, one ring per queue
+    static constexpr uint32_t N = N_, RMASK = RN_ - 1;
+    static_assert((RN_ & (RN_ - 1)) == 0 && RN_ >= N_ && RN_ <= 256, "ring capacity: power of two, >= slots, byte indices");
+    float4 ro[N_];            // origin.xyz, time
+    float4 rd[N_];            // direction.xyz, bits: depth of the segment to trace
+    float4 bt[N_];            // path weight.xyz, bits: global sample index
+    uint4 hp[N_];             // hit: t bits, primitive, instance index | face << 28 | has-instance << 31; flat hit entry
+    uint32_t px[N_];          // pixel of the slot's sample
+    uint8_t ring[VKQ_NQ][RN_]; // slot indices, one ring per queue
     uint2 ct[8];                 // per queue: .x = entries, .y = ring write position
     uint32_t cur_s, cur_y, cur_x, left; // unit cursor: next unit is (sample cur_s, row cur_y, column cur_x); `left` units remain in the chunk
     uint32_t exhausted;          // the global unit counter has run past the end
 };
 
-static_assert((VKQ_RN & (VKQ_RN - 1)) == 0 && VKQ_RN >= VKQ_N && VKQ_RN <= 256, "ring capacity: power of two, >= slots, byte indices");
 
 // A barrier of the warp with itself (named barrier 1 + warp index, 32 threads).  Functionally a __syncwarp; what it buys
 // is in the compiler: ptxas only uses the uniform datapath (uniform loop counters, LDCU constant loads, BRA.U) in code
@@ -78,12 +111,11 @@ VKD void wq_converge() {
     asm volatile("barrier.sync.aligned %0, 32;" ::"r"((threadIdx.x >> 5) + 1u) : "memory");
 #endif
 }
-static_assert(VKQ_WARPS <= 15, "one named barrier per warp of the CTA");
-
+template <class W>
 struct WqCtx {
     const DCamera& cam;
     const RenderArgs& a;
-    WqWarp& S;
+    W& S;
     uint32_t n_pixels;
     unsigned long long n_units;
     unsigned long long* unit_head;
@@ -92,7 +124,8 @@ struct WqCtx {
 
 // Append the lanes with cls != VKQ_NONE to the queue of their class: one match groups the lanes, the first
 // lane of each group moves that queue's counters (no other lane touches them: different groups, different queues).
-VKD void wq_push(WqWarp& S, uint32_t cls, uint32_t slot, uint32_t lane, uint32_t below) {
+template <class W>
+VKD void wq_push(W& S, uint32_t cls, uint32_t slot, uint32_t lane, uint32_t below) {
     const uint32_t m = __match_any_sync(0xFFFFFFFFu, cls);
     const uint32_t leader = __ffs(m) - 1u;
     uint32_t pos = 0;
@@ -102,14 +135,15 @@ VKD void wq_push(WqWarp& S, uint32_t cls, uint32_t slot, uint32_t lane, uint32_t
         S.ct[cls] = make_uint2(c.x + (uint32_t)__popc(m), c.y + (uint32_t)__popc(m));
     }
     pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-    if (cls != VKQ_NONE) S.ring[cls][(pos + __popc(m & below)) & VKQ_RMASK] = (uint8_t)slot;
+    if (cls != VKQ_NONE) S.ring[cls][(pos + __popc(m & below)) & W::RMASK] = (uint8_t)slot;
     __syncwarp();
 }
 
 // The lanes with want == true take the warp's next units and start their camera ray (src/main.rs:187-190).
 // Returns whether this lane got one (false: the frame has no unit left, the slot retires).
-VKD bool wq_regen(const WqCtx& C, bool want, uint32_t slot) {
-    WqWarp& S = C.S;
+template <class W>
+VKD bool wq_regen(const WqCtx<W>& C, bool want, uint32_t slot) {
+    W& S = C.S;
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
     if (m == 0u) return false;
     const uint32_t need = (uint32_t)__popc(m), rank = (uint32_t)__popc(m & C.below);
@@ -213,7 +247,8 @@ VKD uint32_t wq_class_of(const DScene& sc, uint32_t prim, uint32_t inst) {
 struct WqCounts {
     uint4 c01, c23, c45, c67; // EXT END | EMIT DIEL | METAL DIFF | DIFFI -
 };
-VKD WqCounts wq_counts(const WqWarp& S) {
+template <class W>
+VKD WqCounts wq_counts(const W& S) {
     WqCounts c;
     c.c01 = *reinterpret_cast<const uint4*>(&S.ct[0]);
     c.c23 = *reinterpret_cast<const uint4*>(&S.ct[2]);
@@ -223,7 +258,8 @@ VKD WqCounts wq_counts(const WqWarp& S) {
 }
 // The fullest queue: score = entries / batch width (EXT batches are ext_cap wide, the others 32; ext_cap == 0 leaves
 // the extend queue out).  Returns false when every considered queue is empty.  One max chain over (score << 3 | queue).
-VKD bool wq_pick(const WqWarp& S, const WqCounts& c, uint32_t ext_cap, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
+template <class W>
+VKD bool wq_pick(const W& S, const WqCounts& c, uint32_t ext_cap, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
     const uint32_t w = (ext_cap ? ext_cap : 32u) * 8u;
     uint32_t key = ext_cap ? c.c01.x * 256u + VKQ_EXT : 0u; // entries * 32 * 8 | queue
     key = max(key, c.c23.x * w + VKQ_EMIT);
@@ -243,13 +279,14 @@ VKD bool wq_pick(const WqWarp& S, const WqCounts& c, uint32_t ext_cap, uint32_t&
     return (key >> 3) != 0u;
 }
 // Take up to `cap` entries off queue q: returns how many, and the ring position of the first.
-VKD uint32_t wq_pop(WqWarp& S, uint32_t q, uint32_t n_q, uint32_t tail_q, uint32_t cap, uint32_t lane, uint32_t& head) {
+template <class W>
+VKD uint32_t wq_pop(W& S, uint32_t q, uint32_t n_q, uint32_t tail_q, uint32_t cap, uint32_t lane, uint32_t& head) {
     const uint32_t n = min(n_q, cap);
     head = tail_q - n_q;
     __syncwarp();
     if (lane == 0) S.ct[q].x = n_q - n;
     __syncwarp();
-    // (the entries [head, head + n) stay readable: pushes only write at the ring's tail, and a ring holds VKQ_RN >= VKQ_N entries)
+    // (the entries [head, head + n) stay readable: pushes only write at the ring's tail, and a ring holds at least as many entries as the warp has slots)
     return n;
 }
 
@@ -259,15 +296,15 @@ VKD uint32_t wq_pop(WqWarp& S, uint32_t q, uint32_t n_q, uint32_t tail_q, uint32
 // (DScene::flat_shade, decided at upload) skips resolve_hit's walk down and up the wrapper chain: p = o + t d in the
 // world frame, normal = the entry's constant world normal turned against the ray.
 #ifndef VKQ_FAST_RESOLVE
-#define VKQ_FAST_RESOLVE 0
+#define VKQ_FAST_RESOLVE 1 // (Cornell, 1000 spp: 37.9 against 40.0 ms per frame)
 #endif
-template <bool LEGACY, bool FLAT>
-VKD void wq_shade_batch(const DScene& sc, const WqCtx& C, const RenderBuffers& buf, uint32_t q, uint32_t n, uint32_t head, uint32_t& n_drop) {
-    WqWarp& S = C.S;
+template <bool LEGACY, bool FLAT, class W>
+VKD void wq_shade_batch(const DScene& sc, const WqCtx<W>& C, const RenderBuffers& buf, uint32_t q, uint32_t n, uint32_t head, uint32_t& n_drop) {
+    W& S = C.S;
     const RenderArgs& a = C.a;
     const uint32_t lane = C.lane;
     const bool act = lane < n;
-    const uint32_t slot = S.ring[q][(head + (act ? lane : 0u)) & VKQ_RMASK];
+    const uint32_t slot = S.ring[q][(head + (act ? lane : 0u)) & W::RMASK];
     bool alive = false, ended = false;
     if (q != VKQ_END) {
         if (act) {
@@ -344,8 +381,8 @@ VKD void wq_shade_batch(const DScene& sc, const WqCtx& C, const RenderBuffers& b
     // survivors (and regenerated samples) to the extend queue, queued regenerations to theirs: two ballots
     const uint32_t m_ext = __ballot_sync(0xFFFFFFFFu, alive), m_q = __ballot_sync(0xFFFFFFFFu, to_end);
     const uint2 c_ext = S.ct[VKQ_EXT], c_end = S.ct[VKQ_END];
-    if (alive) S.ring[VKQ_EXT][(c_ext.y + __popc(m_ext & C.below)) & VKQ_RMASK] = (uint8_t)slot;
-    if (to_end) S.ring[VKQ_END][(c_end.y + __popc(m_q & C.below)) & VKQ_RMASK] = (uint8_t)slot;
+    if (alive) S.ring[VKQ_EXT][(c_ext.y + __popc(m_ext & C.below)) & W::RMASK] = (uint8_t)slot;
+    if (to_end) S.ring[VKQ_END][(c_end.y + __popc(m_q & C.below)) & W::RMASK] = (uint8_t)slot;
     __syncwarp();
     if (lane == 0) {
         S.ct[VKQ_EXT] = make_uint2(c_ext.x + (uint32_t)__popc(m_ext), c_ext.y + (uint32_t)__popc(m_ext));
@@ -354,9 +391,10 @@ VKD void wq_shade_batch(const DScene& sc, const WqCtx& C, const RenderBuffers& b
     __syncwarp();
 }
 
-VKD void wq_init(WqWarp& S, uint32_t lane) { // every slot starts in the regeneration queue
+template <class W>
+VKD void wq_init(W& S, uint32_t lane) { // every slot starts in the regeneration queue
     if (lane < 8) S.ct[lane] = make_uint2(0u, 0u);
-    for (uint32_t i = lane; i < VKQ_N; i += 32u) S.ring[VKQ_END][i] = (uint8_t)i;
+    for (uint32_t i = lane; i < W::N; i += 32u) S.ring[VKQ_END][i] = (uint8_t)i;
     if (lane == 0) {
         S.left = 0u;
         S.exhausted = 0u;
@@ -365,7 +403,7 @@ VKD void wq_init(WqWarp& S, uint32_t lane) { // every slot starts in the regener
         S.cur_x = 0u;
     }
     __syncwarp();
-    if (lane == 0) S.ct[VKQ_END] = make_uint2(VKQ_N, VKQ_N);
+    if (lane == 0) S.ct[VKQ_END] = make_uint2(W::N, W::N);
     __syncwarp();
 }
 VKD void wq_flush_counters(const RenderBuffers& buf, uint32_t lane, uint32_t n_rays, uint32_t n_drop, uint32_t n_nodes, uint32_t n_prims) {
@@ -386,15 +424,15 @@ VKD void wq_flush_counters(const RenderBuffers& buf, uint32_t lane, uint32_t n_r
 }
 
 // ---- flat scenes: extend = K rays per lane through the flat program, one queue batch at a time ----------------------
-template <bool MEDIA, bool LEGACY>
+template <bool MEDIA, bool LEGACY, class W, int K>
 VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
                          unsigned long long* unit_head) {
     extern __shared__ __align__(16) unsigned char vkq_raw[];
     const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-    WqWarp& S = reinterpret_cast<WqWarp*>(vkq_raw)[threadIdx.x >> 5];
-    const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
+    W& S = reinterpret_cast<W*>(vkq_raw)[threadIdx.x >> 5];
+    const WqCtx<W> C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
     uint32_t n_rays = 0, n_drop = 0, n_prims = 0;
-    constexpr uint32_t EXT_CAP = 32u * VKQ_K;
+    constexpr uint32_t EXT_CAP = 32u * K;
     // a miss under the constant black background of src/main.rs:124 adds nothing: the slot goes straight to regeneration
     const uint32_t miss_cls = wq_black_miss(a) ? (uint32_t)VKQ_END : (uint32_t)VKQ_EMIT;
     wq_init(S, lane);
@@ -409,16 +447,16 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
         }
         // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------------
         wq_converge();
-        float3 o[VKQ_K], d[VKQ_K];
-        float tm[VKQ_K], best_t[VKQ_K];
-        bool live[VKQ_K];
-        uint32_t best_hit[VKQ_K], slot[VKQ_K];
-        MediumXi xi[VKQ_K];
+        float3 o[K], d[K];
+        float tm[K], best_t[K];
+        bool live[K];
+        uint32_t best_hit[K], slot[K];
+        MediumXi xi[K];
 #pragma unroll
-        for (int k = 0; k < VKQ_K; ++k) {
+        for (int k = 0; k < K; ++k) {
             const uint32_t e = lane + 32u * k;
             live[k] = e < n;
-            slot[k] = S.ring[VKQ_EXT][(head + (live[k] ? e : 0u)) & VKQ_RMASK];
+            slot[k] = S.ring[VKQ_EXT][(head + (live[k] ? e : 0u)) & W::RMASK];
             const float4 ro = S.ro[slot[k]], rd = S.rd[slot[k]];
             o[k] = f3(ro);
             d[k] = f3(rd);
@@ -429,9 +467,9 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
             xi[k].rng.pixel = MEDIA ? S.px[slot[k]] : 0u;
             xi[k].rng.sample = MEDIA ? __float_as_uint(S.bt[slot[k]].w) : 0u;
         }
-        trace_flat_k<VKQ_K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit);
+        trace_flat_k<K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit);
 #pragma unroll
-        for (int k = 0; k < VKQ_K; ++k) {
+        for (int k = 0; k < K; ++k) {
             uint32_t cls = VKQ_NONE;
             if (live[k]) {
                 ++n_rays;
@@ -469,12 +507,12 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
 #ifndef VKQ_NODE_STEPS
 #define VKQ_NODE_STEPS 4
 #endif
-template <bool MEDIA, bool LEGACY>
+template <bool MEDIA, bool LEGACY, class W>
 VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf, unsigned long long* unit_head) {
     extern __shared__ __align__(16) unsigned char vkq_raw[];
     const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-    WqWarp& S = reinterpret_cast<WqWarp*>(vkq_raw)[threadIdx.x >> 5];
-    const WqCtx C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
+    W& S = reinterpret_cast<W*>(vkq_raw)[threadIdx.x >> 5];
+    const WqCtx<W> C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
     uint32_t n_rays = 0, n_drop = 0;
     TraceCounters tc = {0u, 0u};
     const uint32_t miss_cls = wq_black_miss(a) ? (uint32_t)VKQ_END : (uint32_t)VKQ_EMIT;
@@ -525,7 +563,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
                 const uint32_t take = wq_pop(S, VKQ_EXT, n_ext, cnt.c01.y, (uint32_t)__popc(m_done), lane, head);
                 const uint32_t rank = (uint32_t)__popc(m_done & below);
                 if (done_lane && rank < take) {
-                    cur = S.ring[VKQ_EXT][(head + rank) & VKQ_RMASK];
+                    cur = S.ring[VKQ_EXT][(head + rank) & W::RMASK];
                     const float4 ro = S.ro[cur], rd = S.rd[cur];
                     o = f3(ro);
                     d = f3(rd);
@@ -559,19 +597,29 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
     wq_flush_counters(buf, lane, n_rays, n_drop, tc.nodes, tc.prims);
 }
 
+using WqFlat = WqWarp<VKQ_N_FLAT, VKQ_RN_FLAT>;
+using WqMedia = WqWarp<VKQ_N_MEDIA, VKQ_RN_MEDIA>;
+using WqBvh = WqWarp<VKQ_N_BVH, VKQ_RN_BVH>;
+static_assert(VKQ_WARPS <= 15, "one named barrier per warp of the CTA");
+
 template <bool MEDIA, bool LEGACY>
-__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB) k_warpq(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
-                                                                unsigned long long* unit_head) {
-    warpq_bvh_body<MEDIA, LEGACY>(sc, cam, a, buf, unit_head);
+__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB_BVH) k_warpq(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
+                                                                    unsigned long long* unit_head) {
+    warpq_bvh_body<MEDIA, LEGACY, WqBvh>(sc, cam, a, buf, unit_head);
 }
-template <bool MEDIA, bool LEGACY>
-__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB) k_warpq_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
-                                                                     const RenderArgs a, const RenderBuffers buf, unsigned long long* unit_head) {
-    warpq_flat_body<MEDIA, LEGACY>(sc, &flat, cam, a, buf, unit_head);
+template <bool LEGACY>
+__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB_FLAT) k_warpq_flat(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
+                                                                          const RenderArgs a, const RenderBuffers buf, unsigned long long* unit_head) {
+    warpq_flat_body<false, LEGACY, WqFlat, VKQ_K_FLAT>(sc, &flat, cam, a, buf, unit_head);
+}
+template <bool LEGACY>
+__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB_MEDIA) k_warpq_flat_media(const DScene sc, const __grid_constant__ FlatProgram flat,
+                                                                                 const DCamera cam, const RenderArgs a, const RenderBuffers buf,
+                                                                                 unsigned long long* unit_head) {
+    warpq_flat_body<true, LEGACY, WqMedia, VKQ_K_MEDIA>(sc, &flat, cam, a, buf, unit_head);
 }
 
-template <class K> static cudaError_t warpq_prepare(K kernel, int* blocks_per_sm) {
-    const size_t smem = VKQ_WARPS * sizeof(WqWarp);
+template <class K> static cudaError_t warpq_prepare(K kernel, size_t smem, int* blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, 32 * VKQ_WARPS, smem);
@@ -582,25 +630,26 @@ cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamer
                          unsigned long long* unit_head, int sm_count, bool legacy, cudaStream_t st) {
     int bps = 0;
     cudaError_t e;
-    const size_t smem = VKQ_WARPS * sizeof(WqWarp);
     const bool media = sc.has_media != 0u;
-#define VKQ_LAUNCH_FLAT(M, G)                                                                                          \
+#define VKQ_LAUNCH_FLAT(KERNEL, WARP)                                                                                  \
     {                                                                                                                  \
-        if ((e = warpq_prepare(k_warpq_flat<M, G>, &bps)) != cudaSuccess) return e;                                    \
-        k_warpq_flat<M, G><<<sm_count * (bps < 1 ? 1 : bps), 32 * VKQ_WARPS, smem, st>>>(sc, *flat, cam, a, b, unit_head); \
+        const size_t smem = VKQ_WARPS * sizeof(WARP);                                                                  \
+        if ((e = warpq_prepare(KERNEL, smem, &bps)) != cudaSuccess) return e;                                          \
+        KERNEL<<<sm_count * (bps < 1 ? 1 : bps), 32 * VKQ_WARPS, smem, st>>>(sc, *flat, cam, a, b, unit_head);          \
     }
 #define VKQ_LAUNCH_BVH(M, G)                                                                                           \
     {                                                                                                                  \
-        if ((e = warpq_prepare(k_warpq<M, G>, &bps)) != cudaSuccess) return e;                                         \
+        const size_t smem = VKQ_WARPS * sizeof(WqBvh);                                                                 \
+        if ((e = warpq_prepare(k_warpq<M, G>, smem, &bps)) != cudaSuccess) return e;                                   \
         k_warpq<M, G><<<sm_count * (bps < 1 ? 1 : bps), 32 * VKQ_WARPS, smem, st>>>(sc, cam, a, b, unit_head);          \
     }
 #if VK_SIMPLE
     (void)legacy; // the trimmed build exists for the HEAD integrator on flat scenes only
-    if (media) VKQ_LAUNCH_FLAT(true, false) else VKQ_LAUNCH_FLAT(false, false)
+    if (media) VKQ_LAUNCH_FLAT(k_warpq_flat_media<false>, WqMedia) else VKQ_LAUNCH_FLAT(k_warpq_flat<false>, WqFlat)
 #else
     if (flat && flat->n) {
-        if (media) { if (legacy) VKQ_LAUNCH_FLAT(true, true) else VKQ_LAUNCH_FLAT(true, false) }
-        else { if (legacy) VKQ_LAUNCH_FLAT(false, true) else VKQ_LAUNCH_FLAT(false, false) }
+        if (media) { if (legacy) VKQ_LAUNCH_FLAT(k_warpq_flat_media<true>, WqMedia) else VKQ_LAUNCH_FLAT(k_warpq_flat_media<false>, WqMedia) }
+        else { if (legacy) VKQ_LAUNCH_FLAT(k_warpq_flat<true>, WqFlat) else VKQ_LAUNCH_FLAT(k_warpq_flat<false>, WqFlat) }
     } else {
         if (media) { if (legacy) VKQ_LAUNCH_BVH(true, true) else VKQ_LAUNCH_BVH(true, false) }
         else { if (legacy) VKQ_LAUNCH_BVH(false, true) else VKQ_LAUNCH_BVH(false, false) }
