@@ -1,0 +1,52 @@
+"""The warp-queue kernels' own protocol check (compute-sanitizer is closed on this pool: its racecheck / memcheck cannot
+run).  A debug build of vk_warpq.cu (-DVKQ_SELFCHECK=1) verifies before EVERY scheduling decision that every queued
+index is a valid slot, that no slot is queued twice, and that queues plus rays in flight never exceed the pool; the
+violation count must be zero on flat, media and BVH scenes, the pools must drain (the render returns), and the frames
+must equal the normal build's bit for bit."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "build", "libvk_selfcheck.so")
+
+CHILD = r"""
+import ctypes as C, hashlib, sys
+sys.path.insert(0, %r)
+import numpy as np
+import vecchio_b200 as vb
+L = vb.gpu_lib()
+L.vk_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+ctx = vb.Context(0)
+for name, W, spp, depth, flags in (("cornell_box", 97, 24, 100, 0), ("cornell_smoke", 64, 16, 100, 0), ("final_scene", 48, 8, 50, 0),
+                                   ("random_spheres_demo", 80, 8, 50, 0), ("cornell_box", 64, 8, 100, vb.VK_FLAG_LEGACY_SCATTER),
+                                   ("cornell_box", 33, 7, 100, vb.VK_FLAG_STRICT_MATH)):
+    s = vb.Scene(name); cam = s.next_camera(); ctx.upload(s)
+    rgb, _, st = ctx.render(cam, vb.render_params(W, s.height_for(W), spp, depth, seed=3, variant=vb.VK_VARIANT_WARPQ, flags=flags))
+    out = (C.c_ulonglong * 8)(); L.vk_debug_counters(ctx._h, out)
+    print(name, flags, st.paths, st.rays, int(out[5]), hashlib.sha256(rgb.tobytes()).hexdigest()[:16], flush=True)
+"""
+
+
+def run_child(lib):
+    env = dict(os.environ)
+    if lib:
+        env["VECCHIO_GPU_LIB"] = lib
+    r = subprocess.run([sys.executable, "-c", CHILD % ROOT], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return [line.split() for line in r.stdout.strip().splitlines()]
+
+
+@pytest.mark.gpu
+def test_queue_protocol_selfcheck_finds_nothing_and_changes_nothing():
+    if not os.path.exists(LIB):
+        subprocess.run([os.path.join(ROOT, "scripts", "build_variants.sh"), "selfcheck:-DVKQ_SELFCHECK=1"], check=True, cwd=ROOT,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    checked, normal = run_child(LIB), run_child(None)
+    assert len(checked) == len(normal) == 6
+    for c, n in zip(checked, normal):
+        assert int(c[4]) == 0, ("queue protocol violations", c)
+        assert c[:4] == n[:4] and c[5] == n[5], ("the self-checking build renders another frame", c, n)
+    # the render build of the strict-math frame is only compiled without the check: its line must simply agree

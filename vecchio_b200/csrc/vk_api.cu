@@ -519,6 +519,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     if (legacy && variant != VK_VARIANT_WARPQ) variant = VK_VARIANT_MEGAKERNEL; // legacy integrator: lane megakernel and warp queues
     if (variant == VK_VARIANT_WARPQ) {
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
+        CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(unsigned long long), c->stream)); // self-check violations (debug builds)
         // (the K-ray flat trace has no subtree entries: a hybrid program means the BVH path)
         const FlatProgram* sflat = flat && flat->n_bvh == 0 ? flat : nullptr;
         const bool simple = !strict && !legacy && sflat && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");

@@ -391,6 +391,47 @@ VKD void wq_shade_batch(const DScene& sc, const WqCtx<W>& C, const RenderBuffers
     __syncwarp();
 }
 
+// VKQ_SELFCHECK (debug builds only: scripts/build_variants.sh selfcheck:-DVKQ_SELFCHECK=1, tests/test_zz_warpq_selfcheck_gpu.py).
+// compute-sanitizer is closed on this pool, so the queue protocol is checked by the kernel itself, before every scheduling
+// decision: every queued index is a valid slot, no slot sits in two queues (or twice in one), and the queues together never
+// hold more entries than the warp has slots.  Violations are counted in counters[5]; the test asserts the count is zero
+// and that the frame equals the normal build's bit for bit.
+#ifndef VKQ_SELFCHECK
+#define VKQ_SELFCHECK 0
+#endif
+template <class W>
+VKD void wq_selfcheck(const W& S, const RenderBuffers& buf, uint32_t lane, uint32_t in_flight) {
+#if VKQ_SELFCHECK
+    uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // 256 slots, one bit each, OR-reduced over the warp per queue entry
+    uint32_t bad = 0, total = 0;
+    for (uint32_t q = 0; q < VKQ_NQ; ++q) {
+        const uint2 c = S.ct[q];
+        total += c.x;
+        if (c.x > W::N) ++bad;
+        for (uint32_t i0 = 0; i0 < c.x; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            const bool have = i < c.x;
+            const uint32_t slot = have ? S.ring[q][(c.y - c.x + i) & W::RMASK] : 0u;
+            if (have && slot >= W::N) ++bad;
+            // a slot twice inside this group of 32: two lanes with the same value
+            const uint32_t same = __match_any_sync(0xFFFFFFFFu, have ? slot : 0x10000u + lane);
+            if (have && __popc(same) != 1) ++bad;
+#pragma unroll
+            for (uint32_t w = 0; w < 8; ++w) {
+                const uint32_t mine = (have && (slot >> 5) == w) ? (1u << (slot & 31u)) : 0u;
+                const uint32_t all = __reduce_or_sync(0xFFFFFFFFu, mine);
+                if (mine & seen[w]) ++bad; // already queued (an earlier group or an earlier queue)
+                seen[w] |= all;
+            }
+        }
+    }
+    if (total + in_flight > W::N) ++bad;
+    if (bad) atomicAdd(&buf.counters[5], (unsigned long long)bad);
+#else
+    (void)S, (void)buf, (void)lane, (void)in_flight;
+#endif
+}
+
 template <class W>
 VKD void wq_init(W& S, uint32_t lane) { // every slot starts in the regeneration queue
     if (lane < 8) S.ct[lane] = make_uint2(0u, 0u);
@@ -439,6 +480,7 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
 #pragma unroll 1
     for (;;) {
         uint32_t q, n_q, tail_q, head;
+        wq_selfcheck(S, buf, lane, 0u);
         if (!wq_pick(S, wq_counts(S), EXT_CAP, q, n_q, tail_q)) break; // every queue is empty: all slots have retired
         const uint32_t n = wq_pop(S, q, n_q, tail_q, q == VKQ_EXT ? EXT_CAP : 32u, lane, head);
         if (q != VKQ_EXT) {
@@ -556,6 +598,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
                 }
                 wq_push(S, cls, slot, lane, below);
             }
+            wq_selfcheck(S, buf, lane, (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, cur != 0xFFFFFFFFu)));
             const WqCounts cnt = wq_counts(S);
             const uint32_t n_ext = __reduce_max_sync(0xFFFFFFFFu, cnt.c01.x); // (provably uniform, see wq_pick)
             if (n_ext != 0u) { // fetch: the idle lanes take the next rays of the extend queue
