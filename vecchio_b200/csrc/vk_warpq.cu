@@ -665,9 +665,15 @@ __global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB_MEDIA) k_warpq_flat_m
 template <class K> static cudaError_t warpq_prepare(K kernel, size_t smem, int* blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    // ask for the largest shared-memory carveout: the occupancy calculator assumes it, the launch does not by itself
-    // (measured: the 6-CTA configurations ran with 4 resident CTAs, `sm__warps_active` 25 % instead of 37.5 %)
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    // The occupancy calculator assumes the largest shared-memory carveout, the launch does not ask for it by itself
+    // (measured: the 6-CTA configurations ran with 4 resident CTAs).  Ask for exactly what the resident CTAs need and no
+    // more: whatever the carveout leaves of the SM's 228 KB is L1, and the BVH kernels' node fetches want it.
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, 32 * VKQ_WARPS, smem);
+    if (e != cudaSuccess) return e;
+    const size_t need = (size_t)(*blocks_per_sm < 1 ? 1 : *blocks_per_sm) * (smem + 1024);
+    int pct = (int)((need * 100 + 233472 - 1) / 233472);
+    pct = pct > 100 ? 100 : pct;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, 32 * VKQ_WARPS, smem);
 }
