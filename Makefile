@@ -49,18 +49,24 @@ $(CSRC)/vk_staged_simple.o: $(CSRC)/vk_staged.cu $(KDEPS)
 $(CSRC)/vk_staged_strict.o: $(CSRC)/vk_staged.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_staged_strict.log || (cat $(CSRC)/ptxas_staged_strict.log; false)
 # the warp-queue kernels (slots, rays per lane and CTAs per SM are set per kernel family in vk_warpq.cu)
-$(CSRC)/vk_warpq_fast.o: $(CSRC)/vk_warpq.cu $(KDEPS)
+KDEPS_WQ := $(KDEPS) $(CSRC)/vk_warpq.cuh
+# the step-queue kernels for BVH scenes
+$(CSRC)/vk_stepq_fast.o: $(CSRC)/vk_stepq.cu $(KDEPS_WQ)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_stepq_fast.log || (cat $(CSRC)/ptxas_stepq_fast.log; false)
+$(CSRC)/vk_stepq_strict.o: $(CSRC)/vk_stepq.cu $(KDEPS_WQ)
+	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_stepq_strict.log || (cat $(CSRC)/ptxas_stepq_strict.log; false)
+$(CSRC)/vk_warpq_fast.o: $(CSRC)/vk_warpq.cu $(KDEPS_WQ)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_warpq_fast.log || (cat $(CSRC)/ptxas_warpq_fast.log; false)
-$(CSRC)/vk_warpq_simple.o: $(CSRC)/vk_warpq.cu $(KDEPS)
+$(CSRC)/vk_warpq_simple.o: $(CSRC)/vk_warpq.cu $(KDEPS_WQ)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVK_SIMPLE=1 $(WQ_SIMPLE) -c -o $@ $< 2> $(CSRC)/ptxas_warpq_simple.log || (cat $(CSRC)/ptxas_warpq_simple.log; false)
-$(CSRC)/vk_warpq_strict.o: $(CSRC)/vk_warpq.cu $(KDEPS)
+$(CSRC)/vk_warpq_strict.o: $(CSRC)/vk_warpq.cu $(KDEPS_WQ)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_warpq_strict.log || (cat $(CSRC)/ptxas_warpq_strict.log; false)
 $(CSRC)/vk_api.o: $(CSRC)/vk_api.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 $(CSRC)/vk_relayout.o: $(CSRC)/vk_relayout.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o $(CSRC)/vk_warpq_fast.o $(CSRC)/vk_warpq_strict.o $(CSRC)/vk_warpq_simple.o
+$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o $(CSRC)/vk_warpq_fast.o $(CSRC)/vk_warpq_strict.o $(CSRC)/vk_warpq_simple.o $(CSRC)/vk_stepq_fast.o $(CSRC)/vk_stepq_strict.o
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 

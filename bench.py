@@ -105,14 +105,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-VARIANT_NAMES = {1: "megakernel", 2: "wavefront", 3: "staged", 4: "warpq"}
+VARIANT_NAMES = {1: "megakernel", 2: "wavefront", 3: "staged", 4: "warpq", 5: "stepq"}
 
 
 def kernel_of(kst, scene):
     flat_program = kst.node_visits == 0  # the flat traversal program visits no BVH node
     return {1: "k_megakernel_flat" if flat_program else ("k_megakernel_dyn" if scene.desc.n_nodes >= 65536 else "k_megakernel"),
             2: "k_wf_extend + k_wf_shade", 3: "k_staged_flat" if flat_program else "k_staged",
-            4: "k_warpq_flat" if flat_program else "k_warpq"}.get(kst.variant, "?")
+            4: "k_warpq_flat" if flat_program else "k_warpq", 5: "k_stepq"}.get(kst.variant, "?")
 
 
 def make_roofline(config, variant_name, kernel_name, aw, k_rays, k_ms, fp32_peak, l2_gbs, peaks, scene_bytes):

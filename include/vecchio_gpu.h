@@ -203,8 +203,11 @@ typedef struct vk_camera {
  * (persistent threads, path regeneration); WAVEFRONT = generate / extend / shade as separate kernels
  * over a slot pool in device memory; STAGED = the persistent megakernel with the wavefront's stages
  * and material sort inside each CTA (slot pool in shared memory); WARPQ = the same stages inside each
- * WARP: per-warp slot pool and per-class queues in shared memory, no barrier anywhere. */
-enum { VK_VARIANT_AUTO = 0, VK_VARIANT_MEGAKERNEL = 1, VK_VARIANT_WAVEFRONT = 2, VK_VARIANT_STAGED = 3, VK_VARIANT_WARPQ = 4 };
+ * WARP: per-warp slot pool and per-class queues in shared memory, no barrier anywhere; STEPQ = warp
+ * queues for BVH scenes with the traversal itself cut into queued steps (node visit / sphere / box /
+ * other leaves), traversal state in shared memory (a flat-program scene runs WARPQ). */
+enum { VK_VARIANT_AUTO = 0, VK_VARIANT_MEGAKERNEL = 1, VK_VARIANT_WAVEFRONT = 2, VK_VARIANT_STAGED = 3, VK_VARIANT_WARPQ = 4,
+       VK_VARIANT_STEPQ = 5 };
 enum {
     VK_FLAG_STRICT_MATH = 1u, /* no FMA contraction, IEEE div/sqrt, division slab test:
                                  the op sequence of the reference, for hit parity    */

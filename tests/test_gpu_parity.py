@@ -462,10 +462,10 @@ def test_full_size_cornell_properties(vb, ctx):
 # Wavefront variant (generate -> extend -> material-sorted shade -> accumulate as separate kernels)
 # ---------------------------------------------------------------------------------------------------
 WF_SCENES = [("cornell_box", 0, 96, 64, 100), ("cornell_smoke", 0, 64, 64, 100), ("final_scene", 0, 64, 32, 100),
-             ("random_spheres_demo", 0, 96, 32, 50), ("bowser_demo", 0, 64, 32, 50)]
+             ("random_spheres_demo", 0, 96, 32, 50), ("bowser_demo", 0, 64, 32, 50), ("stress_spheres", 40, 96, 8, 50)]
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4], ids=["wavefront", "staged", "warpq"])
+@pytest.mark.parametrize("variant", [2, 3, 4, 5], ids=["wavefront", "staged", "warpq", "stepq"])
 @pytest.mark.parametrize("name,param,W,spp,depth", WF_SCENES, ids=[s[0] for s in WF_SCENES])
 def test_variants_equal_megakernel(vb, ctx, name, param, W, spp, depth, variant):
     """Every variant keys Philox by (pixel, global sample, bounce) and adds a finished sample to its pixel's
@@ -481,7 +481,9 @@ def test_variants_equal_megakernel(vb, ctx, name, param, W, spp, depth, variant)
         pw = vb.render_params(W, H, spp, depth, seed=31, variant=variant, flags=flags)
         a, qa, sa = ctx.render(cam, pm, want_sumsq=True)
         b, qb, sb = ctx.render(cam, pw, want_sumsq=True)
-        assert sb.variant == variant and sa.variant == vb.VK_VARIANT_MEGAKERNEL
+        # (step queues are the BVH traversal: on a flat-program scene the request runs the flat warp-queue kernel)
+        ran = vb.VK_VARIANT_WARPQ if (variant == vb.VK_VARIANT_STEPQ and sb.node_visits == 0) else variant
+        assert sb.variant == ran and sa.variant == vb.VK_VARIANT_MEGAKERNEL
         assert (sb.launches > 3 or variant != vb.VK_VARIANT_WAVEFRONT) and sa.paths == sb.paths
         if exact:
             assert np.array_equal(a, b) and np.allclose(qa, qb, rtol=1e-6, atol=0), (name, np.abs(a - b).max())
@@ -553,7 +555,7 @@ def test_rgb8_frame_is_to_color_of_the_float_frame(vb, ctx):
 LEGACY_CASES = [("random_spheres_cover", 96, 128, 50, True), ("cornell_box", 64, 512, 50, False), ("final_scene", 48, 128, 50, False)]
 
 
-@pytest.mark.parametrize("variant", [1, 4], ids=["megakernel", "warpq"])
+@pytest.mark.parametrize("variant", [1, 4, 5], ids=["megakernel", "warpq", "stepq"])
 @pytest.mark.parametrize("name,W,spp,depth,sky", LEGACY_CASES, ids=[c[0] for c in LEGACY_CASES])
 def test_legacy_integrator_image_parity(vb, po, ctx, name, W, spp, depth, sky, variant):
     """The legacy integrator runs in the lane megakernel and in the warp-queue kernel (flat program and BVH)."""
@@ -564,7 +566,7 @@ def test_legacy_integrator_image_parity(vb, po, ctx, name, W, spp, depth, sky, v
     flags = vb.VK_FLAG_LEGACY_SCATTER | (vb.VK_FLAG_SKY_BACKGROUND if sky else 0)
     ro, qo, so = o.render(cam, vb.render_params(W, H, spp, depth, seed=51, flags=flags), want_sumsq=True)
     rg, qg, sg = ctx.render(cam, vb.render_params(W, H, spp, depth, seed=52, flags=flags, variant=variant), want_sumsq=True)
-    assert sg.variant == variant and np.isfinite(rg).all()
+    assert sg.variant == (vb.VK_VARIANT_WARPQ if (variant == vb.VK_VARIANT_STEPQ and sg.node_visits == 0) else variant) and np.isfinite(rg).all()
     assert abs(sg.rays / sg.paths - so.rays / so.paths) <= 0.02 * so.rays / so.paths, (sg.rays / sg.paths, so.rays / so.paths)
     z, nz, diff, se = zscores(rg, qg, spp, ro, qo, spp)
     frac = (np.abs(z[nz]) <= 3.0).mean()

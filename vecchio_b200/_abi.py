@@ -6,7 +6,7 @@ VK_OK = 0
 VK_ERR_INVALID, VK_ERR_NO_DEVICE, VK_ERR_CUDA, VK_ERR_UNSUPPORTED, VK_ERR_NO_SCENE, VK_ERR_OOM = -1, -2, -3, -4, -5, -6
 
 VK_T_NONE, VK_T_NODE, VK_T_SPHERE, VK_T_MSPHERE, VK_T_RECT, VK_T_BOX, VK_T_XFORM, VK_T_MEDIUM = range(8)
-VK_VARIANT_AUTO, VK_VARIANT_MEGAKERNEL, VK_VARIANT_WAVEFRONT, VK_VARIANT_STAGED, VK_VARIANT_WARPQ = 0, 1, 2, 3, 4
+VK_VARIANT_AUTO, VK_VARIANT_MEGAKERNEL, VK_VARIANT_WAVEFRONT, VK_VARIANT_STAGED, VK_VARIANT_WARPQ, VK_VARIANT_STEPQ = 0, 1, 2, 3, 4, 5
 VK_FLAG_STRICT_MATH = 1
 VK_FLAG_FORCE_BVH = 2
 VK_FLAG_LEGACY_SCATTER = 4

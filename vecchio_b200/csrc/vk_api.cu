@@ -38,6 +38,9 @@ struct vk_ctx {
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
     float* partial = nullptr;               // accumulators: W*H*3 x u64 fixed-point sums | W*H*3 x double sums of squares
     size_t partial_floats = 0;
+    float* sq_stack = nullptr; // step-queue kernel: overflow of the traversal stacks (allocated on first use)
+    size_t sq_stack_floats = 0;
+    uint32_t stack_need = 0, levels_sub = 0; // of the uploaded scene (vk_scene_info)
     float* frame = nullptr; // vk_render staging: sum | sumsq | rgb
     size_t frame_floats = 0;
     float* pinned = nullptr; // pinned host staging for the D2H of vk_render
@@ -218,6 +221,7 @@ void vk_destroy(vk_ctx* c) {
     cudaSetDevice(c->device);
     free_scene(c);
     if (c->partial) cudaFree(c->partial);
+    if (c->sq_stack) cudaFree(c->sq_stack);
     if (c->wf_block) cudaFree(c->wf_block);
     if (c->wf_host_counts) cudaFreeHost(c->wf_host_counts);
     if (c->frame) cudaFree(c->frame);
@@ -310,6 +314,8 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     c->wnodes_bytes = wnodes.size() * sizeof(float4);
     c->has_specdiffuse = R.has_specdiffuse;
     c->simple_scene = R.simple;
+    c->stack_need = R.stack_need;
+    c->levels_sub = R.levels_sub;
     c->flat = R.flat;
     c->has_scene = true;
     return VK_OK;
@@ -407,6 +413,7 @@ static uint32_t choose_variant(const vk_ctx* c, const vk_render_params* P) {
     const char* e = std::getenv("VECCHIO_AUTO"); // tuning sweeps: staged | warpq | mega
     if (e && !std::strcmp(e, "staged")) return flat && c->flat.n_bvh == 0 ? (uint32_t)VK_VARIANT_STAGED : (uint32_t)VK_VARIANT_MEGAKERNEL;
     if (e && !std::strcmp(e, "warpq")) return (uint32_t)VK_VARIANT_WARPQ;
+    if (e && !std::strcmp(e, "stepq")) return flat && c->flat.n_bvh == 0 ? (uint32_t)VK_VARIANT_WARPQ : (uint32_t)VK_VARIANT_STEPQ;
     if (e && !std::strcmp(e, "mega")) return (uint32_t)VK_VARIANT_MEGAKERNEL;
     return flat && c->flat.n_bvh == 0 ? (uint32_t)VK_VARIANT_WARPQ : (uint32_t)VK_VARIANT_MEGAKERNEL;
 }
@@ -459,7 +466,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     const uint32_t count = P->spp_count ? P->spp_count : P->spp - P->spp_begin;
     if ((uint64_t)P->spp_begin + count > P->spp) return fail(c, VK_ERR_INVALID, "render: sample slice exceeds spp");
     if ((uint64_t)P->width * P->height > 0x7FFFFFFFull / 3) return fail(c, VK_ERR_INVALID, "render: image too large");
-    if (P->variant > VK_VARIANT_WARPQ) return fail(c, VK_ERR_INVALID, "render: unknown variant");
+    if (P->variant > VK_VARIANT_STEPQ) return fail(c, VK_ERR_INVALID, "render: unknown variant");
     if (!(cam->time0 < cam->time1)) return fail(c, VK_ERR_INVALID, "render: camera time0 >= time1 (gen_range panics, src/main.rs:118)");
     CU(c, cudaSetDevice(c->device));
     const bool strict = (P->flags & VK_FLAG_STRICT_MATH) != 0;
@@ -516,8 +523,23 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     const DCamera dc = to_dcam(cam);
     uint32_t launches = 0;
     uint32_t variant = choose_variant(c, P);
-    if (legacy && variant != VK_VARIANT_WARPQ) variant = VK_VARIANT_MEGAKERNEL; // legacy integrator: lane megakernel and warp queues
-    if (variant == VK_VARIANT_WARPQ) {
+    if (legacy && variant != VK_VARIANT_WARPQ && variant != VK_VARIANT_STEPQ) variant = VK_VARIANT_MEGAKERNEL; // legacy integrator: lane megakernel and warp queues
+    if (variant == VK_VARIANT_STEPQ && flat && flat->n_bvh == 0) variant = VK_VARIANT_WARPQ; // step queues are the BVH traversal; a flat program has none
+    if (variant == VK_VARIANT_STEPQ) {
+        const bool inst = c->levels_sub != 0u;
+        uint32_t glevels = 0;
+        const size_t words = strict ? vkstrict::stepq_stack_words(c->stack_need, inst, c->sm_count, &glevels)
+                                    : vkfast::stepq_stack_words(c->stack_need, inst, c->sm_count, &glevels);
+        if (words) {
+            const int rc = ensure(c, &c->sq_stack, &c->sq_stack_floats, words);
+            if (rc != VK_OK) return rc;
+        }
+        CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
+        CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(unsigned long long), c->stream)); // self-check violations (debug builds)
+        CU(c, strict ? vkstrict::launch_stepq(c->scene, dc, a, b, c->counters + 2, (uint32_t*)c->sq_stack, glevels, inst, c->sm_count, legacy, c->stream)
+                     : vkfast::launch_stepq(c->scene, dc, a, b, c->counters + 2, (uint32_t*)c->sq_stack, glevels, inst, c->sm_count, legacy, c->stream));
+        launches = 1;
+    } else if (variant == VK_VARIANT_WARPQ) {
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
         CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(unsigned long long), c->stream)); // self-check violations (debug builds)
         // (the K-ray flat trace has no subtree entries: a hybrid program means the BVH path)

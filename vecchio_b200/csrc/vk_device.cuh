@@ -452,39 +452,30 @@ VKD void trav_init(Trav& T, const DScene& sc, float3 o, float3 d, float tmax) {
 }
 VKD uint32_t trav_pop(Trav& T) { return T.sp ? T.stack[--T.sp] : VKD_DONE; }
 VKD bool trav_at_node(const Trav& T) { return T.ref != VKD_DONE && VKD_TYPE(T.ref) == VK_T_NODE; }
-// precondition: trav_at_node(T)
-VKD void trav_node_step(Trav& T, const DScene& sc, float tmin, TraceCounters& tc) {
-    const uint32_t ni = VKD_INDEX(T.ref);
-    if (T.enter) { // BVHNode::hit's own `bb.hit` for the world root / an instanced sub-BVH root
-        T.enter = false;
-        const float4 n0 = __ldg(&sc.nodes[2 * ni]), n1 = __ldg(&sc.nodes[2 * ni + 1]);
-        float te;
-        if (!aabb_hit(f3(n0), f3(n1), T.co, T.cd, T.cinv, tmin, T.best.t, te)) {
-            T.ref = trav_pop(T);
-            return;
-        }
-    }
-    ++tc.nodes;
+// One visit of a four-wide node: the four AxisBB::hit tests and the hits sorted by entry distance (r0 nearest; a missed
+// or empty slot is VK_REF_NONE and sorts last).  Shared by the lane traversal (Trav, stack in local memory) and the
+// step-queue kernel (vk_stepq.cu, stack in shared memory).
+VKD void wide_node_test(const DScene& sc, uint32_t ni, float3 co, float3 cd, float3 cinv, float tmin, float tmax, uint32_t& r0, uint32_t& r1,
+                        uint32_t& r2, uint32_t& r3) {
     const float4* w = sc.wnodes + 8u * (size_t)ni;
     const float4 mnx = __ldg(w), mxx = __ldg(w + 1), mny = __ldg(w + 2), mxy = __ldg(w + 3), mnz = __ldg(w + 4), mxz = __ldg(w + 5);
     const float4 rf = __ldg(w + 6);
-    uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
+    r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
     float t0, t1, t2, t3;
     // AxisBB::hit per slot (src/accel.rs:16-35); a missed or empty slot drops out (ref 0, t = +inf)
 #if VK_STRICT
-    if (!(r0 != VK_REF_NONE && aabb_hit(f3(mnx.x, mny.x, mnz.x), f3(mxx.x, mxy.x, mxz.x), T.co, T.cd, T.cinv, tmin, T.best.t, t0))) { r0 = VK_REF_NONE; t0 = CUDART_INF_F; }
-    if (!(r1 != VK_REF_NONE && aabb_hit(f3(mnx.y, mny.y, mnz.y), f3(mxx.y, mxy.y, mxz.y), T.co, T.cd, T.cinv, tmin, T.best.t, t1))) { r1 = VK_REF_NONE; t1 = CUDART_INF_F; }
-    if (!(r2 != VK_REF_NONE && aabb_hit(f3(mnx.z, mny.z, mnz.z), f3(mxx.z, mxy.z, mxz.z), T.co, T.cd, T.cinv, tmin, T.best.t, t2))) { r2 = VK_REF_NONE; t2 = CUDART_INF_F; }
-    if (!(r3 != VK_REF_NONE && aabb_hit(f3(mnx.w, mny.w, mnz.w), f3(mxx.w, mxy.w, mxz.w), T.co, T.cd, T.cinv, tmin, T.best.t, t3))) { r3 = VK_REF_NONE; t3 = CUDART_INF_F; }
+    if (!(r0 != VK_REF_NONE && aabb_hit(f3(mnx.x, mny.x, mnz.x), f3(mxx.x, mxy.x, mxz.x), co, cd, cinv, tmin, tmax, t0))) { r0 = VK_REF_NONE; t0 = CUDART_INF_F; }
+    if (!(r1 != VK_REF_NONE && aabb_hit(f3(mnx.y, mny.y, mnz.y), f3(mxx.y, mxy.y, mxz.y), co, cd, cinv, tmin, tmax, t1))) { r1 = VK_REF_NONE; t1 = CUDART_INF_F; }
+    if (!(r2 != VK_REF_NONE && aabb_hit(f3(mnx.z, mny.z, mnz.z), f3(mxx.z, mxy.z, mxz.z), co, cd, cinv, tmin, tmax, t2))) { r2 = VK_REF_NONE; t2 = CUDART_INF_F; }
+    if (!(r3 != VK_REF_NONE && aabb_hit(f3(mnx.w, mny.w, mnz.w), f3(mxx.w, mxy.w, mxz.w), co, cd, cinv, tmin, tmax, t3))) { r3 = VK_REF_NONE; t3 = CUDART_INF_F; }
 #else
     {   // the same slab test with one FMA per plane: (b - o) * (1/d) = b * (1/d) - o * (1/d)
-        const float3 oi = f3(-T.co.x * T.cinv.x, -T.co.y * T.cinv.y, -T.co.z * T.cinv.z);
-        const float tmax = T.best.t;
+        const float3 oi = f3(-co.x * cinv.x, -co.y * cinv.y, -co.z * cinv.z);
 #define VKD_SLAB(C, R, TO)                                                                                             \
         {                                                                                                              \
-            const float ax = fmaf(mnx.C, T.cinv.x, oi.x), bx = fmaf(mxx.C, T.cinv.x, oi.x);                            \
-            const float ay = fmaf(mny.C, T.cinv.y, oi.y), by = fmaf(mxy.C, T.cinv.y, oi.y);                            \
-            const float az = fmaf(mnz.C, T.cinv.z, oi.z), bz = fmaf(mxz.C, T.cinv.z, oi.z);                            \
+            const float ax = fmaf(mnx.C, cinv.x, oi.x), bx = fmaf(mxx.C, cinv.x, oi.x);                            \
+            const float ay = fmaf(mny.C, cinv.y, oi.y), by = fmaf(mxy.C, cinv.y, oi.y);                            \
+            const float az = fmaf(mnz.C, cinv.z, oi.z), bz = fmaf(mxz.C, cinv.z, oi.z);                            \
             const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));                   \
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));                   \
             const bool miss = (R == VK_REF_NONE) | (tf <= tn);                                                         \
@@ -515,6 +506,22 @@ VKD void trav_node_step(Trav& T, const DScene& sc, float tmin, TraceCounters& tc
     VKD_CSWAP(t1, r1, t3, r3)
     VKD_CSWAP(t1, r1, t2, r2)
 #undef VKD_CSWAP
+}
+// precondition: trav_at_node(T)
+VKD void trav_node_step(Trav& T, const DScene& sc, float tmin, TraceCounters& tc) {
+    const uint32_t ni = VKD_INDEX(T.ref);
+    if (T.enter) { // BVHNode::hit's own `bb.hit` for the world root / an instanced sub-BVH root
+        T.enter = false;
+        const float4 n0 = __ldg(&sc.nodes[2 * ni]), n1 = __ldg(&sc.nodes[2 * ni + 1]);
+        float te;
+        if (!aabb_hit(f3(n0), f3(n1), T.co, T.cd, T.cinv, tmin, T.best.t, te)) {
+            T.ref = trav_pop(T);
+            return;
+        }
+    }
+    ++tc.nodes;
+    uint32_t r0, r1, r2, r3;
+    wide_node_test(sc, ni, T.co, T.cd, T.cinv, tmin, T.best.t, r0, r1, r2, r3);
     // nearest first, the others wait on the stack, farthest deepest
     if (r3 != VK_REF_NONE) T.stack[T.sp++] = r3;
     if (r2 != VK_REF_NONE) T.stack[T.sp++] = r2;

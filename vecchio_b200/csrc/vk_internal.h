@@ -216,6 +216,10 @@ struct WfState {
     cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a,       \
                              const RenderBuffers& b, unsigned long long* unit_head, int sm_count, bool legacy,         \
                              cudaStream_t st);                                                                         \
+    size_t stepq_stack_words(uint32_t stack_need, bool inst, int sm_count, uint32_t* levels);                          \
+    cudaError_t launch_stepq(const DScene& sc, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,        \
+                             unsigned long long* unit_head, uint32_t* gstack, uint32_t glevels, bool inst, int sm_count, \
+                             bool legacy, cudaStream_t st);                                                            \
     cudaError_t launch_wf_generate(const DCamera& cam, const RenderArgs& a, const WfState& w, cudaStream_t st);        \
     cudaError_t launch_wf_extend(const DScene& sc, const FlatProgram* flat, const RenderArgs& a, const WfState& w,     \
                                  const RenderBuffers& b, uint32_t set, cudaStream_t st);                               \

@@ -61,7 +61,7 @@ void usage(FILE* f) {
         "  --devices a,b,..   explicit device list\n"
         "  --out-dir DIR      where output_NNNN.ppm go (default: current directory)\n"
         "  --assets DIR       directory of earthmap.png etc. (default: assets)\n"
-        "  --variant V        auto | megakernel | wavefront | staged\n"
+        "  --variant V        auto | megakernel | wavefront | staged | warpq | stepq\n"
         "  --strict           reference operation order (no FMA contraction)\n"
         "  --legacy           book-1/2 integrator: Material::scatter, no light sampling\n"
         "  --sky              sky-gradient background (with --legacy)\n"
@@ -153,6 +153,7 @@ int parse(int argc, char** argv, Options& o) {
             else if (s == "wavefront") o.variant = VK_VARIANT_WAVEFRONT;
             else if (s == "staged") o.variant = VK_VARIANT_STAGED;
             else if (s == "warpq") o.variant = VK_VARIANT_WARPQ;
+            else if (s == "stepq") o.variant = VK_VARIANT_STEPQ;
             else return 2;
         } else if (a == "--strict") {
             o.flags |= VK_FLAG_STRICT_MATH;
