@@ -278,6 +278,27 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
         std::memcpy(&pperm[(size_t)p * 768 + 512], d->perlins[p].perm_z, 256);
     }
 
+    // shading class per primitive, so that filing a finished traversal costs one byte load (vk_stepq.cu)
+    std::vector<uint8_t> pcls;
+    uint32_t cls_base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    {
+        auto cls_of = [&](uint32_t mat) -> uint8_t {
+            const uint32_t t = mat < d->n_materials ? d->materials[mat].type : (uint32_t)VK_M_LAMBERTIAN;
+            return t == VK_M_DIFFUSE_LIGHT ? 0 : t == VK_M_DIELECTRIC ? 1 : t == VK_M_METAL ? 2 : 3;
+        };
+        cls_base[VK_T_SPHERE] = (uint32_t)pcls.size();
+        for (uint32_t i = 0; i < d->n_spheres; ++i) pcls.push_back(cls_of(d->sphere_mat[i]));
+        cls_base[VK_T_MSPHERE] = (uint32_t)pcls.size();
+        for (uint32_t i = 0; i < d->n_mspheres; ++i) pcls.push_back(cls_of(d->mspheres[i].mat));
+        cls_base[VK_T_RECT] = (uint32_t)pcls.size();
+        for (uint32_t i = 0; i < d->n_rects; ++i) pcls.push_back(cls_of(d->rects[i].mat));
+        cls_base[VK_T_BOX] = (uint32_t)pcls.size();
+        for (uint32_t i = 0; i < d->n_boxes; ++i) pcls.push_back(cls_of(d->boxes[i].mat));
+        cls_base[VK_T_MEDIUM] = (uint32_t)pcls.size();
+        for (uint32_t i = 0; i < d->n_media; ++i) pcls.push_back(cls_of(d->media[i].mat));
+        pcls.push_back(3); // (never empty)
+    }
+
     DScene s{};
     int rc;
 #define UP(field, type, src, n)                                                                                        \
@@ -301,7 +322,9 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     UP(perlin_vec, float4, pvec.data(), pvec.size())
     UP(perlin_perm, uint8_t, pperm.data(), pperm.size())
     UP(flat_shade, float4, R.flat_shade.data(), R.flat_shade.size())
+    UP(prim_cls, uint8_t, pcls.data(), pcls.size())
 #undef UP
+    for (int t = 0; t < 8; ++t) s.cls_base[t] = cls_base[t];
     s.root = d->root;
     s.n_lights = d->n_lights;
     s.has_media = d->n_media > 0;

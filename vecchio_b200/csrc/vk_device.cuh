@@ -69,7 +69,13 @@ VKD float3 at(float3 o, float3 d, float t) { // Ray::at src/main.rs:51-53 (never
 // (pixel, global sample, depth << 8 | block, 0).  Replaces rand::thread_rng() at every call site
 // of the hot path; only the distributions are kept.
 // ---------------------------------------------------------------------------------------------
+// (VK_PHILOX_CALL: one out-of-line copy instead of ~9 inlined ones of 60 instructions each -- the step-queue kernel's
+// executed code must stay inside the 32 KB instruction cache, see vk_stepq.cu)
+#if defined(VK_PHILOX_CALL) && VK_PHILOX_CALL
+static __device__ __noinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#else
 VKD uint4 philox4x32_10(uint4 c, uint2 k) {
+#endif
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;

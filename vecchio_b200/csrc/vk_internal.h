@@ -46,6 +46,8 @@ struct DScene {
     const float4* perlin_vec;   // 256 x float4 per Perlin
     const uint8_t* perlin_perm; // 768 B per Perlin (x, y, z)
     const float4* flat_shade;   // 2 x float4 per hit entry of the flat program (see Relayout::flat_shade); may be empty
+    const uint8_t* prim_cls;    // shading class of every primitive (0 emitter, 1 dielectric, 2 metal, 3 the rest), one byte each:
+    uint32_t cls_base[8];       // entry cls_base[type of the reference] + index of the reference (step-queue kernel's filing)
     uint32_t root;
     uint32_t n_lights;
     uint32_t has_media; // scene holds a ConstantMedium: selects the kernel instantiation with the medium code

@@ -24,6 +24,10 @@
 // The closest hit does not depend on the visiting order and the variates are keyed per (pixel, sample, depth), so the
 // frame is bit-identical to the other variants' (tests/test_gpu_parity.py).  Reference semantics per step are the lane
 // traversal's (vk_device.cuh: trav_node_step / trav_prim_step, src/accel.rs:58-83, src/hittable.rs).
+#ifndef VKS_PHILOX_CALL
+#define VKS_PHILOX_CALL 1
+#endif
+#define VK_PHILOX_CALL VKS_PHILOX_CALL
 #include "vk_warpq.cuh"
 
 namespace VK_NS {
@@ -47,18 +51,32 @@ namespace VK_NS {
 #define VKS_MINB_INST 3
 #endif
 #ifndef VKS_NODE_STEPS
-#define VKS_NODE_STEPS 2 // node visits per batch: lanes whose next reference is a node again go on, the others wait
+#define VKS_NODE_STEPS 3 // node visits per batch: lanes whose next reference is a node again go on, the others wait
 #endif
 #ifndef VKS_LEAF_STEPS
 #define VKS_LEAF_STEPS 2
 #endif
+// A queue per leaf kind only pays when each of them can fill a warp.  Scenes with instanced sub-BVHs are the heterogeneous
+// ones (final scene: boxes, spheres, moving sphere, media, instance chains, a rect) and their slots are larger, so fewer:
+// there every leaf goes through the one generic queue -- its batch runs each kind present at partial lanes, but pays the
+// pop / load / store / file overhead once instead of once per kind.
+#ifndef VKS_MERGE
+#define VKS_MERGE 0
+#endif
+#ifndef VKS_MERGE_INST
+#define VKS_MERGE_INST 1
+#endif
+#ifndef VKS_STICKY
+#define VKS_STICKY 1 // a stage whose queue still holds a full batch runs again: its code is in the instruction cache
+#endif
 #define VKS_FRESH 0xFFFFFFFEu // nx of a slot whose ray segment has just been written: no traversal state yet
 #define VKS_ENTER VKD_DUP     // on a node reference: the node's own box has not been tested (world root / instance root)
 
-template <int N_, int RN_, int SD_, bool INST_>
+template <int N_, int RN_, int SD_, bool INST_, bool MERGE_>
 struct WqStepWarp {
     static constexpr uint32_t N = N_, RMASK = RN_ - 1, NQ = VKQ_NQ_STEP, SD = SD_;
     static constexpr bool INST = INST_;
+    static constexpr bool MERGE = MERGE_; // spheres and boxes go through the generic leaf queue (see VKS_MERGE)
     static_assert((RN_ & (RN_ - 1)) == 0 && RN_ >= N_ && RN_ <= 256, "ring capacity: power of two, >= slots, byte indices");
     float4 ro[N_];                 // world ray: origin.xyz, time
     float4 rd[N_];                 // direction.xyz, bits: depth of the segment
@@ -80,7 +98,7 @@ struct WqStepWarp {
 
 // the fullest of the ten queues (entries << 4 | queue; one max chain, made provably uniform by the reduction: see wq_pick)
 template <class W>
-VKD bool sq_pick(const W& S, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
+VKD bool sq_pick(const W& S, uint32_t last_q, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
     const uint4 c01 = *reinterpret_cast<const uint4*>(&S.ct[0]), c23 = *reinterpret_cast<const uint4*>(&S.ct[2]);
     const uint4 c45 = *reinterpret_cast<const uint4*>(&S.ct[4]), c67 = *reinterpret_cast<const uint4*>(&S.ct[6]);
     const uint4 c89 = *reinterpret_cast<const uint4*>(&S.ct[8]);
@@ -94,6 +112,13 @@ VKD bool sq_pick(const W& S, uint32_t& q, uint32_t& n_q, uint32_t& tail_q) {
     key = max(key, c23.z * 16u + VKQ_DIEL);
     key = max(key, c45.x * 16u + VKQ_METAL);
     key = max(key, c01.z * 16u + VKQ_END);
+#if VKS_STICKY
+    {   // the stage that ran last goes first while it can fill a warp (the scheduler loop otherwise changes stage almost
+        // every iteration, and each change is a walk through code the 6 KB L0 instruction cache has dropped)
+        const uint32_t n_last = S.ct[last_q].x;
+        if (n_last >= 32u) key = max(key, (n_last + 4096u) * 16u + last_q);
+    }
+#endif
     key = __reduce_max_sync(0xFFFFFFFFu, key);
     q = key & 15u;
     const uint2 e = S.ct[q];
@@ -116,11 +141,12 @@ VKD void stepq_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, c
     uint32_t* const gst = gstack + (size_t)(blockIdx.x * VKQ_WARPS + (threadIdx.x >> 5)) * glevels * W::N;
     const float tmin = 0.001f; // world.hit(&r, 0.001, inf) src/main.rs:130
     wq_init(S, lane);
+    uint32_t q = VKQ_END; // the stage that ran last
 #pragma unroll 1
     for (;;) {
         wq_selfcheck(S, buf, lane, 0u);
-        uint32_t q, n_q, tail_q, head;
-        if (!sq_pick(S, q, n_q, tail_q)) break; // every queue empty: all slots have retired
+        uint32_t n_q, tail_q, head;
+        if (!sq_pick(S, q, q, n_q, tail_q)) break; // every queue empty: all slots have retired
         const uint32_t n = wq_pop(S, q, n_q, tail_q, 32u, lane, head);
         if (q >= VKQ_END && q <= VKQ_DIFFI) {
             wq_shade_batch<LEGACY, false>(sc, C, buf, q, n, head, n_drop);
@@ -228,64 +254,80 @@ VKD void stepq_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, c
                     ref = pop();
                 }
             }
-        } else if (act) {
-            // ---- the other leaves: trav_prim_step's cases -------------------------------------------------------------------
-            const uint32_t type = VKD_TYPE(ref);
-            bool entered = false;
-            if (type == VKD_T_EXIT) { // leave the instanced sub-BVH: back to the world ray
-                hp.w = 0u;
-            } else if (type != VK_T_NONE) {
-                float3 to = co, td = cd;
-                uint32_t leaf = ref, inst = hp.w;
-                if (type == VK_T_XFORM) {
-                    leaf = chain_down(sc, ref, to, td) | (ref & VKD_DUP);
-                    inst = ref & ~VKD_DUP;
-                    if (W::INST && VKD_TYPE(leaf) == VK_T_NODE) { // instanced sub-BVH: traverse it in object space
-                        push(VKD_T_EXIT << 28);
-                        S.oo[W::INST ? slot : 0u] = make_float4(to.x, to.y, to.z, 0.0f);
-                        S.od[W::INST ? slot : 0u] = make_float4(td.x, td.y, td.z, 0.0f);
-                        hp.w = inst;
-                        ref = (leaf & ~VKD_DUP) | VKS_ENTER;
-                        entered = true;
+        } else {
+            // ---- the other leaves (all leaves when W::MERGE): trav_prim_step's cases ------------------------------------
+#pragma unroll 1
+            for (int k = 0; k < VKS_LEAF_STEPS; ++k) {
+                const uint32_t type = VKD_TYPE(ref);
+                const bool go = act && ref != VKD_DONE && type != VK_T_NODE && (W::MERGE || (type != VK_T_SPHERE && type != VK_T_BOX));
+                if (!__any_sync(0xFFFFFFFFu, go)) break;
+                if (go) {
+                    bool entered = false;
+                    if (type == VKD_T_EXIT) { // leave the instanced sub-BVH: back to the world ray
+                        hp.w = 0u;
+                        co = f3(S.ro[slot]);
+                        cd = f3(S.rd[slot]);
+                    } else if (type != VK_T_NONE) {
+                        float3 to = co, td = cd;
+                        uint32_t leaf = ref, inst = hp.w;
+                        if (type == VK_T_XFORM) {
+                            leaf = chain_down(sc, ref, to, td) | (ref & VKD_DUP);
+                            inst = ref & ~VKD_DUP;
+                            if (W::INST && VKD_TYPE(leaf) == VK_T_NODE) { // instanced sub-BVH: traverse it in object space
+                                push(VKD_T_EXIT << 28);
+                                S.oo[W::INST ? slot : 0u] = make_float4(to.x, to.y, to.z, 0.0f);
+                                S.od[W::INST ? slot : 0u] = make_float4(td.x, td.y, td.z, 0.0f);
+                                hp.w = inst;
+                                ref = (leaf & ~VKD_DUP) | VKS_ENTER;
+                                entered = true;
+                            }
+                        }
+                        if (!entered) {
+                            float t;
+                            uint32_t face = 0;
+                            bool hit;
+                            ++tc.prims;
+                            if (MEDIA && VKD_TYPE(leaf) == VK_T_MEDIUM) {
+                                MediumXi xi;
+                                xi.table = nullptr;
+                                xi.depth = __float_as_uint(S.rd[slot].w);
+                                xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
+                                xi.rng.pixel = S.px[slot];
+                                xi.rng.sample = __float_as_uint(S.bt[slot].w);
+                                hit = medium_t(sc, leaf, to, td, time, tmin, best_t, xi, t);
+                            } else {
+                                hit = leaf_t(sc, leaf, to, td, rcp3(td), time, tmin, best_t, t, face);
+                            }
+                            if (hit) {
+                                best_t = t;
+                                hp.x = __float_as_uint(t);
+                                hp.y = leaf & ~VKD_DUP;
+                                hp.z = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (face << 28);
+                            }
+                        }
                     }
-                }
-                if (!entered) {
-                    float t;
-                    uint32_t face = 0;
-                    bool hit;
-                    ++tc.prims;
-                    if (MEDIA && VKD_TYPE(leaf) == VK_T_MEDIUM) {
-                        MediumXi xi;
-                        xi.table = nullptr;
-                        xi.depth = __float_as_uint(S.rd[slot].w);
-                        xi.rng.key = make_uint2(a.seed_lo, a.seed_hi);
-                        xi.rng.pixel = S.px[slot];
-                        xi.rng.sample = __float_as_uint(S.bt[slot].w);
-                        hit = medium_t(sc, leaf, to, td, time, tmin, best_t, xi, t);
-                    } else {
-                        hit = leaf_t(sc, leaf, to, td, rcp3(td), time, tmin, best_t, t, face);
-                    }
-                    if (hit) {
-                        best_t = t;
-                        hp.x = __float_as_uint(t);
-                        hp.y = leaf & ~VKD_DUP;
-                        hp.z = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (face << 28);
-                    }
+                    if (!entered) ref = pop();
                 }
             }
-            if (!entered) ref = pop();
         }
         // ---- store the state, file the slot under what it needs next ------------------------------------------------------
         uint32_t cls = VKQ_NONE;
         if (act) {
             S.hp[slot] = hp;
             if (ref == VKD_DONE) {
-                cls = hp.y == VK_REF_NONE ? miss_cls : wq_class_of(sc, hp.y, hp.z & 0x80000000u);
+                if (hp.y == VK_REF_NONE) cls = miss_cls;
+                else { // (wq_class_of's answer from the per-primitive table: one byte load for the few lanes that finish)
+                    const uint32_t c = __ldg(&sc.prim_cls[sc.cls_base[VKD_TYPE(hp.y)] + VKD_INDEX(hp.y)]);
+                    cls = c == 3u ? ((!W::MERGE && (hp.z & 0x80000000u)) ? (uint32_t)VKQ_DIFFI : (uint32_t)VKQ_DIFF) : (uint32_t)VKQ_EMIT + c;
+                }
             } else {
                 S.nx[slot] = ref;
                 S.sp[slot] = (uint8_t)sp;
                 const uint32_t type = VKD_TYPE(ref);
-                cls = type == VK_T_NODE ? (uint32_t)VKQ_EXT : type == VK_T_SPHERE ? (uint32_t)VKQ_SPH : type == VK_T_BOX ? (uint32_t)VKQ_BOX : (uint32_t)VKQ_LEAF;
+                cls = type == VK_T_NODE ? (uint32_t)VKQ_EXT
+                      : (!W::MERGE && type == VK_T_SPHERE) ? (uint32_t)VKQ_SPH
+                      : (!W::MERGE && type == VK_T_BOX)    ? (uint32_t)VKQ_BOX
+                                                           : (uint32_t)VKQ_LEAF;
             }
         }
         wq_push(S, cls, slot, lane, below);
@@ -293,8 +335,8 @@ VKD void stepq_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, c
     wq_flush_counters(buf, lane, n_rays, n_drop, tc.nodes, tc.prims);
 }
 
-using WqStepWorld = WqStepWarp<VKS_N, VKS_RN, VKS_SD, false>;
-using WqStepInst = WqStepWarp<VKS_N_INST, VKS_RN, VKS_SD, true>;
+using WqStepWorld = WqStepWarp<VKS_N, VKS_RN, VKS_SD, false, VKS_MERGE != 0>;
+using WqStepInst = WqStepWarp<VKS_N_INST, VKS_RN, VKS_SD, true, VKS_MERGE_INST != 0>;
 
 template <bool MEDIA, bool LEGACY>
 __global__ void __launch_bounds__(32 * VKQ_WARPS, VKS_MINB) k_stepq(const DScene sc, const DCamera cam, const RenderArgs a, const RenderBuffers buf,
