@@ -57,12 +57,12 @@ def test_queue_protocol_selfcheck_finds_nothing_and_changes_nothing():
 
 @pytest.mark.gpu
 def test_step_queue_overflow_stack_renders_the_same_frames():
-    """The step-queue kernel keeps the first VKS_SD (8) stack entries of a traversal in shared memory and the rest in a
-    per-warp strip of global memory.  A build with VKS_SD=2 pushes almost every stack access of these scenes through
+    """The step-queue kernel keeps the first VKS_SD (4) stack entries of a traversal in shared memory and the rest in a
+    per-warp strip of global memory.  A build with VKS_SD=1 pushes almost every stack access of these scenes through
     the overflow path: same rays, same frames."""
-    lib = os.path.join(ROOT, "build", "libvk_sd2.so")
+    lib = os.path.join(ROOT, "build", "libvk_sd1.so")
     if not os.path.exists(lib):
-        subprocess.run([os.path.join(ROOT, "scripts", "build_variants.sh"), "sd2:-DVKS_SD=2"], check=True, cwd=ROOT,
+        subprocess.run([os.path.join(ROOT, "scripts", "build_variants.sh"), "sd1:-DVKS_SD=1"], check=True, cwd=ROOT,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     shallow, normal = run_child(lib), run_child(None)
     assert len(shallow) == len(normal) == 10

@@ -25,7 +25,7 @@
 // frame is bit-identical to the other variants' (tests/test_gpu_parity.py).  Reference semantics per step are the lane
 // traversal's (vk_device.cuh: trav_node_step / trav_prim_step, src/accel.rs:58-83, src/hittable.rs).
 #ifndef VKS_PHILOX_CALL
-#define VKS_PHILOX_CALL 1
+#define VKS_PHILOX_CALL 0 // (measured: the call costs more than the instruction-cache footprint it saves; final scene 59.3 -> 55.3 ms inlined)
 #endif
 #define VK_PHILOX_CALL VKS_PHILOX_CALL
 #include "vk_warpq.cuh"
@@ -36,19 +36,20 @@ namespace VK_NS {
 #define VKS_N 96 // slots per warp, scenes without instanced sub-BVHs
 #endif
 #ifndef VKS_N_INST
-#define VKS_N_INST 96
+#define VKS_N_INST 104
 #endif
 #ifndef VKS_RN
 #define VKS_RN 128
 #endif
 #ifndef VKS_SD
-#define VKS_SD 8 // stack entries per slot kept in shared memory
+#define VKS_SD 4 // stack entries per slot kept in shared memory (deeper ones: global strip).  Measured: 4 beats 8 -- what the
+                 // pools do not take of the SM's 228 KB is L1, and the node fetches live in it (profiles/r2_sweep_6.log, _7.log)
 #endif
 #ifndef VKS_MINB
 #define VKS_MINB 4
 #endif
 #ifndef VKS_MINB_INST
-#define VKS_MINB_INST 3
+#define VKS_MINB_INST 4
 #endif
 #ifndef VKS_NODE_STEPS
 #define VKS_NODE_STEPS 3 // node visits per batch: lanes whose next reference is a node again go on, the others wait
@@ -66,8 +67,12 @@ namespace VK_NS {
 #ifndef VKS_MERGE_INST
 #define VKS_MERGE_INST 1
 #endif
+#ifndef VKS_PREFETCH
+#define VKS_PREFETCH 0 // 1: when a slot is filed, prefetch what its next step will read (the node's line / the sphere) into L1
+#endif
 #ifndef VKS_STICKY
-#define VKS_STICKY 1 // a stage whose queue still holds a full batch runs again: its code is in the instruction cache
+#define VKS_STICKY 0 // 1: a stage whose queue still holds a full batch runs again (its code is in the L0 instruction cache);
+                     // measured slightly slower (final scene 59.3 against 57.7 ms): the fullest queue first keeps the batches fuller
 #endif
 #define VKS_FRESH 0xFFFFFFFEu // nx of a slot whose ray segment has just been written: no traversal state yet
 #define VKS_ENTER VKD_DUP     // on a node reference: the node's own box has not been tested (world root / instance root)
@@ -324,6 +329,10 @@ VKD void stepq_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, c
                 S.nx[slot] = ref;
                 S.sp[slot] = (uint8_t)sp;
                 const uint32_t type = VKD_TYPE(ref);
+#if VKS_PREFETCH
+                if (type == VK_T_NODE) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.wnodes + 8u * (size_t)VKD_INDEX(ref)));
+                else if (type == VK_T_SPHERE) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.spheres + VKD_INDEX(ref)));
+#endif
                 cls = type == VK_T_NODE ? (uint32_t)VKQ_EXT
                       : (!W::MERGE && type == VK_T_SPHERE) ? (uint32_t)VKQ_SPH
                       : (!W::MERGE && type == VK_T_BOX)    ? (uint32_t)VKQ_BOX
