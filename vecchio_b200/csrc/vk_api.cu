@@ -441,7 +441,11 @@ static uint32_t choose_variant(const vk_ctx* c, const vk_render_params* P) {
     if (flat && c->flat.n_bvh == 0) return (uint32_t)VK_VARIANT_WARPQ;
     // BVH scenes: step queues where every leaf sits in the world frame (random spheres 8.9 against 10.7 ms, 10^6 spheres 23.7
     // against 29.0 ms); scenes with instanced sub-BVHs (final scene: 50.6 against 45.8 ms) stay on the lane megakernel
-    return c->levels_sub == 0u ? (uint32_t)VK_VARIANT_STEPQ : (uint32_t)VK_VARIANT_MEGAKERNEL;
+    // -- and only for frames that fill the pools a few dozen times over: 227 000 slots are resident, and below ~3 M paths
+    // their start-up and drain cost more than the fuller warps gain (random spheres 400x225: 16 spp 1.32 against 1.21 ms,
+    // 32 spp 1.85 against 1.83, 64 spp 2.78 against 3.30; profiles/r2_sweep_9.log)
+    const uint64_t paths = (uint64_t)P->width * P->height * (P->spp_count ? P->spp_count : P->spp - P->spp_begin);
+    return c->levels_sub == 0u && paths >= (4ull << 20) ? (uint32_t)VK_VARIANT_STEPQ : (uint32_t)VK_VARIANT_MEGAKERNEL;
 }
 
 // Lane megakernel for a BVH scene: static (one whole ray per lane and loop iteration) or dynamic

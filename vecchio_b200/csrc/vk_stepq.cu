@@ -67,6 +67,9 @@ namespace VK_NS {
 #ifndef VKS_MERGE_INST
 #define VKS_MERGE_INST 1
 #endif
+#ifndef VKS_INLINE_SPH
+#define VKS_INLINE_SPH 1
+#endif
 #ifndef VKS_PREFETCH
 #define VKS_PREFETCH 0 // 1: when a slot is filed, prefetch what its next step will read (the node's line / the sphere) into L1
 #endif
@@ -217,6 +220,22 @@ VKD void stepq_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, c
                         ref = pop();
                     }
                 }
+#if VKS_INLINE_SPH
+                // a lane that now holds a sphere tests it here, between two node visits, instead of going through the sphere
+                // queue: the test runs at partial lanes, but the lane saves a queue hop and is back for the next visit
+                if (!W::MERGE && act && ref != VKD_DONE && VKD_TYPE(ref) == VK_T_SPHERE) {
+                    const float4 s = __ldg(&sc.spheres[VKD_INDEX(ref)]);
+                    float t;
+                    ++tc.prims;
+                    if (sphere_t(f3(s), s.w, co, cd, tmin, best_t, t)) {
+                        best_t = t;
+                        hp.x = __float_as_uint(t);
+                        hp.y = ref & ~VKD_DUP;
+                        hp.z = hi_inst;
+                    }
+                    ref = pop();
+                }
+#endif
             }
         } else if (q == VKQ_SPH) {
             // ---- Sphere::hit (src/hittable.rs:62-102), distance only ------------------------------------------------------
