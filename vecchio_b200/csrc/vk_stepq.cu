@@ -52,7 +52,11 @@ namespace VK_NS {
 #define VKS_MINB_INST 4
 #endif
 #ifndef VKS_NODE_STEPS
-#define VKS_NODE_STEPS 3 // node visits per batch: lanes whose next reference is a node again go on, the others wait
+#define VKS_NODE_STEPS 6 // node visits per batch: lanes whose next reference is a node again go on (a sphere is tested in
+                         // between, VKS_INLINE_SPH), the others wait.  Measured: 1 / 3 / 6 / 12 visits: 11.9 / 8.9 / 8.5 / 8.6 ms
+#endif
+#ifndef VKS_NODE_STEPS_INST
+#define VKS_NODE_STEPS_INST 3 // (final scene: 50.6 ms with 3, 51.4 with 6)
 #endif
 #ifndef VKS_LEAF_STEPS
 #define VKS_LEAF_STEPS 2
@@ -197,7 +201,7 @@ VKD void stepq_body(const DScene& sc, const DCamera& cam, const RenderArgs& a, c
             // ---- node visits (BVHNode::hit, src/accel.rs:58-83) -------------------------------------------------------
             const float3 cinv = rcp3(cd);
 #pragma unroll 1
-            for (int k = 0; k < VKS_NODE_STEPS; ++k) {
+            for (int k = 0; k < (W::INST ? VKS_NODE_STEPS_INST : VKS_NODE_STEPS); ++k) {
                 const bool go = act && ref != VKD_DONE && VKD_TYPE(ref) == VK_T_NODE;
                 if (!__any_sync(0xFFFFFFFFu, go)) break;
                 if (go) {
