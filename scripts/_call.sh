@@ -1,8 +1,9 @@
 set -x
-BVH="final_scene:800:800:64:100 random_spheres_demo:400:225:256:50 stress_spheres@1000:1920:1080:4:50 random_spheres_demo:400:225:16:50"
-rm -f gpurun_out/r2_sweep_10.log
-J=""; for b in $BVH; do J="$J $b:5"; done
-for tag in is1n6 is1n8 is1n12 is0n6 is1n6l3 n6w5; do
-  VECCHIO_GPU_LIB=build/libvk_$tag.so timeout 300 python scripts/_sweep.py $tag $J >> gpurun_out/r2_sweep_10.log 2>&1
+J="cornell_box:600:600:1000:100:0 cornell_smoke:600:600:500:100:0"
+rm -f gpurun_out/r2_sweep_11.log
+python scripts/_sweep.py slabbox $J >> gpurun_out/r2_sweep_11.log 2>&1
+for tag in n120b4 n120b6; do
+  VECCHIO_GPU_LIB=build/libvk_$tag.so timeout 300 python scripts/_sweep.py $tag cornell_box:600:600:1000:100:0 >> gpurun_out/r2_sweep_11.log 2>&1
 done
-cat gpurun_out/r2_sweep_10.log
+cat gpurun_out/r2_sweep_11.log
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log

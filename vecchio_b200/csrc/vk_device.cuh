@@ -633,6 +633,40 @@ VKD void flat_rects(const FlatProgram& P, uint32_t i0, uint32_t i1, float3 co, f
         }
     }
 }
+#if !VK_STRICT
+// Render build: a Boxy of the flat program as ONE entry, by the slab method (box_t above has the argument: a ray from
+// outside enters through the farthest of its three near planes, a ray from inside leaves through the nearest far
+// plane; acceptance window tmin <= t < best as for a box side, ties to the side that comes first in Boxy::new order).
+// The plane distances are the rect test's own (k - o) * (1/d), NOT one fma each: a ray that starts on a side keeps the
+// exact t = 0 it has in the six-rect form (see the rejected experiment in flat_rects_k).  ~40 instructions per ray
+// instead of six rect tests of ~15.  The winning side's entry of the hit table: sides 0|1, 2|3, 4|5 are consecutive.
+template <int K>
+VKD void flat_boxes_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const float3 (&co)[K], const float3 (&ci)[K], float tmin,
+                      float (&best_t)[K], uint32_t (&best_hit)[K]) {
+#pragma unroll 1
+    for (uint32_t i = i0; i < i1; ++i) {
+        const float4 mn = P.boxes[i].mn, mx = P.boxes[i].mx;
+        const uint32_t hz = __float_as_uint(mn.w), hy = __float_as_uint(mx.w) & 0xFFFFu, hx = __float_as_uint(mx.w) >> 16;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            const float x0 = (mn.x - co[q].x) * ci[q].x, x1 = (mx.x - co[q].x) * ci[q].x;
+            const float y0 = (mn.y - co[q].y) * ci[q].y, y1 = (mx.y - co[q].y) * ci[q].y;
+            const float z0 = (mn.z - co[q].z) * ci[q].z, z1 = (mx.z - co[q].z) * ci[q].z;
+            const float nx = fminf(x0, x1), ny = fminf(y0, y1), nz = fminf(z0, z1);
+            const float fx = fmaxf(x0, x1), fy = fmaxf(y0, y1), fz = fmaxf(z0, z1);
+            const float t_near = fmaxf(fmaxf(nx, ny), nz), t_far = fminf(fminf(fx, fy), fz);
+            const bool enter = t_near >= tmin;
+            const float t = enter ? t_near : t_far;
+            const bool hit = (t_near <= t_far) & (t >= tmin) & (t < best_t[q]);
+            const bool on_z = (enter ? nz : fz) == t, on_y = (enter ? ny : fy) == t;
+            const float at_max = on_z ? z1 : (on_y ? y1 : x1); // distance of the axis' box_max plane: sides 0, 2, 4
+            const uint32_t id = (on_z ? hz : (on_y ? hy : hx)) + (at_max == t ? 0u : 1u);
+            best_t[q] = hit ? t : best_t[q];
+            best_hit[q] = hit ? id : best_hit[q];
+        }
+    }
+}
+#endif
 template <bool MEDIA>
 VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3 d, float time, float tmin, float tmax,
                         const MediumXi& xi, TraceCounters& tc) {
@@ -662,9 +696,20 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
         flat_rects<0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);
         flat_rects<1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, tmin, best_t, best_hit);
         flat_rects<2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, tmin, best_t, best_hit);
+#if VK_STRICT
         flat_rects<0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, tmin, best_t, best_hit);
         flat_rects<1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, tmin, best_t, best_hit);
         flat_rects<2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, tmin, best_t, best_hit);
+#else
+        {
+            const float3 co1[1] = {co}, ci1[1] = {ci};
+            float bt1[1] = {best_t};
+            uint32_t bh1[1] = {best_hit};
+            flat_boxes_k<1>(P, g.box0, g.box1, co1, ci1, tmin, bt1, bh1);
+            best_t = bt1[0];
+            best_hit = bh1[0];
+        }
+#endif
 #pragma unroll 1
         for (uint32_t i = g.sph0; i < g.sph1; ++i) {
             float tt;
@@ -827,9 +872,13 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
         flat_rects_k<K, 0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);
         flat_rects_k<K, 1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, tmin, best_t, best_hit);
         flat_rects_k<K, 2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, tmin, best_t, best_hit);
+#if VK_STRICT
         flat_rects_k<K, 0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, tmin, best_t, best_hit);
         flat_rects_k<K, 1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, tmin, best_t, best_hit);
         flat_rects_k<K, 2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, tmin, best_t, best_hit);
+#else
+        flat_boxes_k<K>(P, g.box0, g.box1, co, ci, tmin, best_t, best_hit);
+#endif
 #pragma unroll 1
         for (uint32_t i = g.sph0; i < g.sph1; ++i) {
             const float4 sp = P.spheres[i].a;

@@ -78,6 +78,7 @@ struct DScene {
 #define VKF_MAX_SPHERES 16
 #define VKF_MAX_MEDIA 4
 #define VKF_MAX_BVH 32
+#define VKF_MAX_BOXES (VKF_MAX_RECTS / 6)
 enum { VKF_OP_TRANSLATE = 0, VKF_OP_ROTX = 1, VKF_OP_ROTY = 2, VKF_OP_ROTZ = 3 };
 struct FlatOp { // one wrapper level, outermost first
     uint32_t kind;
@@ -97,6 +98,10 @@ struct FlatSphere { // Sphere::hit :65-95 | MovingSphere::hit :154-184
     uint32_t hit;
     uint32_t _pad[2];
 };
+struct FlatBox { // Boxy::hit src/hittable.rs:363-365 as ONE entry (render build; the strict build tests its six sides as rects)
+    float4 mn; // box_min, .w = bits: hits[] index of side 0 (sides 0 and 1, the two XY rects, are consecutive entries)
+    float4 mx; // box_max, .w = bits: hits[] index of side 2 (XZ pair) | index of side 4 (YZ pair) << 16
+};
 struct FlatHit { // what the closest entry resolves to
     uint32_t prim; // leaf record (sphere / msphere / rect / box / medium [| VKD_DUP on a medium's second visit])
     uint32_t inst; // outermost wrapper of the chain it sits under, or 0
@@ -110,7 +115,7 @@ struct FlatSeg {
     uint8_t msph0, msph1;       // moving spheres
     uint8_t med0, med1;         // media: hits[] indices [med0, med1) (their prim is the medium ref)
     uint8_t bvh0, bvh1;         // sub-BVH roots [bvh0, bvh1) of FlatProgram::bvh, traversed in this segment's frame
-    uint8_t _pad[2];
+    uint8_t box0, box1;         // boxes [box0, box1) of FlatProgram::boxes: the render build's form of the box-side rect ranges
 };
 struct FlatProgram {
     uint32_t n;      // number of primitive entries; 0 = no program: use the BVH
@@ -135,6 +140,9 @@ struct FlatProgram {
     // The reference applies the wrappers one after the other (src/hittable.rs:508, :591-595); composing them on the host
     // changes the rounding only, so the strict build keeps walking the ops.
     float seg_affine[VKF_MAX_SEGS][12];
+    // Render build: every Boxy of the program once more as one slab-test entry (flat_boxes_k, vk_device.cuh); it replaces the
+    // box-side rect ranges rect0[3..5] there.  Same sides, same hit-table entries.
+    FlatBox boxes[VKF_MAX_BOXES];
 };
 
 struct DCamera {

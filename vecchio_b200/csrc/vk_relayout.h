@@ -220,6 +220,11 @@ struct FlatBuilder {
         std::vector<std::pair<FlatSphere, FlatHit>> sph, msph;
         std::vector<FlatHit> med;
         std::vector<uint32_t> bvh; // roots of homogeneous subtrees kept as BVHs (hybrid program)
+        struct Box {
+            float mn[3], mx[3];
+            size_t at[3]; // position of sides 0, 2, 4 in rects[3], rects[4], rects[5] (sides 1, 3, 5 follow them)
+        };
+        std::vector<Box> boxes;
         uint32_t inst = 0;
     };
     std::vector<Seg> segs;
@@ -308,6 +313,7 @@ struct FlatBuilder {
             const float* mx = b.box_max;
             const uint32_t XY = 0u | (1u << 2) | (2u << 4), XZ = 0u | (2u << 2) | (1u << 4), YZ = 1u | (2u << 2) | (0u << 4);
             Seg& g = segs[si];
+            g.boxes.push_back({{mn[0], mn[1], mn[2]}, {mx[0], mx[1], mx[2]}, {g.rects[3].size(), g.rects[4].size(), g.rects[5].size()}});
             return rect(g, mn[0], mx[0], mn[1], mx[1], mx[2], XY, ref, 0, true) && rect(g, mn[0], mx[0], mn[1], mx[1], mn[2], XY, ref, 1, true) &&
                    rect(g, mn[0], mx[0], mn[2], mx[2], mx[1], XZ, ref, 2, true) && rect(g, mn[0], mx[0], mn[2], mx[2], mn[1], XZ, ref, 3, true) &&
                    rect(g, mn[1], mx[1], mn[2], mx[2], mx[0], YZ, ref, 4, true) && rect(g, mn[1], mx[1], mn[2], mx[2], mn[0], YZ, ref, 5, true);
@@ -342,7 +348,7 @@ struct FlatBuilder {
         segs.emplace_back();
         if (!emit(d->root, 0, 0)) return false;
         if (segs.size() > VKF_MAX_SEGS) return false;
-        uint32_t n_ops = 0, n_rects = 0, n_sph = 0, n_hits = 0, n_med = 0, n_bvh = 0;
+        uint32_t n_ops = 0, n_rects = 0, n_sph = 0, n_hits = 0, n_med = 0, n_bvh = 0, n_boxes = 0;
         for (size_t s = 0; s < segs.size(); ++s) {
             Seg& g = segs[s];
             FlatSeg& o = P->segs[s];
@@ -360,6 +366,15 @@ struct FlatBuilder {
                 }
                 o.rect1[k] = (uint8_t)n_rects;
             }
+            if (n_boxes + g.boxes.size() > VKF_MAX_BOXES) return false;
+            o.box0 = (uint8_t)n_boxes;
+            for (const Seg::Box& b : g.boxes) { // (the sides' hit entries were numbered just above)
+                const uint32_t hz = g.rects[3][b.at[0]].first.hit, hy = g.rects[4][b.at[1]].first.hit, hx = g.rects[5][b.at[2]].first.hit;
+                FlatBox& fb = P->boxes[n_boxes++];
+                fb.mn = make_float4(b.mn[0], b.mn[1], b.mn[2], __uint_as_float_host(hz));
+                fb.mx = make_float4(b.mx[0], b.mx[1], b.mx[2], __uint_as_float_host(hy | (hx << 16)));
+            }
+            o.box1 = (uint8_t)n_boxes;
             if (n_sph + g.sph.size() + g.msph.size() > VKF_MAX_SPHERES) return false;
             o.sph0 = (uint8_t)n_sph;
             for (auto& e : g.sph) {

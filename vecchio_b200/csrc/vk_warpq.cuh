@@ -446,6 +446,9 @@ VKD void wq_flush_counters(const RenderBuffers& buf, uint32_t lane, uint32_t n_r
 }
 
 
+#ifndef VKQ_CAP_BPS
+#define VKQ_CAP_BPS 0 // (A/B builds only: run at most this many CTAs per SM although more would fit)
+#endif
 template <class K> static cudaError_t warpq_prepare(K kernel, size_t smem, int* blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -454,12 +457,15 @@ template <class K> static cudaError_t warpq_prepare(K kernel, size_t smem, int* 
     // more: whatever the carveout leaves of the SM's 228 KB is L1, and the BVH kernels' node fetches want it.
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, 32 * VKQ_WARPS, smem);
     if (e != cudaSuccess) return e;
+    if (VKQ_CAP_BPS && *blocks_per_sm > VKQ_CAP_BPS) *blocks_per_sm = VKQ_CAP_BPS;
     const size_t need = (size_t)(*blocks_per_sm < 1 ? 1 : *blocks_per_sm) * (smem + 1024);
     int pct = (int)((need * 100 + 233472 - 1) / 233472);
     pct = pct > 100 ? 100 : pct;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, 32 * VKQ_WARPS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, 32 * VKQ_WARPS, smem);
+    if (VKQ_CAP_BPS && *blocks_per_sm > VKQ_CAP_BPS) *blocks_per_sm = VKQ_CAP_BPS;
+    return e;
 }
 
 } // namespace VK_NS
