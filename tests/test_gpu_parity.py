@@ -709,7 +709,8 @@ def test_accumulation_does_not_depend_on_who_renders_what(vb, ctx):
 
 
 def test_hybrid_program_renders_the_same_image(vb, ctx, monkeypatch):
-    """The hybrid flat program (VECCHIO_HYBRID=1, off by default because it measured slower) is the same
+    """The hybrid flat program (typed batches for the mixed top of the scene, its homogeneous subtrees walked as BVHs;
+    what VK_VARIANT_WARPQ runs on such a scene, and with VECCHIO_HYBRID_ALL=1 every other kernel too) is the same
     function as the BVH: identical hits on a ray batch and a bit-identical strict-build image."""
     scene, cam = get_scene(vb, "final_scene")
     ctx.upload(scene)
@@ -717,16 +718,17 @@ def test_hybrid_program_renders_the_same_image(vb, ctx, monkeypatch):
     a, _, sa = ctx.render(cam, p)
     rays = camera_rays(cam, 20000, np.random.default_rng(3))
     ha = ctx.intersect(rays, flags=vb.VK_FLAG_STRICT_MATH)
-    monkeypatch.setenv("VECCHIO_HYBRID", "1")
-    ctx.upload(scene)
-    b, _, sb = ctx.render(cam, p)
+    pw = vb.render_params(64, 64, 16, 50, seed=5, flags=vb.VK_FLAG_STRICT_MATH, variant=vb.VK_VARIANT_WARPQ)
+    w, _, sw = ctx.render(cam, pw)  # k_warpq_hybrid
+    monkeypatch.setenv("VECCHIO_HYBRID_ALL", "1")
+    b, _, sb = ctx.render(cam, p)  # the lane megakernel over the hybrid program
     hb = ctx.intersect(rays, flags=vb.VK_FLAG_STRICT_MATH)
-    monkeypatch.delenv("VECCHIO_HYBRID")
-    ctx.upload(scene)
-    assert sb.node_visits < sa.node_visits  # the flat top replaces the upper nodes
+    monkeypatch.delenv("VECCHIO_HYBRID_ALL")
+    assert sb.node_visits < sa.node_visits and sw.node_visits < sa.node_visits  # the flat top replaces the upper nodes
     same = ha["prim"] == hb["prim"]
     assert same.mean() >= 0.999 and np.array_equal(ha["t"][same], hb["t"][same])  # exact ties may resolve differently
     assert np.array_equal(a, b) or np.isclose(a, b, rtol=1e-5, atol=1e-6).mean() > 0.999
+    assert sw.variant == vb.VK_VARIANT_WARPQ and (np.array_equal(a, w) or np.isclose(a, w, rtol=1e-5, atol=1e-6).mean() > 0.999)
 
 
 @pytest.mark.parametrize("name", ["cornell_box", "final_scene", "random_spheres_demo"])

@@ -154,23 +154,26 @@ def test_scene_check_plans_every_shipped_scene(vb):
     for name, (flat, simple, dyn) in want.items():
         s, _ = get_scene(vb, name)
         info = vb.scene_check(s.desc_ptr)
-        assert (info["flat_entries"] > 0, bool(info["simple"]), bool(info["dynamic_megakernel"])) == (flat, simple, dyn), (name, info)
+        whole = info["flat_entries"] > 0 and info["flat_subtrees"] == 0  # (a hybrid program keeps subtrees: still a BVH scene)
+        assert (whole, bool(info["simple"]), bool(info["dynamic_megakernel"])) == (flat, simple, dyn), (name, info)
         assert info["stack_need"] <= 96 and info["wide_nodes"] >= 1
     c = vb.scene_check(get_scene(vb, "cornell_box")[0].desc_ptr)
     # 6 world rects (5 walls + the flipped light) + 6 box sides + 1 sphere, in the world frame + one instance frame
     assert (c["flat_entries"], c["flat_segments"]) == (13, 2)
     f = vb.scene_check(get_scene(vb, "final_scene")[0].desc_ptr)
-    assert f["flat_subtrees"] == 0  # the hybrid program (VECCHIO_HYBRID=1) is off by default: measured slower
+    assert f["flat_subtrees"] == 2  # the hybrid program: what VK_VARIANT_WARPQ runs on this scene (AUTO keeps the lane megakernel)
     # 13 + 511 + 1023 binary nodes collapse into far fewer 4-wide nodes; two BVH levels (world, instanced spheres)
     assert f["wide_nodes"] < (13 + 511 + 1023) * 0.6 and f["wide_levels_instance"] >= 4
 
 
 def test_hybrid_program_plan(vb, monkeypatch):
-    """VECCHIO_HYBRID=1: the mixed top of a heterogeneous scene as typed entries, its homogeneous subtrees as BVH entries."""
-    monkeypatch.setenv("VECCHIO_HYBRID", "1")
+    """The mixed top of a heterogeneous scene as typed entries, its homogeneous subtrees as BVH entries; VECCHIO_HYBRID=0 turns it off."""
     f = vb.scene_check(get_scene(vb, "final_scene")[0].desc_ptr)
     # the 9 loose objects, plus the box field and the instanced sphere cluster as subtrees, in two frames
     assert (f["flat_entries"], f["flat_segments"], f["flat_subtrees"]) == (11, 2, 2)
+    monkeypatch.setenv("VECCHIO_HYBRID", "0")
+    f = vb.scene_check(get_scene(vb, "final_scene")[0].desc_ptr)
+    assert (f["flat_entries"], f["flat_subtrees"]) == (0, 0)
 
 
 def test_scene_check_big_bvh_selects_the_dynamic_megakernel(vb):

@@ -315,6 +315,7 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     UP(boxes, float4, d->boxes, (size_t)d->n_boxes * 2)
     UP(xforms, float4, d->xforms, (size_t)d->n_xforms * 2)
     UP(media, float4, d->media, d->n_media)
+    UP(media_plan, float4, R.media_plan.data(), R.media_plan.size())
     UP(lights, uint32_t, d->lights, d->n_lights)
     UP(materials, uint4, mats.data(), d->n_materials)
     UP(textures, uint4, d->textures, d->n_textures)
@@ -504,6 +505,11 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     const FlatProgram* flat = (c->flat.n && !(P->flags & VK_FLAG_FORCE_BVH)) ? &c->flat : nullptr;
     int bps = 0, bt = 0;
     const bool legacy = (P->flags & VK_FLAG_LEGACY_SCATTER) != 0;
+    uint32_t variant = choose_variant(c, P);
+    if (legacy && variant != VK_VARIANT_WARPQ && variant != VK_VARIANT_STEPQ) variant = VK_VARIANT_MEGAKERNEL; // legacy integrator: lane megakernel and warp queues
+    // a hybrid program (flat top + homogeneous subtrees) is the warp-queue kernel's: every other variant walks the BVH
+    // (lane megakernel on it: 51.5 against 46.1 ms on the final scene, profiles/r2_sweep_12.log)
+    if (flat && flat->n_bvh && variant != VK_VARIANT_WARPQ && !std::getenv("VECCHIO_HYBRID_ALL")) flat = nullptr;
     if (legacy && c->has_specdiffuse)
         return fail(c, VK_ERR_UNSUPPORTED, "render: SpecDiffuse has no legacy scatter (the reference's default unwraps a missing specular ray and panics, src/material.rs:21-28)");
     if (!legacy && c->scene.n_lights == 0)
@@ -552,8 +558,6 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     CU(c, cudaEventRecord(c->ev0, c->stream));
     const DCamera dc = to_dcam(cam);
     uint32_t launches = 0;
-    uint32_t variant = choose_variant(c, P);
-    if (legacy && variant != VK_VARIANT_WARPQ && variant != VK_VARIANT_STEPQ) variant = VK_VARIANT_MEGAKERNEL; // legacy integrator: lane megakernel and warp queues
     if (variant == VK_VARIANT_STEPQ && flat && flat->n_bvh == 0) variant = VK_VARIANT_WARPQ; // step queues are the BVH traversal; a flat program has none
     if (variant == VK_VARIANT_STEPQ) {
         const bool inst = c->levels_sub != 0u;
@@ -572,9 +576,9 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     } else if (variant == VK_VARIANT_WARPQ) {
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
         CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(unsigned long long), c->stream)); // self-check violations (debug builds)
-        // (the K-ray flat trace has no subtree entries: a hybrid program means the BVH path)
-        const FlatProgram* sflat = flat && flat->n_bvh == 0 ? flat : nullptr;
-        const bool simple = !strict && !legacy && sflat && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");
+        // (a hybrid program -- flat top, homogeneous subtrees walked inside extend -- runs k_warpq_hybrid)
+        const FlatProgram* sflat = flat;
+        const bool simple = !strict && !legacy && sflat && sflat->n_bvh == 0 && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");
         CU(c, strict   ? vkstrict::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream)
               : simple ? vkfast_simple::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream)
                        : vkfast::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream));
@@ -753,7 +757,7 @@ int vk_intersect(vk_ctx* c, const vk_ray* rays, size_t n, const float* medium_xi
         STEP(cudaMemcpyAsync(d_xi, medium_xi, n * VK_MEDIUM_XI_SLOTS * sizeof(float), cudaMemcpyHostToDevice, c->stream))
     }
     STEP(cudaMemcpyAsync(d_rays, rays, n * sizeof(vk_ray), cudaMemcpyHostToDevice, c->stream))
-    const FlatProgram* flat = (c->flat.n && !(flags & VK_FLAG_FORCE_BVH)) ? &c->flat : nullptr;
+    const FlatProgram* flat = (c->flat.n && (c->flat.n_bvh == 0 || std::getenv("VECCHIO_HYBRID_ALL")) && !(flags & VK_FLAG_FORCE_BVH)) ? &c->flat : nullptr;
     STEP((flags & VK_FLAG_STRICT_MATH) ? vkstrict::launch_intersect(c->scene, flat, d_rays, n, d_xi, d_hits, c->stream)
                                        : vkfast::launch_intersect(c->scene, flat, d_rays, n, d_xi, d_hits, c->stream))
     STEP(cudaMemcpyAsync(out, d_hits, n * sizeof(vk_hit), cudaMemcpyDeviceToHost, c->stream))

@@ -380,20 +380,79 @@ static __device__ __noinline__ bool medium_t(const DScene& sc, uint32_t ref, flo
                                       const MediumXi xi, float& t) {
     const float4 m = __ldg(&sc.media[VKD_INDEX(ref)]);
     float3 bo = o, bd = d;
+    float t1 = 0.0f, t2 = 0.0f;
+#if VK_STRICT
     const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
     const float3 binv = rcp3(bd);
-    float t1 = 0.0f, t2 = 0.0f;
-    uint32_t face;
-    float lo = -CUDART_INF_F;
+#else
+    // Render build: the boundary's wrapper chain is one affine map composed at upload (Relayout::media_plan), and for a
+    // box or sphere boundary BOTH queries -- rec1 = boundary.hit(-inf, inf), rec2 = boundary.hit(rec1.t + 0.0001, inf)
+    // -- come from ONE evaluation of the slabs / the quadratic: the two calls compute the same six plane distances (the
+    // same two roots) and differ only in which of them their window accepts, so the window logic is replayed on shared
+    // values.  Same arithmetic as box_t / sphere_t, same results as calling them twice.
+    const float4* mp = sc.media_plan + 4u * VKD_INDEX(ref);
+    const float4 mp3 = __ldg(mp + 3);
+    const uint32_t b = __float_as_uint(mp3.x);
+    if (__float_as_uint(mp3.y)) {
+        const float4 r0 = __ldg(mp), r1 = __ldg(mp + 1), r2 = __ldg(mp + 2);
+        bo = f3(fmaf(r0.x, o.x, fmaf(r0.y, o.y, fmaf(r0.z, o.z, r0.w))), fmaf(r1.x, o.x, fmaf(r1.y, o.y, fmaf(r1.z, o.z, r1.w))),
+                fmaf(r2.x, o.x, fmaf(r2.y, o.y, fmaf(r2.z, o.z, r2.w))));
+        bd = f3(fmaf(r0.x, d.x, fmaf(r0.y, d.y, r0.z * d.z)), fmaf(r1.x, d.x, fmaf(r1.y, d.y, r1.z * d.z)),
+                fmaf(r2.x, d.x, fmaf(r2.y, d.y, r2.z * d.z)));
+    }
+    const float3 binv = rcp3(bd);
+    bool spanned = false;
+    if (VKD_TYPE(b) == VK_T_BOX) {
+        const float4 b0 = __ldg(&sc.boxes[2 * VKD_INDEX(b)]), b1 = __ldg(&sc.boxes[2 * VKD_INDEX(b) + 1]);
+        const float3 oi = f3(-bo.x * binv.x, -bo.y * binv.y, -bo.z * binv.z);
+        const float x0 = fmaf(b0.x, binv.x, oi.x), x1 = fmaf(b1.x, binv.x, oi.x);
+        const float y0 = fmaf(b0.y, binv.y, oi.y), y1 = fmaf(b1.y, binv.y, oi.y);
+        const float z0 = fmaf(b0.z, binv.z, oi.z), z1 = fmaf(b1.z, binv.z, oi.z);
+        const float t_near = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+        const float t_far = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+        if (!(t_near <= t_far)) return false;
+        // box_t(tmin, tmax = inf): t = (t_near >= tmin) ? t_near : t_far, accepted when tmin <= t < inf
+        t1 = (t_near >= -CUDART_INF_F) ? t_near : t_far;
+        if (!(t1 >= -CUDART_INF_F && t1 < CUDART_INF_F)) return false;
+        const float lo = t1 + 0.0001f;
+        t2 = (t_near >= lo) ? t_near : t_far;
+        if (!(t2 >= lo && t2 < CUDART_INF_F)) return false;
+        spanned = true;
+    } else if (VKD_TYPE(b) == VK_T_SPHERE) {
+        const float4 sp = __ldg(&sc.spheres[VKD_INDEX(b)]);
+        const float3 oc = bo - f3(sp);
+        const float a = dot3_rn(bd, bd);
+        const float half_b = dot3_rn(oc, bd);
+        const float cc = __fadd_rn(dot3_rn(oc, oc), -__fmul_rn(sp.w, sp.w));
+        const float disc = __fadd_rn(__fmul_rn(half_b, half_b), -__fmul_rn(a, cc));
+        if (!(disc > 0.0f)) return false;
+        const float root = sqrtf(disc);
+        const float ra = (-half_b - root) / a, rb = (-half_b + root) / a;
+        // sphere_t(tmin, tmax = inf): the near root if tmin < it < inf, else the far root under the same test
+        if (-CUDART_INF_F < ra && ra < CUDART_INF_F) t1 = ra;
+        else if (-CUDART_INF_F < rb && rb < CUDART_INF_F) t1 = rb;
+        else return false;
+        const float lo = t1 + 0.0001f;
+        if (lo < ra && ra < CUDART_INF_F) t2 = ra;
+        else if (lo < rb && rb < CUDART_INF_F) t2 = rb;
+        else return false;
+        spanned = true;
+    }
+    if (!spanned)
+#endif
+    {
+        uint32_t face;
+        float lo = -CUDART_INF_F;
 #pragma unroll 1
-    for (int q = 0; q < 2; ++q) { // rec1 = boundary.hit(-inf, inf); rec2 = boundary.hit(rec1.t + 0.0001, inf)
-        float tq;
-        if (!leaf_t(sc, b, bo, bd, binv, time, lo, CUDART_INF_F, tq, face)) return false;
-        if (q == 0) {
-            t1 = tq;
-            lo = tq + 0.0001f;
-        } else
-            t2 = tq;
+        for (int q = 0; q < 2; ++q) { // rec1 = boundary.hit(-inf, inf); rec2 = boundary.hit(rec1.t + 0.0001, inf)
+            float tq;
+            if (!leaf_t(sc, b, bo, bd, binv, time, lo, CUDART_INF_F, tq, face)) return false;
+            if (q == 0) {
+                t1 = tq;
+                lo = tq + 0.0001f;
+            } else
+                t2 = tq;
+        }
     }
     if (t1 < tmin) t1 = tmin;
     if (t2 > tmax) t2 = tmax;
@@ -782,10 +841,14 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
 // K rays per thread through the flat program (the staged kernel traces all the slots a thread owns
 // together): an entry's operands are fetched once for the K rays and the K closest-hit chains are
 // independent, which is the instruction-level parallelism a warp-per-SM-quarter schedule lacks.
+#ifndef VKF_RECT_UNROLL
+#define VKF_RECT_UNROLL 1
+#endif
+constexpr int kFlatRectUnroll = VKF_RECT_UNROLL;
 template <int K, int AX, bool BOX_SIDE>
 VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const float3 (&co)[K], const float3 (&cd)[K], const float3 (&ci)[K],
                       float tmin, float (&best_t)[K], uint32_t (&best_hit)[K]) {
-#pragma unroll 1
+#pragma unroll kFlatRectUnroll
     for (uint32_t i = i0; i < i1; ++i) {
         const float4 bd = P.rects[i].bounds;
         const float k = P.rects[i].k;
@@ -811,7 +874,9 @@ VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const floa
             // |a - centre| <= half extent.  0.6 % faster, but a ray that STARTS on the plane -- every scattered ray --
             // no longer gets t = 0 exactly: the two products cancel to rounding noise of either sign, scaled by 1/d.
             // Dropped samples rose from 26 to 1503 per 3.6e8 paths and light leaked around the box.)
-            bool miss = (tt < tmin) | (tt > best_t[q]) | (a < bd.x) | (a > bd.y) | (b < bd.z) | (b > bd.w);
+            // (the comparison with the closest hit so far comes last: it is the only link between one entry and the next)
+            bool miss = (a < bd.x) | (a > bd.y) | (b < bd.z) | (b > bd.w) | (tt < tmin);
+            miss = miss | (tt > best_t[q]);
             if (BOX_SIDE) miss = miss | !(tt < best_t[q]);
             best_t[q] = miss ? best_t[q] : tt;
             best_hit[q] = miss ? best_hit[q] : id;
@@ -820,9 +885,12 @@ VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const floa
 }
 // `live` masks the rays that exist (an idle slot's ray is traced as a dummy and ignored); out_hit
 // is the index into P.hits or 0xFFFFFFFF.
-template <int K, bool MEDIA>
+// HYBRID: the program may hold homogeneous subtrees (FlatProgram::bvh); a ray whose closest hit came from one gets
+// best_hit = 0xFFFFFFFE and the hit itself in sub[] (as in trace_flat).
+template <int K, bool MEDIA, bool HYBRID = false>
 VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[K], const float3 (&d)[K], const float (&time)[K],
-                      const bool (&live)[K], float tmin, const MediumXi (&xi)[K], float (&best_t)[K], uint32_t (&best_hit)[K]) {
+                      const bool (&live)[K], float tmin, const MediumXi (&xi)[K], float (&best_t)[K], uint32_t (&best_hit)[K],
+                      TraceHit* sub = nullptr, TraceCounters* tc = nullptr) {
 #pragma unroll
     for (int q = 0; q < K; ++q) {
         best_t[q] = CUDART_INF_F;
@@ -914,6 +982,38 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
                     if (live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt)) {
                         best_t[q] = tt;
                         best_hit[q] = i;
+                    }
+                }
+            }
+        }
+        if (HYBRID) { // homogeneous subtrees: every lane walks the 4-wide nodes for its own ray, in this segment's frame
+#pragma unroll 1
+            for (uint32_t i = g.bvh0; i < g.bvh1; ++i) {
+#pragma unroll
+                for (int q = 0; q < K; ++q) {
+                    Trav T;
+                    T.sp = 0;
+                    T.co = co[q];
+                    T.cd = cd[q];
+                    T.cinv = ci[q];
+                    T.cur_inst = P.seg_inst[s];
+                    T.best.t = best_t[q];
+                    T.best.prim = VK_REF_NONE;
+                    T.best.inst = 0;
+                    T.best.face = 0;
+                    T.ref = live[q] ? P.bvh[i] : VKD_DONE;
+                    T.enter = true;
+#pragma unroll 1
+                    for (;;) {
+#pragma unroll 1
+                        while (trav_at_node(T)) trav_node_step(T, sc, tmin, *tc);
+                        if (T.ref == VKD_DONE) break;
+                        trav_prim_step<false>(T, sc, o[q], d[q], time[q], tmin, xi[q], *tc); // leaves only: no wrapper, no medium below
+                    }
+                    if (T.best.prim != VK_REF_NONE) {
+                        best_t[q] = T.best.t;
+                        sub[q] = T.best;
+                        best_hit[q] = 0xFFFFFFFEu;
                     }
                 }
             }

@@ -39,6 +39,7 @@ struct DScene {
     const float4* boxes;    // 2 x float4: {min.xyz, mat}, {max.xyz, -}
     const float4* xforms;   // 2 x float4: {kind, child, -, -}, {a, b, c, -}
     const float4* media;    // {boundary, neg_inv_density, mat, -}
+    const float4* media_plan; // 4 x float4 per medium: the boundary's wrapper chain as one affine map + its leaf (Relayout::media_plan)
     const uint32_t* lights;
     const uint4* materials; // {type, tex, param, aux | needs_uv << 31}
     const uint4* textures;

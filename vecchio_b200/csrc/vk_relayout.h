@@ -212,6 +212,51 @@ struct Validator {
 
 // Unroll the reference's traversal into the typed batches of FlatProgram; false if the scene does not
 // fit (then the BVH is traversed).
+// A chain of wrapper ops (outermost first) composed into one affine map, object = R * world + t, in double.
+// The reference applies the wrappers one after the other (src/hittable.rs:508, :591-595, :680-684, :769-773); composing
+// them changes the rounding only, so only the render build uses the result.  out[0..8] = rows of R, out[9..11] = t.
+inline void compose_flat_ops(const FlatOp* ops, size_t n, float* out) {
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3] = {0, 0, 0};
+    for (size_t k = 0; k < n; ++k) {
+        const FlatOp& op = ops[k];
+        if (op.kind == VKF_OP_TRANSLATE) { // subtracts its offset from the point in the frame reached so far
+            t[0] -= op.a; t[1] -= op.b; t[2] -= op.c;
+            continue;
+        }
+        // world -> object rotations of rot_fwd (vk_device.cuh): Y: x' = c x - s z, z' = s x + c z;
+        // X: y' = c y + s z, z' = -s y + c z;  Z: x' = c x + s y, y' = -s x + c y
+        const double sn = op.a, cs = op.b;
+        double M[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        if (op.kind == VKF_OP_ROTY) { M[0][0] = cs; M[0][2] = -sn; M[2][0] = sn; M[2][2] = cs; }
+        else if (op.kind == VKF_OP_ROTX) { M[1][1] = cs; M[1][2] = sn; M[2][1] = -sn; M[2][2] = cs; }
+        else { M[0][0] = cs; M[0][1] = sn; M[1][0] = -sn; M[1][1] = cs; }
+        double R2[3][3], t2[3];
+        for (int i = 0; i < 3; ++i) {
+            t2[i] = M[i][0] * t[0] + M[i][1] * t[1] + M[i][2] * t[2];
+            for (int j = 0; j < 3; ++j) R2[i][j] = M[i][0] * R[0][j] + M[i][1] * R[1][j] + M[i][2] * R[2][j];
+        }
+        for (int i = 0; i < 3; ++i) {
+            t[i] = t2[i];
+            for (int j = 0; j < 3; ++j) R[i][j] = R2[i][j];
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) out[3 * i + j] = (float)R[i][j];
+        out[9 + i] = (float)t[i];
+    }
+}
+// the ops of a wrapper chain, outermost first (FlipFace leaves the ray alone); returns the first non-wrapper child
+inline vk_ref chain_ops(const vk_scene_desc* d, vk_ref r, std::vector<FlatOp>& ops) {
+    while (VK_REF_TYPE(r) == VK_T_XFORM) {
+        const vk_xform& x = d->xforms[VK_REF_INDEX(r)];
+        if (x.kind == VK_X_TRANSLATE) ops.push_back(FlatOp{VKF_OP_TRANSLATE, x.a, x.b, x.c});
+        else if (x.kind != VK_X_FLIP)
+            ops.push_back(FlatOp{x.kind == VK_X_ROTATE_X ? (uint32_t)VKF_OP_ROTX : (x.kind == VK_X_ROTATE_Y ? (uint32_t)VKF_OP_ROTY : (uint32_t)VKF_OP_ROTZ), x.a, x.b, 0.f});
+        r = x.child;
+    }
+    return r;
+}
+
 struct FlatBuilder {
     const vk_scene_desc* d;
     struct Seg {
@@ -325,14 +370,7 @@ struct FlatBuilder {
             if (si != 0) return false; // nested instances are refused by the validator anyway
             Seg g;
             g.inst = ref; // instance id = outermost wrapper
-            vk_ref r = ref;
-            while (VK_REF_TYPE(r) == VK_T_XFORM) {
-                const vk_xform& x = d->xforms[VK_REF_INDEX(r)];
-                if (x.kind == VK_X_TRANSLATE) g.ops.push_back(FlatOp{VKF_OP_TRANSLATE, x.a, x.b, x.c});
-                else if (x.kind != VK_X_FLIP) // FlipFace leaves the ray alone; the flip happens in resolve_hit
-                    g.ops.push_back(FlatOp{x.kind == VK_X_ROTATE_X ? (uint32_t)VKF_OP_ROTX : (x.kind == VK_X_ROTATE_Y ? (uint32_t)VKF_OP_ROTY : (uint32_t)VKF_OP_ROTZ), x.a, x.b, 0.f});
-                r = x.child;
-            }
+            const vk_ref r = chain_ops(d, ref, g.ops); // (FlipFace leaves the ray alone; the flip happens in resolve_hit)
             segs.push_back(std::move(g));
             return emit(r, segs.size() - 1, dup);
         }
@@ -401,36 +439,7 @@ struct FlatBuilder {
             for (uint32_t r : g.bvh) P->bvh[n_bvh++] = r;
             o.bvh1 = (uint8_t)n_bvh;
             P->seg_inst[s] = g.inst;
-            {   // compose the ops (outermost first) into object = R * world + t, in double
-                double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3] = {0, 0, 0};
-                for (const FlatOp& op : g.ops) {
-                    if (op.kind == VKF_OP_TRANSLATE) {
-                        t[0] -= op.a; t[1] -= op.b; t[2] -= op.c; // o - offset ... but in the CURRENT frame: see below
-                        continue;
-                    }
-                    // world -> object rotations of rot_fwd (vk_device.cuh): Y: x' = c x - s z, z' = s x + c z;
-                    // X: y' = c y + s z, z' = -s y + c z;  Z: x' = c x + s y, y' = -s x + c y
-                    const double sn = op.a, cs = op.b;
-                    double M[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-                    if (op.kind == VKF_OP_ROTY) { M[0][0] = cs; M[0][2] = -sn; M[2][0] = sn; M[2][2] = cs; }
-                    else if (op.kind == VKF_OP_ROTX) { M[1][1] = cs; M[1][2] = sn; M[2][1] = -sn; M[2][2] = cs; }
-                    else { M[0][0] = cs; M[0][1] = sn; M[1][0] = -sn; M[1][1] = cs; }
-                    double R2[3][3], t2[3];
-                    for (int i = 0; i < 3; ++i) {
-                        t2[i] = M[i][0] * t[0] + M[i][1] * t[1] + M[i][2] * t[2];
-                        for (int j = 0; j < 3; ++j) R2[i][j] = M[i][0] * R[0][j] + M[i][1] * R[1][j] + M[i][2] * R[2][j];
-                    }
-                    for (int i = 0; i < 3; ++i) {
-                        t[i] = t2[i];
-                        for (int j = 0; j < 3; ++j) R[i][j] = R2[i][j];
-                    }
-                }
-                // (a translate subtracts its offset from the point in the frame reached so far, which is exactly t -= offset)
-                for (int i = 0; i < 3; ++i) {
-                    for (int j = 0; j < 3; ++j) P->seg_affine[s][3 * i + j] = (float)R[i][j];
-                    P->seg_affine[s][9 + i] = (float)t[i];
-                }
-            }
+            compose_flat_ops(g.ops.data(), g.ops.size(), P->seg_affine[s]);
         }
         P->n_bvh = n_bvh;
         for (uint32_t h = 0; h < n_hits; ++h) { // shading class of each entry's material
@@ -472,6 +481,9 @@ struct Relayout {
     // what leaves the Translate is +-(the rotated axis), turned against the WORLD ray -- whatever the levels below
     // did.  `front` of a plain rect is dot(d, n) < 0, flipped by FlipFace (:300-308).
     std::vector<float4> flat_shade;
+    // Per ConstantMedium, for the render build's medium_t: 4 x float4 = the three rows {R | t} of the boundary's wrapper
+    // chain composed into one affine map, then {boundary leaf, chain present, -, -}.
+    std::vector<float4> media_plan;
     // returns nullptr or the reason the scene is unsupported
     const char* run(const vk_scene_desc* d) {
     // GPU-side re-layout of the node array: a single-object leaf (left == right) is tested twice
@@ -574,7 +586,17 @@ struct Relayout {
             // against 50.0 ms for the plain 4-wide BVH -- the flat top tests all nine loose objects (two
             // media included) for every ray where the BVH culls some, and the subtree traversals keep their
             // divergence.  VECCHIO_HYBRID=1 enables it (parity-tested: same image bit for bit).
-            if (!(heterogeneous && std::getenv("VECCHIO_HYBRID") && fb.build(&flat, true) && flat.n_bvh > 0)) flat = FlatProgram{};
+            const char* hy = std::getenv("VECCHIO_HYBRID");
+            if (!(heterogeneous && !(hy && hy[0] == '0') && fb.build(&flat, true) && flat.n_bvh > 0)) flat = FlatProgram{};
+        }
+        media_plan.assign(4 * (size_t)d->n_media, make_float4(0, 0, 0, 0));
+        for (uint32_t i = 0; i < d->n_media; ++i) {
+            std::vector<FlatOp> ops;
+            const vk_ref leaf = chain_ops(d, d->media[i].boundary, ops);
+            float m[12];
+            compose_flat_ops(ops.data(), ops.size(), m);
+            for (int r = 0; r < 3; ++r) media_plan[4 * i + r] = make_float4(m[3 * r], m[3 * r + 1], m[3 * r + 2], m[9 + r]);
+            media_plan[4 * i + 3] = make_float4(__uint_as_float_host(leaf), __uint_as_float_host(ops.empty() ? 0u : 1u), 0.f, 0.f);
         }
         flat_shade.clear();
         if (flat.n && flat.n_bvh == 0) {

@@ -30,14 +30,19 @@
 namespace VK_NS {
 
 // ---- flat scenes: extend = K rays per lane through the flat program, one queue batch at a time ----------------------
-template <bool MEDIA, bool LEGACY, class W, int K>
+// HYBRID: the program's homogeneous subtrees (FlatProgram::bvh: the final scene's box field and its instanced sphere
+// cluster) are traversed inside the extend stage, every lane for its own ray; what differs between the lanes of a batch is
+// then only how long a walk through ONE kind of tree takes -- the heterogeneous top of the scene (loose spheres, media,
+// rects) is typed batches, and the shading runs on whole batches of a class.
+template <bool MEDIA, bool LEGACY, class W, int K, bool HYBRID = false>
 VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& buf,
                          unsigned long long* unit_head) {
     extern __shared__ __align__(16) unsigned char vkq_raw[];
     const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
     W& S = reinterpret_cast<W*>(vkq_raw)[threadIdx.x >> 5];
-    const WqCtx<W> C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
+    const WqCtx<W> C = wq_ctx(cam, a, S, unit_head, lane);
     uint32_t n_rays = 0, n_drop = 0, n_prims = 0;
+    TraceCounters tc = {0u, 0u};
     constexpr uint32_t EXT_CAP = 32u * K;
     // a miss under the constant black background of src/main.rs:124 adds nothing: the slot goes straight to regeneration
     const uint32_t miss_cls = wq_black_miss(a) ? (uint32_t)VKQ_END : (uint32_t)VKQ_EMIT;
@@ -49,7 +54,7 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
         if (!wq_pick(S, wq_counts(S), EXT_CAP, q, n_q, tail_q)) break; // every queue is empty: all slots have retired
         const uint32_t n = wq_pop(S, q, n_q, tail_q, q == VKQ_EXT ? EXT_CAP : 32u, lane, head);
         if (q != VKQ_EXT) {
-            wq_shade_batch<LEGACY, true>(sc, C, buf, q, n, head, n_drop);
+            wq_shade_batch<LEGACY, !HYBRID>(sc, C, buf, q, n, head, n_drop); // (no shading records for subtree hits)
             continue;
         }
         // ---- extend: world.hit() (src/main.rs:130) for up to EXT_CAP rays, K per lane --------------------------------
@@ -74,7 +79,8 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
             xi[k].rng.pixel = MEDIA ? S.px[slot[k]] : 0u;
             xi[k].rng.sample = MEDIA ? __float_as_uint(S.bt[slot[k]].w) : 0u;
         }
-        trace_flat_k<K, MEDIA>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit);
+        TraceHit sub[K];
+        trace_flat_k<K, MEDIA, HYBRID>(sc, *flat, o, d, tm, live, 0.001f, xi, best_t, best_hit, sub, &tc);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             uint32_t cls = VKQ_NONE;
@@ -83,7 +89,11 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
                 n_prims += flat->n;
                 uint32_t prim = VK_REF_NONE, hi = 0u;
                 cls = miss_cls; // a miss ends the sample like an emitter does
-                if (best_hit[k] != 0xFFFFFFFFu) {
+                if (HYBRID && best_hit[k] == 0xFFFFFFFEu) { // the closest hit came from a subtree
+                    prim = sub[k].prim;
+                    hi = (sub[k].inst ? (0x80000000u | VKD_INDEX(sub[k].inst)) : 0u) | (sub[k].face << 28);
+                    cls = wq_class_of(sc, prim, sub[k].inst);
+                } else if (best_hit[k] != 0xFFFFFFFFu) {
                     const FlatHit& fh = flat->hits[best_hit[k]];
                     prim = fh.prim & ~VKD_DUP;
                     const uint32_t inst = fh.inst;
@@ -95,7 +105,7 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
             if (k == 0 || n > 32u * k) wq_push(S, cls, slot[k], lane, below); // (warp-uniform condition)
         }
     }
-    wq_flush_counters(buf, lane, n_rays, n_drop, 0u, n_prims);
+    wq_flush_counters(buf, lane, n_rays, n_drop, tc.nodes, n_prims + tc.prims);
 }
 
 // ---- BVH scenes: extend = the resumable traversal (Trav, vk_device.cuh) with dynamic fetch ------------------------------
@@ -119,7 +129,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
     extern __shared__ __align__(16) unsigned char vkq_raw[];
     const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
     W& S = reinterpret_cast<W*>(vkq_raw)[threadIdx.x >> 5];
-    const WqCtx<W> C = {cam, a, S, a.width * a.height, (unsigned long long)(a.width * a.height) * a.spp_count, unit_head, lane, below};
+    const WqCtx<W> C = wq_ctx(cam, a, S, unit_head, lane);
     uint32_t n_rays = 0, n_drop = 0;
     TraceCounters tc = {0u, 0u};
     const uint32_t miss_cls = wq_black_miss(a) ? (uint32_t)VKQ_END : (uint32_t)VKQ_EMIT;
@@ -208,6 +218,7 @@ VKD void warpq_bvh_body(const DScene& sc, const DCamera& cam, const RenderArgs& 
 using WqFlat = WqWarp<VKQ_N_FLAT, VKQ_RN_FLAT>;
 using WqMedia = WqWarp<VKQ_N_MEDIA, VKQ_RN_MEDIA>;
 using WqBvh = WqWarp<VKQ_N_BVH, VKQ_RN_BVH>;
+using WqHyb = WqWarp<VKQ_N_HYB, VKQ_RN_HYB>;
 static_assert(VKQ_WARPS <= 15, "one named barrier per warp of the CTA");
 
 template <bool MEDIA, bool LEGACY>
@@ -226,7 +237,13 @@ __global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB_MEDIA) k_warpq_flat_m
                                                                                  unsigned long long* unit_head) {
     warpq_flat_body<true, LEGACY, WqMedia, VKQ_K_MEDIA>(sc, &flat, cam, a, buf, unit_head);
 }
-
+#if !VK_SIMPLE
+template <bool MEDIA, bool LEGACY>
+__global__ void __launch_bounds__(32 * VKQ_WARPS, VKQ_MINB_HYB) k_warpq_hybrid(const DScene sc, const __grid_constant__ FlatProgram flat, const DCamera cam,
+                                                                            const RenderArgs a, const RenderBuffers buf, unsigned long long* unit_head) {
+    warpq_flat_body<MEDIA, LEGACY, WqHyb, 1, true>(sc, &flat, cam, a, buf, unit_head);
+}
+#endif
 
 // grid = sm_count * resident CTAs (persistent); *unit_head must be zero on the stream before the launch
 cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
@@ -250,7 +267,12 @@ cudaError_t launch_warpq(const DScene& sc, const FlatProgram* flat, const DCamer
     (void)legacy; // the trimmed build exists for the HEAD integrator on flat scenes only
     if (media) VKQ_LAUNCH_FLAT(k_warpq_flat_media<false>, WqMedia) else VKQ_LAUNCH_FLAT(k_warpq_flat<false>, WqFlat)
 #else
-    if (flat && flat->n) {
+    if (flat && flat->n && flat->n_bvh) {
+#define VKQ_LAUNCH_HYB(M, G) VKQ_LAUNCH_FLAT((k_warpq_hybrid<M, G>), WqHyb)
+        if (media) { if (legacy) VKQ_LAUNCH_HYB(true, true) else VKQ_LAUNCH_HYB(true, false) }
+        else { if (legacy) VKQ_LAUNCH_HYB(false, true) else VKQ_LAUNCH_HYB(false, false) }
+#undef VKQ_LAUNCH_HYB
+    } else if (flat && flat->n) {
         if (media) { if (legacy) VKQ_LAUNCH_FLAT(k_warpq_flat_media<true>, WqMedia) else VKQ_LAUNCH_FLAT(k_warpq_flat_media<false>, WqMedia) }
         else { if (legacy) VKQ_LAUNCH_FLAT(k_warpq_flat<true>, WqFlat) else VKQ_LAUNCH_FLAT(k_warpq_flat<false>, WqFlat) }
     } else {

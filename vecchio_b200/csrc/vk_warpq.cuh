@@ -52,6 +52,16 @@ namespace VK_NS {
 #ifndef VKQ_MINB_BVH
 #define VKQ_MINB_BVH 6
 #endif
+// hybrid programs (flat top + homogeneous subtrees walked inside extend): the BVH family's shape
+#ifndef VKQ_N_HYB
+#define VKQ_N_HYB 120
+#endif
+#ifndef VKQ_RN_HYB
+#define VKQ_RN_HYB 128
+#endif
+#ifndef VKQ_MINB_HYB
+#define VKQ_MINB_HYB 6
+#endif
 #ifndef VKQ_REGEN_MIN
 #define VKQ_REGEN_MIN 16u // ended lanes of a shade batch are regenerated at once when at least this many ended
 #endif
@@ -95,8 +105,8 @@ struct WqCtx {
     const DCamera& cam;
     const RenderArgs& a;
     W& S;
-    uint32_t n_pixels;
-    unsigned long long n_units;
+    uint32_t chunks_per_row, chunks_per_sample; // a chunk: up to VKQ_CHUNK consecutive pixels of one row of one sample
+    unsigned long long n_chunks;
     unsigned long long* unit_head;
     uint32_t lane, below;
 };
@@ -120,6 +130,10 @@ VKD void wq_push(W& S, uint32_t cls, uint32_t slot, uint32_t lane, uint32_t belo
 
 // The lanes with want == true take the warp's next units and start their camera ray (src/main.rs:187-190).
 // Returns whether this lane got one (false: the frame has no unit left, the slot retires).
+// Units are dealt in CHUNKS from one global counter: a chunk is up to VKQ_CHUNK consecutive pixels of ONE row of ONE
+// sample, so the lanes' units are (s, y, x0 + i) with nothing to wrap and nothing to divide; lane 0 splits the chunk
+// number into (sample, row, row segment) once per chunk.  Which warp renders which unit does not show in the image
+// (Philox is keyed by pixel and sample, the accumulators are integers).
 template <class W>
 VKD bool wq_regen(const WqCtx<W>& C, bool want, uint32_t slot) {
     W& S = C.S;
@@ -137,16 +151,16 @@ VKD bool wq_regen(const WqCtx<W>& C, bool want, uint32_t slot) {
             if (__any_sync(0xFFFFFFFFu, S.exhausted != 0u)) break;
             __syncwarp();
             if (C.lane == 0) {
-                const unsigned long long u0 = atomicAdd(C.unit_head, (unsigned long long)VKQ_CHUNK);
-                if (u0 >= C.n_units) S.exhausted = 1u;
+                const unsigned long long c = atomicAdd(C.unit_head, 1ull);
+                if (c >= C.n_chunks) S.exhausted = 1u;
                 else {
-                    const unsigned long long rem = C.n_units - u0;
-                    const unsigned long long sb = u0 / C.n_pixels;
-                    S.left = rem < VKQ_CHUNK ? (uint32_t)rem : VKQ_CHUNK;
-                    const uint32_t p0 = (uint32_t)(u0 - sb * C.n_pixels); // once per chunk: the per-path code divides nothing
-                    S.cur_s = (uint32_t)sb;
-                    S.cur_y = p0 / C.a.width;
-                    S.cur_x = p0 - (p0 / C.a.width) * C.a.width;
+                    const uint32_t sb = (uint32_t)(c / C.chunks_per_sample);
+                    const uint32_t r = (uint32_t)(c - (unsigned long long)sb * C.chunks_per_sample);
+                    const uint32_t row = r / C.chunks_per_row, x0 = (r - row * C.chunks_per_row) * VKQ_CHUNK;
+                    S.left = min(VKQ_CHUNK, C.a.width - x0);
+                    S.cur_s = sb;
+                    S.cur_y = row;
+                    S.cur_x = x0;
                 }
             }
             __syncwarp();
@@ -155,34 +169,15 @@ VKD bool wq_regen(const WqCtx<W>& C, bool want, uint32_t slot) {
         }
         const uint32_t take = min(need - served, left);
         const uint32_t cs = S.cur_s, cy = S.cur_y, cx = S.cur_x;
-        if (want && rank >= served && rank < served + take) { // units run row-major inside a sample (i = y*width + x)
+        if (want && rank >= served && rank < served + take) {
             x = cx + (rank - served);
             y = cy;
             s = cs;
-            while (x >= C.a.width) {
-                x -= C.a.width;
-                ++y;
-            }
-            while (y >= C.a.height) {
-                y -= C.a.height;
-                ++s;
-            }
             got = true;
         }
         __syncwarp();
         if (C.lane == 0) {
-            uint32_t nx = cx + take, ny = cy, ns = cs;
-            while (nx >= C.a.width) {
-                nx -= C.a.width;
-                ++ny;
-            }
-            while (ny >= C.a.height) {
-                ny -= C.a.height;
-                ++ns;
-            }
-            S.cur_x = nx;
-            S.cur_y = ny;
-            S.cur_s = ns;
+            S.cur_x = cx + take;
             S.left = left - take;
         }
         __syncwarp();
@@ -206,6 +201,11 @@ VKD bool wq_regen(const WqCtx<W>& C, bool want, uint32_t slot) {
     return got;
 }
 
+template <class W>
+VKD WqCtx<W> wq_ctx(const DCamera& cam, const RenderArgs& a, W& S, unsigned long long* unit_head, uint32_t lane) {
+    const uint32_t cpr = (a.width + VKQ_CHUNK - 1u) / VKQ_CHUNK;
+    return WqCtx<W>{cam, a, S, cpr, cpr * a.height, (unsigned long long)(cpr * a.height) * a.spp_count, unit_head, lane, (1u << lane) - 1u};
+}
 VKD bool wq_black_miss(const RenderArgs& a) {
     return !(a.flags & VK_FLAG_SKY_BACKGROUND) && a.background.x == 0.0f && a.background.y == 0.0f && a.background.z == 0.0f;
 }
