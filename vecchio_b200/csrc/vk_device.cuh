@@ -766,7 +766,7 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
             uint32_t bh1[1] = {best_hit};
             flat_boxes_k<1>(P, g.box0, g.box1, co1, ci1, tmin, bt1, bh1);
             best_t = bt1[0];
-            best_hit = bh1[0];
+            best_hit = bh1[0] == 0xFFFFFFFFu ? bh1[0] : VKF_HIT_INDEX(bh1[0]); // (the box entries carry class-tagged ids)
         }
 #endif
 #pragma unroll 1
@@ -841,18 +841,17 @@ VKD TraceHit trace_flat(const DScene& sc, const FlatProgram& P, float3 o, float3
 // K rays per thread through the flat program (the staged kernel traces all the slots a thread owns
 // together): an entry's operands are fetched once for the K rays and the K closest-hit chains are
 // independent, which is the instruction-level parallelism a warp-per-SM-quarter schedule lacks.
-#ifndef VKF_RECT_UNROLL
-#define VKF_RECT_UNROLL 1
-#endif
-constexpr int kFlatRectUnroll = VKF_RECT_UNROLL;
 template <int K, int AX, bool BOX_SIDE>
 VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const float3 (&co)[K], const float3 (&cd)[K], const float3 (&ci)[K],
                       float tmin, float (&best_t)[K], uint32_t (&best_hit)[K]) {
-#pragma unroll kFlatRectUnroll
+    // (unrolled by two, ptxas fetches the operands with per-thread LDC instead of uniform LDCU and the loop grows; the six
+    // compares of a ray as three independent two-compare chains joined by one PLOP3 -- depth 3 instead of 6, one more
+    // instruction -- is 1 % slower: the loop is bound by what it issues, not by the predicate chain, profiles/r2_sweep_15.log)
+#pragma unroll 1
     for (uint32_t i = i0; i < i1; ++i) {
         const float4 bd = P.rects[i].bounds;
         const float k = P.rects[i].k;
-        const uint32_t id = P.rects[i].hit;
+        const uint32_t id = P.rects[i].hitc;
 #pragma unroll
         for (int q = 0; q < K; ++q) {
             float tt, a, b;
@@ -883,8 +882,8 @@ VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const floa
         }
     }
 }
-// `live` masks the rays that exist (an idle slot's ray is traced as a dummy and ignored); out_hit
-// is the index into P.hits or 0xFFFFFFFF.
+// `live` masks the rays that exist (an idle slot's ray is traced as a dummy and ignored); best_hit
+// is 0xFFFFFFFF or the class-tagged id of the entry (VKF_HITC: index into P.hits | queue class << 8).
 // HYBRID: the program may hold homogeneous subtrees (FlatProgram::bvh); a ray whose closest hit came from one gets
 // best_hit = 0xFFFFFFFE and the hit itself in sub[] (as in trace_flat).
 template <int K, bool MEDIA, bool HYBRID = false>
@@ -950,7 +949,7 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
 #pragma unroll 1
         for (uint32_t i = g.sph0; i < g.sph1; ++i) {
             const float4 sp = P.spheres[i].a;
-            const uint32_t id = P.spheres[i].hit;
+            const uint32_t id = P.spheres[i].hitc;
 #pragma unroll
             for (int q = 0; q < K; ++q) {
                 float tt;
@@ -968,7 +967,7 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
                 float tt;
                 if (sphere_t(msphere_center(P.spheres[i].a, P.spheres[i].b, P.spheres[i].time1, time[q]), P.spheres[i].a.w, co[q], cd[q], tmin, best_t[q], tt)) {
                     best_t[q] = tt;
-                    best_hit[q] = P.spheres[i].hit;
+                    best_hit[q] = P.spheres[i].hitc;
                 }
             }
         }
@@ -981,7 +980,7 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
                     float tt;
                     if (live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt)) {
                         best_t[q] = tt;
-                        best_hit[q] = i;
+                        best_hit[q] = VKF_HITC(i, P.hits[i].cls, P.hits[i].inst);
                     }
                 }
             }

@@ -88,8 +88,9 @@ struct FlatOp { // one wrapper level, outermost first
 struct FlatRect { // Rect::hit src/hittable.rs:230-239
     float4 bounds; // c0, c1, d0, d1
     float k;
-    uint32_t hit; // index into FlatProgram::hits
-    uint32_t _pad[2];
+    uint32_t hit;  // index into FlatProgram::hits
+    uint32_t hitc; // the same index | queue class of the entry << 8 (VKF_HITC): what the K-ray trace returns
+    uint32_t _pad;
 };
 
 struct FlatSphere { // Sphere::hit :65-95 | MovingSphere::hit :154-184
@@ -97,11 +98,17 @@ struct FlatSphere { // Sphere::hit :65-95 | MovingSphere::hit :154-184
     float4 b; // moving: center1, time0
     float time1;
     uint32_t hit;
-    uint32_t _pad[2];
+    uint32_t hitc; // hit | queue class << 8
+    uint32_t _pad;
 };
+// Queue class of a hit-table entry, carried in bits 8.. of the ids the K-ray trace returns (trace_flat_k), so that the
+// warp-queue kernels file a traced ray without looking its entry up: 2 emitter, 3 dielectric, 4 metal, 5 diffuse,
+// 6 diffuse behind an instance chain (the VKQ_* queue numbers of vk_warpq.cuh, asserted there).
+#define VKF_HITC(index, cls, inst) ((uint32_t)(index) | (((cls) == 0u ? 2u : (cls) == 1u ? 3u : (cls) == 2u ? 4u : ((inst) ? 6u : 5u)) << 8))
+#define VKF_HIT_INDEX(id) ((id)&0xFFu)
 struct FlatBox { // Boxy::hit src/hittable.rs:363-365 as ONE entry (render build; the strict build tests its six sides as rects)
-    float4 mn; // box_min, .w = bits: hits[] index of side 0 (sides 0 and 1, the two XY rects, are consecutive entries)
-    float4 mx; // box_max, .w = bits: hits[] index of side 2 (XZ pair) | index of side 4 (YZ pair) << 16
+    float4 mn; // box_min, .w = bits: class-tagged id of side 0 (sides 0 and 1, the two XY rects, are consecutive entries)
+    float4 mx; // box_max, .w = bits: class-tagged id of side 2 (XZ pair) | of side 4 (YZ pair) << 16
 };
 struct FlatHit { // what the closest entry resolves to
     uint32_t prim; // leaf record (sphere / msphere / rect / box / medium [| VKD_DUP on a medium's second visit])

@@ -17,6 +17,11 @@ namespace vkhost {
 // scene validation: everything the kernels assume is checked here, and anything the GPU path does
 // not implement is refused with VK_ERR_UNSUPPORTED instead of being rendered wrongly.
 // ------------------------------------------------------------------------------------------------
+inline uint32_t __float_as_uint_host(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
 inline float __uint_as_float_host(uint32_t u) {
     float f;
     std::memcpy(&f, &u, 4);
@@ -457,6 +462,15 @@ struct FlatBuilder {
             const uint32_t t = d->materials[mat].type;
             P->hits[h].cls = t == VK_M_DIFFUSE_LIGHT ? 0u : t == VK_M_DIELECTRIC ? 1u : t == VK_M_METAL ? 2u : 3u;
         }
+        static_assert(VKF_MAX_RECTS + VKF_MAX_SPHERES + VKF_MAX_MEDIA <= 256, "class-tagged ids keep the entry in 8 bits");
+        auto tagged = [&](uint32_t h) { return VKF_HITC(h, P->hits[h].cls, P->hits[h].inst); };
+        for (uint32_t i = 0; i < n_rects; ++i) P->rects[i].hitc = tagged(P->rects[i].hit);
+        for (uint32_t i = 0; i < n_sph; ++i) P->spheres[i].hitc = tagged(P->spheres[i].hit);
+        for (uint32_t i = 0; i < n_boxes; ++i) { // (a Boxy has one material: its six sides share the class)
+            const uint32_t hz = __float_as_uint_host(P->boxes[i].mn.w), hyx = __float_as_uint_host(P->boxes[i].mx.w);
+            P->boxes[i].mn.w = __uint_as_float_host(tagged(hz));
+            P->boxes[i].mx.w = __uint_as_float_host(tagged(hyx & 0xFFFFu) | (tagged(hyx >> 16) << 16));
+        }
         P->n_segs = (uint32_t)segs.size();
         P->n = n_hits + n_bvh;
         return P->n > 0;
@@ -608,6 +622,10 @@ struct Relayout {
                 const vk_ref pr = fh.prim & ~VKD_DUP;
                 const uint32_t i = VK_REF_INDEX(pr);
                 uint32_t a2, flip, mat;
+                // every entry: {-, leaf, instance | face << 28 | has-instance << 31, -}: what the shade stage hands to resolve_hit
+                // when the HitRec cannot be written down directly (the slot only keeps the distance and the entry)
+                flat_shade[2 * h + 1] = make_float4(0.f, __uint_as_float_host(pr),
+                                                    __uint_as_float_host((fh.inst ? (0x80000000u | VKD_INDEX(fh.inst)) : 0u) | (fh.face << 28)), 0.f);
                 if (VK_REF_TYPE(pr) == VK_T_RECT) {
                     a2 = (d->rects[i].axes >> 4) & 3u;
                     flip = (d->rects[i].axes & VK_RECT_FLIP) ? 1u : 0u;
@@ -642,7 +660,7 @@ struct Relayout {
                 }
                 if (!ok) continue;
                 flat_shade[2 * h] = make_float4(n[0], n[1], n[2], __uint_as_float_host(1u | (flip << 1)));
-                flat_shade[2 * h + 1] = make_float4(__uint_as_float_host(mat), 0.f, 0.f, 0.f);
+                flat_shade[2 * h + 1].x = __uint_as_float_host(mat);
             }
         }
         has_specdiffuse = false;

@@ -222,7 +222,7 @@ VKD void staged_body(const DScene& sc, const FlatProgram* flat, const DCamera& c
                         uint32_t prim = VK_REF_NONE, hi = 0u;
                         cls = VKS_C_TERMINATE;
                         if (best_hit[q] != 0xFFFFFFFFu) {
-                            const FlatHit& fh = flat->hits[best_hit[q]];
+                            const FlatHit& fh = flat->hits[VKF_HIT_INDEX(best_hit[q])];
                             prim = fh.prim & ~VKD_DUP;
                             const uint32_t inst = fh.inst;
                             hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);

@@ -94,11 +94,16 @@ VKD void warpq_flat_body(const DScene& sc, const FlatProgram* flat, const DCamer
                     hi = (sub[k].inst ? (0x80000000u | VKD_INDEX(sub[k].inst)) : 0u) | (sub[k].face << 28);
                     cls = wq_class_of(sc, prim, sub[k].inst);
                 } else if (best_hit[k] != 0xFFFFFFFFu) {
-                    const FlatHit& fh = flat->hits[best_hit[k]];
-                    prim = fh.prim & ~VKD_DUP;
-                    const uint32_t inst = fh.inst;
-                    hi = (inst ? (0x80000000u | VKD_INDEX(inst)) : 0u) | (fh.face << 28);
-                    cls = fh.cls == 0u ? VKQ_EMIT : fh.cls == 1u ? VKQ_DIEL : fh.cls == 2u ? VKQ_METAL : (inst ? VKQ_DIFFI : VKQ_DIFF);
+                    // the trace returns class-tagged ids: the ray is filed without a look at its entry; the shade stage finds
+                    // the leaf and its instance under the entry (DScene::flat_shade) if it needs them at all
+                    cls = best_hit[k] >> 8;
+                    best_hit[k] = VKF_HIT_INDEX(best_hit[k]);
+                    prim = 1u; // (anything but VK_REF_NONE)
+                    if (HYBRID) { // (no shading records for a hybrid program: the slot carries the leaf itself)
+                        const FlatHit& fh = flat->hits[best_hit[k]];
+                        prim = fh.prim & ~VKD_DUP;
+                        hi = (fh.inst ? (0x80000000u | VKD_INDEX(fh.inst)) : 0u) | (fh.face << 28);
+                    }
                 }
                 S.hp[slot[k]] = make_uint4(__float_as_uint(best_t[k]), prim, hi, best_hit[k]); // .w: entry of the flat program's hit table
             }

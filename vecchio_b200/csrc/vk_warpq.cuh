@@ -32,16 +32,16 @@ namespace VK_NS {
 #define VKQ_MINB_FLAT 4
 #endif
 #ifndef VKQ_N_MEDIA
-#define VKQ_N_MEDIA 120
+#define VKQ_N_MEDIA 144
 #endif
 #ifndef VKQ_RN_MEDIA
-#define VKQ_RN_MEDIA 128
+#define VKQ_RN_MEDIA 256
 #endif
 #ifndef VKQ_K_MEDIA
 #define VKQ_K_MEDIA 1
 #endif
 #ifndef VKQ_MINB_MEDIA
-#define VKQ_MINB_MEDIA 6
+#define VKQ_MINB_MEDIA 5
 #endif
 #ifndef VKQ_N_BVH
 #define VKQ_N_BVH 120
@@ -69,6 +69,8 @@ namespace VK_NS {
 // (7 .. 9: the traversal-step queues of vk_stepq.cu, where VKQ_EXT holds the rays whose next step is a node visit)
 enum { VKQ_EXT = 0, VKQ_END = 1, VKQ_EMIT = 2, VKQ_DIEL = 3, VKQ_METAL = 4, VKQ_DIFF = 5, VKQ_DIFFI = 6, VKQ_NQ = 7,
        VKQ_SPH = 7, VKQ_BOX = 8, VKQ_LEAF = 9, VKQ_NQ_STEP = 10, VKQ_NONE = 15 };
+static_assert(VKF_HITC(0, 0, 0) >> 8 == VKQ_EMIT && VKF_HITC(0, 1, 0) >> 8 == VKQ_DIEL && VKF_HITC(0, 2, 0) >> 8 == VKQ_METAL &&
+              VKF_HITC(0, 3, 0) >> 8 == VKQ_DIFF && VKF_HITC(0, 3, 1) >> 8 == VKQ_DIFFI, "the flat program's class-tagged ids name these queues");
 
 template <int N_, int RN_>
 struct WqWarp {
@@ -302,34 +304,39 @@ VKD void wq_shade_batch(const DScene& sc, const WqCtx<W>& C, const RenderBuffers
                 rng.pixel = pixel;
                 rng.sample = __float_as_uint(bt.w);
                 rng.key = make_uint2(a.seed_lo, a.seed_hi);
-                const uint32_t hi = hp.z;
-                TraceHit h;
-                h.t = __uint_as_float(hp.x);
-                h.prim = prim;
-                h.inst = (hi & 0x80000000u) ? (((uint32_t)VK_T_XFORM << 28) | (hi & 0x07FFFFFFu)) : 0u;
-                h.face = (hi >> 28) & 7u;
                 HitRecD rec;
                 bool direct = false;
+                uint32_t leaf = prim, hi = hp.z;
+                if (FLAT) { // a flat program's slot keeps the distance and the hit-table entry; the rest hangs under the entry
+                    const float4 fs1 = __ldg(&sc.flat_shade[2u * hp.w + 1u]);
+                    leaf = __float_as_uint(fs1.y);
+                    hi = __float_as_uint(fs1.z);
 #if VKQ_FAST_RESOLVE && !VK_STRICT
-                if (FLAT) {
                     const float4 fs = __ldg(&sc.flat_shade[2u * hp.w]);
                     const uint32_t fl = __float_as_uint(fs.w);
                     if (fl & 1u) {
                         direct = true;
                         const float3 nw = f3(fs);
                         const bool toward = dot3(d, nw) < 0.0f;
-                        rec.p = at(o, d, h.t);
+                        rec.t = __uint_as_float(hp.x);
+                        rec.p = at(o, d, rec.t);
                         rec.normal = toward ? nw : -nw;
                         rec.front = (toward ? 1u : 0u) ^ ((fl >> 1) & 1u);
-                        rec.t = h.t;
                         rec.u = 0.0f;
                         rec.v = 0.0f;
-                        rec.mat = __float_as_uint(__ldg(&sc.flat_shade[2u * hp.w + 1u]).x);
+                        rec.mat = __float_as_uint(fs1.x);
                         rec.m = __ldg(&sc.materials[rec.mat]);
                     }
-                }
 #endif
-                if (!direct) resolve_hit(sc, h, o, d, time, false, rec);
+                }
+                if (!direct) {
+                    TraceHit h;
+                    h.t = __uint_as_float(hp.x);
+                    h.prim = leaf;
+                    h.inst = (hi & 0x80000000u) ? (((uint32_t)VK_T_XFORM << 28) | (hi & 0x07FFFFFFu)) : 0u;
+                    h.face = (hi >> 28) & 7u;
+                    resolve_hit(sc, h, o, d, time, false, rec);
+                }
                 alive = LEGACY ? shade_legacy(sc, rec, rng, depth, o, d, time, beta, L, valid)
                                : shade(sc, rec, rng, depth, o, d, time, beta, L, valid);
                 if (alive && ++depth > a.max_depth) alive = false; // `depth > MAX_DEPTH` -> 0 (src/main.rs:126)
