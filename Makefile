@@ -32,8 +32,11 @@ KDEPS := $(CSRC)/vk_device.cuh $(CSRC)/vk_internal.h $(CSRC)/vk_relayout.h inclu
 
 # the device code is compiled twice: contracted FMA ("fast") and -fmad=false ("strict", the
 # reference's op sequence, used for hit parity)
+# (the lane megakernels keep medium_t's two boundary queries as two calls: the one-evaluation form of the queue kernels
+# is 13 % faster on Cornell smoke there and 2.3 % SLOWER here -- final scene 47.2 against 46.1 ms, profiles/r2_sweep_16.log:
+# less arithmetic, but a larger body in a kernel whose top stall is instruction fetch)
 $(CSRC)/vk_kernels_fast.o: $(CSRC)/vk_kernels.cu $(KDEPS)
-	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_fast.log || (cat $(CSRC)/ptxas_fast.log; false)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVKD_MEDIUM_SPAN=0 -c -o $@ $< 2> $(CSRC)/ptxas_fast.log || (cat $(CSRC)/ptxas_fast.log; false)
 $(CSRC)/vk_kernels_strict.o: $(CSRC)/vk_kernels.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_strict.log || (cat $(CSRC)/ptxas_strict.log; false)
 $(CSRC)/vk_wavefront_fast.o: $(CSRC)/vk_wavefront.cu $(KDEPS)

@@ -299,6 +299,8 @@ typedef struct vk_scene_info {
     uint32_t wide_levels_instance;
     uint32_t stack_need;           /* traversal stack entries needed (<= 96)                               */
     uint32_t dynamic_megakernel;   /* 1 = BVH large enough for the dynamic re-fill megakernel               */
+    uint32_t flat_boxes;           /* Boxy entries of the flat program (render build: one slab test each)   */
+    uint32_t flat_direct;          /* hit-table entries whose HitRec the shade stage writes down directly   */
 } vk_scene_info;
 int vk_scene_check(const vk_scene_desc* scene, vk_scene_info* info, char* err, size_t err_len);
 

@@ -160,6 +160,11 @@ def test_scene_check_plans_every_shipped_scene(vb):
     c = vb.scene_check(get_scene(vb, "cornell_box")[0].desc_ptr)
     # 6 world rects (5 walls + the flipped light) + 6 box sides + 1 sphere, in the world frame + one instance frame
     assert (c["flat_entries"], c["flat_segments"]) == (13, 2)
+    # render build: the Boxy once more as ONE slab-test entry; every rect and box side (Lambertian / light, no (u, v)) gets a
+    # shading record the shade stage writes the HitRec from, the glass sphere does not
+    assert (c["flat_boxes"], c["flat_direct"]) == (1, 12)
+    sm = vb.scene_check(get_scene(vb, "cornell_smoke")[0].desc_ptr)
+    assert (sm["flat_entries"], sm["flat_boxes"], sm["flat_direct"]) == (8, 0, 6)  # the two boxes are medium boundaries, not entries
     f = vb.scene_check(get_scene(vb, "final_scene")[0].desc_ptr)
     assert f["flat_subtrees"] == 2  # the hybrid program: what VK_VARIANT_WARPQ runs on this scene (AUTO keeps the lane megakernel)
     # 13 + 511 + 1023 binary nodes collapse into far fewer 4-wide nodes; two BVH levels (world, instanced spheres)

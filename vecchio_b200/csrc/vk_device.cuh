@@ -373,6 +373,9 @@ VKD bool leaf_t(const DScene& sc, uint32_t ref, float3 o, float3 d, float3 inv_d
     }
 }
 
+#ifndef VKD_MEDIUM_SPAN
+#define VKD_MEDIUM_SPAN 1 // (0: the reference's two boundary queries as two calls, in the render build too -- A/B only)
+#endif
 // ConstantMedium::hit (src/hittable.rs:453-493).  The boundary is a leaf, possibly behind a wrapper
 // chain (t is invariant under the chain).
 // (out of line; MediumXi by value so that the callers' copies stay in registers)
@@ -381,7 +384,7 @@ static __device__ __noinline__ bool medium_t(const DScene& sc, uint32_t ref, flo
     const float4 m = __ldg(&sc.media[VKD_INDEX(ref)]);
     float3 bo = o, bd = d;
     float t1 = 0.0f, t2 = 0.0f;
-#if VK_STRICT
+#if VK_STRICT || !VKD_MEDIUM_SPAN
     const uint32_t b = chain_down(sc, __float_as_uint(m.x), bo, bd);
     const float3 binv = rcp3(bd);
 #else
