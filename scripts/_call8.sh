@@ -1,5 +1,6 @@
 set -x
 nvidia-smi --query-gpu=index,name --format=csv | head -3
+python -m pytest tests/test_zz_frames_gpu.py -m gpu -q -k "two_gpus or multi_context" > gpurun_out/r2_pytest_2gpu.log 2>&1; tail -2 gpurun_out/r2_pytest_2gpu.log
 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --no-other-configs > gpurun_out/r2_scale_n1.json 2> gpurun_out/r2_scale_n1.err; cut -c1-200 gpurun_out/r2_scale_n1.json
 for n in 2 4 8; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/r2_scale_n$n.json 2> gpurun_out/r2_scale_n$n.err; cut -c1-200 gpurun_out/r2_scale_n$n.json
@@ -18,4 +19,3 @@ for n in (2, 4, 8):
     del m
 PY
 cat gpurun_out/r2_multi_8gpu.log
-vecchio_b200/lib/vecchio_gpu_render --scene 1 --width 600 --spp 1000 --gpus 8 --out-dir gpurun_out --frames 2 2>&1 | tail -3
