@@ -889,6 +889,99 @@ VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const floa
 // is 0xFFFFFFFF or the class-tagged id of the entry (VKF_HITC: index into P.hits | queue class << 8).
 // HYBRID: the program may hold homogeneous subtrees (FlatProgram::bvh); a ray whose closest hit came from one gets
 // best_hit = 0xFFFFFFFE and the hit itself in sub[] (as in trace_flat).
+// One segment of the program: (co, cd) is the ray in the segment's frame, (o, d) the world ray.
+template <int K, bool MEDIA, bool HYBRID>
+VKD void flat_segment_k(const DScene& sc, const FlatProgram& P, const FlatSeg& g, uint32_t s, const float3 (&o)[K], const float3 (&d)[K],
+                        const float3 (&co)[K], const float3 (&cd)[K], const float (&time)[K], const bool (&live)[K], float tmin,
+                        const MediumXi (&xi)[K], float (&best_t)[K], uint32_t (&best_hit)[K], TraceHit* sub, TraceCounters* tc) {
+    float3 ci[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) ci[q] = rcp3(cd[q]);
+    flat_rects_k<K, 0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);
+    flat_rects_k<K, 1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, tmin, best_t, best_hit);
+    flat_rects_k<K, 2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, tmin, best_t, best_hit);
+#if VK_STRICT
+    flat_rects_k<K, 0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, tmin, best_t, best_hit);
+    flat_rects_k<K, 1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, tmin, best_t, best_hit);
+    flat_rects_k<K, 2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, tmin, best_t, best_hit);
+#else
+    flat_boxes_k<K>(P, g.box0, g.box1, co, ci, tmin, best_t, best_hit);
+#endif
+#pragma unroll 1
+    for (uint32_t i = g.sph0; i < g.sph1; ++i) {
+        const float4 sp = P.spheres[i].a;
+        const uint32_t id = P.spheres[i].hitc;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            float tt;
+            if (sphere_t(f3(sp), sp.w, co[q], cd[q], tmin, best_t[q], tt)) {
+                best_t[q] = tt;
+                best_hit[q] = id;
+            }
+        }
+    }
+#if !VK_SIMPLE
+#pragma unroll 1
+    for (uint32_t i = g.msph0; i < g.msph1; ++i) {
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            float tt;
+            if (sphere_t(msphere_center(P.spheres[i].a, P.spheres[i].b, P.spheres[i].time1, time[q]), P.spheres[i].a.w, co[q], cd[q], tmin, best_t[q], tt)) {
+                best_t[q] = tt;
+                best_hit[q] = P.spheres[i].hitc;
+            }
+        }
+    }
+#endif
+    if (MEDIA) {
+#pragma unroll 1
+        for (uint32_t i = g.med0; i < g.med1; ++i) {
+#pragma unroll // (static indices: a rolled loop over q sends co / cd / best_t / xi to local memory for the whole function)
+            for (int q = 0; q < K; ++q) {
+                float tt;
+                if (live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt)) {
+                    best_t[q] = tt;
+                    best_hit[q] = VKF_HITC(i, P.hits[i].cls, P.hits[i].inst);
+                }
+            }
+        }
+    }
+    if (HYBRID) { // homogeneous subtrees: every lane walks the 4-wide nodes for its own ray, in this segment's frame
+#pragma unroll 1
+        for (uint32_t i = g.bvh0; i < g.bvh1; ++i) {
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                Trav T;
+                T.sp = 0;
+                T.co = co[q];
+                T.cd = cd[q];
+                T.cinv = ci[q];
+                T.cur_inst = P.seg_inst[s];
+                T.best.t = best_t[q];
+                T.best.prim = VK_REF_NONE;
+                T.best.inst = 0;
+                T.best.face = 0;
+                T.ref = live[q] ? P.bvh[i] : VKD_DONE;
+                T.enter = true;
+#pragma unroll 1
+                for (;;) {
+#pragma unroll 1
+                    while (trav_at_node(T)) trav_node_step(T, sc, tmin, *tc);
+                    if (T.ref == VKD_DONE) break;
+                    trav_prim_step<false>(T, sc, o[q], d[q], time[q], tmin, xi[q], *tc); // leaves only: no wrapper, no medium below
+                }
+                if (T.best.prim != VK_REF_NONE) {
+                    best_t[q] = T.best.t;
+                    sub[q] = T.best;
+                    best_hit[q] = 0xFFFFFFFEu;
+                }
+            }
+        }
+    }
+}
+#ifndef VKF_PEEL_WORLD
+#define VKF_PEEL_WORLD 1
+#endif
 template <int K, bool MEDIA, bool HYBRID = false>
 VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[K], const float3 (&d)[K], const float (&time)[K],
                       const bool (&live)[K], float tmin, const MediumXi (&xi)[K], float (&best_t)[K], uint32_t (&best_hit)[K],
@@ -899,10 +992,41 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
         best_hit[q] = 0xFFFFFFFFu;
     }
     const uint32_t n_segs = P.n_segs;
+#if !VK_STRICT && VKF_PEEL_WORLD
+    // Segment 0 is the world frame (no ops, FlatBuilder::build): the ray as it is.  Inside the loop the world ray would
+    // be copied into the registers the instance segments overwrite, 6 moves per ray and segment (1.9 % of the Cornell
+    // kernel's instructions).  Measured (profiles/r2_sweep_17.log): Cornell 32.65 -> 32.53 ms, perlin demo 2.98 -> 2.78 ms;
+    // the media kernels LOSE 1.2 % (Cornell smoke 21.56 -> 21.83 ms: one segment, and a second copy of the medium loop
+    // for nothing), so they keep the loop below.
+    if constexpr (!MEDIA) {
+    flat_segment_k<K, MEDIA, HYBRID>(sc, P, P.segs[0], 0u, o, d, o, d, time, live, tmin, xi, best_t, best_hit, sub, tc);
+#pragma unroll 1
+    for (uint32_t s = 1; s < n_segs; ++s) {
+        const FlatSeg& g = P.segs[s];
+        float3 co[K], cd[K];
+        {   // the chain as one affine map (composed at upload): no loop, no switch on the wrapper kind
+            const float* m = P.seg_affine[s];
+            const float r00 = m[0], r01 = m[1], r02 = m[2], r10 = m[3], r11 = m[4], r12 = m[5], r20 = m[6], r21 = m[7], r22 = m[8];
+            const float t0 = m[9], t1 = m[10], t2 = m[11];
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                const float3 wo = o[q], wd = d[q];
+                co[q] = f3(fmaf(r00, wo.x, fmaf(r01, wo.y, fmaf(r02, wo.z, t0))), fmaf(r10, wo.x, fmaf(r11, wo.y, fmaf(r12, wo.z, t1))),
+                           fmaf(r20, wo.x, fmaf(r21, wo.y, fmaf(r22, wo.z, t2))));
+                cd[q] = f3(fmaf(r00, wd.x, fmaf(r01, wd.y, r02 * wd.z)), fmaf(r10, wd.x, fmaf(r11, wd.y, r12 * wd.z)),
+                           fmaf(r20, wd.x, fmaf(r21, wd.y, r22 * wd.z)));
+            }
+        }
+        flat_segment_k<K, MEDIA, HYBRID>(sc, P, g, s, o, d, co, cd, time, live, tmin, xi, best_t, best_hit, sub, tc);
+    }
+    return;
+    }
+#endif
+    {
 #pragma unroll 1
     for (uint32_t s = 0; s < n_segs; ++s) {
         const FlatSeg& g = P.segs[s];
-        float3 co[K], cd[K], ci[K];
+        float3 co[K], cd[K];
 #pragma unroll
         for (int q = 0; q < K; ++q) {
             co[q] = o[q];
@@ -937,89 +1061,8 @@ VKD void trace_flat_k(const DScene& sc, const FlatProgram& P, const float3 (&o)[
             }
         }
 #endif
-#pragma unroll
-        for (int q = 0; q < K; ++q) ci[q] = rcp3(cd[q]);
-        flat_rects_k<K, 0, false>(P, g.rect0[0], g.rect1[0], co, cd, ci, tmin, best_t, best_hit);
-        flat_rects_k<K, 1, false>(P, g.rect0[1], g.rect1[1], co, cd, ci, tmin, best_t, best_hit);
-        flat_rects_k<K, 2, false>(P, g.rect0[2], g.rect1[2], co, cd, ci, tmin, best_t, best_hit);
-#if VK_STRICT
-        flat_rects_k<K, 0, true>(P, g.rect0[3], g.rect1[3], co, cd, ci, tmin, best_t, best_hit);
-        flat_rects_k<K, 1, true>(P, g.rect0[4], g.rect1[4], co, cd, ci, tmin, best_t, best_hit);
-        flat_rects_k<K, 2, true>(P, g.rect0[5], g.rect1[5], co, cd, ci, tmin, best_t, best_hit);
-#else
-        flat_boxes_k<K>(P, g.box0, g.box1, co, ci, tmin, best_t, best_hit);
-#endif
-#pragma unroll 1
-        for (uint32_t i = g.sph0; i < g.sph1; ++i) {
-            const float4 sp = P.spheres[i].a;
-            const uint32_t id = P.spheres[i].hitc;
-#pragma unroll
-            for (int q = 0; q < K; ++q) {
-                float tt;
-                if (sphere_t(f3(sp), sp.w, co[q], cd[q], tmin, best_t[q], tt)) {
-                    best_t[q] = tt;
-                    best_hit[q] = id;
-                }
-            }
-        }
-#if !VK_SIMPLE
-#pragma unroll 1
-        for (uint32_t i = g.msph0; i < g.msph1; ++i) {
-#pragma unroll
-            for (int q = 0; q < K; ++q) {
-                float tt;
-                if (sphere_t(msphere_center(P.spheres[i].a, P.spheres[i].b, P.spheres[i].time1, time[q]), P.spheres[i].a.w, co[q], cd[q], tmin, best_t[q], tt)) {
-                    best_t[q] = tt;
-                    best_hit[q] = P.spheres[i].hitc;
-                }
-            }
-        }
-#endif
-        if (MEDIA) {
-#pragma unroll 1
-            for (uint32_t i = g.med0; i < g.med1; ++i) {
-#pragma unroll // (static indices: a rolled loop over q sends co / cd / best_t / xi to local memory for the whole function)
-                for (int q = 0; q < K; ++q) {
-                    float tt;
-                    if (live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt)) {
-                        best_t[q] = tt;
-                        best_hit[q] = VKF_HITC(i, P.hits[i].cls, P.hits[i].inst);
-                    }
-                }
-            }
-        }
-        if (HYBRID) { // homogeneous subtrees: every lane walks the 4-wide nodes for its own ray, in this segment's frame
-#pragma unroll 1
-            for (uint32_t i = g.bvh0; i < g.bvh1; ++i) {
-#pragma unroll
-                for (int q = 0; q < K; ++q) {
-                    Trav T;
-                    T.sp = 0;
-                    T.co = co[q];
-                    T.cd = cd[q];
-                    T.cinv = ci[q];
-                    T.cur_inst = P.seg_inst[s];
-                    T.best.t = best_t[q];
-                    T.best.prim = VK_REF_NONE;
-                    T.best.inst = 0;
-                    T.best.face = 0;
-                    T.ref = live[q] ? P.bvh[i] : VKD_DONE;
-                    T.enter = true;
-#pragma unroll 1
-                    for (;;) {
-#pragma unroll 1
-                        while (trav_at_node(T)) trav_node_step(T, sc, tmin, *tc);
-                        if (T.ref == VKD_DONE) break;
-                        trav_prim_step<false>(T, sc, o[q], d[q], time[q], tmin, xi[q], *tc); // leaves only: no wrapper, no medium below
-                    }
-                    if (T.best.prim != VK_REF_NONE) {
-                        best_t[q] = T.best.t;
-                        sub[q] = T.best;
-                        best_hit[q] = 0xFFFFFFFEu;
-                    }
-                }
-            }
-        }
+        flat_segment_k<K, MEDIA, HYBRID>(sc, P, g, s, o, d, co, cd, time, live, tmin, xi, best_t, best_hit, sub, tc);
+    }
     }
 }
 
