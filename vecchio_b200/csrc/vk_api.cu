@@ -329,6 +329,11 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     s.root = d->root;
     s.n_lights = d->n_lights;
     s.has_media = d->n_media > 0;
+    s.light0_a = s.light0_b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d->n_lights >= 1 && VK_REF_TYPE(d->lights[0]) == VK_T_RECT) {
+        static_assert(sizeof(vk_rect) == 2 * sizeof(float4), "device rect record");
+        std::memcpy(&s.light0_a, &d->rects[VK_REF_INDEX(d->lights[0])], 2 * sizeof(float4));
+    }
     CU(c, cudaStreamSynchronize(c->stream)); // host staging vectors die at return
     c->scene = s;
     c->n_nodes = d->n_nodes;

@@ -52,6 +52,13 @@ struct DScene {
     uint32_t root;
     uint32_t n_lights;
     uint32_t has_media; // scene holds a ConstantMedium: selects the kernel instantiation with the medium code
+    // A "simple" scene's one light, an unflipped Rect (Relayout::simple requires it): its record {c0,c1,d0,d1} {k, axes, mat, -}
+    // once more in the kernel parameters, so that the trimmed build samples it from the constant bank (uniform loads, uniform
+    // branches on its axes) instead of through lights[0] -> rects[] (three dependent loads per diffuse bounce and a per-lane
+    // decode of the axes): Cornell 32.53 -> 31.14 ms, Cornell smoke 21.56 -> 21.08 ms.  The same shortcut as an extra
+    // branch in the general builds LOSES (final scene 45.8 -> 48.9 ms, api demo 2.03 -> 2.30 ms: a second copy of the rect
+    // code in kernels that are bound by instruction fetch; profiles/r2_sweep_18.log), so they do not have it.
+    float4 light0_a, light0_b;
 };
 #define VKD_MAT_NEEDS_UV 0x80000000u
 
