@@ -25,6 +25,12 @@ struct vk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::string err;
     std::vector<void*> scene_allocs;
+    // Scene arena: one device block the arrays of an upload are carved from, sized by the previous upload (a caller that
+    // uploads per frame -- bench.py's e2e step -- pays ~20 cudaMalloc / cudaFree pairs per upload without it); arrays that
+    // do not fit fall back to their own allocation (scene_allocs) and the block grows before the next upload.
+    char* arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0, arena_need = 0;
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr}; // vk_render: D2H in chunks, copy-out of one while the next arrives
     DScene scene{};
     FlatProgram flat{}; // flat.n == 0: scene too large, BVH traversal
     bool has_scene = false;
@@ -125,8 +131,15 @@ template <class T> int upload(vk_ctx* c, const T* src, size_t n, const T** dst) 
     *dst = nullptr;
     if (n == 0) n = 1; // keep pointers valid
     void* p = nullptr;
-    CU(c, cudaMalloc(&p, n * sizeof(T)));
-    c->scene_allocs.push_back(p);
+    const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    c->arena_need += bytes;
+    if (c->arena && c->arena_used + bytes <= c->arena_cap) {
+        p = c->arena + c->arena_used;
+        c->arena_used += bytes;
+    } else {
+        CU(c, cudaMalloc(&p, n * sizeof(T)));
+        c->scene_allocs.push_back(p);
+    }
     if (src) CU(c, cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     *dst = (const T*)p;
     return VK_OK;
@@ -134,6 +147,7 @@ template <class T> int upload(vk_ctx* c, const T* src, size_t n, const T** dst) 
 void free_scene(vk_ctx* c) {
     for (void* p : c->scene_allocs) cudaFree(p);
     c->scene_allocs.clear();
+    c->arena_used = 0;
     c->has_scene = false;
 }
 int ensure(vk_ctx* c, float** buf, size_t* have, size_t want) {
@@ -220,6 +234,9 @@ void vk_destroy(vk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     free_scene(c);
+    if (c->arena) cudaFree(c->arena);
+    for (cudaEvent_t e : c->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (c->partial) cudaFree(c->partial);
     if (c->sq_stack) cudaFree(c->sq_stack);
     if (c->wf_block) cudaFree(c->wf_block);
@@ -253,6 +270,15 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     if (!v.run()) return fail(c, v.code, "vk_scene_upload: " + v.err);
     CU(c, cudaSetDevice(c->device));
     free_scene(c);
+    if (c->arena_need > c->arena_cap) { // the previous upload did not fit: grow (cudaFree waits for the work that reads the old block)
+        if (c->arena) cudaFree(c->arena);
+        c->arena = nullptr;
+        c->arena_cap = 0;
+        const size_t want = c->arena_need + c->arena_need / 4;
+        if (cudaMalloc((void**)&c->arena, want) == cudaSuccess) c->arena_cap = want;
+        else (void)cudaGetLastError(); // no block: every array gets its own allocation, as on a first upload
+    }
+    c->arena_need = 0;
 
     Relayout R;
     if (const char* why = R.run(d)) return fail(c, VK_ERR_UNSUPPORTED, std::string("vk_scene_upload: ") + why);
@@ -694,11 +720,23 @@ int vk_render(vk_ctx* c, const vk_camera* cam, const vk_render_params* P, float*
     if (rc != VK_OK) return rc;
     k_finalize<<<(unsigned)((plane + 255) / 256), 256, 0, c->stream>>>(d_sum, d_rgb, plane, (float)P->spp);
     CU(c, cudaGetLastError());
-    CU(c, cudaMemcpyAsync(c->pinned, d_rgb, plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    // the frame comes back in four chunks: the caller's (pageable) buffer is filled from the pinned staging chunk by chunk
+    // while the later chunks are still on the bus
+    constexpr int NCH = 4;
+    size_t off[NCH + 1];
+    for (int i = 0; i <= NCH; ++i) off[i] = plane * (size_t)i / NCH;
+    for (int i = 0; i < NCH; ++i) {
+        if (!c->ev_chunk[i]) CU(c, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+        CU(c, cudaMemcpyAsync(c->pinned + off[i], d_rgb + off[i], (off[i + 1] - off[i]) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaEventRecord(c->ev_chunk[i], c->stream));
+    }
     if (out_sumsq) CU(c, cudaMemcpyAsync(c->pinned + plane, d_sq, plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaEventRecord(c->ev1, c->stream));
+    for (int i = 0; i < NCH; ++i) {
+        CU(c, cudaEventSynchronize(c->ev_chunk[i]));
+        std::memcpy(out_rgb + off[i], c->pinned + off[i], (off[i + 1] - off[i]) * sizeof(float));
+    }
     CU(c, cudaStreamSynchronize(c->stream));
-    std::memcpy(out_rgb, c->pinned, plane * sizeof(float));
     if (out_sumsq) std::memcpy(out_sumsq, c->pinned + plane, plane * sizeof(float));
     st.launches += 1;
     c->launches = 0;
