@@ -889,6 +889,47 @@ VKD void flat_rects_k(const FlatProgram& P, uint32_t i0, uint32_t i1, const floa
 // is 0xFFFFFFFF or the class-tagged id of the entry (VKF_HITC: index into P.hits | queue class << 8).
 // HYBRID: the program may hold homogeneous subtrees (FlatProgram::bvh); a ray whose closest hit came from one gets
 // best_hit = 0xFFFFFFFE and the hit itself in sub[] (as in trace_flat).
+#if !VK_STRICT
+// ConstantMedium::hit for a flat-program entry whose boundary is a Boxy, on operands from the constant bank (FlatMedium):
+// medium_t's render-build arithmetic -- the boundary chain as one affine map, both boundary queries replayed on one slab
+// evaluation -- without the call, the loads of the medium / plan / box records and the switch on the boundary's type.
+#ifndef VKF_INLINE_MEDIA
+#define VKF_INLINE_MEDIA 1
+#endif
+VKD bool flat_medium_box(const FlatMedium& fm, uint32_t ref, float3 o, float3 d, float tmin, float tmax, const MediumXi& xi, float& t) {
+    float3 bo = o, bd = d;
+    if (__float_as_uint(fm.mx.w) & 2u) {
+        const float* m = fm.aff;
+        bo = f3(fmaf(m[0], o.x, fmaf(m[1], o.y, fmaf(m[2], o.z, m[9]))), fmaf(m[3], o.x, fmaf(m[4], o.y, fmaf(m[5], o.z, m[10]))),
+                fmaf(m[6], o.x, fmaf(m[7], o.y, fmaf(m[8], o.z, m[11]))));
+        bd = f3(fmaf(m[0], d.x, fmaf(m[1], d.y, m[2] * d.z)), fmaf(m[3], d.x, fmaf(m[4], d.y, m[5] * d.z)),
+                fmaf(m[6], d.x, fmaf(m[7], d.y, m[8] * d.z)));
+    }
+    const float3 binv = rcp3(bd);
+    const float3 oi = f3(-bo.x * binv.x, -bo.y * binv.y, -bo.z * binv.z);
+    const float x0 = fmaf(fm.mn.x, binv.x, oi.x), x1 = fmaf(fm.mx.x, binv.x, oi.x);
+    const float y0 = fmaf(fm.mn.y, binv.y, oi.y), y1 = fmaf(fm.mx.y, binv.y, oi.y);
+    const float z0 = fmaf(fm.mn.z, binv.z, oi.z), z1 = fmaf(fm.mx.z, binv.z, oi.z);
+    const float t_near = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    const float t_far = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    if (!(t_near <= t_far)) return false;
+    float t1 = (t_near >= -CUDART_INF_F) ? t_near : t_far; // (the window logic of box_t, see medium_t)
+    if (!(t1 >= -CUDART_INF_F && t1 < CUDART_INF_F)) return false;
+    const float lo = t1 + 0.0001f;
+    float t2 = (t_near >= lo) ? t_near : t_far;
+    if (!(t2 >= lo && t2 < CUDART_INF_F)) return false;
+    if (t1 < tmin) t1 = tmin;
+    if (t2 > tmax) t2 = tmax;
+    if (t1 >= t2) return false;
+    if (t1 < 0.0f) t1 = 0.0f;
+    const float ray_length = sqrtf(length2(d));
+    const float distance_inside_boundary = (t2 - t1) * ray_length;
+    const float hit_distance = fm.mn.w * logf(xi.get(VKD_INDEX(ref), (ref & VKD_DUP) ? 1u : 0u));
+    if (hit_distance > distance_inside_boundary) return false;
+    t = t1 + hit_distance / ray_length;
+    return true;
+}
+#endif
 // One segment of the program: (co, cd) is the ray in the segment's frame, (o, d) the world ray.
 template <int K, bool MEDIA, bool HYBRID>
 VKD void flat_segment_k(const DScene& sc, const FlatProgram& P, const FlatSeg& g, uint32_t s, const float3 (&o)[K], const float3 (&d)[K],
@@ -936,10 +977,20 @@ VKD void flat_segment_k(const DScene& sc, const FlatProgram& P, const FlatSeg& g
     if (MEDIA) {
 #pragma unroll 1
         for (uint32_t i = g.med0; i < g.med1; ++i) {
+#if !VK_STRICT && VKF_INLINE_MEDIA
+            const FlatMedium& fm = P.fmed[P.seg_fm0[s] + (i - g.med0)];
+            const bool inline_box = (__float_as_uint(fm.mx.w) & 1u) != 0u; // (uniform: the constant bank)
+#endif
 #pragma unroll // (static indices: a rolled loop over q sends co / cd / best_t / xi to local memory for the whole function)
             for (int q = 0; q < K; ++q) {
                 float tt;
-                if (live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt)) {
+                bool hit;
+#if !VK_STRICT && VKF_INLINE_MEDIA
+                if (inline_box) hit = live[q] && flat_medium_box(fm, P.hits[i].prim, co[q], cd[q], tmin, best_t[q], xi[q], tt);
+                else
+#endif
+                    hit = live[q] && medium_t(sc, P.hits[i].prim, co[q], cd[q], time[q], tmin, best_t[q], xi[q], tt);
+                if (hit) {
                     best_t[q] = tt;
                     best_hit[q] = VKF_HITC(i, P.hits[i].cls, P.hits[i].inst);
                 }

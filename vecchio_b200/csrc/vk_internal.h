@@ -117,6 +117,14 @@ struct FlatBox { // Boxy::hit src/hittable.rs:363-365 as ONE entry (render build
     float4 mn; // box_min, .w = bits: class-tagged id of side 0 (sides 0 and 1, the two XY rects, are consecutive entries)
     float4 mx; // box_max, .w = bits: class-tagged id of side 2 (XZ pair) | of side 4 (YZ pair) << 16
 };
+// A ConstantMedium entry of the flat program whose boundary is a Boxy (Cornell smoke), for the render build's K-ray trace:
+// everything medium_t would fetch -- the medium record, its boundary chain as one affine map, the box -- in the constant
+// bank, so the test runs inline on uniform operands (flat_medium_box).  flags 0: not such an entry, medium_t handles it.
+struct FlatMedium {
+    float aff[12]; // rows of R, then t: boundary frame = R * segment frame + t (identity without a chain)
+    float4 mn;     // box_min, .w = -1 / density
+    float4 mx;     // box_max, .w = bits: 1 = inline box entry | 2 = the boundary has a wrapper chain
+};
 struct FlatHit { // what the closest entry resolves to
     uint32_t prim; // leaf record (sphere / msphere / rect / box / medium [| VKD_DUP on a medium's second visit])
     uint32_t inst; // outermost wrapper of the chain it sits under, or 0
@@ -158,6 +166,10 @@ struct FlatProgram {
     // Render build: every Boxy of the program once more as one slab-test entry (flat_boxes_k, vk_device.cuh); it replaces the
     // box-side rect ranges rect0[3..5] there.  Same sides, same hit-table entries.
     FlatBox boxes[VKF_MAX_BOXES];
+    FlatMedium fmed[VKF_MAX_MEDIA];
+    uint8_t seg_fm0[VKF_MAX_SEGS]; // per segment: fmed entry of its first medium (entry i of hits[] is fmed[seg_fm0[s] + i - med0]);
+                                   // kept out of FlatSeg: growing that record moves every array behind it in the constant bank,
+                                   // which costs the Cornell kernel 0.5 % (31.15 -> 31.32 ms, profiles/r2_sweep_21.log)
 };
 
 struct DCamera {

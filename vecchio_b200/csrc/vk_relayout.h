@@ -434,7 +434,19 @@ struct FlatBuilder {
             o.msph1 = (uint8_t)n_sph;
             if (n_med + g.med.size() > VKF_MAX_MEDIA) return false;
             o.med0 = (uint8_t)n_hits;
+            P->seg_fm0[s] = (uint8_t)n_med;
             for (const FlatHit& h : g.med) {
+                FlatMedium& fm = P->fmed[n_med];
+                fm = FlatMedium{};
+                const vk_medium& md = d->media[VK_REF_INDEX(h.prim & ~VKD_DUP)];
+                std::vector<FlatOp> ops;
+                const vk_ref leaf = chain_ops(d, md.boundary, ops);
+                compose_flat_ops(ops.data(), ops.size(), fm.aff);
+                if (VK_REF_TYPE(leaf) == VK_T_BOX) {
+                    const vk_box& b = d->boxes[VK_REF_INDEX(leaf)];
+                    fm.mn = make_float4(b.box_min[0], b.box_min[1], b.box_min[2], md.neg_inv_density);
+                    fm.mx = make_float4(b.box_max[0], b.box_max[1], b.box_max[2], __uint_as_float_host(1u | (ops.empty() ? 0u : 2u)));
+                }
                 P->hits[n_hits++] = h;
                 ++n_med;
             }
