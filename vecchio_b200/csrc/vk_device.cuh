@@ -1533,8 +1533,11 @@ VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, u
     return light_random_other(sc, ref, o, x0, x1, x2);
 #endif
 }
+#ifndef VK_LIGHT0
+#define VK_LIGHT0 0
+#endif
 VKD float lights_pdf_value(const DScene& sc, float3 o, float3 v) {
-#if VK_SIMPLE
+#if VK_SIMPLE || VK_LIGHT0
     // (the one unflipped Rect light, from the kernel parameters: DScene::light0_a)
     return 0.0f + 1.0f * rect_pdf_value(sc.light0_a, sc.light0_b.x, __float_as_uint(sc.light0_b.y), o, v); // sum = 0.0 + weight * pdf with weight 1/1
 #endif
@@ -1647,7 +1650,7 @@ VKD bool shade_xi(const DScene& sc, const HitRecD& rec, const XI& xi, float3& o,
 #endif
     float3 nd;
     if (u01(r.x) < 0.5f) { // MixturePDF::generate src/util.rs:177-185 -> HittablePDF -> list random
-#if VK_SIMPLE
+#if VK_SIMPLE || VK_LIGHT0
         nd = rect_random(sc.light0_a, sc.light0_b.x, __float_as_uint(sc.light0_b.y), rec.p, r.y, r.z); // the one (unflipped Rect) light
 #else
         const uint32_t li = sc.n_lights > 1 ? min(sc.n_lights - 1u, (uint32_t)(u01(r.w) * (float)sc.n_lights)) : 0u;
