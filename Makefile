@@ -37,6 +37,9 @@ KDEPS := $(CSRC)/vk_device.cuh $(CSRC)/vk_internal.h $(CSRC)/vk_relayout.h inclu
 # less arithmetic, but a larger body in a kernel whose top stall is instruction fetch)
 $(CSRC)/vk_kernels_fast.o: $(CSRC)/vk_kernels.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVKD_MEDIUM_SPAN=0 -c -o $@ $< 2> $(CSRC)/ptxas_fast.log || (cat $(CSRC)/ptxas_fast.log; false)
+# the render build once more for scenes whose light list is one unflipped Rect (VK_LIGHT0, namespace vkfast_l0; see vk_device.cuh)
+$(CSRC)/vk_kernels_l0.o: $(CSRC)/vk_kernels.cu $(KDEPS)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVKD_MEDIUM_SPAN=0 -DVK_LIGHT0=1 -c -o $@ $< 2> $(CSRC)/ptxas_l0.log || (cat $(CSRC)/ptxas_l0.log; false)
 $(CSRC)/vk_kernels_strict.o: $(CSRC)/vk_kernels.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_strict.log || (cat $(CSRC)/ptxas_strict.log; false)
 $(CSRC)/vk_wavefront_fast.o: $(CSRC)/vk_wavefront.cu $(KDEPS)
@@ -56,6 +59,10 @@ KDEPS_WQ := $(KDEPS) $(CSRC)/vk_warpq.cuh
 # the step-queue kernels for BVH scenes
 $(CSRC)/vk_stepq_fast.o: $(CSRC)/vk_stepq.cu $(KDEPS_WQ)
 	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -c -o $@ $< 2> $(CSRC)/ptxas_stepq_fast.log || (cat $(CSRC)/ptxas_stepq_fast.log; false)
+$(CSRC)/vk_stepq_l0.o: $(CSRC)/vk_stepq.cu $(KDEPS_WQ)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVK_LIGHT0=1 -c -o $@ $< 2> $(CSRC)/ptxas_stepq_l0.log || (cat $(CSRC)/ptxas_stepq_l0.log; false)
+$(CSRC)/vk_warpq_l0.o: $(CSRC)/vk_warpq.cu $(KDEPS_WQ)
+	$(NVCC) $(NVFLAGS) -prec-div=false -prec-sqrt=false -DVK_STRICT=0 -DVK_LIGHT0=1 -c -o $@ $< 2> $(CSRC)/ptxas_warpq_l0.log || (cat $(CSRC)/ptxas_warpq_l0.log; false)
 $(CSRC)/vk_stepq_strict.o: $(CSRC)/vk_stepq.cu $(KDEPS_WQ)
 	$(NVCC) $(NVFLAGS) -fmad=false -DVK_STRICT=1 -c -o $@ $< 2> $(CSRC)/ptxas_stepq_strict.log || (cat $(CSRC)/ptxas_stepq_strict.log; false)
 $(CSRC)/vk_warpq_fast.o: $(CSRC)/vk_warpq.cu $(KDEPS_WQ)
@@ -69,7 +76,7 @@ $(CSRC)/vk_api.o: $(CSRC)/vk_api.cu $(KDEPS)
 $(CSRC)/vk_relayout.o: $(CSRC)/vk_relayout.cu $(KDEPS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o $(CSRC)/vk_warpq_fast.o $(CSRC)/vk_warpq_strict.o $(CSRC)/vk_warpq_simple.o $(CSRC)/vk_stepq_fast.o $(CSRC)/vk_stepq_strict.o
+$(LIBDIR)/libvecchio_gpu.so: $(CSRC)/vk_api.o $(CSRC)/vk_relayout.o $(CSRC)/vk_kernels_fast.o $(CSRC)/vk_kernels_strict.o $(CSRC)/vk_wavefront_fast.o $(CSRC)/vk_wavefront_strict.o $(CSRC)/vk_staged_fast.o $(CSRC)/vk_staged_strict.o $(CSRC)/vk_staged_simple.o $(CSRC)/vk_warpq_fast.o $(CSRC)/vk_warpq_strict.o $(CSRC)/vk_warpq_simple.o $(CSRC)/vk_stepq_fast.o $(CSRC)/vk_stepq_strict.o $(CSRC)/vk_kernels_l0.o $(CSRC)/vk_warpq_l0.o $(CSRC)/vk_stepq_l0.o
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 

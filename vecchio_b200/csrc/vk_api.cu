@@ -40,6 +40,7 @@ struct vk_ctx {
     size_t l2_persist_max = 0, l2_window_max = 0; // device limits for persisting L2 lines / the policy window
     bool has_specdiffuse = false;
     bool simple_scene = false; // only what the VK_SIMPLE build of the staged kernel keeps (see vk_device.cuh)
+    bool one_rect_light = false; // the light list is exactly one unflipped Rect: the VK_LIGHT0 builds apply
     unsigned long long* debug = nullptr;    // per-CTA diagnostics of the staged kernel (VK_DEBUG_CTAS x 4 words)
     unsigned long long* counters = nullptr; // [0] rays [1] dropped [2] work head
     float* partial = nullptr;               // accumulators: W*H*3 x u64 fixed-point sums | W*H*3 x double sums of squares
@@ -369,6 +370,7 @@ int vk_scene_upload(vk_ctx* c, const vk_scene_desc* d) {
     c->wnodes_bytes = wnodes.size() * sizeof(float4);
     c->has_specdiffuse = R.has_specdiffuse;
     c->simple_scene = R.simple;
+    c->one_rect_light = d->n_lights == 1 && VK_REF_TYPE(d->lights[0]) == VK_T_RECT && !(d->rects[VK_REF_INDEX(d->lights[0])].axes & VK_RECT_FLIP);
     c->stack_need = R.stack_need;
     c->levels_sub = R.levels_sub;
     c->flat = R.flat;
@@ -545,7 +547,10 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         return fail(c, VK_ERR_UNSUPPORTED, "render: SpecDiffuse has no legacy scatter (the reference's default unwraps a missing specular ray and panics, src/material.rs:21-28)");
     if (!legacy && c->scene.n_lights == 0)
         return fail(c, VK_ERR_INVALID, "render: empty light list (the reference panics: choose().unwrap(), src/hittable.rs:431); only VK_FLAG_LEGACY_SCATTER renders without lights");
+    // the render build compiled for a light list of one unflipped Rect (VK_LIGHT0, see vk_device.cuh)
+    const bool l0 = !strict && !legacy && c->one_rect_light && !std::getenv("VECCHIO_NO_LIGHT0");
     CU(c, strict ? vkstrict::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt)
+          : l0   ? vkfast_l0::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt)
                  : vkfast::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt));
     if (bps < 1) bps = 1;
     const int grid = c->sm_count * bps;
@@ -602,6 +607,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
         CU(c, cudaMemsetAsync(c->counters + 5, 0, sizeof(unsigned long long), c->stream)); // self-check violations (debug builds)
         CU(c, strict ? vkstrict::launch_stepq(c->scene, dc, a, b, c->counters + 2, (uint32_t*)c->sq_stack, glevels, inst, c->sm_count, legacy, c->stream)
+              : l0   ? vkfast_l0::launch_stepq(c->scene, dc, a, b, c->counters + 2, (uint32_t*)c->sq_stack, glevels, inst, c->sm_count, legacy, c->stream)
                      : vkfast::launch_stepq(c->scene, dc, a, b, c->counters + 2, (uint32_t*)c->sq_stack, glevels, inst, c->sm_count, legacy, c->stream));
         launches = 1;
     } else if (variant == VK_VARIANT_WARPQ) {
@@ -612,6 +618,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
         const bool simple = !strict && !legacy && sflat && sflat->n_bvh == 0 && c->simple_scene && !std::getenv("VECCHIO_NO_SIMPLE");
         CU(c, strict   ? vkstrict::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream)
               : simple ? vkfast_simple::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream)
+              : l0     ? vkfast_l0::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream)
                        : vkfast::launch_warpq(c->scene, sflat, dc, a, b, c->counters + 2, c->sm_count, legacy, c->stream));
         launches = 1;
     } else if (variant == VK_VARIANT_WAVEFRONT) {
@@ -632,10 +639,12 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     } else if (!flat && !legacy && use_dynamic_megakernel(c)) {
         CU(c, cudaMemsetAsync(c->counters + 2, 0, sizeof(unsigned long long), c->stream)); // unit queue head
         CU(c, strict ? vkstrict::launch_megakernel_dyn(c->scene, dc, a, b, c->counters + 2, c->sm_count, c->stream)
+              : l0   ? vkfast_l0::launch_megakernel_dyn(c->scene, dc, a, b, c->counters + 2, c->sm_count, c->stream)
                      : vkfast::launch_megakernel_dyn(c->scene, dc, a, b, c->counters + 2, c->sm_count, c->stream));
         launches = 1;
     } else {
         CU(c, strict ? vkstrict::launch_megakernel(c->scene, flat, dc, a, b, grid, legacy, c->stream)
+              : l0   ? vkfast_l0::launch_megakernel(c->scene, flat, dc, a, b, grid, legacy, c->stream)
                      : vkfast::launch_megakernel(c->scene, flat, dc, a, b, grid, legacy, c->stream));
         launches = 1;
     }

@@ -23,10 +23,21 @@
 #ifndef VK_SIMPLE
 #define VK_SIMPLE 0
 #endif
+// VK_LIGHT0=1 (namespace vkfast_l0; vk_kernels.cu, vk_warpq.cu, vk_stepq.cu): the general render build with the light
+// list compiled as what every shipped scene has -- exactly one unflipped Rect -- read from the kernel parameters
+// (DScene::light0_a / _b) instead of the general list code (Sphere / Boxy lights, several lights, the records behind
+// lights[] -> rects[]).  vk_scene_upload decides (vk_ctx::one_rect_light); anything else runs namespace vkfast.  A
+// REPLACEMENT, so the body shrinks: 4 % on the final scene, bowser, balls and random-spheres scenes; as an extra branch
+// next to the general code it LOST 7 % (profiles/r2_sweep_18.log, r2_sweep_22.log).
+#ifndef VK_LIGHT0
+#define VK_LIGHT0 0
+#endif
 #if VK_STRICT
 #define VK_NS vkstrict
 #elif VK_SIMPLE
 #define VK_NS vkfast_simple
+#elif VK_LIGHT0
+#define VK_NS vkfast_l0
 #else
 #define VK_NS vkfast
 #endif
@@ -1533,9 +1544,6 @@ VKD float3 light_random(const DScene& sc, uint32_t ref, float3 o, uint32_t x0, u
     return light_random_other(sc, ref, o, x0, x1, x2);
 #endif
 }
-#ifndef VK_LIGHT0
-#define VK_LIGHT0 0
-#endif
 VKD float lights_pdf_value(const DScene& sc, float3 o, float3 v) {
 #if VK_SIMPLE || VK_LIGHT0
     // (the one unflipped Rect light, from the kernel parameters: DScene::light0_a)

@@ -265,6 +265,7 @@ struct WfState {
     }
 VK_DECLARE_LAUNCHERS(vkfast)
 VK_DECLARE_LAUNCHERS(vkstrict)
+VK_DECLARE_LAUNCHERS(vkfast_l0) // (vk_kernels.cu, vk_warpq.cu, vk_stepq.cu with VK_LIGHT0=1: the megakernel, warp-queue and step-queue launchers only)
 namespace vkfast_simple { // vk_staged.cu / vk_warpq.cu compiled with VK_SIMPLE=1: kernels for "simple" flat scenes (see vk_device.cuh)
 cudaError_t launch_staged(const DScene& sc, const FlatProgram* flat, const DCamera& cam, const RenderArgs& a, const RenderBuffers& b,
                           unsigned long long* unit_head, int sm_count, cudaStream_t st);
