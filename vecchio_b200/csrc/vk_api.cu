@@ -548,7 +548,7 @@ static int render_into(vk_ctx* c, const vk_camera* cam, const vk_render_params* 
     if (!legacy && c->scene.n_lights == 0)
         return fail(c, VK_ERR_INVALID, "render: empty light list (the reference panics: choose().unwrap(), src/hittable.rs:431); only VK_FLAG_LEGACY_SCATTER renders without lights");
     // the render build compiled for a light list of one unflipped Rect (VK_LIGHT0, see vk_device.cuh)
-    const bool l0 = !strict && !legacy && c->one_rect_light && !std::getenv("VECCHIO_NO_LIGHT0");
+    const bool l0 = !strict && !legacy && c->one_rect_light && !c->has_specdiffuse && !std::getenv("VECCHIO_NO_LIGHT0");
     CU(c, strict ? vkstrict::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt)
           : l0   ? vkfast_l0::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt)
                  : vkfast::megakernel_occupancy(flat != nullptr, c->scene.has_media, legacy, &bps, &bt));

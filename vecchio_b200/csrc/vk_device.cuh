@@ -26,7 +26,8 @@
 // VK_LIGHT0=1 (namespace vkfast_l0; vk_kernels.cu, vk_warpq.cu, vk_stepq.cu): the general render build with the light
 // list compiled as what every shipped scene has -- exactly one unflipped Rect -- read from the kernel parameters
 // (DScene::light0_a / _b) instead of the general list code (Sphere / Boxy lights, several lights, the records behind
-// lights[] -> rects[]).  vk_scene_upload decides (vk_ctx::one_rect_light); anything else runs namespace vkfast.  A
+// lights[] -> rects[]), and without SpecDiffuse (its choice draws a Philox block of its own, inlined into every shade).
+// vk_scene_upload decides (vk_ctx::one_rect_light && !has_specdiffuse); anything else runs namespace vkfast.  A
 // REPLACEMENT, so the body shrinks: 4 % on the final scene, bowser, balls and random-spheres scenes; as an extra branch
 // next to the general code it LOST 7 % (profiles/r2_sweep_18.log, r2_sweep_22.log).
 #ifndef VK_LIGHT0
@@ -1610,7 +1611,7 @@ VKD bool shade_xi(const DScene& sc, const HitRecD& rec, const XI& xi, float3& o,
     uint32_t type = m.x;
     uint32_t spdf_type = type; // whose scattering_pdf applies
     float3 emitted = f3(0.0f, 0.0f, 0.0f);
-    if (!VK_SIMPLE && type == VK_M_SPECDIFFUSE) { // src/material.rs:474-488: emitted() is the trait default (0)
+    if (!VK_SIMPLE && !VK_LIGHT0 && type == VK_M_SPECDIFFUSE) { // src/material.rs:474-488: emitted() is the trait default (0)
         const uint32_t diffuse = m.w & ~VKD_MAT_NEEDS_UV;
         spdf_type = __ldg(&sc.materials[diffuse]).x;
         m = __ldg(&sc.materials[u01(xi.spec()) < __uint_as_float(m.z) ? m.y : diffuse]);
