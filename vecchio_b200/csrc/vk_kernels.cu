@@ -14,12 +14,15 @@ namespace VK_NS {
 // Resident CTAs per SM the register allocation must allow.  Measured on B200 (profiles/): the flat
 // kernel gains 20 % going from 4 (122 regs) to 8 (64 regs, a few spills) -- it is latency bound on
 // dependent ALU chains and indexed constant loads, so more warps win over fewer spills; the BVH
-// kernel is flat between 5 and 8.
+// kernel was flat between 5 and 8 in round 1.  Round 2's body (profiles/r2_sweep_23.log, 4 / 5 / 6 / 7 / 8 CTAs =
+// 114 / 96 / 80 / 72 / 64 registers, 0 / 56 / 290 / 416 / 460 B of spill stores): final scene 43.9 / 42.3 / 42.8 / 44.0 / 44.3 ms,
+// bowser 5.11 / 4.92 / 5.40 / 5.50 / 5.85 ms, random spheres at 16 spp 1.24 / 1.18 / 1.21 / 1.20 / 1.20 ms -- five it is
+// (256-thread CTAs at the same occupancy: no change).
 #ifndef VK_MINB_FLAT
 #define VK_MINB_FLAT 8
 #endif
 #ifndef VK_MINB_BVH
-#define VK_MINB_BVH 6
+#define VK_MINB_BVH 5
 #endif
 
 // Work decomposition (deterministic for a seed whatever the grid):

@@ -63,7 +63,8 @@ namespace VK_NS {
 #define VKQ_MINB_HYB 6
 #endif
 #ifndef VKQ_REGEN_MIN
-#define VKQ_REGEN_MIN 16u // ended lanes of a shade batch are regenerated at once when at least this many ended
+#define VKQ_REGEN_MIN 32u // ended lanes of a shade batch are regenerated at once when at least this many ended (8 / 16 / 32:
+                          // Cornell 31.34 / 31.20 / 31.13 ms, smoke 18.54 / 18.47 / 18.42 ms, profiles/r2_sweep_23.log)
 #endif
 #define VKQ_CHUNK 256u
 // (7 .. 9: the traversal-step queues of vk_stepq.cu, where VKQ_EXT holds the rays whose next step is a node visit)
