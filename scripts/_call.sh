@@ -1,7 +1,5 @@
-# ncu evidence of the final build: bench launch list, full captures of the Cornell warp-queue kernel and the final-scene lane megakernel
+# sanity of the from-scratch rebuild (make clean; make): smoke and a short bench line
 set -x
-bash scripts/gpu_profile.sh
-python scripts/render_once.py final_scene 16 0 > gpurun_out/plain_f.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_megakernel -s 1 -c 1 -f -o gpurun_out/prof_r2_final_scene_megakernel \
-    python scripts/render_once.py final_scene 16 0 > gpurun_out/ncu_full_f.log 2>&1; echo "full rc=$?"
-cat gpurun_out/plain_f.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-other-configs 2> gpurun_out/bench_short.err | cut -c1-700
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "variants_equal_megakernel or hit_parity_fast_math or render_build_hits_equal" 2>&1 | tail -3
