@@ -7,6 +7,8 @@ restated in plain Python straight from the Rust --
 
     src/scene.rs:167-284   random_spheres_demo        src/scene.rs:630-730  cornell_box
     src/scene.rs:732-874   final_scene                SURVEY 8(d)           Cornell smoke (authored, book 2)
+    src/scene.rs:93-165    balls_demo                 src/scene.rs:286-337  perlin_demo
+    src/scene.rs:340-628   Bowser::new, bowser_demo (RotateX / RotateZ::new: src/hittable.rs:639-674, 728-763)
     src/accel.rs:36-50, 98-136   AxisBB::surrounding_box, BVHNode::new (random axis, stable sort, len/2 split)
     src/hittable.rs:97-102, 186-196, 258-269, 367-369, 495-497, 525-531, 542-574   bounding_box of every type
     src/material.rs:357-377      Perlin::new          src/main.rs:71-109    Camera::new
@@ -166,7 +168,7 @@ def translate(h, offset):
     return {"kind": "translate", "offset": np.asarray(offset, dtype=F), "child": h}
 
 
-def rotate_y(h, angle):  # RotateY::new :542-574
+def _rotate(kind, h, angle, turn):  # RotateX / RotateY / RotateZ::new (:639-674, :542-574, :728-763): sin, cos, the rotated box
     rad = F(angle) * F(math.pi / 180.0)  # f32::to_radians
     s, c = F(np.sin(rad)), F(np.cos(rad))
     bmin, bmax = bounding_box(h)
@@ -177,9 +179,21 @@ def rotate_y(h, angle):  # RotateY::new :542-574
                 x = bmax[0] if i == 1 else bmin[0]
                 y = bmax[1] if j == 1 else bmin[1]
                 z = bmax[2] if k == 1 else bmin[2]
-                t = v3(F(c * x) + F(s * z), y, F(-s * x) + F(c * z))
+                t = turn(s, c, x, y, z)
                 mn, mx = np.minimum(mn, t), np.maximum(mx, t)
-    return {"kind": "rotate_y", "sin": s, "cos": c, "child": h, "bb": (mn, mx)}
+    return {"kind": kind, "sin": s, "cos": c, "child": h, "bb": (mn, mx)}
+
+
+def rotate_y(h, angle):  # :542-574
+    return _rotate("rotate_y", h, angle, lambda s, c, x, y, z: v3(F(c * x) + F(s * z), y, F(-s * x) + F(c * z)))
+
+
+def rotate_x(h, angle):  # :639-674
+    return _rotate("rotate_x", h, angle, lambda s, c, x, y, z: v3(x, F(c * y) - F(s * z), F(s * y) + F(c * z)))
+
+
+def rotate_z(h, angle):  # :728-763
+    return _rotate("rotate_z", h, angle, lambda s, c, x, y, z: v3(F(c * x) - F(s * y), F(s * x) + F(c * y), z))
 
 
 def constant_medium(boundary, density, tex):  # ConstantMedium::new :443-451
@@ -211,7 +225,7 @@ def bounding_box(h):
     if k == "translate":
         lo, hi = bounding_box(h["child"])
         return lo + h["offset"], hi + h["offset"]
-    if k == "rotate_y":
+    if k in ("rotate_x", "rotate_y", "rotate_z"):
         return h["bb"]
     if k == "medium":
         return bounding_box(h["boundary"])
@@ -348,7 +362,92 @@ def final_scene(rng, assets_dir):  # src/scene.rs:732-874
     return objects, [light_shape], cam, 1.0
 
 
-SCENES = {"cornell_box": cornell_box, "cornell_smoke": cornell_smoke, "random_spheres_demo": random_spheres_demo, "final_scene": final_scene}
+def _demo_light_and_camera():  # the light and FixedCamera shared by balls_demo (:129-163) and perlin_demo (:303-336)
+    light_shape = rect("xz", -6, 6, -6, 6, 8, diffuse_light(solid(4, 4, 4)))
+    cam = camera_new((0, 2, 10), (0, 1, 0), (0, 1, 0), 40.0, F(16.0) / F(9.0), 0.0, 10.0, 0.0, 1.0)
+    return light_shape, cam
+
+
+def balls_demo(rng, assets_dir):  # src/scene.rs:93-165
+    world = [sphere((0, 0, -1), 0.5, lambertian(solid(0.1, 0.2, 0.5))),
+             sphere((0, -100.5, -1), 100.0, lambertian(solid(0.8, 0.8, 0.8))),
+             sphere((1, 0, -1), 0.5, metal(solid(0.8, 0.6, 0.2), 0.3)),
+             sphere((-1, 0, -1), 0.5, dielectric(1.5)),
+             sphere((-1, 0, -1), -0.45, dielectric(1.5))]  # the hollow glass ball: negative radius
+    light_shape, cam = _demo_light_and_camera()
+    world.append(flip_face(light_shape))
+    return world, [light_shape], cam, F(16.0) / F(9.0)
+
+
+def perlin_demo(rng, assets_dir):  # src/scene.rs:286-337
+    pertext = lambertian(noise_texture(rng, 2.0))  # Perlin::new draws here, before anything else
+    world = [sphere((0, -1000, 0), 1000.0, pertext), sphere((0, 2, 0), 2.0, pertext)]
+    light_shape, cam = _demo_light_and_camera()
+    world.append(flip_face(light_shape))
+    return world, [light_shape], cam, F(16.0) / F(9.0)
+
+
+def _bowser(rng, assets_dir, x, y, z):  # Bowser::new src/scene.rs:344-541: 28 parts under a BVH of their own
+    x, y, z = F(x), F(y), F(z)
+
+    def X(d):  # `x - 2.0`, `x + 2.0`
+        return x + F(d)
+
+    def Y(d):  # `y - 1.875 + d`, evaluated left to right in f32
+        return (y - F(1.875)) + F(d)
+
+    def Z(d):  # `z + 4.5 - d`
+        return (z + F(4.5)) - F(d)
+
+    def img(name):
+        return lambertian(image_texture("assets/" + name, assets_dir))
+
+    parts = [rect("xy", X(-2.0), X(2.0), Y(1.0), Y(4.0), Z(3.0), img("bowser_face.png")),
+             rect("xz", X(-2.0), X(2.0), Z(6.0), Z(3.0), Y(4.0), img("bowser_top.png")),
+             rect("xy", X(-2.0), X(2.0), Y(1.0), Y(4.0), Z(6.0), img("bowser_back.png")),
+             rect("yz", Y(1.0), Y(4.0), Z(6.0), Z(3.0), X(-2.0), img("bowser_side.png")),
+             rect("yz", Y(1.0), Y(4.0), Z(6.0), Z(3.0), X(2.0), img("bowser_side.png"))]
+    grey = lambertian(solid(0.278, 0.387, 0.438))
+    parts.append(rect("xz", X(-2.0), X(2.0), Z(6.0), Z(3.0), Y(1.0), grey))
+    brown = lambertian(solid(0.4, 0.2, 0.1))
+    lightgrey = lambertian(solid(0.601, 0.687, 0.723))
+    # (x0, y0, z0) - (x1, y1, z1) as the offsets the Rust adds to x, `y - 1.875` and subtracts from `z + 4.5`
+    boxes = [
+        # feet :424-443
+        (grey, -1.5, 0.5, 4.75, -0.5, 1.0, 4.25), (grey, 0.5, 0.5, 4.75, 1.5, 1.0, 4.25),
+        (grey, -1.5, 0.25, 4.75, -0.5, 0.5, 3.5), (grey, 0.5, 0.25, 4.75, 1.5, 0.5, 3.5),
+        # arms :448-477
+        (brown, -2.25, 1.75, 4.65, -2.00, 2.75, 4.35), (brown, -2.50, 1.75, 4.65, -2.25, 2.50, 4.35),
+        (brown, -2.75, 1.75, 4.65, -2.50, 2.25, 4.35), (brown, 2.00, 1.75, 4.65, 2.25, 2.75, 4.35),
+        (brown, 2.25, 1.75, 4.65, 2.50, 2.50, 4.35), (brown, 2.50, 1.75, 4.65, 2.75, 2.25, 4.35),
+        # face rim :482-501
+        (lightgrey, -2.0, 3.875, 3.00, 2.0, 4.00, 2.875), (lightgrey, -2.0, 1.0, 3.00, 2.0, 1.125, 2.875),
+        (lightgrey, -2.0, 1.125, 3.00, -1.875, 3.875, 2.875), (lightgrey, 1.875, 1.125, 3.00, 2.0, 3.875, 2.875),
+        # the eight port frames at the back :504-545
+        (lightgrey, -1.875, 1.625, 6.125, -0.875, 1.75, 6.0), (lightgrey, -1.875, 1.125, 6.125, -0.875, 1.25, 6.0),
+        (lightgrey, -1.875, 1.25, 6.125, -1.750, 1.625, 6.0), (lightgrey, -1.0, 1.25, 6.125, -0.875, 1.625, 6.0),
+        (lightgrey, 0.875, 1.625, 6.125, 1.875, 1.75, 6.0), (lightgrey, 0.875, 1.125, 6.125, 1.875, 1.25, 6.0),
+        (lightgrey, 1.750, 1.25, 6.125, 1.875, 1.625, 6.0), (lightgrey, 0.875, 1.25, 6.125, 1.0, 1.625, 6.0)]
+    for m, x0, y0, z0, x1, y1, z1 in boxes:
+        parts.append(boxy((X(x0), Y(y0), Z(z0)), (X(x1), Y(y1), Z(z1)), m))
+    return bvh_new(parts, rng)  # `Bowser` itself only forwards hit / bounding_box to this node (:543-550)
+
+
+def bowser_demo(rng, assets_dir):  # src/scene.rs:552-628
+    checker = {"kind": "checker", "odd": solid(0.1, 0.1, 0.1), "even": solid(0.9, 0.9, 0.9)}
+    world = [sphere((0, -1000, 0), 1000.0, lambertian(checker))]
+    world.append(translate(rotate_x(rotate_y(rotate_z(_bowser(rng, assets_dir, 0.0, 0.0, 0.0), 0.0), 0.0), 0.0), (0.0, 1.625, -4.5)))
+    light_shape = rect("xy", -2, 2, 1, 4, 3, diffuse_light(image_texture("assets/twitter.png", assets_dir)))
+    world.append(flip_face(light_shape))
+    # RotatingCamera's first frame (:65-91, :597-625): angle -35, radius 20, height 2.5
+    rad = F(-35.0) * F(math.pi / 180.0)
+    look = (F(20.0) * F(np.cos(rad)), F(2.5), F(20.0) * F(np.sin(rad)))
+    cam = camera_new(look, (0, 2, 0), (0, 1, 0), 20.0, F(16.0) / F(9.0), 0.0, 10.0, 0.0, 1.0)
+    return world, [light_shape], cam, F(16.0) / F(9.0)
+
+
+SCENES = {"cornell_box": cornell_box, "cornell_smoke": cornell_smoke, "random_spheres_demo": random_spheres_demo, "final_scene": final_scene,
+          "balls_demo": balls_demo, "perlin_demo": perlin_demo, "bowser_demo": bowser_demo}
 
 
 def build(name, seed=1, assets_dir=None):

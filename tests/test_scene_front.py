@@ -12,7 +12,7 @@ import pytest
 from conftest import get_scene
 from oracle import scene_front as sf
 
-NAMES = ["cornell_box", "cornell_smoke", "random_spheres_demo", "final_scene"]
+NAMES = ["cornell_box", "cornell_smoke", "random_spheres_demo", "final_scene", "balls_demo", "perlin_demo", "bowser_demo"]
 
 
 @pytest.fixture(scope="module")
@@ -29,7 +29,7 @@ def test_lowered_scene_equals_the_independent_front_end(pairs, name):
     front, product, scene = pairs[name]
     st = sf.compare(front, product)
     # almost everything is bit-identical; only values that went through sin / cos / tan may differ in the last place
-    assert st["leaves"] > 100 and st["exact"] >= 0.98 * st["leaves"], st
+    assert st["leaves"] > 60 and st["exact"] >= 0.98 * st["leaves"], st
     c = scene.census()
     if name == "cornell_box":
         assert (c["nodes"], c["rects"], c["boxes"], c["spheres"], c["xforms"], c["lights"]) == (7, 7, 1, 1, 2, 1)
