@@ -450,6 +450,26 @@ SCENES = {"cornell_box": cornell_box, "cornell_smoke": cornell_smoke, "random_sp
           "balls_demo": balls_demo, "perlin_demo": perlin_demo, "bowser_demo": bowser_demo}
 
 
+# cam_iter of each builder: FixedCamera yields its camera once (src/scene.rs:24-46); RotatingCamera (:48-91) yields
+# Camera::new from (radius cos a, height, radius sin a) while a <= limit, a += incr in f32
+ROTATING = {"random_spheres_demo": dict(lookat=(0, 1.5, 0), vfov=20.0, height=2.5, angle=25.0, radius=20.0, incr=0.5, limit=360.0),   # :254-281
+            "bowser_demo": dict(lookat=(0, 2, 0), vfov=20.0, height=2.5, angle=-35.0, radius=20.0, incr=0.5, limit=360.0 - 35.0)}  # :597-625
+
+
+def cameras(name, seed=1, assets_dir=None):
+    """Every camera `for cam in config.cam_iter` (src/main.rs:176) sees, in order."""
+    if name not in ROTATING:
+        yield SCENES[name](Rng(seed), assets_dir)[2]
+        return
+    r = ROTATING[name]
+    angle, incr, limit = F(r["angle"]), F(r["incr"]), F(r["limit"])
+    while not angle > limit:
+        rad = angle * F(math.pi / 180.0)
+        look = (F(r["radius"]) * F(np.cos(rad)), F(r["height"]), F(r["radius"]) * F(np.sin(rad)))
+        yield camera_new(look, r["lookat"], (0, 1, 0), r["vfov"], F(16.0) / F(9.0), 0.0, 10.0, 0.0, 1.0)
+        angle = angle + incr
+
+
 def build(name, seed=1, assets_dir=None):
     """The reference's main(): scene builder, then BVHNode::new(&mut config.world) (src/main.rs:159-169)."""
     rng = Rng(seed)

@@ -87,3 +87,21 @@ def test_the_comparison_notices_structure_changes(pairs):
     p["perm_y"][3], p["perm_y"][4] = p["perm_y"][4], p["perm_y"][3]
     with pytest.raises(AssertionError):
         sf.compare(pairs["final_scene"][0], bad)
+
+
+@pytest.mark.parametrize("name,frames", [("random_spheres_demo", 671), ("bowser_demo", 721), ("cornell_box", 1), ("perlin_demo", 1)])
+def test_camera_iterator_yields_the_reference_s_frames(vb, name, frames):
+    """`for cam in config.cam_iter` (src/main.rs:176): FixedCamera once, RotatingCamera 671 / 721 turntable frames
+    (src/scene.rs:24-91, 254-281, 597-625) -- the product's iterator against the front end's, frame by frame."""
+    scene = vb.Scene(name, seed=1)
+    keys = ("origin", "lower_left_corner", "horizontal", "vertical", "u", "v", "w")
+    n = 0
+    for want in sf.cameras(name, seed=1, assets_dir=vb.ASSETS_DIR):
+        cam = scene.next_camera()
+        assert cam is not None, f"{name}: the product's iterator ended after {n} frames"
+        for k in keys:
+            got = np.array(getattr(cam, k)[:], dtype=np.float32)
+            assert np.allclose(got, want[k], rtol=2e-6, atol=2e-6 * float(np.abs(want[k]).max()) + 1e-6), f"{name} frame {n}: {k} {got} != {want[k]}"
+        assert (cam.lens_radius, cam.time0, cam.time1) == (float(want["lens_radius"]), float(want["time0"]), float(want["time1"]))
+        n += 1
+    assert n == frames and scene.next_camera() is None
