@@ -13,6 +13,14 @@
 use std::collections::HashMap;
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
+use std::sync::Arc;
+
+use crate::hittable::HittableSS;
+use crate::material::{MaterialSS, TextureSS};
+use crate::vec3::Vec3;
+
+/// `Vec3` is not `repr(C)` (src/vec3.rs:3-8): copied field by field.
+pub fn v3(v: Vec3) -> [f32; 3] { [v.x, v.y, v.z] }
 
 pub type vk_ref = u32; // (type << 28) | index ; 0 == none
 pub const VK_API_VERSION: u32 = 1;
@@ -24,6 +32,21 @@ pub const VK_T_BOX: u32 = 5;
 pub const VK_T_XFORM: u32 = 6;
 pub const VK_T_MEDIUM: u32 = 7;
 pub const VK_RECT_FLIP: u32 = 0x100;
+pub const VK_X_TRANSLATE: u32 = 0;
+pub const VK_X_ROTATE_X: u32 = 1;
+pub const VK_X_ROTATE_Y: u32 = 2;
+pub const VK_X_ROTATE_Z: u32 = 3;
+pub const VK_X_FLIP: u32 = 4;
+pub const VK_M_LAMBERTIAN: u32 = 0;
+pub const VK_M_METAL: u32 = 1;
+pub const VK_M_DIELECTRIC: u32 = 2;
+pub const VK_M_DIFFUSE_LIGHT: u32 = 3;
+pub const VK_M_ISOTROPIC: u32 = 4;
+pub const VK_M_SPECDIFFUSE: u32 = 5;
+pub const VK_TEX_SOLID: u32 = 0;
+pub const VK_TEX_CHECKER: u32 = 1;
+pub const VK_TEX_IMAGE: u32 = 2;
+pub const VK_TEX_NOISE: u32 = 3;
 pub const fn vk_mkref(t: u32, i: u32) -> vk_ref { (t << 28) | (i & 0x0FFF_FFFF) }
 
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct vk_node { pub bb_min: [f32; 3], pub left: vk_ref, pub bb_max: [f32; 3], pub right: vk_ref }
@@ -102,7 +125,47 @@ pub struct Lowering {
     pub rects: Vec<vk_rect>, pub boxes: Vec<vk_box>, pub xforms: Vec<vk_xform>, pub media: Vec<vk_medium>,
     pub lights: Vec<vk_ref>, pub materials: Vec<vk_material>, pub textures: Vec<vk_texture>, pub texels: Vec<u8>,
     pub perlins: Vec<vk_perlin>,
-    pub memo: HashMap<usize, u32>, // Arc::as_ptr(..) as *const () as usize -> record index / ref
+    // allocation address -> record: Arc::as_ptr(..) as *const () as usize (one map per trait, one for flipped rects)
+    pub memo_h: HashMap<usize, vk_ref>, pub memo_flip: HashMap<usize, vk_ref>, pub memo_m: HashMap<usize, u32>, pub memo_t: HashMap<usize, u32>,
+}
+
+impl Lowering {
+    /// `h.lower(self)`, once per allocation: a sub-BVH under two wrappers, a rect that is both a world object
+    /// (inside its FlipFace) and a light, come out as ONE record.  The C++ model of these three is
+    /// `Lowering::hittable / material / texture` in vecchio_b200/host/vecchio.cpp.
+    pub fn hittable(&mut self, h: &Arc<HittableSS>) -> Result<vk_ref, GpuError> {
+        let key = Arc::as_ptr(h) as *const () as usize;
+        if let Some(&r) = self.memo_h.get(&key) { return Ok(r); }
+        let r = h.lower(self)?;
+        self.memo_h.insert(key, r);
+        Ok(r)
+    }
+    pub fn material(&mut self, m: &Arc<MaterialSS>) -> Result<u32, GpuError> {
+        let key = Arc::as_ptr(m) as *const () as usize;
+        if let Some(&i) = self.memo_m.get(&key) { return Ok(i); }
+        let i = m.lower(self)?;
+        self.memo_m.insert(key, i);
+        Ok(i)
+    }
+    pub fn texture(&mut self, t: &Arc<TextureSS>) -> Result<u32, GpuError> {
+        let key = Arc::as_ptr(t) as *const () as usize;
+        if let Some(&i) = self.memo_t.get(&key) { return Ok(i); }
+        let i = t.lower(self)?;
+        self.memo_t.insert(key, i);
+        Ok(i)
+    }
+    pub fn push_material(&mut self, type_: u32, tex: u32, param: f32, aux: u32) -> u32 {
+        self.materials.push(vk_material { type_, tex, param, aux });
+        (self.materials.len() - 1) as u32
+    }
+    pub fn push_texture(&mut self, type_: u32, w: [u32; 3]) -> u32 {
+        self.textures.push(vk_texture { type_, w });
+        (self.textures.len() - 1) as u32
+    }
+    pub fn push_xform(&mut self, kind: u32, child: vk_ref, a: f32, b: f32, c: f32) -> vk_ref {
+        self.xforms.push(vk_xform { kind, child, _pad0: [0; 2], a, b, c, _pad1: 0 });
+        vk_mkref(VK_T_XFORM, (self.xforms.len() - 1) as u32)
+    }
 }
 
 /// The ONE method added to each of the reference's traits (they are otherwise opaque: no `Any`,
@@ -118,8 +181,8 @@ pub struct Lowering {
 /// }
 /// impl Hittable for Sphere {                      // src/hittable.rs:63
 ///     fn lower(&self, b: &mut gpu::Lowering) -> Result<gpu::vk_ref, gpu::GpuError> {
-///         let mat = self.material.lower(b)?;      // Material::lower -> index into b.materials
-///         b.spheres.push(gpu::vk_sphere { center: self.center.into(), radius: self.radius });
+///         let mat = b.material(&self.material)?;  // memoised Material::lower -> index into b.materials
+///         b.spheres.push(gpu::vk_sphere { center: gpu::v3(self.center), radius: self.radius });
 ///         b.sphere_mat.push(mat);
 ///         Ok(gpu::vk_mkref(gpu::VK_T_SPHERE, (b.spheres.len() - 1) as u32))
 ///     }
@@ -128,12 +191,14 @@ pub struct Lowering {
 ///     fn lower(&self, b: &mut gpu::Lowering) -> Result<gpu::vk_ref, gpu::GpuError> {
 ///         let i = b.nodes.len();                  // depth first, parent before children, left first
 ///         b.nodes.push(Default::default());
-///         let left = self.left.lower(b)?;
-///         let right = if Arc::ptr_eq(&self.left, &self.right) { left } else { self.right.lower(b)? };
-///         b.nodes[i] = gpu::vk_node { bb_min: self.bb.min.into(), left, bb_max: self.bb.max.into(), right };
+///         let left = b.hittable(&self.left)?;
+///         let right = if Arc::ptr_eq(&self.left, &self.right) { left } else { b.hittable(&self.right)? };
+///         b.nodes[i] = gpu::vk_node { bb_min: gpu::v3(self.bb.min), left, bb_max: gpu::v3(self.bb.max), right };
 ///         Ok(gpu::vk_mkref(gpu::VK_T_NODE, i as u32))
 ///     }
 /// }
+/// // The complete set -- every Hittable, Material and Texture the reference ships, Camera::lower, the call in main() --
+/// // is rust/lower_impls.rs, block by block under the file each block is pasted into.  In short:
 /// // FlipFace(Rect) sets VK_RECT_FLIP on a copy of the rect record; FlipFace of anything else,
 /// // Translate and RotateX/Y/Z push one vk_xform {kind, child, a, b, c} (offset | sin, cos);
 /// // Boxy pushes one vk_box; ConstantMedium one vk_medium {boundary.lower()?, -1/density, phase};

@@ -243,3 +243,31 @@ def test_rust_binding_constants_equal_the_header_s():
     for k, v in consts.items():
         assert k in enums, f"{k} is not a constant of the header"
         assert int(v.replace("_", ""), 0) == enums[k], f"{k}: rust {v}, header {enums[k]}"
+
+
+def test_rust_lower_impls_use_what_the_binding_defines():
+    """rust/lower_impls.rs (the lower() of every shipped type, uncompiled like gpu.rs): every `gpu::` name it uses is defined
+    in rust/gpu.rs, every struct literal names exactly the struct's fields, every reference type of SURVEY 8(a) has a block."""
+    rust = re.sub(r"//[^\n]*", " ", open(RUST).read())
+    impls_raw = open(os.path.join(ROOT, "rust", "lower_impls.rs")).read()
+    impls = re.sub(r"//[^\n]*", " ", impls_raw)
+    defined = set(re.findall(r"pub\s+(?:const\s+fn|const|fn|struct|enum|type)\s+(\w+)", rust))
+    used = set(re.findall(r"\bgpu::(\w+)", impls))
+    assert used and used <= defined, f"not defined in rust/gpu.rs: {sorted(used - defined)}"
+    methods = set(re.findall(r"pub\s+fn\s+(\w+)\s*\(\s*&mut\s+self", rust))
+    for m in set(re.findall(r"\bb\.(\w+)\(", impls)):
+        assert m in methods, f"Lowering has no method `{m}`"
+    structs, _ = _rust_layout()
+    n_literals = 0
+    for name, body in re.findall(r"gpu::(vk_\w+)\s*\{([^{}]*)\}", impls):
+        fields = [part.split(":")[0].strip() for part in _split_top_level(body) if part.strip()]
+        assert sorted(fields) == sorted(f for f, *_ in structs[name]["fields"]), f"{name} literal: fields {fields}"
+        n_literals += 1
+    assert n_literals >= 8
+    vec_fields = set(re.findall(r"pub\s+(\w+):\s*Vec<", rust)) | set(re.findall(r"pub\s+(memo_\w+):", rust))
+    for f in set(re.findall(r"\bb\.(\w+)\.(?:push|len|get|insert|extend_from_slice)\b", impls)):
+        assert f in vec_fields, f"Lowering has no field `{f}`"
+    for ty in ("Sphere", "MovingSphere", "Rect", "FlipFace", "Boxy", "ConstantMedium", "Translate", "RotateX", "RotateY", "RotateZ", "BVHNode",
+               "Lambertian", "Metal", "Dielectric", "DiffuseLight", "Isotropic", "SpecDiffuse", "SolidColor", "Checker", "ImageTexture",
+               "NoiseTexture", "Camera"):
+        assert re.search(rf"^impl {ty} \{{", impls_raw, flags=re.M), f"no lower() block for {ty}"
