@@ -192,6 +192,27 @@ struct Validator {
         for (uint32_t i = 0; i < d->n_boxes; ++i)
             if (d->boxes[i].mat >= d->n_materials) return bad(VK_ERR_INVALID, "box material out of range");
         if (d->n_nodes > VKD_INDEX(0xFFFFFFFFu) || d->n_spheres > VKD_INDEX(0xFFFFFFFFu)) return bad(VK_ERR_UNSUPPORTED, "too many primitives");
+        // Every record, reachable from the root or not: the layout planner walks whole arrays (all xforms for the instanced
+        // sub-BVHs, all nodes for the single-object leaves, all media), so a stray record with a wild reference must be
+        // refused here, not only the ones the traversal below reaches (found by tests/sanitize_host.cpp under ASan).
+        auto ref_ok = [&](vk_ref r) {
+            const uint32_t t = VK_REF_TYPE(r), ix = VK_REF_INDEX(r);
+            const uint32_t lim = t == VK_T_NODE ? d->n_nodes : t == VK_T_SPHERE ? d->n_spheres : t == VK_T_MSPHERE ? d->n_mspheres
+                               : t == VK_T_RECT ? d->n_rects : t == VK_T_BOX ? d->n_boxes : t == VK_T_XFORM ? d->n_xforms
+                               : t == VK_T_MEDIUM ? d->n_media : 0;
+            return ix < lim;
+        };
+        for (uint32_t i = 0; i < d->n_nodes; ++i)
+            if (!ref_ok(d->nodes[i].left) || !ref_ok(d->nodes[i].right)) return bad(VK_ERR_INVALID, "BVH node holds a reference out of range");
+        for (uint32_t i = 0; i < d->n_xforms; ++i) {
+            if (!ref_ok(d->xforms[i].child)) return bad(VK_ERR_INVALID, "transform holds a reference out of range");
+            chain_end(VK_REF(VK_T_XFORM, i)); // kinds, and that the chain ends (a cycle of wrappers runs into the depth limit)
+            if (code != VK_OK) return false;
+        }
+        for (uint32_t i = 0; i < d->n_media; ++i) {
+            if (!ref_ok(d->media[i].boundary)) return bad(VK_ERR_INVALID, "medium boundary out of range");
+            if (d->media[i].mat >= d->n_materials) return bad(VK_ERR_INVALID, "medium material out of range");
+        }
         node_depth.assign(d->n_nodes, 0);
         node_medium.assign(d->n_nodes, 0);
         node_inchain.assign(d->n_nodes, 0);
