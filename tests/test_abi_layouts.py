@@ -43,13 +43,10 @@ def _c_structs(text):
             if decl.startswith("__union__"):
                 fields.append("<union>:" + decl.split()[1])
                 continue
-            # "const float* a, *b" does not occur; pointers carry their star on the type: "const vk_node* nodes"
-            head, _, rest = decl.rpartition(" ") if "," not in decl else (decl[:decl.index(",")].rpartition(" ")[0], "", None)
-            if "," in decl:
-                first = decl[:decl.index(",")].rpartition(" ")[2]
-                names = [first] + [d.strip() for d in decl[decl.index(",") + 1:].split(",")]
-            else:
-                names = [rest]
+            # "type a[3], b, c": the type is everything up to the last space of the first declarator; pointers carry their
+            # star on the type ("const vk_node* nodes"), "const float* a, *b" does not occur in the header
+            declarators = decl.split(",")
+            names = [declarators[0].rpartition(" ")[2]] + [x.strip() for x in declarators[1:]]
             for n in names:
                 fields.append(re.sub(r"\[.*", "", n).lstrip("*"))
         out[name] = fields
