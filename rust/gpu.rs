@@ -15,8 +15,8 @@ use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
 use std::sync::Arc;
 
-use crate::hittable::HittableSS;
-use crate::material::{MaterialSS, TextureSS};
+use crate::hittable::{Hittable, HittableSS};                    // the traits must be in scope to call `lower` on the trait objects
+use crate::material::{Material, MaterialSS, Texture, TextureSS};
 use crate::vec3::Vec3;
 
 /// `Vec3` is not `repr(C)` (src/vec3.rs:3-8): copied field by field.
